@@ -1,0 +1,173 @@
+"""ctypes front end of the CPU oracle (TEST INFRASTRUCTURE ONLY -- see oracle/lid3d.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+Arrays are exposed as numpy views in the reference's Fortran layout (order="F"):
+f (19,nx,ny,nz), f_post (19,nx+2,ny+2,nz+2), rho/u/v/w (nx,ny,nz).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(native=False):
+    target = "native" if native else "all"
+    subprocess.check_call(["make", "-s", "-C", _HERE, target])
+    return os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
+
+
+def load(native=False):
+    path = os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
+    src_mtime = max(os.path.getmtime(os.path.join(_HERE, s)) for s in os.listdir(_HERE) if s.endswith(".c"))
+    if not os.path.exists(path) or os.path.getmtime(path) < src_mtime:
+        path = build(native)
+    lib = C.CDLL(path)
+    lib.orc_world_create.restype = C.c_void_p
+    lib.orc_world_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double]
+    lib.orc_world_destroy.argtypes = [C.c_void_p]
+    lib.orc_rank_ptr.restype = _dp
+    lib.orc_rank_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.orc_rank_info.argtypes = [C.c_void_p, C.c_int, _ip]
+    lib.orc_world_info.argtypes = [C.c_void_p, _ip, _dp, _ip]
+    for name in ("orc_initial", "orc_collision", "orc_exchange", "orc_streaming", "orc_bounceback", "orc_macro"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = None
+    lib.orc_check.argtypes = [C.c_void_p]
+    lib.orc_check.restype = C.c_double
+    lib.orc_step.argtypes = [C.c_void_p, C.c_int]
+    lib.orc_step.restype = None
+    lib.orc_dims_create.argtypes = [C.c_int, _ip]
+    lib.orc_decompose_1d.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip]
+    lib.orc_moments.argtypes = [_dp, _dp]
+    lib.orc_inverse.argtypes = [_dp, _dp]
+    lib.orc_meq.argtypes = [C.c_double] * 4 + [_dp]
+    lib.orc_collide_cell.argtypes = [_dp] + [C.c_double] * 6 + [_dp]
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+EX = np.array([0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0])
+EY = np.array([0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1])
+EZ = np.array([0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1])
+OPP = np.array([0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15])
+W = np.array([1 / 3] + [1 / 18] * 6 + [1 / 36] * 12)
+
+
+class Rank:
+    """numpy views (no copies) of one emulated MPI rank's arrays."""
+
+    def __init__(self, world, r):
+        L = world._lib
+        info = (C.c_int * 27)()
+        L.orc_rank_info(world._h, r, info)
+        self.n = tuple(info[0:3])
+        self.coords = tuple(info[3:6])
+        self.start = tuple(info[6:9])
+        self.nbr_surface = {s: info[8 + s] for s in range(1, 7)}
+        self.nbr_line = {a: info[8 + a] for a in range(7, 19)}
+        nx, ny, nz = self.n
+
+        def view(which, shape):
+            p = L.orc_rank_ptr(world._h, r, which)
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array(p, shape=(n,)).reshape(shape, order="F")
+
+        self.f = view(0, (19, nx, ny, nz))
+        self.f_post = view(1, (19, nx + 2, ny + 2, nz + 2))
+        self.rho, self.u, self.v, self.w = (view(q, (nx, ny, nz)) for q in (2, 3, 4, 5))
+        self.up, self.vp, self.wp = (view(q, (nx, ny, nz)) for q in (6, 7, 8))
+
+
+class LidWorld:
+    """All P emulated ranks of the lid-driven cavity (L3/main.f90) in one process."""
+
+    def __init__(self, total, nprocs=1, dims=None, Re=1000.0, U0=0.1, rho0=1.0, native=False):
+        self._lib = load(native) if native else lib()
+        d = (C.c_int * 3)(*(dims if dims else (0, 0, 0)))
+        self._h = self._lib.orc_world_create(total[0], total[1], total[2], nprocs, d, Re, U0, rho0)
+        self.total = tuple(total)
+        self.nprocs = nprocs
+        self.U0, self.Re, self.rho0 = U0, Re, rho0
+        self.ranks = [Rank(self, r) for r in range(nprocs)]
+        dd = (C.c_int * 3)()
+        pp = (C.c_double * 4)()
+        it = C.c_int()
+        self._lib.orc_world_info(self._h, dd, pp, C.byref(it))
+        self.dims = tuple(dd)
+        self.tauf, self.Snu, self.Sq = pp[0], pp[1], pp[2]
+
+    def close(self):
+        if self._h:
+            self.ranks = []
+            self._lib.orc_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initial(self):
+        self._lib.orc_initial(self._h)
+
+    def collision(self):
+        self._lib.orc_collision(self._h)
+
+    def message_passing_sendrecv(self):
+        self._lib.orc_exchange(self._h)
+
+    def streaming(self):
+        self._lib.orc_streaming(self._h)
+
+    def bounceback(self):
+        self._lib.orc_bounceback(self._h)
+
+    def macro(self):
+        self._lib.orc_macro(self._h)
+
+    def check(self):
+        return self._lib.orc_check(self._h)
+
+    def step(self, n=1):
+        self._lib.orc_step(self._h, n)
+
+    def gather(self, name):
+        """Assemble a global (nx,ny,nz) field (or (19,...) for f) from the ranks, like output() does."""
+        lead = (19,) if name == "f" else ()
+        out = np.empty(lead + self.total, order="F")
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            out[(slice(None),) * len(lead) + sl] = getattr(R, name)
+        return out
+
+    def scatter(self, name, glob):
+        lead = 1 if name == "f" else 0
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            getattr(R, name)[...] = glob[(slice(None),) * lead + sl]
+
+
+def feq(rho, u, v, w):
+    """Second-order equilibrium of L3/initial.f90:63-73, vectorised (rho,u,v,w broadcastable)."""
+    rho, u, v, w = (np.asarray(a, dtype=np.float64) for a in (rho, u, v, w))
+    us2 = u * u + v * v + w * w
+    out = np.empty((19,) + np.broadcast(rho, u).shape)
+    for a in range(19):
+        un = u * EX[a] + v * EY[a] + w * EZ[a]
+        out[a] = rho * W[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2)
+    return out

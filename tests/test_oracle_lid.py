@@ -1,0 +1,282 @@
+"""Pins for the CPU oracle of the D3Q19 lid-driven-cavity path (oracle/lid3d.c).
+
+The reference (cheryli/MGLC) ships no tests or golden vectors and cannot be compiled here, so the
+oracle is pinned by analytic known answers and by the reference's implicit seq == MPI contract:
+  * the hand-expanded transforms are the published d'Humieres (2002) D3Q19 matrix and its inverse
+    (L3/collision.f90:20-70 vs :118-189),
+  * M feq = meq for every moment except m12 (missing-rho quirk, L3/collision.f90:85),
+  * rest equilibrium is a collision fixed point, a delta population moves by e_alpha,
+  * closed-cavity mass is conserved, no NaN escapes the poisoned (uninitialised) wall halos,
+  * an independent numpy statement of the unified boundary rule reproduces
+    streaming()+bounceback() bit for bit,
+  * P-rank runs (uneven blocks) equal the 1-rank run bit for bit.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+dp = C.POINTER(C.c_double)
+
+
+def _vec(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(dp)
+
+
+def forward_matrix():
+    L = orc.lib()
+    M = np.zeros((19, 19))
+    for a in range(19):
+        e, ep = _vec(np.eye(19)[a])
+        m, mp = _vec(np.zeros(19))
+        L.orc_moments(ep, mp)
+        M[:, a] = m
+    return M
+
+
+def inverse_matrix():
+    L = orc.lib()
+    Mi = np.zeros((19, 19))
+    for a in range(19):
+        e, ep = _vec(np.eye(19)[a])
+        f, fp = _vec(np.zeros(19))
+        L.orc_inverse(ep, fp)
+        Mi[:, a] = f
+    return Mi
+
+
+def dhumieres_d3q19():
+    cx, cy, cz = orc.EX.astype(float), orc.EY.astype(float), orc.EZ.astype(float)
+    c2 = cx * cx + cy * cy + cz * cz
+    rows = [np.ones(19), 19 * c2 - 30, (21 * c2 * c2 - 53 * c2 + 24) / 2,
+            cx, (5 * c2 - 9) * cx, cy, (5 * c2 - 9) * cy, cz, (5 * c2 - 9) * cz,
+            3 * cx * cx - c2, (3 * c2 - 5) * (3 * cx * cx - c2), cy * cy - cz * cz, (3 * c2 - 5) * (cy * cy - cz * cz),
+            cx * cy, cy * cz, cx * cz,
+            (cy * cy - cz * cz) * cx, (cz * cz - cx * cx) * cy, (cx * cx - cy * cy) * cz]
+    return np.array(rows)
+
+
+def test_forward_transform_is_dhumieres_matrix():
+    assert np.array_equal(forward_matrix(), dhumieres_d3q19())
+
+
+def test_inverse_transform_is_matrix_inverse():
+    M, Mi = forward_matrix(), inverse_matrix()
+    assert np.abs(Mi @ M - np.eye(19)).max() < 5e-16
+    # rows of M are mutually orthogonal => M^-1 = M^T diag(1/|row|^2)
+    norms = (M * M).sum(axis=1)
+    assert np.allclose(Mi, M.T / norms, rtol=0, atol=1e-17 + 2e-16 * np.abs(M.T / norms).max())
+
+
+def test_roundtrip_random_populations():
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        f, fp = _vec(rng.random(19))
+        m, mp = _vec(np.zeros(19))
+        g, gp = _vec(np.zeros(19))
+        L.orc_moments(fp, mp)
+        L.orc_inverse(mp, gp)
+        assert np.abs(g - f).max() < 1e-15
+
+
+def test_meq_is_moments_of_feq_except_m12_quirk():
+    L = orc.lib()
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        rho = 1.0 + 0.03 * rng.uniform(-1, 1)
+        u, v, w = 0.05 * rng.uniform(-1, 1, 3)
+        f, fp = _vec(orc.feq(rho, u, v, w))
+        m, mp = _vec(np.zeros(19))
+        me, mep = _vec(np.zeros(19))
+        L.orc_moments(fp, mp)
+        L.orc_meq(rho, u, v, w, mep)
+        # kinetic (non-hydrodynamic) moments of the 2nd-order feq: only those the reference's meq models
+        ok = [0, 1, 3, 5, 7, 9, 11, 13, 14, 15]
+        assert np.abs(m[ok] - me[ok]).max() < 1e-14
+        # quirk: meq(12) = -1/2 (v^2 - w^2) without rho (L3/collision.f90:85)
+        assert me[12] == -1.0 / 2.0 * (v * v - w * w)
+        assert me[10] == -1.0 / 2.0 * rho * (2.0 * u * u - v * v - w * w)
+
+
+def test_rest_equilibrium_is_fixed_point():
+    L = orc.lib()
+    f, fp = _vec(orc.feq(1.0, 0.0, 0.0, 0.0))
+    g, gp = _vec(np.zeros(19))
+    L.orc_collide_cell(fp, 1.0, 0.0, 0.0, 0.0, 1.0 / 0.5195, 1.2, gp)
+    assert np.abs(g - f).max() < 2e-16
+
+
+def test_parameters_config1():
+    wd = orc.LidWorld((65, 65, 65), 1)
+    tau = 0.1 * 65.0 / 1000.0 * 3.0 + 0.5
+    assert wd.tauf == tau and wd.Snu == 1.0 / tau
+    assert wd.Sq == 8.0 * (2.0 * tau - 1.0) / (8.0 * tau - 1.0)
+    assert abs(tau - 0.5195) < 1e-15
+    wd.close()
+
+
+def test_dims_create_and_decompose():
+    L = orc.lib()
+    d = (C.c_int * 3)()
+    expect = {1: (1, 1, 1), 2: (2, 1, 1), 3: (3, 1, 1), 4: (2, 2, 1), 6: (3, 2, 1), 8: (2, 2, 2), 12: (3, 2, 2), 16: (4, 2, 2)}
+    for n, e in expect.items():
+        L.orc_dims_create(n, d)
+        assert tuple(d) == e
+    n, s = C.c_int(), C.c_int()
+    got = []
+    for r in range(2):
+        L.orc_decompose_1d(65, r, 2, C.byref(n), C.byref(s))
+        got.append((n.value, s.value))
+    assert got == [(33, 0), (32, 33)]            # first (65 mod 2) ranks get +1, L3/main.f90:149-153
+    tot = 0
+    for r in range(7):
+        L.orc_decompose_1d(65, r, 7, C.byref(n), C.byref(s))
+        assert s.value == tot
+        tot += n.value
+    assert tot == 65
+
+
+def test_neighbour_tables_2x2x2():
+    wd = orc.LidWorld((8, 8, 8), 8)
+    assert wd.dims == (2, 2, 2)
+    R0 = wd.ranks[0]                      # coords (0,0,0); rank = (c0*2 + c1)*2 + c2
+    assert R0.coords == (0, 0, 0)
+    assert R0.nbr_surface == {1: 4, 2: -1, 3: 2, 4: -1, 5: 1, 6: -1}
+    assert R0.nbr_line[7] == 6 and R0.nbr_line[11] == 5 and R0.nbr_line[15] == 3
+    for a in (8, 9, 10, 12, 13, 14, 16, 17, 18):
+        assert R0.nbr_line[a] == -1
+    R7 = wd.ranks[7]
+    assert R7.coords == (1, 1, 1) and R7.nbr_line[10] == 1 and R7.nbr_line[14] == 2 and R7.nbr_line[18] == 4
+    wd.close()
+
+
+def test_delta_population_moves_by_e_alpha():
+    wd = orc.LidWorld((7, 6, 5), 1)
+    R = wd.ranks[0]
+    for a in range(19):
+        R.f_post[...] = 0.0
+        R.f_post[a, 3, 3, 2] = 1.0           # f_post index == cell index (halo at 0)
+        wd.streaming()
+        where = np.argwhere(R.f != 0.0)
+        assert len(where) == 1
+        # f has no halo: cell (i,j,k) lives at [i-1, j-1, k-1]
+        assert tuple(where[0]) == (a, 3 + orc.EX[a] - 1, 3 + orc.EY[a] - 1, 2 + orc.EZ[a] - 1)
+    wd.close()
+
+
+def unified_rule_numpy(f_post, rho_prev, coords, dims, U0):
+    """streaming()+bounceback() as the single rule of SURVEY Appendix A, written independently."""
+    q, nxh, nyh, nzh = f_post.shape
+    nx, ny, nz = nxh - 2, nyh - 2, nzh - 2
+    f = np.empty((19, nx, ny, nz), order="F")
+    n = (nx, ny, nz)
+    for a in range(19):
+        e = (orc.EX[a], orc.EY[a], orc.EZ[a])
+        src = f_post[a, 1 - e[0]:1 - e[0] + nx, 1 - e[1]:1 - e[1] + ny, 1 - e[2]:1 - e[2] + nz].copy()
+        bb = f_post[orc.OPP[a], 1:nx + 1, 1:ny + 1, 1:nz + 1]
+        out = np.zeros((nx, ny, nz), dtype=bool)       # upstream outside the GLOBAL box
+        for d in range(3):
+            idx = [slice(None)] * 3
+            if e[d] == 1 and coords[d] == 0:
+                idx[d] = 0
+                out[tuple(idx)] = True
+            if e[d] == -1 and coords[d] == dims[d] - 1:
+                idx[d] = n[d] - 1
+                out[tuple(idx)] = True
+        val = np.where(out, bb, src)
+        if coords[2] == dims[2] - 1 and e[2] == -1 and a in (13, 14):
+            sign = U0 if a == 14 else -U0
+            val[:, :, nz - 1] = bb[:, :, nz - 1] - rho_prev[:, :, nz - 1] / 6.0 * sign
+        f[a] = val
+    return f
+
+
+@pytest.mark.parametrize("nprocs", [1, 2, 4, 8])
+def test_unified_boundary_rule_matches_stream_plus_bounceback(nprocs):
+    wd = orc.LidWorld((9, 8, 7), nprocs)
+    rng = np.random.default_rng(3)
+    for R in wd.ranks:
+        nx, ny, nz = R.n
+        R.f_post[:, 1:nx + 1, 1:ny + 1, 1:nz + 1] = rng.random((19, nx, ny, nz))
+        R.rho[...] = 1.0 + 0.1 * rng.random(R.n)
+    wd.message_passing_sendrecv()
+    wd.streaming()
+    wd.bounceback()
+    for R in wd.ranks:
+        assert not np.isnan(R.f).any()       # wall halos (NaN-poisoned) never survive into f
+        fp = np.nan_to_num(R.f_post, nan=-7.0)
+        expect = unified_rule_numpy(fp, R.rho, R.coords, wd.dims, wd.U0)
+        assert np.array_equal(R.f, expect)
+    wd.close()
+
+
+def test_mass_conserved_in_closed_cavity():
+    wd = orc.LidWorld((12, 11, 10), 1)
+    wd.initial()
+    m0 = wd.ranks[0].f.sum()
+    wd.step(50)
+    m1 = wd.ranks[0].f.sum()
+    assert abs(m1 - m0) / m0 < 1e-13
+    assert not np.isnan(wd.ranks[0].f).any()
+    # the lid drags fluid in +x just under the lid
+    assert wd.ranks[0].u[:, :, -1].mean() > 1e-3
+    wd.close()
+
+
+def _run(total, nprocs, nsteps, dims=None, seed=None):
+    wd = orc.LidWorld(total, nprocs, dims=dims)
+    wd.initial()
+    if seed is not None:
+        rng = np.random.default_rng(seed)
+        rho = 1.0 + 0.01 * rng.uniform(-1, 1, total)
+        u, v, w = (0.05 * rng.uniform(-1, 1, total) for _ in range(3))
+        wd.scatter("rho", np.asfortranarray(rho))
+        wd.scatter("u", np.asfortranarray(u))
+        wd.scatter("v", np.asfortranarray(v))
+        wd.scatter("w", np.asfortranarray(w))
+        wd.scatter("f", np.asfortranarray(orc.feq(rho, u, v, w)))
+    wd.step(nsteps)
+    out = {k: wd.gather(k) for k in ("f", "rho", "u", "v", "w")}
+    out["errorU"] = wd.check()
+    wd.close()
+    return out
+
+
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (8, None), (3, (1, 3, 1)), (4, (1, 2, 2)), (6, None)])
+def test_decomposition_invariance_bit_exact(nprocs, dims):
+    total = (13, 11, 9)
+    ref = _run(total, 1, 12, seed=1234)
+    got = _run(total, nprocs, 12, dims=dims, seed=1234)
+    for k in ("f", "rho", "u", "v", "w"):
+        assert np.array_equal(ref[k], got[k]), k
+    # check(): per-rank partial sums are added in rank order, so errorU agrees to rounding only
+    assert abs(ref["errorU"] - got["errorU"]) <= 1e-14 * ref["errorU"]
+
+
+def test_check_matches_numpy_and_omits_w_term():
+    wd = orc.LidWorld((10, 9, 8), 1)
+    wd.initial()
+    wd.step(5)
+    R = wd.ranks[0]
+    up, vp = R.up.copy(), R.vp.copy()
+    e1 = ((R.u - up) ** 2 + (R.v - vp) ** 2).sum()      # no w term, L3/check.f90:15
+    e2 = (R.u ** 2 + R.v ** 2 + R.w ** 2).sum()
+    got = wd.check()
+    assert abs(got - np.sqrt(e1) / np.sqrt(e2)) < 1e-13 * got
+    assert np.array_equal(R.up, R.u) and np.array_equal(R.wp, R.w)
+    wd.close()
+
+
+def test_golden_fixture_regression():
+    """Golden vectors made by tests/golden/make_golden.py (oracle output; guards the oracle itself)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "lid_9x8x7.npz")
+    g = np.load(path)
+    out = _run((9, 8, 7), 1, int(g["nsteps"]), seed=int(g["seed"]))
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(out[k], g[k]), k
+    assert out["errorU"] == float(g["errorU"])
