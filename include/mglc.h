@@ -1,0 +1,181 @@
+/*
+ * mglc.h -- C ABI of libmglc.so: the B200-native replacement for the per-timestep hot path of
+ * cheryli/MGLC (collide + stream lattice update, boundary kernels, 3-D subdomain halo exchange).
+ *
+ * The reference has no FFI today: its drivers call argument-less Fortran subroutines over
+ * `module commondata` globals (MPI/Lid_driven_cavity/fortran/3d/mpi_3d_blocked/main.f90:85-103,
+ * "L3" below).  This header defines the seam a driver binds through ISO_C_BINDING
+ * (fortran/mglc_iso_c.f90).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns MGLC_OK (0) or a negative MGLC_E_* code; nothing aborts or throws;
+ *    mglc_last_error() returns a thread-local message for the last failure.
+ *  - all array pointers are HOST pointers to the reference's Fortran layout (column-major, the
+ *    population index fastest): f(0:18,nx,ny,nz), f_post(0:18,0:nx+1,0:ny+1,0:nz+1),
+ *    rho,u,v,w(nx,ny,nz) (L3/initial.f90:35-44).  The library copies; it keeps no caller pointer.
+ *  - one handle = one subdomain on one GPU, used by one host thread at a time (the reference's own
+ *    rule: one MPI rank, strictly sequential).
+ *  - there is NO CPU fallback: without a CUDA device the device entry points return MGLC_E_NOGPU.
+ */
+#ifndef MGLC_H
+#define MGLC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGLC_VERSION 100
+
+/* ---- status codes ---- */
+#define MGLC_OK          0
+#define MGLC_E_INVALID  (-1)   /* bad argument / descriptor */
+#define MGLC_E_CUDA     (-2)   /* CUDA runtime error */
+#define MGLC_E_NCCL     (-3)   /* NCCL error */
+#define MGLC_E_NOMEM    (-4)   /* device or host allocation failed */
+#define MGLC_E_STATE    (-5)   /* call not valid in the handle's current state */
+#define MGLC_E_NOGPU    (-6)   /* no CUDA device: the product has no CPU path */
+#define MGLC_E_DIVERGED (-7)   /* device-side fatal-physics flag (reference: stop / MPI_Abort) */
+
+/* ---- enums (plain ints in the ABI) ---- */
+enum { MGLC_D3Q19 = 0, MGLC_D3Q19_D3Q7 = 1, MGLC_D2Q9 = 2 };
+/* collision operator: MGLC_MRT_LID reproduces L3/collision.f90 including the meq(12) quirk (:85) */
+enum { MGLC_MRT_LID = 0, MGLC_MRT_THERMAL = 1, MGLC_BGK = 2 };
+/* arithmetic: STRICT keeps the reference's expression order, true divisions and no FMA contraction
+ * (bit-identical to the CPU oracle); FAST uses reciprocal multiplies + FMA (<= 1e-12 rel. L2). */
+enum { MGLC_ARITH_FAST = 0, MGLC_ARITH_STRICT = 1 };
+/* how halos move between subdomains */
+enum { MGLC_TRANSPORT_NONE = 0, MGLC_TRANSPORT_LOCAL = 1, MGLC_TRANSPORT_NCCL = 2 };
+/* fused-kernel variant (MGLC_KERNEL_AUTO picks the fastest validated one) */
+enum { MGLC_KERNEL_AUTO = 0, MGLC_KERNEL_DIRECT = 1, MGLC_KERNEL_TMA = 2 };
+
+typedef struct mglc_lbm   mglc_lbm;     /* opaque: one subdomain on one GPU */
+typedef struct mglc_comm  mglc_comm;    /* opaque: NCCL communicator wrapper */
+typedef struct mglc_group mglc_group;   /* opaque: P subdomains driven by one process */
+
+/* Plain-old-data descriptor; replaces the compile-time `parameter`s of `module commondata`
+ * (L3/commondata.f90:4-15,42-53). */
+typedef struct mglc_lbm_desc {
+    int lattice;        /* MGLC_D3Q19 ...                                              */
+    int collision;      /* MGLC_MRT_LID ...                                            */
+    int arith;          /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT                         */
+    int kernel;         /* MGLC_KERNEL_*                                               */
+    int gn[3];          /* total_nx, total_ny, total_nz          (commondata.f90:4)    */
+    int dims[3];        /* Cartesian process grid, dims(0) <-> x (main.f90:24)         */
+    int coords[3];      /* my coordinates in it                  (main.f90:36)         */
+    int ln[3];          /* local nx, ny, nz                      (main.f90:37-39)      */
+    int start[3];       /* 0-based global offset of local cell 1                       */
+    double tau;         /* tauf                                  (commondata.f90:9)    */
+    double U0;          /* lid speed                             (commondata.f90:8)    */
+    double rho0;        /* initial density                       (commondata.f90:7)    */
+    int device;         /* CUDA device ordinal                                         */
+    int reserved[7];
+} mglc_lbm_desc;
+
+/* one halo message of message_passing_sendrecv() (L3/ex_sendrecv.f90): dir 0..5 = faces
+ * +x,-x,+y,-y,+z,-z (5 populations each), dir 7..18 = the edge that population `dir` crosses. */
+typedef struct mglc_halo_msg {
+    int dir;            /* direction id as above                                       */
+    int send_to;        /* rank receiving my outgoing data, -1 = MPI_PROC_NULL         */
+    int recv_from;      /* rank whose data lands in my opposite halo, -1 = none        */
+    int npop;           /* 5 for faces, 1 for edges                                    */
+    int send_count;     /* doubles I send  (npop * my slab size)                       */
+    int recv_count;     /* doubles I receive (npop * sender's slab size)               */
+    int pops[5];        /* population indices, ascending (tag order of ex_sendrecv.f90) */
+} mglc_halo_msg;
+
+/* ================= host-only helpers (work without a GPU) ================= */
+int         mglc_version(void);
+const char *mglc_last_error(void);
+const char *mglc_strerror(int code);
+int         mglc_device_count(int *n);
+
+/* MPI_Dims_create(np,3,dims) with dims=0 -- L3/main.f90:24 */
+int mglc_dims_create(int nranks, int dims[3]);
+/* decompose_1d -- L3/main.f90:144-155 (first total_n mod nranks ranks get one extra plane) */
+int mglc_decompose_1d(int total_n, int rank, int nranks, int *local_n, int *start);
+/* MPI_Cart_rank / MPI_Cart_coords of the row-major communicator -- L3/main.f90:25,36 */
+int mglc_cart_rank(const int dims[3], const int coords[3], int *rank /* -1 outside */);
+int mglc_cart_coords(const int dims[3], int rank, int coords[3]);
+/* MPI_Cart_shift x3 + MPI_Cart_find_corners -- L3/main.f90:43-47,158-212.
+ * nbr_surface[0..5] = +x,-x,+y,-y,+z,-z ; nbr_line[0..11] = populations 7..18 ; -1 = PROC_NULL */
+int mglc_cart_neighbors(const int dims[3], const int coords[3], int nbr_surface[6], int nbr_line[12]);
+/* fill a descriptor the way L3/main.f90:24-39 + commondata.f90:9 do: dims (if dims[0]==0) from
+ * nranks, coords/ln/start from rank, tau = U0*total_nx/Re*3+0.5 */
+int mglc_lbm_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_zero[3], int nranks,
+                       int rank, double reynolds, double U0, double rho0);
+/* the 18 messages of one message_passing_sendrecv() for this subdomain, in the reference's order */
+int mglc_halo_plan(const mglc_lbm_desc *d, mglc_halo_msg msgs[18], int *nmsgs);
+/* relaxation rates Snu, Sq -- L3/commondata.f90:42 */
+int mglc_relaxation_rates(double tau, double *Snu, double *Sq);
+
+/* ================= communicator (one process per GPU) ================= */
+/* ncclGetUniqueId / ncclCommInitRank; the id is broadcast by the caller (MPI_Bcast in a Fortran
+ * driver, torch.distributed in the Python harness).  Replaces MPI_Cart_create, L3/main.f90:25. */
+int mglc_comm_unique_id(char id[128]);
+int mglc_comm_init_rank(mglc_comm **c, const char id[128], int nranks, int rank, int device);
+int mglc_comm_destroy(mglc_comm *c);
+
+/* ================= one subdomain ================= */
+/* allocate(f, f_post, rho,u,v,w,up,vp,wp) -- L3/initial.f90:35-44 ; comm may be NULL (1 rank) */
+int mglc_lbm_create(mglc_lbm **h, const mglc_lbm_desc *d, mglc_comm *comm_or_null);
+int mglc_lbm_destroy(mglc_lbm *h);                       /* deallocate -- L3/main.f90:123-131 */
+/* initial(): rho0, u=U0 on the lid plane, f = feq -- L3/initial.f90:46-73 (device-side) */
+int mglc_lbm_initial(mglc_lbm *h);
+int mglc_lbm_upload(mglc_lbm *h, const double *f, const double *rho, const double *u,
+                    const double *v, const double *w);   /* any pointer may be NULL = keep */
+int mglc_lbm_upload_fpost(mglc_lbm *h, const double *f_post);    /* with halo, for bit-exact tests */
+int mglc_lbm_download_macro(mglc_lbm *h, double *rho, double *u, double *v, double *w); /* output(), L3/output.f90:12-119 */
+int mglc_lbm_download_f(mglc_lbm *h, double *f);         /* backupData()-style checkpoints */
+int mglc_lbm_download_fpost(mglc_lbm *h, double *f_post);
+
+/* one call per reference subroutine (a driver can swap ONE call at a time) */
+int mglc_collision(mglc_lbm *h);    /* collision()                 L3/collision.f90:1-205   */
+int mglc_exchange(mglc_lbm *h);     /* message_passing_sendrecv()  L3/ex_sendrecv.f90:1-129 */
+int mglc_streaming(mglc_lbm *h);    /* streaming()                 L3/streaming.f90:1-23    */
+int mglc_bounceback(mglc_lbm *h);   /* bounceback()                L3/bounce_back.f90:1-86  */
+int mglc_macro(mglc_lbm *h);        /* macro()                     L3/macro.f90:1-28        */
+int mglc_check(mglc_lbm *h, double *errorU);   /* check() incl. Allreduce  L3/check.f90:1-37 */
+
+/* fused fast path == nsteps iterations of the loop body L3/main.f90:85-97
+ * (collision, exchange, streaming, bounceback, macro); prologue/epilogue handled inside, the state
+ * afterwards (f, f_post, rho,u,v,w) is the reference's state after the same number of iterations */
+int mglc_lbm_step(mglc_lbm *h, int nsteps);
+int mglc_lbm_sync(mglc_lbm *h);
+/* same, bracketed by CUDA events on the handle's compute stream; *ms = device time */
+int mglc_lbm_step_timed(mglc_lbm *h, int nsteps, float *ms);
+/* number of kernels this handle has launched so far / device time of the fused kernels only */
+int mglc_lbm_launch_count(mglc_lbm *h, long long *n);
+/* per-launch CUDA-event timing of the fused kernel on its launching stream (off by default);
+ * mglc_lbm_kernel_time returns and resets the accumulated device time and launch count */
+int mglc_lbm_set_profiling(mglc_lbm *h, int on);
+int mglc_lbm_kernel_time(mglc_lbm *h, float *fused_ms, long long *fused_launches);
+/* page-locked host memory for the caller's f / rho,u,v,w arrays (c_f_pointer on the Fortran side), so
+ * upload/download run at full PCIe rate; pageable pointers are accepted everywhere too */
+int mglc_host_alloc(void **p, size_t bytes);
+int mglc_host_free(void *p);
+int mglc_lbm_device_bytes(mglc_lbm *h, long long *bytes);
+int mglc_lbm_get_desc(mglc_lbm *h, mglc_lbm_desc *d);
+
+/* ================= P subdomains in one process (harness / tests / single-process multi-GPU) ===== */
+/* creates nranks subdomains of the global lattice gn with the reference decomposition; subdomain r
+ * lives on devices[r] (NULL = all on device 0); halos move by device-to-device copies */
+int mglc_group_create(mglc_group **g, const mglc_lbm_desc *global_desc, int nranks, const int *devices_or_null);
+int mglc_group_destroy(mglc_group *g);
+int mglc_group_size(mglc_group *g, int *nranks);
+int mglc_group_rank(mglc_group *g, int r, mglc_lbm **h);      /* borrowed handle */
+int mglc_group_initial(mglc_group *g);
+int mglc_group_collision(mglc_group *g);
+int mglc_group_exchange(mglc_group *g);
+int mglc_group_streaming(mglc_group *g);
+int mglc_group_bounceback(mglc_group *g);
+int mglc_group_macro(mglc_group *g);
+int mglc_group_check(mglc_group *g, double *errorU);
+int mglc_group_step(mglc_group *g, int nsteps);
+int mglc_group_step_timed(mglc_group *g, int nsteps, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGLC_H */

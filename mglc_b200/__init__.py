@@ -1,0 +1,14 @@
+"""mglc_b200 -- B200-native hot path of cheryli/MGLC (collide+stream lattice update, boundary kernels,
+3-D subdomain halo exchange) behind the C ABI of include/mglc.h.
+
+Everything that computes lives in libmglc.so (hand-written sm_100a CUDA, built by
+`__graft_entry__.build()` / `make -C mglc_b200/csrc`).  This package is the thin host-side mirror of the
+reference driver's interface; it has no CPU or PyTorch fallback and raises if the library is missing.
+"""
+from . import _lib
+from ._lib import MglcError, lib
+from .lbm import (Communicator, LidDrivenCavity, Subdomain, cart_neighbors, decompose_1d, dims_create,
+                  halo_plan, make_desc)
+
+__all__ = ["MglcError", "lib", "Communicator", "LidDrivenCavity", "Subdomain", "cart_neighbors",
+           "decompose_1d", "dims_create", "halo_plan", "make_desc", "_lib"]

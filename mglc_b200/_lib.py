@@ -1,0 +1,122 @@
+"""ctypes binding of libmglc.so (the C ABI in include/mglc.h).
+
+The library is the product; this module only declares its entry points.  There is no fallback: if the
+shared object is missing the import fails, and without a CUDA device the device entry points return
+MGLC_E_NOGPU, which `check()` turns into an exception.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmglc.so")
+
+OK, E_INVALID, E_CUDA, E_NCCL, E_NOMEM, E_STATE, E_NOGPU, E_DIVERGED = 0, -1, -2, -3, -4, -5, -6, -7
+D3Q19, D3Q19_D3Q7, D2Q9 = 0, 1, 2
+MRT_LID, MRT_THERMAL, BGK = 0, 1, 2
+ARITH_FAST, ARITH_STRICT = 0, 1
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+
+
+class MglcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmglc error {code}: {msg}")
+        self.code = code
+
+
+class LbmDesc(C.Structure):
+    _fields_ = [("lattice", C.c_int), ("collision", C.c_int), ("arith", C.c_int), ("kernel", C.c_int),
+                ("gn", C.c_int * 3), ("dims", C.c_int * 3), ("coords", C.c_int * 3), ("ln", C.c_int * 3),
+                ("start", C.c_int * 3), ("tau", C.c_double), ("U0", C.c_double), ("rho0", C.c_double),
+                ("device", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class HaloMsg(C.Structure):
+    _fields_ = [("dir", C.c_int), ("send_to", C.c_int), ("recv_from", C.c_int), ("npop", C.c_int),
+                ("send_count", C.c_int), ("recv_count", C.c_int), ("pops", C.c_int * 5)]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/mglc.h one to one
+SIGNATURES = {
+    "mglc_version": (C.c_int, []),
+    "mglc_last_error": (C.c_char_p, []),
+    "mglc_strerror": (C.c_char_p, [C.c_int]),
+    "mglc_device_count": (C.c_int, [_ip]),
+    "mglc_dims_create": (C.c_int, [C.c_int, _ip]),
+    "mglc_decompose_1d": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip]),
+    "mglc_cart_rank": (C.c_int, [_ip, _ip, _ip]),
+    "mglc_cart_coords": (C.c_int, [_ip, C.c_int, _ip]),
+    "mglc_cart_neighbors": (C.c_int, [_ip, _ip, _ip, _ip]),
+    "mglc_lbm_desc_init": (C.c_int, [C.POINTER(LbmDesc), _ip, _ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "mglc_halo_plan": (C.c_int, [C.POINTER(LbmDesc), C.POINTER(HaloMsg), _ip]),
+    "mglc_relaxation_rates": (C.c_int, [C.c_double, _dp, _dp]),
+    "mglc_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "mglc_comm_init_rank": (C.c_int, [_vpp, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "mglc_comm_destroy": (C.c_int, [_vp]),
+    "mglc_lbm_create": (C.c_int, [_vpp, C.POINTER(LbmDesc), _vp]),
+    "mglc_lbm_destroy": (C.c_int, [_vp]),
+    "mglc_lbm_initial": (C.c_int, [_vp]),
+    "mglc_lbm_upload": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mglc_lbm_upload_fpost": (C.c_int, [_vp, _vp]),
+    "mglc_lbm_download_macro": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mglc_lbm_download_f": (C.c_int, [_vp, _vp]),
+    "mglc_lbm_download_fpost": (C.c_int, [_vp, _vp]),
+    "mglc_collision": (C.c_int, [_vp]),
+    "mglc_exchange": (C.c_int, [_vp]),
+    "mglc_streaming": (C.c_int, [_vp]),
+    "mglc_bounceback": (C.c_int, [_vp]),
+    "mglc_macro": (C.c_int, [_vp]),
+    "mglc_check": (C.c_int, [_vp, _dp]),
+    "mglc_lbm_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_lbm_sync": (C.c_int, [_vp]),
+    "mglc_lbm_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_lbm_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_lbm_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
+    "mglc_lbm_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "mglc_host_alloc": (C.c_int, [_vpp, C.c_size_t]),
+    "mglc_host_free": (C.c_int, [_vp]),
+    "mglc_lbm_device_bytes": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_lbm_get_desc": (C.c_int, [_vp, C.POINTER(LbmDesc)]),
+    "mglc_group_create": (C.c_int, [_vpp, C.POINTER(LbmDesc), C.c_int, _ip]),
+    "mglc_group_destroy": (C.c_int, [_vp]),
+    "mglc_group_size": (C.c_int, [_vp, _ip]),
+    "mglc_group_rank": (C.c_int, [_vp, C.c_int, _vpp]),
+    "mglc_group_initial": (C.c_int, [_vp]),
+    "mglc_group_collision": (C.c_int, [_vp]),
+    "mglc_group_exchange": (C.c_int, [_vp]),
+    "mglc_group_streaming": (C.c_int, [_vp]),
+    "mglc_group_bounceback": (C.c_int, [_vp]),
+    "mglc_group_macro": (C.c_int, [_vp]),
+    "mglc_group_check": (C.c_int, [_vp, _dp]),
+    "mglc_group_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_group_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libmglc.so (once).  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C mglc_b200/csrc`).  mglc_b200 has no CPU/PyTorch fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise MglcError(rc, lib().mglc_last_error().decode() or lib().mglc_strerror(rc).decode())
+    return rc

@@ -1,0 +1,108 @@
+// common.cuh -- internal: device geometry of one subdomain, error plumbing, kernel launch prototypes.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/mglc.h"
+
+namespace mglc {
+
+constexpr int Q = 19;
+// x-index of interior cell i=1 inside a padded row: rows start 128-byte aligned and so does i=1, so
+// every warp-wide store of 32 consecutive cells is line-aligned.  Halo i=0 sits at OX-1.
+constexpr int OX = 16;
+
+// SoA population layout F[a][k][j][x], one-cell halo in every dimension (k,j in 0..n+1), x padded.
+struct Geom {
+    int nx, ny, nz;        // interior size
+    int px;                // x pitch in doubles (multiple of 16)
+    int py, pz;            // ny+2, nz+2
+    long long sy, sz, sq;  // strides in doubles: row, plane, population
+    // wall flags: 1 if the face is a physical wall of the global box (coords==0 / dims-1), L3/bounce_back.f90
+    int wall[6];           // +x,-x,+y,-y,+z,-z  (same order as nbr_surface)
+    int lid;               // 1 if this subdomain holds the moving lid (coords(2)==dims(2)-1)
+    __host__ __device__ long long idx(int a, int i, int j, int k) const {
+        return a * sq + k * sz + j * sy + (i + OX - 1);
+    }
+    __host__ __device__ long long cell(int i, int j, int k) const {   // macro fields (nx,ny,nz), 1-based
+        return (long long)(i - 1) + (long long)nx * ((j - 1) + (long long)ny * (k - 1));
+    }
+};
+
+inline Geom make_geom(int nx, int ny, int nz) {
+    Geom g{};
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.px = ((nx + OX + 1 + 15) / 16) * 16;
+    g.py = ny + 2; g.pz = nz + 2;
+    g.sy = g.px; g.sz = (long long)g.px * g.py; g.sq = g.sz * g.pz;
+    return g;
+}
+
+struct LbmParams {
+    double Snu, Sq, U0, rho0;
+};
+
+// D3Q19 tables, L3/commondata.f90:32-40 (host copies; device code uses constexpr switch tables)
+static const int h_ex[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+static const int h_ey[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+static const int h_ez[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+static const int h_opp[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+// populations crossing each face, ascending = tag order of L3/ex_sendrecv.f90:12,20,29,37,46,54
+static const int h_face_pops[6][5] = {{1, 7, 9, 11, 13}, {2, 8, 10, 12, 14}, {3, 7, 8, 15, 17},
+                                      {4, 9, 10, 16, 18}, {5, 11, 12, 15, 16}, {6, 13, 14, 17, 18}};
+
+void set_error(const char *fmt, ...);
+
+#define MGLC_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ::mglc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorMemoryAllocation) ? MGLC_E_NOMEM : MGLC_E_CUDA;            \
+        }                                                                                     \
+    } while (0)
+
+// ---- kernel launchers (each returns the number of kernels it launched) ----
+// Two builds of the same kernel source: namespace strict (-fmad=false, true divisions: bit-identical
+// to the CPU oracle) and namespace fast (reciprocal multiplies + FMA).
+#define MGLC_DECLARE_LBM_LAUNCHERS                                                                   \
+    int launch_collision(const Geom &g, const LbmParams &p, const double *F, const double *rho,      \
+                         const double *u, const double *v, const double *w, double *Fpost,           \
+                         cudaStream_t s);                                                            \
+    /* stream + macro + collide: pull from Fin (halo'd, post-collision) -> post-collision Fout;      \
+       box = [i0,i1]x[j0,j1]x[k0,k1] inclusive, 1-based interior cells */                            \
+    int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout,             \
+                     double *rho_field, const int box[6], cudaStream_t s);                           \
+    /* stream + macro (epilogue of a fused run): Fin (post-collision) -> F (pre-collision) + fields */\
+    int launch_stream_macro(const Geom &g, const double *Fin, double *F, double *rho, double *u,     \
+                            double *v, double *w, cudaStream_t s);
+
+namespace strict { MGLC_DECLARE_LBM_LAUNCHERS }
+namespace fast { MGLC_DECLARE_LBM_LAUNCHERS }
+
+// exact (copy / order-preserving) kernels, built once with -fmad=false
+int launch_initial(const Geom &g, const LbmParams &p, double *F, double *rho, double *u, double *v,
+                   double *w, cudaStream_t s);
+int launch_streaming(const Geom &g, const double *Fpost, double *F, cudaStream_t s);
+int launch_bounceback(const Geom &g, const LbmParams &p, const double *Fpost, const double *rho, double *F,
+                      cudaStream_t s);
+int launch_macro(const Geom &g, const double *F, double *rho, double *u, double *v, double *w, cudaStream_t s);
+// halo of Fpost at physical walls <- bounce-back values, so that a plain pull reproduces streaming+bounceback
+int launch_wallfill(const Geom &g, const LbmParams &p, double *Fpost, const double *rho, cudaStream_t s);
+// check(): partial[0] += sum (du^2+dv^2), partial[1] += sum(u^2+v^2+w^2); then up<-u, vp<-v, wp<-w
+int launch_check(const Geom &g, const double *u, const double *v, const double *w, double *up, double *vp,
+                 double *wp, double *partial2, cudaStream_t s);
+// halo pack/unpack for one message (dir 0..5 faces, 7..18 edges), buffer layout [slot][t2][t1]
+int launch_pack(const Geom &g, const double *Fpost, int dir, double *buf, cudaStream_t s);
+int launch_unpack(const Geom &g, double *Fpost, int dir, const double *buf, cudaStream_t s);
+// AoS (reference layout) <-> SoA transposes over a linear cell range [c0, c0+ncells)
+int launch_aos_to_soa(const Geom &g, const double *aos_chunk, double *F, long long c0, long long ncells,
+                      int with_halo, cudaStream_t s);
+int launch_soa_to_aos(const Geom &g, const double *F, double *aos_chunk, long long c0, long long ncells,
+                      int with_halo, cudaStream_t s);
+int launch_fill(double *p, long long n, double value, cudaStream_t s);
+int check_scratch_doubles();
+void msg_dims(const Geom &g, int dir, int &n1, int &n2, int &npop);
+
+}  // namespace mglc

@@ -1,0 +1,326 @@
+// exact_kernels.cu -- kernels whose results are bit-defined (copies, order-preserving sums, IEEE
+// divisions): initial(), streaming(), bounceback(), macro(), the wall-halo fill used by the fused path,
+// check() reductions, halo pack/unpack and the AoS<->SoA transposes of upload/download.
+// Built with -fmad=false so nothing is contracted; see lbm_kernels.inl for the collision kernels.
+#include "common.cuh"
+#include "d3q19_mrt.inl"
+
+namespace mglc {
+
+__constant__ int c_ex[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+__constant__ int c_ey[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+__constant__ int c_ez[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+__constant__ int c_opp[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+__constant__ int c_face_pops[6][5] = {{1, 7, 9, 11, 13}, {2, 8, 10, 12, 14}, {3, 7, 8, 15, 17},
+                                      {4, 9, 10, 16, 18}, {5, 11, 12, 15, 16}, {6, 13, 14, 17, 18}};
+
+static inline dim3 grid3(int nx, int ny, int nz, int tx) { return dim3((nx + tx - 1) / tx, ny, nz); }
+
+// ---- initial(), L3/initial.f90:46-73 -----------------------------------------------------------
+__global__ void k_initial(Geom g, LbmParams p, double *__restrict__ F, double *__restrict__ rho,
+                          double *__restrict__ u, double *__restrict__ v, double *__restrict__ w) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const double r0 = p.rho0;
+    const double uu = (g.lid && k == g.nz) ? p.U0 : 0.0, vv = 0.0, ww = 0.0;   // top boundary, :55-61
+    const long long m = g.cell(i, j, k);
+    rho[m] = r0; u[m] = uu; v[m] = vv; w[m] = ww;
+    const double us2 = uu * uu + vv * vv + ww * ww;
+    const long long c = g.idx(0, i, j, k);
+#pragma unroll
+    for (int a = 0; a < Q; ++a) {
+        const double omega = (a == 0) ? 1.0 / 3.0 : (a < 7 ? 1.0 / 18.0 : 1.0 / 36.0);
+        const double un = uu * (double)c_ex[a] + vv * (double)c_ey[a] + ww * (double)c_ez[a];
+        F[a * g.sq + c] = r0 * omega * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+    }
+}
+
+int launch_initial(const Geom &g, const LbmParams &p, double *F, double *rho, double *u, double *v, double *w,
+                   cudaStream_t s) {
+    k_initial<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, F, rho, u, v, w);
+    return 1;
+}
+
+// ---- streaming(), L3/streaming.f90:8-20: f(a,x) = f_post(a, x - e_a), halo read as it is ---------
+__global__ void __launch_bounds__(128) k_streaming(Geom g, const double *__restrict__ Fpost, double *__restrict__ F) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j, k);
+#pragma unroll
+    for (int a = 0; a < Q; ++a)
+        F[a * g.sq + c] = Fpost[a * g.sq + c - c_ez[a] * g.sz - c_ey[a] * g.sy - c_ex[a]];
+}
+
+int launch_streaming(const Geom &g, const double *Fpost, double *F, cudaStream_t s) {
+    k_streaming<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, Fpost, F);
+    return 1;
+}
+
+// moving-lid correction of L3/bounce_back.f90:77-78 for the bounced population `a` (13 or 14)
+__device__ __forceinline__ double lid_term(double val, double rho, double U0, int a) {
+    const double uw = (a == 14) ? U0 : -U0;
+    return val - rho / 6.0 * uw;
+}
+
+// ---- bounceback(), L3/bounce_back.f90:6-83, in place on f after streaming ------------------------
+// One pass per wall face; a population entering through two walls gets the same value from both
+// passes (half-way bounce-back), and the lid term is keyed on the cell (k == nz on the lid rank) so the
+// reference's "z processed last" outcome holds whichever pass writes last.
+__global__ void k_bounceback(Geom g, LbmParams p, const double *__restrict__ Fpost, const double *__restrict__ rho,
+                             double *__restrict__ F) {
+    const int face = blockIdx.y;
+    if (!g.wall[face]) return;
+    const int axis = face >> 1;
+    const int n1 = (axis == 0) ? g.ny : g.nx, n2 = (axis == 2) ? g.ny : g.nz;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 * n2) return;
+    const int t1 = 1 + t % n1, t2 = 1 + t / n1;
+    const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz);
+    const int fix = (face & 1) ? 1 : nfix;                 // +face -> last layer, -face -> first layer
+    const int i = (axis == 0) ? fix : t1;
+    const int j = (axis == 1) ? fix : (axis == 0 ? t1 : t2);
+    const int k = (axis == 2) ? fix : t2;
+    const long long c = g.idx(0, i, j, k);
+    const bool on_lid = g.lid && k == g.nz;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int a = c_face_pops[face ^ 1][q];            // populations that come out of this wall
+        double val = Fpost[c_opp[a] * g.sq + c];
+        if (on_lid && (a == 13 || a == 14)) val = lid_term(val, rho[g.cell(i, j, k)], p.U0, a);
+        F[a * g.sq + c] = val;
+    }
+}
+
+int launch_bounceback(const Geom &g, const LbmParams &p, const double *Fpost, const double *rho, double *F,
+                      cudaStream_t s) {
+    const int big = max(max(g.nx * g.ny, g.nx * g.nz), g.ny * g.nz);
+    k_bounceback<<<dim3((big + 127) / 128, 6), 128, 0, s>>>(g, p, Fpost, rho, F);
+    return 1;
+}
+
+// ---- wall-halo fill: the unified boundary rule applied to the halo ------------
+// For every halo cell h that lies outside the global box and every population a that would be pulled
+// from h by an interior cell x = h + e_a:  Fpost_a(h) := Fpost_opp(a)(x)  [- lid term].  A plain pull from
+// the halo then yields exactly streaming() followed by bounceback().
+__global__ void k_wallfill(Geom g, LbmParams p, double *__restrict__ Fpost, const double *__restrict__ rho) {
+    const int face = blockIdx.y;
+    if (!g.wall[face]) return;
+    const int axis = face >> 1;
+    const int n1 = ((axis == 0) ? g.ny : g.nx) + 2, n2 = ((axis == 2) ? g.ny : g.nz) + 2;   // incl. rims
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 * n2) return;
+    const int t1 = t % n1, t2 = t / n1;
+    const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz);
+    const int fix = (face & 1) ? 0 : nfix + 1;
+    const int i = (axis == 0) ? fix : t1;
+    const int j = (axis == 1) ? fix : (axis == 0 ? t1 : t2);
+    const int k = (axis == 2) ? fix : t2;
+    const long long ch = g.idx(0, i, j, k);
+    const bool above_lid = g.lid && k == g.nz + 1;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int a = c_face_pops[face ^ 1][q];            // populations entering through this wall
+        const int xi = i + c_ex[a], xj = j + c_ey[a], xk = k + c_ez[a];
+        if (xi < 1 || xi > g.nx || xj < 1 || xj > g.ny || xk < 1 || xk > g.nz) continue;
+        double val = Fpost[c_opp[a] * g.sq + g.idx(0, xi, xj, xk)];
+        if (above_lid && (a == 13 || a == 14)) val = lid_term(val, rho[g.cell(xi, xj, xk)], p.U0, a);
+        Fpost[a * g.sq + ch] = val;
+    }
+}
+
+int launch_wallfill(const Geom &g, const LbmParams &p, double *Fpost, const double *rho, cudaStream_t s) {
+    const int big = max(max((g.nx + 2) * (g.ny + 2), (g.nx + 2) * (g.nz + 2)), (g.ny + 2) * (g.nz + 2));
+    k_wallfill<<<dim3((big + 127) / 128, 6), 128, 0, s>>>(g, p, Fpost, rho);
+    return 1;
+}
+
+// ---- macro(), L3/macro.f90:6-25 ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_macro(Geom g, const double *__restrict__ F, double *__restrict__ rho,
+                                               double *__restrict__ u, double *__restrict__ v, double *__restrict__ w) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j, k);
+    double f[19];
+#pragma unroll
+    for (int a = 0; a < Q; ++a) f[a] = F[a * g.sq + c];
+    double r, uu, vv, ww;
+    d3q19_macro(f, r, uu, vv, ww);
+    const long long m = g.cell(i, j, k);
+    rho[m] = r; u[m] = uu; v[m] = vv; w[m] = ww;
+}
+
+int launch_macro(const Geom &g, const double *F, double *rho, double *u, double *v, double *w, cudaStream_t s) {
+    k_macro<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, F, rho, u, v, w);
+    return 1;
+}
+
+// ---- check(), L3/check.f90:12-23: two sums (error1 has no w term, :15) + up,vp,wp <- u,v,w ----------
+constexpr int CHECK_BLOCKS = 592;   // 4 x 148 SMs; fixed so the summation order is reproducible
+__global__ void __launch_bounds__(256) k_check_partial(long long n, const double *__restrict__ u,
+                                                       const double *__restrict__ v, const double *__restrict__ w,
+                                                       double *__restrict__ up, double *__restrict__ vp,
+                                                       double *__restrict__ wp, double *__restrict__ part) {
+    double e1 = 0.0, e2 = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const double a = u[q], b = v[q], c = w[q];
+        const double da = a - up[q], db = b - vp[q];
+        e1 += da * da + db * db;
+        e2 += a * a + b * b + c * c;
+        up[q] = a; vp[q] = b; wp[q] = c;
+    }
+    __shared__ double s1[256], s2[256];
+    s1[threadIdx.x] = e1; s2[threadIdx.x] = e2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 + 2 * blockIdx.x] = s1[0]; part[3 + 2 * blockIdx.x] = s2[0]; }
+}
+__global__ void k_check_final(int nblocks, double *__restrict__ part) {
+    double e1 = 0.0, e2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) { e1 += part[2 + 2 * b]; e2 += part[3 + 2 * b]; }
+    part[0] = e1; part[1] = e2;
+}
+int check_scratch_doubles() { return 2 + 2 * CHECK_BLOCKS; }
+int launch_check(const Geom &g, const double *u, const double *v, const double *w, double *up, double *vp,
+                 double *wp, double *part, cudaStream_t s) {
+    const long long n = (long long)g.nx * g.ny * g.nz;
+    k_check_partial<<<CHECK_BLOCKS, 256, 0, s>>>(n, u, v, w, up, vp, wp, part);
+    k_check_final<<<1, 1, 0, s>>>(CHECK_BLOCKS, part);
+    return 2;
+}
+
+// ---- halo pack / unpack, replacing the MPI derived datatypes surface_x/y/z, line_x/y/z -------------
+// (L3/main.f90:52-72) and the 42 Sendrecv of L3/ex_sendrecv.f90.  Message `dir`: 0..5 = faces
+// +x,-x,+y,-y,+z,-z carrying 5 populations in ascending order; 7..18 = the edge crossed by that
+// population.  Buffer layout [slot][t2][t1], t1 the faster tangential index.
+// cell coordinates of element (t1,t2) of message dir; recv=0: source layer in the interior,
+// recv=1: destination layer in the halo of the receiver
+__device__ __forceinline__ void msg_cell(const Geom &g, int dir, int recv, int t1, int t2, int &i, int &j, int &k) {
+    if (dir < 6) {
+        const int axis = dir >> 1, plus = !(dir & 1);
+        const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz);
+        const int fix = recv ? (plus ? 0 : nfix + 1) : (plus ? nfix : 1);
+        i = (axis == 0) ? fix : 1 + t1;
+        j = (axis == 1) ? fix : (axis == 0 ? 1 + t1 : 1 + t2);
+        k = (axis == 2) ? fix : 1 + t2;
+    } else {
+        const int e[3] = {c_ex[dir], c_ey[dir], c_ez[dir]};
+        const int n[3] = {g.nx, g.ny, g.nz};
+        int x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (e[d] == 0) x[d] = 1 + t1;
+            else if (e[d] > 0) x[d] = recv ? 0 : n[d];
+            else x[d] = recv ? n[d] + 1 : 1;
+        }
+        i = x[0]; j = x[1]; k = x[2];
+    }
+}
+
+__global__ void k_pack(Geom g, const double *__restrict__ Fpost, int dir, int n1, int n2, int npop,
+                       double *__restrict__ buf) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long per = (long long)n1 * n2;
+    if (t >= per * npop) return;
+    const int slot = (int)(t / per);
+    const int r = (int)(t % per);
+    int i, j, k;
+    msg_cell(g, dir, 0, r % n1, r / n1, i, j, k);
+    const int a = (dir < 6) ? c_face_pops[dir][slot] : dir;
+    buf[t] = Fpost[g.idx(a, i, j, k)];
+}
+__global__ void k_unpack(Geom g, double *__restrict__ Fpost, int dir, int n1, int n2, int npop,
+                         const double *__restrict__ buf) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long per = (long long)n1 * n2;
+    if (t >= per * npop) return;
+    const int slot = (int)(t / per);
+    const int r = (int)(t % per);
+    int i, j, k;
+    msg_cell(g, dir, 1, r % n1, r / n1, i, j, k);
+    const int a = (dir < 6) ? c_face_pops[dir][slot] : dir;
+    Fpost[g.idx(a, i, j, k)] = buf[t];
+}
+
+void msg_dims(const Geom &g, int dir, int &n1, int &n2, int &npop) {
+    if (dir < 6) {
+        const int axis = dir >> 1;
+        n1 = (axis == 0) ? g.ny : g.nx; n2 = (axis == 2) ? g.ny : g.nz; npop = 5;
+    } else {
+        n1 = (h_ex[dir] == 0) ? g.nx : (h_ey[dir] == 0 ? g.ny : g.nz); n2 = 1; npop = 1;
+    }
+}
+int launch_pack(const Geom &g, const double *Fpost, int dir, double *buf, cudaStream_t s) {
+    int n1, n2, npop;
+    msg_dims(g, dir, n1, n2, npop);
+    const long long n = (long long)n1 * n2 * npop;
+    k_pack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, Fpost, dir, n1, n2, npop, buf);
+    return 1;
+}
+int launch_unpack(const Geom &g, double *Fpost, int dir, const double *buf, cudaStream_t s) {
+    int n1, n2, npop;
+    msg_dims(g, dir, n1, n2, npop);
+    const long long n = (long long)n1 * n2 * npop;
+    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, Fpost, dir, n1, n2, npop, buf);
+    return 1;
+}
+
+// ---- AoS (reference: population index fastest) <-> SoA transposes ----------------------------------
+// A block moves TILE consecutive cells (linear reference order) through shared memory so that both the
+// AoS side (19*TILE contiguous doubles) and the SoA side (TILE contiguous cells per population) coalesce.
+constexpr int TILE = 128;
+__device__ __forceinline__ long long soa_cell_index(const Geom &g, long long cell, int with_halo) {
+    const int ex_ = with_halo ? 2 : 0;
+    const long long lx = g.nx + ex_, ly = g.ny + ex_;
+    const int i = (int)(cell % lx), j = (int)((cell / lx) % ly), k = (int)(cell / (lx * ly));
+    const int o = with_halo ? 0 : 1;
+    return g.idx(0, i + o, j + o, k + o);
+}
+__global__ void __launch_bounds__(256) k_aos_to_soa(Geom g, const double *__restrict__ aos, double *__restrict__ F,
+                                                    long long c0, long long ncells, int with_halo) {
+    __shared__ double sm[TILE * Q];
+    const long long t0 = (long long)blockIdx.x * TILE;
+    const int nt = (int)min((long long)TILE, ncells - t0);
+    for (int q = threadIdx.x; q < nt * Q; q += blockDim.x) sm[q] = aos[t0 * Q + q];
+    __syncthreads();
+    const int t = threadIdx.x % TILE;
+    if (t < nt) {
+        const long long c = soa_cell_index(g, c0 + t0 + t, with_halo);
+        for (int a = threadIdx.x / TILE; a < Q; a += blockDim.x / TILE) F[a * g.sq + c] = sm[t * Q + a];
+    }
+}
+__global__ void __launch_bounds__(256) k_soa_to_aos(Geom g, const double *__restrict__ F, double *__restrict__ aos,
+                                                    long long c0, long long ncells, int with_halo) {
+    __shared__ double sm[TILE * Q];
+    const long long t0 = (long long)blockIdx.x * TILE;
+    const int nt = (int)min((long long)TILE, ncells - t0);
+    const int t = threadIdx.x % TILE;
+    if (t < nt) {
+        const long long c = soa_cell_index(g, c0 + t0 + t, with_halo);
+        for (int a = threadIdx.x / TILE; a < Q; a += blockDim.x / TILE) sm[t * Q + a] = F[a * g.sq + c];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nt * Q; q += blockDim.x) aos[t0 * Q + q] = sm[q];
+}
+int launch_aos_to_soa(const Geom &g, const double *aos, double *F, long long c0, long long ncells, int with_halo,
+                      cudaStream_t s) {
+    k_aos_to_soa<<<(unsigned)((ncells + TILE - 1) / TILE), 256, 0, s>>>(g, aos, F, c0, ncells, with_halo);
+    return 1;
+}
+int launch_soa_to_aos(const Geom &g, const double *F, double *aos, long long c0, long long ncells, int with_halo,
+                      cudaStream_t s) {
+    k_soa_to_aos<<<(unsigned)((ncells + TILE - 1) / TILE), 256, 0, s>>>(g, F, aos, c0, ncells, with_halo);
+    return 1;
+}
+
+__global__ void k_fill(double *p, long long n, double v) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) p[q] = v;
+}
+int launch_fill(double *p, long long n, double value, cudaStream_t s) {
+    k_fill<<<1184, 256, 0, s>>>(p, n, value);
+    return 1;
+}
+
+}  // namespace mglc

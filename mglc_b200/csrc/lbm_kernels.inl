@@ -1,0 +1,111 @@
+// lbm_kernels.inl -- D3Q19 lattice-update kernels; compiled twice (lbm_strict.cu / lbm_fast.cu).
+//
+// Device layout (common.cuh): SoA F[a][k][j][x] with a one-cell halo; thread <-> cell, threadIdx.x runs
+// along x so every population access of a warp is one contiguous 256-byte segment.  The pull scheme
+// reads population a at (x - e_a): reads with ex = +-1 are shifted by 8 bytes (served from the same
+// L1/L2 lines), every store is 128-byte aligned.
+//
+// The fused kernel is the reference loop body rotated by half a step: it performs streaming()
+// (L3/streaming.f90) + bounceback() (L3/bounce_back.f90, pre-applied to the halo by wallfill) +
+// macro() (L3/macro.f90) of step n and collision() (L3/collision.f90) of step n+1, so a step costs
+// one read and one write of the 19 populations: 304 B/cell.
+#include "common.cuh"
+#include "d3q19_mrt.inl"
+
+namespace mglc {
+namespace MGLC_NS {
+
+// pull the 19 populations that arrive at cell c (c = linear index of the cell in population 0)
+#define MGLC_PULL(a, dx, dy, dz) f[a] = __ldg(Fin + (a) * sq + (c - (dz) * sz - (dy) * sy - (dx)))
+#define MGLC_PULL_ALL()                                                                        \
+    MGLC_PULL(0, 0, 0, 0);                                                                     \
+    MGLC_PULL(1, 1, 0, 0);   MGLC_PULL(2, -1, 0, 0);  MGLC_PULL(3, 0, 1, 0);   MGLC_PULL(4, 0, -1, 0);  \
+    MGLC_PULL(5, 0, 0, 1);   MGLC_PULL(6, 0, 0, -1);                                           \
+    MGLC_PULL(7, 1, 1, 0);   MGLC_PULL(8, -1, 1, 0);  MGLC_PULL(9, 1, -1, 0);  MGLC_PULL(10, -1, -1, 0); \
+    MGLC_PULL(11, 1, 0, 1);  MGLC_PULL(12, -1, 0, 1); MGLC_PULL(13, 1, 0, -1); MGLC_PULL(14, -1, 0, -1); \
+    MGLC_PULL(15, 0, 1, 1);  MGLC_PULL(16, 0, -1, 1); MGLC_PULL(17, 0, 1, -1); MGLC_PULL(18, 0, -1, -1)
+
+// collision(): F (interior) + rho,u,v,w -> Fpost (interior)
+__global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const double *__restrict__ F,
+                                                   const double *__restrict__ rho, const double *__restrict__ u,
+                                                   const double *__restrict__ v, const double *__restrict__ w,
+                                                   double *__restrict__ Fpost) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long sq = g.sq;
+    const long long c = g.idx(0, i, j, k);
+    const long long m = g.cell(i, j, k);
+    double f[19], fp[19];
+#pragma unroll
+    for (int a = 0; a < 19; ++a) f[a] = F[a * sq + c];
+    d3q19_collide(f, rho[m], u[m], v[m], w[m], p.Snu, p.Sq, fp);
+#pragma unroll
+    for (int a = 0; a < 19; ++a) Fpost[a * sq + c] = fp[a];
+}
+
+// fused: pull (stream + wall bounce-back through the pre-filled halo) -> macro -> collide -> store
+__global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const double *__restrict__ Fin,
+                                                  double *__restrict__ Fout, double *__restrict__ rho_field,
+                                                  int i0, int i1, int j0, int k0) {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
+    if (i > i1) return;
+    const long long sq = g.sq, sy = g.sy, sz = g.sz;
+    const long long c = g.idx(0, i, j, k);
+    double f[19], fp[19];
+    MGLC_PULL_ALL();
+    double rho, u, v, w;
+    d3q19_macro(f, rho, u, v, w);
+    d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
+#pragma unroll
+    for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
+    // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
+    // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro())
+    if (g.lid && k == g.nz) rho_field[g.cell(i, j, k)] = rho;
+}
+
+// epilogue of a fused run: pull -> f (pre-collision, as the reference leaves it) and macro fields
+__global__ void __launch_bounds__(128) k_stream_macro(Geom g, const double *__restrict__ Fin,
+                                                      double *__restrict__ F, double *__restrict__ rho_o,
+                                                      double *__restrict__ u_o, double *__restrict__ v_o,
+                                                      double *__restrict__ w_o) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long sq = g.sq, sy = g.sy, sz = g.sz;
+    const long long c = g.idx(0, i, j, k);
+    double f[19];
+    MGLC_PULL_ALL();
+#pragma unroll
+    for (int a = 0; a < 19; ++a) F[a * sq + c] = f[a];
+    double rho, u, v, w;
+    d3q19_macro(f, rho, u, v, w);
+    const long long m = g.cell(i, j, k);
+    rho_o[m] = rho; u_o[m] = u; v_o[m] = v; w_o[m] = w;
+}
+
+static inline dim3 grid_for(int nxs, int nys, int nzs, int tx) { return dim3((nxs + tx - 1) / tx, nys, nzs); }
+
+int launch_collision(const Geom &g, const LbmParams &p, const double *F, const double *rho, const double *u,
+                     const double *v, const double *w, double *Fpost, cudaStream_t s) {
+    k_collision<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, F, rho, u, v, w, Fpost);
+    return 1;
+}
+
+int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout, double *rho_field,
+                 const int box[6], cudaStream_t s) {
+    const int nxs = box[1] - box[0] + 1, nys = box[3] - box[2] + 1, nzs = box[5] - box[4] + 1;
+    if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
+    k_fused<<<grid_for(nxs, nys, nzs, 128), 128, 0, s>>>(g, p, Fin, Fout, rho_field, box[0], box[1], box[2], box[4]);
+    return 1;
+}
+
+int launch_stream_macro(const Geom &g, const double *Fin, double *F, double *rho, double *u, double *v,
+                        double *w, cudaStream_t s) {
+    k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, Fin, F, rho, u, v, w);
+    return 1;
+}
+
+}  // namespace MGLC_NS
+}  // namespace mglc

@@ -1,0 +1,310 @@
+"""GPU parity tests of the D3Q19 lid-driven-cavity path: libmglc.so (through the C ABI, via ctypes)
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * streaming(), message_passing_sendrecv(), bounceback(), macro(), initial(): bit-exact
+  * collision() / step(N): bit-exact in MGLC_ARITH_STRICT; in MGLC_ARITH_FAST rho,u,v,w agree with the
+    oracle to <= 1e-12 relative L2 and <= 1e-10 max pointwise
+  * P-subdomain runs (uneven blocks) reproduce the 1-subdomain run bit for bit
+"""
+import os
+
+import numpy as np
+import pytest
+
+import mglc_b200 as mg
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-12      # north_star tolerance on macroscopic fields
+MAX_ABS = 1e-10
+
+
+def rel_l2(a, b):
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def seeded_state(total, seed=1234):
+    """SURVEY 8(d) stress input: f = feq(rho = 1 + 0.01 xi, u = 0.05 xi) so every moment is non-trivial."""
+    rng = np.random.default_rng(seed)
+    rho = np.asfortranarray(1.0 + 0.01 * rng.uniform(-1, 1, total))
+    u, v, w = (np.asfortranarray(0.05 * rng.uniform(-1, 1, total)) for _ in range(3))
+    f = np.asfortranarray(orc.feq(rho, u, v, w))
+    return f, rho, u, v, w
+
+
+def oracle_world(total, nprocs=1, dims=None, seed=None):
+    wd = orc.LidWorld(total, nprocs, dims=dims)
+    wd.initial()
+    if seed is not None:
+        f, rho, u, v, w = seeded_state(total, seed)
+        for k, a in (("f", f), ("rho", rho), ("u", u), ("v", v), ("w", w)):
+            wd.scatter(k, a)
+    return wd
+
+
+def gpu_world(total, nprocs=1, dims=None, seed=None, arith="strict"):
+    sim = mg.LidDrivenCavity(total, nprocs=nprocs, dims=dims, arith=arith)
+    sim.initial()
+    if seed is not None:
+        sim.scatter(*seeded_state(total, seed))
+    return sim
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_initial_bit_exact():
+    total = (34, 33, 32)
+    wd, sim = oracle_world(total), gpu_world(total)
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    m = sim.gather_macro()
+    for k in m:
+        assert np.array_equal(m[k], wd.gather(k)), k
+    wd.close(); sim.close()
+
+
+def test_upload_download_roundtrip():
+    total = (37, 5, 9)           # nx not a multiple of anything; exercises the transpose tails
+    sim = mg.LidDrivenCavity(total)
+    rng = np.random.default_rng(7)
+    f = np.asfortranarray(rng.random((19,) + total))
+    fp = np.asfortranarray(rng.random((19, total[0] + 2, total[1] + 2, total[2] + 2)))
+    fields = [np.asfortranarray(rng.random(total)) for _ in range(4)]
+    R = sim.ranks[0]
+    R.upload(f, *fields)
+    R.upload_fpost(fp)
+    assert np.array_equal(R.download_f(), f)
+    assert np.array_equal(R.download_fpost(), fp)
+    m = R.download_macro()
+    for k, a in zip(("rho", "u", "v", "w"), fields):
+        assert np.array_equal(m[k], a)
+    sim.close()
+
+
+def test_streaming_bit_exact():
+    """f_post = rng(7).random() on 34x33x32 including the halo; == on every double."""
+    total = (34, 33, 32)
+    rng = np.random.default_rng(7)
+    fp = np.asfortranarray(rng.random((19, 36, 35, 34)))
+    wd = orc.LidWorld(total, 1)
+    wd.ranks[0].f_post[...] = fp
+    wd.streaming()
+    sim = mg.LidDrivenCavity(total)
+    sim.ranks[0].upload_fpost(fp)
+    sim.streaming()
+    assert np.array_equal(sim.ranks[0].download_f(), wd.ranks[0].f)
+    wd.close(); sim.close()
+
+
+def test_bounceback_and_macro_bit_exact():
+    total = (18, 17, 16)
+    rng = np.random.default_rng(8)
+    fp = np.asfortranarray(rng.random((19, 20, 19, 18)))
+    rho = np.asfortranarray(1.0 + 0.1 * rng.random(total))
+    wd = orc.LidWorld(total, 1)
+    R = wd.ranks[0]
+    R.f_post[...] = fp
+    R.rho[...] = rho
+    wd.streaming(); wd.bounceback()
+    f_bb = R.f.copy(order="F")
+    wd.macro()
+    sim = mg.LidDrivenCavity(total)
+    S = sim.ranks[0]
+    S.upload_fpost(fp)
+    S.upload(rho=rho)
+    sim.streaming(); sim.bounceback()
+    assert np.array_equal(S.download_f(), f_bb)
+    sim.macro()
+    m = S.download_macro()
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(m[k], getattr(R, k)), k
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_collision(arith):
+    total = (21, 10, 11)
+    wd = oracle_world(total, seed=99)
+    sim = gpu_world(total, seed=99, arith=arith)
+    wd.collision(); sim.collision()
+    nx, ny, nz = total
+    want = wd.ranks[0].f_post[:, 1:nx + 1, 1:ny + 1, 1:nz + 1]
+    got = sim.ranks[0].download_fpost()[:, 1:nx + 1, 1:ny + 1, 1:nz + 1]
+    if arith == "strict":
+        assert np.array_equal(got, want)
+    else:
+        assert np.abs(got - want).max() < 1e-15
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("total,nsteps", [((13, 11, 9), 1), ((13, 11, 9), 2), ((13, 11, 9), 25), ((40, 24, 17), 10)])
+def test_fused_step_strict_is_bit_exact(total, nsteps):
+    """The rotated fused loop (collide | halo+walls | stream+macro+collide ... | stream+macro) must leave
+    exactly the reference's state after the same number of loop bodies: f, f_post (interior), rho,u,v,w."""
+    wd = oracle_world(total, seed=5)
+    sim = gpu_world(total, seed=5, arith="strict")
+    wd.step(nsteps); sim.step(nsteps)
+    m = sim.gather_macro()
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(m[k], wd.gather(k)), k
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    nx, ny, nz = total
+    assert np.array_equal(sim.ranks[0].download_fpost()[:, 1:nx + 1, 1:ny + 1, 1:nz + 1],
+                          wd.ranks[0].f_post[:, 1:nx + 1, 1:ny + 1, 1:nz + 1])
+    # a second call continues from the same state (prologue/epilogue are consistent)
+    wd.step(3); sim.step(3)
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    wd.close(); sim.close()
+
+
+def test_unfused_sequence_equals_fused_step():
+    total = (20, 12, 9)
+    a, b = gpu_world(total, seed=3, arith="fast"), gpu_world(total, seed=3, arith="fast")
+    for _ in range(4):
+        a.collision(); a.message_passing_sendrecv(); a.streaming(); a.bounceback(); a.macro()
+    b.step(4)
+    ma, mb = a.gather_macro(), b.gather_macro()
+    for k in ma:
+        assert np.array_equal(ma[k], mb[k]), k
+    assert np.array_equal(a.gather("f"), b.gather("f"))
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("nsteps", [1, 10, 100])
+def test_config1_fast_within_tolerance(nsteps):
+    """Config 1: 65^3, Re=1000, U0=0.1 from initial(); fast arithmetic vs oracle."""
+    total = (65, 65, 65)
+    wd, sim = oracle_world(total), gpu_world(total, arith="fast")
+    wd.step(nsteps); sim.step(nsteps)
+    m = sim.gather_macro()
+    for k in ("rho", "u", "v", "w"):
+        ref = wd.gather(k)
+        assert rel_l2(m[k], ref) <= REL_L2, (k, rel_l2(m[k], ref))
+        assert np.abs(m[k] - ref).max() <= MAX_ABS, k
+    e_ref, e_gpu = wd.check(), sim.check()
+    assert abs(e_gpu - e_ref) <= 1e-10 * e_ref
+    wd.close(); sim.close()
+
+
+def test_config1_2000_steps_errorU_and_fields():
+    total = (65, 65, 65)
+    wd, sim = oracle_world(total), gpu_world(total, arith="fast")
+    wd.step(2000); sim.step(2000)
+    m = sim.gather_macro()
+    for k in ("rho", "u", "v", "w"):
+        ref = wd.gather(k)
+        assert rel_l2(m[k], ref) <= REL_L2, (k, rel_l2(m[k], ref))
+        assert np.abs(m[k] - ref).max() <= MAX_ABS, k
+    e_ref, e_gpu = wd.check(), sim.check()
+    assert abs(e_gpu - e_ref) <= 1e-9 * e_ref
+    wd.close(); sim.close()
+
+
+def test_stress_input_fast_within_tolerance():
+    total = (33, 31, 29)
+    wd, sim = oracle_world(total, seed=1234), gpu_world(total, seed=1234, arith="fast")
+    wd.step(50); sim.step(50)
+    m = sim.gather_macro()
+    for k in ("rho", "u", "v", "w"):
+        ref = wd.gather(k)
+        assert rel_l2(m[k], ref) <= REL_L2, (k, rel_l2(m[k], ref))
+        assert np.abs(m[k] - ref).max() <= MAX_ABS, k
+    wd.close(); sim.close()
+
+
+def test_golden_fixture():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lid_9x8x7.npz"))
+    for arith in ("strict", "fast"):
+        sim = gpu_world((9, 8, 7), seed=int(g["seed"]), arith=arith)
+        sim.step(int(g["nsteps"]))
+        m = sim.gather_macro()
+        for k in ("rho", "u", "v", "w"):
+            if arith == "strict":
+                assert np.array_equal(m[k], g[k]), k
+            else:
+                assert rel_l2(m[k], g[k]) <= REL_L2 and np.abs(m[k] - g[k]).max() <= MAX_ABS
+        e = sim.check()
+        assert abs(e - float(g["errorU"])) <= 1e-12 * float(g["errorU"])
+        sim.close()
+
+
+# ---- P subdomains (one process, device-to-device halo copies) -------------------------------------------
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (8, None), (3, (1, 3, 1)), (4, (1, 2, 2)), (12, None)])
+def test_exchange_bit_exact(nprocs, dims):
+    """message_passing_sendrecv() alone: random f_post interiors, halos compared where the reference writes."""
+    total = (14, 13, 12)
+    wd = orc.LidWorld(total, nprocs, dims=dims)
+    sim = mg.LidDrivenCavity(total, nprocs=nprocs, dims=dims)
+    assert sim.dims == wd.dims
+    rng = np.random.default_rng(17)
+    for R, S in zip(wd.ranks, sim.ranks):
+        assert S.n == R.n and S.start == R.start
+        nx, ny, nz = R.n
+        fp = np.zeros((19, nx + 2, ny + 2, nz + 2), order="F")
+        fp[:, 1:nx + 1, 1:ny + 1, 1:nz + 1] = rng.random((19, nx, ny, nz))
+        R.f_post[...] = np.nan
+        R.f_post[:, 1:nx + 1, 1:ny + 1, 1:nz + 1] = fp[:, 1:nx + 1, 1:ny + 1, 1:nz + 1]
+        S.upload_fpost(fp)
+    wd.message_passing_sendrecv()
+    sim.message_passing_sendrecv()
+    touched = 0
+    for R, S in zip(wd.ranks, sim.ranks):
+        got = S.download_fpost()
+        written = ~np.isnan(R.f_post)
+        assert np.array_equal(got[written], R.f_post[written])
+        assert np.all(got[~written] == 0.0)            # nothing else is touched
+        nx, ny, nz = R.n
+        touched += written.sum() - 19 * nx * ny * nz
+    assert touched > 0
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (8, None), (6, None), (4, (1, 1, 4))])
+def test_decomposition_invariance_bit_exact(nprocs, dims):
+    """P-subdomain fused run == 1-rank oracle, bit for bit (uneven 13/11/9 splits)."""
+    total = (13, 11, 9)
+    wd = oracle_world(total, seed=1234)
+    sim = gpu_world(total, nprocs=nprocs, dims=dims, seed=1234, arith="strict")
+    wd.step(12); sim.step(12)
+    m = sim.gather_macro()
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(m[k], wd.gather(k)), k
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    e_ref, e_gpu = wd.check(), sim.check()
+    assert abs(e_gpu - e_ref) <= 1e-12 * e_ref
+    wd.close(); sim.close()
+
+
+def test_config1_decomposed_2x2x2_fast_matches_single_gpu_run():
+    """65^3 on 8 subdomains (33/32 split): identical per-cell arithmetic => bit-identical to 1 subdomain."""
+    total = (65, 65, 65)
+    one, many = gpu_world(total, arith="fast"), gpu_world(total, nprocs=8, arith="fast")
+    one.step(20); many.step(20)
+    a, b = one.gather_macro(), many.gather_macro()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    one.close(); many.close()
+
+
+# ---- full-size properties (config 3: 768^3) ---------------------------------------------------------------
+def test_full_size_768_properties():
+    """At BASELINE's full size the oracle is too slow; check size-independent properties instead:
+    closed-cavity mass conservation, no NaN, y-mirror symmetry of the lid-driven flow."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n = 768 if free > 170e9 else 512
+    total = (n, n, n)
+    sim = mg.LidDrivenCavity(total, arith="fast")
+    sim.initial()
+    sim.step(4)
+    m = sim.ranks[0].download_macro()
+    rho, u, v = m["rho"], m["u"], m["v"]
+    assert np.isfinite(rho).all() and np.isfinite(u).all()
+    mass = rho.sum(dtype=np.float64)
+    assert abs(mass - float(n) ** 3) / float(n) ** 3 < 1e-12
+    top = u[:, :, -1]
+    assert top.mean() > 0.05                                     # the lid drags the top layer
+    assert np.abs(u[:, :, -3:] - u[:, ::-1, -3:]).max() < 1e-13  # mirror symmetry in y
+    assert np.abs(v[:, :, -3:] + v[:, ::-1, -3:]).max() < 1e-13
+    assert np.all(u[:, :, : n // 2] == 0.0)                      # 4 steps cannot reach the lower half
+    sim.close()
