@@ -1,0 +1,153 @@
+!> ISO_C_BINDING interface to libmglc.so (include/mglc.h) for MGLC's Fortran drivers.
+!!
+!! The reference has no bind(C) layer; its time loops call argument-less subroutines over
+!! `module commondata` (MPI/Lid_driven_cavity/fortran/3d/mpi_3d_blocked/main.f90:85-103).  With this
+!! module a driver keeps its own `main`, arrays and output routines and swaps the loop body for the
+!! GPU path, one call at a time or all at once (see INTEGRATION.md).
+!!
+!! Not compiled in the authoring image (no Fortran compiler there); it is declarative and mirrors the
+!! C header one to one.  Link with:  mpif90 ... mglc_iso_c.f90 main.f90 -L<repo>/mglc_b200 -lmglc
+module mglc_iso_c
+    use, intrinsic :: iso_c_binding
+    implicit none
+
+    integer(c_int), parameter :: MGLC_OK = 0
+    integer(c_int), parameter :: MGLC_D3Q19 = 0, MGLC_MRT_LID = 0
+    integer(c_int), parameter :: MGLC_ARITH_FAST = 0, MGLC_ARITH_STRICT = 1
+
+    !> mglc_lbm_desc: replaces the compile-time parameters of commondata (commondata.f90:4-15,42-53)
+    type, bind(C) :: mglc_lbm_desc
+        integer(c_int) :: lattice, collision, arith, kernel
+        integer(c_int) :: gn(3), dims(3), coords(3), ln(3), start(3)
+        real(c_double) :: tau, U0, rho0
+        integer(c_int) :: device
+        integer(c_int) :: reserved(7)
+    end type mglc_lbm_desc
+
+    interface
+        ! ---- host-only helpers -------------------------------------------------------------------
+        function mglc_lbm_desc_init(d, gn, dims_or_zero, nranks, rank, reynolds, U0, rho0) &
+                bind(C, name="mglc_lbm_desc_init") result(rc)
+            import :: c_int, c_double, mglc_lbm_desc
+            type(mglc_lbm_desc), intent(out) :: d
+            integer(c_int), intent(in) :: gn(3), dims_or_zero(3)
+            integer(c_int), value :: nranks, rank
+            real(c_double), value :: reynolds, U0, rho0
+            integer(c_int) :: rc
+        end function
+        function mglc_last_error() bind(C, name="mglc_last_error") result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        ! ---- communicator: the id is MPI_Bcast by the driver --------------------------------------
+        function mglc_comm_unique_id(id) bind(C, name="mglc_comm_unique_id") result(rc)
+            import :: c_int, c_char
+            character(kind=c_char), intent(out) :: id(128)
+            integer(c_int) :: rc
+        end function
+        function mglc_comm_init_rank(comm, id, nranks, rank, device) bind(C, name="mglc_comm_init_rank") result(rc)
+            import :: c_int, c_char, c_ptr
+            type(c_ptr), intent(out) :: comm
+            character(kind=c_char), intent(in) :: id(128)
+            integer(c_int), value :: nranks, rank, device
+            integer(c_int) :: rc
+        end function
+        function mglc_comm_destroy(comm) bind(C, name="mglc_comm_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        ! ---- one subdomain ------------------------------------------------------------------------
+        function mglc_lbm_create(h, d, comm) bind(C, name="mglc_lbm_create") result(rc)
+            import :: c_int, c_ptr, mglc_lbm_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_lbm_desc), intent(in) :: d
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_destroy(h) bind(C, name="mglc_lbm_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_initial(h) bind(C, name="mglc_lbm_initial") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        !> f(0:18,nx,ny,nz), rho,u,v,w(nx,ny,nz): the driver's own arrays, passed as they are
+        function mglc_lbm_upload(h, f, rho, u, v, w) bind(C, name="mglc_lbm_upload") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: f(*), rho(*), u(*), v(*), w(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_download_macro(h, rho, u, v, w) bind(C, name="mglc_lbm_download_macro") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: rho(*), u(*), v(*), w(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_download_f(h, f) bind(C, name="mglc_lbm_download_f") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: f(*)
+            integer(c_int) :: rc
+        end function
+        ! one call per reference subroutine
+        function mglc_collision(h) bind(C, name="mglc_collision") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_exchange(h) bind(C, name="mglc_exchange") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_streaming(h) bind(C, name="mglc_streaming") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_bounceback(h) bind(C, name="mglc_bounceback") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_macro(h) bind(C, name="mglc_macro") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_check(h, errorU) bind(C, name="mglc_check") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU
+            integer(c_int) :: rc
+        end function
+        !> nsteps iterations of the loop body main.f90:85-97 in fused form
+        function mglc_lbm_step(h, nsteps) bind(C, name="mglc_lbm_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_sync(h) bind(C, name="mglc_lbm_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_host_alloc(p, bytes) bind(C, name="mglc_host_alloc") result(rc)
+            import :: c_int, c_ptr, c_size_t
+            type(c_ptr), intent(out) :: p
+            integer(c_size_t), value :: bytes
+            integer(c_int) :: rc
+        end function
+        function mglc_host_free(p) bind(C, name="mglc_host_free") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: p
+            integer(c_int) :: rc
+        end function
+    end interface
+end module mglc_iso_c

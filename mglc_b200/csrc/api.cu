@@ -47,6 +47,10 @@ struct mglc_lbm {
     int rank, nranks;
     double *buf[2];          // two halo'd SoA lattices; buf[cur] = f (pre-collision), buf[cur^1] = f_post
     int cur;
+    // rotated: a fused run is in flight -- buf[cur^1] already holds the NEXT step's post-collision
+    // populations (before exchange), buf[cur] the last step's f_post with its halos, and only the lid
+    // plane of rho is current.  canonicalise() turns this back into the reference's state (f, rho,u,v,w).
+    int rotated;
     double *rho, *u, *v, *w, *up, *vp, *wp;
     double *scratch;         // check() partial sums
     cudaStream_t s, s_comm;
@@ -256,6 +260,8 @@ extern "C" int mglc_lbm_sync(mglc_lbm *h) {
     return MGLC_OK;
 }
 
+static int canonicalise(mglc_lbm *h);
+
 // ---- host <-> device transfers in the reference layout ---------------------------------------------------
 static int ensure_stage(mglc_lbm *h) {
     if (h->stage) return MGLC_OK;
@@ -292,6 +298,7 @@ static int copy_field(mglc_lbm *h, double *host, double *dev, bool to_device) {
 extern "C" int mglc_lbm_upload(mglc_lbm *h, const double *f, const double *rho, const double *u, const double *v,
                                const double *w) {
     MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
     if (f) MGLC_TRY(transfer_lattice(h, const_cast<double *>(f), F_(h), 0, true));
     MGLC_TRY(copy_field(h, const_cast<double *>(rho), h->rho, true));
     MGLC_TRY(copy_field(h, const_cast<double *>(u), h->u, true));
@@ -302,11 +309,13 @@ extern "C" int mglc_lbm_upload(mglc_lbm *h, const double *f, const double *rho, 
 }
 extern "C" int mglc_lbm_upload_fpost(mglc_lbm *h, const double *f_post) {
     MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
     if (!f_post) return MGLC_E_INVALID;
     return transfer_lattice(h, const_cast<double *>(f_post), Fpost_(h), 1, true);
 }
 extern "C" int mglc_lbm_download_macro(mglc_lbm *h, double *rho, double *u, double *v, double *w) {
     MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
     MGLC_TRY(copy_field(h, rho, h->rho, false));
     MGLC_TRY(copy_field(h, u, h->u, false));
     MGLC_TRY(copy_field(h, v, h->v, false));
@@ -316,17 +325,20 @@ extern "C" int mglc_lbm_download_macro(mglc_lbm *h, double *rho, double *u, doub
 }
 extern "C" int mglc_lbm_download_f(mglc_lbm *h, double *f) {
     MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
     if (!f) return MGLC_E_INVALID;
     return transfer_lattice(h, f, F_(h), 0, false);
 }
 extern "C" int mglc_lbm_download_fpost(mglc_lbm *h, double *f_post) {
     MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
     if (!f_post) return MGLC_E_INVALID;
     return transfer_lattice(h, f_post, Fpost_(h), 1, false);
 }
 
 // ---- single-subdomain building blocks ---------------------------------------------------------------------
 static int do_initial(mglc_lbm *h) {
+    h->rotated = 0;
     h->launches += launch_initial(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, h->s);
     if (h->up) {
         const size_t b = (size_t)ncell(h) * sizeof(double);
@@ -337,6 +349,7 @@ static int do_initial(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_collision(mglc_lbm *h) {
+    MGLC_TRY(canonicalise(h));
     h->launches += strict_(h) ? strict::launch_collision(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, Fpost_(h), h->s)
                               : fast::launch_collision(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, Fpost_(h), h->s);
     return MGLC_OK;
@@ -371,19 +384,18 @@ static int do_exchange_nccl(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_streaming(mglc_lbm *h) {
+    MGLC_TRY(canonicalise(h));
     h->launches += launch_streaming(h->g, Fpost_(h), F_(h), h->s);
     return MGLC_OK;
 }
 static int do_bounceback(mglc_lbm *h) {
+    MGLC_TRY(canonicalise(h));
     h->launches += launch_bounceback(h->g, h->p, Fpost_(h), h->rho, F_(h), h->s);
     return MGLC_OK;
 }
 static int do_macro(mglc_lbm *h) {
+    MGLC_TRY(canonicalise(h));
     h->launches += launch_macro(h->g, F_(h), h->rho, h->u, h->v, h->w, h->s);
-    return MGLC_OK;
-}
-static int do_wallfill(mglc_lbm *h) {
-    h->launches += launch_wallfill(h->g, h->p, Fpost_(h), h->rho, h->s);
     return MGLC_OK;
 }
 // fused stream+macro+collide over the whole subdomain: reads f_post (incl. halo), writes the NEXT f_post
@@ -421,8 +433,18 @@ static int do_fused(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_stream_macro(mglc_lbm *h) {
-    h->launches += strict_(h) ? strict::launch_stream_macro(h->g, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s)
-                              : fast::launch_stream_macro(h->g, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s);
+    h->launches += strict_(h) ? strict::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s)
+                              : fast::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s);
+    return MGLC_OK;
+}
+// Leave the rotated state: the last step's f_post (with halos) is still intact in buf[cur]; pull it into
+// the other lattice (discarding the pre-computed next collision, which collision() will redo) and write
+// rho,u,v,w.  Afterwards f, f_post, rho,u,v,w are the reference's after the same number of loop bodies.
+static int canonicalise(mglc_lbm *h) {
+    if (!h->rotated) return MGLC_OK;
+    h->cur ^= 1;
+    MGLC_TRY(do_stream_macro(h));
+    h->rotated = 0;
     return MGLC_OK;
 }
 static int ensure_prev(mglc_lbm *h) {
@@ -437,6 +459,7 @@ static int ensure_prev(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_check_partial(mglc_lbm *h) {
+    MGLC_TRY(canonicalise(h));
     MGLC_TRY(ensure_prev(h));
     h->launches += launch_check(h->g, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->s);
     return MGLC_OK;
@@ -450,7 +473,12 @@ static int not_in_group(mglc_lbm *h, const char *what) {
 // ---- public per-subroutine entry points ------------------------------------------------------------------
 extern "C" int mglc_lbm_initial(mglc_lbm *h) { MGLC_TRY(use(h)); return do_initial(h); }
 extern "C" int mglc_collision(mglc_lbm *h) { MGLC_TRY(use(h)); return do_collision(h); }
-extern "C" int mglc_exchange(mglc_lbm *h) { MGLC_TRY(use(h)); MGLC_TRY(not_in_group(h, "mglc_exchange")); return do_exchange_nccl(h); }
+extern "C" int mglc_exchange(mglc_lbm *h) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(not_in_group(h, "mglc_exchange"));
+    MGLC_TRY(canonicalise(h));
+    return do_exchange_nccl(h);
+}
 extern "C" int mglc_streaming(mglc_lbm *h) { MGLC_TRY(use(h)); return do_streaming(h); }
 extern "C" int mglc_bounceback(mglc_lbm *h) { MGLC_TRY(use(h)); return do_bounceback(h); }
 extern "C" int mglc_macro(mglc_lbm *h) { MGLC_TRY(use(h)); return do_macro(h); }
@@ -469,19 +497,19 @@ extern "C" int mglc_check(mglc_lbm *h, double *errorU) {
     return MGLC_OK;
 }
 
-// nsteps iterations of: collision, exchange, streaming, bounceback, macro  (L3/main.f90:85-97)
+// nsteps iterations of: collision, exchange, streaming, bounceback, macro  (L3/main.f90:85-97).
+// Rotated by half a step: [collision once] then nsteps x (exchange -> fused pull+walls+macro+collide).
+// The handle stays rotated afterwards, so back-to-back calls pay neither prologue nor epilogue; any
+// entry point that needs the reference's state calls canonicalise() first.
 static int step_impl(mglc_lbm *h, int nsteps) {
     if (nsteps < 0) { set_error("mglc_lbm_step: nsteps=%d", nsteps); return MGLC_E_INVALID; }
     if (nsteps == 0) return MGLC_OK;
-    MGLC_TRY(do_collision(h));                       // step 1's collision()
-    for (int it = 1; it < nsteps; ++it) {
-        MGLC_TRY(do_exchange_nccl(h));               // step it: exchange, then walls into the halo
-        MGLC_TRY(do_wallfill(h));
+    if (!h->rotated) MGLC_TRY(do_collision(h));      // the first step's collision()
+    for (int it = 0; it < nsteps; ++it) {
+        MGLC_TRY(do_exchange_nccl(h));               // exchange of step it
         MGLC_TRY(do_fused(h));                       // streaming+bounceback+macro of step it, collision of it+1
     }
-    MGLC_TRY(do_exchange_nccl(h));
-    MGLC_TRY(do_wallfill(h));
-    MGLC_TRY(do_stream_macro(h));                    // streaming+bounceback+macro of the last step
+    h->rotated = 1;
     return MGLC_OK;
 }
 extern "C" int mglc_lbm_step(mglc_lbm *h, int nsteps) {
@@ -615,7 +643,11 @@ static int group_exchange(mglc_group *g) {
 
 extern "C" int mglc_group_initial(mglc_group *g) { GROUP_EACH(g, do_initial); }
 extern "C" int mglc_group_collision(mglc_group *g) { GROUP_EACH(g, do_collision); }
-extern "C" int mglc_group_exchange(mglc_group *g) { if (!g) return MGLC_E_INVALID; return group_exchange(g); }
+extern "C" int mglc_group_exchange(mglc_group *g) {
+    if (!g) return MGLC_E_INVALID;
+    FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(canonicalise(h)); }
+    return group_exchange(g);
+}
 extern "C" int mglc_group_streaming(mglc_group *g) { GROUP_EACH(g, do_streaming); }
 extern "C" int mglc_group_bounceback(mglc_group *g) { GROUP_EACH(g, do_bounceback); }
 extern "C" int mglc_group_macro(mglc_group *g) { GROUP_EACH(g, do_macro); }
@@ -638,16 +670,12 @@ extern "C" int mglc_group_check(mglc_group *g, double *errorU) {
 static int group_step_impl(mglc_group *g, int nsteps) {
     if (nsteps < 0) return MGLC_E_INVALID;
     if (nsteps == 0) return MGLC_OK;
-    FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_collision(h)); }
-    for (int it = 1; it <= nsteps; ++it) {
+    FOR_RANKS(g, h) { MGLC_TRY(use(h)); if (!h->rotated) MGLC_TRY(do_collision(h)); }
+    for (int it = 0; it < nsteps; ++it) {
         MGLC_TRY(group_exchange(g));
-        FOR_RANKS(g, h) {
-            MGLC_TRY(use(h));
-            MGLC_TRY(do_wallfill(h));
-            if (it < nsteps) MGLC_TRY(do_fused(h));
-            else MGLC_TRY(do_stream_macro(h));
-        }
+        FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_fused(h)); }
     }
+    FOR_RANKS(g, h) h->rotated = 1;
     return MGLC_OK;
 }
 extern "C" int mglc_group_step(mglc_group *g, int nsteps) {

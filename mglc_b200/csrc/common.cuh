@@ -75,8 +75,8 @@ void set_error(const char *fmt, ...);
     int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout,             \
                      double *rho_field, const int box[6], cudaStream_t s);                           \
     /* stream + macro (epilogue of a fused run): Fin (post-collision) -> F (pre-collision) + fields */\
-    int launch_stream_macro(const Geom &g, const double *Fin, double *F, double *rho, double *u,     \
-                            double *v, double *w, cudaStream_t s);
+    int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F,         \
+                            double *rho, double *u, double *v, double *w, cudaStream_t s);
 
 namespace strict { MGLC_DECLARE_LBM_LAUNCHERS }
 namespace fast { MGLC_DECLARE_LBM_LAUNCHERS }
@@ -88,8 +88,6 @@ int launch_streaming(const Geom &g, const double *Fpost, double *F, cudaStream_t
 int launch_bounceback(const Geom &g, const LbmParams &p, const double *Fpost, const double *rho, double *F,
                       cudaStream_t s);
 int launch_macro(const Geom &g, const double *F, double *rho, double *u, double *v, double *w, cudaStream_t s);
-// halo of Fpost at physical walls <- bounce-back values, so that a plain pull reproduces streaming+bounceback
-int launch_wallfill(const Geom &g, const LbmParams &p, double *Fpost, const double *rho, cudaStream_t s);
 // check(): partial[0] += sum (du^2+dv^2), partial[1] += sum(u^2+v^2+w^2); then up<-u, vp<-v, wp<-w
 int launch_check(const Geom &g, const double *u, const double *v, const double *w, double *up, double *vp,
                  double *wp, double *partial2, cudaStream_t s);

@@ -1,6 +1,5 @@
 // exact_kernels.cu -- kernels whose results are bit-defined (copies, order-preserving sums, IEEE
-// divisions): initial(), streaming(), bounceback(), macro(), the wall-halo fill used by the fused path,
-// check() reductions, halo pack/unpack and the AoS<->SoA transposes of upload/download.
+// divisions): initial(), streaming(), bounceback(), macro(), check() reductions, halo pack/unpack and the AoS<->SoA transposes of upload/download.
 // Built with -fmad=false so nothing is contracted; see lbm_kernels.inl for the collision kernels.
 #include "common.cuh"
 #include "d3q19_mrt.inl"
@@ -95,42 +94,6 @@ int launch_bounceback(const Geom &g, const LbmParams &p, const double *Fpost, co
                       cudaStream_t s) {
     const int big = max(max(g.nx * g.ny, g.nx * g.nz), g.ny * g.nz);
     k_bounceback<<<dim3((big + 127) / 128, 6), 128, 0, s>>>(g, p, Fpost, rho, F);
-    return 1;
-}
-
-// ---- wall-halo fill: the unified boundary rule applied to the halo ------------
-// For every halo cell h that lies outside the global box and every population a that would be pulled
-// from h by an interior cell x = h + e_a:  Fpost_a(h) := Fpost_opp(a)(x)  [- lid term].  A plain pull from
-// the halo then yields exactly streaming() followed by bounceback().
-__global__ void k_wallfill(Geom g, LbmParams p, double *__restrict__ Fpost, const double *__restrict__ rho) {
-    const int face = blockIdx.y;
-    if (!g.wall[face]) return;
-    const int axis = face >> 1;
-    const int n1 = ((axis == 0) ? g.ny : g.nx) + 2, n2 = ((axis == 2) ? g.ny : g.nz) + 2;   // incl. rims
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n1 * n2) return;
-    const int t1 = t % n1, t2 = t / n1;
-    const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz);
-    const int fix = (face & 1) ? 0 : nfix + 1;
-    const int i = (axis == 0) ? fix : t1;
-    const int j = (axis == 1) ? fix : (axis == 0 ? t1 : t2);
-    const int k = (axis == 2) ? fix : t2;
-    const long long ch = g.idx(0, i, j, k);
-    const bool above_lid = g.lid && k == g.nz + 1;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int a = c_face_pops[face ^ 1][q];            // populations entering through this wall
-        const int xi = i + c_ex[a], xj = j + c_ey[a], xk = k + c_ez[a];
-        if (xi < 1 || xi > g.nx || xj < 1 || xj > g.ny || xk < 1 || xk > g.nz) continue;
-        double val = Fpost[c_opp[a] * g.sq + g.idx(0, xi, xj, xk)];
-        if (above_lid && (a == 13 || a == 14)) val = lid_term(val, rho[g.cell(xi, xj, xk)], p.U0, a);
-        Fpost[a * g.sq + ch] = val;
-    }
-}
-
-int launch_wallfill(const Geom &g, const LbmParams &p, double *Fpost, const double *rho, cudaStream_t s) {
-    const int big = max(max((g.nx + 2) * (g.ny + 2), (g.nx + 2) * (g.nz + 2)), (g.ny + 2) * (g.nz + 2));
-    k_wallfill<<<dim3((big + 127) / 128, 6), 128, 0, s>>>(g, p, Fpost, rho);
     return 1;
 }
 

@@ -6,7 +6,7 @@
 // L1/L2 lines), every store is 128-byte aligned.
 //
 // The fused kernel is the reference loop body rotated by half a step: it performs streaming()
-// (L3/streaming.f90) + bounceback() (L3/bounce_back.f90, pre-applied to the halo by wallfill) +
+// (L3/streaming.f90) + bounceback() (L3/bounce_back.f90, folded into the pull, see d3q19_walls) +
 // macro() (L3/macro.f90) of step n and collision() (L3/collision.f90) of step n+1, so a step costs
 // one read and one write of the 19 populations: 304 B/cell.
 #include "common.cuh"
@@ -15,15 +15,39 @@
 namespace mglc {
 namespace MGLC_NS {
 
-// pull the 19 populations that arrive at cell c (c = linear index of the cell in population 0)
-#define MGLC_PULL(a, dx, dy, dz) f[a] = __ldg(Fin + (a) * sq + (c - (dz) * sz - (dy) * sy - (dx)))
-#define MGLC_PULL_ALL()                                                                        \
-    MGLC_PULL(0, 0, 0, 0);                                                                     \
-    MGLC_PULL(1, 1, 0, 0);   MGLC_PULL(2, -1, 0, 0);  MGLC_PULL(3, 0, 1, 0);   MGLC_PULL(4, 0, -1, 0);  \
-    MGLC_PULL(5, 0, 0, 1);   MGLC_PULL(6, 0, 0, -1);                                           \
-    MGLC_PULL(7, 1, 1, 0);   MGLC_PULL(8, -1, 1, 0);  MGLC_PULL(9, 1, -1, 0);  MGLC_PULL(10, -1, -1, 0); \
-    MGLC_PULL(11, 1, 0, 1);  MGLC_PULL(12, -1, 0, 1); MGLC_PULL(13, 1, 0, -1); MGLC_PULL(14, -1, 0, -1); \
-    MGLC_PULL(15, 0, 1, 1);  MGLC_PULL(16, 0, -1, 1); MGLC_PULL(17, 0, 1, -1); MGLC_PULL(18, 0, -1, -1)
+// Pull the 19 populations that arrive at cell c (c = linear index of the cell in population 0), with
+// bounceback() (L3/bounce_back.f90:6-83) folded in as the unified boundary rule:
+// a population whose upstream cell x - e_a lies outside the GLOBAL box takes the opposite
+// post-collision population of the cell itself, f_a(x) = f_post_opp(a)(x); through the moving lid,
+// populations 14 / 13 also get - rho/6*(+U0) / - rho/6*(-U0) with rho left by the previous macro()
+// (:77-78).  The value is the same whichever wall "wins", and z-last precedence is kept because the lid
+// term is keyed on the cell.  The wall test only selects the load ADDRESS (no divergent branch, no
+// extra live registers); wall halos are never read.
+struct WallFlags { bool xp, xm, yp, ym, zp, zm; };
+__device__ __forceinline__ WallFlags wall_flags(const Geom &g, int i, int j, int k) {
+    return WallFlags{g.wall[0] && i == g.nx, g.wall[1] && i == 1, g.wall[2] && j == g.ny,
+                     g.wall[3] && j == 1,    g.wall[4] && k == g.nz, g.wall[5] && k == 1};
+}
+#define MGLC_PULL(a, o, dx, dy, dz)                                                                         \
+    {                                                                                                       \
+        const bool wall_ = ((dx) == 1 && wf.xm) || ((dx) == -1 && wf.xp) || ((dy) == 1 && wf.ym) ||        \
+                           ((dy) == -1 && wf.yp) || ((dz) == 1 && wf.zm) || ((dz) == -1 && wf.zp);         \
+        f[a] = __ldg(Fin + (wall_ ? (o) * sq + c : (a) * sq + (c - (dz) * sz - (dy) * sy - (dx))));        \
+    }
+#define MGLC_PULL_ALL()                                                                                     \
+    f[0] = __ldg(Fin + c);                                                                                  \
+    MGLC_PULL(1, 2, 1, 0, 0)    MGLC_PULL(2, 1, -1, 0, 0)   MGLC_PULL(3, 4, 0, 1, 0)    MGLC_PULL(4, 3, 0, -1, 0)   \
+    MGLC_PULL(5, 6, 0, 0, 1)    MGLC_PULL(6, 5, 0, 0, -1)                                                   \
+    MGLC_PULL(7, 10, 1, 1, 0)   MGLC_PULL(8, 9, -1, 1, 0)   MGLC_PULL(9, 8, 1, -1, 0)   MGLC_PULL(10, 7, -1, -1, 0) \
+    MGLC_PULL(11, 14, 1, 0, 1)  MGLC_PULL(12, 13, -1, 0, 1) MGLC_PULL(13, 12, 1, 0, -1) MGLC_PULL(14, 11, -1, 0, -1) \
+    MGLC_PULL(15, 18, 0, 1, 1)  MGLC_PULL(16, 17, 0, -1, 1) MGLC_PULL(17, 16, 0, 1, -1) MGLC_PULL(18, 15, 0, -1, -1)
+// moving lid; explicit _rn intrinsics so the fast build cannot contract this into an FMA
+#define MGLC_LID(rho_field)                                                       \
+    if (wf.zp) {                                                                  \
+        const double r6 = __ddiv_rn((rho_field)[g.cell(i, j, k)], 6.0);          \
+        f[14] = __dsub_rn(f[14], __dmul_rn(r6, p.U0));                            \
+        f[13] = __dsub_rn(f[13], __dmul_rn(r6, -p.U0));                           \
+    }
 
 // collision(): F (interior) + rho,u,v,w -> Fpost (interior)
 __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const double *__restrict__ F,
@@ -44,7 +68,7 @@ __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const do
     for (int a = 0; a < 19; ++a) Fpost[a * sq + c] = fp[a];
 }
 
-// fused: pull (stream + wall bounce-back through the pre-filled halo) -> macro -> collide -> store
+// fused: pull (streaming) -> wall bounce-back -> macro -> collide -> store
 __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const double *__restrict__ Fin,
                                                   double *__restrict__ Fout, double *__restrict__ rho_field,
                                                   int i0, int i1, int j0, int k0) {
@@ -53,8 +77,10 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     if (i > i1) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k);
+    const WallFlags wf = wall_flags(g, i, j, k);
     double f[19], fp[19];
     MGLC_PULL_ALL();
+    MGLC_LID(rho_field);
     double rho, u, v, w;
     d3q19_macro(f, rho, u, v, w);
     d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
@@ -66,7 +92,7 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
 }
 
 // epilogue of a fused run: pull -> f (pre-collision, as the reference leaves it) and macro fields
-__global__ void __launch_bounds__(128) k_stream_macro(Geom g, const double *__restrict__ Fin,
+__global__ void __launch_bounds__(128) k_stream_macro(Geom g, LbmParams p, const double *__restrict__ Fin,
                                                       double *__restrict__ F, double *__restrict__ rho_o,
                                                       double *__restrict__ u_o, double *__restrict__ v_o,
                                                       double *__restrict__ w_o) {
@@ -75,8 +101,10 @@ __global__ void __launch_bounds__(128) k_stream_macro(Geom g, const double *__re
     if (i > g.nx) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k);
+    const WallFlags wf = wall_flags(g, i, j, k);
     double f[19];
     MGLC_PULL_ALL();
+    MGLC_LID(rho_o);
 #pragma unroll
     for (int a = 0; a < 19; ++a) F[a * sq + c] = f[a];
     double rho, u, v, w;
@@ -101,9 +129,9 @@ int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *F
     return 1;
 }
 
-int launch_stream_macro(const Geom &g, const double *Fin, double *F, double *rho, double *u, double *v,
-                        double *w, cudaStream_t s) {
-    k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, Fin, F, rho, u, v, w);
+int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F, double *rho, double *u,
+                        double *v, double *w, cudaStream_t s) {
+    k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, Fin, F, rho, u, v, w);
     return 1;
 }
 
