@@ -175,6 +175,34 @@ int mglc_group_check(mglc_group *g, double *errorU);
 int mglc_group_step(mglc_group *g, int nsteps);
 int mglc_group_step_timed(mglc_group *g, int nsteps, float *ms);
 
+/* ================= Jacobi halo-exchange path (MPI/Laplace/fortran/jacobi2d_mpi.f90, "LAP") =================
+ * ndim = 2 is the reference's problem; ndim = 3 its six-neighbour extension (BASELINE.json config 2).
+ * Host arrays are the reference's: column-major A(0:nx+1, 0:ny+1 [, 0:nz+1]) with one ghost layer
+ * (LAP:78-81).  A handle owns either ONE subdomain (one process per GPU, halos over NCCL) or all P
+ * subdomains of the process grid (mglc_jacobi_create_local: halos by device-to-device copies); `r` below
+ * is the index among the subdomains the handle owns (0 for a one-subdomain handle). */
+typedef struct mglc_jacobi mglc_jacobi;
+/* MPI_Dims_create(nranks, ndim, dims) with dims = 0 -- LAP:47 (ndim = 2) / L3/main.f90:24 (ndim = 3) */
+int mglc_dims_create_nd(int nranks, int ndim, int dims[3]);
+/* MPI_Cart_create + decompose_1d + MPI_Cart_shift + allocate -- LAP:47-81 */
+int mglc_jacobi_create(mglc_jacobi **h, int ndim, const int gn[3], const int dims_or_zero[3], int nranks,
+                       int rank, int device, mglc_comm *comm_or_null);
+int mglc_jacobi_create_local(mglc_jacobi **h, int ndim, const int gn[3], const int dims_or_zero[3],
+                             int nranks, const int *devices_or_null);
+int mglc_jacobi_destroy(mglc_jacobi *h);                                  /* deallocate -- LAP:121-124 */
+int mglc_jacobi_nlocal(mglc_jacobi *h, int *n);
+int mglc_jacobi_info(mglc_jacobi *h, int r, int dims[3], int ln[3], int start[3], int coords[3], int nbr[6]);
+int mglc_jacobi_init(mglc_jacobi *h);                                     /* init() -- LAP:144-166 */
+int mglc_jacobi_upload(mglc_jacobi *h, int r, const double *A, const double *A_new, const double *f); /* NULL = keep */
+int mglc_jacobi_download(mglc_jacobi *h, int r, double *A, double *A_new);
+int mglc_jacobi_exchange(mglc_jacobi *h);      /* exchange_message(A)              LAP:223-254 */
+int mglc_jacobi_sweep(mglc_jacobi *h);         /* jacobi(A, A_new) + role swap     LAP:170-182, 97-103 */
+int mglc_jacobi_step(mglc_jacobi *h, int nits);            /* nits x (exchange, sweep)  LAP:94-103 */
+int mglc_jacobi_step_timed(mglc_jacobi *h, int nits, float *ms);
+int mglc_jacobi_check_diff(mglc_jacobi *h, double *error_max);   /* check_diff + Allreduce(MAX)  LAP:105-107,185-204 */
+int mglc_jacobi_launch_count(mglc_jacobi *h, long long *n);
+int mglc_jacobi_sync(mglc_jacobi *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,23 @@ SIGNATURES = {
     "mglc_group_check": (C.c_int, [_vp, _dp]),
     "mglc_group_step": (C.c_int, [_vp, C.c_int]),
     "mglc_group_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    # Jacobi path
+    "mglc_dims_create_nd": (C.c_int, [C.c_int, C.c_int, _ip]),
+    "mglc_jacobi_create": (C.c_int, [_vpp, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, _vp]),
+    "mglc_jacobi_create_local": (C.c_int, [_vpp, C.c_int, _ip, _ip, C.c_int, _ip]),
+    "mglc_jacobi_destroy": (C.c_int, [_vp]),
+    "mglc_jacobi_nlocal": (C.c_int, [_vp, _ip]),
+    "mglc_jacobi_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "mglc_jacobi_init": (C.c_int, [_vp]),
+    "mglc_jacobi_upload": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "mglc_jacobi_download": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "mglc_jacobi_exchange": (C.c_int, [_vp]),
+    "mglc_jacobi_sweep": (C.c_int, [_vp]),
+    "mglc_jacobi_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_jacobi_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_jacobi_check_diff": (C.c_int, [_vp, _dp]),
+    "mglc_jacobi_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_jacobi_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

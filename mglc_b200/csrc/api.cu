@@ -3,42 +3,15 @@
 // halo exchange over NCCL (one process per GPU) or device-to-device copies (P subdomains in one
 // process), and timing / launch accounting.  There is no CPU path: without a device every entry
 // point here fails with MGLC_E_NOGPU.
-#include <nccl.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "common.cuh"
+#include "halo.cuh"
 
 using namespace mglc;
-
-#define MGLC_NCCL(call)                                                                        \
-    do {                                                                                       \
-        ncclResult_t r_ = (call);                                                              \
-        if (r_ != ncclSuccess) {                                                               \
-            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_));   \
-            return MGLC_E_NCCL;                                                                \
-        }                                                                                      \
-    } while (0)
-#define MGLC_TRY(call)            \
-    do {                          \
-        int rc_ = (call);         \
-        if (rc_ != MGLC_OK) return rc_; \
-    } while (0)
-
-struct Msg {
-    int dir, send_to, recv_from;
-    long long send_count, recv_count;
-    double *sbuf, *rbuf;
-};
-
-struct mglc_comm {
-    ncclComm_t nccl;
-    int nranks, rank, device;
-};
 
 struct mglc_lbm {
     mglc_lbm_desc d;
@@ -52,6 +25,12 @@ struct mglc_lbm {
     // plane of rho is current.  canonicalise() turns this back into the reference's state (f, rho,u,v,w).
     int rotated;
     double *rho, *u, *v, *w, *up, *vp, *wp;
+    // lid plane (k = nz) of rho for the moving-lid term, L3/bounce_back.f90:77-78.  A fused launch reads
+    // the plane the previous macro() left (lid_next) and writes this step's into the other side buffer,
+    // so the plane it read (lid_last_in) stays intact for canonicalise().  In the reference's state
+    // lid_next is simply the top plane of the rho field.
+    double *rho_lid[2];
+    const double *lid_next, *lid_last_in;
     double *scratch;         // check() partial sums
     cudaStream_t s, s_comm;
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1, ev_shell, ev_halo;
@@ -78,17 +57,6 @@ struct mglc_group {
 };
 
 // ---------------------------------------------------------------------------------------------------
-static int require_gpu() {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        (void)cudaGetLastError();
-        set_error("no CUDA device available: libmglc.so has no CPU fallback (%s)",
-                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-        return MGLC_E_NOGPU;
-    }
-    return MGLC_OK;
-}
 static int use(mglc_lbm *h) {
     if (!h) { set_error("null handle"); return MGLC_E_INVALID; }
     MGLC_CUDA(cudaSetDevice(h->d.device));
@@ -161,7 +129,7 @@ extern "C" int mglc_lbm_destroy(mglc_lbm *h) {
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
-    double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage};
+    double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage, h->rho_lid[0], h->rho_lid[1]};
     for (double *p : fields) cudaFree(p);
     for (int m = 0; m < h->nmsgs; ++m) { cudaFree(h->msgs[m].sbuf); cudaFree(h->msgs[m].rbuf); }
     cudaEvent_t evs[] = {h->ev_packed, h->ev_copied, h->ev_t0, h->ev_t1, h->ev_shell, h->ev_halo};
@@ -211,6 +179,9 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
         if (cudaMemsetAsync(*f, 0, (size_t)n * sizeof(double), h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
     }
     if ((rc = dmalloc(h, &h->scratch, check_scratch_doubles()))) return fail(rc);
+    for (int b = 0; b < 2; ++b)
+        if ((rc = dmalloc(h, &h->rho_lid[b], (long long)h->g.nx * h->g.ny))) return fail(rc);
+    h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
     // halo plan + buffers
     mglc_halo_msg plan[18];
     mglc_halo_plan(d, plan, &h->nmsgs);
@@ -339,6 +310,7 @@ extern "C" int mglc_lbm_download_fpost(mglc_lbm *h, double *f_post) {
 // ---- single-subdomain building blocks ---------------------------------------------------------------------
 static int do_initial(mglc_lbm *h) {
     h->rotated = 0;
+    h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
     h->launches += launch_initial(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, h->s);
     if (h->up) {
         const size_t b = (size_t)ncell(h) * sizeof(double);
@@ -423,8 +395,12 @@ static int do_fused(mglc_lbm *h) {
         if (h->prof_used == PROF_PAIRS) MGLC_TRY(prof_flush(h));
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used], h->s));
     }
-    h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, Fpost_(h), F_(h), h->rho, box, h->s)
-                              : fast::launch_fused(h->g, h->p, Fpost_(h), F_(h), h->rho, box, h->s);
+    const double *lid_in = h->lid_next;
+    double *lid_out = (lid_in == h->rho_lid[0]) ? h->rho_lid[1] : h->rho_lid[0];
+    h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s)
+                              : fast::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s);
+    h->lid_last_in = lid_in;
+    h->lid_next = lid_out;
     if (h->profiling) {
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used + 1], h->s));
         h->prof_used += 1;
@@ -433,8 +409,9 @@ static int do_fused(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_stream_macro(mglc_lbm *h) {
-    h->launches += strict_(h) ? strict::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s)
-                              : fast::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->rho, h->u, h->v, h->w, h->s);
+    h->launches += strict_(h) ? strict::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->lid_last_in, h->rho, h->u, h->v, h->w, h->s)
+                              : fast::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->lid_last_in, h->rho, h->u, h->v, h->w, h->s);
+    h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
     return MGLC_OK;
 }
 // Leave the rotated state: the last step's f_post (with halos) is still intact in buf[cur]; pull it into

@@ -73,10 +73,11 @@ void set_error(const char *fmt, ...);
     /* stream + macro + collide: pull from Fin (halo'd, post-collision) -> post-collision Fout;      \
        box = [i0,i1]x[j0,j1]x[k0,k1] inclusive, 1-based interior cells */                            \
     int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout,             \
-                     double *rho_field, const int box[6], cudaStream_t s);                           \
+                     const double *rho_lid_in, double *rho_lid_out, const int box[6], cudaStream_t s); \
     /* stream + macro (epilogue of a fused run): Fin (post-collision) -> F (pre-collision) + fields */\
     int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F,         \
-                            double *rho, double *u, double *v, double *w, cudaStream_t s);
+                            const double *rho_lid_in, double *rho, double *u, double *v, double *w,  \
+                            cudaStream_t s);
 
 namespace strict { MGLC_DECLARE_LBM_LAUNCHERS }
 namespace fast { MGLC_DECLARE_LBM_LAUNCHERS }

@@ -42,9 +42,10 @@ __device__ __forceinline__ WallFlags wall_flags(const Geom &g, int i, int j, int
     MGLC_PULL(11, 14, 1, 0, 1)  MGLC_PULL(12, 13, -1, 0, 1) MGLC_PULL(13, 12, 1, 0, -1) MGLC_PULL(14, 11, -1, 0, -1) \
     MGLC_PULL(15, 18, 0, 1, 1)  MGLC_PULL(16, 17, 0, -1, 1) MGLC_PULL(17, 16, 0, 1, -1) MGLC_PULL(18, 15, 0, -1, -1)
 // moving lid; explicit _rn intrinsics so the fast build cannot contract this into an FMA
-#define MGLC_LID(rho_field)                                                       \
+// rho_lid: the lid plane (k = nz) of rho as the previous macro() left it, indexed (i-1) + nx*(j-1)
+#define MGLC_LID(rho_lid)                                                         \
     if (wf.zp) {                                                                  \
-        const double r6 = __ddiv_rn((rho_field)[g.cell(i, j, k)], 6.0);          \
+        const double r6 = __ddiv_rn((rho_lid)[(i - 1) + (long long)g.nx * (j - 1)], 6.0); \
         f[14] = __dsub_rn(f[14], __dmul_rn(r6, p.U0));                            \
         f[13] = __dsub_rn(f[13], __dmul_rn(r6, -p.U0));                           \
     }
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const do
 
 // fused: pull (streaming) -> wall bounce-back -> macro -> collide -> store
 __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const double *__restrict__ Fin,
-                                                  double *__restrict__ Fout, double *__restrict__ rho_field,
-                                                  int i0, int i1, int j0, int k0) {
+                                                  double *__restrict__ Fout, const double *__restrict__ rho_lid_in,
+                                                  double *__restrict__ rho_lid_out, int i0, int i1, int j0, int k0) {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
     if (i > i1) return;
@@ -80,22 +81,23 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     const WallFlags wf = wall_flags(g, i, j, k);
     double f[19], fp[19];
     MGLC_PULL_ALL();
-    MGLC_LID(rho_field);
+    MGLC_LID(rho_lid_in);
     double rho, u, v, w;
     d3q19_macro(f, rho, u, v, w);
     d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
     // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
-    // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro())
-    if (g.lid && k == g.nz) rho_field[g.cell(i, j, k)] = rho;
+    // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro()); it goes to the other
+    // side buffer so that the plane this launch read stays intact for canonicalise()
+    if (g.lid && k == g.nz) rho_lid_out[(i - 1) + (long long)g.nx * (j - 1)] = rho;
 }
 
 // epilogue of a fused run: pull -> f (pre-collision, as the reference leaves it) and macro fields
 __global__ void __launch_bounds__(128) k_stream_macro(Geom g, LbmParams p, const double *__restrict__ Fin,
-                                                      double *__restrict__ F, double *__restrict__ rho_o,
-                                                      double *__restrict__ u_o, double *__restrict__ v_o,
-                                                      double *__restrict__ w_o) {
+                                                      double *__restrict__ F, const double *rho_lid_in,
+                                                      double *rho_o, double *__restrict__ u_o,
+                                                      double *__restrict__ v_o, double *__restrict__ w_o) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128) k_stream_macro(Geom g, LbmParams p, const
     const WallFlags wf = wall_flags(g, i, j, k);
     double f[19];
     MGLC_PULL_ALL();
-    MGLC_LID(rho_o);
+    MGLC_LID(rho_lid_in);     // may alias the top plane of rho_o: read here, written below by the same thread
 #pragma unroll
     for (int a = 0; a < 19; ++a) F[a * sq + c] = f[a];
     double rho, u, v, w;
@@ -121,17 +123,17 @@ int launch_collision(const Geom &g, const LbmParams &p, const double *F, const d
     return 1;
 }
 
-int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout, double *rho_field,
-                 const int box[6], cudaStream_t s) {
+int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout, const double *rho_lid_in,
+                 double *rho_lid_out, const int box[6], cudaStream_t s) {
     const int nxs = box[1] - box[0] + 1, nys = box[3] - box[2] + 1, nzs = box[5] - box[4] + 1;
     if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
-    k_fused<<<grid_for(nxs, nys, nzs, 128), 128, 0, s>>>(g, p, Fin, Fout, rho_field, box[0], box[1], box[2], box[4]);
+    k_fused<<<grid_for(nxs, nys, nzs, 128), 128, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[4]);
     return 1;
 }
 
-int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F, double *rho, double *u,
-                        double *v, double *w, cudaStream_t s) {
-    k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, Fin, F, rho, u, v, w);
+int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F, const double *rho_lid_in,
+                        double *rho, double *u, double *v, double *w, cudaStream_t s) {
+    k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, Fin, F, rho_lid_in, rho, u, v, w);
     return 1;
 }
 

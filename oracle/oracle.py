@@ -171,3 +171,89 @@ def feq(rho, u, v, w):
         un = u * EX[a] + v * EY[a] + w * EZ[a]
         out[a] = rho * W[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Jacobi (oracle/jacobi.c)
+def _jac_lib():
+    L = lib()
+    if not getattr(L, "_jac_ready", False):
+        L.jac_world_create.restype = C.c_void_p
+        L.jac_world_create.argtypes = [C.c_int] * 5 + [_ip]
+        L.jac_world_destroy.argtypes = [C.c_void_p]
+        L.jac_ptr.restype = _dp
+        L.jac_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.jac_rank_info.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.jac_world_dims.argtypes = [C.c_void_p, _ip]
+        L.jac_dims_create.argtypes = [C.c_int, C.c_int, _ip]
+        for name in ("jac_init", "jac_exchange", "jac_sweep"):
+            getattr(L, name).argtypes = [C.c_void_p]
+            getattr(L, name).restype = None
+        L.jac_step.argtypes = [C.c_void_p, C.c_int]
+        L.jac_step.restype = None
+        L.jac_check_diff.argtypes = [C.c_void_p]
+        L.jac_check_diff.restype = C.c_double
+        L._jac_ready = True
+    return L
+
+
+class JacobiWorld:
+    """All P emulated ranks of the Jacobi driver (LAP) in one process; ndim = len(total)."""
+
+    def __init__(self, total, nprocs=1, dims=None):
+        self._lib = _jac_lib()
+        self.ndim = len(total)
+        self.total = tuple(total)
+        t = tuple(total) + (1,) * (3 - self.ndim)
+        d = (C.c_int * 3)(*((tuple(dims) + (1,))[:3] if dims else (0, 0, 0)))
+        self._h = self._lib.jac_world_create(self.ndim, t[0], t[1], t[2], nprocs, d)
+        self.nprocs = nprocs
+        dd = (C.c_int * 3)()
+        self._lib.jac_world_dims(self._h, dd)
+        self.dims = tuple(dd)[:self.ndim]
+        self.info = []
+        for r in range(nprocs):
+            o = (C.c_int * 15)()
+            self._lib.jac_rank_info(self._h, r, o)
+            self.info.append(dict(n=tuple(o[0:3])[:self.ndim], coords=tuple(o[3:6])[:self.ndim],
+                                  start=tuple(o[6:9])[:self.ndim], nbr=tuple(o[9:15])[:2 * self.ndim]))
+
+    def close(self):
+        if self._h:
+            self._lib.jac_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def array(self, r, which="A"):
+        """numpy view (no copy) of rank r's A / A_new / f / A_p; re-fetch after sweeps (the roles swap)."""
+        shape = tuple(n + 2 for n in self.info[r]["n"])
+        p = self._lib.jac_ptr(self._h, r, {"A": 0, "A_new": 1, "f": 2, "A_p": 3}[which])
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape, order="F")
+
+    def init(self):
+        self._lib.jac_init(self._h)
+
+    def exchange_message(self):
+        self._lib.jac_exchange(self._h)
+
+    def jacobi(self):
+        self._lib.jac_sweep(self._h)
+
+    def step(self, nits=1):
+        self._lib.jac_step(self._h, nits)
+
+    def check_diff(self):
+        return self._lib.jac_check_diff(self._h)
+
+    def gather(self):
+        out = np.full(self.total, np.nan, order="F")
+        for r, inf in enumerate(self.info):
+            sl = tuple(slice(s, s + n) for s, n in zip(inf["start"], inf["n"]))
+            inner = tuple(slice(1, n + 1) for n in inf["n"])
+            out[sl] = self.array(r)[inner]
+        return out
