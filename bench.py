@@ -59,12 +59,16 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per fused launch from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+def ncu_traffic(cells_per_launch):
+    """dram bytes per fused launch from the committed ncu capture of the same launch size
+    (profiles/ncu_traffic.json), or None when no capture of that size exists."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for cap in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["captures"]:
+            if cap["cells_per_launch"] == cells_per_launch:
+                return cap
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -292,7 +296,7 @@ def main():
     peak, peak_src = hbm_peak()
     avg_ms = fms.value / max(1, fl.value)
     achieved = BYTES_PER_CELL * cells_local / (avg_ms * 1e-3) / 1e9
-    tr = ncu_traffic()
+    tr = ncu_traffic(cells_local)
     roofline = {"bound": "hbm", "kernel": "mglc::fast::k_fused" if args.arith == "fast" else "mglc::strict::k_fused",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
