@@ -257,3 +257,123 @@ class JacobiWorld:
             inner = tuple(slice(1, n + 1) for n in inf["n"])
             out[sl] = self.array(r)[inner]
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Thermal double-distribution cavity (oracle/thermal3d.c)
+class ThParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("Rayleigh", "Prandtl", "Mach", "Ekman", "Thot", "Tcold", "Tref", "tauf",
+                                          "viscosity", "diffusivity", "omegaRatating", "paraA", "gBeta1", "gBeta",
+                                          "Snu", "Sq", "Qd", "Qnu")]
+
+
+TH_ADIABATIC, TH_CONST_HOT, TH_CONST_COLD = 0, 1, 2
+TH_FIELDS = {"f": 0, "f_post": 1, "g": 2, "g_post": 3, "rho": 4, "u": 5, "v": 6, "w": 7, "T": 8, "Fx": 9, "Fy": 10,
+             "Fz": 11, "up": 12, "vp": 13, "wp": 14, "Tp": 15}
+
+
+def _th_lib():
+    L = lib()
+    if not getattr(L, "_th_ready", False):
+        L.th_world_create.restype = C.c_void_p
+        L.th_world_create.argtypes = [C.c_int] * 4 + [_ip, _ip] + [C.c_double] * 4
+        L.th_world_destroy.argtypes = [C.c_void_p]
+        L.th_rank_ptr.restype = _dp
+        L.th_rank_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.th_rank_info.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.th_world_info.argtypes = [C.c_void_p, _ip, C.POINTER(ThParams), _ip]
+        L.th_make_params.argtypes = [C.c_int] + [C.c_double] * 7 + [C.POINTER(ThParams)]
+        for name in ("th_initial", "th_collision", "th_exchange_f", "th_streaming", "th_bounceback", "th_collisionT",
+                     "th_exchange_g", "th_streamingT", "th_bouncebackT", "th_macro", "th_macroT"):
+            getattr(L, name).argtypes = [C.c_void_p]
+            getattr(L, name).restype = None
+        L.th_step.argtypes = [C.c_void_p, C.c_int]
+        L.th_step.restype = None
+        L.th_check.argtypes = [C.c_void_p, _dp, _dp]
+        L.th_feq_cell.argtypes = [C.c_double] * 4 + [_dp]
+        L.th_geq_cell.argtypes = [C.c_double] * 5 + [_dp]
+        L.th_collide_cell.argtypes = [_dp] + [C.c_double] * 5 + [C.POINTER(ThParams), _dp, _dp]
+        L.th_collideT_cell.argtypes = [_dp] + [C.c_double] * 4 + [C.POINTER(ThParams), _dp]
+        L.th_macro_cell.argtypes = [_dp] + [C.c_double] * 3 + [_dp]
+        L._th_ready = True
+    return L
+
+
+def th_params(total_nz=51, Rayleigh=1e6, Prandtl=0.71, Mach=0.1, Ekman=0.001, Thot=1.0, Tcold=0.0, Tref=0.0):
+    p = ThParams()
+    _th_lib().th_make_params(total_nz, Rayleigh, Prandtl, Mach, Ekman, Thot, Tcold, Tref, C.byref(p))
+    return p
+
+
+class ThermalRank:
+    def __init__(self, world, r):
+        L = world._lib
+        info = (C.c_int * 27)()
+        L.th_rank_info(world._h, r, info)
+        self.n = tuple(info[0:3])
+        self.coords = tuple(info[3:6])
+        self.start = tuple(info[6:9])
+        nx, ny, nz = self.n
+        shapes = {"f": (19, nx, ny, nz), "f_post": (19, nx + 2, ny + 2, nz + 2), "g": (7, nx, ny, nz),
+                  "g_post": (7, nx + 2, ny + 2, nz + 2)}
+        for name, which in TH_FIELDS.items():
+            shape = shapes.get(name, (nx, ny, nz))
+            p = L.th_rank_ptr(world._h, r, which)
+            setattr(self, name, np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape, order="F"))
+
+
+class ThermalWorld:
+    """All P emulated ranks of the buoyancy-driven cavity (B3) in one process."""
+
+    def __init__(self, total, nprocs=1, dims=None, bcT=None, Rayleigh=1e6, Prandtl=0.71, Mach=0.1, Ekman=0.001):
+        self._lib = _th_lib()
+        d = (C.c_int * 3)(*(dims if dims else (0, 0, 0)))
+        bc = (C.c_int * 6)(*bcT) if bcT else None
+        self._h = self._lib.th_world_create(total[0], total[1], total[2], nprocs, d, bc, Rayleigh, Prandtl, Mach, Ekman)
+        self.total, self.nprocs = tuple(total), nprocs
+        self.ranks = [ThermalRank(self, r) for r in range(nprocs)]
+        dd, bb = (C.c_int * 3)(), (C.c_int * 6)()
+        self.p = ThParams()
+        self._lib.th_world_info(self._h, dd, C.byref(self.p), bb)
+        self.dims, self.bcT = tuple(dd), tuple(bb)
+
+    def close(self):
+        if self._h:
+            self.ranks = []
+            self._lib.th_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self):
+        eu, et = C.c_double(), C.c_double()
+        self._lib.th_check(self._h, C.byref(eu), C.byref(et))
+        return eu.value, et.value
+
+    def step(self, n=1):
+        self._lib.th_step(self._h, n)
+
+    def gather(self, name):
+        lead = {"f": (19,), "g": (7,)}.get(name, ())
+        out = np.empty(lead + self.total, order="F")
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            out[(slice(None),) * len(lead) + sl] = getattr(R, name)
+        return out
+
+    def scatter(self, name, glob):
+        lead = 1 if name in ("f", "g") else 0
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            getattr(R, name)[...] = glob[(slice(None),) * lead + sl]
+
+
+for _name, _sub in (("initial", "th_initial"), ("collision", "th_collision"), ("f_message_passing_sendrecv", "th_exchange_f"),
+                    ("streaming", "th_streaming"), ("bounceback", "th_bounceback"), ("collisionT", "th_collisionT"),
+                    ("g_message_passing_sendrecv", "th_exchange_g"), ("streamingT", "th_streamingT"),
+                    ("bouncebackT", "th_bouncebackT"), ("macro", "th_macro"), ("macroT", "th_macroT")):
+    setattr(ThermalWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))

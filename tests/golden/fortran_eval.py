@@ -1,0 +1,144 @@
+"""Machine evaluation of straight-line Fortran loop bodies of the REFERENCE (golden-vector generator only).
+
+The reference's per-cell arithmetic lives in Fortran sources that no compiler in this image can build.
+Its hot loops are plain assignment statements over fp64 scalars and small fixed arrays, which map one to
+one onto Python floats (IEEE binary64, same left-to-right evaluation of equal-precedence operators, no
+FMA contraction, no extended precision).  `translate()` turns the text of a loop body -- taken verbatim
+from the reference file at generation time, never stored in this repo -- into Python source; `run()` executes it
+on given inputs.  Used by tests/golden/make_golden_fortran.py to pin the CPU oracle to the reference's own
+source text.
+
+Supported subset: assignments, `do v = a, b` / `enddo` counted loops, `if (...) then` / `endif` blocks are NOT
+supported (none occur in the bodies we evaluate); `&` continuations, `!` comments and `!$omp` lines are
+dropped; `d0`-style exponents, dsqrt/dabs/dble intrinsics.  Array references are rewritten by a caller-
+supplied table: per-cell arrays f(alpha,i,j,k) -> f[alpha], fields rho(i,j,k) -> rho, locals m(3) -> m[3].
+"""
+import math
+import re
+
+
+def _logical_lines(text):
+    out, cur = [], ""
+    for raw in text.splitlines():
+        line = raw.split("!")[0].rstrip()          # comments (also drops !$omp directives)
+        if not line.strip():
+            continue
+        s = line.strip()
+        if s.startswith("&"):
+            s = s[1:].lstrip()
+        if s.endswith("&"):
+            cur += s[:-1] + " "
+            continue
+        out.append(cur + s)
+        cur = ""
+    if cur:
+        out.append(cur)
+    return out
+
+
+_NUM = re.compile(r"(?<![\w.])(\d+\.?\d*|\.\d+)[dD]([+-]?\d+)")
+
+
+def _numbers(s):
+    return _NUM.sub(lambda m: f"{m.group(1)}e{m.group(2)}" if m.group(2) not in ("0", "+0") else
+                    (m.group(1) if "." in m.group(1) else m.group(1) + ".0"), s)
+
+
+def _split_args(s):
+    """split 'a, b(c,d), e' at top-level commas"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def _rewrite_refs(s, cell_arrays, fields, local_arrays):
+    """rewrite NAME(args) for known names; innermost-first so nested references work"""
+    names = {**{n: "cell" for n in cell_arrays}, **{n: "field" for n in fields}, **{n: "local" for n in local_arrays}}
+    pat = re.compile(r"\b(" + "|".join(sorted(map(re.escape, names), key=len, reverse=True)) + r")\s*\(([^()]*)\)")
+    while True:
+        m = pat.search(s)
+        if not m:
+            return s
+        name, args = m.group(1), _split_args(m.group(2))
+        kind = names[name]
+        if kind == "cell":
+            rep = f"{name}__[{args[0]}]"            # f(alpha,i,j,k) -> f__[alpha]
+        elif kind == "field":
+            rep = f"{name}__"                       # rho(i,j,k) -> rho__
+        else:
+            rep = f"{name}__[{args[0]}]"
+        s = s[:m.start()] + rep + s[m.end():]
+
+
+def translate(text, cell_arrays=(), fields=(), local_arrays=()):
+    """Fortran loop-body text -> Python source.  All names are lower-cased; rewritten names get a '__'
+    suffix so they cannot collide with Python keywords or the intrinsics."""
+    py, indent = [], 0
+    for line in _logical_lines(text.lower()):
+        line = _numbers(line)
+        m = re.match(r"do\s+(\w+)\s*=\s*(.+?)\s*,\s*(.+)$", line)
+        if m:
+            py.append("    " * indent + f"for {m.group(1)} in range(int({m.group(2)}), int({m.group(3)}) + 1):")
+            indent += 1
+            continue
+        if re.match(r"end\s*do$", line):
+            indent -= 1
+            continue
+        line = _rewrite_refs(line, [a.lower() for a in cell_arrays], [a.lower() for a in fields],
+                             [a.lower() for a in local_arrays])
+        line = re.sub(r"\bdsqrt\b", "sqrt", line)
+        line = re.sub(r"\bdabs\b", "abs", line)
+        line = re.sub(r"\bdble\b", "float", line)
+        line = line.replace("**", " ** ")
+        py.append("    " * indent + line)
+    if indent != 0:
+        raise ValueError("unbalanced do/enddo in translated body")
+    return "\n".join(py)
+
+
+class _Arr(dict):
+    """Fortran-style small array with arbitrary lower bound."""
+
+    def __missing__(self, k):
+        raise KeyError(f"array element {k} read before assignment")
+
+
+def run(py_src, cell_in=None, field_in=None, scalars=None, local_arrays=(), cell_out=(), field_out=()):
+    """Execute translated source.  cell_in: {name: sequence}, field_in: {name: float},
+    scalars: {name: number} (parameters such as snu, sq, nx).  Returns {name: list or float}."""
+    ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range}
+    for name, seq in (cell_in or {}).items():
+        ns[name.lower() + "__"] = _Arr({k: float(x) for k, x in enumerate(seq)})
+    for name, val in (field_in or {}).items():
+        ns[name.lower() + "__"] = float(val)
+    for name in local_arrays:
+        ns.setdefault(name.lower() + "__", _Arr())
+    for name in cell_out:
+        ns.setdefault(name.lower() + "__", _Arr())
+    for name, val in (scalars or {}).items():
+        ns[name.lower()] = val
+    exec(compile(py_src, "<reference loop body>", "exec"), ns)
+    out = {}
+    for name in cell_out:
+        a = ns[name.lower() + "__"]
+        out[name] = [a[k] for k in sorted(a)]
+    for name in field_out:
+        out[name] = ns[name.lower() + "__"]
+    return out
+
+
+def read_lines(path, first, last):
+    """lines first..last (1-based, inclusive) of a reference source file"""
+    with open(path, errors="replace") as fh:
+        lines = fh.read().splitlines()
+    return "\n".join(lines[first - 1:last])
