@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGLC_VERSION 100
+#define MGLC_VERSION 101
 
 /* ---- status codes ---- */
 #define MGLC_OK          0
@@ -47,6 +47,9 @@ enum { MGLC_MRT_LID = 0, MGLC_MRT_THERMAL = 1, MGLC_BGK = 2 };
 enum { MGLC_ARITH_FAST = 0, MGLC_ARITH_STRICT = 1 };
 /* how halos move between subdomains */
 enum { MGLC_TRANSPORT_NONE = 0, MGLC_TRANSPORT_LOCAL = 1, MGLC_TRANSPORT_NCCL = 2 };
+/* thermal wall kinds of bouncebackT() (B3 = MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90:1100-1210):
+ * adiabatic g_a = g_post_opp, constant temperature g_a = -g_post_opp + (6+paraA)/21 * Thot|Tcold */
+enum { MGLC_BCT_ADIABATIC = 0, MGLC_BCT_CONST_HOT = 1, MGLC_BCT_CONST_COLD = 2 };
 /* fused-kernel variant (MGLC_KERNEL_AUTO picks the fastest validated one) */
 enum { MGLC_KERNEL_AUTO = 0, MGLC_KERNEL_DIRECT = 1, MGLC_KERNEL_TMA = 2 };
 
@@ -70,7 +73,14 @@ typedef struct mglc_lbm_desc {
     double U0;          /* lid speed                             (commondata.f90:8)    */
     double rho0;        /* initial density                       (commondata.f90:7)    */
     int device;         /* CUDA device ordinal                                         */
-    int reserved[7];
+    /* ---- MGLC_D3Q19_D3Q7 only (module commondata of B3:26-47,73-74; BC macros B3:5-19) ---- */
+    int bcT[6];         /* thermal wall kind per face +x,-x,+y,-y,+z,-z : MGLC_BCT_*       */
+    int reserved[1];
+    double paraA;       /* 42*sqrt(3)*diffusivity - 6                                  */
+    double gBeta;       /* Ra*nu*kappa/total_nz^3                                      */
+    double Tref, Thot, Tcold;
+    double omegaRot;    /* omegaRatating = nu/2/Ekman/total_nz^2 (Coriolis)            */
+    double Qd, Qnu;     /* D3Q7 relaxation rates 3-sqrt(3), 4*sqrt(3)-6                */
 } mglc_lbm_desc;
 
 /* one halo message of message_passing_sendrecv() (L3/ex_sendrecv.f90): dir 0..5 = faces
@@ -105,6 +115,11 @@ int mglc_cart_neighbors(const int dims[3], const int coords[3], int nbr_surface[
  * nranks, coords/ln/start from rank, tau = U0*total_nx/Re*3+0.5 */
 int mglc_lbm_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_zero[3], int nranks,
                        int rank, double reynolds, double U0, double rho0);
+/* thermal descriptor the way B3 does it: decomposition as above; tau = 0.5 + Ma*total_nz*sqrt(3 Pr/Ra),
+ * paraA, gBeta, omegaRot, Qd, Qnu from B3:33-47,73-74; Thot = 1, Tcold = Tref = 0; the shipped
+ * benchmarkCavity wall set (y walls constant T, hot at j = 1; x and z walls adiabatic; all walls no-slip) */
+int mglc_thermal_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_zero[3], int nranks, int rank,
+                           double rayleigh, double prandtl, double mach, double ekman);
 /* the 18 messages of one message_passing_sendrecv() for this subdomain, in the reference's order */
 int mglc_halo_plan(const mglc_lbm_desc *d, mglc_halo_msg msgs[18], int *nmsgs);
 /* relaxation rates Snu, Sq -- L3/commondata.f90:42 */
@@ -138,7 +153,23 @@ int mglc_bounceback(mglc_lbm *h);   /* bounceback()                L3/bounce_bac
 int mglc_macro(mglc_lbm *h);        /* macro()                     L3/macro.f90:1-28        */
 int mglc_check(mglc_lbm *h, double *errorU);   /* check() incl. Allreduce  L3/check.f90:1-37 */
 
-/* fused fast path == nsteps iterations of the loop body L3/main.f90:85-97
+/* thermal double-distribution handles (lattice == MGLC_D3Q19_D3Q7): mglc_collision / mglc_exchange /
+ * mglc_streaming / mglc_bounceback / mglc_macro above act on f as B3's collision (+force, B3:640-864),
+ * f_message_passing_sendrecv, streaming, bounceback (no-slip on all walls), macro (+F/2, B3:986-1010);
+ * the temperature populations have their own five subroutines */
+int mglc_collisionT(mglc_lbm *h);   /* collisionT()                  B3:1014-1070 */
+int mglc_exchange_g(mglc_lbm *h);   /* g_message_passing_sendrecv()  B3:1421-1468 */
+int mglc_streamingT(mglc_lbm *h);   /* streamingT()                  B3:1075-1098 */
+int mglc_bouncebackT(mglc_lbm *h);  /* bouncebackT()                 B3:1100-1210 */
+int mglc_macroT(mglc_lbm *h);       /* macroT()                      B3:1215-1232 */
+int mglc_check_thermal(mglc_lbm *h, double *errorU, double *errorT);   /* check()  B3:1236-1283 */
+/* g (0:6,nx,ny,nz), g_post (0:6,0:nx+1,..), T, Fx,Fy,Fz (nx,ny,nz); any pointer may be NULL = skip */
+int mglc_lbm_upload_thermal(mglc_lbm *h, const double *g, const double *T, const double *Fx, const double *Fy, const double *Fz);
+int mglc_lbm_download_thermal(mglc_lbm *h, double *g, double *T, double *Fx, double *Fy, double *Fz);
+int mglc_lbm_upload_gpost(mglc_lbm *h, const double *g_post);
+int mglc_lbm_download_gpost(mglc_lbm *h, double *g_post);
+
+/* fused fast path == nsteps iterations of the loop body L3/main.f90:85-97 (B3:222-248 for thermal handles)
  * (collision, exchange, streaming, bounceback, macro); prologue/epilogue handled inside, the state
  * afterwards (f, f_post, rho,u,v,w) is the reference's state after the same number of iterations */
 int mglc_lbm_step(mglc_lbm *h, int nsteps);
@@ -172,6 +203,12 @@ int mglc_group_streaming(mglc_group *g);
 int mglc_group_bounceback(mglc_group *g);
 int mglc_group_macro(mglc_group *g);
 int mglc_group_check(mglc_group *g, double *errorU);
+int mglc_group_collisionT(mglc_group *g);
+int mglc_group_exchange_g(mglc_group *g);
+int mglc_group_streamingT(mglc_group *g);
+int mglc_group_bouncebackT(mglc_group *g);
+int mglc_group_macroT(mglc_group *g);
+int mglc_group_check_thermal(mglc_group *g, double *errorU, double *errorT);
 int mglc_group_step(mglc_group *g, int nsteps);
 int mglc_group_step_timed(mglc_group *g, int nsteps, float *ms);
 

@@ -15,6 +15,7 @@ D3Q19, D3Q19_D3Q7, D2Q9 = 0, 1, 2
 MRT_LID, MRT_THERMAL, BGK = 0, 1, 2
 ARITH_FAST, ARITH_STRICT = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+BCT_ADIABATIC, BCT_CONST_HOT, BCT_CONST_COLD = 0, 1, 2
 
 
 class MglcError(RuntimeError):
@@ -27,7 +28,9 @@ class LbmDesc(C.Structure):
     _fields_ = [("lattice", C.c_int), ("collision", C.c_int), ("arith", C.c_int), ("kernel", C.c_int),
                 ("gn", C.c_int * 3), ("dims", C.c_int * 3), ("coords", C.c_int * 3), ("ln", C.c_int * 3),
                 ("start", C.c_int * 3), ("tau", C.c_double), ("U0", C.c_double), ("rho0", C.c_double),
-                ("device", C.c_int), ("reserved", C.c_int * 7)]
+                ("device", C.c_int), ("bcT", C.c_int * 6), ("reserved", C.c_int * 1),
+                ("paraA", C.c_double), ("gBeta", C.c_double), ("Tref", C.c_double), ("Thot", C.c_double),
+                ("Tcold", C.c_double), ("omegaRot", C.c_double), ("Qd", C.c_double), ("Qnu", C.c_double)]
 
 
 class HaloMsg(C.Structure):
@@ -94,6 +97,24 @@ SIGNATURES = {
     "mglc_group_check": (C.c_int, [_vp, _dp]),
     "mglc_group_step": (C.c_int, [_vp, C.c_int]),
     "mglc_group_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    # thermal double-distribution path
+    "mglc_thermal_desc_init": (C.c_int, [C.POINTER(LbmDesc), _ip, _ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "mglc_collisionT": (C.c_int, [_vp]),
+    "mglc_exchange_g": (C.c_int, [_vp]),
+    "mglc_streamingT": (C.c_int, [_vp]),
+    "mglc_bouncebackT": (C.c_int, [_vp]),
+    "mglc_macroT": (C.c_int, [_vp]),
+    "mglc_check_thermal": (C.c_int, [_vp, _dp, _dp]),
+    "mglc_lbm_upload_thermal": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mglc_lbm_download_thermal": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mglc_lbm_upload_gpost": (C.c_int, [_vp, _vp]),
+    "mglc_lbm_download_gpost": (C.c_int, [_vp, _vp]),
+    "mglc_group_collisionT": (C.c_int, [_vp]),
+    "mglc_group_exchange_g": (C.c_int, [_vp]),
+    "mglc_group_streamingT": (C.c_int, [_vp]),
+    "mglc_group_bouncebackT": (C.c_int, [_vp]),
+    "mglc_group_macroT": (C.c_int, [_vp]),
+    "mglc_group_check_thermal": (C.c_int, [_vp, _dp, _dp]),
     # Jacobi path
     "mglc_dims_create_nd": (C.c_int, [C.c_int, C.c_int, _ip]),
     "mglc_jacobi_create": (C.c_int, [_vpp, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, _vp]),

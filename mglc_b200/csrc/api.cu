@@ -36,8 +36,15 @@ struct mglc_lbm {
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1, ev_shell, ev_halo;
     long long launches;
     long long bytes;
-    Msg msgs[18];
+    Msg msgs[24];            // 0..17 f messages (faces, edges); 18..23 g faces (dir 20+face) for thermal handles
     int nmsgs;
+    // thermal double-distribution state (lattice == MGLC_D3Q19_D3Q7)
+    bool thermal;
+    ThermalParams tp;
+    double *gbuf[2];         // gbuf[cur] = g, gbuf[cur^1] = g_post (ping-pong in lockstep with buf)
+    double *T, *Tp;
+    double *Fc[2];           // Fx,Fy,Fz back to back; Fc[fc_cur] = the force collision() wrote / macro() reads
+    int fc_cur;
     bool has_neighbors;
     mglc_comm *comm;
     mglc_group *group;
@@ -53,8 +60,10 @@ struct mglc_lbm {
 
 struct mglc_group {
     std::vector<mglc_lbm *> r;
+    std::vector<Port> ports;
     mglc_lbm_desc global;
 };
+enum { MSG_F = 1, MSG_G = 2, MSG_ALL = 3 };
 
 // ---------------------------------------------------------------------------------------------------
 static int use(mglc_lbm *h) {
@@ -70,6 +79,8 @@ template <class T> static int dmalloc(mglc_lbm *h, T **p, long long count) {
 static inline long long ncell(const mglc_lbm *h) { return (long long)h->g.nx * h->g.ny * h->g.nz; }
 static inline double *F_(mglc_lbm *h) { return h->buf[h->cur]; }
 static inline double *Fpost_(mglc_lbm *h) { return h->buf[h->cur ^ 1]; }
+static inline double *G_(mglc_lbm *h) { return h->gbuf[h->cur]; }
+static inline double *Gpost_(mglc_lbm *h) { return h->gbuf[h->cur ^ 1]; }
 static inline bool strict_(const mglc_lbm *h) { return h->d.arith == MGLC_ARITH_STRICT; }
 
 extern "C" int mglc_device_count(int *n) {
@@ -110,8 +121,13 @@ extern "C" int mglc_comm_destroy(mglc_comm *c) {
 
 // ---- create / destroy -------------------------------------------------------------------------------
 static int validate(const mglc_lbm_desc *d) {
-    if (d->lattice != MGLC_D3Q19) { set_error("mglc_lbm_create: lattice %d not supported by this handle type", d->lattice); return MGLC_E_INVALID; }
-    if (d->collision != MGLC_MRT_LID) { set_error("mglc_lbm_create: collision operator %d not supported", d->collision); return MGLC_E_INVALID; }
+    if (d->lattice != MGLC_D3Q19 && d->lattice != MGLC_D3Q19_D3Q7) { set_error("mglc_lbm_create: lattice %d not supported by this handle type", d->lattice); return MGLC_E_INVALID; }
+    if (d->collision != (d->lattice == MGLC_D3Q19 ? MGLC_MRT_LID : MGLC_MRT_THERMAL)) { set_error("mglc_lbm_create: collision operator %d not supported with lattice %d", d->collision, d->lattice); return MGLC_E_INVALID; }
+    if (d->lattice == MGLC_D3Q19_D3Q7) {
+        for (int f = 0; f < 6; ++f)
+            if (d->bcT[f] < MGLC_BCT_ADIABATIC || d->bcT[f] > MGLC_BCT_CONST_COLD) { set_error("mglc_lbm_create: bcT[%d]=%d", f, d->bcT[f]); return MGLC_E_INVALID; }
+        if (d->bcT[0] || d->bcT[1]) { set_error("mglc_lbm_create: the reference has no constant-temperature x walls (B3:1186-1205)"); return MGLC_E_INVALID; }
+    }
     for (int q = 0; q < 3; ++q) {
         if (d->ln[q] < 1 || d->gn[q] < d->ln[q] || d->dims[q] < 1 || d->coords[q] < 0 || d->coords[q] >= d->dims[q] ||
             d->start[q] < 0 || d->start[q] + d->ln[q] > d->gn[q]) {
@@ -129,7 +145,8 @@ extern "C" int mglc_lbm_destroy(mglc_lbm *h) {
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
-    double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage, h->rho_lid[0], h->rho_lid[1]};
+    double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage, h->rho_lid[0], h->rho_lid[1],
+                        h->gbuf[0], h->gbuf[1], h->T, h->Tp, h->Fc[0], h->Fc[1]};
     for (double *p : fields) cudaFree(p);
     for (int m = 0; m < h->nmsgs; ++m) { cudaFree(h->msgs[m].sbuf); cudaFree(h->msgs[m].rbuf); }
     cudaEvent_t evs[] = {h->ev_packed, h->ev_copied, h->ev_t0, h->ev_t1, h->ev_shell, h->ev_halo};
@@ -154,9 +171,20 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
         h->g.wall[2 * q] = (d->coords[q] == d->dims[q] - 1);      // +face is a physical wall
         h->g.wall[2 * q + 1] = (d->coords[q] == 0);               // -face
     }
-    h->g.lid = h->g.wall[4];                                      // coords(2) == dims(2)-1, L3/bounce_back.f90:72
+    h->thermal = (d->lattice == MGLC_D3Q19_D3Q7);
+    h->g.lid = h->thermal ? 0 : h->g.wall[4];                     // coords(2) == dims(2)-1, L3/bounce_back.f90:72
     mglc_relaxation_rates(d->tau, &h->p.Snu, &h->p.Sq);
     h->p.U0 = d->U0; h->p.rho0 = d->rho0;
+    if (h->thermal) {
+        ThermalParams &tp = h->tp;
+        tp.Snu = h->p.Snu; tp.Sq = h->p.Sq; tp.Qd = d->Qd; tp.Qnu = d->Qnu; tp.paraA = d->paraA; tp.gBeta = d->gBeta;
+        tp.Tref = d->Tref; tp.omegaRot = d->omegaRot; tp.Thot = d->Thot; tp.Tcold = d->Tcold;
+        for (int f = 0; f < 6; ++f) {
+            tp.bcT[f] = d->bcT[f];
+            const double Tw = d->bcT[f] == MGLC_BCT_CONST_HOT ? d->Thot : d->Tcold;
+            tp.wallT[f] = (6.0 + d->paraA) / 21.0 * Tw;              // B3:1128,1137,1148,1157
+        }
+    }
     h->nranks = d->dims[0] * d->dims[1] * d->dims[2];
     mglc_cart_rank(d->dims, d->coords, &h->rank);
     h->comm = comm;
@@ -178,6 +206,16 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
         if ((rc = dmalloc(h, f, n))) return fail(rc);
         if (cudaMemsetAsync(*f, 0, (size_t)n * sizeof(double), h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
     }
+    if (h->thermal) {
+        for (int b = 0; b < 2; ++b) {
+            if ((rc = dmalloc(h, &h->gbuf[b], QT * h->g.sq))) return fail(rc);
+            if (cudaMemsetAsync(h->gbuf[b], 0, (size_t)QT * h->g.sq * sizeof(double), h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
+            if ((rc = dmalloc(h, &h->Fc[b], 3 * n))) return fail(rc);
+            if (cudaMemsetAsync(h->Fc[b], 0, (size_t)3 * n * sizeof(double), h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
+        }
+        if ((rc = dmalloc(h, &h->T, n))) return fail(rc);
+        if (cudaMemsetAsync(h->T, 0, (size_t)n * sizeof(double), h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
+    }
     if ((rc = dmalloc(h, &h->scratch, check_scratch_doubles()))) return fail(rc);
     for (int b = 0; b < 2; ++b)
         if ((rc = dmalloc(h, &h->rho_lid[b], (long long)h->g.nx * h->g.ny))) return fail(rc);
@@ -193,6 +231,17 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
         if (M.send_count && (rc = dmalloc(h, &M.sbuf, M.send_count))) return fail(rc);
         if (M.recv_count && (rc = dmalloc(h, &M.rbuf, M.recv_count))) return fail(rc);
         if (M.send_count || M.recv_count) h->has_neighbors = true;
+    }
+    if (h->thermal) {              // g_message_passing_sendrecv(): one population per face, B3:1421-1468
+        for (int face = 0; face < 6; ++face) {
+            Msg &M = h->msgs[h->nmsgs++];
+            const Msg &Ff = h->msgs[face];                        // same neighbours and slab as f's face message
+            M.dir = 20 + face; M.send_to = Ff.send_to; M.recv_from = Ff.recv_from; M.skip = 0;
+            M.send_count = Ff.send_count / 5; M.recv_count = Ff.recv_count / 5;
+            M.sbuf = M.rbuf = nullptr;
+            if (M.send_count && (rc = dmalloc(h, &M.sbuf, M.send_count))) return fail(rc);
+            if (M.recv_count && (rc = dmalloc(h, &M.rbuf, M.recv_count))) return fail(rc);
+        }
     }
     if (cudaStreamSynchronize(h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
     *out = h;
@@ -240,8 +289,9 @@ static int ensure_stage(mglc_lbm *h) {
     return dmalloc(h, &h->stage, h->stage_doubles);
 }
 // f (0:18,nx,ny,nz) or f_post (0:18,0:nx+1,...) on the host <-> SoA lattice on the device
-static int transfer_lattice(mglc_lbm *h, double *host, double *dev, int with_halo, bool to_device) {
+static int transfer_lattice(mglc_lbm *h, double *host, double *dev, int with_halo, bool to_device, int nq = Q) {
     MGLC_TRY(ensure_stage(h));
+    const int Q = nq;
     const int e = with_halo ? 2 : 0;
     const long long total = (long long)(h->g.nx + e) * (h->g.ny + e) * (h->g.nz + e);
     const long long chunk = h->stage_doubles / Q;
@@ -249,9 +299,9 @@ static int transfer_lattice(mglc_lbm *h, double *host, double *dev, int with_hal
         const long long nc = std::min(chunk, total - c0);
         if (to_device) {
             MGLC_CUDA(cudaMemcpyAsync(h->stage, host + c0 * Q, (size_t)nc * Q * sizeof(double), cudaMemcpyHostToDevice, h->s));
-            h->launches += launch_aos_to_soa(h->g, h->stage, dev, c0, nc, with_halo, h->s);
+            h->launches += launch_aos_to_soa(h->g, nq, h->stage, dev, c0, nc, with_halo, h->s);
         } else {
-            h->launches += launch_soa_to_aos(h->g, dev, h->stage, c0, nc, with_halo, h->s);
+            h->launches += launch_soa_to_aos(h->g, nq, dev, h->stage, c0, nc, with_halo, h->s);
             MGLC_CUDA(cudaMemcpyAsync(host + c0 * Q, h->stage, (size_t)nc * Q * sizeof(double), cudaMemcpyDeviceToHost, h->s));
         }
     }
@@ -311,6 +361,12 @@ extern "C" int mglc_lbm_download_fpost(mglc_lbm *h, double *f_post) {
 static int do_initial(mglc_lbm *h) {
     h->rotated = 0;
     h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
+    if (h->thermal) {
+        h->launches += launch_th_initial(h->g, h->tp, F_(h), G_(h), h->rho, h->u, h->v, h->w, h->T, h->s);
+        MGLC_CUDA(cudaMemsetAsync(Fpost_(h), 0, (size_t)Q * h->g.sq * sizeof(double), h->s));      // f_post = 0, B3:624
+        MGLC_CUDA(cudaMemsetAsync(Gpost_(h), 0, (size_t)QT * h->g.sq * sizeof(double), h->s));     // g_post = 0, B3:625
+        if (h->Tp) MGLC_CUDA(cudaMemsetAsync(h->Tp, 0, (size_t)ncell(h) * sizeof(double), h->s));
+    } else
     h->launches += launch_initial(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, h->s);
     if (h->up) {
         const size_t b = (size_t)ncell(h) * sizeof(double);
@@ -322,36 +378,44 @@ static int do_initial(mglc_lbm *h) {
 }
 static int do_collision(mglc_lbm *h) {
     MGLC_TRY(canonicalise(h));
+    if (h->thermal) {
+        h->launches += strict_(h) ? strict::launch_th_collision(h->g, h->tp, F_(h), h->rho, h->u, h->v, h->w, h->T, Fpost_(h), h->Fc[h->fc_cur], h->s)
+                                  : fast::launch_th_collision(h->g, h->tp, F_(h), h->rho, h->u, h->v, h->w, h->T, Fpost_(h), h->Fc[h->fc_cur], h->s);
+        return MGLC_OK;
+    }
     h->launches += strict_(h) ? strict::launch_collision(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, Fpost_(h), h->s)
                               : fast::launch_collision(h->g, h->p, F_(h), h->rho, h->u, h->v, h->w, Fpost_(h), h->s);
     return MGLC_OK;
 }
+// which = MSG_F (f messages), MSG_G (g messages) or MSG_ALL: mark the others as skipped
+static void select_msgs(mglc_lbm *h, int which) {
+    for (int m = 0; m < h->nmsgs; ++m) h->msgs[m].skip = !(((h->msgs[m].dir >= 20) ? MSG_G : MSG_F) & which);
+}
 static int do_pack(mglc_lbm *h, cudaStream_t s) {
-    for (int m = 0; m < h->nmsgs; ++m)
-        if (h->msgs[m].send_count) h->launches += launch_pack(h->g, Fpost_(h), h->msgs[m].dir, h->msgs[m].sbuf, s);
+    for (int m = 0; m < h->nmsgs; ++m) {
+        const Msg &M = h->msgs[m];
+        if (!M.send_count || M.skip) continue;
+        h->launches += (M.dir >= 20) ? launch_pack_g(h->g, Gpost_(h), M.dir - 20, M.sbuf, s)
+                                     : launch_pack(h->g, Fpost_(h), M.dir, M.sbuf, s);
+    }
     return MGLC_OK;
 }
 static int do_unpack(mglc_lbm *h, cudaStream_t s) {
-    for (int m = 0; m < h->nmsgs; ++m)
-        if (h->msgs[m].recv_count) h->launches += launch_unpack(h->g, Fpost_(h), h->msgs[m].dir, h->msgs[m].rbuf, s);
-    return MGLC_OK;
-}
-static int do_nccl_sendrecv(mglc_lbm *h, cudaStream_t s) {
-    MGLC_NCCL(ncclGroupStart());
     for (int m = 0; m < h->nmsgs; ++m) {
-        Msg &M = h->msgs[m];
-        if (M.send_count) MGLC_NCCL(ncclSend(M.sbuf, (size_t)M.send_count, ncclDouble, M.send_to, h->comm->nccl, s));
-        if (M.recv_count) MGLC_NCCL(ncclRecv(M.rbuf, (size_t)M.recv_count, ncclDouble, M.recv_from, h->comm->nccl, s));
+        const Msg &M = h->msgs[m];
+        if (!M.recv_count || M.skip) continue;
+        h->launches += (M.dir >= 20) ? launch_unpack_g(h->g, Gpost_(h), M.dir - 20, M.rbuf, s)
+                                     : launch_unpack(h->g, Fpost_(h), M.dir, M.rbuf, s);
     }
-    MGLC_NCCL(ncclGroupEnd());
     return MGLC_OK;
 }
 // message_passing_sendrecv() for a handle that owns a communicator (one process per GPU)
-static int do_exchange_nccl(mglc_lbm *h) {
+static int do_exchange_nccl(mglc_lbm *h, int which = MSG_ALL) {
     if (!h->has_neighbors) return MGLC_OK;
     if (!h->comm) { set_error("exchange: subdomain has neighbours but no communicator"); return MGLC_E_STATE; }
+    select_msgs(h, which);
     MGLC_TRY(do_pack(h, h->s));
-    MGLC_TRY(do_nccl_sendrecv(h, h->s));
+    MGLC_TRY(halo_nccl_sendrecv(h->msgs, h->nmsgs, h->comm, h->s));
     MGLC_TRY(do_unpack(h, h->s));
     return MGLC_OK;
 }
@@ -367,7 +431,37 @@ static int do_bounceback(mglc_lbm *h) {
 }
 static int do_macro(mglc_lbm *h) {
     MGLC_TRY(canonicalise(h));
-    h->launches += launch_macro(h->g, F_(h), h->rho, h->u, h->v, h->w, h->s);
+    if (h->thermal) h->launches += launch_th_macro(h->g, F_(h), h->Fc[h->fc_cur], h->rho, h->u, h->v, h->w, h->s);
+    else h->launches += launch_macro(h->g, F_(h), h->rho, h->u, h->v, h->w, h->s);
+    return MGLC_OK;
+}
+static int need_thermal(mglc_lbm *h, const char *what) {
+    if (!h->thermal) { set_error("%s: the handle is not a thermal (MGLC_D3Q19_D3Q7) lattice", what); return MGLC_E_STATE; }
+    return MGLC_OK;
+}
+static int do_collisionT(mglc_lbm *h) {
+    MGLC_TRY(need_thermal(h, "collisionT"));
+    MGLC_TRY(canonicalise(h));
+    h->launches += strict_(h) ? strict::launch_th_collisionT(h->g, h->tp, G_(h), h->u, h->v, h->w, h->T, Gpost_(h), h->s)
+                              : fast::launch_th_collisionT(h->g, h->tp, G_(h), h->u, h->v, h->w, h->T, Gpost_(h), h->s);
+    return MGLC_OK;
+}
+static int do_streamingT(mglc_lbm *h) {
+    MGLC_TRY(need_thermal(h, "streamingT"));
+    MGLC_TRY(canonicalise(h));
+    h->launches += launch_streamingT(h->g, Gpost_(h), G_(h), h->s);
+    return MGLC_OK;
+}
+static int do_bouncebackT(mglc_lbm *h) {
+    MGLC_TRY(need_thermal(h, "bouncebackT"));
+    MGLC_TRY(canonicalise(h));
+    h->launches += launch_bouncebackT(h->g, h->tp, Gpost_(h), G_(h), h->s);
+    return MGLC_OK;
+}
+static int do_macroT(mglc_lbm *h) {
+    MGLC_TRY(need_thermal(h, "macroT"));
+    MGLC_TRY(canonicalise(h));
+    h->launches += launch_macroT(h->g, G_(h), h->T, h->s);
     return MGLC_OK;
 }
 // fused stream+macro+collide over the whole subdomain: reads f_post (incl. halo), writes the NEXT f_post
@@ -395,12 +489,18 @@ static int do_fused(mglc_lbm *h) {
         if (h->prof_used == PROF_PAIRS) MGLC_TRY(prof_flush(h));
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used], h->s));
     }
+    if (h->thermal) {
+        h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), h->Fc[h->fc_cur], h->Fc[h->fc_cur ^ 1], box, h->s)
+                                  : fast::launch_th_fused(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), h->Fc[h->fc_cur], h->Fc[h->fc_cur ^ 1], box, h->s);
+        h->fc_cur ^= 1;          // Fc[fc_cur] now belongs to the collision in flight, Fc[fc_cur^1] to the completed step
+    } else {
     const double *lid_in = h->lid_next;
     double *lid_out = (lid_in == h->rho_lid[0]) ? h->rho_lid[1] : h->rho_lid[0];
     h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s)
                               : fast::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s);
     h->lid_last_in = lid_in;
     h->lid_next = lid_out;
+    }
     if (h->profiling) {
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used + 1], h->s));
         h->prof_used += 1;
@@ -409,6 +509,13 @@ static int do_fused(mglc_lbm *h) {
     return MGLC_OK;
 }
 static int do_stream_macro(mglc_lbm *h) {
+    if (h->thermal) {
+        const double *Fc_done = h->Fc[h->fc_cur ^ 1];        // the force the completed step's collision computed
+        h->launches += strict_(h) ? strict::launch_th_stream_macro(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), Fc_done, h->rho, h->u, h->v, h->w, h->T, h->s)
+                                  : fast::launch_th_stream_macro(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), Fc_done, h->rho, h->u, h->v, h->w, h->T, h->s);
+        h->fc_cur ^= 1;
+        return MGLC_OK;
+    }
     h->launches += strict_(h) ? strict::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->lid_last_in, h->rho, h->u, h->v, h->w, h->s)
                               : fast::launch_stream_macro(h->g, h->p, Fpost_(h), F_(h), h->lid_last_in, h->rho, h->u, h->v, h->w, h->s);
     h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
@@ -433,12 +540,17 @@ static int ensure_prev(mglc_lbm *h) {
     MGLC_CUDA(cudaMemsetAsync(h->up, 0, (size_t)n * sizeof(double), h->s));     // up = vp = wp = 0, L3/initial.f90:50-52
     MGLC_CUDA(cudaMemsetAsync(h->vp, 0, (size_t)n * sizeof(double), h->s));
     MGLC_CUDA(cudaMemsetAsync(h->wp, 0, (size_t)n * sizeof(double), h->s));
+    if (h->thermal) {
+        MGLC_TRY(dmalloc(h, &h->Tp, n));
+        MGLC_CUDA(cudaMemsetAsync(h->Tp, 0, (size_t)n * sizeof(double), h->s));      // Tp = 0, B3:619
+    }
     return MGLC_OK;
 }
 static int do_check_partial(mglc_lbm *h) {
     MGLC_TRY(canonicalise(h));
     MGLC_TRY(ensure_prev(h));
-    h->launches += launch_check(h->g, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->s);
+    if (h->thermal) h->launches += launch_th_check(h->g, h->u, h->v, h->w, h->T, h->up, h->vp, h->wp, h->Tp, h->scratch, h->s);
+    else h->launches += launch_check(h->g, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->s);
     return MGLC_OK;
 }
 
@@ -454,24 +566,87 @@ extern "C" int mglc_exchange(mglc_lbm *h) {
     MGLC_TRY(use(h));
     MGLC_TRY(not_in_group(h, "mglc_exchange"));
     MGLC_TRY(canonicalise(h));
-    return do_exchange_nccl(h);
+    return do_exchange_nccl(h, MSG_F);
 }
+extern "C" int mglc_exchange_g(mglc_lbm *h) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(not_in_group(h, "mglc_exchange_g"));
+    MGLC_TRY(need_thermal(h, "mglc_exchange_g"));
+    MGLC_TRY(canonicalise(h));
+    return do_exchange_nccl(h, MSG_G);
+}
+extern "C" int mglc_collisionT(mglc_lbm *h) { MGLC_TRY(use(h)); return do_collisionT(h); }
+extern "C" int mglc_streamingT(mglc_lbm *h) { MGLC_TRY(use(h)); return do_streamingT(h); }
+extern "C" int mglc_bouncebackT(mglc_lbm *h) { MGLC_TRY(use(h)); return do_bouncebackT(h); }
+extern "C" int mglc_macroT(mglc_lbm *h) { MGLC_TRY(use(h)); return do_macroT(h); }
 extern "C" int mglc_streaming(mglc_lbm *h) { MGLC_TRY(use(h)); return do_streaming(h); }
 extern "C" int mglc_bounceback(mglc_lbm *h) { MGLC_TRY(use(h)); return do_bounceback(h); }
 extern "C" int mglc_macro(mglc_lbm *h) { MGLC_TRY(use(h)); return do_macro(h); }
 
+static int check_impl(mglc_lbm *h, double *errorU, double *errorT) {
+    MGLC_TRY(do_check_partial(h));
+    if (h->comm && h->nranks > 1)   // MPI_Allreduce(SUM) x2 (L3/check.f90:27-28) or x4 (B3:1268-1271)
+        MGLC_NCCL(ncclAllReduce(h->scratch, h->scratch, 4, ncclDouble, ncclSum, h->comm->nccl, h->s));
+    double e[4];
+    MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    *errorU = sqrt(e[0]) / sqrt(e[1]);
+    if (errorT) *errorT = e[2] / e[3];
+    return MGLC_OK;
+}
 extern "C" int mglc_check(mglc_lbm *h, double *errorU) {
     MGLC_TRY(use(h));
     MGLC_TRY(not_in_group(h, "mglc_check"));
     if (!errorU) return MGLC_E_INVALID;
-    MGLC_TRY(do_check_partial(h));
-    if (h->comm && h->nranks > 1)   // MPI_Allreduce(SUM) x2, L3/check.f90:27-28
-        MGLC_NCCL(ncclAllReduce(h->scratch, h->scratch, 2, ncclDouble, ncclSum, h->comm->nccl, h->s));
-    double e[2];
-    MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
+    return check_impl(h, errorU, nullptr);
+}
+extern "C" int mglc_check_thermal(mglc_lbm *h, double *errorU, double *errorT) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(not_in_group(h, "mglc_check_thermal"));
+    MGLC_TRY(need_thermal(h, "mglc_check_thermal"));
+    if (!errorU || !errorT) return MGLC_E_INVALID;
+    return check_impl(h, errorU, errorT);
+}
+extern "C" int mglc_lbm_upload_thermal(mglc_lbm *h, const double *g, const double *T, const double *Fx, const double *Fy,
+                                       const double *Fz) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(need_thermal(h, "mglc_lbm_upload_thermal"));
+    MGLC_TRY(canonicalise(h));
+    if (g) MGLC_TRY(transfer_lattice(h, const_cast<double *>(g), G_(h), 0, true, QT));
+    MGLC_TRY(copy_field(h, const_cast<double *>(T), h->T, true));
+    double *Fc = h->Fc[h->fc_cur];
+    MGLC_TRY(copy_field(h, const_cast<double *>(Fx), Fc, true));
+    MGLC_TRY(copy_field(h, const_cast<double *>(Fy), Fc + ncell(h), true));
+    MGLC_TRY(copy_field(h, const_cast<double *>(Fz), Fc + 2 * ncell(h), true));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
-    *errorU = sqrt(e[0]) / sqrt(e[1]);
     return MGLC_OK;
+}
+extern "C" int mglc_lbm_download_thermal(mglc_lbm *h, double *g, double *T, double *Fx, double *Fy, double *Fz) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(need_thermal(h, "mglc_lbm_download_thermal"));
+    MGLC_TRY(canonicalise(h));
+    if (g) MGLC_TRY(transfer_lattice(h, g, G_(h), 0, false, QT));
+    MGLC_TRY(copy_field(h, T, h->T, false));
+    double *Fc = h->Fc[h->fc_cur];
+    MGLC_TRY(copy_field(h, Fx, Fc, false));
+    MGLC_TRY(copy_field(h, Fy, Fc + ncell(h), false));
+    MGLC_TRY(copy_field(h, Fz, Fc + 2 * ncell(h), false));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    return MGLC_OK;
+}
+extern "C" int mglc_lbm_upload_gpost(mglc_lbm *h, const double *g_post) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(need_thermal(h, "mglc_lbm_upload_gpost"));
+    MGLC_TRY(canonicalise(h));
+    if (!g_post) return MGLC_E_INVALID;
+    return transfer_lattice(h, const_cast<double *>(g_post), Gpost_(h), 1, true, QT);
+}
+extern "C" int mglc_lbm_download_gpost(mglc_lbm *h, double *g_post) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(need_thermal(h, "mglc_lbm_download_gpost"));
+    MGLC_TRY(canonicalise(h));
+    if (!g_post) return MGLC_E_INVALID;
+    return transfer_lattice(h, g_post, Gpost_(h), 1, false, QT);
 }
 
 // nsteps iterations of: collision, exchange, streaming, bounceback, macro  (L3/main.f90:85-97).
@@ -481,7 +656,10 @@ extern "C" int mglc_check(mglc_lbm *h, double *errorU) {
 static int step_impl(mglc_lbm *h, int nsteps) {
     if (nsteps < 0) { set_error("mglc_lbm_step: nsteps=%d", nsteps); return MGLC_E_INVALID; }
     if (nsteps == 0) return MGLC_OK;
-    if (!h->rotated) MGLC_TRY(do_collision(h));      // the first step's collision()
+    if (!h->rotated) {                               // the first step's collision() (and collisionT())
+        MGLC_TRY(do_collision(h));
+        if (h->thermal) MGLC_TRY(do_collisionT(h));
+    }
     for (int it = 0; it < nsteps; ++it) {
         MGLC_TRY(do_exchange_nccl(h));               // exchange of step it
         MGLC_TRY(do_fused(h));                       // streaming+bounceback+macro of step it, collision of it+1
@@ -571,6 +749,7 @@ extern "C" int mglc_group_create(mglc_group **out, const mglc_lbm_desc *gd, int 
                 cudaDeviceCanAccessPeer(&can, a->d.device, b->d.device);
                 if (can) { cudaSetDevice(a->d.device); cudaDeviceEnablePeerAccess(b->d.device, 0); (void)cudaGetLastError(); }
             }
+    for (mglc_lbm *h : g->r) g->ports.push_back(Port{h->d.device, h->s, h->ev_packed, h->ev_copied, h->msgs, h->nmsgs});
     *out = g;
     return MGLC_OK;
 }
@@ -591,31 +770,11 @@ extern "C" int mglc_group_rank(mglc_group *g, int r, mglc_lbm **h) {
 
 // message_passing_sendrecv() across the group: pack on every sender, receiver-driven device-to-device
 // copies (ordered by events), unpack on every receiver
-static int group_exchange(mglc_group *g) {
-    FOR_RANKS(g, h) {
-        if (!h->has_neighbors) continue;
-        MGLC_TRY(use(h));
-        // the peers that copied out of my send buffers last time must be done before I overwrite them
-        for (int m = 0; m < h->nmsgs; ++m)
-            if (h->msgs[m].send_count) MGLC_CUDA(cudaStreamWaitEvent(h->s, g->r[h->msgs[m].send_to]->ev_copied, 0));
-        MGLC_TRY(do_pack(h, h->s));
-        MGLC_CUDA(cudaEventRecord(h->ev_packed, h->s));
-    }
-    FOR_RANKS(g, h) {
-        if (!h->has_neighbors) continue;
-        MGLC_TRY(use(h));
-        for (int m = 0; m < h->nmsgs; ++m) {
-            Msg &M = h->msgs[m];
-            if (!M.recv_count) continue;
-            mglc_lbm *src = g->r[M.recv_from];
-            MGLC_CUDA(cudaStreamWaitEvent(h->s, src->ev_packed, 0));
-            MGLC_CUDA(cudaMemcpyPeerAsync(M.rbuf, h->d.device, src->msgs[m].sbuf, src->d.device,
-                                          (size_t)M.recv_count * sizeof(double), h->s));
-        }
-        MGLC_CUDA(cudaEventRecord(h->ev_copied, h->s));
-        MGLC_TRY(do_unpack(h, h->s));
-    }
-    return MGLC_OK;
+static int group_exchange(mglc_group *g, int which = MSG_ALL) {
+    FOR_RANKS(g, h) select_msgs(h, which);
+    return halo_local_exchange(
+        g->ports, [&](int r, cudaStream_t s) { return do_pack(g->r[r], s); },
+        [&](int r, cudaStream_t s) { return do_unpack(g->r[r], s); });
 }
 
 extern "C" int mglc_group_initial(mglc_group *g) { GROUP_EACH(g, do_initial); }
@@ -623,31 +782,52 @@ extern "C" int mglc_group_collision(mglc_group *g) { GROUP_EACH(g, do_collision)
 extern "C" int mglc_group_exchange(mglc_group *g) {
     if (!g) return MGLC_E_INVALID;
     FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(canonicalise(h)); }
-    return group_exchange(g);
+    return group_exchange(g, MSG_F);
 }
+extern "C" int mglc_group_exchange_g(mglc_group *g) {
+    if (!g) return MGLC_E_INVALID;
+    FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(need_thermal(h, "mglc_group_exchange_g")); MGLC_TRY(canonicalise(h)); }
+    return group_exchange(g, MSG_G);
+}
+extern "C" int mglc_group_collisionT(mglc_group *g) { GROUP_EACH(g, do_collisionT); }
+extern "C" int mglc_group_streamingT(mglc_group *g) { GROUP_EACH(g, do_streamingT); }
+extern "C" int mglc_group_bouncebackT(mglc_group *g) { GROUP_EACH(g, do_bouncebackT); }
+extern "C" int mglc_group_macroT(mglc_group *g) { GROUP_EACH(g, do_macroT); }
 extern "C" int mglc_group_streaming(mglc_group *g) { GROUP_EACH(g, do_streaming); }
 extern "C" int mglc_group_bounceback(mglc_group *g) { GROUP_EACH(g, do_bounceback); }
 extern "C" int mglc_group_macro(mglc_group *g) { GROUP_EACH(g, do_macro); }
 
-extern "C" int mglc_group_check(mglc_group *g, double *errorU) {
-    if (!g || !errorU) return MGLC_E_INVALID;
-    double t1 = 0.0, t2 = 0.0;
+static int group_check_impl(mglc_group *g, double *errorU, double *errorT) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
     FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_check_partial(h)); }
     FOR_RANKS(g, h) {                       // Allreduce(SUM) modelled as a rank-ordered host sum
         MGLC_TRY(use(h));
-        double e[2];
+        double e[4];
         MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
         MGLC_CUDA(cudaStreamSynchronize(h->s));
-        t1 += e[0]; t2 += e[1];
+        for (int q = 0; q < 4; ++q) t[q] += e[q];
     }
-    *errorU = sqrt(t1) / sqrt(t2);
+    *errorU = sqrt(t[0]) / sqrt(t[1]);
+    if (errorT) *errorT = t[2] / t[3];
     return MGLC_OK;
+}
+extern "C" int mglc_group_check(mglc_group *g, double *errorU) {
+    if (!g || !errorU) return MGLC_E_INVALID;
+    return group_check_impl(g, errorU, nullptr);
+}
+extern "C" int mglc_group_check_thermal(mglc_group *g, double *errorU, double *errorT) {
+    if (!g || !errorU || !errorT) return MGLC_E_INVALID;
+    FOR_RANKS(g, h) MGLC_TRY(need_thermal(h, "mglc_group_check_thermal"));
+    return group_check_impl(g, errorU, errorT);
 }
 
 static int group_step_impl(mglc_group *g, int nsteps) {
     if (nsteps < 0) return MGLC_E_INVALID;
     if (nsteps == 0) return MGLC_OK;
-    FOR_RANKS(g, h) { MGLC_TRY(use(h)); if (!h->rotated) MGLC_TRY(do_collision(h)); }
+    FOR_RANKS(g, h) {
+        MGLC_TRY(use(h));
+        if (!h->rotated) { MGLC_TRY(do_collision(h)); if (h->thermal) MGLC_TRY(do_collisionT(h)); }
+    }
     for (int it = 0; it < nsteps; ++it) {
         MGLC_TRY(group_exchange(g));
         FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_fused(h)); }

@@ -43,6 +43,15 @@ struct LbmParams {
     double Snu, Sq, U0, rho0;
 };
 
+// thermal double-distribution path (MGLC_D3Q19_D3Q7), B3 = MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90
+constexpr int QT = 7;
+struct ThermalParams {
+    double Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, omegaRot;   // B3:30-47,73-74
+    double Thot, Tcold;
+    double wallT[6];     // (6+paraA)/21 * T_wall per face (+x,-x,+y,-y,+z,-z), B3:1128-1163; used when bcT[face] != 0
+    int bcT[6];          // MGLC_BCT_ADIABATIC or a constant-temperature kind
+};
+
 // D3Q19 tables, L3/commondata.f90:32-40 (host copies; device code uses constexpr switch tables)
 static const int h_ex[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
 static const int h_ey[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
@@ -79,8 +88,24 @@ void set_error(const char *fmt, ...);
                             const double *rho_lid_in, double *rho, double *u, double *v, double *w,  \
                             cudaStream_t s);
 
-namespace strict { MGLC_DECLARE_LBM_LAUNCHERS }
-namespace fast { MGLC_DECLARE_LBM_LAUNCHERS }
+// thermal launchers: Fc = the three force fields Fx,Fy,Fz stored back to back (ncell doubles each)
+#define MGLC_DECLARE_THERMAL_LAUNCHERS                                                               \
+    int launch_th_collision(const Geom &g, const ThermalParams &tp, const double *F, const double *rho, \
+                            const double *u, const double *v, const double *w, const double *T,     \
+                            double *Fpost, double *Fc, cudaStream_t s);                              \
+    int launch_th_collisionT(const Geom &g, const ThermalParams &tp, const double *G, const double *u, \
+                             const double *v, const double *w, const double *T, double *Gpost,       \
+                             cudaStream_t s);                                                        \
+    /* streaming+bounceback+streamingT+bouncebackT+macro+macroT of step n, collision+collisionT of n+1 */ \
+    int launch_th_fused(const Geom &g, const ThermalParams &tp, const double *Fin, double *Fout,     \
+                        const double *Gin, double *Gout, const double *Fc_in, double *Fc_out,        \
+                        const int box[6], cudaStream_t s);                                           \
+    int launch_th_stream_macro(const Geom &g, const ThermalParams &tp, const double *Fin, double *F, \
+                               const double *Gin, double *G, const double *Fc_in, double *rho,       \
+                               double *u, double *v, double *w, double *T, cudaStream_t s);
+
+namespace strict { MGLC_DECLARE_LBM_LAUNCHERS MGLC_DECLARE_THERMAL_LAUNCHERS }
+namespace fast { MGLC_DECLARE_LBM_LAUNCHERS MGLC_DECLARE_THERMAL_LAUNCHERS }
 
 // exact (copy / order-preserving) kernels, built once with -fmad=false
 int launch_initial(const Geom &g, const LbmParams &p, double *F, double *rho, double *u, double *v,
@@ -95,11 +120,25 @@ int launch_check(const Geom &g, const double *u, const double *v, const double *
 // halo pack/unpack for one message (dir 0..5 faces, 7..18 edges), buffer layout [slot][t2][t1]
 int launch_pack(const Geom &g, const double *Fpost, int dir, double *buf, cudaStream_t s);
 int launch_unpack(const Geom &g, double *Fpost, int dir, const double *buf, cudaStream_t s);
-// AoS (reference layout) <-> SoA transposes over a linear cell range [c0, c0+ncells)
-int launch_aos_to_soa(const Geom &g, const double *aos_chunk, double *F, long long c0, long long ncells,
+// AoS (reference layout) <-> SoA transposes over a linear cell range [c0, c0+ncells); nq = 19 or 7
+int launch_aos_to_soa(const Geom &g, int nq, const double *aos_chunk, double *F, long long c0, long long ncells,
                       int with_halo, cudaStream_t s);
-int launch_soa_to_aos(const Geom &g, const double *F, double *aos_chunk, long long c0, long long ncells,
+int launch_soa_to_aos(const Geom &g, int nq, const double *F, double *aos_chunk, long long c0, long long ncells,
                       int with_halo, cudaStream_t s);
+// thermal exact kernels (B3): initial(), streamingT(), bouncebackT(), macro() with F/2, macroT(), check()
+int launch_th_initial(const Geom &g, const ThermalParams &tp, double *F, double *G, double *rho, double *u, double *v,
+                      double *w, double *T, cudaStream_t s);
+int launch_streamingT(const Geom &g, const double *Gpost, double *G, cudaStream_t s);
+int launch_bouncebackT(const Geom &g, const ThermalParams &tp, const double *Gpost, double *G, cudaStream_t s);
+int launch_th_macro(const Geom &g, const double *F, const double *Fc, double *rho, double *u, double *v, double *w,
+                    cudaStream_t s);
+int launch_macroT(const Geom &g, const double *G, double *T, cudaStream_t s);
+// partial[0..3] = sum |du|^2 (u,v,w), sum |u|^2, sum |dT|, sum |T|; then up,vp,wp,Tp <- u,v,w,T
+int launch_th_check(const Geom &g, const double *u, const double *v, const double *w, const double *T, double *up,
+                    double *vp, double *wp, double *Tp, double *partial4, cudaStream_t s);
+// g halo messages: face dir 0..5 carries the single population dir+1 (B3:1421-1468)
+int launch_pack_g(const Geom &g, const double *Gpost, int face, double *buf, cudaStream_t s);
+int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, cudaStream_t s);
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
 int check_scratch_doubles();
 void msg_dims(const Geom &g, int dir, int &n1, int &n2, int &npop);

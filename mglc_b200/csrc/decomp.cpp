@@ -3,6 +3,7 @@
 // computed without MPI.  Nothing here touches a GPU, so it is testable on a CPU-only machine.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 
 #include "../../include/mglc.h"
@@ -130,6 +131,32 @@ int mglc_lbm_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_zero
     }
     d->tau = U0 * (double)gn[0] / reynolds * 3.0 + 0.5;      // L3/commondata.f90:9
     d->U0 = U0; d->rho0 = rho0; d->device = 0;
+    return MGLC_OK;
+}
+
+int mglc_thermal_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_zero[3], int nranks, int rank,
+                           double rayleigh, double prandtl, double mach, double ekman) {
+    int rc = mglc_lbm_desc_init(d, gn, dims_or_zero, nranks, rank, 1.0, 0.0, 1.0);
+    if (rc) return rc;
+    if (!(rayleigh > 0.0) || !(prandtl > 0.0) || !(ekman > 0.0)) { set_error("mglc_thermal_desc_init: Ra, Pr, Ek must be positive"); return MGLC_E_INVALID; }
+    d->lattice = MGLC_D3Q19_D3Q7; d->collision = MGLC_MRT_THERMAL;
+    const double nz = (double)gn[2];
+    // module commondata, B3:33-47,73-74 (same operation order)
+    d->tau = 0.5 + mach * nz * sqrt(3.0 * prandtl / rayleigh);
+    const double viscosity = (d->tau - 0.5) / 3.0;
+    const double diffusivity = viscosity / prandtl;
+    d->omegaRot = viscosity / 2.0 / ekman / (double)(gn[2] * gn[2]);
+    d->paraA = 42.0 * sqrt(3.0) * diffusivity - 6.0;
+    const double gBeta1 = rayleigh * viscosity * diffusivity / nz;
+    d->gBeta = gBeta1 / (double)(gn[2] * gn[2]);
+    d->Thot = 1.0; d->Tcold = 0.0; d->Tref = 0.0;
+    d->Qd = 3.0 - sqrt(3.0);
+    d->Qnu = 4.0 * sqrt(3.0) - 6.0;
+    d->U0 = 0.0; d->rho0 = 1.0;
+    // benchmarkCavity: LeftRightWallsConstT (hot at j = 1), TopBottomPlatesAdiabatic, BackFrontWallsAdiabatic (B3:15-19)
+    const int shipped[6] = {MGLC_BCT_ADIABATIC, MGLC_BCT_ADIABATIC, MGLC_BCT_CONST_COLD, MGLC_BCT_CONST_HOT,
+                            MGLC_BCT_ADIABATIC, MGLC_BCT_ADIABATIC};
+    memcpy(d->bcT, shipped, sizeof shipped);
     return MGLC_OK;
 }
 

@@ -3,6 +3,7 @@
 // Built with -fmad=false so nothing is contracted; see lbm_kernels.inl for the collision kernels.
 #include "common.cuh"
 #include "d3q19_mrt.inl"
+#include "d3q19_thermal.inl"
 
 namespace mglc {
 
@@ -145,7 +146,7 @@ __global__ void k_check_final(int nblocks, double *__restrict__ part) {
     for (int b = 0; b < nblocks; ++b) { e1 += part[2 + 2 * b]; e2 += part[3 + 2 * b]; }
     part[0] = e1; part[1] = e2;
 }
-int check_scratch_doubles() { return 2 + 2 * CHECK_BLOCKS; }
+int check_scratch_doubles() { return 4 + 4 * CHECK_BLOCKS; }
 int launch_check(const Geom &g, const double *u, const double *v, const double *w, double *up, double *vp,
                  double *wp, double *part, cudaStream_t s) {
     const long long n = (long long)g.nx * g.ny * g.nz;
@@ -234,6 +235,7 @@ int launch_unpack(const Geom &g, double *Fpost, int dir, const double *buf, cuda
 // A block moves TILE consecutive cells (linear reference order) through shared memory so that both the
 // AoS side (19*TILE contiguous doubles) and the SoA side (TILE contiguous cells per population) coalesce.
 constexpr int TILE = 128;
+// NQ = populations per cell in the AoS array (19 for f / f_post, 7 for g / g_post)
 __device__ __forceinline__ long long soa_cell_index(const Geom &g, long long cell, int with_halo) {
     const int ex_ = with_halo ? 2 : 0;
     const long long lx = g.nx + ex_, ly = g.ny + ex_;
@@ -241,8 +243,10 @@ __device__ __forceinline__ long long soa_cell_index(const Geom &g, long long cel
     const int o = with_halo ? 0 : 1;
     return g.idx(0, i + o, j + o, k + o);
 }
+template <int NQ>
 __global__ void __launch_bounds__(256) k_aos_to_soa(Geom g, const double *__restrict__ aos, double *__restrict__ F,
                                                     long long c0, long long ncells, int with_halo) {
+    constexpr int Q = NQ;
     __shared__ double sm[TILE * Q];
     const long long t0 = (long long)blockIdx.x * TILE;
     const int nt = (int)min((long long)TILE, ncells - t0);
@@ -254,8 +258,10 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(Geom g, const double *__rest
         for (int a = threadIdx.x / TILE; a < Q; a += blockDim.x / TILE) F[a * g.sq + c] = sm[t * Q + a];
     }
 }
+template <int NQ>
 __global__ void __launch_bounds__(256) k_soa_to_aos(Geom g, const double *__restrict__ F, double *__restrict__ aos,
                                                     long long c0, long long ncells, int with_halo) {
+    constexpr int Q = NQ;
     __shared__ double sm[TILE * Q];
     const long long t0 = (long long)blockIdx.x * TILE;
     const int nt = (int)min((long long)TILE, ncells - t0);
@@ -267,14 +273,194 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(Geom g, const double *__rest
     __syncthreads();
     for (int q = threadIdx.x; q < nt * Q; q += blockDim.x) aos[t0 * Q + q] = sm[q];
 }
-int launch_aos_to_soa(const Geom &g, const double *aos, double *F, long long c0, long long ncells, int with_halo,
+int launch_aos_to_soa(const Geom &g, int nq, const double *aos, double *F, long long c0, long long ncells, int with_halo,
                       cudaStream_t s) {
-    k_aos_to_soa<<<(unsigned)((ncells + TILE - 1) / TILE), 256, 0, s>>>(g, aos, F, c0, ncells, with_halo);
+    const unsigned nb = (unsigned)((ncells + TILE - 1) / TILE);
+    if (nq == 19) k_aos_to_soa<19><<<nb, 256, 0, s>>>(g, aos, F, c0, ncells, with_halo);
+    else k_aos_to_soa<7><<<nb, 256, 0, s>>>(g, aos, F, c0, ncells, with_halo);
     return 1;
 }
-int launch_soa_to_aos(const Geom &g, const double *F, double *aos, long long c0, long long ncells, int with_halo,
+int launch_soa_to_aos(const Geom &g, int nq, const double *F, double *aos, long long c0, long long ncells, int with_halo,
                       cudaStream_t s) {
-    k_soa_to_aos<<<(unsigned)((ncells + TILE - 1) / TILE), 256, 0, s>>>(g, F, aos, c0, ncells, with_halo);
+    const unsigned nb = (unsigned)((ncells + TILE - 1) / TILE);
+    if (nq == 19) k_soa_to_aos<19><<<nb, 256, 0, s>>>(g, F, aos, c0, ncells, with_halo);
+    else k_soa_to_aos<7><<<nb, 256, 0, s>>>(g, F, aos, c0, ncells, with_halo);
+    return 1;
+}
+
+// ==================== thermal double-distribution path (B3) ====================
+// initial(), B3:409-638: rho = 1, u = 0, T = 0 except the layer next to a constant-temperature y or z wall
+// (B3:542-587), f = feq(rho,u), g = omegaT * T * (1 + 21/(6+paraA) e.u)
+__global__ void k_th_initial(Geom g, ThermalParams tp, double *__restrict__ F, double *__restrict__ G,
+                             double *__restrict__ rho, double *__restrict__ u, double *__restrict__ v,
+                             double *__restrict__ w, double *__restrict__ T) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    double Tc = 0.0;
+    // same order as the reference: y walls (hot side first), then z walls
+    if (g.wall[3] && j == 1 && tp.bcT[3]) Tc = tp.bcT[3] == MGLC_BCT_CONST_HOT ? tp.Thot : tp.Tcold;
+    if (g.wall[2] && j == g.ny && tp.bcT[2]) Tc = tp.bcT[2] == MGLC_BCT_CONST_HOT ? tp.Thot : tp.Tcold;
+    if (g.wall[5] && k == 1 && tp.bcT[5]) Tc = tp.bcT[5] == MGLC_BCT_CONST_HOT ? tp.Thot : tp.Tcold;
+    if (g.wall[4] && k == g.nz && tp.bcT[4]) Tc = tp.bcT[4] == MGLC_BCT_CONST_HOT ? tp.Thot : tp.Tcold;
+    const double r0 = 1.0, uu = 0.0, vv = 0.0, ww = 0.0;
+    const long long m = g.cell(i, j, k), c = g.idx(0, i, j, k);
+    rho[m] = r0; u[m] = uu; v[m] = vv; w[m] = ww; T[m] = Tc;
+    const double us2 = uu * uu + vv * vv + ww * ww;
+#pragma unroll
+    for (int a = 0; a < Q; ++a) {
+        const double omega = (a == 0) ? 1.0 / 3.0 : (a < 7 ? 1.0 / 18.0 : 1.0 / 36.0);
+        const double un = uu * (double)c_ex[a] + vv * (double)c_ey[a] + ww * (double)c_ez[a];
+        F[a * g.sq + c] = r0 * omega * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+    }
+#pragma unroll
+    for (int a = 0; a < QT; ++a) {
+        const double omegaT = (a == 0) ? (1.0 - tp.paraA) / 7.0 : (tp.paraA + 6.0) / 42.0;
+        const double unT = uu * (double)c_ex[a] + vv * (double)c_ey[a] + ww * (double)c_ez[a];
+        G[a * g.sq + c] = omegaT * Tc * (1.0 + 21.0 / (6.0 + tp.paraA) * unT);
+    }
+}
+int launch_th_initial(const Geom &g, const ThermalParams &tp, double *F, double *G, double *rho, double *u, double *v,
+                      double *w, double *T, cudaStream_t s) {
+    k_th_initial<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, tp, F, G, rho, u, v, w, T);
+    return 1;
+}
+
+// streamingT(), B3:1075-1098
+__global__ void __launch_bounds__(128) k_streamingT(Geom g, const double *__restrict__ Gpost, double *__restrict__ G) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j, k);
+#pragma unroll
+    for (int a = 0; a < QT; ++a) G[a * g.sq + c] = Gpost[a * g.sq + c - c_ez[a] * g.sz - c_ey[a] * g.sy - c_ex[a]];
+}
+int launch_streamingT(const Geom &g, const double *Gpost, double *G, cudaStream_t s) {
+    k_streamingT<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, Gpost, G);
+    return 1;
+}
+
+// bouncebackT(), B3:1100-1210, in place on g after streamingT: one population per wall face
+__global__ void k_bouncebackT(Geom g, ThermalParams tp, const double *__restrict__ Gpost, double *__restrict__ G) {
+    const int face = blockIdx.y;
+    if (!g.wall[face]) return;
+    const int axis = face >> 1;
+    const int n1 = (axis == 0) ? g.ny : g.nx, n2 = (axis == 2) ? g.ny : g.nz;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 * n2) return;
+    const int t1 = 1 + t % n1, t2 = 1 + t / n1;
+    const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz);
+    const int fix = (face & 1) ? 1 : nfix;
+    const int i = (axis == 0) ? fix : t1;
+    const int j = (axis == 1) ? fix : (axis == 0 ? t1 : t2);
+    const int k = (axis == 2) ? fix : t2;
+    const long long c = g.idx(0, i, j, k);
+    const int a = (face & 1) ? 2 * axis + 1 : 2 * axis + 2;      // population leaving the wall
+    const int o = (face & 1) ? 2 * axis + 2 : 2 * axis + 1;
+    const double raw = Gpost[o * g.sq + c];
+    G[a * g.sq + c] = tp.bcT[face] ? (-raw + tp.wallT[face]) : raw;
+}
+int launch_bouncebackT(const Geom &g, const ThermalParams &tp, const double *Gpost, double *G, cudaStream_t s) {
+    const int big = max(max(g.nx * g.ny, g.nx * g.nz), g.ny * g.nz);
+    k_bouncebackT<<<dim3((big + 127) / 128, 6), 128, 0, s>>>(g, tp, Gpost, G);
+    return 1;
+}
+
+// macro() with the half-force term, B3:986-1010; Fc = Fx,Fy,Fz back to back
+__global__ void __launch_bounds__(128) k_th_macro(Geom g, const double *__restrict__ F, const double *__restrict__ Fc,
+                                                  double *__restrict__ rho, double *__restrict__ u,
+                                                  double *__restrict__ v, double *__restrict__ w) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j, k), m = g.cell(i, j, k), n = (long long)g.nx * g.ny * g.nz;
+    double f[19];
+#pragma unroll
+    for (int a = 0; a < Q; ++a) f[a] = F[a * g.sq + c];
+    double r, uu, vv, ww;
+    d3q19_macro_forced(f, Fc[m], Fc[n + m], Fc[2 * n + m], r, uu, vv, ww);
+    rho[m] = r; u[m] = uu; v[m] = vv; w[m] = ww;
+}
+int launch_th_macro(const Geom &g, const double *F, const double *Fc, double *rho, double *u, double *v, double *w,
+                    cudaStream_t s) {
+    k_th_macro<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, F, Fc, rho, u, v, w);
+    return 1;
+}
+// macroT(), B3:1215-1232
+__global__ void __launch_bounds__(128) k_macroT(Geom g, const double *__restrict__ G, double *__restrict__ T) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j, k);
+    double gq[7];
+#pragma unroll
+    for (int a = 0; a < QT; ++a) gq[a] = G[a * g.sq + c];
+    T[g.cell(i, j, k)] = d3q7_temperature(gq);
+}
+int launch_macroT(const Geom &g, const double *G, double *T, cudaStream_t s) {
+    k_macroT<<<grid3(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, G, T);
+    return 1;
+}
+
+// check(), B3:1236-1283: four sums (errorU WITH the w term here) + previous-field update
+__global__ void __launch_bounds__(256) k_th_check_partial(long long n, const double *__restrict__ u, const double *__restrict__ v,
+                                                          const double *__restrict__ w, const double *__restrict__ T,
+                                                          double *__restrict__ up, double *__restrict__ vp,
+                                                          double *__restrict__ wp, double *__restrict__ Tp,
+                                                          double *__restrict__ part) {
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const double a = u[q], b = v[q], c = w[q], t = T[q];
+        const double da = a - up[q], db = b - vp[q], dc = c - wp[q];
+        e[0] += da * da + db * db + dc * dc;
+        e[1] += a * a + b * b + c * c;
+        e[2] += fabs(t - Tp[q]);
+        e[3] += fabs(t);
+        up[q] = a; vp[q] = b; wp[q] = c; Tp[q] = t;
+    }
+    __shared__ double sm[4][256];
+    for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] = e[q];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] += sm[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) part[4 + 4 * blockIdx.x + threadIdx.x] = sm[threadIdx.x][0];
+}
+__global__ void k_th_check_final(int nblocks, double *__restrict__ part) {
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = 0; b < nblocks; ++b) for (int q = 0; q < 4; ++q) e[q] += part[4 + 4 * b + q];
+    for (int q = 0; q < 4; ++q) part[q] = e[q];
+}
+int launch_th_check(const Geom &g, const double *u, const double *v, const double *w, const double *T, double *up, double *vp,
+                    double *wp, double *Tp, double *part, cudaStream_t s) {
+    const long long n = (long long)g.nx * g.ny * g.nz;
+    k_th_check_partial<<<CHECK_BLOCKS, 256, 0, s>>>(n, u, v, w, T, up, vp, wp, Tp, part);
+    k_th_check_final<<<1, 1, 0, s>>>(CHECK_BLOCKS, part);
+    return 2;
+}
+
+// g halo messages, B3:1421-1468: face `face` carries population face+1 of the last interior layer
+__global__ void k_pack_g(Geom g, const double *__restrict__ Gpost, int face, int n1, int n2, double *__restrict__ buf) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)n1 * n2) return;
+    int i, j, k;
+    msg_cell(g, face, 0, (int)(t % n1), (int)(t / n1), i, j, k);
+    buf[t] = Gpost[g.idx(face + 1, i, j, k)];
+}
+__global__ void k_unpack_g(Geom g, double *__restrict__ Gpost, int face, int n1, int n2, const double *__restrict__ buf) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)n1 * n2) return;
+    int i, j, k;
+    msg_cell(g, face, 1, (int)(t % n1), (int)(t / n1), i, j, k);
+    Gpost[g.idx(face + 1, i, j, k)] = buf[t];
+}
+int launch_pack_g(const Geom &g, const double *Gpost, int face, double *buf, cudaStream_t s) {
+    int n1, n2, npop;
+    msg_dims(g, face, n1, n2, npop);
+    k_pack_g<<<(unsigned)(((long long)n1 * n2 + 255) / 256), 256, 0, s>>>(g, Gpost, face, n1, n2, buf);
+    return 1;
+}
+int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, cudaStream_t s) {
+    int n1, n2, npop;
+    msg_dims(g, face, n1, n2, npop);
+    k_unpack_g<<<(unsigned)(((long long)n1 * n2 + 255) / 256), 256, 0, s>>>(g, Gpost, face, n1, n2, buf);
     return 1;
 }
 

@@ -21,6 +21,7 @@ struct Msg {
     int dir, send_to, recv_from;
     long long send_count, recv_count;
     double *sbuf, *rbuf;
+    int skip;            // 1 = leave this message out of the current exchange (e.g. g messages during f's)
 };
 
 #define MGLC_NCCL(call)                                                                        \
@@ -42,6 +43,7 @@ inline int halo_nccl_sendrecv(const Msg *msgs, int n, mglc_comm *comm, cudaStrea
     MGLC_NCCL(ncclGroupStart());
     for (int m = 0; m < n; ++m) {
         const Msg &M = msgs[m];
+        if (M.skip) continue;
         if (M.send_count) MGLC_NCCL(ncclSend(M.sbuf, (size_t)M.send_count, ncclDouble, M.send_to, comm->nccl, s));
         if (M.recv_count) MGLC_NCCL(ncclRecv(M.rbuf, (size_t)M.recv_count, ncclDouble, M.recv_from, comm->nccl, s));
     }
@@ -68,7 +70,8 @@ int halo_local_exchange(std::vector<Port> &ports, Pack pack, Unpack unpack) {
         MGLC_CUDA(cudaSetDevice(p.device));
         // the peers that copied out of my send buffers last time must be done before I overwrite them
         for (int m = 0; m < p.nmsgs; ++m)
-            if (p.msgs[m].send_count) MGLC_CUDA(cudaStreamWaitEvent(p.s, ports[p.msgs[m].send_to].ev_copied, 0));
+            if (p.msgs[m].send_count && !p.msgs[m].skip)
+                MGLC_CUDA(cudaStreamWaitEvent(p.s, ports[p.msgs[m].send_to].ev_copied, 0));
         MGLC_TRY(pack(r, p.s));
         MGLC_CUDA(cudaEventRecord(p.ev_packed, p.s));
     }
@@ -77,7 +80,7 @@ int halo_local_exchange(std::vector<Port> &ports, Pack pack, Unpack unpack) {
         MGLC_CUDA(cudaSetDevice(p.device));
         for (int m = 0; m < p.nmsgs; ++m) {
             Msg &M = p.msgs[m];
-            if (!M.recv_count) continue;
+            if (!M.recv_count || M.skip) continue;
             Port &src = ports[M.recv_from];
             MGLC_CUDA(cudaStreamWaitEvent(p.s, src.ev_packed, 0));
             MGLC_CUDA(cudaMemcpyPeerAsync(M.rbuf, p.device, src.msgs[m].sbuf, src.device,

@@ -11,6 +11,7 @@
 // one read and one write of the 19 populations: 304 B/cell.
 #include "common.cuh"
 #include "d3q19_mrt.inl"
+#include "d3q19_thermal.inl"
 
 namespace mglc {
 namespace MGLC_NS {
@@ -136,6 +137,8 @@ int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, do
     k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, Fin, F, rho_lid_in, rho, u, v, w);
     return 1;
 }
+
+#include "thermal_kernels.inl"
 
 }  // namespace MGLC_NS
 }  // namespace mglc

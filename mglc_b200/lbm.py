@@ -61,6 +61,27 @@ def make_desc(total, nranks=1, rank=0, dims=None, Re=1000.0, U0=0.1, rho0=1.0, a
     return d
 
 
+def make_thermal_desc(total, nranks=1, rank=0, dims=None, Rayleigh=1e6, Prandtl=0.71, Mach=0.1, Ekman=0.001, bcT=None,
+                      arith="fast", device=0, param_nz=None):
+    """Descriptor of the buoyancy-driven cavity the way B3's module commondata computes it (B3:26-47,73-74).
+    param_nz: evaluate tau, paraA, gBeta, omegaRot for a cavity of that height instead of total[2] (tests)."""
+    d = L.LbmDesc()
+    dz = (C.c_int * 3)(*(dims if dims else (0, 0, 0)))
+    L.check(L.lib().mglc_thermal_desc_init(C.byref(d), (C.c_int * 3)(*total), dz, nranks, rank, Rayleigh, Prandtl, Mach, Ekman))
+    if param_nz is not None:
+        q = L.LbmDesc()
+        L.check(L.lib().mglc_thermal_desc_init(C.byref(q), (C.c_int * 3)(1, 1, param_nz), (C.c_int * 3)(1, 1, 1), 1, 0,
+                                               Rayleigh, Prandtl, Mach, Ekman))
+        for k in ("tau", "paraA", "gBeta", "omegaRot"):
+            setattr(d, k, getattr(q, k))
+    d.arith = L.ARITH_STRICT if arith == "strict" else L.ARITH_FAST
+    d.device = device
+    if bcT is not None:
+        for q in range(6):
+            d.bcT[q] = bcT[q]
+    return d
+
+
 def halo_plan(desc):
     msgs = (L.HaloMsg * 18)()
     n = C.c_int()
@@ -128,6 +149,32 @@ class Subdomain:
         nx, ny, nz = self.n
         out = np.empty((19, nx + 2, ny + 2, nz + 2), order="F")
         L.check(L.lib().mglc_lbm_download_fpost(self._h, _ptr(out)))
+        return out
+
+    # ---- thermal handles ----
+    def upload_thermal(self, g=None, T=None, Fx=None, Fy=None, Fz=None):
+        nx, ny, nz = self.n
+        g = None if g is None else _farray(g, (7, nx, ny, nz), "g")
+        fields = [None if a is None else _farray(a, self.n, k) for k, a in zip("T Fx Fy Fz".split(), (T, Fx, Fy, Fz))]
+        L.check(L.lib().mglc_lbm_upload_thermal(self._h, _ptr(g), *[_ptr(a) for a in fields]))
+
+    def download_thermal(self, with_g=True):
+        out = {k: np.empty(self.n, order="F") for k in ("T", "Fx", "Fy", "Fz")}
+        g = np.empty((7,) + self.n, order="F") if with_g else None
+        L.check(L.lib().mglc_lbm_download_thermal(self._h, _ptr(g), *[_ptr(out[k]) for k in ("T", "Fx", "Fy", "Fz")]))
+        if with_g:
+            out["g"] = g
+        return out
+
+    def upload_gpost(self, g_post):
+        nx, ny, nz = self.n
+        gp = _farray(g_post, (7, nx + 2, ny + 2, nz + 2), "g_post")
+        L.check(L.lib().mglc_lbm_upload_gpost(self._h, _ptr(gp)))
+
+    def download_gpost(self):
+        nx, ny, nz = self.n
+        out = np.empty((7, nx + 2, ny + 2, nz + 2), order="F")
+        L.check(L.lib().mglc_lbm_download_gpost(self._h, _ptr(out)))
         return out
 
     def launch_count(self):
@@ -277,3 +324,84 @@ class LidDrivenCavity:
             sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
             R.upload(None if f is None else f[(slice(None),) + sl],
                      *[None if a is None else a[sl] for a in (rho, u, v, w)])
+
+
+class BuoyancyDrivenCavity(LidDrivenCavity):
+    """Thermal double-distribution cavity (D3Q19 MRT flow + D3Q7 MRT temperature, Boussinesq + Coriolis) on
+    B200(s); method names follow MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90:222-248."""
+
+    def __init__(self, total, nprocs=1, dims=None, Rayleigh=1e6, Prandtl=0.71, Mach=0.1, Ekman=0.001, bcT=None,
+                 arith="fast", device=0, devices=None, comm=None, param_nz=None):
+        lib = L.lib()
+        self.total = tuple(total)
+        self._group = self._single = None
+        self._comm = comm
+        mk = lambda nr, r, dev: make_thermal_desc(total, nr, r, dims, Rayleigh, Prandtl, Mach, Ekman, bcT, arith, dev, param_nz)
+        if comm is not None:
+            d = mk(comm.nranks, comm.rank, comm.device)
+            h = C.c_void_p()
+            L.check(lib.mglc_lbm_create(C.byref(h), C.byref(d), comm._h))
+            self._single, self.ranks, self.nprocs = h, [Subdomain(h)], comm.nranks
+        elif nprocs == 1:
+            d = mk(1, 0, device)
+            h = C.c_void_p()
+            L.check(lib.mglc_lbm_create(C.byref(h), C.byref(d), None))
+            self._single, self.ranks, self.nprocs = h, [Subdomain(h)], 1
+        else:
+            d = mk(nprocs, 0, device)
+            g = C.c_void_p()
+            dev = (C.c_int * nprocs)(*devices) if devices else None
+            L.check(lib.mglc_group_create(C.byref(g), C.byref(d), nprocs, dev))
+            self._group, self.ranks, self.nprocs = g, [], nprocs
+            for r in range(nprocs):
+                h = C.c_void_p()
+                L.check(lib.mglc_group_rank(g, r, C.byref(h)))
+                self.ranks.append(Subdomain(h))
+        self.desc = self.ranks[0].desc
+        self.dims = tuple(self.desc.dims)
+        self.tauf = self.desc.tau
+
+    # f side: collision / f_message_passing_sendrecv / streaming / bounceback / macro are inherited
+    def f_message_passing_sendrecv(self):
+        self.message_passing_sendrecv()
+
+    def collisionT(self):
+        self._call("mglc_collisionT", "mglc_group_collisionT")
+
+    def g_message_passing_sendrecv(self):
+        self._call("mglc_exchange_g", "mglc_group_exchange_g")
+
+    def streamingT(self):
+        self._call("mglc_streamingT", "mglc_group_streamingT")
+
+    def bouncebackT(self):
+        self._call("mglc_bouncebackT", "mglc_group_bouncebackT")
+
+    def macroT(self):
+        self._call("mglc_macroT", "mglc_group_macroT")
+
+    def check(self):
+        eu, et = C.c_double(), C.c_double()
+        self._call("mglc_check_thermal", "mglc_group_check_thermal", C.byref(eu), C.byref(et))
+        return eu.value, et.value
+
+    def gather(self, name):
+        if name in ("rho", "u", "v", "w", "f"):
+            return super().gather(name)
+        lead = (7,) if name == "g" else ()
+        out = np.empty(lead + self.total, order="F")
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            out[(slice(None),) * len(lead) + sl] = R.download_thermal(with_g=(name == "g"))[name]
+        return out
+
+    def gather_macro(self):
+        out = super().gather_macro()
+        out["T"] = self.gather("T")
+        return out
+
+    def scatter_thermal(self, g=None, T=None, Fx=None, Fy=None, Fz=None):
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            R.upload_thermal(None if g is None else g[(slice(None),) + sl],
+                             *[None if a is None else a[sl] for a in (T, Fx, Fy, Fz)])

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     src = open(os.path.join(ROOT, "include", "mglc.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mglc_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(mglc_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mglc.h but not exported by libmglc.so"
     assert set(names) == set(L.SIGNATURES), set(names) ^ set(L.SIGNATURES)
-    assert mg.lib().mglc_version() == 100
+    assert mg.lib().mglc_version() == 101
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -1,0 +1,221 @@
+"""GPU parity tests of the thermal double-distribution path (D3Q19 MRT + forcing, D3Q7 MRT temperature;
+BASELINE.json config 4): libmglc.so through the C ABI against the CPU oracle, the vectors machine-evaluated
+from the reference's Fortran source, and size-independent properties.
+
+Bars: initial, streaming(T), bounceback(T), macro(T), both exchanges bit-exact; collision(T) / step(N)
+bit-exact in MGLC_ARITH_STRICT and rho,u,v,w,T <= 1e-12 rel. L2 / <= 1e-10 max in MGLC_ARITH_FAST."""
+import os
+
+import numpy as np
+import pytest
+
+import mglc_b200 as mg
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_kernels.npz"))
+REL_L2, MAX_ABS = 1e-12, 1e-10
+FIELDS = ("rho", "u", "v", "w", "T")
+
+
+def rel_l2(a, b):
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def seeded_state(total, seed):
+    rng = np.random.default_rng(seed)
+    rho = np.asfortranarray(1.0 + 0.01 * rng.uniform(-1, 1, total))
+    u, v, w = (np.asfortranarray(0.03 * rng.uniform(-1, 1, total)) for _ in range(3))
+    T = np.asfortranarray(rng.uniform(0, 1, total))
+    f = np.asfortranarray(orc.feq(rho, u, v, w) * (1 + 0.01 * rng.uniform(-1, 1, (19,) + tuple(total))))
+    g = np.asfortranarray(T[None] / 7.0 * (1 + 0.2 * rng.uniform(-1, 1, (7,) + tuple(total))))
+    return dict(f=f, g=g, rho=rho, u=u, v=v, w=w, T=T)
+
+
+def worlds(total, nprocs=1, dims=None, seed=None, arith="strict", bcT=None, **kw):
+    wd = orc.ThermalWorld(total, nprocs, dims, bcT=bcT, **kw)
+    sim = mg.BuoyancyDrivenCavity(total, nprocs=nprocs, dims=dims, arith=arith, bcT=bcT, **kw)
+    wd.initial(); sim.initial()
+    if seed is not None:
+        st = seeded_state(total, seed)
+        for k, a in st.items():
+            wd.scatter(k, a)
+        sim.scatter(st["f"], st["rho"], st["u"], st["v"], st["w"])
+        sim.scatter_thermal(g=st["g"], T=st["T"])
+    return wd, sim
+
+
+def assert_state_equal(sim, wd, names=FIELDS + ("f", "g", "Fx", "Fy", "Fz")):
+    for k in names:
+        assert np.array_equal(sim.gather(k), wd.gather(k)), k
+
+
+def test_descriptor_matches_reference_module_parameters():
+    P = dict(zip([str(n) for n in GOLD["th_params/names"]], GOLD["th_params/values"]))
+    d = mg.make_thermal_desc((51, 51, 51))
+    for mine, ref in [("tau", "tauf"), ("paraA", "paraa"), ("gBeta", "gbeta"), ("omegaRot", "omegaratating"), ("Qd", "qd"), ("Qnu", "qnu")]:
+        assert getattr(d, mine) == P[ref], mine
+
+
+def test_initial_bit_exact():
+    for nprocs in (1, 4):
+        wd, sim = worlds((12, 9, 7), nprocs)
+        assert_state_equal(sim, wd, FIELDS + ("f", "g"))
+        for R, S in zip(wd.ranks, sim.ranks):
+            assert np.all(S.download_fpost() == 0.0) and np.all(S.download_gpost() == 0.0)
+        wd.close(); sim.close()
+
+
+def test_strict_kernels_match_reference_source_vectors():
+    """GPU collision (+force), macro, collisionT against the machine-evaluated Fortran text, every bit."""
+    n = GOLD["th_collision/f"].shape[0]
+    sim = mg.BuoyancyDrivenCavity((n, 1, 1), arith="strict", param_nz=51)
+    S = sim.ranks[0]
+    s = GOLD["th_collision/ruvwT"]
+    col = lambda a: np.asfortranarray(a.reshape(n, 1, 1))
+    S.upload(f=np.asfortranarray(GOLD["th_collision/f"].T.reshape(19, n, 1, 1)), rho=col(s[:, 0]), u=col(s[:, 1]), v=col(s[:, 2]), w=col(s[:, 3]))
+    S.upload_thermal(T=col(s[:, 4]))
+    sim.collision()
+    got = S.download_fpost()[:, 1:n + 1, 1, 1]
+    assert np.array_equal(got.T, GOLD["th_collision/f_post"])
+    th = S.download_thermal(with_g=False)
+    assert np.array_equal(np.stack([th[k][:, 0, 0] for k in ("Fx", "Fy", "Fz")], axis=1), GOLD["th_collision/F"])
+    # macro() with the golden force
+    Fv = GOLD["th_macro/F"]
+    S.upload_thermal(Fx=col(Fv[:, 0]), Fy=col(Fv[:, 1]), Fz=col(Fv[:, 2]))
+    sim.macro()
+    m = S.download_macro()
+    assert np.array_equal(np.stack([m[k][:, 0, 0] for k in ("rho", "u", "v", "w")], axis=1), GOLD["th_macro/ruvw"])
+    # collisionT()
+    s = GOLD["th_collisionT/uvwT"]
+    S.upload(u=col(s[:, 0]), v=col(s[:, 1]), w=col(s[:, 2]))
+    S.upload_thermal(g=np.asfortranarray(GOLD["th_collisionT/g"].T.reshape(7, n, 1, 1)), T=col(s[:, 3]))
+    sim.collisionT()
+    assert np.array_equal(S.download_gpost()[:, 1:n + 1, 1, 1].T, GOLD["th_collisionT/g_post"])
+    sim.close()
+
+
+def test_fast_collision_close_to_reference_source_vectors():
+    n = GOLD["th_collision/f"].shape[0]
+    sim = mg.BuoyancyDrivenCavity((n, 1, 1), arith="fast", param_nz=51)
+    S = sim.ranks[0]
+    s = GOLD["th_collision/ruvwT"]
+    col = lambda a: np.asfortranarray(a.reshape(n, 1, 1))
+    S.upload(f=np.asfortranarray(GOLD["th_collision/f"].T.reshape(19, n, 1, 1)), rho=col(s[:, 0]), u=col(s[:, 1]), v=col(s[:, 2]), w=col(s[:, 3]))
+    S.upload_thermal(T=col(s[:, 4]))
+    sim.collision()
+    assert np.abs(S.download_fpost()[:, 1:n + 1, 1, 1].T - GOLD["th_collision/f_post"]).max() < 1e-15
+    s = GOLD["th_collisionT/uvwT"]
+    S.upload(u=col(s[:, 0]), v=col(s[:, 1]), w=col(s[:, 2]))
+    S.upload_thermal(g=np.asfortranarray(GOLD["th_collisionT/g"].T.reshape(7, n, 1, 1)), T=col(s[:, 3]))
+    sim.collisionT()
+    assert np.abs(S.download_gpost()[:, 1:n + 1, 1, 1].T - GOLD["th_collisionT/g_post"]).max() < 1e-15
+    sim.close()
+
+
+@pytest.mark.parametrize("bcT", [None, [0, 0, 0, 0, 2, 1], [0] * 6])      # shipped cavity, RB convection set, all adiabatic
+def test_unfused_subroutines_bit_exact(bcT):
+    total = (18, 11, 9)
+    wd, sim = worlds(total, 1, seed=21, bcT=bcT)
+    for name in ("collision", "f_message_passing_sendrecv", "streaming", "bounceback", "collisionT",
+                 "g_message_passing_sendrecv", "streamingT", "bouncebackT", "macro", "macroT"):
+        getattr(wd, name)(); getattr(sim, name)()
+        assert_state_equal(sim, wd)
+    nx, ny, nz = total
+    inner = (slice(None), slice(1, nx + 1), slice(1, ny + 1), slice(1, nz + 1))
+    assert np.array_equal(sim.ranks[0].download_fpost()[inner], wd.ranks[0].f_post[inner])
+    assert np.array_equal(sim.ranks[0].download_gpost()[inner], wd.ranks[0].g_post[inner])
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("total,nsteps", [((13, 11, 9), 1), ((13, 11, 9), 2), ((13, 11, 9), 25), ((40, 9, 17), 10)])
+def test_fused_step_strict_is_bit_exact(total, nsteps):
+    wd, sim = worlds(total, 1, seed=5)
+    wd.step(nsteps); sim.step(nsteps)
+    assert_state_equal(sim, wd)
+    wd.step(3); sim.step(3)            # a second call continues from the rotated state
+    assert_state_equal(sim, wd)
+    assert sim.check() == wd.check()
+    wd.close(); sim.close()
+
+
+def test_unfused_sequence_equals_fused_step_fast():
+    total = (20, 12, 9)
+    _, a = worlds(total, 1, seed=3, arith="fast")
+    _, b = worlds(total, 1, seed=3, arith="fast")
+    for _ in range(4):
+        for name in ("collision", "f_message_passing_sendrecv", "streaming", "bounceback", "collisionT",
+                     "g_message_passing_sendrecv", "streamingT", "bouncebackT", "macro", "macroT"):
+            getattr(a, name)()
+    b.step(4)
+    for k in FIELDS + ("f", "g", "Fx", "Fy", "Fz"):
+        assert np.array_equal(a.gather(k), b.gather(k)), k
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("nsteps", [1, 10, 100, 2000])
+def test_config4_parity_51cubed_fast_within_tolerance(nsteps):
+    """The shipped problem: 51^3, Ra = 1e6, Pr = 0.71, Ma = 0.1, Ek = 1e-3, from initial()."""
+    total = (51, 51, 51)
+    wd, sim = worlds(total, 1, arith="fast")
+    wd.step(nsteps); sim.step(nsteps)
+    for k in FIELDS:
+        a, b = sim.gather(k), wd.gather(k)
+        assert rel_l2(a, b) <= REL_L2 and np.abs(a - b).max() <= MAX_ABS, (k, rel_l2(a, b), np.abs(a - b).max())
+    eu, et = sim.check(); ou, ot = wd.check()
+    assert np.isclose(eu, ou, rtol=1e-9) and np.isclose(et, ot, rtol=1e-9)
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (8, None), (6, None), (3, (1, 3, 1)), (4, (1, 1, 4))])
+def test_decomposition_invariance_and_exchange_bit_exact(nprocs, dims):
+    total = (13, 11, 9)
+    wd, sim = worlds(total, nprocs, dims, seed=9)
+    # exchange of both population sets: every halo value, bit for bit
+    wd.collision(); sim.collision(); wd.collisionT(); sim.collisionT()
+    wd.f_message_passing_sendrecv(); sim.f_message_passing_sendrecv()
+    wd.g_message_passing_sendrecv(); sim.g_message_passing_sendrecv()
+    for R, S in zip(wd.ranks, sim.ranks):
+        assert np.array_equal(S.download_fpost(), R.f_post)
+        assert np.array_equal(S.download_gpost(), R.g_post)
+    wd.close(); sim.close()
+    one, _ = worlds(total, 1, seed=9)
+    _, many = worlds(total, nprocs, dims, seed=9)
+    one.step(12); many.step(12)
+    assert_state_equal(many, one)
+    one.close(); many.close()
+
+
+def test_config4_51cubed_2x2x2_fast_matches_oracle():
+    total = (51, 51, 51)
+    wd, sim = worlds(total, 8, arith="fast")
+    wd.step(200); sim.step(200)
+    for k in FIELDS:
+        a, b = sim.gather(k), wd.gather(k)
+        assert rel_l2(a, b) <= REL_L2 and np.abs(a - b).max() <= MAX_ABS, k
+    wd.close(); sim.close()
+
+
+def test_full_size_256_block_properties():
+    """Config 4 block size per GPU (512^3 over 2x2x2): closed cavity conserves mass; with all walls adiabatic
+    total heat is conserved; temperatures stay bounded."""
+    total = (256, 256, 256)
+    sim = mg.BuoyancyDrivenCavity(total, arith="fast")
+    sim.initial()
+    m0 = sim.gather("rho").sum()
+    sim.step(60)
+    rho, T = sim.gather("rho"), sim.gather("T")
+    assert abs(rho.sum() - m0) / m0 < 1e-12
+    assert np.isfinite(T).all() and T.min() > -0.2 and T.max() < 1.2
+    assert T[:, 0, :].mean() > 0.9 and np.abs(sim.gather("w")).max() > 0.0
+    sim.close()
+    sim = mg.BuoyancyDrivenCavity(total, arith="fast", bcT=[0] * 6)
+    sim.initial()
+    rng = np.random.default_rng(0)
+    T0 = np.asfortranarray(rng.random(total))
+    p = sim.desc.paraA
+    g0 = np.asfortranarray(np.stack([T0 * ((1.0 - p) / 7.0 if a == 0 else (p + 6.0) / 42.0) for a in range(7)]))
+    sim.scatter_thermal(g=g0, T=T0)
+    sim.step(20)
+    assert abs(sim.gather("T").sum() - T0.sum()) / T0.sum() < 1e-12
+    sim.close()
