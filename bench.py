@@ -42,7 +42,9 @@ def parse_args():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="mglc", choices=["mglc", "reference"])
-    p.add_argument("--size", type=int, default=768, help="per-GPU block edge (weak) / global edge (strong)")
+    p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi"],
+                   help="lid = BASELINE.json's metric (default); thermal / jacobi = the other configs, for profiles/")
+    p.add_argument("--size", type=int, default=0, help="per-GPU block edge (weak) / global edge (strong); 0 = the workload's config size")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--arith", default="fast", choices=["fast", "strict"])
     p.add_argument("--no-e2e", action="store_true")
@@ -132,9 +134,10 @@ def host_mem_available():
     return 0
 
 
-def lattice_bytes(n):
+def lattice_bytes(n, thermal=False):
     px = ((n + 17 + 15) // 16) * 16
-    return 2 * 19 * px * (n + 2) * (n + 2) * 8 + 7 * n ** 3 * 8 + (1 << 28)
+    pops, fields = (2 * 26, 19) if thermal else (2 * 19, 7)
+    return pops * px * (n + 2) * (n + 2) * 8 + fields * n ** 3 * 8 + (1 << 28)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -206,9 +209,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    thermal = args.workload == "thermal"
+    if args.size == 0:
+        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512}[args.workload]
+    if args.workload == "jacobi":
+        import bench_jacobi
+        bench_jacobi.main(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
+        if thermal:
+            raise SystemExit("bench.py: --impl reference times the headline (lid) workload only")
         run_reference(args, rank)
         return
+    bytes_per_cell = 464 if thermal else BYTES_PER_CELL      # thermal: (19+7) x 16 B + 48 B of carried force
 
     import numpy as np
     import torch
@@ -248,7 +261,7 @@ def main():
     free, _ = torch.cuda.mem_get_info()
     per_gpu = [n, n, n] if args.scaling == "weak" else [n // d for d in dims]
     reduced = False
-    while lattice_bytes(max(per_gpu)) > free and n > 64:
+    while lattice_bytes(max(per_gpu), thermal) > free and n > 64:
         n -= 64
         per_gpu = [n, n, n] if args.scaling == "weak" else [n // d for d in dims]
         reduced = True
@@ -261,8 +274,9 @@ def main():
             dist.broadcast_object_list(box, src=0)
             return box[0]
         comm = mg.Communicator(world, rank, local_rank, bcast)
-    sim = mg.LidDrivenCavity(gn, comm=comm, arith=args.arith, device=local_rank) if comm else \
-        mg.LidDrivenCavity(gn, arith=args.arith, device=local_rank)
+    Driver = mg.BuoyancyDrivenCavity if thermal else mg.LidDrivenCavity
+    sim = Driver(gn, comm=comm, arith=args.arith, device=local_rank) if comm else \
+        Driver(gn, arith=args.arith, device=local_rank)
     sub = sim.ranks[0]
     cells_local = int(np.prod(sub.n))
     cells_total = int(np.prod(gn))
@@ -295,18 +309,19 @@ def main():
     barrier()
     peak, peak_src = hbm_peak()
     avg_ms = fms.value / max(1, fl.value)
-    achieved = BYTES_PER_CELL * cells_local / (avg_ms * 1e-3) / 1e9
-    tr = ncu_traffic(cells_local)
-    roofline = {"bound": "hbm", "kernel": "mglc::fast::k_fused" if args.arith == "fast" else "mglc::strict::k_fused",
+    achieved = bytes_per_cell * cells_local / (avg_ms * 1e-3) / 1e9
+    tr = None if thermal else ncu_traffic(cells_local)
+    kname = "k_th_fused" if thermal else "k_fused"
+    roofline = {"bound": "hbm", "kernel": f"mglc::{args.arith}::{kname}",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": cells_local,
+                "bytes_per_cell": bytes_per_cell, "cells_per_launch": cells_local,
                 "avg_launch_ms": round(avg_ms, 4), "launches_timed": fl.value,
                 "traffic_source": (tr or {}).get("source")}
 
     # ---- end to end through the C ABI with host arrays ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not thermal:
         e2e = run_e2e(args, sim, sub, lib, L, np, barrier, reduce_max, cells_local, cells_total, world)
 
     sim.close()
@@ -314,7 +329,7 @@ def main():
         comm.close()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not thermal:
         try:
             cpu = cpu_baseline(args.cpu_seconds)
         except Exception as ex:   # the baseline is a reported extra, never the product
@@ -325,10 +340,12 @@ def main():
             "metric": "MLUPS", "value": round(value, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"lid_driven_cavity_d3q19_mrt_{per_gpu[0]}x{per_gpu[1]}x{per_gpu[2]}_per_gpu",
-                       "global_lattice": list(gn), "decomposition": "x".join(map(str, dims)), "Re": 1000.0, "U0": 0.1,
+            "config": {"workload": ("buoyancy_driven_cavity_d3q19_d3q7_mrt" if thermal else "lid_driven_cavity_d3q19_mrt") +
+                                   f"_{per_gpu[0]}x{per_gpu[1]}x{per_gpu[2]}_per_gpu",
+                       "global_lattice": list(gn), "decomposition": "x".join(map(str, dims)),
+                       **({"Ra": 1e6, "Pr": 0.71, "Ma": 0.1, "Ek": 1e-3} if thermal else {"Re": 1000.0, "U0": 0.1}),
                        "arith": args.arith, "storage": "SoA fp64, ping-pong, 1-cell halo",
-                       "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (19 * cells_local * 8 / 1e9),
+                       "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % ((26 if thermal else 19) * cells_local * 8 / 1e9),
                        "reduced_to_fit": reduced, "wall_ms_per_step": round(wall_ms / args.steps, 4)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
