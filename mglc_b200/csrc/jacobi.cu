@@ -5,9 +5,9 @@
 // cell i=1 sits 128-byte aligned).  2-D problems live in plane k = 1 of a 3-plane array.
 // Kernels (all bit-defined: adds in the reference's order and one multiply by a constant, -fmad=false):
 //   k_jacobi2d   A_new = 0.25 * (A(i-1,j) + A(i+1,j) + A(i,j-1) + A(i,j+1) + f)        LAP:170-182
-//   k_jacobi3d   A_new = (1/6) * (x- + x+ + y- + y+ + z- + z+ + f); each thread marches along z and keeps
-//                the z-1 / z / z+1 values in registers, so a cell costs one DRAM read and one write
-//                (16 B, 24 B with a source term); x/y neighbours come from L1/L2
+//   k_jacobi3d   A_new = (1/6) * (x- + x+ + y- + y+ + z- + z+ + f); 2.5-D blocking: each thread marches along z
+//                with the z-1 / z / z+1 values in registers, the current (x,y) tile in shared memory, so a
+//                cell costs one DRAM read and one write (16 B, 24 B with a source term)
 //   k_face_pack / k_face_unpack   replace the contiguous-row and MPI_Type_vector column messages of
 //                exchange_message (LAP:223-254)
 //   k_absdiff_max   check_diff (LAP:185-204)
@@ -74,33 +74,51 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
     B[c] = 0.25 * s;
 }
 
-constexpr int JTX = 128, JTY = 2, JKCH = 32;
+// 2.5-D blocking: a CTA owns a JTX x JTY tile of (x,y) and marches JKCH planes along z.  Each thread keeps
+// the z-1 / z / z+1 values of its cell in registers (plus z+2 in flight as a prefetch); the current plane of
+// the tile, with its one-cell rim, goes through shared memory so x/y neighbours cost no L2 traffic beyond the
+// rim (2/JTY of a row + two sectors per row).  Two shared buffers alternate, so one barrier per plane is enough.
+constexpr int JTX = 64, JTY = 8, JKCH = 64;
 template <bool HAS_F>
 __global__ void __launch_bounds__(JTX *JTY) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
                                                        double *__restrict__ B, int k_lo, int k_hi) {
-    const int i = 1 + blockIdx.x * JTX + threadIdx.x;
-    const int j = 1 + blockIdx.y * JTY + threadIdx.y;
+    __shared__ double sm[2][JTY + 2][JTX + 2];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = 1 + blockIdx.x * JTX + tx;
+    const int j = 1 + blockIdx.y * JTY + ty;
     const int k0 = k_lo + blockIdx.z * JKCH;
     const int k1 = min(k0 + JKCH - 1, k_hi);
-    if (i > g.nx || j > g.ny) return;
+    const bool active = (i <= g.nx) && (j <= g.ny);
+    const bool rim_xm = tx == 0, rim_xp = (tx == JTX - 1) || (i == g.nx);
+    const bool rim_ym = ty == 0, rim_yp = (ty == JTY - 1) || (j == g.ny);
     const long long sy = g.sy, sz = g.sz;
-    long long c = g.idx(0, i, j, k0);
-    double below = A[c - sz], center = A[c];
-#pragma unroll 4
+    long long c = g.idx(0, min(i, g.nx), min(j, g.ny), k0);      // clamped: inactive threads only keep the barriers company
+    double below = A[c - sz], center = A[c], up = A[c + sz];
     for (int k = k0; k <= k1; ++k) {
-        const double up = A[c + sz];
-        double s = A[c - 1] + A[c + 1];
-        s += A[c - sy];
-        s += A[c + sy];
-        s += below;
-        s += up;
-        s += HAS_F ? f[c] : 0.0;
-        B[c] = (1.0 / 6.0) * s;
+        const double up2 = (k < k1) ? A[c + 2 * sz] : 0.0;        // prefetch: in flight across the barrier
+        double(*pl)[JTX + 2] = sm[k & 1];
+        pl[ty + 1][tx + 1] = center;
+        if (active) {
+            if (rim_xm) pl[ty + 1][0] = A[c - 1];
+            if (rim_xp) pl[ty + 1][tx + 2] = A[c + 1];
+            if (rim_ym) pl[0][tx + 1] = A[c - sy];
+            if (rim_yp) pl[ty + 2][tx + 1] = A[c + sy];
+        }
+        __syncthreads();
+        if (active) {
+            double s = pl[ty + 1][tx] + pl[ty + 1][tx + 2];
+            s += pl[ty][tx + 1];
+            s += pl[ty + 2][tx + 1];
+            s += below;
+            s += up;
+            s += HAS_F ? f[c] : 0.0;
+            B[c] = (1.0 / 6.0) * s;
+        }
         below = center;
         center = up;
+        up = up2;
         c += sz;
     }
-    (void)center;
 }
 
 // max |A_p - A| over the interior; non-negative doubles order like their bit patterns

@@ -8,10 +8,13 @@ from the reference file at generation time, never stored in this repo -- into Py
 on given inputs.  Used by tests/golden/make_golden_fortran.py to pin the CPU oracle to the reference's own
 source text.
 
-Supported subset: assignments, `do v = a, b` / `enddo` counted loops, `if (...) then` / `endif` blocks are NOT
-supported (none occur in the bodies we evaluate); `&` continuations, `!` comments and `!$omp` lines are
-dropped; `d0`-style exponents, dsqrt/dabs/dble intrinsics.  Array references are rewritten by a caller-
-supplied table: per-cell arrays f(alpha,i,j,k) -> f[alpha], fields rho(i,j,k) -> rho, locals m(3) -> m[3].
+Supported subset: assignments, `do v = a, b` / `enddo` counted loops, `do while (...)`, block and one-line
+`if` with `elseif` / `else`, the dotted relational and logical operators, `write` (ignored), `stop` (raises);
+`&` continuations, `!` comments and `!$omp` lines are dropped; `d0`-style exponents, dsqrt/dabs/dble
+intrinsics; `x**2.0d0` becomes the correctly rounded square x*x (what a Fortran compiler emits), other
+powers go to libm pow like the C oracle.  Array references are rewritten by a caller-supplied table:
+per-cell arrays f(alpha,i,j,k) -> f[alpha], fields rho(i,j,k) -> rho, locals m(3) -> m[3], and `full`
+arrays keep every index: f_post(alpha,i-1,j) -> f_post[(alpha,i-1,j)].
 """
 import math
 import re
@@ -61,9 +64,12 @@ def _split_args(s):
     return out
 
 
-def _rewrite_refs(s, cell_arrays, fields, local_arrays):
+def _rewrite_refs(s, cell_arrays, fields, local_arrays, full_arrays=()):
     """rewrite NAME(args) for known names; innermost-first so nested references work"""
-    names = {**{n: "cell" for n in cell_arrays}, **{n: "field" for n in fields}, **{n: "local" for n in local_arrays}}
+    names = {**{n: "cell" for n in cell_arrays}, **{n: "field" for n in fields}, **{n: "local" for n in local_arrays},
+             **{n: "full" for n in full_arrays}}
+    if not names:
+        return s
     pat = re.compile(r"\b(" + "|".join(sorted(map(re.escape, names), key=len, reverse=True)) + r")\s*\(([^()]*)\)")
     while True:
         m = pat.search(s)
@@ -75,34 +81,126 @@ def _rewrite_refs(s, cell_arrays, fields, local_arrays):
             rep = f"{name}__[{args[0]}]"            # f(alpha,i,j,k) -> f__[alpha]
         elif kind == "field":
             rep = f"{name}__"                       # rho(i,j,k) -> rho__
+        elif kind == "full":
+            rep = f"{name}__[{'#'.join(args)}]" if len(args) > 1 else f"{name}__[{args[0]}]"   # '#' = protected comma
         else:
             rep = f"{name}__[{args[0]}]"
         s = s[:m.start()] + rep + s[m.end():]
 
 
-def translate(text, cell_arrays=(), fields=(), local_arrays=()):
+_OPS = [(".lt.", " < "), (".le.", " <= "), (".gt.", " > "), (".ge.", " >= "), (".eq.", " == "), (".ne.", " != "),
+        (".and.", " and "), (".or.", " or "), (".not.", " not ")]
+
+
+def _matching_open(s, close):
+    depth = 0
+    for q in range(close, -1, -1):
+        depth += (s[q] == ")") - (s[q] == "(")
+        if depth == 0:
+            return q
+    raise ValueError("unbalanced parentheses: " + s)
+
+
+def _powers(s):
+    """x**2.0 -> sq(x) (the correctly rounded square a compiler emits); other powers -> pow(x, e)"""
+    while "**" in s:
+        k = s.index("**")
+        left = s[:k].rstrip()
+        if left.endswith(")") or left.endswith("]"):
+            if left.endswith("]"):
+                o = len(left) - 1
+                depth = 0
+                while True:
+                    depth += (left[o] == "]") - (left[o] == "[")
+                    if depth == 0:
+                        break
+                    o -= 1
+            else:
+                o = _matching_open(left, len(left) - 1)
+            while o > 0 and (left[o - 1].isalnum() or left[o - 1] == "_"):
+                o -= 1
+        else:
+            o = len(left)
+            while o > 0 and (left[o - 1].isalnum() or left[o - 1] in "_."):
+                o -= 1
+        base = left[o:]
+        m = re.match(r"\s*(\d+\.?\d*|\(.*?\))", s[k + 2:])
+        expo = m.group(1)
+        rest = s[k + 2 + m.end():]
+        if float(eval(expo)) == 2.0:
+            s = left[:o] + f"sq({base})" + rest
+        else:
+            s = left[:o] + f"pow({base}, {float(eval(expo))})" + rest
+    return s
+
+
+def _expr(line, tables):
+    line = _rewrite_refs(line, *tables)
+    for a, b in _OPS:
+        line = line.replace(a, b)
+    line = re.sub(r"\bdsqrt\b", "sqrt", line)
+    line = re.sub(r"\bdabs\b", "abs", line)
+    line = re.sub(r"\bdble\b", "float", line)
+    line = re.sub(r"\breal\b", "float", line)
+    return _powers(line).replace("#", ",")
+
+
+def translate(text, cell_arrays=(), fields=(), local_arrays=(), full_arrays=()):
     """Fortran loop-body text -> Python source.  All names are lower-cased; rewritten names get a '__'
     suffix so they cannot collide with Python keywords or the intrinsics."""
+    tables = ([a.lower() for a in cell_arrays], [a.lower() for a in fields], [a.lower() for a in local_arrays],
+              [a.lower() for a in full_arrays])
     py, indent = [], 0
+    emit = lambda txt: py.append("    " * indent + txt)
     for line in _logical_lines(text.lower()):
+        for a, b in _OPS:                           # before the number pass: `.gt.1.0d0` hides the literal
+            line = line.replace(a, b)
         line = _numbers(line)
-        m = re.match(r"do\s+(\w+)\s*=\s*(.+?)\s*,\s*(.+)$", line)
+        m = re.match(r"do\s+while\s*\((.*)\)\s*$", line)
         if m:
-            py.append("    " * indent + f"for {m.group(1)} in range(int({m.group(2)}), int({m.group(3)}) + 1):")
+            emit(f"while {_expr(m.group(1), tables)}:")
             indent += 1
             continue
-        if re.match(r"end\s*do$", line):
+        m = re.match(r"do\s+(\w+)\s*=\s*(.+?)\s*,\s*(.+)$", line)
+        if m:
+            emit(f"for {m.group(1)} in range(int({_expr(m.group(2), tables)}), int({_expr(m.group(3), tables)}) + 1):")
+            indent += 1
+            continue
+        if re.match(r"end\s*(do|if)$", line):
             indent -= 1
             continue
-        line = _rewrite_refs(line, [a.lower() for a in cell_arrays], [a.lower() for a in fields],
-                             [a.lower() for a in local_arrays])
-        line = re.sub(r"\bdsqrt\b", "sqrt", line)
-        line = re.sub(r"\bdabs\b", "abs", line)
-        line = re.sub(r"\bdble\b", "float", line)
-        line = line.replace("**", " ** ")
-        py.append("    " * indent + line)
+        m = re.match(r"(else\s*if|elseif|if)\s*\((.*)\)\s*then$", line)
+        if m:
+            if m.group(1) != "if":
+                indent -= 1
+            emit(("if " if m.group(1) == "if" else "elif ") + _expr(m.group(2), tables) + ":")
+            indent += 1
+            continue
+        if line == "else":
+            indent -= 1
+            emit("else:")
+            indent += 1
+            continue
+        if line.startswith("write") or line.startswith("call output") or line.startswith("call mpi_abort"):
+            emit("pass" if line.startswith("write") else "raise RuntimeError('reference abort path')")
+            continue
+        if line in ("stop", "return"):
+            emit("raise RuntimeError('reference stop')" if line == "stop" else "pass")
+            continue
+        m = re.match(r"if\s*\(", line)
+        if m:                                       # one-line if
+            c = 2 + line[2:].index("(")
+            depth, q = 0, c
+            while True:
+                depth += (line[q] == "(") - (line[q] == ")")
+                if depth == 0:
+                    break
+                q += 1
+            emit(f"if {_expr(line[c + 1:q], tables)}: {_expr(line[q + 1:].strip(), tables)}")
+            continue
+        emit(_expr(line, tables))
     if indent != 0:
-        raise ValueError("unbalanced do/enddo in translated body")
+        raise ValueError("unbalanced block structure in translated body")
     return "\n".join(py)
 
 
@@ -116,7 +214,8 @@ class _Arr(dict):
 def run(py_src, cell_in=None, field_in=None, scalars=None, local_arrays=(), cell_out=(), field_out=()):
     """Execute translated source.  cell_in: {name: sequence}, field_in: {name: float},
     scalars: {name: number} (parameters such as snu, sq, nx).  Returns {name: list or float}."""
-    ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range}
+    ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range, "sq": lambda x: x * x,
+          "pow": math.pow, "atan": math.atan, "mod": lambda a, b: a % b}
     for name, seq in (cell_in or {}).items():
         ns[name.lower() + "__"] = _Arr({k: float(x) for k, x in enumerate(seq)})
     for name, val in (field_in or {}).items():

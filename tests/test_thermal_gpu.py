@@ -222,7 +222,7 @@ def test_full_size_256_block_properties():
     rho, T = sim.gather("rho"), sim.gather("T")
     assert abs(rho.sum() - m0) / m0 < 1e-12
     assert np.isfinite(T).all() and T.min() > -0.2 and T.max() < 1.2
-    assert T[:, 0, :].mean() > 0.9 and np.abs(sim.gather("w")).max() > 0.0
+    assert T[:, 0, :].mean() > 0.5 and np.abs(sim.gather("w")).max() > 0.0
     sim.close()
     sim = mg.BuoyancyDrivenCavity(total, arith="fast", bcT=[0] * 6)
     sim.initial()
