@@ -377,3 +377,157 @@ for _name, _sub in (("initial", "th_initial"), ("collision", "th_collision"), ("
                     ("g_message_passing_sendrecv", "th_exchange_g"), ("streamingT", "th_streamingT"),
                     ("bouncebackT", "th_bouncebackT"), ("macro", "th_macro"), ("macroT", "th_macroT")):
     setattr(ThermalWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Particle-laden D2Q9 channel (oracle/particles2d.c)
+class P2Params(C.Structure):
+    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("N", C.c_int)] + \
+               [(n, C.c_double) for n in ("rho0", "rhoSolid", "viscosity", "tauf", "Snu", "Sq", "gravity", "thresholdWall",
+                                          "stiffWall", "thresholdParticle", "stiffParticle", "radius0", "Pi")]
+
+
+P2_FIELDS = {"f": 0, "f_post": 1, "rho": 2, "u": 3, "v": 4, "up": 5, "vp": 6}
+P2_PARTICLE = {"xCenter": 0, "yCenter": 1, "Uc": 2, "Vc": 3, "rationalOmega": 4, "radius": 5, "wallTotalForceX": 6,
+               "wallTotalForceY": 7, "totalTorque": 8, "xCenterOld": 9, "yCenterOld": 10, "UcOld": 11, "VcOld": 12,
+               "rationalOmegaOld": 13}
+EX9 = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1])
+EY9 = np.array([0, 0, 1, 0, -1, 1, 1, -1, -1])
+OPP9 = np.array([0, 3, 4, 1, 2, 7, 8, 5, 6])
+
+
+def _p2_lib():
+    L = lib()
+    if not getattr(L, "_p2_ready", False):
+        pp = C.POINTER(P2Params)
+        L.p2_default_params.argtypes = [pp]
+        L.p2_dims_create.argtypes = [C.c_int, C.c_int, C.c_int, _ip]
+        L.p2_world_create.restype = C.c_void_p
+        L.p2_world_create.argtypes = [pp, C.c_int, _ip]
+        L.p2_world_destroy.argtypes = [C.c_void_p]
+        L.p2_rank_ptr.restype = _dp
+        L.p2_rank_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.p2_rank_obst.restype = _ip
+        L.p2_rank_obst.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.p2_rank_info.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.p2_particle_ptr.restype = _dp
+        L.p2_particle_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.p2_world_info.argtypes = [C.c_void_p, _ip, _dp, _ip]
+        L.p2_get_params.argtypes = [C.c_void_p, pp]
+        for name in ("p2_initial", "p2_collision", "p2_send_all_fp", "p2_send_all_f", "p2_streaming", "p2_bounceback",
+                     "p2_bounceback_particle", "p2_macro", "p2_calForce", "p2_updateCenter"):
+            getattr(L, name).argtypes = [C.c_void_p]
+            getattr(L, name).restype = None
+        L.p2_check.argtypes = [C.c_void_p]
+        L.p2_check.restype = C.c_double
+        L.p2_step.argtypes = [C.c_void_p, C.c_int]
+        L.p2_step.restype = None
+        L.p2_collide_cell.argtypes = [_dp] + [C.c_double] * 5 + [_dp]
+        L.p2_macro_cell.argtypes = [_dp, _dp]
+        L.p2_calQ.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+        L.p2_particle_forces.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.p2_particle_advance.argtypes = [pp] + [C.c_double] * 9 + [_dp]
+        L.p2_set_rhoAvg.argtypes = [C.c_void_p, C.c_double]
+        L.p2_bb_link_r.argtypes = [C.c_void_p] + [C.c_int] * 5
+        L.p2_force_link_r.argtypes = [C.c_void_p] + [C.c_int] * 5 + [_dp]
+        L.p2_refill_cell_r.argtypes = [C.c_void_p] + [C.c_int] * 4
+        L._p2_ready = True
+    return L
+
+
+def p2_default_params(**over):
+    p = P2Params()
+    _p2_lib().p2_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+class ParticleRank:
+    def __init__(self, world, r):
+        L = world._lib
+        info = (C.c_int * 14)()
+        L.p2_rank_info(world._h, r, info)
+        self.n = (info[0], info[1])
+        self.coords = (info[2], info[3])
+        self.start = (info[4], info[5])
+        self.nbr = dict(zip(("left", "right", "bottom", "top", "tl", "tr", "bl", "br"), info[6:14]))
+        nx, ny = self.n
+        shapes = {"f": (9, nx + 6, ny + 6), "f_post": (9, nx + 4, ny + 4)}
+        for name, which in P2_FIELDS.items():
+            shape = shapes.get(name, (nx, ny))
+            p = L.p2_rank_ptr(world._h, r, which)
+            setattr(self, name, np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape, order="F"))
+        for name, which in (("obst", 0), ("obstNew", 1)):
+            p = L.p2_rank_obst(world._h, r, which)
+            setattr(self, name, np.ctypeslib.as_array(p, shape=((nx + 2) * (ny + 2),)).reshape((nx + 2, ny + 2), order="F"))
+
+
+class ParticleWorld:
+    """All P emulated ranks of the particle driver (P4/main.F90) in one process.  Particle positions are an
+    input (the reference draws them from a compiler-specific random_number)."""
+
+    def __init__(self, x, y, radius=None, nprocs=1, dims=None, **params):
+        self._lib = _p2_lib()
+        x = np.asarray(x, dtype=np.float64)
+        self.p = p2_default_params(N=len(x), **params)
+        d = (C.c_int * 2)(*(dims if dims else (0, 0)))
+        self._h = self._lib.p2_world_create(C.byref(self.p), nprocs, d)
+        self.nprocs, self.N = nprocs, len(x)
+        self.total = (self.p.total_nx, self.p.total_ny)
+        for name, which in P2_PARTICLE.items():
+            ptr = self._lib.p2_particle_ptr(self._h, which)
+            setattr(self, name, np.ctypeslib.as_array(ptr, shape=(self.N,)))
+        self.xCenter[:] = x
+        self.yCenter[:] = y
+        self.radius[:] = self.p.radius0 if radius is None else radius
+        self.ranks = [ParticleRank(self, r) for r in range(nprocs)]
+        dd, sc, ie = (C.c_int * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
+        self._lib.p2_world_info(self._h, dd, sc, ie)
+        self.dims = tuple(dd)
+
+    def close(self):
+        if self._h:
+            self.ranks = []
+            self._lib.p2_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        dd, sc, ie = (C.c_int * 2)(), (C.c_double * 2)(), (C.c_int * 2)()
+        self._lib.p2_world_info(self._h, dd, sc, ie)
+        return dict(rhoAvg=sc[0], errorU=sc[1], itc=ie[0], error_flag=ie[1])
+
+    def check(self):
+        return self._lib.p2_check(self._h)
+
+    def step(self, n=1):
+        self._lib.p2_step(self._h, n)
+
+    def gather(self, name):
+        out = np.empty(self.total, order="F", dtype=np.int32 if name.startswith("obst") else np.float64) if name not in ("f", "f_post") \
+            else np.empty((9,) + self.total, order="F")
+        for R in self.ranks:
+            nx, ny = R.n
+            sl = (slice(R.start[0], R.start[0] + nx), slice(R.start[1], R.start[1] + ny))
+            if name == "f":
+                out[(slice(None),) + sl] = R.f[:, 3:nx + 3, 3:ny + 3]
+            elif name == "f_post":
+                out[(slice(None),) + sl] = R.f_post[:, 2:nx + 2, 2:ny + 2]
+            elif name.startswith("obst"):
+                out[sl] = getattr(R, name)[1:nx + 1, 1:ny + 1]
+            else:
+                out[sl] = getattr(R, name)
+        return out
+
+
+for _name, _sub in (("initial", "p2_initial"), ("collision", "p2_collision"), ("send_all_fp", "p2_send_all_fp"),
+                    ("send_all_f", "p2_send_all_f"), ("streaming", "p2_streaming"), ("bounceback", "p2_bounceback"),
+                    ("bounceback_particle", "p2_bounceback_particle"), ("macro", "p2_macro"), ("calForce", "p2_calForce"),
+                    ("updateCenter", "p2_updateCenter")):
+    setattr(ParticleWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))

@@ -650,3 +650,9 @@ void p2_step(p2_world *w, int n) {
         p2_updateCenter(w);
     }
 }
+
+/* ---- small entry points for the per-link / per-node golden-vector tests ---------------------------------- */
+void p2_set_rhoAvg(p2_world *w, double v) { w->rhoAvg = v; }
+void p2_bb_link_r(p2_world *w, int r, int i, int j, int alpha, int c) { p2_bb_link(w, &w->r[r], i, j, alpha, c); }
+int p2_force_link_r(p2_world *w, int r, int i, int j, int alpha, int c, double *out) { return p2_force_link(w, &w->r[r], i, j, alpha, c, out); }
+int p2_refill_cell_r(p2_world *w, int r, int i, int j, int c) { return p2_refill_cell(w, &w->r[r], i, j, c); }

@@ -128,7 +128,7 @@ def _powers(s):
         expo = m.group(1)
         rest = s[k + 2 + m.end():]
         if float(eval(expo)) == 2.0:
-            s = left[:o] + f"sq({base})" + rest
+            s = left[:o] + f"square__({base})" + rest
         else:
             s = left[:o] + f"pow({base}, {float(eval(expo))})" + rest
     return s
@@ -214,7 +214,7 @@ class _Arr(dict):
 def run(py_src, cell_in=None, field_in=None, scalars=None, local_arrays=(), cell_out=(), field_out=()):
     """Execute translated source.  cell_in: {name: sequence}, field_in: {name: float},
     scalars: {name: number} (parameters such as snu, sq, nx).  Returns {name: list or float}."""
-    ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range, "sq": lambda x: x * x,
+    ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range, "square__": lambda x: x * x,
           "pow": math.pow, "atan": math.atan, "mod": lambda a, b: a % b}
     for name, seq in (cell_in or {}).items():
         ns[name.lower() + "__"] = _Arr({k: float(x) for k, x in enumerate(seq)})
