@@ -240,6 +240,62 @@ int mglc_jacobi_check_diff(mglc_jacobi *h, double *error_max);   /* check_diff +
 int mglc_jacobi_launch_count(mglc_jacobi *h, long long *n);
 int mglc_jacobi_sync(mglc_jacobi *h);
 
+/* ================= particle-laden D2Q9 path (MPI/Micro_particles/fortran/case4/mpi_particle/, "P4") =================
+ * Host arrays are the reference's (P4/freeall.F90:13-17): f(0:8,-2:nx+3,-2:ny+3), f_post(0:8,-1:nx+2,-1:ny+2),
+ * obst(0:nx+1,0:ny+1) integer, rho,u,v(nx,ny); column-major.  Particle state is replicated (size nparticles), like the
+ * reference's module arrays.  The reference draws its initial particle positions from a compiler-specific
+ * random_number (P4/initial.F90:52-75), so positions are an input here.  A handle owns ONE subdomain (one process
+ * per GPU, halos and reductions over NCCL) or all P of them (mglc_p2d_create_local); `r` = index among those owned. */
+typedef struct mglc_p2d mglc_p2d;
+typedef struct mglc_p2d_desc {           /* module commondata, P4/commondata.F90:3-62 */
+    int total_nx, total_ny;              /* 201 x 801                                      */
+    int nparticles;                      /* cNumMax                                        */
+    int reserved;
+    double rho0, rhoSolid, viscosity;    /* 1, 1.01, 0.05 (tauf = 3 nu + 0.5)              */
+    double radius0;                      /* 10                                             */
+    double gravity;                      /* 980 * t0^2 / l0                                */
+    double thresholdWall, stiffWall, thresholdParticle, stiffParticle;
+} mglc_p2d_desc;
+int mglc_p2d_desc_init(mglc_p2d_desc *d, int nparticles);            /* the shipped constants */
+/* MPI_Dims_create_2d -- P4/mpi_starts.F90:160-180 (smallest halo message wins) */
+int mglc_p2d_dims_create(int nranks, int total_nx, int total_ny, int dims[2]);
+int mglc_p2d_create(mglc_p2d **h, const mglc_p2d_desc *d, const int dims_or_zero[2], int nranks, int rank, int device,
+                    mglc_comm *comm_or_null);                          /* mpi_starts + allocate_all */
+int mglc_p2d_create_local(mglc_p2d **h, const mglc_p2d_desc *d, const int dims_or_zero[2], int nranks,
+                          const int *devices_or_null);
+int mglc_p2d_destroy(mglc_p2d *h);                                      /* free_all -- P4/freeall.F90:23-41 */
+int mglc_p2d_nlocal(mglc_p2d *h, int *n);
+int mglc_p2d_info(mglc_p2d *h, int r, int dims[2], int ln[2], int start[2], int coords[2], int nbr[8]);
+/* xCenter, yCenter, Uc, Vc, rationalOmega, radius; NULL = keep */
+int mglc_p2d_set_particles(mglc_p2d *h, const double *x, const double *y, const double *U, const double *V,
+                           const double *omega, const double *radius);
+/* ... and wallTotalForceX/Y, totalTorque; NULL = skip */
+int mglc_p2d_get_particles(mglc_p2d *h, double *x, double *y, double *U, double *V, double *omega, double *Fx,
+                           double *Fy, double *torque);
+int mglc_p2d_set_forces(mglc_p2d *h, const double *Fx, const double *Fy, const double *torque);
+int mglc_p2d_upload(mglc_p2d *h, int r, const double *f, const double *f_post, const double *rho, const double *u,
+                    const double *v, const int *obst);                  /* NULL = keep */
+int mglc_p2d_download(mglc_p2d *h, int r, double *f, double *f_post, double *rho, double *u, double *v, int *obst);
+int mglc_p2d_initial(mglc_p2d *h);               /* initial() after the positions are set   P4/initial.F90:79-199 */
+int mglc_p2d_collision(mglc_p2d *h);             /* collision()            P4/fluid.F90:1-72                    */
+int mglc_p2d_send_all_fp(mglc_p2d *h);           /* send_all_fp()          P4/message_send_all.F90:84-148       */
+int mglc_p2d_streaming(mglc_p2d *h);             /* streaming()            P4/fluid.F90:75-111                  */
+int mglc_p2d_bounceback(mglc_p2d *h);            /* bounceback()           P4/fluid.F90:115-161                 */
+int mglc_p2d_bounceback_particle(mglc_p2d *h, int recompute_rho_avg);   /* P4/particle_bounceback.F90:1-96 (1 = as the reference) */
+int mglc_p2d_macro(mglc_p2d *h);                 /* macro()                P4/fluid.F90:164-184                 */
+int mglc_p2d_calforce(mglc_p2d *h);              /* calForce()             P4/particle_force.F90:1-212          */
+int mglc_p2d_send_all_f(mglc_p2d *h);            /* send_all_f()           P4/message_send_all.F90:1-81         */
+int mglc_p2d_update_center(mglc_p2d *h);         /* updateCenter()         P4/particle_update.F90:1-209         */
+int mglc_p2d_check(mglc_p2d *h, double *errorU); /* check()                P4/fluid.F90:187-221                 */
+int mglc_p2d_step(mglc_p2d *h, int nsteps);      /* nsteps loop bodies     P4/main.F90:35-73                    */
+int mglc_p2d_step_timed(mglc_p2d *h, int nsteps, float *ms);
+int mglc_p2d_set_rho_avg(mglc_p2d *h, double rhoAvg);
+int mglc_p2d_get_rho_avg(mglc_p2d *h, double *rhoAvg);
+/* the reference's stop / MPI_Abort conditions, raised on the device: returns MGLC_E_DIVERGED when any is set */
+int mglc_p2d_error_flags(mglc_p2d *h, int *flags);
+int mglc_p2d_launch_count(mglc_p2d *h, long long *n);
+int mglc_p2d_sync(mglc_p2d *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,8 +8,9 @@ reference driver's interface; it has no CPU or PyTorch fallback and raises if th
 from . import _lib
 from ._lib import MglcError, lib
 from .jacobi import Jacobi, dims_create_nd
+from .particles import ParticleChannel
 from .lbm import (BuoyancyDrivenCavity, Communicator, LidDrivenCavity, make_thermal_desc, Subdomain, cart_neighbors, decompose_1d, dims_create,
                   halo_plan, make_desc)
 
 __all__ = ["MglcError", "lib", "BuoyancyDrivenCavity", "Communicator", "LidDrivenCavity", "make_thermal_desc", "Subdomain", "cart_neighbors",
-           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "_lib"]
+           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "_lib"]

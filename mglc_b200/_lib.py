@@ -38,6 +38,12 @@ class HaloMsg(C.Structure):
                 ("send_count", C.c_int), ("recv_count", C.c_int), ("pops", C.c_int * 5)]
 
 
+class P2dDesc(C.Structure):
+    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("nparticles", C.c_int), ("reserved", C.c_int)] + \
+               [(n, C.c_double) for n in ("rho0", "rhoSolid", "viscosity", "radius0", "gravity", "thresholdWall", "stiffWall",
+                                          "thresholdParticle", "stiffParticle")]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _vp = C.c_void_p
@@ -132,6 +138,37 @@ SIGNATURES = {
     "mglc_jacobi_check_diff": (C.c_int, [_vp, _dp]),
     "mglc_jacobi_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_jacobi_sync": (C.c_int, [_vp]),
+    # particle-laden D2Q9 path
+    "mglc_p2d_desc_init": (C.c_int, [C.POINTER(P2dDesc), C.c_int]),
+    "mglc_p2d_dims_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip]),
+    "mglc_p2d_create": (C.c_int, [_vpp, C.POINTER(P2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
+    "mglc_p2d_create_local": (C.c_int, [_vpp, C.POINTER(P2dDesc), _ip, C.c_int, _ip]),
+    "mglc_p2d_destroy": (C.c_int, [_vp]),
+    "mglc_p2d_nlocal": (C.c_int, [_vp, _ip]),
+    "mglc_p2d_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "mglc_p2d_set_particles": (C.c_int, [_vp] + [_vp] * 6),
+    "mglc_p2d_get_particles": (C.c_int, [_vp] + [_vp] * 8),
+    "mglc_p2d_set_forces": (C.c_int, [_vp] + [_vp] * 3),
+    "mglc_p2d_upload": (C.c_int, [_vp, C.c_int] + [_vp] * 6),
+    "mglc_p2d_download": (C.c_int, [_vp, C.c_int] + [_vp] * 6),
+    "mglc_p2d_initial": (C.c_int, [_vp]),
+    "mglc_p2d_collision": (C.c_int, [_vp]),
+    "mglc_p2d_send_all_fp": (C.c_int, [_vp]),
+    "mglc_p2d_streaming": (C.c_int, [_vp]),
+    "mglc_p2d_bounceback": (C.c_int, [_vp]),
+    "mglc_p2d_bounceback_particle": (C.c_int, [_vp, C.c_int]),
+    "mglc_p2d_macro": (C.c_int, [_vp]),
+    "mglc_p2d_calforce": (C.c_int, [_vp]),
+    "mglc_p2d_send_all_f": (C.c_int, [_vp]),
+    "mglc_p2d_update_center": (C.c_int, [_vp]),
+    "mglc_p2d_check": (C.c_int, [_vp, _dp]),
+    "mglc_p2d_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_p2d_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_p2d_set_rho_avg": (C.c_int, [_vp, C.c_double]),
+    "mglc_p2d_get_rho_avg": (C.c_int, [_vp, _dp]),
+    "mglc_p2d_error_flags": (C.c_int, [_vp, _ip]),
+    "mglc_p2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_p2d_sync": (C.c_int, [_vp]),
 }
 
 _lib = None
