@@ -181,6 +181,9 @@ int mglc_lbm_launch_count(mglc_lbm *h, long long *n);
 /* per-launch CUDA-event timing of the fused kernel on its launching stream (off by default);
  * mglc_lbm_kernel_time returns and resets the accumulated device time and launch count */
 int mglc_lbm_set_profiling(mglc_lbm *h, int on);
+/* comm/compute overlap of the fused step (boundary shell -> exchange on a second stream || interior), the schedule of
+ * collision_with_message_exchange, lid3_mpi_nonblock.f90:1108-1230.  On by default; 0 = exchange, then update. */
+int mglc_lbm_set_overlap(mglc_lbm *h, int on);
 int mglc_lbm_kernel_time(mglc_lbm *h, float *fused_ms, long long *fused_launches);
 /* page-locked host memory for the caller's f / rho,u,v,w arrays (c_f_pointer on the Fortran side), so
  * upload/download run at full PCIe rate; pageable pointers are accepted everywhere too */

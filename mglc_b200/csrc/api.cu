@@ -24,6 +24,10 @@ struct mglc_lbm {
     // populations (before exchange), buf[cur] the last step's f_post with its halos, and only the lid
     // plane of rho is current.  canonicalise() turns this back into the reference's state (f, rho,u,v,w).
     int rotated;
+    // overlapped schedule (L3nb:1108-1230): the halo exchange of the lattice just written runs on s_comm while the
+    // interior update runs on s.  halo_inflight: that exchange has been issued for buf[cur^1]; s must wait for
+    // ev_halo before anything reads those halos.  overlap: 1 = use the schedule when the handle has neighbours + NCCL
+    int halo_inflight, overlap;
     double *rho, *u, *v, *w, *up, *vp, *wp;
     // lid plane (k = nz) of rho for the moving-lid term, L3/bounce_back.f90:77-78.  A fused launch reads
     // the plane the previous macro() left (lid_next) and writes this step's into the other side buffer,
@@ -188,6 +192,7 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
     h->nranks = d->dims[0] * d->dims[1] * d->dims[2];
     mglc_cart_rank(d->dims, d->coords, &h->rank);
     h->comm = comm;
+    h->overlap = 1;
     int rc = MGLC_OK;
     auto fail = [&](int code) { mglc_lbm_destroy(h); return code; };
     if ((rc = cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking) == cudaSuccess ? MGLC_OK : MGLC_E_CUDA)) return fail(rc);
@@ -479,8 +484,20 @@ static int prof_flush(mglc_lbm *h) {
     h->prof_used = 0;
     return MGLC_OK;
 }
-static int do_fused(mglc_lbm *h) {
-    const int box[6] = {1, h->g.nx, 1, h->g.ny, 1, h->g.nz};
+// one launch of the fused kernel over `box`, reading lattice `in` (with halos) and writing `out`; the lid plane /
+// force buffers are the step's (see fused_begin)
+struct FusedIO { const double *Fin, *Gin, *lid_in, *Fc_in; double *Fout, *Gout, *lid_out, *Fc_out; };
+static int launch_fused_box(mglc_lbm *h, const FusedIO &io, const int box[6]) {
+    if (h->thermal)
+        h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s)
+                                  : fast::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s);
+    else
+        h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, io.Fin, io.Fout, io.lid_in, io.lid_out, box, h->s)
+                                  : fast::launch_fused(h->g, h->p, io.Fin, io.Fout, io.lid_in, io.lid_out, box, h->s);
+    return MGLC_OK;
+}
+// buffers of the coming fused step + per-step profiling event; fused_end() rotates them
+static int fused_begin(mglc_lbm *h, FusedIO &io) {
     if (h->profiling) {
         if (!h->prof_ev) {
             h->prof_ev = new std::vector<cudaEvent_t>(2 * PROF_PAIRS);
@@ -489,23 +506,83 @@ static int do_fused(mglc_lbm *h) {
         if (h->prof_used == PROF_PAIRS) MGLC_TRY(prof_flush(h));
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used], h->s));
     }
+    io = FusedIO{};
+    io.Fin = Fpost_(h); io.Fout = F_(h);
     if (h->thermal) {
-        h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), h->Fc[h->fc_cur], h->Fc[h->fc_cur ^ 1], box, h->s)
-                                  : fast::launch_th_fused(h->g, h->tp, Fpost_(h), F_(h), Gpost_(h), G_(h), h->Fc[h->fc_cur], h->Fc[h->fc_cur ^ 1], box, h->s);
-        h->fc_cur ^= 1;          // Fc[fc_cur] now belongs to the collision in flight, Fc[fc_cur^1] to the completed step
+        io.Gin = Gpost_(h); io.Gout = G_(h);
+        io.Fc_in = h->Fc[h->fc_cur]; io.Fc_out = h->Fc[h->fc_cur ^ 1];
     } else {
-    const double *lid_in = h->lid_next;
-    double *lid_out = (lid_in == h->rho_lid[0]) ? h->rho_lid[1] : h->rho_lid[0];
-    h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s)
-                              : fast::launch_fused(h->g, h->p, Fpost_(h), F_(h), lid_in, lid_out, box, h->s);
-    h->lid_last_in = lid_in;
-    h->lid_next = lid_out;
+        io.lid_in = h->lid_next;
+        io.lid_out = (io.lid_in == h->rho_lid[0]) ? h->rho_lid[1] : h->rho_lid[0];
     }
+    return MGLC_OK;
+}
+// roles swap: the lattice just written becomes f_post of the next step
+static void fused_swap(mglc_lbm *h, const FusedIO &io) {
+    if (h->thermal) h->fc_cur ^= 1;   // Fc[fc_cur] now belongs to the collision in flight, Fc[fc_cur^1] to the completed step
+    else { h->lid_last_in = io.lid_in; h->lid_next = io.lid_out; }
+    h->cur ^= 1;
+}
+static int fused_end(mglc_lbm *h) {
     if (h->profiling) {
         MGLC_CUDA(cudaEventRecord((*h->prof_ev)[2 * h->prof_used + 1], h->s));
         h->prof_used += 1;
     }
-    h->cur ^= 1;
+    return MGLC_OK;
+}
+// fused stream+macro+collide over the whole subdomain: reads f_post (incl. halo), writes the NEXT f_post into the
+// buffer that held f, then the two buffers swap roles
+static int do_fused(mglc_lbm *h) {
+    const int box[6] = {1, h->g.nx, 1, h->g.ny, 1, h->g.nz};
+    FusedIO io;
+    MGLC_TRY(fused_begin(h, io));
+    MGLC_TRY(launch_fused_box(h, io, box));
+    fused_swap(h, io);
+    return fused_end(h);
+}
+// Overlapped step (the schedule of L3nb collision_with_message_exchange, :1108-1230): the cells next to a
+// NEIGHBOUR face first (thin slabs: one plane in y and z, 32 cells in x so a warp still stores full lines),
+// then their populations are packed, exchanged and unpacked on s_comm while the interior runs on s.
+constexpr int SHELL_X = 32;
+static int do_fused_overlapped(mglc_lbm *h) {
+    const Geom &g = h->g;
+    const int n[3] = {g.nx, g.ny, g.nz};
+    const int want[3] = {SHELL_X, 1, 1};
+    int lo[3], hi[3];                 // interior box per axis
+    for (int d = 0; d < 3; ++d) {
+        const bool nb_plus = !g.wall[2 * d], nb_minus = !g.wall[2 * d + 1];
+        int tm = nb_minus ? std::min(want[d], n[d]) : 0, tp = nb_plus ? std::min(want[d], n[d]) : 0;
+        if (tm + tp > n[d]) { tm = n[d]; tp = 0; }
+        lo[d] = 1 + tm; hi[d] = n[d] - tp;
+    }
+    FusedIO io;
+    MGLC_TRY(fused_begin(h, io));
+    // disjoint shell slabs: z slabs span everything, y slabs the interior k range, x slabs the interior j,k range
+    const int zs[2][2] = {{1, lo[2] - 1}, {hi[2] + 1, n[2]}}, ys[2][2] = {{1, lo[1] - 1}, {hi[1] + 1, n[1]}},
+              xs[2][2] = {{1, lo[0] - 1}, {hi[0] + 1, n[0]}};
+    for (int q = 0; q < 2; ++q) { const int box[6] = {1, n[0], 1, n[1], zs[q][0], zs[q][1]}; MGLC_TRY(launch_fused_box(h, io, box)); }
+    for (int q = 0; q < 2; ++q) { const int box[6] = {1, n[0], ys[q][0], ys[q][1], lo[2], hi[2]}; MGLC_TRY(launch_fused_box(h, io, box)); }
+    for (int q = 0; q < 2; ++q) { const int box[6] = {xs[q][0], xs[q][1], lo[1], hi[1], lo[2], hi[2]}; MGLC_TRY(launch_fused_box(h, io, box)); }
+    MGLC_CUDA(cudaEventRecord(h->ev_shell, h->s));
+    fused_swap(h, io);                // from here on Fpost_(h) is the lattice being written: pack/unpack address it
+    MGLC_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_shell, 0));
+    select_msgs(h, MSG_ALL);
+    MGLC_TRY(do_pack(h, h->s_comm));
+    MGLC_TRY(halo_nccl_sendrecv(h->msgs, h->nmsgs, h->comm, h->s_comm));
+    MGLC_TRY(do_unpack(h, h->s_comm));
+    MGLC_CUDA(cudaEventRecord(h->ev_halo, h->s_comm));
+    h->halo_inflight = 1;
+    const int box[6] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]};
+    MGLC_TRY(launch_fused_box(h, io, box));
+    return fused_end(h);
+}
+// make the halos of f_post (and g_post) of the coming step valid on stream s
+static int halos_for_next_step(mglc_lbm *h) {
+    if (h->halo_inflight) {
+        MGLC_CUDA(cudaStreamWaitEvent(h->s, h->ev_halo, 0));
+        h->halo_inflight = 0;
+        return MGLC_OK;
+    }
     return MGLC_OK;
 }
 static int do_stream_macro(mglc_lbm *h) {
@@ -526,6 +603,10 @@ static int do_stream_macro(mglc_lbm *h) {
 // rho,u,v,w.  Afterwards f, f_post, rho,u,v,w are the reference's after the same number of loop bodies.
 static int canonicalise(mglc_lbm *h) {
     if (!h->rotated) return MGLC_OK;
+    if (h->halo_inflight) {           // the exchange of the discarded lattice must be off the wire before it is reused
+        MGLC_CUDA(cudaStreamWaitEvent(h->s, h->ev_halo, 0));
+        h->halo_inflight = 0;
+    }
     h->cur ^= 1;
     MGLC_TRY(do_stream_macro(h));
     h->rotated = 0;
@@ -660,9 +741,12 @@ static int step_impl(mglc_lbm *h, int nsteps) {
         MGLC_TRY(do_collision(h));
         if (h->thermal) MGLC_TRY(do_collisionT(h));
     }
+    const bool overlapped = h->overlap && h->has_neighbors && h->comm;
     for (int it = 0; it < nsteps; ++it) {
-        MGLC_TRY(do_exchange_nccl(h));               // exchange of step it
-        MGLC_TRY(do_fused(h));                       // streaming+bounceback+macro of step it, collision of it+1
+        if (h->halo_inflight) MGLC_TRY(halos_for_next_step(h));   // exchange of step it already ran beside the last interior
+        else MGLC_TRY(do_exchange_nccl(h));                       // exchange of step it
+        if (overlapped) MGLC_TRY(do_fused_overlapped(h));
+        else MGLC_TRY(do_fused(h));                  // streaming+bounceback+macro of step it, collision of it+1
     }
     h->rotated = 1;
     return MGLC_OK;
@@ -684,6 +768,14 @@ extern "C" int mglc_lbm_step_timed(mglc_lbm *h, int nsteps, float *ms) {
     MGLC_CUDA(cudaEventSynchronize(h->ev_t1));
     MGLC_CUDA(cudaGetLastError());
     MGLC_CUDA(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+    return MGLC_OK;
+}
+// 1 (default) = overlap the halo exchange with the interior update when the handle has neighbours and a
+// communicator; 0 = exchange, then update (what the blocking reference driver does, L3/main.f90:89-93)
+extern "C" int mglc_lbm_set_overlap(mglc_lbm *h, int on) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(canonicalise(h));
+    h->overlap = on ? 1 : 0;
     return MGLC_OK;
 }
 extern "C" int mglc_lbm_set_profiling(mglc_lbm *h, int on) {

@@ -5,8 +5,8 @@
 // cell i=1 sits 128-byte aligned).  2-D problems live in plane k = 1 of a 3-plane array.
 // Kernels (all bit-defined: adds in the reference's order and one multiply by a constant, -fmad=false):
 //   k_jacobi2d   A_new = 0.25 * (A(i-1,j) + A(i+1,j) + A(i,j-1) + A(i,j+1) + f)        LAP:170-182
-//   k_jacobi3d   A_new = (1/6) * (x- + x+ + y- + y+ + z- + z+ + f); 2.5-D blocking: each thread marches along z
-//                with the z-1 / z / z+1 values in registers, the current (x,y) tile in shared memory, so a
+//   k_jacobi3d   A_new = (1/6) * (x- + x+ + y- + y+ + z- + z+ + f); register blocking: a thread marches along z with
+//                the z-1 / z / z+1 values of 4 consecutive rows in registers, x neighbours by warp shuffle, so a
 //                cell costs one DRAM read and one write (16 B, 24 B with a source term)
 //   k_face_pack / k_face_unpack   replace the contiguous-row and MPI_Type_vector column messages of
 //                exchange_message (LAP:223-254)
@@ -74,49 +74,50 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
     B[c] = 0.25 * s;
 }
 
-// 2.5-D blocking: a CTA owns a JTX x JTY tile of (x,y) and marches JKCH planes along z.  Each thread keeps
-// the z-1 / z / z+1 values of its cell in registers (plus z+2 in flight as a prefetch); the current plane of
-// the tile, with its one-cell rim, goes through shared memory so x/y neighbours cost no L2 traffic beyond the
-// rim (2/JTY of a row + two sectors per row).  Two shared buffers alternate, so one barrier per plane is enough.
-constexpr int JTX = 64, JTY = 8, JKCH = 64;
+// Register blocking, no barriers: a thread owns JRY consecutive rows of one x column and marches JKCH planes along
+// z with the z-1 / z / z+1 values of its JRY cells in registers.  y neighbours are the thread's own registers
+// (plus one row above and one below the strip per plane), x neighbours come from the adjacent lanes by shuffle
+// (warp-edge lanes read them), z neighbours from the marching registers: per cell one DRAM read, one write and
+// about 2/JRY extra L2 reads.
+constexpr int JTX = 128, JRY = 4, JKCH = 64;
 template <bool HAS_F>
-__global__ void __launch_bounds__(JTX *JTY) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
-                                                       double *__restrict__ B, int k_lo, int k_hi) {
-    __shared__ double sm[2][JTY + 2][JTX + 2];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i = 1 + blockIdx.x * JTX + tx;
-    const int j = 1 + blockIdx.y * JTY + ty;
+__global__ void __launch_bounds__(JTX, 8) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
+                                                     double *__restrict__ B, int k_lo, int k_hi) {
+    const int i = 1 + blockIdx.x * JTX + threadIdx.x;
+    const int j0 = 1 + blockIdx.y * JRY;
     const int k0 = k_lo + blockIdx.z * JKCH;
     const int k1 = min(k0 + JKCH - 1, k_hi);
-    const bool active = (i <= g.nx) && (j <= g.ny);
-    const bool rim_xm = tx == 0, rim_xp = (tx == JTX - 1) || (i == g.nx);
-    const bool rim_ym = ty == 0, rim_yp = (ty == JTY - 1) || (j == g.ny);
+    const int lane = threadIdx.x & 31;
+    const bool active = i <= g.nx;
+    const bool edge_m = lane == 0, edge_p = lane == 31 || i >= g.nx;
     const long long sy = g.sy, sz = g.sz;
-    long long c = g.idx(0, min(i, g.nx), min(j, g.ny), k0);      // clamped: inactive threads only keep the barriers company
-    double below = A[c - sz], center = A[c], up = A[c + sz];
+    long long row[JRY];                           // rows past ny fold onto the ghost row ny+1: loaded, never stored
+#pragma unroll
+    for (int r = 0; r < JRY; ++r) row[r] = (long long)(min(j0 + r, g.ny + 1) - j0) * sy;
+    const long long row_p = (long long)(min(j0 + JRY, g.ny + 1) - j0) * sy;
+    long long c = g.idx(0, min(i, g.nx), j0, k0);
+    double below[JRY], cen[JRY], up[JRY];
+#pragma unroll
+    for (int r = 0; r < JRY; ++r) { below[r] = A[c + row[r] - sz]; cen[r] = A[c + row[r]]; }
     for (int k = k0; k <= k1; ++k) {
-        const double up2 = (k < k1) ? A[c + 2 * sz] : 0.0;        // prefetch: in flight across the barrier
-        double(*pl)[JTX + 2] = sm[k & 1];
-        pl[ty + 1][tx + 1] = center;
-        if (active) {
-            if (rim_xm) pl[ty + 1][0] = A[c - 1];
-            if (rim_xp) pl[ty + 1][tx + 2] = A[c + 1];
-            if (rim_ym) pl[0][tx + 1] = A[c - sy];
-            if (rim_yp) pl[ty + 2][tx + 1] = A[c + sy];
+#pragma unroll
+        for (int r = 0; r < JRY; ++r) up[r] = A[c + row[r] + sz];
+        const double ym = A[c - sy], yp = A[c + row_p];
+#pragma unroll
+        for (int r = 0; r < JRY; ++r) {
+            double xm = __shfl_up_sync(0xffffffffu, cen[r], 1), xp = __shfl_down_sync(0xffffffffu, cen[r], 1);
+            if (edge_m) xm = A[c + row[r] - 1];
+            if (edge_p) xp = A[c + row[r] + 1];
+            double s = xm + xp;
+            s += (r == 0) ? ym : cen[r - 1];
+            s += (r == JRY - 1) ? yp : cen[r + 1];
+            s += below[r];
+            s += up[r];
+            s += HAS_F ? f[c + row[r]] : 0.0;
+            if (active && j0 + r <= g.ny) B[c + row[r]] = (1.0 / 6.0) * s;
         }
-        __syncthreads();
-        if (active) {
-            double s = pl[ty + 1][tx] + pl[ty + 1][tx + 2];
-            s += pl[ty][tx + 1];
-            s += pl[ty + 2][tx + 1];
-            s += below;
-            s += up;
-            s += HAS_F ? f[c] : 0.0;
-            B[c] = (1.0 / 6.0) * s;
-        }
-        below = center;
-        center = up;
-        up = up2;
+#pragma unroll
+        for (int r = 0; r < JRY; ++r) { below[r] = cen[r]; cen[r] = up[r]; }
         c += sz;
     }
 }
@@ -431,8 +432,8 @@ static int jac_sweep(mglc_jacobi *h) {
             if (S->f) k_jacobi2d<true><<<grid, 128, 0, S->s>>>(S->g, A, S->f, B);
             else k_jacobi2d<false><<<grid, 128, 0, S->s>>>(S->g, A, nullptr, B);
         } else {
-            const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JTY - 1) / JTY, (S->n[2] + JKCH - 1) / JKCH);
-            const dim3 block(JTX, JTY);
+            const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JRY - 1) / JRY, (S->n[2] + JKCH - 1) / JKCH);
+            const dim3 block(JTX);
             if (S->f) k_jacobi3d<true><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2]);
             else k_jacobi3d<false><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2]);
         }

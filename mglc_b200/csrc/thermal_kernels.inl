@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(128) k_th_collisionT(Geom g, ThermalParams tp,
 __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, const double *__restrict__ Fin,
                                                      double *__restrict__ Fout, const double *__restrict__ Gin,
                                                      double *__restrict__ Gout, const double *__restrict__ Fc_in,
-                                                     double *__restrict__ Fc_out, int i0, int i1, int j0, int k0) {
+                                                     double *__restrict__ Fc_out, int i0, int i1, int j0, int j1, int k0) {
+    // block (128,1) for full rows, (32,4) for the thin x-slabs of the boundary shell (see launch below)
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
-    if (i > i1) return;
+    const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
+    if (i > i1 || j > j1) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k), m = g.cell(i, j, k);
     const long long n = (long long)g.nx * g.ny * g.nz;
@@ -133,8 +134,9 @@ int launch_th_fused(const Geom &g, const ThermalParams &tp, const double *Fin, d
                     double *Gout, const double *Fc_in, double *Fc_out, const int box[6], cudaStream_t s) {
     const int nxs = box[1] - box[0] + 1, nys = box[3] - box[2] + 1, nzs = box[5] - box[4] + 1;
     if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
-    k_th_fused<<<grid_for(nxs, nys, nzs, 128), 128, 0, s>>>(g, tp, Fin, Fout, Gin, Gout, Fc_in, Fc_out, box[0], box[1],
-                                                           box[2], box[4]);
+    const dim3 block = nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
+    const dim3 grid((nxs + block.x - 1) / block.x, (nys + block.y - 1) / block.y, nzs);
+    k_th_fused<<<grid, block, 0, s>>>(g, tp, Fin, Fout, Gin, Gout, Fc_in, Fc_out, box[0], box[1], box[2], box[3], box[4]);
     return 1;
 }
 int launch_th_stream_macro(const Geom &g, const ThermalParams &tp, const double *Fin, double *F, const double *Gin,
