@@ -42,7 +42,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="mglc", choices=["mglc", "reference"])
-    p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi"],
+    p.add_argument("--no-overlap", action="store_true", help="exchange halos, THEN update (blocking schedule) instead of overlapping")
+    p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi", "particles"],
                    help="lid = BASELINE.json's metric (default); thermal / jacobi = the other configs, for profiles/")
     p.add_argument("--size", type=int, default=0, help="per-GPU block edge (weak) / global edge (strong); 0 = the workload's config size")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -211,10 +212,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     thermal = args.workload == "thermal"
     if args.size == 0:
-        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512}[args.workload]
+        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0}[args.workload]
     if args.workload == "jacobi":
         import bench_jacobi
         bench_jacobi.main(args, rank, local_rank, world)
+        return
+    if args.workload == "particles":
+        import bench_jacobi
+        bench_jacobi.particles(args, rank, local_rank, world)
         return
     if args.impl == "reference":
         if thermal:
@@ -278,6 +283,8 @@ def main():
     sim = Driver(gn, comm=comm, arith=args.arith, device=local_rank) if comm else \
         Driver(gn, arith=args.arith, device=local_rank)
     sub = sim.ranks[0]
+    if args.no_overlap:
+        L.check(L.lib().mglc_lbm_set_overlap(sub._h, 0))
     cells_local = int(np.prod(sub.n))
     cells_total = int(np.prod(gn))
     sim.initial()
@@ -345,6 +352,8 @@ def main():
                        "global_lattice": list(gn), "decomposition": "x".join(map(str, dims)),
                        **({"Ra": 1e6, "Pr": 0.71, "Ma": 0.1, "Ek": 1e-3} if thermal else {"Re": 1000.0, "U0": 0.1}),
                        "arith": args.arith, "storage": "SoA fp64, ping-pong, 1-cell halo",
+                       "halo_exchange": "none (1 subdomain)" if world == 1 else ("NCCL send/recv, blocking before the update" if args.no_overlap else
+                                        "NCCL send/recv on a second stream, overlapped with the interior update"),
                        "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % ((26 if thermal else 19) * cells_local * 8 / 1e9),
                        "reduced_to_fit": reduced, "wall_ms_per_step": round(wall_ms / args.steps, 4)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),

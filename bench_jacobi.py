@@ -103,3 +103,56 @@ def main(args, rank, local_rank, world):
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def particles(args, rank, local_rank, world):
+    """bench.py --workload particles: the reference's shipped particle problem (201 x 801 nodes, 64 particles, D2Q9;
+    BASELINE.json config 5 in the reference's own 2-D form).  The whole state is L2-resident (1.4 MB per population
+    set), so a step is bounded by kernel-launch latency, not HBM: the line reports MLUPS and microseconds per step."""
+    import numpy as np
+    import torch
+
+    import bench as B
+    import mglc_b200 as mg
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "MLUPS", "value": None, "note": "particles bench runs on one GPU (161k nodes)"}))
+        return
+    torch.cuda.set_device(local_rank)
+    rng = np.random.default_rng(11)
+    xs, ys, tx, ty = [], [], 25.0, 25.0
+    for _ in range(64):
+        xs.append(tx + (rng.random() - 0.5) * 20); ys.append(ty + (rng.random() - 0.5) * 20)
+        tx += 50.0
+        if tx > 200.0:
+            tx, ty = 25.0, ty + 50.0
+    sim = mg.ParticleChannel(xs, ys, device=local_rank)
+    sim.initial()
+    steps = max(args.steps, 200)
+    sim.step(max(args.warmup, 3)); sim.sync()
+    l0 = sim.launch_count()
+    sampler = B.ClockSampler(local_rank); sampler.start()
+    ms = sim.step_timed(steps)
+    clocks = sampler.stop()
+    launches = sim.launch_count() - l0
+    cells = 201 * 801
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        wd = orc.ParticleWorld(xs, ys, nprocs=1)
+        wd.initial(); wd.step(2)
+        t0 = time.perf_counter(); wd.step(40); dt = time.perf_counter() - t0
+        cpu = {"value": round(cells * 40 / dt / 1e6, 2), "unit": "MLUPS", "cores": 1, "kind": "port",
+               "sample": f"201x801, 64 particles, 40 steps ({dt:.1f} s), oracle/particles2d.c"}
+        wd.close()
+    flags = sim.error_flags()
+    sim.close()
+    print(json.dumps({
+        "metric": "MLUPS", "value": round(cells * steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": "micro_particles_d2q9_201x801_64_particles", "error_flags": flags,
+                                                         "l2": "state is L2-resident by design of the reference problem (161k nodes)"},
+        "roofline": {"bound": "launch latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "launches_per_step": round(launches / steps, 2), "us_per_step": round(ms / steps * 1e3, 2)},
+        "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
