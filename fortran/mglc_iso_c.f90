@@ -12,7 +12,8 @@ module mglc_iso_c
     implicit none
 
     integer(c_int), parameter :: MGLC_OK = 0
-    integer(c_int), parameter :: MGLC_D3Q19 = 0, MGLC_MRT_LID = 0
+    integer(c_int), parameter :: MGLC_D3Q19 = 0, MGLC_D3Q19_D3Q7 = 1, MGLC_MRT_LID = 0, MGLC_MRT_THERMAL = 1
+    integer(c_int), parameter :: MGLC_BCT_ADIABATIC = 0, MGLC_BCT_CONST_HOT = 1, MGLC_BCT_CONST_COLD = 2
     integer(c_int), parameter :: MGLC_ARITH_FAST = 0, MGLC_ARITH_STRICT = 1
 
     !> mglc_lbm_desc: replaces the compile-time parameters of commondata (commondata.f90:4-15,42-53)
@@ -21,8 +22,17 @@ module mglc_iso_c
         integer(c_int) :: gn(3), dims(3), coords(3), ln(3), start(3)
         real(c_double) :: tau, U0, rho0
         integer(c_int) :: device
-        integer(c_int) :: reserved(7)
+        integer(c_int) :: bcT(6)                  ! thermal wall kinds, +x,-x,+y,-y,+z,-z (bouyancy3d_mpi.F90:5-19)
+        integer(c_int) :: reserved(1)
+        real(c_double) :: paraA, gBeta, Tref, Thot, Tcold, omegaRot, Qd, Qnu   ! bouyancy3d_mpi.F90:33-47,73-74
     end type mglc_lbm_desc
+
+    !> mglc_p2d_desc: module commondata of the particle driver (case4/mpi_particle/commondata.F90:3-62)
+    type, bind(C) :: mglc_p2d_desc
+        integer(c_int) :: total_nx, total_ny, nparticles, reserved
+        real(c_double) :: rho0, rhoSolid, viscosity, radius0, gravity
+        real(c_double) :: thresholdWall, stiffWall, thresholdParticle, stiffParticle
+    end type mglc_p2d_desc
 
     interface
         ! ---- host-only helpers -------------------------------------------------------------------
@@ -147,6 +157,169 @@ module mglc_iso_c
         function mglc_host_free(p) bind(C, name="mglc_host_free") result(rc)
             import :: c_int, c_ptr
             type(c_ptr), value :: p
+            integer(c_int) :: rc
+        end function
+
+        ! ---- thermal double-distribution driver (Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90:222-248) --------
+        function mglc_thermal_desc_init(d, gn, dims_or_zero, nranks, rank, rayleigh, prandtl, mach, ekman) &
+                bind(C, name="mglc_thermal_desc_init") result(rc)
+            import :: c_int, c_double, mglc_lbm_desc
+            type(mglc_lbm_desc), intent(out) :: d
+            integer(c_int), intent(in) :: gn(3), dims_or_zero(3)
+            integer(c_int), value :: nranks, rank
+            real(c_double), value :: rayleigh, prandtl, mach, ekman
+            integer(c_int) :: rc
+        end function
+        !> g(0:6,nx,ny,nz), T, Fx, Fy, Fz (nx,ny,nz)
+        function mglc_lbm_upload_thermal(h, g, T, Fx, Fy, Fz) bind(C, name="mglc_lbm_upload_thermal") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: g(*), T(*), Fx(*), Fy(*), Fz(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_lbm_download_thermal(h, g, T, Fx, Fy, Fz) bind(C, name="mglc_lbm_download_thermal") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: g(*), T(*), Fx(*), Fy(*), Fz(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_collisionT(h) bind(C, name="mglc_collisionT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_exchange_g(h) bind(C, name="mglc_exchange_g") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_streamingT(h) bind(C, name="mglc_streamingT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_bouncebackT(h) bind(C, name="mglc_bouncebackT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_macroT(h) bind(C, name="mglc_macroT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_check_thermal(h, errorU, errorT) bind(C, name="mglc_check_thermal") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU, errorT
+            integer(c_int) :: rc
+        end function
+        ! ---- Jacobi driver (MPI/Laplace/fortran/jacobi2d_mpi.f90:94-112) ---------------------------------------------
+        function mglc_jacobi_create(h, ndim, gn, dims_or_zero, nranks, rank, device, comm) bind(C, name="mglc_jacobi_create") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), intent(out) :: h
+            integer(c_int), value :: ndim, nranks, rank, device
+            integer(c_int), intent(in) :: gn(3), dims_or_zero(3)
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        !> A(0:nx+1,0:ny+1[,0:nz+1]) exactly as allocated at jacobi2d_mpi.f90:78-81; c_null_ptr-free variants: pass the arrays
+        function mglc_jacobi_upload(h, r, A, A_new, f) bind(C, name="mglc_jacobi_upload") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(in) :: A(*), A_new(*), f(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_download(h, r, A, A_new) bind(C, name="mglc_jacobi_download") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(out) :: A(*), A_new(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_step(h, nits) bind(C, name="mglc_jacobi_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nits
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_check_diff(h, error_max) bind(C, name="mglc_jacobi_check_diff") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: error_max
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_destroy(h) bind(C, name="mglc_jacobi_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- particle driver (Micro_particles/fortran/case4/mpi_particle/main.F90:35-73) -----------------------------
+        function mglc_p2d_desc_init(d, nparticles) bind(C, name="mglc_p2d_desc_init") result(rc)
+            import :: c_int, mglc_p2d_desc
+            type(mglc_p2d_desc), intent(out) :: d
+            integer(c_int), value :: nparticles
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_create(h, d, dims_or_zero, nranks, rank, device, comm) bind(C, name="mglc_p2d_create") result(rc)
+            import :: c_int, c_ptr, mglc_p2d_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_p2d_desc), intent(in) :: d
+            integer(c_int), intent(in) :: dims_or_zero(2)
+            integer(c_int), value :: nranks, rank, device
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        !> xCenter, yCenter, Uc, Vc, rationalOmega, radius (cNumMax each)
+        function mglc_p2d_set_particles(h, x, y, U, V, omega, radius) bind(C, name="mglc_p2d_set_particles") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: x(*), y(*), U(*), V(*), omega(*), radius(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_get_particles(h, x, y, U, V, omega, Fx, Fy, torque) bind(C, name="mglc_p2d_get_particles") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: x(*), y(*), U(*), V(*), omega(*), Fx(*), Fy(*), torque(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_initial(h) bind(C, name="mglc_p2d_initial") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        !> nsteps x (collision, send_all_fp, streaming, bounceback, bounceback_particle, macro, calForce, send_all_f, updateCenter)
+        function mglc_p2d_step(h, nsteps) bind(C, name="mglc_p2d_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_check(h, errorU) bind(C, name="mglc_p2d_check") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU
+            integer(c_int) :: rc
+        end function
+        !> the reference's stop / MPI_Abort conditions as a flag word; rc = MGLC_E_DIVERGED when any is set
+        function mglc_p2d_error_flags(h, flags) bind(C, name="mglc_p2d_error_flags") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), intent(out) :: flags
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_download(h, r, f, f_post, rho, u, v, obst) bind(C, name="mglc_p2d_download") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(out) :: f(*), f_post(*), rho(*), u(*), v(*)
+            integer(c_int), intent(out) :: obst(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_destroy(h) bind(C, name="mglc_p2d_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
             integer(c_int) :: rc
         end function
     end interface
