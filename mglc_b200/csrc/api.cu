@@ -126,7 +126,8 @@ extern "C" int mglc_comm_destroy(mglc_comm *c) {
 // ---- create / destroy -------------------------------------------------------------------------------
 static int validate(const mglc_lbm_desc *d) {
     if (d->lattice != MGLC_D3Q19 && d->lattice != MGLC_D3Q19_D3Q7) { set_error("mglc_lbm_create: lattice %d not supported by this handle type", d->lattice); return MGLC_E_INVALID; }
-    if (d->collision != (d->lattice == MGLC_D3Q19 ? MGLC_MRT_LID : MGLC_MRT_THERMAL)) { set_error("mglc_lbm_create: collision operator %d not supported with lattice %d", d->collision, d->lattice); return MGLC_E_INVALID; }
+    if (d->collision != (d->lattice == MGLC_D3Q19 ? MGLC_MRT_LID : MGLC_MRT_THERMAL) &&
+        !(d->lattice == MGLC_D3Q19 && d->collision == MGLC_BGK)) { set_error("mglc_lbm_create: collision operator %d not supported with lattice %d", d->collision, d->lattice); return MGLC_E_INVALID; }
     if (d->lattice == MGLC_D3Q19_D3Q7) {
         for (int f = 0; f < 6; ++f)
             if (d->bcT[f] < MGLC_BCT_ADIABATIC || d->bcT[f] > MGLC_BCT_CONST_COLD) { set_error("mglc_lbm_create: bcT[%d]=%d", f, d->bcT[f]); return MGLC_E_INVALID; }
@@ -179,6 +180,7 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
     h->g.lid = h->thermal ? 0 : h->g.wall[4];                     // coords(2) == dims(2)-1, L3/bounce_back.f90:72
     mglc_relaxation_rates(d->tau, &h->p.Snu, &h->p.Sq);
     h->p.U0 = d->U0; h->p.rho0 = d->rho0;
+    h->p.bgk = d->collision == MGLC_BGK;
     if (h->thermal) {
         ThermalParams &tp = h->tp;
         tp.Snu = h->p.Snu; tp.Sq = h->p.Sq; tp.Qd = d->Qd; tp.Qnu = d->Qnu; tp.paraA = d->paraA; tp.gBeta = d->gBeta;

@@ -41,6 +41,7 @@ inline Geom make_geom(int nx, int ny, int nz) {
 
 struct LbmParams {
     double Snu, Sq, U0, rho0;
+    int bgk;             // 1 = MGLC_BGK (L3/collision.f90:191-198), 0 = the MRT operator
 };
 
 // thermal double-distribution path (MGLC_D3Q19_D3Q7), B3 = MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90

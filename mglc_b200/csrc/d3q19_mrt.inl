@@ -210,3 +210,34 @@ __device__ __forceinline__ void d3q19_collide(const double (&f)[19], double rho,
     fp[18] = cyz - (ky + q17) - (kz - q18) + q14;
 }
 #endif
+
+// The single-relaxation-time alternative the reference keeps as a comment block at the end of collision()'s
+// cell loop (L3/collision.f90:191-198): feq as in initial() (L3/initial.f90:63-73), every population relaxed at
+// Snu.  Strict build: the reference's expression order (un = u*ex + v*ey + w*ez with the integer components
+// promoted, rho*omega*(...) left to right).  Fast build: shared 1 - 1.5 us2 and rho*omega, FMA.
+__device__ __forceinline__ void d3q19_collide_bgk(const double (&f)[19], double rho, double u, double v, double w,
+                                                  double Snu, double (&fp)[19]) {
+    constexpr double ex[19] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+    constexpr double ey[19] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+    constexpr double ez[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+    const double us2 = u * u + v * v + w * w;
+#ifdef MGLC_STRICT
+#pragma unroll
+    for (int a = 0; a < 19; ++a) {
+        const double om = a == 0 ? 1.0 / 3.0 : (a < 7 ? 1.0 / 18.0 : 1.0 / 36.0);
+        const double un = u * ex[a] + v * ey[a] + w * ez[a];
+        const double feq = rho * om * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+        fp[a] = f[a] - Snu * (f[a] - feq);
+    }
+#else
+    const double base = 1.0 - 1.5 * us2;
+    const double r0 = rho * (1.0 / 3.0), r1 = rho * (1.0 / 18.0), r2 = rho * (1.0 / 36.0);
+#pragma unroll
+    for (int a = 0; a < 19; ++a) {
+        const double un = ex[a] * u + ey[a] * v + ez[a] * w;        // folds to +-u +-v at compile time
+        const double feq = (a == 0 ? r0 : (a < 7 ? r1 : r2)) * (base + un * (3.0 + 4.5 * un));
+        fp[a] = f[a] + Snu * (feq - f[a]);
+    }
+#endif
+}
+

@@ -51,7 +51,16 @@ __device__ __forceinline__ WallFlags wall_flags(const Geom &g, int i, int j, int
         f[13] = __dsub_rn(f[13], __dmul_rn(r6, -p.U0));                           \
     }
 
+// collision operator selected at compile time: the MRT of L3/collision.f90:20-189 or the BGK alternative of :191-198
+template <bool BGK>
+__device__ __forceinline__ void collide(const double (&f)[19], double rho, double u, double v, double w, const LbmParams &p,
+                                        double (&fp)[19]) {
+    if (BGK) d3q19_collide_bgk(f, rho, u, v, w, p.Snu, fp);
+    else d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
+}
+
 // collision(): F (interior) + rho,u,v,w -> Fpost (interior)
+template <bool BGK>
 __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const double *__restrict__ F,
                                                    const double *__restrict__ rho, const double *__restrict__ u,
                                                    const double *__restrict__ v, const double *__restrict__ w,
@@ -65,12 +74,13 @@ __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const do
     double f[19], fp[19];
 #pragma unroll
     for (int a = 0; a < 19; ++a) f[a] = F[a * sq + c];
-    d3q19_collide(f, rho[m], u[m], v[m], w[m], p.Snu, p.Sq, fp);
+    collide<BGK>(f, rho[m], u[m], v[m], w[m], p, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fpost[a * sq + c] = fp[a];
 }
 
 // fused: pull (streaming) -> wall bounce-back -> macro -> collide -> store
+template <bool BGK>
 __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const double *__restrict__ Fin,
                                                   double *__restrict__ Fout, const double *__restrict__ rho_lid_in,
                                                   double *__restrict__ rho_lid_out, int i0, int i1, int j0, int j1, int k0) {
@@ -86,7 +96,7 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     MGLC_LID(rho_lid_in);
     double rho, u, v, w;
     d3q19_macro(f, rho, u, v, w);
-    d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
+    collide<BGK>(f, rho, u, v, w, p, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
     // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
@@ -121,7 +131,8 @@ static inline dim3 grid_for(int nxs, int nys, int nzs, int tx) { return dim3((nx
 
 int launch_collision(const Geom &g, const LbmParams &p, const double *F, const double *rho, const double *u,
                      const double *v, const double *w, double *Fpost, cudaStream_t s) {
-    k_collision<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, F, rho, u, v, w, Fpost);
+    if (p.bgk) k_collision<true><<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, F, rho, u, v, w, Fpost);
+    else k_collision<false><<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, F, rho, u, v, w, Fpost);
     return 1;
 }
 
@@ -131,7 +142,8 @@ int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *F
     if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
     const dim3 block = nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
     const dim3 grid((nxs + block.x - 1) / block.x, (nys + block.y - 1) / block.y, nzs);
-    k_fused<<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4]);
+    if (p.bgk) k_fused<true><<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4]);
+    else k_fused<false><<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4]);
     return 1;
 }
 

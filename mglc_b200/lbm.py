@@ -51,13 +51,17 @@ def cart_neighbors(dims, coords):
 
 
 def make_desc(total, nranks=1, rank=0, dims=None, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", device=0,
-              kernel=L.KERNEL_AUTO):
+              kernel=L.KERNEL_AUTO, collision="mrt"):
     d = L.LbmDesc()
     dz = (C.c_int * 3)(*(dims if dims else (0, 0, 0)))
     L.check(L.lib().mglc_lbm_desc_init(C.byref(d), (C.c_int * 3)(*total), dz, nranks, rank, Re, U0, rho0))
     d.arith = L.ARITH_STRICT if arith == "strict" else L.ARITH_FAST
     d.device = device
     d.kernel = kernel
+    if collision not in ("mrt", "bgk"):
+        raise ValueError(f"collision must be 'mrt' or 'bgk', not {collision!r}")
+    if collision == "bgk":          # the alternative operator of L3/collision.f90:191-198
+        d.collision = L.BGK
     return d
 
 
@@ -192,7 +196,7 @@ class LidDrivenCavity:
     """D3Q19 MRT lid-driven cavity on B200(s); method names follow L3/main.f90:85-103."""
 
     def __init__(self, total, nprocs=1, dims=None, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", device=0,
-                 devices=None, comm=None, kernel=L.KERNEL_AUTO):
+                 devices=None, comm=None, kernel=L.KERNEL_AUTO, collision="mrt"):
         lib = L.lib()
         self.total = tuple(total)
         self.U0, self.Re, self.rho0 = U0, Re, rho0
@@ -200,21 +204,21 @@ class LidDrivenCavity:
         self._single = None
         self._comm = comm
         if comm is not None:
-            d = make_desc(total, comm.nranks, comm.rank, dims, Re, U0, rho0, arith, comm.device, kernel)
+            d = make_desc(total, comm.nranks, comm.rank, dims, Re, U0, rho0, arith, comm.device, kernel, collision)
             h = C.c_void_p()
             L.check(lib.mglc_lbm_create(C.byref(h), C.byref(d), comm._h))
             self._single = h
             self.ranks = [Subdomain(h)]
             self.nprocs = comm.nranks
         elif nprocs == 1:
-            d = make_desc(total, 1, 0, dims, Re, U0, rho0, arith, device, kernel)
+            d = make_desc(total, 1, 0, dims, Re, U0, rho0, arith, device, kernel, collision)
             h = C.c_void_p()
             L.check(lib.mglc_lbm_create(C.byref(h), C.byref(d), None))
             self._single = h
             self.ranks = [Subdomain(h)]
             self.nprocs = 1
         else:
-            d = make_desc(total, nprocs, 0, dims, Re, U0, rho0, arith, device, kernel)
+            d = make_desc(total, nprocs, 0, dims, Re, U0, rho0, arith, device, kernel, collision)
             g = C.c_void_p()
             dev = (C.c_int * nprocs)(*devices) if devices else None
             L.check(lib.mglc_group_create(C.byref(g), C.byref(d), nprocs, dev))

@@ -44,6 +44,7 @@ typedef struct orc_world {
     int dims[3];
     int np;
     double Re, rho0, U0, tauf, Snu, Sq;
+    int bgk;               /* 1 = the single-relaxation-time alternative, L3/collision.f90:191-198 (commented out there) */
     int itc;
     double errorU;
     orc_rank *r;
@@ -170,12 +171,14 @@ void orc_world_info(orc_world *w, int *dims, double *params /* tauf,Snu,Sq,error
     *itc = w->itc;
 }
 
+/* weights, L3/commondata.f90:29-31 */
+static const double omega[Q] = {1.0 / 3.0,
+    1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0,
+    1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0,
+    1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
+
 /* ---- initial(), L3/initial.f90:1-76 ---------------------------------------------------------- */
 void orc_initial(orc_world *w) {
-    static const double omega[Q] = {1.0 / 3.0,
-        1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0, 1.0 / 18.0,
-        1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0,
-        1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
     w->itc = 0;
     w->errorU = 100.0;
     for (int r = 0; r < w->np; ++r) {
@@ -291,9 +294,31 @@ void orc_collide_cell(const double *f, double rho, double u, double v, double w,
     orc_inverse(mp, fp);
 }
 
+/* The BGK alternative the reference keeps as a comment block at the end of the cell loop
+ * (L3/collision.f90:191-198): feq as in initial(), one rate Snu for every population. */
+void orc_collide_cell_bgk(const double *f, double rho, double u, double v, double w, double Snu, double *fp) {
+    double us2 = u * u + v * v + w * w;
+    for (int a = 0; a < Q; ++a) {
+        double un = u * (double)ex[a] + v * (double)ey[a] + w * (double)ez[a];
+        double feq = rho * omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+        fp[a] = f[a] - Snu * (f[a] - feq);
+    }
+}
+
+void orc_world_set_bgk(orc_world *w, int on) { w->bgk = on ? 1 : 0; }
+
 void orc_collision(orc_world *w) {
     for (int r = 0; r < w->np; ++r) {
         orc_rank *R = &w->r[r];
+        if (w->bgk) {
+#pragma omp parallel for schedule(static)
+            for (int k = 1; k <= R->nz; ++k)
+            for (int j = 1; j <= R->ny; ++j)
+            for (int i = 1; i <= R->nx; ++i)
+                orc_collide_cell_bgk(&F(R, 0, i, j, k), S(R, rho, i, j, k), S(R, u, i, j, k), S(R, v, i, j, k),
+                                     S(R, w, i, j, k), w->Snu, &FP(R, 0, i, j, k));
+            continue;
+        }
 #pragma omp parallel for schedule(static)
         for (int k = 1; k <= R->nz; ++k)
         for (int j = 1; j <= R->ny; ++j)

@@ -47,6 +47,8 @@ def load(native=False):
     lib.orc_inverse.argtypes = [_dp, _dp]
     lib.orc_meq.argtypes = [C.c_double] * 4 + [_dp]
     lib.orc_collide_cell.argtypes = [_dp] + [C.c_double] * 6 + [_dp]
+    lib.orc_collide_cell_bgk.argtypes = [_dp] + [C.c_double] * 5 + [_dp]
+    lib.orc_world_set_bgk.argtypes = [C.c_void_p, C.c_int]
     return lib
 
 
@@ -95,10 +97,13 @@ class Rank:
 class LidWorld:
     """All P emulated ranks of the lid-driven cavity (L3/main.f90) in one process."""
 
-    def __init__(self, total, nprocs=1, dims=None, Re=1000.0, U0=0.1, rho0=1.0, native=False):
+    def __init__(self, total, nprocs=1, dims=None, Re=1000.0, U0=0.1, rho0=1.0, native=False, collision="mrt"):
         self._lib = load(native) if native else lib()
         d = (C.c_int * 3)(*(dims if dims else (0, 0, 0)))
         self._h = self._lib.orc_world_create(total[0], total[1], total[2], nprocs, d, Re, U0, rho0)
+        if collision not in ("mrt", "bgk"):
+            raise ValueError(collision)
+        self._lib.orc_world_set_bgk(self._h, int(collision == "bgk"))   # L3/collision.f90:191-198
         self.total = tuple(total)
         self.nprocs = nprocs
         self.U0, self.Re, self.rho0 = U0, Re, rho0

@@ -25,6 +25,13 @@ void shim_collide(int strict, const double *f, double rho, double u, double v, d
     else fast_ns::d3q19_collide(fi, rho, u, v, w, Snu, Sq, fo);
     for (int a = 0; a < 19; ++a) fp[a] = fo[a];
 }
+void shim_collide_bgk(int strict, const double *f, double rho, double u, double v, double w, double Snu, double *fp) {
+    double fi[19], fo[19];
+    for (int a = 0; a < 19; ++a) fi[a] = f[a];
+    if (strict) strict_ns::d3q19_collide_bgk(fi, rho, u, v, w, Snu, fo);
+    else fast_ns::d3q19_collide_bgk(fi, rho, u, v, w, Snu, fo);
+    for (int a = 0; a < 19; ++a) fp[a] = fo[a];
+}
 void shim_macro(const double *f, double *out4) {
     double fi[19];
     for (int a = 0; a < 19; ++a) fi[a] = f[a];

@@ -119,6 +119,7 @@ def shim(tmp_path_factory):
     dp = C.POINTER(C.c_double)
     S.shim_collide.argtypes = [C.c_int, dp] + [C.c_double] * 6 + [dp]
     S.shim_macro.argtypes = [dp, dp]
+    S.shim_collide_bgk.argtypes = [C.c_int, dp] + [C.c_double] * 5 + [dp]
     return S
 
 
@@ -144,6 +145,25 @@ def test_kernel_arithmetic_source_matches_oracle(shim):
             r = r + f[q]
         su = sum_in_order(f, orc.EX)
         assert m[0] == r and m[1] == su / r
+    assert worst < 1e-15
+
+
+def test_bgk_arithmetic_source_matches_oracle(shim):
+    """d3q19_collide_bgk (L3/collision.f90:191-198) compiled for the host: strict == oracle bitwise, fast to rounding."""
+    dp = C.POINTER(C.c_double)
+    O = orc.lib()
+    rng = np.random.default_rng(43)
+    worst = 0.0
+    for _ in range(3000):
+        rho = 1 + 0.05 * rng.uniform(-1, 1)
+        u, v, w = 0.1 * rng.uniform(-1, 1, 3)
+        f = np.ascontiguousarray(orc.feq(rho, u, v, w) * (1 + 0.05 * rng.uniform(-1, 1, 19)))
+        a, b, c = np.zeros(19), np.zeros(19), np.zeros(19)
+        O.orc_collide_cell_bgk(f.ctypes.data_as(dp), rho, u, v, w, 1 / 0.5195, a.ctypes.data_as(dp))
+        shim.shim_collide_bgk(1, f.ctypes.data_as(dp), rho, u, v, w, 1 / 0.5195, b.ctypes.data_as(dp))
+        shim.shim_collide_bgk(0, f.ctypes.data_as(dp), rho, u, v, w, 1 / 0.5195, c.ctypes.data_as(dp))
+        assert np.array_equal(a, b)
+        worst = max(worst, np.abs(a - c).max())
     assert worst < 1e-15
 
 

@@ -34,8 +34,8 @@ def seeded_state(total, seed=1234):
     return f, rho, u, v, w
 
 
-def oracle_world(total, nprocs=1, dims=None, seed=None):
-    wd = orc.LidWorld(total, nprocs, dims=dims)
+def oracle_world(total, nprocs=1, dims=None, seed=None, collision="mrt"):
+    wd = orc.LidWorld(total, nprocs, dims=dims, collision=collision)
     wd.initial()
     if seed is not None:
         f, rho, u, v, w = seeded_state(total, seed)
@@ -44,8 +44,8 @@ def oracle_world(total, nprocs=1, dims=None, seed=None):
     return wd
 
 
-def gpu_world(total, nprocs=1, dims=None, seed=None, arith="strict"):
-    sim = mg.LidDrivenCavity(total, nprocs=nprocs, dims=dims, arith=arith)
+def gpu_world(total, nprocs=1, dims=None, seed=None, arith="strict", collision="mrt"):
+    sim = mg.LidDrivenCavity(total, nprocs=nprocs, dims=dims, arith=arith, collision=collision)
     sim.initial()
     if seed is not None:
         sim.scatter(*seeded_state(total, seed))
@@ -155,6 +155,49 @@ def test_fused_step_strict_is_bit_exact(total, nsteps):
     wd.step(3); sim.step(3)
     assert np.array_equal(sim.gather("f"), wd.gather("f"))
     wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_bgk_collision(arith):
+    """The BGK alternative of L3/collision.f90:191-198 (MGLC_BGK): strict bit-exact, fast to rounding."""
+    total = (21, 10, 11)
+    wd = oracle_world(total, seed=98, collision="bgk")
+    sim = gpu_world(total, seed=98, arith=arith, collision="bgk")
+    wd.collision(); sim.collision()
+    nx, ny, nz = total
+    want = wd.ranks[0].f_post[:, 1:nx + 1, 1:ny + 1, 1:nz + 1]
+    got = sim.ranks[0].download_fpost()[:, 1:nx + 1, 1:ny + 1, 1:nz + 1]
+    if arith == "strict":
+        assert np.array_equal(got, want)
+    else:
+        assert np.abs(got - want).max() < 1e-15
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("nprocs", [1, 4])
+def test_bgk_step(nprocs):
+    """N loop bodies with the BGK operator: strict bit-exact (1 and 4 subdomains), fast within the north-star tolerance."""
+    total, nsteps = (33, 18, 14), 40
+    wd = orc.LidWorld(total, 1, collision="bgk")
+    wd.initial(); wd.step(nsteps)
+    for arith in ("strict", "fast"):
+        sim = mg.LidDrivenCavity(total, nprocs=nprocs, arith=arith, collision="bgk")
+        sim.initial(); sim.step(nsteps)
+        m = sim.gather_macro()
+        for k in ("rho", "u", "v", "w"):
+            ref = wd.gather(k)
+            if arith == "strict":
+                assert np.array_equal(m[k], ref), k
+            else:
+                assert rel_l2(m[k], ref) <= REL_L2 and np.abs(m[k] - ref).max() <= MAX_ABS, k
+        if arith == "strict":
+            assert np.array_equal(sim.gather("f"), wd.gather("f"))
+        sim.close()
+    # and it really is a different operator from the MRT one
+    mrt = orc.LidWorld(total, 1)
+    mrt.initial(); mrt.step(nsteps)
+    assert np.abs(mrt.gather("u") - wd.gather("u")).max() > 1e-6
+    mrt.close(); wd.close()
 
 
 def test_unfused_sequence_equals_fused_step():

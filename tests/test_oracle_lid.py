@@ -313,3 +313,68 @@ def test_macro_and_feq_match_reference_source_bit_for_bit():
     r = REF_GOLD["lid_feq/ruvw"]
     assert np.array_equal(orc.feq(r[:, 0], r[:, 1], r[:, 2], r[:, 3]).T, REF_GOLD["lid_feq/f"])
     wd.close()
+
+
+# ---- the BGK alternative (L3/collision.f90:191-198, a comment block in the reference) ----------------------
+
+def test_bgk_equilibrium_is_fixed_point_and_conserves_moments():
+    L = orc.lib()
+    L.orc_collide_cell_bgk.argtypes = [dp] + [C.c_double] * 5 + [dp]
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        rho = 1 + 0.05 * rng.uniform(-1, 1)
+        u, v, w = 0.1 * rng.uniform(-1, 1, 3)
+        fe, fep = _vec(orc.feq(rho, u, v, w))
+        out, outp = _vec(np.zeros(19))
+        L.orc_collide_cell_bgk(fep, rho, u, v, w, 1.7, outp)
+        assert np.abs(out - fe).max() < 1e-16            # f = feq  ->  f_post = feq
+        # a perturbed state relaxes toward feq at rate Snu and keeps rho and rho*u (moments of f == of feq)
+        f, fp = _vec(fe * (1 + 0.05 * rng.uniform(-1, 1, 19)))
+        r = f.sum()
+        uu, vv, ww = (f * orc.EX).sum() / r, (f * orc.EY).sum() / r, (f * orc.EZ).sum() / r
+        L.orc_collide_cell_bgk(fp, r, uu, vv, ww, 1.7, outp)
+        assert abs(out.sum() - r) < 1e-14
+        for e, q in ((orc.EX, uu), (orc.EY, vv), (orc.EZ, ww)):
+            assert abs((out * e).sum() - r * q) < 1e-14
+        assert np.allclose(out, f - 1.7 * (f - orc.feq(r, uu, vv, ww)), rtol=0, atol=1e-16)
+
+
+def test_bgk_is_mrt_with_equal_rates_when_quirk_vanishes():
+    """With every relaxation rate equal the MRT operator is f - s (f - M^-1 meq); M^-1 meq is the second-order feq
+    except for the rho-less meq(12) (L3/collision.f90:85), which vanishes when v^2 == w^2.  An independent pin that
+    ties the BGK restatement to the MRT one (transforms, meq and feq)."""
+    L = orc.lib()
+    L.orc_collide_cell_bgk.argtypes = [dp] + [C.c_double] * 5 + [dp]
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        fe = orc.feq(1 + 0.05 * rng.uniform(-1, 1), *(0.1 * rng.uniform(-1, 1, 3)))
+        f, fp = _vec(fe * (1 + 0.05 * rng.uniform(-1, 1, 19)))
+        # symmetrise so that the y and z momenta agree: swap-average the y<->z mirrored populations
+        perm = [0, 1, 2, 5, 6, 3, 4, 11, 12, 13, 14, 7, 8, 9, 10, 15, 17, 16, 18]
+        f[:] = 0.5 * (f + f[perm])
+        r = f.sum()
+        uu, vv, ww = (f * orc.EX).sum() / r, (f * orc.EY).sum() / r, (f * orc.EZ).sum() / r
+        assert abs(vv - ww) < 1e-16
+        ww = vv
+        s = 1.0 / 0.62
+        a, ap = _vec(np.zeros(19))
+        b, bp = _vec(np.zeros(19))
+        L.orc_collide_cell_bgk(fp, r, uu, vv, ww, s, ap)
+        L.orc_collide_cell(fp, r, uu, vv, ww, s, s, bp)
+        # the conserved moments have rate 0 in the MRT table; with rho,u the true moments of f that changes nothing
+        assert np.abs(a - b).max() < 5e-16
+
+
+@pytest.mark.parametrize("nprocs", [2, 8])
+def test_bgk_run_decomposition_invariant_and_mass_conserving(nprocs):
+    total = (11, 9, 8)
+    one = orc.LidWorld(total, 1, collision="bgk")
+    many = orc.LidWorld(total, nprocs, collision="bgk")
+    one.initial(); many.initial()
+    m0 = one.gather("f").sum()
+    one.step(12); many.step(12)
+    for k in ("rho", "u", "v", "w", "f"):
+        assert np.array_equal(one.gather(k), many.gather(k)), k
+    assert abs(one.gather("f").sum() - m0) < 1e-10
+    assert np.isfinite(one.gather("f")).all()
+    one.close(); many.close()
