@@ -42,7 +42,11 @@ def parse_args():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="mglc", choices=["mglc", "reference"])
-    p.add_argument("--no-overlap", action="store_true", help="exchange halos, THEN update (blocking schedule) instead of overlapping")
+    p.add_argument("--no-overlap", action="store_true", help="same as --halo blocking")
+    p.add_argument("--halo", default="auto", choices=["auto", "direct", "overlap", "blocking"],
+                   help="multi-GPU halo transport of the fused step: direct = stores into the neighbours' halos over NVLink "
+                        "(CUDA IPC), overlap = NCCL exchange beside the interior update, blocking = NCCL exchange, then update; "
+                        "auto = direct when the mappings came up, else overlap")
     p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi", "particles"],
                    help="lid = BASELINE.json's metric (default); thermal / jacobi = the other configs, for profiles/")
     p.add_argument("--size", type=int, default=0, help="per-GPU block edge (weak) / global edge (strong); 0 = the workload's config size")
@@ -284,7 +288,13 @@ def main():
         Driver(gn, arith=args.arith, device=local_rank)
     sub = sim.ranks[0]
     if args.no_overlap:
-        L.check(L.lib().mglc_lbm_set_overlap(sub._h, 0))
+        args.halo = "blocking"
+    avail = C.c_int()
+    L.check(L.lib().mglc_lbm_direct_halo(sub._h, C.byref(avail)))
+    if args.halo == "auto":
+        args.halo = "direct" if avail.value else "overlap"
+    if world > 1:
+        L.check(L.lib().mglc_lbm_set_overlap(sub._h, {"direct": 2, "overlap": 1, "blocking": 0}[args.halo]))
     cells_local = int(np.prod(sub.n))
     cells_total = int(np.prod(gn))
     sim.initial()
@@ -352,8 +362,10 @@ def main():
                        "global_lattice": list(gn), "decomposition": "x".join(map(str, dims)),
                        **({"Ra": 1e6, "Pr": 0.71, "Ma": 0.1, "Ek": 1e-3} if thermal else {"Re": 1000.0, "U0": 0.1}),
                        "arith": args.arith, "storage": "SoA fp64, ping-pong, 1-cell halo",
-                       "halo_exchange": "none (1 subdomain)" if world == 1 else ("NCCL send/recv, blocking before the update" if args.no_overlap else
-                                        "NCCL send/recv on a second stream, overlapped with the interior update"),
+                       "halo_exchange": "none (1 subdomain)" if world == 1 else {
+                           "direct": "fused kernel stores outgoing populations into the neighbours' halos over NVLink (CUDA IPC) + flag barrier",
+                           "overlap": "NCCL send/recv on a second stream, overlapped with the interior update",
+                           "blocking": "NCCL send/recv, blocking before the update"}[args.halo],
                        "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % ((26 if thermal else 19) * cells_local * 8 / 1e9),
                        "reduced_to_fit": reduced, "wall_ms_per_step": round(wall_ms / args.steps, 4)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),

@@ -181,9 +181,21 @@ int mglc_lbm_launch_count(mglc_lbm *h, long long *n);
 /* per-launch CUDA-event timing of the fused kernel on its launching stream (off by default);
  * mglc_lbm_kernel_time returns and resets the accumulated device time and launch count */
 int mglc_lbm_set_profiling(mglc_lbm *h, int on);
-/* comm/compute overlap of the fused step (boundary shell -> exchange on a second stream || interior), the schedule of
- * collision_with_message_exchange, lid3_mpi_nonblock.f90:1108-1230.  On by default; 0 = exchange, then update. */
-int mglc_lbm_set_overlap(mglc_lbm *h, int on);
+/* How the fused step moves halos between subdomains (mode):
+ *   2  direct halo stores: the fused kernel writes the outgoing populations of its boundary cells straight into the
+ *      neighbours' halo cells over NVLink (peer access inside one process, CUDA IPC mappings between processes, set up
+ *      collectively by mglc_lbm_create / mglc_group_create), followed by a flag barrier between neighbours.  No pack,
+ *      send/recv or unpack; the transfer overlaps the update cell by cell.  Default when the mappings exist.
+ *   1  overlapped exchange: boundary shell first, pack -> ncclSend/ncclRecv -> unpack on a second stream beside the
+ *      interior update, the schedule of collision_with_message_exchange, lid3_mpi_nonblock.f90:1108-1230.
+ *      Default otherwise.
+ *   0  blocking exchange, then update: message_passing_sendrecv() as the blocking driver does it, L3/main.f90:89-93.
+ * With mode 2 every call that leaves the fused loop (upload, download, the per-subroutine entry points) must be made
+ * by all ranks between the same two mglc_lbm_step calls, like the reference's subroutines; a rank out of step is
+ * reported by mglc_lbm_sync / mglc_check as MGLC_E_STATE instead of hanging. */
+int mglc_lbm_set_overlap(mglc_lbm *h, int mode);
+/* 1 if the direct-halo mappings of mode 2 are established for this handle */
+int mglc_lbm_direct_halo(mglc_lbm *h, int *available);
 int mglc_lbm_kernel_time(mglc_lbm *h, float *fused_ms, long long *fused_launches);
 /* page-locked host memory for the caller's f / rho,u,v,w arrays (c_f_pointer on the Fortran side), so
  * upload/download run at full PCIe rate; pageable pointers are accepted everywhere too */

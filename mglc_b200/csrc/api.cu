@@ -52,6 +52,18 @@ struct mglc_lbm {
     bool has_neighbors;
     mglc_comm *comm;
     mglc_group *group;
+    // direct halo stores (PeerTable, common.cuh): overlap == 2.  pt_dev[b] is the table for a launch that writes
+    // buf[b]; flags = the 32 barrier words neighbours raise; epoch counts direct launches; direct_valid: the halos
+    // of the lattice written last are being filled by the neighbours' launches of the same epoch
+    int direct, direct_valid;
+    PeerTable *pt_dev[2];
+    SyncTable sync;
+    unsigned long long *flags, epoch;
+    int parity_sent;                     // ping-pong index of the lattice my last direct launch wrote (neighbours must agree)
+    int *d_err;
+    int nbr_rank[19];                    // rank at coords + e_d, -1 = none
+    cudaEvent_t ev_done[2];              // group mode: my direct launch of epoch e is recorded in ev_done[e & 1]
+    std::vector<void *> *ipc_opened;     // comm mode: mappings to close on destroy
     double *stage;           // device staging for AoS<->SoA transposes
     long long stage_doubles;
     // optional per-launch timing of the fused kernel (CUDA events on the launching stream)
@@ -145,10 +157,15 @@ static int validate(const mglc_lbm_desc *d) {
     return MGLC_OK;
 }
 
+static int wait_direct(mglc_lbm *h);
 extern "C" int mglc_lbm_destroy(mglc_lbm *h) {
     if (!h) return MGLC_OK;
     cudaSetDevice(h->d.device);
+    if (h->direct && h->direct_valid && h->s) wait_direct(h);      // neighbours may still be storing into my halos
     cudaDeviceSynchronize();
+    if (h->ipc_opened) { for (void *q : *h->ipc_opened) cudaIpcCloseMemHandle(q); delete h->ipc_opened; }
+    cudaFree(h->pt_dev[0]); cudaFree(h->pt_dev[1]); cudaFree(h->flags); cudaFree(h->d_err);
+    for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
     double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage, h->rho_lid[0], h->rho_lid[1],
                         h->gbuf[0], h->gbuf[1], h->T, h->Tp, h->Fc[0], h->Fc[1]};
@@ -250,8 +267,122 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
             if (M.recv_count && (rc = dmalloc(h, &M.rbuf, M.recv_count))) return fail(rc);
         }
     }
+    // neighbour table and the barrier words of the direct-halo path (set up by setup_direct_* once peers are known)
+    for (int dd = 0; dd < 19; ++dd) {
+        h->nbr_rank[dd] = -1;
+        if (dd == 6) continue;
+        const int e[3] = {dd < 6 ? (dd >> 1 == 0 ? 1 - 2 * (dd & 1) : 0) : h_ex[dd], dd < 6 ? (dd >> 1 == 1 ? 1 - 2 * (dd & 1) : 0) : h_ey[dd],
+                          dd < 6 ? (dd >> 1 == 2 ? 1 - 2 * (dd & 1) : 0) : h_ez[dd]};
+        const int c[3] = {d->coords[0] + e[0], d->coords[1] + e[1], d->coords[2] + e[2]};
+        mglc_cart_rank(d->dims, c, &h->nbr_rank[dd]);
+    }
+    if (cudaMalloc((void **)&h->flags, 32 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc((void **)&h->d_err, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->pt_dev[0], sizeof(PeerTable)) != cudaSuccess || cudaMalloc((void **)&h->pt_dev[1], sizeof(PeerTable)) != cudaSuccess)
+        return fail(MGLC_E_NOMEM);
+    cudaMemsetAsync(h->flags, 0, 32 * sizeof(unsigned long long), h->s);
+    cudaMemsetAsync(h->d_err, 0, sizeof(int), h->s);
+    for (cudaEvent_t &e : h->ev_done) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(MGLC_E_CUDA);
     if (cudaStreamSynchronize(h->s) != cudaSuccess) return fail(MGLC_E_CUDA);
     *out = h;
+    return MGLC_OK;
+}
+
+// ---- direct halo stores: wiring ------------------------------------------------------------------------------
+static inline int opp_dir(int d) { return d < 6 ? (d ^ 1) : h_opp[d]; }
+struct PeerView { double *buf[2], *gbuf[2]; unsigned long long *flags; int ln[3]; };
+// fill pt_dev[0..1] and sync from the neighbours' lattices as seen from this GPU
+static int install_peers(mglc_lbm *h, const PeerView *view /* [19], valid where nbr_rank >= 0 */) {
+    PeerTable pt[2];
+    memset(pt, 0, sizeof pt);
+    memset(&h->sync, 0, sizeof h->sync);
+    for (int d = 0; d < 19; ++d) {
+        if (d == 6 || h->nbr_rank[d] < 0) continue;
+        const Geom pg = make_geom(view[d].ln[0], view[d].ln[1], view[d].ln[2]);
+        for (int b = 0; b < 2; ++b) {
+            pt[b].mask |= 1u << d;
+            pt[b].F[d] = view[d].buf[b];
+            if (d < 6) pt[b].G[d] = view[d].gbuf[b];
+            pt[b].sy[d] = pg.sy; pt[b].sz[d] = pg.sz; pt[b].sq[d] = pg.sq;
+            pt[b].n[d][0] = pg.nx; pt[b].n[d][1] = pg.ny; pt[b].n[d][2] = pg.nz;
+        }
+        h->sync.mask |= 1u << d;
+        h->sync.signal[d] = view[d].flags + opp_dir(d);     // the neighbour sees me in the opposite direction
+        h->sync.wait[d] = h->flags + d;
+    }
+    for (int b = 0; b < 2; ++b) MGLC_CUDA(cudaMemcpy(h->pt_dev[b], &pt[b], sizeof(PeerTable), cudaMemcpyHostToDevice));
+    h->direct = 1;
+    return MGLC_OK;
+}
+// one process per GPU: exchange CUDA IPC handles of the lattices and the barrier words through the communicator,
+// map the neighbours' allocations (peer access over NVLink) and agree collectively on whether the path is usable
+struct IpcRecord { cudaIpcMemHandle_t buf[2], gbuf[2], flags; int ln[3]; int thermal; };
+static int setup_direct_ipc(mglc_lbm *h) {
+    if (!h->comm || h->nranks < 2 || getenv("MGLC_NO_DIRECT")) return MGLC_OK;
+    const int P = h->nranks;
+    IpcRecord mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = 1;
+    const unsigned long long magic = 0x6d676c6300000000ull + (unsigned long long)h->rank;
+    ok &= cudaMemcpy(h->flags + 31, &magic, sizeof magic, cudaMemcpyHostToDevice) == cudaSuccess;
+    for (int b = 0; b < 2; ++b) {
+        ok &= cudaIpcGetMemHandle(&mine.buf[b], h->buf[b]) == cudaSuccess;
+        if (h->thermal) ok &= cudaIpcGetMemHandle(&mine.gbuf[b], h->gbuf[b]) == cudaSuccess;
+    }
+    ok &= cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
+    (void)cudaGetLastError();
+    for (int q = 0; q < 3; ++q) mine.ln[q] = h->d.ln[q];
+    mine.thermal = h->thermal;
+    char *dev_all = nullptr;
+    MGLC_CUDA(cudaMalloc((void **)&dev_all, (size_t)(P + 1) * sizeof(IpcRecord)));
+    MGLC_CUDA(cudaMemcpy(dev_all + (size_t)P * sizeof(IpcRecord), &mine, sizeof mine, cudaMemcpyHostToDevice));
+    MGLC_NCCL(ncclAllGather(dev_all + (size_t)P * sizeof(IpcRecord), dev_all, sizeof(IpcRecord), ncclChar, h->comm->nccl, h->s));
+    std::vector<IpcRecord> all(P);
+    MGLC_CUDA(cudaMemcpyAsync(all.data(), dev_all, (size_t)P * sizeof(IpcRecord), cudaMemcpyDeviceToHost, h->s));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    cudaFree(dev_all);
+    h->ipc_opened = new std::vector<void *>();
+    std::vector<PeerView> by_rank(P);
+    std::vector<char> have(P, 0);
+    PeerView view[19];
+    memset(view, 0, sizeof view);
+    auto open = [&](const cudaIpcMemHandle_t &hd, void **out) {
+        if (cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); *out = nullptr; return 0; }
+        h->ipc_opened->push_back(*out);
+        return 1;
+    };
+    for (int d = 0; d < 19 && ok; ++d) {
+        const int r = h->nbr_rank[d];
+        if (d == 6 || r < 0) continue;
+        if (!have[r]) {
+            PeerView &v = by_rank[r];
+            memset(&v, 0, sizeof v);
+            for (int b = 0; b < 2 && ok; ++b) {
+                ok &= open(all[r].buf[b], (void **)&v.buf[b]);
+                if (h->thermal && ok) ok &= open(all[r].gbuf[b], (void **)&v.gbuf[b]);
+            }
+            if (ok) ok &= open(all[r].flags, (void **)&v.flags);
+            if (ok) {           // the mapping must start at the neighbour's own pointer, not at some enclosing block
+                unsigned long long seen = 0;
+                ok &= cudaMemcpy(&seen, v.flags + 31, sizeof seen, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                      seen == 0x6d676c6300000000ull + (unsigned long long)r;
+                (void)cudaGetLastError();
+            }
+            for (int q = 0; q < 3; ++q) v.ln[q] = all[r].ln[q];
+            have[r] = 1;
+        }
+        view[d] = by_rank[r];
+    }
+    // collective verdict: everybody or nobody
+    int *dev_ok = nullptr;
+    MGLC_CUDA(cudaMalloc((void **)&dev_ok, sizeof(int)));
+    MGLC_CUDA(cudaMemcpy(dev_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
+    MGLC_NCCL(ncclAllReduce(dev_ok, dev_ok, 1, ncclInt, ncclMin, h->comm->nccl, h->s));
+    MGLC_CUDA(cudaMemcpyAsync(&ok, dev_ok, sizeof ok, cudaMemcpyDeviceToHost, h->s));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    cudaFree(dev_ok);
+    if (!ok) return MGLC_OK;                     // stay on the NCCL transport
+    MGLC_TRY(install_peers(h, view));
+    h->overlap = 2;
     return MGLC_OK;
 }
 
@@ -261,7 +392,12 @@ extern "C" int mglc_lbm_create(mglc_lbm **h, const mglc_lbm_desc *d, mglc_comm *
                   d->dims[0], d->dims[1], d->dims[2]);
         return MGLC_E_INVALID;
     }
-    return create_impl(h, d, comm_or_null);
+    MGLC_TRY(create_impl(h, d, comm_or_null));
+    if (comm_or_null && (*h)->has_neighbors) {
+        const int rc = setup_direct_ipc(*h);        // collective over the communicator; failure to map = NCCL transport
+        if (rc) { mglc_lbm_destroy(*h); *h = nullptr; return rc; }
+    }
+    return MGLC_OK;
 }
 
 extern "C" int mglc_lbm_get_desc(mglc_lbm *h, mglc_lbm_desc *d) {
@@ -284,6 +420,12 @@ extern "C" int mglc_lbm_sync(mglc_lbm *h) {
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s_comm));
     MGLC_CUDA(cudaGetLastError());
+    if (h->direct) {
+        int e = 0;
+        MGLC_CUDA(cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
+        if (e & 1) { set_error("direct halo path: a neighbour did not reach the barrier within 20 s (ranks out of step?)"); return MGLC_E_STATE; }
+        if (e & 2) { set_error("direct halo path: a neighbour wrote the other ping-pong lattice (calls between mglc_lbm_step must be made by every rank)"); return MGLC_E_STATE; }
+    }
     return MGLC_OK;
 }
 
@@ -542,14 +684,55 @@ static int do_fused(mglc_lbm *h) {
     fused_swap(h, io);
     return fused_end(h);
 }
+// Direct-halo step: one launch over the whole subdomain that also stores the outgoing populations of its boundary
+// cells into the neighbours' halos over NVLink (PeerTable), then the signal half of the neighbour barrier.  Nothing
+// is packed, sent or unpacked; the transfer rides along with the update, tile by tile.
+static int do_fused_direct(mglc_lbm *h) {
+    const int box[6] = {1, h->g.nx, 1, h->g.ny, 1, h->g.nz};
+    FusedIO io;
+    MGLC_TRY(fused_begin(h, io));
+    const PeerTable *pt = h->pt_dev[h->cur];                 // io.Fout == buf[cur]: the neighbours write the same parity
+    if (h->thermal)
+        h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt)
+                                  : fast::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt);
+    else
+        h->launches += strict_(h) ? strict::launch_fused(h->g, h->p, io.Fin, io.Fout, io.lid_in, io.lid_out, box, h->s, pt)
+                                  : fast::launch_fused(h->g, h->p, io.Fin, io.Fout, io.lid_in, io.lid_out, box, h->s, pt);
+    const int parity = h->cur;                               // of the lattice just written (before the swap)
+    fused_swap(h, io);
+    MGLC_TRY(fused_end(h));
+    h->epoch += 1;
+    h->parity_sent = parity;
+    if (h->group) MGLC_CUDA(cudaEventRecord(h->ev_done[h->epoch & 1], h->s));
+    else h->launches += launch_halo_signal(h->sync, h->epoch * 2 + (unsigned long long)parity, h->s);
+    h->direct_valid = 1;
+    return MGLC_OK;
+}
+// the wait half: every neighbour has finished the launch of my current epoch (its stores into my halos are complete,
+// and it no longer reads the halos my next launch will overwrite)
+static mglc_lbm *group_member(mglc_group *g, int r);
+static int wait_direct(mglc_lbm *h) {
+    if (h->group) {
+        for (int d = 0; d < 19; ++d) {
+            if (d == 6 || h->nbr_rank[d] < 0) continue;
+            MGLC_CUDA(cudaStreamWaitEvent(h->s, group_member(h->group, h->nbr_rank[d])->ev_done[h->epoch & 1], 0));
+        }
+    } else h->launches += launch_halo_wait(h->sync, h->epoch * 2 + (unsigned long long)h->parity_sent, h->d_err, h->s);
+    h->direct_valid = 0;
+    return MGLC_OK;
+}
 // Overlapped step (the schedule of L3nb collision_with_message_exchange, :1108-1230): the cells next to a
 // NEIGHBOUR face first (thin slabs: one plane in y and z, 32 cells in x so a warp still stores full lines),
 // then their populations are packed, exchanged and unpacked on s_comm while the interior runs on s.
-constexpr int SHELL_X = 32;
+static int shell_x() {
+    static int v = 0;
+    if (!v) { v = 32; if (const char *e = getenv("MGLC_SHELL_X")) v = std::max(1, std::min(128, atoi(e))); }
+    return v;
+}
 static int do_fused_overlapped(mglc_lbm *h) {
     const Geom &g = h->g;
     const int n[3] = {g.nx, g.ny, g.nz};
-    const int want[3] = {SHELL_X, 1, 1};
+    const int want[3] = {shell_x(), 1, 1};
     int lo[3], hi[3];                 // interior box per axis
     for (int d = 0; d < 3; ++d) {
         const bool nb_plus = !g.wall[2 * d], nb_minus = !g.wall[2 * d + 1];
@@ -609,6 +792,7 @@ static int canonicalise(mglc_lbm *h) {
         MGLC_CUDA(cudaStreamWaitEvent(h->s, h->ev_halo, 0));
         h->halo_inflight = 0;
     }
+    if (h->direct_valid) MGLC_TRY(wait_direct(h));
     h->cur ^= 1;
     MGLC_TRY(do_stream_macro(h));
     h->rotated = 0;
@@ -743,11 +927,14 @@ static int step_impl(mglc_lbm *h, int nsteps) {
         MGLC_TRY(do_collision(h));
         if (h->thermal) MGLC_TRY(do_collisionT(h));
     }
-    const bool overlapped = h->overlap && h->has_neighbors && h->comm;
+    const bool direct = h->overlap == 2 && h->direct && h->has_neighbors && h->comm;
+    const bool overlapped = h->overlap == 1 && h->has_neighbors && h->comm;
     for (int it = 0; it < nsteps; ++it) {
-        if (h->halo_inflight) MGLC_TRY(halos_for_next_step(h));   // exchange of step it already ran beside the last interior
+        if (h->direct_valid) MGLC_TRY(wait_direct(h));            // the neighbours' launches stored the halos of step it
+        else if (h->halo_inflight) MGLC_TRY(halos_for_next_step(h));   // exchange of step it already ran beside the last interior
         else MGLC_TRY(do_exchange_nccl(h));                       // exchange of step it
-        if (overlapped) MGLC_TRY(do_fused_overlapped(h));
+        if (direct) MGLC_TRY(do_fused_direct(h));
+        else if (overlapped) MGLC_TRY(do_fused_overlapped(h));
         else MGLC_TRY(do_fused(h));                  // streaming+bounceback+macro of step it, collision of it+1
     }
     h->rotated = 1;
@@ -777,7 +964,14 @@ extern "C" int mglc_lbm_step_timed(mglc_lbm *h, int nsteps, float *ms) {
 extern "C" int mglc_lbm_set_overlap(mglc_lbm *h, int on) {
     MGLC_TRY(use(h));
     MGLC_TRY(canonicalise(h));
-    h->overlap = on ? 1 : 0;
+    if (on < 0 || on > 2) { set_error("mglc_lbm_set_overlap: mode %d (0 blocking, 1 overlapped exchange, 2 direct halo stores)", on); return MGLC_E_INVALID; }
+    if (on == 2 && !h->direct && h->has_neighbors) { set_error("mglc_lbm_set_overlap: the neighbours' lattices are not mapped on this GPU"); return MGLC_E_STATE; }
+    h->overlap = on;
+    return MGLC_OK;
+}
+extern "C" int mglc_lbm_direct_halo(mglc_lbm *h, int *available) {
+    if (!h || !available) return MGLC_E_INVALID;
+    *available = h->direct;
     return MGLC_OK;
 }
 extern "C" int mglc_lbm_set_profiling(mglc_lbm *h, int on) {
@@ -810,6 +1004,8 @@ extern "C" int mglc_host_free(void *p) {
 // ---- P subdomains in one process ----------------------------------------------------------------------------
 extern "C" int mglc_group_destroy(mglc_group *g) {
     if (!g) return MGLC_OK;
+    // quiesce every member before the first one is freed: neighbours store into each other's halos
+    for (mglc_lbm *h : g->r) { cudaSetDevice(h->d.device); cudaDeviceSynchronize(); h->direct_valid = 0; }
     for (mglc_lbm *h : g->r) mglc_lbm_destroy(h);
     delete g;
     return MGLC_OK;
@@ -844,6 +1040,28 @@ extern "C" int mglc_group_create(mglc_group **out, const mglc_lbm_desc *gd, int 
                 if (can) { cudaSetDevice(a->d.device); cudaDeviceEnablePeerAccess(b->d.device, 0); (void)cudaGetLastError(); }
             }
     for (mglc_lbm *h : g->r) g->ports.push_back(Port{h->d.device, h->s, h->ev_packed, h->ev_copied, h->msgs, h->nmsgs});
+    // direct halo stores inside one process: the neighbours' lattices are plain device pointers (same device, or peer
+    // access enabled above); ordering goes through events instead of flag words
+    bool reachable = nranks > 1 && !getenv("MGLC_NO_DIRECT");
+    for (mglc_lbm *a : g->r)
+        for (mglc_lbm *b : g->r)
+            if (reachable && a->d.device != b->d.device) { int can = 0; cudaDeviceCanAccessPeer(&can, a->d.device, b->d.device); reachable = can != 0; }
+    if (reachable)
+        for (mglc_lbm *h : g->r) {
+            PeerView view[19];
+            memset(view, 0, sizeof view);
+            for (int dd = 0; dd < 19; ++dd) {
+                if (dd == 6 || h->nbr_rank[dd] < 0) continue;
+                mglc_lbm *n = g->r[h->nbr_rank[dd]];
+                for (int b = 0; b < 2; ++b) { view[dd].buf[b] = n->buf[b]; view[dd].gbuf[b] = n->gbuf[b]; }
+                view[dd].flags = n->flags;
+                for (int q = 0; q < 3; ++q) view[dd].ln[q] = n->d.ln[q];
+            }
+            int rc = use(h);
+            if (!rc) rc = install_peers(h, view);
+            if (rc) { mglc_group_destroy(g); return rc; }
+            h->overlap = 2;
+        }
     *out = g;
     return MGLC_OK;
 }
@@ -854,6 +1072,7 @@ extern "C" int mglc_group_rank(mglc_group *g, int r, mglc_lbm **h) {
     return MGLC_OK;
 }
 
+static mglc_lbm *group_member(mglc_group *g, int r) { return g->r[r]; }
 #define FOR_RANKS(g, h) for (mglc_lbm * h : (g)->r)
 #define GROUP_EACH(g, fn)                       \
     do {                                        \
@@ -918,13 +1137,22 @@ extern "C" int mglc_group_check_thermal(mglc_group *g, double *errorU, double *e
 static int group_step_impl(mglc_group *g, int nsteps) {
     if (nsteps < 0) return MGLC_E_INVALID;
     if (nsteps == 0) return MGLC_OK;
+    // a member that was brought back to the reference's state on its own (per-subdomain download, ...) has flipped its
+    // ping-pong parity relative to the others; direct stores need every member on the same parity
+    bool mixed = false;
+    FOR_RANKS(g, h) mixed = mixed || (h->rotated != g->r[0]->rotated);
+    if (mixed) FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(canonicalise(h)); }
     FOR_RANKS(g, h) {
         MGLC_TRY(use(h));
         if (!h->rotated) { MGLC_TRY(do_collision(h)); if (h->thermal) MGLC_TRY(do_collisionT(h)); }
     }
+    const bool direct = g->r[0]->direct && g->r[0]->overlap == 2 && g->r.size() > 1;
     for (int it = 0; it < nsteps; ++it) {
-        MGLC_TRY(group_exchange(g));
-        FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_fused(h)); }
+        bool all_valid = true;
+        FOR_RANKS(g, h) all_valid = all_valid && h->direct_valid;
+        FOR_RANKS(g, h) if (h->direct_valid) { MGLC_TRY(use(h)); MGLC_TRY(wait_direct(h)); }
+        if (!all_valid) MGLC_TRY(group_exchange(g));
+        FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(direct ? do_fused_direct(h) : do_fused(h)); }
     }
     FOR_RANKS(g, h) h->rotated = 1;
     return MGLC_OK;

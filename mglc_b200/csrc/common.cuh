@@ -39,6 +39,29 @@ inline Geom make_geom(int nx, int ny, int nz) {
     return g;
 }
 
+// Direct halo stores (fused step on several GPUs): where a neighbouring subdomain's lattice is mapped into this
+// GPU's address space (peer access inside one process, CUDA IPC between processes, both over NVLink), the fused
+// kernel writes the outgoing populations of its boundary cells straight into the neighbour's halo cells instead
+// of leaving them to pack -> ncclSend/ncclRecv -> unpack.  Entry d = direction of the message: 0..5 faces
+// +x,-x,+y,-y,+z,-z (5 populations, ex_sendrecv.f90:12-59; thermal: + g population d+1, B3:1421-1468),
+// 7..18 the edge population d crosses (ex_sendrecv.f90:64-123).  The neighbour's block can differ in size by one
+// cell per axis (decompose_1d), so its strides and extents are carried too.
+struct PeerTable {
+    unsigned mask;             // bit d set: there is a neighbour in direction d
+    double *F[19];             // the neighbour's f_post lattice being written this step (same ping-pong parity)
+    double *G[6];              // thermal: its g_post lattice
+    long long sy[19], sz[19], sq[19];
+    int n[19][3];              // the neighbour's interior size
+};
+
+// the flag words of the neighbour barrier that goes with PeerTable: signal[d] = my slot in the memory of the
+// neighbour in direction d, wait[d] = the slot that neighbour raises in mine
+struct SyncTable {
+    unsigned mask;
+    unsigned long long *signal[19];
+    unsigned long long *wait[19];
+};
+
 struct LbmParams {
     double Snu, Sq, U0, rho0;
     int bgk;             // 1 = MGLC_BGK (L3/collision.f90:191-198), 0 = the MRT operator
@@ -83,7 +106,8 @@ void set_error(const char *fmt, ...);
     /* stream + macro + collide: pull from Fin (halo'd, post-collision) -> post-collision Fout;      \
        box = [i0,i1]x[j0,j1]x[k0,k1] inclusive, 1-based interior cells */                            \
     int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout,             \
-                     const double *rho_lid_in, double *rho_lid_out, const int box[6], cudaStream_t s); \
+                     const double *rho_lid_in, double *rho_lid_out, const int box[6], cudaStream_t s, \
+                     const PeerTable *peers = nullptr);   /* device pointer; non-null: direct halo stores */ \
     /* stream + macro (epilogue of a fused run): Fin (post-collision) -> F (pre-collision) + fields */\
     int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, double *F,         \
                             const double *rho_lid_in, double *rho, double *u, double *v, double *w,  \
@@ -100,7 +124,7 @@ void set_error(const char *fmt, ...);
     /* streaming+bounceback+streamingT+bouncebackT+macro+macroT of step n, collision+collisionT of n+1 */ \
     int launch_th_fused(const Geom &g, const ThermalParams &tp, const double *Fin, double *Fout,     \
                         const double *Gin, double *Gout, const double *Fc_in, double *Fc_out,        \
-                        const int box[6], cudaStream_t s);                                           \
+                        const int box[6], cudaStream_t s, const PeerTable *peers = nullptr);         \
     int launch_th_stream_macro(const Geom &g, const ThermalParams &tp, const double *Fin, double *F, \
                                const double *Gin, double *G, const double *Fc_in, double *rho,       \
                                double *u, double *v, double *w, double *T, cudaStream_t s);
@@ -141,6 +165,8 @@ int launch_th_check(const Geom &g, const double *u, const double *v, const doubl
 int launch_pack_g(const Geom &g, const double *Gpost, int face, double *buf, cudaStream_t s);
 int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, cudaStream_t s);
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
+int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s);
+int launch_halo_wait(const SyncTable &t, unsigned long long epoch, int *err, cudaStream_t s);
 int check_scratch_doubles();
 void msg_dims(const Geom &g, int dir, int &n1, int &n2, int &npop);
 

@@ -467,6 +467,43 @@ int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, c
 __global__ void k_fill(double *p, long long n, double v) {
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) p[q] = v;
 }
+// ---- neighbour barrier of the direct-halo path --------------------------------------------------------------------
+// After a fused launch that stored into the neighbours' halos, every subdomain raises its epoch in a flag word that
+// lives in each neighbour's memory (signal); before anything reads its own halos it waits until all neighbours have
+// raised theirs (wait).  Kernel completion orders the halo stores before the flag store on the same stream; the wait
+// gives up after ~20 s and sets *err instead of hanging the device.
+__global__ void k_halo_signal(SyncTable t, unsigned long long epoch /* the word, see k_halo_wait */) {
+    const int d = threadIdx.x;
+    if (d < 19 && (t.mask >> d & 1u)) {
+        __threadfence_system();
+        *(volatile unsigned long long *)t.signal[d] = epoch;
+    }
+}
+// word = 2 * epoch + ping-pong index of the lattice the launch wrote: neighbours out of step on the index are reported
+__global__ void k_halo_wait(SyncTable t, unsigned long long word, int *err) {
+    const int d = threadIdx.x;
+    if (d < 19 && (t.mask >> d & 1u)) {
+        unsigned long long t0, seen;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (((seen = *(volatile unsigned long long *)t.wait[d]) >> 1) < (word >> 1)) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 20000000000ull) { atomicOr(err, 1); break; }
+            __nanosleep(200);
+        }
+        if ((seen >> 1) == (word >> 1) && ((seen ^ word) & 1ull)) atomicOr(err, 2);
+        __threadfence_system();
+    }
+}
+int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s) {
+    k_halo_signal<<<1, 32, 0, s>>>(t, epoch);
+    return 1;
+}
+int launch_halo_wait(const SyncTable &t, unsigned long long word, int *err, cudaStream_t s) {
+    k_halo_wait<<<1, 32, 0, s>>>(t, word, err);
+    return 1;
+}
+
 int launch_fill(double *p, long long n, double value, cudaStream_t s) {
     k_fill<<<1184, 256, 0, s>>>(p, n, value);
     return 1;

@@ -13,6 +13,7 @@
 //   k_absdiff_max   check_diff (LAP:185-204)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -74,19 +75,19 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
     B[c] = 0.25 * s;
 }
 
-// Register blocking, no barriers: a thread owns JRY consecutive rows of one x column and marches JKCH planes along
+// Register blocking, no barriers: a thread owns JRY consecutive rows of one x column and marches `kch` planes along
 // z with the z-1 / z / z+1 values of its JRY cells in registers.  y neighbours are the thread's own registers
 // (plus one row above and one below the strip per plane), x neighbours come from the adjacent lanes by shuffle
 // (warp-edge lanes read them), z neighbours from the marching registers: per cell one DRAM read, one write and
 // about 2/JRY extra L2 reads.
-constexpr int JTX = 128, JRY = 4, JKCH = 64;
+constexpr int JTX = 128, JRY = 4;
 template <bool HAS_F>
 __global__ void __launch_bounds__(JTX, 8) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
-                                                     double *__restrict__ B, int k_lo, int k_hi) {
+                                                     double *__restrict__ B, int k_lo, int k_hi, int kch) {
     const int i = 1 + blockIdx.x * JTX + threadIdx.x;
     const int j0 = 1 + blockIdx.y * JRY;
-    const int k0 = k_lo + blockIdx.z * JKCH;
-    const int k1 = min(k0 + JKCH - 1, k_hi);
+    const int k0 = k_lo + blockIdx.z * kch;
+    const int k1 = min(k0 + kch - 1, k_hi);
     const int lane = threadIdx.x & 31;
     const bool active = i <= g.nx;
     const bool edge_m = lane == 0, edge_p = lane == 31 || i >= g.nx;
@@ -120,6 +121,14 @@ __global__ void __launch_bounds__(JTX, 8) k_jacobi3d(Geom g, const double *__res
         for (int r = 0; r < JRY; ++r) { below[r] = cen[r]; cen[r] = up[r]; }
         c += sz;
     }
+}
+
+// planes a CTA marches: short chunks keep the last wave of CTAs small (the sweep of a 512^3 block lasts only
+// ~0.4 ms, so a partly filled last wave costs several per cent), long chunks re-read fewer start-up planes
+static int jacobi_kch(int nz) {
+    static int v = 0;
+    if (!v) { v = 8; if (const char *e = getenv("MGLC_JACOBI_KCH")) v = std::max(1, atoi(e)); }
+    return std::min(v, nz);
 }
 
 // max |A_p - A| over the interior; non-negative doubles order like their bit patterns
@@ -432,10 +441,11 @@ static int jac_sweep(mglc_jacobi *h) {
             if (S->f) k_jacobi2d<true><<<grid, 128, 0, S->s>>>(S->g, A, S->f, B);
             else k_jacobi2d<false><<<grid, 128, 0, S->s>>>(S->g, A, nullptr, B);
         } else {
-            const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JRY - 1) / JRY, (S->n[2] + JKCH - 1) / JKCH);
+            const int kch = jacobi_kch(S->n[2]);
+            const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JRY - 1) / JRY, (S->n[2] + kch - 1) / kch);
             const dim3 block(JTX);
-            if (S->f) k_jacobi3d<true><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2]);
-            else k_jacobi3d<false><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2]);
+            if (S->f) k_jacobi3d<true><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2], kch);
+            else k_jacobi3d<false><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2], kch);
         }
         S->launches += 1;
         S->cur ^= 1;

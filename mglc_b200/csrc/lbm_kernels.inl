@@ -51,6 +51,64 @@ __device__ __forceinline__ WallFlags wall_flags(const Geom &g, int i, int j, int
         f[13] = __dsub_rn(f[13], __dmul_rn(r6, -p.U0));                           \
     }
 
+
+// ---- direct halo stores (PeerTable, common.cuh) ------------------------------------------------------------------
+// Halo cell of the neighbour in direction (EX,EY,EZ) that receives what cell (i,j,k) sends there: along an axis the
+// message crosses the neighbour's halo layer is 0 (sent in +direction) or n'+1 (sent in -direction); along the other
+// axes the neighbour shares this block's index range (Cartesian blocks), L3/ex_sendrecv.f90:12-123.
+template <int EX, int EY, int EZ>
+__device__ __forceinline__ long long peer_cell(const PeerTable *__restrict__ pt, int D, int i, int j, int k) {
+    const int ii = EX > 0 ? 0 : (EX < 0 ? pt->n[D][0] + 1 : i);
+    const int jj = EY > 0 ? 0 : (EY < 0 ? pt->n[D][1] + 1 : j);
+    const int kk = EZ > 0 ? 0 : (EZ < 0 ? pt->n[D][2] + 1 : k);
+    return kk * pt->sz[D] + jj * pt->sy[D] + (ii + OX - 1);
+}
+#define MGLC_PEER_FACE(D, EX, EY, EZ, a0, a1, a2, a3, a4)                                   \
+    if (pm & (1u << (D))) {                                                                   \
+        double *P = pt->F[D];                                                                 \
+        const long long o = peer_cell<EX, EY, EZ>(pt, D, i, j, k), q = pt->sq[D];             \
+        P[(a0) * q + o] = fp[a0]; P[(a1) * q + o] = fp[a1]; P[(a2) * q + o] = fp[a2];         \
+        P[(a3) * q + o] = fp[a3]; P[(a4) * q + o] = fp[a4];                                   \
+    }
+#define MGLC_PEER_EDGE(A, EX, EY, EZ)                                                        \
+    if (pm & (1u << (A))) pt->F[A][(A) * pt->sq[A] + peer_cell<EX, EY, EZ>(pt, A, i, j, k)] = fp[A];
+// the outgoing populations of a boundary cell, in the message sets of message_passing_sendrecv()
+__device__ __forceinline__ void peer_store_f(const PeerTable *__restrict__ pt, const Geom &g, int i, int j, int k,
+                                             const double (&fp)[19]) {
+    const unsigned pm = pt->mask;
+    const bool xp = i == g.nx, xm = i == 1, yp = j == g.ny, ym = j == 1, zp = k == g.nz, zm = k == 1;
+    if (!(xp | xm | yp | ym | zp | zm)) return;
+    if (xp) MGLC_PEER_FACE(0, 1, 0, 0, 1, 7, 9, 11, 13)
+    if (xm) MGLC_PEER_FACE(1, -1, 0, 0, 2, 8, 10, 12, 14)
+    if (yp) MGLC_PEER_FACE(2, 0, 1, 0, 3, 7, 8, 15, 17)
+    if (ym) MGLC_PEER_FACE(3, 0, -1, 0, 4, 9, 10, 16, 18)
+    if (zp) MGLC_PEER_FACE(4, 0, 0, 1, 5, 11, 12, 15, 16)
+    if (zm) MGLC_PEER_FACE(5, 0, 0, -1, 6, 13, 14, 17, 18)
+    if (xp && yp) MGLC_PEER_EDGE(7, 1, 1, 0)
+    if (xm && yp) MGLC_PEER_EDGE(8, -1, 1, 0)
+    if (xp && ym) MGLC_PEER_EDGE(9, 1, -1, 0)
+    if (xm && ym) MGLC_PEER_EDGE(10, -1, -1, 0)
+    if (xp && zp) MGLC_PEER_EDGE(11, 1, 0, 1)
+    if (xm && zp) MGLC_PEER_EDGE(12, -1, 0, 1)
+    if (xp && zm) MGLC_PEER_EDGE(13, 1, 0, -1)
+    if (xm && zm) MGLC_PEER_EDGE(14, -1, 0, -1)
+    if (yp && zp) MGLC_PEER_EDGE(15, 0, 1, 1)
+    if (ym && zp) MGLC_PEER_EDGE(16, 0, -1, 1)
+    if (yp && zm) MGLC_PEER_EDGE(17, 0, 1, -1)
+    if (ym && zm) MGLC_PEER_EDGE(18, 0, -1, -1)
+}
+// thermal: face d carries the single g population d+1 (B3:1421-1468), no edges
+__device__ __forceinline__ void peer_store_g(const PeerTable *__restrict__ pt, const Geom &g, int i, int j, int k,
+                                             const double (&gp)[7]) {
+    const unsigned pm = pt->mask;
+    if (i == g.nx && (pm & 1u)) pt->G[0][1 * pt->sq[0] + peer_cell<1, 0, 0>(pt, 0, i, j, k)] = gp[1];
+    if (i == 1 && (pm & 2u)) pt->G[1][2 * pt->sq[1] + peer_cell<-1, 0, 0>(pt, 1, i, j, k)] = gp[2];
+    if (j == g.ny && (pm & 4u)) pt->G[2][3 * pt->sq[2] + peer_cell<0, 1, 0>(pt, 2, i, j, k)] = gp[3];
+    if (j == 1 && (pm & 8u)) pt->G[3][4 * pt->sq[3] + peer_cell<0, -1, 0>(pt, 3, i, j, k)] = gp[4];
+    if (k == g.nz && (pm & 16u)) pt->G[4][5 * pt->sq[4] + peer_cell<0, 0, 1>(pt, 4, i, j, k)] = gp[5];
+    if (k == 1 && (pm & 32u)) pt->G[5][6 * pt->sq[5] + peer_cell<0, 0, -1>(pt, 5, i, j, k)] = gp[6];
+}
+
 // collision operator selected at compile time: the MRT of L3/collision.f90:20-189 or the BGK alternative of :191-198
 template <bool BGK>
 __device__ __forceinline__ void collide(const double (&f)[19], double rho, double u, double v, double w, const LbmParams &p,
@@ -80,10 +138,12 @@ __global__ void __launch_bounds__(128) k_collision(Geom g, LbmParams p, const do
 }
 
 // fused: pull (streaming) -> wall bounce-back -> macro -> collide -> store
-template <bool BGK>
+// PEER: also store the outgoing populations of boundary cells into the neighbours' halos (PeerTable)
+template <bool BGK, bool PEER>
 __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const double *__restrict__ Fin,
                                                   double *__restrict__ Fout, const double *__restrict__ rho_lid_in,
-                                                  double *__restrict__ rho_lid_out, int i0, int i1, int j0, int j1, int k0) {
+                                                  double *__restrict__ rho_lid_out, int i0, int i1, int j0, int j1, int k0,
+                                                  const PeerTable *__restrict__ pt) {
     // block (128,1) for full rows, (32,4) for the thin x-slabs of the boundary shell (see launch below)
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
@@ -99,6 +159,7 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     collide<BGK>(f, rho, u, v, w, p, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
+    if (PEER) peer_store_f(pt, g, i, j, k, fp);
     // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
     // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro()); it goes to the other
     // side buffer so that the plane this launch read stays intact for canonicalise()
@@ -137,13 +198,16 @@ int launch_collision(const Geom &g, const LbmParams &p, const double *F, const d
 }
 
 int launch_fused(const Geom &g, const LbmParams &p, const double *Fin, double *Fout, const double *rho_lid_in,
-                 double *rho_lid_out, const int box[6], cudaStream_t s) {
+                 double *rho_lid_out, const int box[6], cudaStream_t s, const PeerTable *pt) {
     const int nxs = box[1] - box[0] + 1, nys = box[3] - box[2] + 1, nzs = box[5] - box[4] + 1;
     if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
-    const dim3 block = nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
+    // narrow x slabs (the shell next to an x neighbour): keep 128 threads busy by stacking rows
+    const dim3 block = nxs <= 8 ? dim3(8, 16) : nxs <= 16 ? dim3(16, 8) : nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
     const dim3 grid((nxs + block.x - 1) / block.x, (nys + block.y - 1) / block.y, nzs);
-    if (p.bgk) k_fused<true><<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4]);
-    else k_fused<false><<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4]);
+#define MGLC_LAUNCH_FUSED(B, P) k_fused<B, P><<<grid, block, 0, s>>>(g, p, Fin, Fout, rho_lid_in, rho_lid_out, box[0], box[1], box[2], box[3], box[4], pt)
+    if (pt) { if (p.bgk) MGLC_LAUNCH_FUSED(true, true); else MGLC_LAUNCH_FUSED(false, true); }
+    else { if (p.bgk) MGLC_LAUNCH_FUSED(true, false); else MGLC_LAUNCH_FUSED(false, false); }
+#undef MGLC_LAUNCH_FUSED
     return 1;
 }
 

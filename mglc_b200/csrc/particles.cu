@@ -17,6 +17,7 @@
 // The whole problem (201 x 801 nodes in the shipped case) is L2-resident; one step is a handful of small launches.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,7 +52,7 @@ struct P2 {              // module commondata, P4/commondata.F90
 enum { PX_ = 0, PY_, PU_, PV_, POM_, PRAD_, PINERTIA_, PXO_, PYO_, PUO_, PVO_, POMO_, PFX_, PFY_, PTQ_, PSX_, PSY_, PST_, PFIELDS_ };
 // PFX/PFY/PTQ = wallTotalForceX/Y, totalTorque; PSX/PSY/PST = this rank's link sums before the Allreduce
 
-enum { ST_STREAM = 1, ST_WALLBB = 2, ST_PBB = 4, ST_MACRO = 8, ST_FORCE = 16 };
+enum { ST_STREAM = 1, ST_WALLBB = 2, ST_PBB = 4, ST_MACRO = 8, ST_FORCE = 16, ST_COUNT = 32 };
 enum { ERR_CALQ = 1, ERR_Q = 2, ERR_OWNER = 4, ERR_INTERPENETRATION = 8, ERR_WALL = 16, ERR_REFILL = 32 };
 
 __device__ __forceinline__ bool inside(const G2 &g, int i, int j, double xc, double yc, double rad) {
@@ -59,21 +60,9 @@ __device__ __forceinline__ bool inside(const G2 &g, int i, int j, double xc, dou
     return (dx * dx + dy * dy) <= rad * rad;
 }
 
-// calQ, P4/particle_bounceback.F90:98-141: bisection along link alpha to |dist - radius| < 1e-9 (single literal)
-__device__ int calQ(double xc, double yc, double rad, double i, double j, int alpha, double &x0, double &y0, double &q) {
-    const double epsRadius = (double)1e-9f;
-    const double exa = (double)c9x[alpha], eya = (double)c9y[alpha];
-    q = 0.5;
-    double qTemp = 0.5;
-    x0 = i + qTemp * exa; y0 = j + qTemp * eya;
-    while (fabs(sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc)) - rad) >= epsRadius) {
-        const double d = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
-        if (d > rad) { qTemp = qTemp / 2.0; x0 = x0 + qTemp * exa; y0 = y0 + qTemp * eya; q = q + qTemp; }
-        else if (d < rad) { qTemp = qTemp / 2.0; x0 = x0 - qTemp * exa; y0 = y0 - qTemp * eya; q = q - qTemp; }
-        else return ERR_CALQ;
-        if (qTemp == 0.0) return ERR_CALQ;
-    }
-    return (q > 1.0 || q < 0.0) ? ERR_Q : 0;
+#include "p2d_calq.inl"
+__device__ __forceinline__ int calQ(double xc, double yc, double rad, double i, double j, int alpha, double &x0, double &y0, double &q) {
+    return calQ_link(xc, yc, rad, i, j, (double)c9x[alpha], (double)c9y[alpha], x0, y0, q);
 }
 
 __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, double u, double v, double Snu, double Sq, double (&fp)[9]) {
@@ -146,7 +135,64 @@ __global__ void k_p_initial(G2 g, P2 p, const double *__restrict__ ps, double *_
     }
 }
 
-// ---- collision(), P4/fluid.F90:1-72: fluid nodes only; optionally the block partial sums for rhoAvg ------------
+// Two sums over a whole grid of 128-thread blocks, reproducible: block partials (tree-reduced in shared memory) are
+// stored by block index; the block that takes the last ticket adds them in a fixed order and writes out[0..1].
+// Every thread of every block must call this.
+__device__ void grid_sum2(double a, double b, double *__restrict__ partials, unsigned *__restrict__ ticket, double *__restrict__ out) {
+    __shared__ double s1[128], s2[128];
+    __shared__ bool last;
+    const int t = threadIdx.x;
+    s1[t] = a; s2[t] = b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) { s1[t] += s1[t + o]; s2[t] += s2[t + o]; }
+        __syncthreads();
+    }
+    const unsigned nb = gridDim.x * gridDim.y, bi = blockIdx.y * gridDim.x + blockIdx.x;
+    if (t == 0) {
+        partials[2 * bi] = s1[0]; partials[2 * bi + 1] = s2[0];
+        __threadfence();
+        last = atomicInc(ticket, nb - 1) == nb - 1;          // wraps to 0: ready for the next launch
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double x = 0.0, y = 0.0;
+    for (unsigned q = t; q < nb; q += 128) { x += __ldcg(&partials[2 * q]); y += __ldcg(&partials[2 * q + 1]); }
+    s1[t] = x; s2[t] = y;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) { s1[t] += s1[t + o]; s2[t] += s2[t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) { out[0] = s1[0]; out[1] = s2[0]; }
+}
+
+// collision() of the fused step: the same node update, plus the sums bounceback_particle() needs for rhoAvg
+// (P4/particle_bounceback.F90:15-35: rho over the fluid nodes and their number) since this kernel already reads
+// rho and obst of every node
+__global__ void __launch_bounds__(128) k_p_collision_sum(G2 g, P2 p, const double *__restrict__ F, const double *__restrict__ rho,
+                                                         const double *__restrict__ u, const double *__restrict__ v,
+                                                         const int *__restrict__ obst, double *__restrict__ Fp,
+                                                         double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                         double *__restrict__ out) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+    double sr = 0.0, sc = 0.0;
+    if (i <= g.nx && obst[g.idx(0, i, j)] == 0) {
+        const long long c = g.idx(0, i, j), m = g.cell(i, j);
+        double f[9], fp[9];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
+        const double r = rho[m];
+        d2q9_collide(f, r, u[m], v[m], p.Snu, p.Sq, fp);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) Fp[a * g.sq + c] = fp[a];
+        sr = r; sc = 1.0;
+    }
+    grid_sum2(sr, sc, partials, ticket, out);
+}
+
+// ---- collision(), P4/fluid.F90:1-72: fluid nodes only ------------
 __global__ void __launch_bounds__(128) k_p_collision(G2 g, P2 p, const double *__restrict__ F, const double *__restrict__ rho,
                                                      const double *__restrict__ u, const double *__restrict__ v,
                                                      const int *__restrict__ obst, double *__restrict__ Fp) {
@@ -194,7 +240,8 @@ template <int STAGES>
 __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__restrict__ ps_in, double *__restrict__ ps_sum,
                                                   const double *__restrict__ Fp, double *__restrict__ F,
                                                   const int *__restrict__ obst, double *__restrict__ rho, double *__restrict__ u,
-                                                  double *__restrict__ v, const double *__restrict__ rhoAvgPart, int *__restrict__ err) {
+                                                  double *__restrict__ v, const double *__restrict__ rhoAvgPart, int *__restrict__ err,
+                                                  int *__restrict__ nlinks) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
     const bool in_range = i <= g.nx;
     const int ic = in_range ? i : g.nx;
@@ -202,6 +249,16 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
     const int N = p.N;
     const bool fluid = in_range && obst[c] == 0;
     double f[9];
+    // ST_COUNT (fused step): number of links of this node that end in a solid node; k_p_links counts them down and the
+    // thread that handles the last one redoes macro() for the node
+    if ((STAGES & ST_COUNT) && in_range) {
+        int nl = 0;
+        if (fluid) {
+#pragma unroll
+            for (int a = 1; a < 9; ++a) nl += obst[c + c9y[a] * (long long)g.px + c9x[a]] == 1;
+        }
+        nlinks[g.cell(i, j)] = nl;
+    }
     // streaming(), P4/fluid.F90:97-108: every interior node, skipped when the upstream node is solid
     if (in_range) {
         if (STAGES & ST_STREAM) {
@@ -340,14 +397,131 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
     }
 }
 
+
+// ---- fused step: bounceback_particle() + the link sums of calForce(), one block per particle ------------------------
+// The node kernel (k_p_update<STREAM|WALLBB|MACRO|COUNT>) leaves in nlinks the number of links of every fluid node that
+// end in a solid node.  Here block cn scans the bounding box of particle cn for those links (fluid node -> node inside
+// THIS particle; no search over the other particles), gives every link its own thread (prefix sum over the per-node
+// counts -> queue in shared memory), and per link does what P4/particle_bounceback.F90:52-75 and
+// P4/particle_force.F90:52-66 do: calQ bisection, quadratic-interpolated bounce-back into f(r(alpha)), momentum exchange
+// with that final value.  The thread that finishes a node's last link redoes macro() for it (P4/fluid.F90:164-184).
+// Link sums are reduced in a fixed order (thread-strided partial sums, then a shared-memory tree): reproducible, no atomics.
+constexpr int LK_T = 256;
+__global__ void __launch_bounds__(LK_T) k_p_links(G2 g, P2 p, const double *__restrict__ ps, double *__restrict__ ps_sum,
+                                                  const double *__restrict__ Fp, double *F, const int *__restrict__ obst,
+                                                  int *nlinks, double *rho, double *u, double *v,
+                                                  const double *__restrict__ rhoAvgPart, int *__restrict__ err) {
+    __shared__ int queue[LK_T * 8];
+    __shared__ int wsum[LK_T / 32];
+    __shared__ double r1[LK_T], r2[LK_T], r3[LK_T];
+    const int cn = blockIdx.x, N = p.N, t = threadIdx.x;
+    const double xc = ps[PX_ * N + cn], yc = ps[PY_ * N + cn], rad = ps[PRAD_ * N + cn];
+    const double om = ps[POM_ * N + cn], Uc = ps[PU_ * N + cn], Vc = ps[PV_ * N + cn];
+    const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
+    // local index range of the fluid nodes that can touch the particle (one node beyond its extent), clipped to the interior
+    const int li0 = max(1, (int)floor(xc - rad) - 1 - g.i_start), li1 = min(g.nx, (int)ceil(xc + rad) + 1 - g.i_start);
+    const int lj0 = max(1, (int)floor(yc - rad) - 1 - g.j_start), lj1 = min(g.ny, (int)ceil(yc + rad) + 1 - g.j_start);
+    const int bw = li1 - li0 + 1, bh = lj1 - lj0 + 1;
+    const int nnodes = (bw > 0 && bh > 0) ? bw * bh : 0;
+    double lfx = 0.0, lfy = 0.0, ltq = 0.0;
+    // one link: bisection, bounce-back, momentum exchange, and macro() when it was the node's last
+    auto do_link = [&](int e) {
+        const int a = e & 15, nn = e >> 4;
+        const int i = li0 + nn % bw, j = lj0 + nn / bw;
+        const long long c = g.idx(0, i, j), m = g.cell(i, j);
+        double x0, y0, q;
+        const int rc = calQ(xc, yc, rad, (double)(i + g.i_start), (double)(j + g.j_start), a, x0, y0, q);
+        if (rc) atomicOr(err, rc);
+        else {
+            const double temp1 = -(y0 - yc) * om, temp2 = (x0 - xc) * om;
+            const int ra = c9r[a];
+            const double exr = (double)c9x[ra], eyr = (double)c9y[ra];
+            const double omega = a < 5 ? 1.0 / 9.0 : 1.0 / 36.0;
+            const double fp0 = Fp[a * g.sq + c];
+            const long long c1 = c - c9y[a] * (long long)g.px - c9x[a];
+            double val;
+            if (q < 0.5) {                       // P4/particle_bounceback.F90:66-69
+                const long long c2 = c1 - c9y[a] * (long long)g.px - c9x[a];
+                val = q * (1.0 + 2.0 * q) * fp0 + (1.0 - 4.0 * q * q) * Fp[a * g.sq + c1] - q * (1.0 - 2.0 * q) * Fp[a * g.sq + c2]
+                    + 6.0 * omega * rhoAvg * (exr * (Uc + temp1) + eyr * (Vc + temp2));
+            } else {                             // :71-74
+                val = fp0 / q / (1.0 + 2.0 * q) + Fp[ra * g.sq + c] * (2.0 * q - 1.0) / q
+                    - Fp[ra * g.sq + c1] * (2.0 * q - 1.0) / (2.0 * q + 1.0)
+                    + 6.0 * omega * rhoAvg / q / (1.0 + 2.0 * q) * (exr * (Uc + temp1) + eyr * (Vc + temp2));
+            }
+            F[ra * g.sq + c] = val;
+            // momentum exchange over the link, P4/particle_force.F90:60-62, with the node's final f(r(alpha)) = val
+            const double tfx = ((double)c9x[a] - Uc - temp1) * fp0 - (exr - Uc - temp1) * val;
+            const double tfy = ((double)c9y[a] - Vc - temp2) * fp0 - (eyr - Vc - temp2) * val;
+            lfx += tfx; lfy += tfy; ltq += (x0 - xc) * tfy - (y0 - yc) * tfx;
+        }
+        __threadfence();
+        if (atomicSub(&nlinks[m], 1) == 1) {     // every link of this node is in: macro(), P4/fluid.F90:164-184
+            __threadfence();
+            double f[9];
+#pragma unroll
+            for (int b = 0; b < 9; ++b) f[b] = __ldcg(&F[b * g.sq + c]);
+            const double r = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
+            rho[m] = r;
+            u[m] = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / r;
+            v[m] = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / r;
+        }
+    };
+    // pass 1: scan the box LK_T nodes at a time and queue every link (prefix sum of the per-node counts gives each
+    // link a fixed slot); pass 2: one link per thread.  The queue is drained early only if a box holds more links
+    // than it has room for (a particle far larger than the shipped radius).
+    int queued = 0;                                            // uniform across the block
+    for (int base = 0; base < nnodes; base += LK_T) {
+        const int n = base + t;
+        int bits = 0, cnt = 0;
+        if (n < nnodes) {
+            const int i = li0 + n % bw, j = lj0 + n / bw;
+            const long long c = g.idx(0, i, j);
+            if (obst[c] == 0) {
+#pragma unroll
+                for (int a = 1; a < 9; ++a) {
+                    const int ip = i + c9x[a], jp = j + c9y[a];
+                    if (obst[c + c9y[a] * (long long)g.px + c9x[a]] == 1 && inside(g, ip, jp, xc, yc, rad)) { bits |= 1 << a; ++cnt; }
+                }
+            }
+        }
+        int inc = cnt;                                         // inclusive prefix sum of cnt over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if ((t & 31) >= o) inc += y; }
+        __syncthreads();                                       // wsum of the previous chunk has been read
+        if ((t & 31) == 31) wsum[t >> 5] = inc;
+        __syncthreads();
+        int off = inc - cnt, total = 0;
+#pragma unroll
+        for (int w = 0; w < LK_T / 32; ++w) { if (w < (t >> 5)) off += wsum[w]; total += wsum[w]; }
+        if (queued + total > LK_T * 8) {                       // no room: drain first
+            for (int l = t; l < queued; l += LK_T) do_link(queue[l]);
+            __syncthreads();
+            queued = 0;
+        }
+        off += queued;
+        for (int a = 1; a < 9; ++a) if (bits & (1 << a)) queue[off++] = (n << 4) | a;
+        queued += total;
+    }
+    __syncthreads();
+    for (int l = t; l < queued; l += LK_T) do_link(queue[l]);
+    r1[t] = lfx; r2[t] = lfy; r3[t] = ltq;
+    __syncthreads();
+    for (int o = LK_T / 2; o > 0; o >>= 1) {
+        if (t < o) { r1[t] += r1[t + o]; r2[t] += r2[t + o]; r3[t] += r3[t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) { ps_sum[PSX_ * N + cn] = r1[0]; ps_sum[PSY_ * N + cn] = r2[0]; ps_sum[PST_ * N + cn] = r3[0]; }
+}
+
 // ---- the per-particle tail of calForce (P4/particle_force.F90:95-190) and the kinematics of updateCenter
 // (P4/particle_update.F90:25-50).  Every rank integrates every particle from the same Allreduced sums, which
 // yields what the reference's owner-computes + masked Allreduce (message_particle.F90:470-497) leaves everywhere.
 enum { PT_FORCES = 1, PT_ADVANCE = 2 };
-__global__ void k_p_particles(P2 p, double *__restrict__ ps, const double *__restrict__ rhoAvgPart, int what, int *__restrict__ err) {
+__global__ void k_p_particles(P2 p, double *ps, const double *__restrict__ rhoAvgPart, int what, int *__restrict__ err) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, N = p.N;
-    if (c >= N) return;
-    if (what & PT_FORCES) {
+    const bool on = c < N;
+    if ((what & PT_FORCES) && on) {
         const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
         const double rad = ps[PRAD_ * N + c], xc = ps[PX_ * N + c], yc = ps[PY_ * N + c];
         double forceScale = p.Pi * (rad * rad) * (p.rhoSolid - rhoAvg) * p.gravity / p.stiffParticle;
@@ -378,12 +552,78 @@ __global__ void k_p_particles(P2 p, double *__restrict__ ps, const double *__res
         ps[PFY_ * N + c] = ps[PSY_ * N + c] - (p.rhoSolid - rhoAvg) * p.Pi * (p.radius0 * p.radius0) * p.gravity + Fyij + Fwy;
         ps[PTQ_ * N + c] = ps[PST_ * N + c];
     }
-    if (what & PT_ADVANCE) {
+    if ((what & PT_ADVANCE) && on) {
         const double xo = ps[PX_ * N + c], yo = ps[PY_ * N + c], Uo = ps[PU_ * N + c], Vo = ps[PV_ * N + c], oo = ps[POM_ * N + c];
         ps[PXO_ * N + c] = xo; ps[PYO_ * N + c] = yo; ps[PUO_ * N + c] = Uo; ps[PVO_ * N + c] = Vo; ps[POMO_ * N + c] = oo;
         const double ax = ps[PFX_ * N + c] / p.Pi / (p.radius0 * p.radius0) / p.rhoSolid;
         const double ay = ps[PFY_ * N + c] / p.Pi / (p.radius0 * p.radius0) / p.rhoSolid;
         const double aOmega = ps[PTQ_ * N + c] / ps[PINERTIA_ * N + c];       // 0.5*rhoSolid*Pi*radius**4 from the host's libm
+        ps[PU_ * N + c] = Uo + ax;
+        ps[PV_ * N + c] = Vo + ay;
+        ps[POM_ * N + c] = oo + aOmega;
+        ps[PX_ * N + c] = xo + Uo + 0.5 * ax;
+        ps[PY_ * N + c] = yo + Vo + 0.5 * ay;
+    }
+}
+
+// Fused-step form of the two passes above for one block: a warp per particle evaluates the pair terms of the spring
+// force 32 at a time and adds them in ascending order of the partner index (the reference's loop order, so the sums
+// round identically); after a barrier the kinematics run one particle per thread.
+__global__ void __launch_bounds__(1024) k_p_particles_block(P2 p, double *ps, const double *__restrict__ rhoAvgPart, int *__restrict__ err) {
+    const int N = p.N, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
+    for (int c = threadIdx.x >> 5; c < N; c += nw) {
+        const double rad = ps[PRAD_ * N + c], xc = ps[PX_ * N + c], yc = ps[PY_ * N + c];
+        double forceScale = p.Pi * (rad * rad) * (p.rhoSolid - rhoAvg) * p.gravity / p.stiffParticle;
+        double Fxij = 0.0, Fyij = 0.0;
+        for (int base = 0; base < N; base += 32) {
+            const int c2 = base + lane;
+            double tx = 0.0, ty = 0.0;
+            int kind = 0;
+            if (c2 < N && c2 != c) {
+                const double x2 = ps[PX_ * N + c2], y2 = ps[PY_ * N + c2], r2 = ps[PRAD_ * N + c2];
+                const double dij = sqrt((xc - x2) * (xc - x2) + (yc - y2) * (yc - y2));
+                if (dij >= (rad + r2 + p.thresholdParticle)) {
+                } else if (dij >= (rad + r2)) {
+                    const double t = (dij - rad - r2 - p.thresholdParticle) / p.thresholdParticle;
+                    tx = forceScale * (t * t) * (xc - x2) / dij;
+                    ty = forceScale * (t * t) * (yc - y2) / dij;
+                    kind = 1;
+                } else kind = 2;
+            }
+            if (__ballot_sync(0xffffffffu, kind == 2) && lane == 0) atomicOr(err, ERR_INTERPENETRATION);
+            unsigned m = __ballot_sync(0xffffffffu, kind == 1);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                Fxij = Fxij + __shfl_sync(0xffffffffu, tx, l);
+                Fyij = Fyij + __shfl_sync(0xffffffffu, ty, l);
+                m &= m - 1;
+            }
+        }
+        if (lane == 0) {
+            double Fwx = 0.0, Fwy = 0.0;
+            forceScale = p.Pi * (rad * rad) * (p.rhoSolid - p.rho0) * p.gravity / p.stiffWall;
+            double dw = yc - rad - 1.0;
+            if (dw < 0) atomicOr(err, ERR_WALL);
+            else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwy = Fwy + forceScale * (t * t); }
+            dw = xc - rad - 1.0;
+            if (dw < 0) atomicOr(err, ERR_WALL);
+            else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwx = Fwx + forceScale * (t * t); }
+            dw = (double)p.total_nx - xc - rad;
+            if (dw < 0) atomicOr(err, ERR_WALL);
+            else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwx = Fwx - forceScale * (t * t); }
+            ps[PFX_ * N + c] = ps[PSX_ * N + c] + Fxij + Fwx;
+            ps[PFY_ * N + c] = ps[PSY_ * N + c] - (p.rhoSolid - rhoAvg) * p.Pi * (p.radius0 * p.radius0) * p.gravity + Fyij + Fwy;
+            ps[PTQ_ * N + c] = ps[PST_ * N + c];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        const double xo = ps[PX_ * N + c], yo = ps[PY_ * N + c], Uo = ps[PU_ * N + c], Vo = ps[PV_ * N + c], oo = ps[POM_ * N + c];
+        ps[PXO_ * N + c] = xo; ps[PYO_ * N + c] = yo; ps[PUO_ * N + c] = Uo; ps[PVO_ * N + c] = Vo; ps[POMO_ * N + c] = oo;
+        const double ax = ps[PFX_ * N + c] / p.Pi / (p.radius0 * p.radius0) / p.rhoSolid;
+        const double ay = ps[PFY_ * N + c] / p.Pi / (p.radius0 * p.radius0) / p.rhoSolid;
+        const double aOmega = ps[PTQ_ * N + c] / ps[PINERTIA_ * N + c];
         ps[PU_ * N + c] = Uo + ax;
         ps[PV_ * N + c] = Vo + ay;
         ps[POM_ * N + c] = oo + aOmega;
@@ -406,6 +646,55 @@ __global__ void __launch_bounds__(128) k_p_mask(G2 g, P2 p, const double *__rest
         const long long m = g.cell(i, j);
         rho[m] = p.rhoSolid; u[m] = 0.0; v[m] = 0.0;
     }
+}
+
+
+// updateCenter of the fused step: the mask rebuild of k_p_mask, plus (a) the sums for the second rhoAvg
+// (P4/particle_update.F90:105-120: rho over the nodes that are fluid in obstNew, after the reset above), (b) the check that
+// k_p_links consumed every link the node kernel counted (a link into a solid node no particle owns: ERR_OWNER).
+// A block first collects the particles whose extent reaches its row segment, then tests its nodes against those only.
+__global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, const double *__restrict__ ps, const int *__restrict__ obst,
+                                                    int *__restrict__ obstNew, double *__restrict__ rho, double *__restrict__ u,
+                                                    double *__restrict__ v, const int *__restrict__ nlinks, int *__restrict__ err,
+                                                    double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                    double *__restrict__ out) {
+    __shared__ int list[128];
+    __shared__ int nlist;
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), j = (int)blockIdx.y, N = p.N;
+    if (threadIdx.x == 0) nlist = 0;
+    __syncthreads();
+    const double gj = (double)(j + g.j_start), gi_lo = (double)((int)(blockIdx.x * blockDim.x) + g.i_start),
+                 gi_hi = gi_lo + (double)(blockDim.x - 1);
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        const double xc = ps[PX_ * N + c], yc = ps[PY_ * N + c], rad = ps[PRAD_ * N + c];
+        // conservative: one node of slack on every side of the particle's bounding box
+        if (fabs(gj - yc) <= rad + 1.0 && xc + rad + 1.0 >= gi_lo && xc - rad - 1.0 <= gi_hi) {
+            const int pos = atomicAdd(&nlist, 1);
+            if (pos < 128) list[pos] = c;
+        }
+    }
+    __syncthreads();
+    double sr = 0.0, sc = 0.0;
+    if (i <= g.nx + 1) {
+        int solid = 0;
+        if (nlist <= 128) {
+            for (int q = 0; q < nlist; ++q) {
+                const int c = list[q];
+                if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+            }
+        } else {
+            for (int c = 0; c < N; ++c)
+                if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+        }
+        obstNew[g.idx(0, i, j)] = solid;
+        if (i >= 1 && i <= g.nx && j >= 1 && j <= g.ny) {
+            const long long m = g.cell(i, j);
+            if (solid) { rho[m] = p.rhoSolid; u[m] = 0.0; v[m] = 0.0; }
+            else { sr = rho[m]; sc = 1.0; }
+            if (obst[g.idx(0, i, j)] == 0 && nlinks[m] != 0) atomicOr(err, ERR_OWNER);
+        }
+    }
+    grid_sum2(sr, sc, partials, ticket, out);
 }
 
 // updateCenter, P4/particle_update.F90:122-203: a solid node that became fluid is refilled by 3-point extrapolation
@@ -531,6 +820,12 @@ struct Sub {
     G2 g;
     double *F, *Fp, *rho, *u, *v, *up, *vp, *ps, *part, *stage;
     int *obst, *obstNew, *err, *istage;
+    int *nlinks;                     // fused step: links into solid nodes still to be bounced back, per interior node
+    double *gpart;                   // fused step: per-block partial sums of grid_sum2 (2 per block)
+    unsigned *ticket;                // [0] collision+sum launch, [1] mask+sum launch
+    int launches_per_step;
+    int *obst0;                      // the allocation obst pointed to at create time (graph parity)
+    cudaGraphExec_t gexec[2];        // one captured step per obst/obstNew parity (single-subdomain handles)
     cudaStream_t s;
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
     Msg msgs[16];                    // 0..7 f_post (depth 2), 8..15 f (depth 3)
@@ -587,6 +882,8 @@ static void p_free_sub(Sub *S) {
     double *bufs[] = {S->F, S->Fp, S->rho, S->u, S->v, S->up, S->vp, S->ps, S->part, S->stage};
     for (double *b : bufs) cudaFree(b);
     cudaFree(S->obst); cudaFree(S->obstNew); cudaFree(S->err); cudaFree(S->istage);
+    cudaFree(S->nlinks); cudaFree(S->gpart); cudaFree(S->ticket);
+    for (cudaGraphExec_t e : S->gexec) if (e) cudaGraphExecDestroy(e);
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
     cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -633,6 +930,13 @@ static int p_make_sub(mglc_p2d *h, int rank, int device, Sub **out) {
         cudaMalloc((void **)&S->istage, (size_t)(S->nx + 2) * (S->ny + 2) * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&S->err, sizeof(int)) != cudaSuccess || cudaMalloc((void **)&S->ps, (size_t)PFIELDS_ * N * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void **)&S->part, (size_t)(2 + 2 * 1024) * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); return fail(MGLC_E_NOMEM); }
+    const size_t nblk = (size_t)((S->nx + 2 + 127) / 128) * (S->ny + 2);          // the larger of the two summing grids
+    if (cudaMalloc((void **)&S->nlinks, (size_t)S->nx * S->ny * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&S->gpart, 2 * nblk * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&S->ticket, 2 * sizeof(unsigned)) != cudaSuccess) { (void)cudaGetLastError(); return fail(MGLC_E_NOMEM); }
+    cudaMemsetAsync(S->nlinks, 0, (size_t)S->nx * S->ny * sizeof(int), S->s);
+    cudaMemsetAsync(S->ticket, 0, 2 * sizeof(unsigned), S->s);
+    S->obst0 = S->obst;
     double **flds[] = {&S->rho, &S->u, &S->v, &S->up, &S->vp};
     for (double **f : flds) { if (cudaMalloc((void **)f, fld) != cudaSuccess) return fail(MGLC_E_NOMEM); cudaMemsetAsync(*f, 0, fld, S->s); }
     cudaMemsetAsync(S->F, 0, lat, S->s); cudaMemsetAsync(S->Fp, 0, lat, S->s);
@@ -982,7 +1286,7 @@ extern "C" int mglc_p2d_get_rho_avg(mglc_p2d *h, double *rhoAvg) {
 template <int STAGES> static int p_update(mglc_p2d *h) {
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_update<STAGES><<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->part, S->err);
+        k_p_update<STAGES><<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->part, S->err, S->nlinks);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -1083,19 +1387,121 @@ extern "C" int mglc_p2d_check(mglc_p2d *h, double *errorU) {
     return MGLC_OK;
 }
 
-// nsteps iterations of the loop body P4/main.F90:35-73.  Fused: collision | exchange f_post | one kernel for streaming +
-// bounceback + bounceback_particle + macro + link sums | per-particle forces and kinematics | exchange f | mask + refill.
+// sum part[0..1] across subdomains (the two MPI_Allreduce of bounceback_particle / updateCenter)
+static int p_reduce_part(mglc_p2d *h) {
+    if (h->nranks == 1) return MGLC_OK;
+    if (h->comm) {
+        Sub *S = h->subs[0];
+        MGLC_TRY(p_use(S));
+        MGLC_NCCL(ncclAllReduce(S->part, S->part, 2, ncclDouble, ncclSum, h->comm->nccl, S->s));
+        return MGLC_OK;
+    }
+    double tot[2] = {0.0, 0.0};
+    P_EACH(h, S) {                       // rank-ordered host sum, like the oracle
+        MGLC_TRY(p_use(S));
+        double e[2];
+        MGLC_CUDA(cudaMemcpyAsync(e, S->part, sizeof e, cudaMemcpyDeviceToHost, S->s));
+        MGLC_CUDA(cudaStreamSynchronize(S->s));
+        tot[0] += e[0]; tot[1] += e[1];
+    }
+    P_EACH(h, S) { MGLC_TRY(p_use(S)); MGLC_CUDA(cudaMemcpyAsync(S->part, tot, sizeof tot, cudaMemcpyHostToDevice, S->s)); MGLC_CUDA(cudaStreamSynchronize(S->s)); }
+    return MGLC_OK;
+}
+
+// One loop body of P4/main.F90:35-73, fused:
+//   k_p_collision_sum   collision() + the rhoAvg sums of bounceback_particle()
+//   [send_all_fp]       2-deep f_post halos
+//   k_p_update<...>     streaming() + bounceback() + macro() per node, counting each node's links into solid nodes
+//   k_p_links           bounceback_particle() + the link sums of calForce(), one block per particle, one thread per link
+//   k_p_particles       Allreduced link sums -> spring forces, gravity, kinematics (calForce tail + updateCenter head)
+//   [send_all_f]        3-deep f halos
+//   k_p_mask_sum        new mask + the second rhoAvg sums;  k_p_refill   refill of uncovered nodes
+// 6 launches on one GPU; every reduction has a fixed order, so a run is reproducible bit for bit.
+static int p_enqueue_step(mglc_p2d *h) {
+    const int N = h->p.N;
+    P_EACH(h, S) {
+        MGLC_TRY(p_use(S));
+        k_p_collision_sum<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->F, S->rho, S->u, S->v, S->obst, S->Fp, S->gpart, S->ticket, S->part);
+        S->launches += 1;
+    }
+    MGLC_TRY(p_exchange(h, 0));
+    MGLC_TRY(p_reduce_part(h));
+    P_EACH(h, S) {
+        MGLC_TRY(p_use(S));
+        k_p_update<ST_STREAM | ST_WALLBB | ST_MACRO | ST_COUNT><<<grid_int(S), 128, 0, S->s>>>(
+            S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->part, S->err, S->nlinks);
+        S->launches += 1;
+        if (N) {
+            k_p_links<<<N, LK_T, 0, S->s>>>(S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->nlinks, S->rho, S->u, S->v, S->part, S->err);
+            S->launches += 1;
+        }
+    }
+    if (N) {
+        if (h->nranks > 1) MGLC_TRY(p_force_tail(h, PT_FORCES | PT_ADVANCE));      // Allreduce of the link sums + the two passes
+        else {
+            Sub *S = h->subs[0];
+            k_p_particles_block<<<1, std::min(1024, 32 * N), 0, S->s>>>(h->p, S->ps, S->part, S->err);
+            S->launches += 1;
+        }
+    }
+    MGLC_TRY(p_exchange(h, 1));
+    P_EACH(h, S) {
+        MGLC_TRY(p_use(S));
+        k_p_mask_sum<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obst, S->obstNew, S->rho, S->u, S->v,
+                                                                               S->nlinks, S->err, S->gpart, S->ticket + 1, S->part);
+        S->launches += 1;
+    }
+    MGLC_TRY(p_reduce_part(h));
+    P_EACH(h, S) {
+        MGLC_TRY(p_use(S));
+        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
+        S->launches += 1;
+        std::swap(S->obst, S->obstNew);      // obst = obstNew, P4/particle_update.F90:206
+    }
+    return MGLC_OK;
+}
+
+// the previous fused schedule (one node kernel does the particle links too): kept for A/B runs, MGLC_P2D_LEGACY=1
+static int p_step_legacy(mglc_p2d *h) {
+    MGLC_TRY(mglc_p2d_collision(h));
+    MGLC_TRY(p_exchange(h, 0));
+    MGLC_TRY(p_fluid_average(h, false));
+    MGLC_TRY(p_zero_sums(h));
+    MGLC_TRY((p_update<ST_STREAM | ST_WALLBB | ST_PBB | ST_MACRO | ST_FORCE>(h)));
+    MGLC_TRY(p_force_tail(h, PT_FORCES | PT_ADVANCE));
+    MGLC_TRY(p_exchange(h, 1));
+    return p_mask_refill(h);
+}
+
+// nsteps loop bodies.  A single-subdomain handle replays the step as a CUDA graph (one graph per obst/obstNew parity,
+// captured the first time that parity comes up): the whole state is L2-resident and a step is a few microseconds of
+// kernels, so launch overhead would otherwise dominate.
 static int p_step_impl(mglc_p2d *h, int nsteps) {
     if (nsteps < 0) return MGLC_E_INVALID;
+    static const bool legacy = getenv("MGLC_P2D_LEGACY") != nullptr, nograph = getenv("MGLC_P2D_NOGRAPH") != nullptr;
+    const bool graph = !legacy && !nograph && h->nranks == 1 && h->subs.size() == 1;
     for (int it = 0; it < nsteps; ++it) {
-        MGLC_TRY(mglc_p2d_collision(h));
-        MGLC_TRY(p_exchange(h, 0));
-        MGLC_TRY(p_fluid_average(h, false));
-        MGLC_TRY(p_zero_sums(h));
-        MGLC_TRY((p_update<ST_STREAM | ST_WALLBB | ST_PBB | ST_MACRO | ST_FORCE>(h)));
-        MGLC_TRY(p_force_tail(h, PT_FORCES | PT_ADVANCE));
-        MGLC_TRY(p_exchange(h, 1));
-        MGLC_TRY(p_mask_refill(h));
+        if (legacy) { MGLC_TRY(p_step_legacy(h)); continue; }
+        if (!graph) { MGLC_TRY(p_enqueue_step(h)); continue; }
+        Sub *S = h->subs[0];
+        MGLC_TRY(p_use(S));
+        const int par = S->obst == S->obst0 ? 0 : 1;
+        if (!S->gexec[par]) {
+            const long long l0 = S->launches;
+            cudaGraph_t gr = nullptr;
+            MGLC_CUDA(cudaStreamBeginCapture(S->s, cudaStreamCaptureModeRelaxed));
+            const int rc = p_enqueue_step(h);                 // swaps obst / obstNew like an executed step
+            const cudaError_t ce = cudaStreamEndCapture(S->s, &gr);
+            if (rc || ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); set_error("mglc_p2d_step: graph capture failed"); return rc ? rc : MGLC_E_CUDA; }
+            const cudaError_t ie = cudaGraphInstantiate(&S->gexec[par], gr, 0);
+            cudaGraphDestroy(gr);
+            if (ie != cudaSuccess) { S->gexec[par] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return MGLC_E_CUDA; }
+            S->launches_per_step = (int)(S->launches - l0);
+        } else {
+            std::swap(S->obst, S->obstNew);
+            S->launches += S->launches_per_step;
+        }
+        MGLC_CUDA(cudaGraphLaunch(S->gexec[par], S->s));
     }
     return MGLC_OK;
 }

@@ -60,10 +60,12 @@ __global__ void __launch_bounds__(128) k_th_collisionT(Geom g, ThermalParams tp,
     for (int a = 0; a < 7; ++a) Gpost[a * sq + c] = gp[a];
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, const double *__restrict__ Fin,
                                                      double *__restrict__ Fout, const double *__restrict__ Gin,
                                                      double *__restrict__ Gout, const double *__restrict__ Fc_in,
-                                                     double *__restrict__ Fc_out, int i0, int i1, int j0, int j1, int k0) {
+                                                     double *__restrict__ Fc_out, int i0, int i1, int j0, int j1, int k0,
+                                                     const PeerTable *__restrict__ pt) {
     // block (128,1) for full rows, (32,4) for the thin x-slabs of the boundary shell (see launch below)
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
         d3q7_collide(gq, u, v, w, T, tp, gp);                 // collisionT() of step n+1
 #pragma unroll
         for (int a = 0; a < 7; ++a) Gout[a * sq + c] = gp[a];
+        if (PEER) peer_store_g(pt, g, i, j, k, gp);
     }
     thermal_force(rho, u, v, T, tp, Fx, Fy, Fz);              // force of step n+1's collision
     Fc_out[m] = Fx; Fc_out[n + m] = Fy; Fc_out[2 * n + m] = Fz;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
     d3q19_collide_thermal(f, rho, u, v, w, Fx, Fy, Fz, tp, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
+    if (PEER) peer_store_f(pt, g, i, j, k, fp);
 }
 
 // leave the rotated state: pull f and g into the pre-collision lattices and write rho,u,v,w,T
@@ -131,12 +135,13 @@ int launch_th_collisionT(const Geom &g, const ThermalParams &tp, const double *G
     return 1;
 }
 int launch_th_fused(const Geom &g, const ThermalParams &tp, const double *Fin, double *Fout, const double *Gin,
-                    double *Gout, const double *Fc_in, double *Fc_out, const int box[6], cudaStream_t s) {
+                    double *Gout, const double *Fc_in, double *Fc_out, const int box[6], cudaStream_t s, const PeerTable *pt) {
     const int nxs = box[1] - box[0] + 1, nys = box[3] - box[2] + 1, nzs = box[5] - box[4] + 1;
     if (nxs <= 0 || nys <= 0 || nzs <= 0) return 0;
-    const dim3 block = nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
+    const dim3 block = nxs <= 8 ? dim3(8, 16) : nxs <= 16 ? dim3(16, 8) : nxs <= 32 ? dim3(32, 4) : dim3(128, 1);
     const dim3 grid((nxs + block.x - 1) / block.x, (nys + block.y - 1) / block.y, nzs);
-    k_th_fused<<<grid, block, 0, s>>>(g, tp, Fin, Fout, Gin, Gout, Fc_in, Fc_out, box[0], box[1], box[2], box[3], box[4]);
+    if (pt) k_th_fused<true><<<grid, block, 0, s>>>(g, tp, Fin, Fout, Gin, Gout, Fc_in, Fc_out, box[0], box[1], box[2], box[3], box[4], pt);
+    else k_th_fused<false><<<grid, block, 0, s>>>(g, tp, Fin, Fout, Gin, Gout, Fc_in, Fc_out, box[0], box[1], box[2], box[3], box[4], nullptr);
     return 1;
 }
 int launch_th_stream_macro(const Geom &g, const ThermalParams &tp, const double *Fin, double *F, const double *Gin,

@@ -44,10 +44,21 @@ def main():
         from oracle import oracle as orc
     ok = True
 
-    # ---- lid-driven cavity, uneven blocks, strict arithmetic: bit-exact, with and without comm/compute overlap ----
+    # ---- lid-driven cavity, uneven blocks, strict arithmetic: bit-exact in every halo mode:
+    #      2 = direct stores into the neighbours' halos (CUDA IPC mappings), 1 = overlapped NCCL exchange, 0 = blocking ----
     total, nsteps = (41, 37, 35), 12
-    for overlap in (1, 0):
+    import ctypes as C
+    for overlap in (2, 1, 0):
         sim = mg.LidDrivenCavity(total, comm=comm, arith="strict")
+        if overlap == 2:
+            avail = C.c_int()
+            L.check(L.lib().mglc_lbm_direct_halo(sim.ranks[0]._h, C.byref(avail)))
+            if rank == 0:
+                print(f"direct halo mappings: {'established' if avail.value else 'UNAVAILABLE (NCCL transport)'}")
+            if not avail.value:
+                ok = ok and bool(os.environ.get("MGLC_NO_DIRECT"))     # on an NVLink box the mappings must come up
+                sim.close()
+                continue
         L.check(L.lib().mglc_lbm_set_overlap(sim.ranks[0]._h, overlap))
         sim.initial()
         sim.step(5); sim.step(nsteps - 5)            # two calls: the rotated state carries the in-flight exchange across
@@ -72,8 +83,14 @@ def main():
 
     # ---- thermal cavity ----
     total, nsteps = (27, 25, 23), 10
-    for overlap in (1, 0):
+    for overlap in (2, 1, 0):
         sim = mg.BuoyancyDrivenCavity(total, comm=comm, arith="strict")
+        if overlap == 2:
+            avail = C.c_int()
+            L.check(L.lib().mglc_lbm_direct_halo(sim.ranks[0]._h, C.byref(avail)))
+            if not avail.value:
+                sim.close()
+                continue
         L.check(L.lib().mglc_lbm_set_overlap(sim.ranks[0]._h, overlap))
         sim.initial()
         sim.step(4); sim.step(nsteps - 4)

@@ -7,6 +7,7 @@ Bars (BASELINE.json north_star):
     oracle to <= 1e-12 relative L2 and <= 1e-10 max pointwise
   * P-subdomain runs (uneven blocks) reproduce the 1-subdomain run bit for bit
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -316,6 +317,53 @@ def test_decomposition_invariance_bit_exact(nprocs, dims):
     e_ref, e_gpu = wd.check(), sim.check()
     assert abs(e_gpu - e_ref) <= 1e-12 * e_ref
     wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (8, None), (12, None), (4, (1, 1, 4))])
+def test_direct_halo_stores_equal_packed_exchange(nprocs, dims, monkeypatch):
+    """The fused step with direct stores into the neighbours' halos (mode 2, the default for a group) leaves exactly
+    what pack -> copy -> unpack leaves (MGLC_NO_DIRECT=1), f_post halos included, and both equal the 1-rank oracle."""
+    total, nsteps = (23, 19, 17), 9
+    sims = []
+    for no_direct in (False, True):
+        if no_direct:
+            monkeypatch.setenv("MGLC_NO_DIRECT", "1")
+        sim = gpu_world(total, nprocs=nprocs, dims=dims, seed=21, arith="strict")
+        avail = C.c_int()
+        mg._lib.check(mg._lib.lib().mglc_lbm_direct_halo(sim.ranks[0]._h, C.byref(avail)))
+        assert bool(avail.value) == (not no_direct)
+        sim.step(4); sim.step(nsteps - 4)
+        sims.append(sim)
+    monkeypatch.delenv("MGLC_NO_DIRECT")
+    wd = oracle_world(total, seed=21)
+    wd.step(nsteps)
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(sims[0].gather_macro()[k], wd.gather(k)), k
+        assert np.array_equal(sims[1].gather_macro()[k], wd.gather(k)), k
+    assert np.array_equal(sims[0].gather("f"), wd.gather("f"))
+    # continue stepping after the state was brought back to the reference's (download above): still identical
+    for s_ in sims:
+        s_.step(3)
+    wd.step(3)
+    assert np.array_equal(sims[0].gather("f"), wd.gather("f")) and np.array_equal(sims[1].gather("f"), wd.gather("f"))
+    for s_ in sims:
+        s_.close()
+    wd.close()
+
+
+def test_direct_halo_survives_a_member_leaving_the_fused_loop_alone():
+    """One subdomain of a group is downloaded on its own between two step() calls (its ping-pong parity flips);
+    the next step() must bring the others into line instead of storing halos into the wrong lattice."""
+    total = (20, 14, 12)
+    sim = gpu_world(total, nprocs=4, seed=8, arith="strict")
+    wd = oracle_world(total, seed=8)
+    sim.step(3); wd.step(3)
+    sim.ranks[2].download_macro()
+    sim.step(4); wd.step(4)
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(sim.gather_macro()[k], wd.gather(k)), k
+    sim.close(); wd.close()
 
 
 def test_config1_decomposed_2x2x2_fast_matches_single_gpu_run():

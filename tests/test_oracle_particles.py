@@ -205,3 +205,60 @@ def test_decomposition_invariance_within_summation_order(nprocs, dims):
     for k in ("xCenter", "yCenter", "Uc", "Vc", "rationalOmega"):
         assert np.allclose(getattr(many, k), getattr(one, k), rtol=0, atol=1e-12), k
     one.close(); many.close()
+
+
+# ---- the product's calQ (mglc_b200/csrc/p2d_calq.inl, compiled for the host) ------------------------------------------
+
+@pytest.fixture(scope="module")
+def calq_shim(tmp_path_factory):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path_factory.mktemp("calq") / "calq_host.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out,
+                           os.path.join(root, "tests", "host_shim", "calq_host.cpp")])
+    S = C.CDLL(out)
+    S.shim_calq.argtypes = [C.c_double] * 7 + [dp]
+    return S
+
+
+def test_product_calQ_matches_reference_source_vectors(calq_shim):
+    """The square-root-free far-field halvings must not change a single bit of q, x0, y0 (vectors evaluated from the
+    reference's Fortran text, P4/particle_bounceback.F90:98-141)."""
+    xc, yc, rad = GOLD["link/particle"][:3]
+    for n, (i, j, a) in enumerate(GOLD["link/ija"]):
+        out = np.empty(3)
+        assert calq_shim.shim_calq(xc, yc, rad, float(i), float(j), float(orc.EX9[int(a)]), float(orc.EY9[int(a)]), ptr(out)) == 0
+        q, x0, y0 = GOLD["link/q_x0_y0"][n]
+        assert (out[2], out[0], out[1]) == (q, x0, y0), n
+
+
+def test_product_calQ_matches_oracle_on_random_and_grazing_links(calq_shim):
+    rng = np.random.default_rng(2024)
+    checked = grazing = 0
+    for trial in range(400):
+        rad = float(rng.uniform(2.5, 14.0))
+        xc, yc = (float(v) for v in rng.uniform(30.0, 34.0, 2))
+        wd = orc.ParticleWorld([xc], [yc], radius=[rad], total_nx=64, total_ny=64)
+        wd.initial()
+        lo, hi = int(np.floor(xc - rad)) - 1, int(np.ceil(xc + rad)) + 1
+        for i in range(lo, hi + 1):
+            for j in range(int(np.floor(yc - rad)) - 1, int(np.ceil(yc + rad)) + 2):
+                if (i - xc) ** 2 + (j - yc) ** 2 <= rad * rad:
+                    continue
+                for a in range(1, 9):
+                    ip, jp = i + int(orc.EX9[a]), j + int(orc.EY9[a])
+                    if (ip - xc) ** 2 + (jp - yc) ** 2 > rad * rad:
+                        continue
+                    q, x0, y0 = C.c_double(), C.c_double(), C.c_double()
+                    rc = wd._lib.p2_calQ(wd._h, 0, float(i), float(j), a, C.byref(x0), C.byref(y0), C.byref(q))
+                    out = np.empty(3)
+                    rc2 = calq_shim.shim_calq(xc, yc, rad, float(i), float(j), float(orc.EX9[a]), float(orc.EY9[a]), ptr(out))
+                    assert (rc == 0) == (rc2 == 0)
+                    if rc == 0:
+                        assert (out[0], out[1], out[2]) == (x0.value, y0.value, q.value), (trial, i, j, a)
+                    checked += 1
+                    grazing += q.value < 0.02 or q.value > 0.98
+        wd.close()
+        if checked > 40000:
+            break
+    assert checked > 20000 and grazing > 200
