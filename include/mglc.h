@@ -169,6 +169,15 @@ int mglc_lbm_download_thermal(mglc_lbm *h, double *g, double *T, double *Fx, dou
 int mglc_lbm_upload_gpost(mglc_lbm *h, const double *g_post);
 int mglc_lbm_download_gpost(mglc_lbm *h, double *g_post);
 
+/* in-loop diagnostics on the device: no full-field download needed during long runs.
+ * calNuRe(): NuVolAvg = sum(w T)/N * total_nz/diffusivity + 1, ReVolAvg = sqrt(sum(u^2+v^2+w^2)/N) * total_nz/viscosity over the
+ * global box, viscosity = (tau-1/2)/3, diffusivity = viscosity/Prandtl -- B3/mpi_blocked/RaNu.F90:13-47, module.F90:38-39 */
+int mglc_calNuRe(mglc_lbm *h, double prandtl, double *NuVolAvg, double *ReVolAvg);
+/* one line of rho|u|v|w|T (field 0..4) along `axis` through global 1-based (g1, g2) on the two other axes, e.g. getVelocity()'s
+ * u(nxHalf,nyHalf,:) and w(:,nyHalf,nzHalf), L3/output.f90:334-344.  out holds ln[axis] values starting at global index *first;
+ * *count = 0 when the line does not cross this subdomain */
+int mglc_lbm_download_line(mglc_lbm *h, int field, int axis, int g1, int g2, double *out, int *first, int *count);
+
 /* fused fast path == nsteps iterations of the loop body L3/main.f90:85-97 (B3:222-248 for thermal handles)
  * (collision, exchange, streaming, bounceback, macro); prologue/epilogue handled inside, the state
  * afterwards (f, f_post, rho,u,v,w) is the reference's state after the same number of iterations */
@@ -224,6 +233,7 @@ int mglc_group_streamingT(mglc_group *g);
 int mglc_group_bouncebackT(mglc_group *g);
 int mglc_group_macroT(mglc_group *g);
 int mglc_group_check_thermal(mglc_group *g, double *errorU, double *errorT);
+int mglc_group_calNuRe(mglc_group *g, double prandtl, double *NuVolAvg, double *ReVolAvg);
 int mglc_group_step(mglc_group *g, int nsteps);
 int mglc_group_step_timed(mglc_group *g, int nsteps, float *ms);
 
@@ -310,6 +320,41 @@ int mglc_p2d_get_rho_avg(mglc_p2d *h, double *rhoAvg);
 int mglc_p2d_error_flags(mglc_p2d *h, int *flags);
 int mglc_p2d_launch_count(mglc_p2d *h, long long *n);
 int mglc_p2d_sync(mglc_p2d *h);
+
+/* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
+ * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /
+ * the Python gather hand back.  Unformatted files use the gfortran record framing the reference's Makefiles produce:
+ * [int32 n][payload][int32 n], records above 2147483639 bytes split into subrecords (negative markers). */
+enum { MGLC_FILE_LID_PLT = 0, MGLC_FILE_LID_BIN = 1, MGLC_FILE_LID_DAT = 2, MGLC_FILE_THERMAL_PLT = 3,
+       MGLC_FILE_THERMAL_BIN = 4, MGLC_FILE_BACKUP = 5 };
+/* one Fortran `write(unit) list` per record; max_subrecord_or_0 = 0 keeps gfortran's 2147483639 */
+int mglc_unformatted_write(const char *path, int nrecords, const void *const *records, const long long *bytes,
+                           long long max_subrecord_or_0);
+int mglc_unformatted_read(const char *path, int nrecords, void *const *records, const long long *bytes);
+/* output_binary(): records u, v, rho -- L3/output.f90:350-367 (w is not written by the reference) */
+int mglc_output_binary_lid(const char *path, const double *u, const double *v, const double *rho, int nx, int ny, int nz);
+/* output_binary(): records u, v, w, T -- B3:1593-1618 */
+int mglc_output_binary_thermal(const char *path, const double *u, const double *v, const double *w, const double *T,
+                               int nx, int ny, int nz);
+/* backupData(): records u, v, w, T, f(0:18,nx,ny,nz), g(0:6,nx,ny,nz) -- B3/seq/bouyancy3d.F90:1011-1029;
+ * mglc_backup_read = initial() with loadInitField = 1, seq:367-378 */
+int mglc_backup_write(const char *path, const double *u, const double *v, const double *w, const double *T,
+                      const double *f, const double *g, int nx, int ny, int nz);
+int mglc_backup_read(const char *path, double *u, double *v, double *w, double *T, double *f, double *g, int nx, int ny, int nz);
+/* xp(0:total_n+1): 0, i - 0.5, total_n -- L3/initial.f90:18-31, B3:459-472 */
+int mglc_grid_coords(int total_n, double *xp);
+/* output_Tecplot(): "#!TDV101", one ordered zone, POINT packing, 7 float variables X Y Z U V W Pressure(= rho/3)
+ * -- L3/output.f90:175-313; thermal: ... W T -- B3:1623-1773.  xp,yp,zp are (0:n+1) as above */
+int mglc_output_tecplot_lid(const char *path, const double *xp, const double *yp, const double *zp, const double *u,
+                            const double *v, const double *w, const double *rho, int nx, int ny, int nz);
+int mglc_output_tecplot_thermal(const char *path, const double *xp, const double *yp, const double *zp, const double *u,
+                                const double *v, const double *w, const double *T, int nx, int ny, int nz);
+/* getVelocity(): the centre-line profiles u(nxHalf,nyHalf,:)/U0 vs zp/nz and w(:,nyHalf,nzHalf)/U0 vs xp/nx, as numbers
+ * (the reference prints them list-directed, which is compiler-specific) -- L3/output.f90:318-347 */
+int mglc_get_velocity(const double *xp, const double *zp, const double *u, const double *w, int nx, int ny, int nz,
+                      double U0, double *uz, double *zn, double *xn, double *wx);
+/* the drivers' file names for iteration itc: kind = MGLC_FILE_* */
+int mglc_output_filename(char *out, size_t cap, int kind, int itc);
 
 #ifdef __cplusplus
 }

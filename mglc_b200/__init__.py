@@ -5,7 +5,7 @@ Everything that computes lives in libmglc.so (hand-written sm_100a CUDA, built b
 `__graft_entry__.build()` / `make -C mglc_b200/csrc`).  This package is the thin host-side mirror of the
 reference driver's interface; it has no CPU or PyTorch fallback and raises if the library is missing.
 """
-from . import _lib
+from . import _lib, formats
 from ._lib import MglcError, lib
 from .jacobi import Jacobi, dims_create_nd
 from .particles import ParticleChannel
@@ -13,4 +13,4 @@ from .lbm import (BuoyancyDrivenCavity, Communicator, LidDrivenCavity, make_ther
                   halo_plan, make_desc)
 
 __all__ = ["MglcError", "lib", "BuoyancyDrivenCavity", "Communicator", "LidDrivenCavity", "make_thermal_desc", "Subdomain", "cart_neighbors",
-           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "_lib"]
+           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "_lib", "formats"]

@@ -123,6 +123,21 @@ SIGNATURES = {
     "mglc_group_bouncebackT": (C.c_int, [_vp]),
     "mglc_group_macroT": (C.c_int, [_vp]),
     "mglc_group_check_thermal": (C.c_int, [_vp, _dp, _dp]),
+    # diagnostics and on-disk formats
+    "mglc_calNuRe": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+    "mglc_group_calNuRe": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+    "mglc_lbm_download_line": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _ip, _ip]),
+    "mglc_unformatted_write": (C.c_int, [C.c_char_p, C.c_int, _vpp, C.POINTER(C.c_longlong), C.c_longlong]),
+    "mglc_unformatted_read": (C.c_int, [C.c_char_p, C.c_int, _vpp, C.POINTER(C.c_longlong)]),
+    "mglc_output_binary_lid": (C.c_int, [C.c_char_p, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "mglc_output_binary_thermal": (C.c_int, [C.c_char_p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "mglc_backup_write": (C.c_int, [C.c_char_p] + [_vp] * 6 + [C.c_int] * 3),
+    "mglc_backup_read": (C.c_int, [C.c_char_p] + [_vp] * 6 + [C.c_int] * 3),
+    "mglc_grid_coords": (C.c_int, [C.c_int, _vp]),
+    "mglc_output_tecplot_lid": (C.c_int, [C.c_char_p] + [_vp] * 7 + [C.c_int] * 3),
+    "mglc_output_tecplot_thermal": (C.c_int, [C.c_char_p] + [_vp] * 7 + [C.c_int] * 3),
+    "mglc_get_velocity": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
+    "mglc_output_filename": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int]),
     # Jacobi path
     "mglc_dims_create_nd": (C.c_int, [C.c_int, C.c_int, _ip]),
     "mglc_jacobi_create": (C.c_int, [_vpp, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int, _vp]),

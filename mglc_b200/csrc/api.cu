@@ -874,6 +874,55 @@ extern "C" int mglc_check_thermal(mglc_lbm *h, double *errorU, double *errorT) {
     if (!errorU || !errorT) return MGLC_E_INVALID;
     return check_impl(h, errorU, errorT);
 }
+// calNuRe(): B3/mpi_blocked/RaNu.F90:13-47.  The reference's subroutine sums over one rank's block (its call is commented
+// out in the MPI driver, B3:264); here the two sums are all-reduced and the averages taken over the global box, which is
+// what the sequential driver computes (B3/seq/bouyancy3d.F90, calNuRe).
+static void nure_from_sums(const mglc_lbm *h, double prandtl, const double sums[2], double *Nu, double *Re) {
+    const double viscosity = (h->d.tau - 0.5) / 3.0, diffusivity = viscosity / prandtl;      // module commondata, B3:38-39
+    const double ncells = (double)((long long)h->d.gn[0] * h->d.gn[1] * h->d.gn[2]), nz = (double)h->d.gn[2];
+    *Nu = sums[0] / ncells * nz / diffusivity + 1.0;
+    *Re = sqrt(sums[1] / ncells) * nz / viscosity;
+}
+static int do_nure_partial(mglc_lbm *h) {
+    MGLC_TRY(need_thermal(h, "mglc_calNuRe"));
+    MGLC_TRY(canonicalise(h));
+    h->launches += launch_nure(h->g, h->u, h->v, h->w, h->T, h->scratch, h->s);
+    return MGLC_OK;
+}
+extern "C" int mglc_calNuRe(mglc_lbm *h, double prandtl, double *NuVolAvg, double *ReVolAvg) {
+    MGLC_TRY(use(h));
+    MGLC_TRY(not_in_group(h, "mglc_calNuRe"));
+    if (!NuVolAvg || !ReVolAvg || !(prandtl > 0.0)) { set_error("mglc_calNuRe: bad arguments"); return MGLC_E_INVALID; }
+    MGLC_TRY(do_nure_partial(h));
+    if (h->comm && h->nranks > 1) MGLC_NCCL(ncclAllReduce(h->scratch, h->scratch, 2, ncclDouble, ncclSum, h->comm->nccl, h->s));
+    double e[2];
+    MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    nure_from_sums(h, prandtl, e, NuVolAvg, ReVolAvg);
+    return MGLC_OK;
+}
+// one line of a macroscopic field along `axis` through the global 1-based indices (g1, g2) of the other two axes (ascending
+// axis order), e.g. u(nxHalf, nyHalf, :) of getVelocity(), L3/output.f90:334-344, without a full-field download.
+// field: 0 rho, 1 u, 2 v, 3 w, 4 T.  A subdomain the line does not cross returns *count = 0.
+extern "C" int mglc_lbm_download_line(mglc_lbm *h, int field, int axis, int g1, int g2, double *out, int *first, int *count) {
+    MGLC_TRY(use(h));
+    if (field < 0 || field > 4 || axis < 0 || axis > 2 || !out || !first || !count) { set_error("mglc_lbm_download_line: bad arguments"); return MGLC_E_INVALID; }
+    if (field == 4) MGLC_TRY(need_thermal(h, "mglc_lbm_download_line"));
+    MGLC_TRY(canonicalise(h));
+    const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+    const int l1 = g1 - h->d.start[a1], l2 = g2 - h->d.start[a2];      // 1-based local
+    *first = h->d.start[axis] + 1;
+    if (l1 < 1 || l1 > h->d.ln[a1] || l2 < 1 || l2 > h->d.ln[a2]) { *count = 0; return MGLC_OK; }
+    const double *src = field == 0 ? h->rho : field == 1 ? h->u : field == 2 ? h->v : field == 3 ? h->w : h->T;
+    const long long stride[3] = {1, h->g.nx, (long long)h->g.nx * h->g.ny};
+    const double *p0 = src + (l1 - 1) * stride[a1] + (l2 - 1) * stride[a2];
+    const int n = h->d.ln[axis];
+    MGLC_CUDA(cudaMemcpy2DAsync(out, sizeof(double), p0, (size_t)stride[axis] * sizeof(double), sizeof(double), (size_t)n,
+                                cudaMemcpyDeviceToHost, h->s));
+    MGLC_CUDA(cudaStreamSynchronize(h->s));
+    *count = n;
+    return MGLC_OK;
+}
 extern "C" int mglc_lbm_upload_thermal(mglc_lbm *h, const double *g, const double *T, const double *Fx, const double *Fy,
                                        const double *Fz) {
     MGLC_TRY(use(h));
@@ -1132,6 +1181,21 @@ extern "C" int mglc_group_check_thermal(mglc_group *g, double *errorU, double *e
     if (!g || !errorU || !errorT) return MGLC_E_INVALID;
     FOR_RANKS(g, h) MGLC_TRY(need_thermal(h, "mglc_group_check_thermal"));
     return group_check_impl(g, errorU, errorT);
+}
+
+extern "C" int mglc_group_calNuRe(mglc_group *g, double prandtl, double *NuVolAvg, double *ReVolAvg) {
+    if (!g || !NuVolAvg || !ReVolAvg || !(prandtl > 0.0)) return MGLC_E_INVALID;
+    double t[2] = {0.0, 0.0};
+    FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(do_nure_partial(h)); }
+    FOR_RANKS(g, h) {                       // Allreduce(SUM) modelled as a rank-ordered host sum
+        MGLC_TRY(use(h));
+        double e[2];
+        MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
+        MGLC_CUDA(cudaStreamSynchronize(h->s));
+        t[0] += e[0]; t[1] += e[1];
+    }
+    nure_from_sums(g->r[0], prandtl, t, NuVolAvg, ReVolAvg);
+    return MGLC_OK;
 }
 
 static int group_step_impl(mglc_group *g, int nsteps) {

@@ -164,6 +164,7 @@ int launch_th_check(const Geom &g, const double *u, const double *v, const doubl
 // g halo messages: face dir 0..5 carries the single population dir+1 (B3:1421-1468)
 int launch_pack_g(const Geom &g, const double *Gpost, int face, double *buf, cudaStream_t s);
 int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, cudaStream_t s);
+int launch_nure(const Geom &g, const double *u, const double *v, const double *w, const double *T, double *part, cudaStream_t s);
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
 int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s);
 int launch_halo_wait(const SyncTable &t, unsigned long long epoch, int *err, cudaStream_t s);

@@ -467,6 +467,38 @@ int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, c
 __global__ void k_fill(double *p, long long n, double v) {
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) p[q] = v;
 }
+// ---- calNuRe(): volume sums  sum(w*T)  and  sum(u*u+v*v+w*w)  (B3/mpi_blocked/RaNu.F90:13-22,36-45) ----------------
+// part[0..1] = the two sums of this subdomain; fixed grid and tree order, so the result is reproducible run to run
+__global__ void __launch_bounds__(256) k_nure_partial(long long n, const double *__restrict__ u, const double *__restrict__ v,
+                                                      const double *__restrict__ w, const double *__restrict__ T,
+                                                      double *__restrict__ part) {
+    double a1 = 0.0, a2 = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const double a = u[q], b = v[q], c = w[q];
+        a1 += c * T[q];
+        a2 += a * a + b * b + c * c;
+    }
+    __shared__ double s1[256], s2[256];
+    s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[4 + 2 * blockIdx.x] = s1[0]; part[5 + 2 * blockIdx.x] = s2[0]; }
+}
+__global__ void k_nure_final(int nblocks, double *__restrict__ part) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) { a1 += part[4 + 2 * b]; a2 += part[5 + 2 * b]; }
+    part[0] = a1; part[1] = a2;
+}
+int launch_nure(const Geom &g, const double *u, const double *v, const double *w, const double *T, double *part, cudaStream_t s) {
+    const long long n = (long long)g.nx * g.ny * g.nz;
+    k_nure_partial<<<CHECK_BLOCKS, 256, 0, s>>>(n, u, v, w, T, part);
+    k_nure_final<<<1, 1, 0, s>>>(CHECK_BLOCKS, part);
+    return 2;
+}
+
 // ---- neighbour barrier of the direct-halo path --------------------------------------------------------------------
 // After a fused launch that stored into the neighbours' halos, every subdomain raises its epoch in a flag word that
 // lives in each neighbour's memory (signal); before anything reads its own halos it waits until all neighbours have

@@ -330,6 +330,42 @@ class LidDrivenCavity:
                      *[None if a is None else a[sl] for a in (rho, u, v, w)])
 
 
+    # ---- output(): gather + the reference's files (L3/output.f90:12-132) ----
+    def download_line(self, field, axis, g1, g2):
+        """One line of rho|u|v|w|T along `axis` through global 1-based (g1, g2), read from the device without a
+        full-field download (getVelocity's profiles, L3/output.f90:334-344)."""
+        fid = {"rho": 0, "u": 1, "v": 2, "w": 3, "T": 4}[field]
+        out = np.full(self.total[axis], np.nan)
+        for R in self.ranks:
+            buf = np.empty(R.n[axis])
+            first, count = C.c_int(), C.c_int()
+            L.check(L.lib().mglc_lbm_download_line(R._h, fid, axis, g1, g2, _ptr(buf), C.byref(first), C.byref(count)))
+            if count.value:
+                out[first.value - 1:first.value - 1 + count.value] = buf[:count.value]
+        return out
+
+    def getVelocity(self):
+        """u(nxHalf,nyHalf,:)/U0 and w(:,nyHalf,nzHalf)/U0 with their coordinates, L3/output.f90:318-347"""
+        from . import formats as F
+        nx, ny, nz = self.total
+        h = [(n - 1) // 2 + 1 for n in self.total]
+        uz = self.download_line("u", 2, h[0], h[1]) / self.U0
+        wx = self.download_line("w", 0, h[1], h[2]) / self.U0
+        return uz, F.grid_coords(nz)[1:-1] / float(nz), F.grid_coords(nx)[1:-1] / float(nx), wx
+
+    def output(self, directory, itc, binary=True):
+        """output(): MRTcavity-<itc 9 digits>.plt (+ MRTcavity-<itc>.bin); returns the paths written"""
+        import os
+        from . import formats as F
+        m = self.gather_macro()
+        paths = [os.path.join(directory, F.output_filename(F.FILE_LID_PLT, itc))]
+        F.output_tecplot_lid(paths[0], m["u"], m["v"], m["w"], m["rho"])
+        if binary:
+            paths.append(os.path.join(directory, F.output_filename(F.FILE_LID_BIN, itc)))
+            F.output_binary_lid(paths[1], m["u"], m["v"], m["rho"])
+        return paths
+
+
 class BuoyancyDrivenCavity(LidDrivenCavity):
     """Thermal double-distribution cavity (D3Q19 MRT flow + D3Q7 MRT temperature, Boussinesq + Coriolis) on
     B200(s); method names follow MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90:222-248."""
@@ -409,3 +445,45 @@ class BuoyancyDrivenCavity(LidDrivenCavity):
             sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
             R.upload_thermal(None if g is None else g[(slice(None),) + sl],
                              *[None if a is None else a[sl] for a in (T, Fx, Fy, Fz)])
+
+    # ---- diagnostics and files (B3/mpi_blocked/RaNu.F90, B3:1473-1755, seq backupData) ----
+    def calNuRe(self, Prandtl=0.71):
+        """(NuVolAvg, ReVolAvg) of the current fields, reduced on the device -- RaNu.F90:13-47"""
+        nu, re = C.c_double(), C.c_double()
+        self._call("mglc_calNuRe", "mglc_group_calNuRe", Prandtl, C.byref(nu), C.byref(re))
+        return nu.value, re.value
+
+    def output(self, directory, itc):
+        """output(): buoyancyCavity-<itc>.bin and .plt, B3:1577-1578"""
+        import os
+        from . import formats as F
+        m = self.gather_macro()
+        paths = [os.path.join(directory, F.output_filename(k, itc)) for k in (F.FILE_THERMAL_BIN, F.FILE_THERMAL_PLT)]
+        F.output_binary_thermal(paths[0], m["u"], m["v"], m["w"], m["T"])
+        F.output_tecplot_thermal(paths[1], m["u"], m["v"], m["w"], m["T"])
+        return paths
+
+    def backupData(self, directory, itc):
+        """backupFile-<itc>.bin: u, v, w, T, f, g -- B3/seq/bouyancy3d.F90:1011-1029"""
+        import os
+        from . import formats as F
+        m = self.gather_macro()
+        path = os.path.join(directory, F.output_filename(F.FILE_BACKUP, itc))
+        F.backup_write(path, m["u"], m["v"], m["w"], m["T"], self.gather("f"), self.gather("g"))
+        return path
+
+    def loadInitField(self, path, rho="reference"):
+        """initial() with loadInitField = 1 (B3/seq/bouyancy3d.F90:289,367-391): u,v,w,T,f,g from the backup.  The reference
+        does not store rho and restarts with rho = 1 (:289) until the first macro(); rho="macro" instead recomputes it
+        from f in macro()'s summation order (:739), which makes the restart continue bit for bit."""
+        from . import formats as F
+        b = F.backup_read(path, self.total)
+        if rho == "macro":
+            r = np.zeros(self.total, order="F")
+            for a in range(19):
+                r += b["f"][a]
+        else:
+            r = np.ones(self.total, order="F")
+        self.scatter(f=b["f"], rho=r, u=b["u"], v=b["v"], w=b["w"])
+        self.scatter_thermal(g=b["g"], T=b["T"])
+        return b

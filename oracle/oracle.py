@@ -359,6 +359,12 @@ class ThermalWorld:
         self._lib.th_check(self._h, C.byref(eu), C.byref(et))
         return eu.value, et.value
 
+    def calNuRe(self, Prandtl=0.71):
+        nu, re = C.c_double(), C.c_double()
+        self._lib.th_calNuRe.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        self._lib.th_calNuRe(self._h, Prandtl, C.byref(nu), C.byref(re))
+        return nu.value, re.value
+
     def step(self, n=1):
         self._lib.th_step(self._h, n)
 

@@ -616,6 +616,25 @@ void th_check(th_world *w, double *errorU, double *errorT) {
     *errorU = w->errorU; *errorT = w->errorT;
 }
 
+/* ---- calNuRe(), B3/mpi_blocked/RaNu.F90:13-47: loop-order sums (k, j, i) per rank, rank-ordered sum over the ranks (the
+ * Allreduce the MPI driver would need), averages over the global box; viscosity, diffusivity from module.F90:38-39 ---- */
+void th_calNuRe(th_world *w, double prandtl, double *NuVolAvg, double *ReVolAvg) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int r = 0; r < w->np; ++r) {
+        th_rank *R = &w->r[r];
+        double NuVolAvg_temp = 0.0, ReVolAvg_temp = 0.0;
+        size_t n = (size_t)R->nx * R->ny * R->nz;
+        for (size_t q = 0; q < n; ++q) NuVolAvg_temp = NuVolAvg_temp + R->w[q] * R->T[q];
+        for (size_t q = 0; q < n; ++q)
+            ReVolAvg_temp = ReVolAvg_temp + (R->u[q] * R->u[q] + R->v[q] * R->v[q] + R->w[q] * R->w[q]);
+        t1 += NuVolAvg_temp; t2 += ReVolAvg_temp;
+    }
+    const double viscosity = (w->p.tauf - 0.5) / 3.0, diffusivity = viscosity / prandtl;
+    const double ncell = (double)((long long)w->total[0] * w->total[1] * w->total[2]), nz = (double)w->total[2];
+    *NuVolAvg = t1 / ncell * nz / diffusivity + 1.0;
+    *ReVolAvg = sqrt(t2 / ncell) * nz / viscosity;
+}
+
 /* n iterations of the driver loop body, B3:222-248 */
 void th_step(th_world *w, int n) {
     for (int s = 0; s < n; ++s) {
