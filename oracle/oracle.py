@@ -542,3 +542,142 @@ for _name, _sub in (("initial", "p2_initial"), ("collision", "p2_collision"), ("
                     ("bounceback_particle", "p2_bounceback_particle"), ("macro", "p2_macro"), ("calForce", "p2_calForce"),
                     ("updateCenter", "p2_updateCenter")):
     setattr(ParticleWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 2-D D2Q9 lid-driven cavity (oracle/lid2d.c): variant "c" = MPI/Lid_driven_cavity/c/lid_driven_cavity.c,
+# variant "f" = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked
+L2_FIELDS = {"f": 0, "f_post": 1, "rho": 2, "u": 3, "v": 4, "up": 5, "vp": 6}
+L2_VARIANTS = {"c": 0, "f": 1}
+
+
+def _l2_lib():
+    L = lib()
+    if not getattr(L, "_l2_ready", False):
+        L.l2_world_create.restype = C.c_void_p
+        L.l2_world_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double]
+        L.l2_world_destroy.argtypes = [C.c_void_p]
+        L.l2_world_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), _dp]
+        L.l2_rank_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.l2_rank_ptr.restype = _dp
+        L.l2_rank_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for fn in ("l2_initial", "l2_collision", "l2_exchange", "l2_streaming", "l2_bounceback", "l2_macro"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.l2_check.restype = C.c_double
+        L.l2_check.argtypes = [C.c_void_p]
+        L.l2_step.argtypes = [C.c_void_p, C.c_int]
+        L.l2_collide_cell.argtypes = [C.c_int, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
+        L.l2_dims_create.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L._l2_ready = True
+    return L
+
+
+class Lid2DRank:
+    def __init__(self, world, r):
+        L = world._lib
+        info = (C.c_int * 14)()
+        L.l2_rank_info(world._h, r, info)
+        self.n, self.coords, self.start = tuple(info[0:2]), tuple(info[2:4]), tuple(info[4:6])
+        self.nbr, self.cnr = tuple(info[6:10]), tuple(info[10:14])
+        nx, ny = self.n
+        shapes = {"f": (9, nx, ny), "f_post": (9, nx + 2, ny + 2)}
+        for name, which in L2_FIELDS.items():
+            shape = shapes.get(name, (nx, ny))
+            p = L.l2_rank_ptr(world._h, r, which)
+            setattr(self, name, np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape, order="F"))
+
+
+class Lid2DWorld:
+    """All P emulated ranks of the 2-D lid-driven cavity in one process."""
+
+    def __init__(self, total, nprocs=1, dims=None, variant="f", Re=1000.0, U0=0.1, rho0=1.0):
+        self._lib = _l2_lib()
+        d = (C.c_int * 2)(*(dims if dims else (0, 0)))
+        self._h = self._lib.l2_world_create(total[0], total[1], nprocs, d, L2_VARIANTS[variant], Re, U0, rho0)
+        self.total, self.nprocs, self.variant = tuple(total), nprocs, variant
+        self.ranks = [Lid2DRank(self, r) for r in range(nprocs)]
+        dd, par = (C.c_int * 2)(), (C.c_double * 3)()
+        self._lib.l2_world_info(self._h, dd, par)
+        self.dims, (self.tauf, self.Snu, self.Sq) = tuple(dd), tuple(par)
+
+    def close(self):
+        if self._h:
+            self.ranks = []
+            self._lib.l2_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self):
+        return self._lib.l2_check(self._h)
+
+    def step(self, n=1):
+        self._lib.l2_step(self._h, n)
+
+    def gather(self, name):
+        lead = (9,) if name == "f" else ()
+        out = np.empty(lead + self.total, order="F")
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            out[(slice(None),) * len(lead) + sl] = getattr(R, name)
+        return out
+
+    def scatter(self, name, glob):
+        lead = 1 if name == "f" else 0
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            getattr(R, name)[...] = glob[(slice(None),) * lead + sl]
+
+
+for _name, _sub in (("initial", "l2_initial"), ("collision", "l2_collision"), ("message_passing_sendrecv", "l2_exchange"),
+                    ("streaming", "l2_streaming"), ("bounceback", "l2_bounceback"), ("macro", "l2_macro")):
+    setattr(Lid2DWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))
+
+
+def l2_collide_cell(variant, f, rho, u, v, Snu, Sq):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    out = np.empty(9)
+    _l2_lib().l2_collide_cell(L2_VARIANTS[variant], f.ctypes.data_as(_dp), rho, u, v, Snu, Sq, out.ctypes.data_as(_dp))
+    return out
+
+
+class RefLid2D:
+    """The reference's own compiled C program (oracle/_ref/liblid2d_ref.so, built from
+    /root/reference/MPI/Lid_driven_cavity/c/lid_driven_cavity.c by `make -C oracle ref`): its functions and global arrays."""
+    NX = NY = 200
+
+    def __init__(self, path=None):
+        import os
+        path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liblid2d_ref.so")
+        self.lib = C.CDLL(path)            # RTLD_LOCAL: its globals are named rho, u, v, f ...
+        for fn in ("initial", "collision", "streaming", "boundary", "macro", "output_binary"):
+            getattr(self.lib, fn).restype = C.c_int
+        self.lib.check.restype = C.c_double
+        self.lib.check.argtypes = [C.c_int]
+        self.lib.output_tecplot.argtypes = [C.c_int]
+        n = self.NX * self.NY
+
+        def arr(name, shape):
+            a = (C.c_double * int(np.prod(shape))).in_dll(self.lib, name)
+            return np.ctypeslib.as_array(a).reshape(shape)            # C order: [NX][NY]([9])
+        self.f, self.f_post = arr("f", (self.NX, self.NY, 9)), arr("f_post", (self.NX, self.NY, 9))
+        self.rho, self.u, self.v = (arr(k, (self.NX, self.NY)) for k in ("rho", "u", "v"))
+        self.up, self.vp = arr("up", (self.NX, self.NY)), arr("vp", (self.NX, self.NY))
+
+    def scalar(self, name):
+        return C.c_double.in_dll(self.lib, name).value
+
+    def step(self, n=1):                  # the body of main()'s while loop, c:57-63
+        for _ in range(n):
+            self.lib.collision(); self.lib.streaming(); self.lib.boundary(); self.lib.macro()
+
+    # the C arrays seen in the oracle's layout: f(0:8, nx, ny), rho(nx, ny)
+    def f_F(self, post=False):
+        return np.asfortranarray(np.transpose(self.f_post if post else self.f, (2, 0, 1)))
+
+    def field_F(self, name):
+        return np.asfortranarray(getattr(self, name))

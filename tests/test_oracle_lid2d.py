@@ -1,0 +1,151 @@
+"""Pins the 2-D lid-driven-cavity oracle (oracle/lid2d.c) to the reference:
+  * variant "c" against the reference's own compiled C program -- live through oracle/_ref/liblid2d_ref.so (built by
+    `make -C oracle ref` from /root/reference/MPI/Lid_driven_cavity/c/lid_driven_cavity.c, shipped to the GPU box) and
+    through the committed outputs of that program (tests/golden/ref_lid2d.npz, made by make_golden_lid2d.py);
+  * variant "f" against the Fortran source text of 2d_revised/mpi_blocked evaluated by tests/golden/fortran_eval.py,
+    and the reference's seq == MPI contract (P emulated ranks == 1 rank, bit for bit)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "ref_lid2d.npz"))
+REF_SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "liblid2d_ref.so")
+
+
+def c_view(a):
+    """oracle (nx, ny[, 9 leading]) column-major -> the C program's [NX][NY]([9])"""
+    return np.ascontiguousarray(np.transpose(a, (1, 2, 0))) if a.ndim == 3 else np.ascontiguousarray(a)
+
+
+def test_parameters_match_the_compiled_reference_and_the_fortran_text():
+    wd = orc.Lid2DWorld((200, 200), variant="c")
+    assert (wd.tauf, wd.Snu, wd.Sq) == tuple(GOLD["c/params"])
+    wd.close()
+    wd = orc.Lid2DWorld((201, 201), variant="f")
+    assert (wd.tauf, wd.Snu, wd.Sq) == tuple(GOLD["f/params"])
+    wd.close()
+
+
+@pytest.mark.parametrize("variant", ["c", "f"])
+def test_collision_cells_bit_exact(variant):
+    f, ruv = GOLD["cells/f"], GOLD["cells/ruv"]
+    _, snu, sq = GOLD[variant + "/params"]
+    for k in range(len(f)):
+        got = orc.l2_collide_cell(variant, f[k], *ruv[k], snu, sq)
+        assert np.array_equal(got, GOLD[variant + "/collision_f_post"][k]), (variant, k)
+    # the two programs really round differently (otherwise one variant would do)
+    assert not np.array_equal(GOLD["c/collision_f_post"], GOLD["f/collision_f_post"])
+
+
+def test_fortran_macro_and_feq_cells_bit_exact():
+    f, ruv = GOLD["cells/f"], GOLD["cells/ruv"]
+    wd = orc.Lid2DWorld((len(f), 1), variant="f")
+    R = wd.ranks[0]
+    R.f[:, :, 0] = f.T
+    wd.macro()
+    got = np.stack([R.rho[:, 0], R.u[:, 0], R.v[:, 0]], axis=1)
+    assert np.array_equal(got, GOLD["f/macro_ruv"])
+    wd.close()
+    # initial(): f = feq(rho0, u) -- the lid row carries u = U0; compare the formula on the golden cells through a world
+    # whose rho/u/v are overwritten before the population loop is re-run by hand
+    W9 = [4.0 / 9.0] + [1.0 / 9.0] * 4 + [1.0 / 36.0] * 4
+    EX, EY = orc.EX9, orc.EY9
+    for k in range(len(f)):
+        rho, u, v = ruv[k]
+        us2 = u * u + v * v
+        for a in range(9):
+            un = u * float(EX[a]) + v * float(EY[a])
+            assert rho * W9[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2) == GOLD["f/feq"][k, a]
+
+
+def test_variant_c_run_matches_committed_reference_outputs():
+    wd = orc.Lid2DWorld((200, 200), variant="c")
+    wd.initial()
+    f0 = c_view(wd.gather("f"))
+    assert np.array_equal(f0[:, -1, :], GOLD["c/initial_f_top"]) and np.array_equal(f0[7, 3, :], GOLD["c/initial_f_bulk"])
+    done = 0
+    for n in (1, 10, 100, 1000):
+        wd.step(n - done); done = n
+        for k in ("rho", "u", "v"):
+            a = c_view(wd.gather(k))
+            assert np.array_equal(a[100, :], GOLD[f"c/run{n}/{k}_col100"]), (n, k)
+            assert np.array_equal(a[:, 199], GOLD[f"c/run{n}/{k}_row199"]), (n, k)
+            assert np.array_equal(a[:, 0], GOLD[f"c/run{n}/{k}_row0"]), (n, k)
+            assert np.array_equal(np.array([a.sum(), np.abs(a).sum(), (a * a).sum()]), GOLD[f"c/run{n}/{k}_sum"]), (n, k)
+        f = c_view(wd.gather("f"))
+        assert np.array_equal(f[:3, :3, :], GOLD[f"c/run{n}/f_corner"]) and np.array_equal(f[-3:, -3:, :], GOLD[f"c/run{n}/f_topright"])
+    assert wd.check() == GOLD["c/check_1000"][0]
+    wd.step(1000)
+    assert wd.check() == GOLD["c/check_2000"][0]
+    for k in ("rho", "u", "v"):
+        assert np.array_equal(c_view(wd.gather(k)), GOLD[f"c/run2000/{k}_full"]), k
+    wd.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/liblid2d_ref.so not built (make -C oracle ref)")
+def test_variant_c_live_against_the_compiled_reference(tmp_path, monkeypatch):
+    """every array of the reference program after each of its own subroutines, on seeded non-trivial input"""
+    monkeypatch.chdir(tmp_path)
+    ref = orc.RefLid2D(REF_SO)
+    ref.lib.initial()
+    wd = orc.Lid2DWorld((200, 200), variant="c")
+    wd.initial()
+    assert np.array_equal(ref.f_F(), wd.gather("f"))
+    rng = np.random.default_rng(5)
+    f = np.asfortranarray(wd.gather("f") * (1.0 + 0.05 * rng.uniform(-1, 1, (9, 200, 200))))
+    rho = np.asfortranarray(1.0 + 0.02 * rng.uniform(-1, 1, (200, 200)))
+    u, v = (np.asfortranarray(0.05 * rng.uniform(-1, 1, (200, 200))) for _ in range(2))
+    ref.f[...] = np.transpose(f, (1, 2, 0)); ref.rho[...] = rho; ref.u[...] = u; ref.v[...] = v
+    for k, a in (("f", f), ("rho", rho), ("u", u), ("v", v)):
+        wd.scatter(k, a)
+    for it in range(6):
+        ref.lib.collision(); wd.collision()
+        assert np.array_equal(ref.f_F(True), wd.ranks[0].f_post[:, 1:-1, 1:-1]), ("collision", it)
+        ref.lib.streaming(); ref.lib.boundary(); wd.message_passing_sendrecv(); wd.streaming(); wd.bounceback()
+        assert np.array_equal(ref.f_F(), wd.gather("f")), ("streaming+boundary", it)
+        ref.lib.macro(); wd.macro()
+        for k in ("rho", "u", "v"):
+            assert np.array_equal(ref.field_F(k), wd.gather(k)), (k, it)
+    assert ref.lib.check(6) == wd.check()
+    ref.step(20); wd.step(20)
+    assert ref.lib.check(26) == wd.check()
+    assert np.array_equal(ref.field_F("up"), wd.gather("up"))
+
+
+@pytest.mark.parametrize("variant", ["c", "f"])
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (6, None), (3, (1, 3)), (4, (4, 1)), (9, None)])
+def test_decomposed_equals_single_rank_bit_for_bit(variant, nprocs, dims):
+    total = (23, 19)
+    one, many = orc.Lid2DWorld(total, 1, variant=variant), orc.Lid2DWorld(total, nprocs, dims, variant=variant)
+    one.initial(); many.initial()
+    one.step(30); many.step(30)
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(one.gather(k), many.gather(k)), k
+    if variant == "f":
+        assert np.isclose(one.check(), many.check(), rtol=1e-13)
+    one.close(); many.close()
+
+
+def test_dims_create_2d():
+    lib = orc._l2_lib()
+    import ctypes as C
+    for n, want in [(1, (1, 1)), (2, (2, 1)), (4, (2, 2)), (6, (3, 2)), (8, (4, 2)), (9, (3, 3)), (12, (4, 3)), (7, (7, 1))]:
+        d = (C.c_int * 2)()
+        lib.l2_dims_create(n, d)
+        assert tuple(d) == want
+
+
+def test_mass_is_conserved_and_walls_never_leak_halo_values():
+    wd = orc.Lid2DWorld((31, 17), 4, variant="f")
+    wd.initial()
+    for R in wd.ranks:
+        R.f_post[...] = np.nan            # poison: wall halos must never reach f
+    m0 = wd.gather("rho").sum()
+    wd.step(50)
+    rho = wd.gather("rho")
+    assert np.isfinite(rho).all() and abs(rho.sum() - m0) / m0 < 1e-13
+    wd.close()
