@@ -2,8 +2,11 @@
 NCCL at N > 1).  One step = one exchange_message + one jacobi sweep (LAP:94-103).  Prints ONE JSON line in the
 shape of bench.py's; the metric is million cell updates per second, algorithmic traffic 16 B/cell (one read,
 one write; the source term is identically zero in the reference problem and is not read)."""
+import ctypes as C
 import json
 import os
+import sys
+import tempfile
 import time
 
 
@@ -155,4 +158,73 @@ def particles(args, rank, local_rank, world):
                                                          "l2": "state is L2-resident by design of the reference problem (161k nodes)"},
         "roofline": {"bound": "launch latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
                      "launches_per_step": round(launches / steps, 2), "us_per_step": round(ms / steps * 1e3, 2)},
+        "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+
+
+def lid2d(args, rank, local_rank, world):
+    """bench.py --workload lid2d: the reference's 2-D D2Q9 lid-driven cavity on one GPU, lattice far larger than
+    L2 (default 8192 x 8192: 4.8 GB per population set).  Roofline: 144 B/cell = 9 loads + 9 stores of fp64 per fused launch.
+    cpu_baseline: the reference's OWN compiled C program (oracle/_ref/liblid2d_ref.so, 200 x 200 as shipped, one thread)."""
+    import torch
+
+    import bench as B
+    import mglc_b200 as mg
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "MLUPS", "value": None, "note": "lid2d bench runs on one GPU"}))
+        return
+    torch.cuda.set_device(local_rank)
+    n = args.size or 8192
+    sim = mg.LidDrivenCavity2D((n, n), variant="f", strict=args.arith == "strict", device=local_rank)
+    sim.initial()
+    sim.step(max(args.warmup, 3)); sim.sync()
+    l0 = sim.launch_count()
+    sampler = B.ClockSampler(local_rank); sampler.start()
+    ms = sim.step_timed(args.steps)
+    clocks = sampler.stop()
+    launches = sim.launch_count() - l0
+    err = sim.check()
+    sim.close()
+    cells = n * n
+    peak, peak_src = B.hbm_peak()
+    # a step(K) call is collision + (K-1) fused launches + stream/macro: all three move 144-176 B/cell; report the whole step
+    achieved = 144.0 * cells * args.steps / (ms * 1e-3) / 1e9
+    cpu = None
+    ref_so = os.path.join(B.ROOT, "oracle", "_ref", "liblid2d_ref.so")
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        if os.path.exists(ref_so):
+            cwd = os.getcwd()
+            tmp = tempfile.mkdtemp()
+            os.chdir(tmp)                  # the reference program writes its output files into the working directory
+            sys.stdout.flush()
+            saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+            os.dup2(null, 1)               # ... and prints a banner: keep this process's stdout to the one JSON line
+            try:
+                ref = orc.RefLid2D(ref_so)
+                ref.lib.initial(); ref.step(20)
+                t0 = time.perf_counter(); ref.step(2000); dt = time.perf_counter() - t0
+                C.CDLL(None).fflush(None)
+            finally:
+                os.dup2(saved, 1); os.close(saved); os.close(null)
+                os.chdir(cwd)
+            cpu = {"value": round(200 * 200 * 2000 / dt / 1e6, 2), "unit": "MLUPS", "cores": 1, "kind": "reference",
+                   "sample": f"MPI/Lid_driven_cavity/c/lid_driven_cavity.c as shipped (200x200), 2000 steps ({dt:.1f} s), gcc -O2"}
+        else:
+            wd = orc.Lid2DWorld((1024, 1024), 1)
+            wd.initial(); wd.step(2)
+            t0 = time.perf_counter(); wd.step(20); dt = time.perf_counter() - t0
+            wd.close()
+            cpu = {"value": round(1024 * 1024 * 20 / dt / 1e6, 2), "unit": "MLUPS", "cores": 1, "kind": "port",
+                   "sample": f"1024x1024, 20 steps ({dt:.1f} s), oracle/lid2d.c"}
+    print(json.dumps({
+        "metric": "MLUPS", "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lid_driven_cavity_d2q9_mrt_{n}x{n}", "Re": 1000.0, "U0": 0.1, "arith": args.arith, "errorU": err,
+                   "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (9 * cells * 8 / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": f"mglc::{args.arith}::k_l2_fused", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 144,
+                     "cells_per_launch": cells, "note": "whole step(K) call timed: collision + (K-1) fused + stream/macro launches"},
         "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGLC_VERSION 101
+#define MGLC_VERSION 102
 
 /* ---- status codes ---- */
 #define MGLC_OK          0
@@ -320,6 +320,48 @@ int mglc_p2d_get_rho_avg(mglc_p2d *h, double *rhoAvg);
 int mglc_p2d_error_flags(mglc_p2d *h, int *flags);
 int mglc_p2d_launch_count(mglc_p2d *h, long long *n);
 int mglc_p2d_sync(mglc_p2d *h);
+
+/* ================= 2-D D2Q9 lid-driven cavity =================
+ * The reference ships it twice: L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c (plain C, one domain, 200 x 200) and
+ * L2F = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/ (Fortran + MPI, 2-D Cartesian blocks, 201 x 201).  They differ only
+ * in the rounding of collision() (L2C: (...)/36.0 and meq(8) = u*v, c:186-255; L2F: per-term divisions and meq(8) = rho*u*v,
+ * evolution.f90:15-70) and in check(); `variant` picks the one to reproduce.  Host arrays are L2F's, column-major:
+ * f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v(nx,ny) (initial.f90:30-38); L2C's f[NX][NY][9] is the same memory read as
+ * (0:8,ny,nx), i.e. the caller transposes x and y.  A handle owns ONE subdomain (one process per GPU, halos over NCCL) or
+ * all P of them (mglc_l2d_create_local); `r` = index among those owned. */
+enum { MGLC_L2D_C = 0, MGLC_L2D_F = 1 };
+typedef struct mglc_l2d mglc_l2d;
+typedef struct mglc_l2d_desc {
+    int total_nx, total_ny;              /* commondata.f90:4 ; c:9-10                       */
+    int variant;                         /* MGLC_L2D_C | MGLC_L2D_F                         */
+    int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT             */
+    double reynolds, U0, rho0;           /* 1000, 0.1, 1    commondata.f90:6-8 ; c:15-17    */
+} mglc_l2d_desc;
+int mglc_l2d_desc_init(mglc_l2d_desc *d, int variant);                  /* the shipped constants of that program */
+/* MPI_Dims_create(np,2) + MPI_Cart_create + decompose_1d + MPI_Cart_shift + MPI_Cart_find_corners + allocate -- main.f90:24-60,
+ * initial.f90:30-38; tau = U0*total_nx/Re*3 + 0.5, Snu, Sq -- commondata.f90:9,31 */
+int mglc_l2d_create(mglc_l2d **h, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks, int rank, int device,
+                    mglc_comm *comm_or_null);
+int mglc_l2d_create_local(mglc_l2d **h, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks, const int *devices_or_null);
+int mglc_l2d_destroy(mglc_l2d *h);
+int mglc_l2d_nlocal(mglc_l2d *h, int *n);
+/* nbr[0..3] = right(+x), left(-x), top(+y), bottom(-y); nbr[4..7] = where populations 5..8 go; -1 = MPI_PROC_NULL */
+int mglc_l2d_info(mglc_l2d *h, int r, int dims[2], int ln[2], int start[2], int coords[2], int nbr[8]);
+int mglc_l2d_params(mglc_l2d *h, double *tau, double *Snu, double *Sq);
+int mglc_l2d_upload(mglc_l2d *h, int r, const double *f, const double *f_post, const double *rho, const double *u,
+                    const double *v);                                   /* NULL = keep */
+int mglc_l2d_download(mglc_l2d *h, int r, double *f, double *f_post, double *rho, double *u, double *v);
+int mglc_l2d_initial(mglc_l2d *h);      /* initial()                    initial.f90:40-66   == c:123-151 */
+int mglc_l2d_collision(mglc_l2d *h);    /* collision()                  evolution.f90:1-71   == c:186-255 */
+int mglc_l2d_exchange(mglc_l2d *h);     /* message_passing_sendrecv()   ex_sendrecv.f90:1-81             */
+int mglc_l2d_streaming(mglc_l2d *h);    /* streaming()                  evolution.f90:75-94  == c:262-283 */
+int mglc_l2d_bounceback(mglc_l2d *h);   /* bounceback() / boundary()    bounceback.f90:1-44 == c:286-313 */
+int mglc_l2d_macro(mglc_l2d *h);        /* macro()                      evolution.f90:98-112 == c:318-338 */
+int mglc_l2d_check(mglc_l2d *h, double *errorU);   /* check()           evolution.f90:115-150 == c:341-363 */
+int mglc_l2d_step(mglc_l2d *h, int nsteps);        /* nsteps loop bodies  main.f90:66-82    == c:57-63   */
+int mglc_l2d_step_timed(mglc_l2d *h, int nsteps, float *ms);
+int mglc_l2d_launch_count(mglc_l2d *h, long long *n);
+int mglc_l2d_sync(mglc_l2d *h);
 
 /* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
  * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /

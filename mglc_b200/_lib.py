@@ -16,6 +16,7 @@ MRT_LID, MRT_THERMAL, BGK = 0, 1, 2
 ARITH_FAST, ARITH_STRICT = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 BCT_ADIABATIC, BCT_CONST_HOT, BCT_CONST_COLD = 0, 1, 2
+L2D_C, L2D_F = 0, 1
 
 
 class MglcError(RuntimeError):
@@ -42,6 +43,11 @@ class P2dDesc(C.Structure):
     _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("nparticles", C.c_int), ("reserved", C.c_int)] + \
                [(n, C.c_double) for n in ("rho0", "rhoSolid", "viscosity", "radius0", "gravity", "thresholdWall", "stiffWall",
                                           "thresholdParticle", "stiffParticle")]
+
+
+class L2dDesc(C.Structure):
+    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("variant", C.c_int), ("arith", C.c_int),
+                ("reynolds", C.c_double), ("U0", C.c_double), ("rho0", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -186,6 +192,27 @@ SIGNATURES = {
     "mglc_p2d_error_flags": (C.c_int, [_vp, _ip]),
     "mglc_p2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_p2d_sync": (C.c_int, [_vp]),
+    # 2-D D2Q9 lid-driven cavity
+    "mglc_l2d_desc_init": (C.c_int, [C.POINTER(L2dDesc), C.c_int]),
+    "mglc_l2d_create": (C.c_int, [_vpp, C.POINTER(L2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
+    "mglc_l2d_create_local": (C.c_int, [_vpp, C.POINTER(L2dDesc), _ip, C.c_int, _ip]),
+    "mglc_l2d_destroy": (C.c_int, [_vp]),
+    "mglc_l2d_nlocal": (C.c_int, [_vp, _ip]),
+    "mglc_l2d_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "mglc_l2d_params": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "mglc_l2d_upload": (C.c_int, [_vp, C.c_int] + [_vp] * 5),
+    "mglc_l2d_download": (C.c_int, [_vp, C.c_int] + [_vp] * 5),
+    "mglc_l2d_initial": (C.c_int, [_vp]),
+    "mglc_l2d_collision": (C.c_int, [_vp]),
+    "mglc_l2d_exchange": (C.c_int, [_vp]),
+    "mglc_l2d_streaming": (C.c_int, [_vp]),
+    "mglc_l2d_bounceback": (C.c_int, [_vp]),
+    "mglc_l2d_macro": (C.c_int, [_vp]),
+    "mglc_l2d_check": (C.c_int, [_vp, _dp]),
+    "mglc_l2d_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_l2d_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_l2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_l2d_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

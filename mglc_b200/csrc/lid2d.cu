@@ -1,0 +1,624 @@
+// lid2d.cu -- the reference's 2-D D2Q9 MRT lid-driven cavity behind the mglc_l2d_* entry points of mglc.h:
+//   L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c                      (plain C, one domain, 200 x 200)
+//   L2F = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/*.f90     (Fortran + MPI, 2-D Cartesian blocks, 201 x 201)
+// The two programs differ only in the rounding of collision() and in check(); `variant` selects which one is reproduced.
+// This file holds the strict build of the collision / fused kernels (-fmad=false), the copy-type subroutines (streaming,
+// bounceback, macro, initial, check, halo pack/unpack, layout transposes) and the host side; lid2d_fast.cu is the
+// throughput build of the same kernel source.
+#define MGLC_NS strict
+#define MGLC_STRICT 1
+#include "lid2d_kernels.inl"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "halo.cuh"
+
+using namespace mglc;
+
+namespace {
+
+// commondata.f90:25-27 == c:24-25
+__constant__ int c_ex9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+__constant__ int c_ey9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+const int h_ex9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+const int h_ey9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+// populations leaving through each side, ascending = tag order of ex_sendrecv.f90:9-45 (to right, left, top, bottom)
+__constant__ int c_face_pops9[4][3] = {{1, 5, 8}, {3, 6, 7}, {2, 5, 6}, {4, 7, 8}};
+
+// initial(): initial.f90:40-66 == c:123-151
+__global__ void __launch_bounds__(128) k_l2_initial(Geom2 g, L2Params p, int lid, double *__restrict__ F, double *__restrict__ rho,
+                                                    double *__restrict__ u, double *__restrict__ v, double *__restrict__ up,
+                                                    double *__restrict__ vp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+    if (i > g.nx) return;
+    const double omega[9] = {4.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
+    const long long c = g.idx(0, i, j), m = g.cell(i, j);
+    const double r = p.rho0, uu = (lid && j == g.ny) ? p.U0 : 0.0, vv = 0.0;
+    rho[m] = r; u[m] = uu; v[m] = vv; up[m] = 0.0; vp[m] = 0.0;
+    const double us2 = uu * uu + vv * vv;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        const double un = uu * (double)c_ex9[a] + vv * (double)c_ey9[a];
+        F[a * g.sq + c] = r * omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+    }
+}
+
+// streaming(): evolution.f90:80-97 (pull from the halo'd f_post; wall halos are read as they are, like the reference)
+__global__ void __launch_bounds__(128) k_l2_streaming(Geom2 g, const double *__restrict__ Fpost, double *__restrict__ F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) F[a * g.sq + c] = Fpost[a * g.sq + c - c_ey9[a] * g.sy - c_ex9[a]];
+}
+
+// bounceback(): bounceback.f90:7-40 == boundary(), c:286-313.  One thread per wall cell applies left, right, bottom, top in
+// the reference's order, so the later wall wins in the corners exactly as in the sequential loops.
+__global__ void __launch_bounds__(128) k_l2_bounceback(Geom2 g, L2Params p, const double *__restrict__ Fpost,
+                                                       const double *__restrict__ rho, double *__restrict__ F) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int i, j;
+    if (t < g.nx) { i = t + 1; j = 1; }
+    else if (t < 2 * g.nx) { i = t - g.nx + 1; j = g.ny; if (g.ny == 1) return; }
+    else if (t < 2 * g.nx + (g.ny - 2)) { i = 1; j = t - 2 * g.nx + 2; }
+    else if (t < 2 * g.nx + 2 * (g.ny - 2)) { i = g.nx; j = t - 2 * g.nx - (g.ny - 2) + 2; if (g.nx == 1) return; }
+    else return;
+    const long long c = g.idx(0, i, j), sq = g.sq;
+    if (g.wall[1] && i == 1) { F[1 * sq + c] = Fpost[3 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[8 * sq + c] = Fpost[6 * sq + c]; }
+    if (g.wall[0] && i == g.nx) { F[3 * sq + c] = Fpost[1 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; F[7 * sq + c] = Fpost[5 * sq + c]; }
+    if (g.wall[3] && j == 1) { F[2 * sq + c] = Fpost[4 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; }
+    if (g.wall[2] && j == g.ny) {
+        const double r = rho[g.cell(i, j)];
+        F[4 * sq + c] = Fpost[2 * sq + c];
+        F[7 * sq + c] = Fpost[5 * sq + c] - r * p.U0 / 6.0;
+        F[8 * sq + c] = Fpost[6 * sq + c] - r * (-p.U0) / 6.0;
+    }
+}
+
+// macro(): evolution.f90:105-113 == c:321-336
+__global__ void __launch_bounds__(128) k_l2_macro(Geom2 g, const double *__restrict__ F, double *__restrict__ rho,
+                                                  double *__restrict__ u, double *__restrict__ v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j), m = g.cell(i, j);
+    double f[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
+    const double r = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
+    rho[m] = r;
+    u[m] = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / r;
+    v[m] = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / r;
+}
+
+// the lid row of rho, kept beside the rotated loop (the lid term uses rho of the previous macro(), bounceback.f90:35-36)
+__global__ void k_l2_lid_row(Geom2 g, const double *__restrict__ rho, double *__restrict__ lid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i <= g.nx) lid[i - 1] = rho[g.cell(i, g.ny)];
+}
+
+// check(): evolution.f90:128-147 == c:341-363: error1 = sum (du^2 + dv^2), error2 = sum (u^2 + v^2); up, vp <- u, v
+constexpr int L2_CHECK_BLOCKS = 296;   // fixed: reproducible summation order
+__global__ void __launch_bounds__(256) k_l2_check_partial(long long n, const double *__restrict__ u, const double *__restrict__ v,
+                                                          double *__restrict__ up, double *__restrict__ vp, double *__restrict__ part) {
+    double e1 = 0.0, e2 = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const double a = u[q], b = v[q];
+        const double da = a - up[q], db = b - vp[q];
+        e1 += da * da + db * db;
+        e2 += a * a + b * b;
+        up[q] = a; vp[q] = b;
+    }
+    __shared__ double s1[256], s2[256];
+    s1[threadIdx.x] = e1; s2[threadIdx.x] = e2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 + 2 * blockIdx.x] = s1[0]; part[3 + 2 * blockIdx.x] = s2[0]; }
+}
+__global__ void k_l2_check_final(int nblocks, double *__restrict__ part) {
+    double e1 = 0.0, e2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) { e1 += part[2 + 2 * b]; e2 += part[3 + 2 * b]; }
+    part[0] = e1; part[1] = e2;
+}
+
+// halo messages of message_passing_sendrecv(), ex_sendrecv.f90:9-78: dir 0..3 = to right(+x), left(-x), top(+y), bottom(-y), three
+// populations over the interior range, buffer [slot][t]; dir 4..7 = the corner population 5..8 crosses, one value.
+__device__ __forceinline__ void l2_msg_cell(const Geom2 &g, int dir, int ghost, int t, int &i, int &j) {
+    if (dir < 4) {
+        const int axis = dir >> 1, plus = !(dir & 1);
+        const int nfix = axis == 0 ? g.nx : g.ny;
+        const int fix = ghost ? (plus ? 0 : nfix + 1) : (plus ? nfix : 1);
+        i = axis == 0 ? fix : 1 + t;
+        j = axis == 1 ? fix : 1 + t;
+    } else {
+        const int a = dir + 1, px = c_ex9[a] > 0, py = c_ey9[a] > 0;
+        i = ghost ? (px ? 0 : g.nx + 1) : (px ? g.nx : 1);
+        j = ghost ? (py ? 0 : g.ny + 1) : (py ? g.ny : 1);
+    }
+}
+__global__ void k_l2_pack(Geom2 g, const double *__restrict__ Fpost, int dir, int n1, int npop, double *__restrict__ buf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 * npop) return;
+    int i, j;
+    l2_msg_cell(g, dir, 0, t % n1, i, j);
+    const int a = dir < 4 ? c_face_pops9[dir][t / n1] : dir + 1;
+    buf[t] = Fpost[g.idx(a, i, j)];
+}
+__global__ void k_l2_unpack(Geom2 g, double *__restrict__ Fpost, int dir, int n1, int npop, const double *__restrict__ buf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 * npop) return;
+    int i, j;
+    l2_msg_cell(g, dir, 1, t % n1, i, j);
+    const int a = dir < 4 ? c_face_pops9[dir][t / n1] : dir + 1;
+    Fpost[g.idx(a, i, j)] = buf[t];
+}
+
+// reference layout (population index fastest; with_halo: (0:8,0:nx+1,0:ny+1), else (0:8,nx,ny)) <-> SoA rows
+__global__ void __launch_bounds__(128) k_l2_aos_to_soa(Geom2 g, const double *__restrict__ aos, double *__restrict__ F, int with_halo) {
+    const int w = with_halo ? g.nx + 2 : g.nx, hgt = with_halo ? g.ny + 2 : g.ny;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= hgt) return;
+    const int i = with_halo ? x : x + 1, j = with_halo ? y : y + 1;
+    const long long src = 9LL * (x + (long long)w * y), c = g.idx(0, i, j);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) F[a * g.sq + c] = aos[src + a];
+}
+__global__ void __launch_bounds__(128) k_l2_soa_to_aos(Geom2 g, const double *__restrict__ F, double *__restrict__ aos, int with_halo) {
+    const int w = with_halo ? g.nx + 2 : g.nx, hgt = with_halo ? g.ny + 2 : g.ny;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= hgt) return;
+    const int i = with_halo ? x : x + 1, j = with_halo ? y : y + 1;
+    const long long dst = 9LL * (x + (long long)w * y), c = g.idx(0, i, j);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) aos[dst + a] = F[a * g.sq + c];
+}
+
+struct L2Sub {
+    int n[2], coords[2], start[2];
+    int nbr[4];          // right(+x), left(-x), top(+y), bottom(-y); -1 = MPI_PROC_NULL     main.f90:46-47
+    int cnr[4];          // the neighbours populations 5..8 travel to                        MPI_Cart_find_corners, main.f90:120-170
+    int device;
+    Geom2 g;
+    double *F;           // f      (pre-collision)
+    double *P[2];        // f_post = P[cur]; the rotated loop ping-pongs between the two
+    int cur;
+    double *rho, *u, *v, *up, *vp;
+    double *lid[2];      // rho of the lid row, ping-pong beside P
+    double *stage;       // reference-layout staging for upload / download
+    double *scratch;     // check() partial sums
+    cudaStream_t s;
+    cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
+    Msg msgs[8];
+    long long launches;
+};
+
+}  // namespace
+
+struct mglc_l2d {
+    mglc_l2d_desc d;
+    int dims[2], nranks;
+    double tau;
+    L2Params p;
+    std::vector<L2Sub *> subs;      // the subdomains this process owns (all of them, or exactly one)
+    std::vector<Port> ports;
+    mglc_comm *comm;
+};
+
+extern "C" int mglc_l2d_desc_init(mglc_l2d_desc *d, int variant) {
+    if (!d || (variant != MGLC_L2D_C && variant != MGLC_L2D_F)) { set_error("mglc_l2d_desc_init: variant=%d", variant); return MGLC_E_INVALID; }
+    memset(d, 0, sizeof *d);
+    d->variant = variant;
+    d->total_nx = d->total_ny = variant == MGLC_L2D_C ? 200 : 201;      // c:9-10 ; commondata.f90:4
+    d->arith = MGLC_ARITH_FAST;
+    d->reynolds = 1000.0; d->U0 = 0.1; d->rho0 = 1.0;                   // c:15-17 ; commondata.f90:6-8
+    return MGLC_OK;
+}
+
+static int l2_use(L2Sub *S) { MGLC_CUDA(cudaSetDevice(S->device)); return MGLC_OK; }
+
+static void l2_free_sub(L2Sub *S) {
+    if (!S) return;
+    cudaSetDevice(S->device);
+    if (S->s) cudaStreamSynchronize(S->s);
+    double *bufs[] = {S->F, S->P[0], S->P[1], S->rho, S->u, S->v, S->up, S->vp, S->lid[0], S->lid[1], S->stage, S->scratch};
+    for (double *p : bufs) cudaFree(p);
+    for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
+    cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (S->s) cudaStreamDestroy(S->s);
+    (void)cudaGetLastError();
+    delete S;
+}
+
+extern "C" int mglc_l2d_destroy(mglc_l2d *h) {
+    if (!h) return MGLC_OK;
+    for (L2Sub *S : h->subs) l2_free_sub(S);
+    delete h;
+    return MGLC_OK;
+}
+
+static int l2_cart_rank(const int dims[2], int c0, int c1) {
+    if (c0 < 0 || c0 >= dims[0] || c1 < 0 || c1 >= dims[1]) return -1;
+    return c0 * dims[1] + c1;
+}
+static void l2_msg_dims(const L2Sub *S, int dir, int &n1, int &npop) {
+    if (dir < 4) { n1 = (dir >> 1) == 0 ? S->n[1] : S->n[0]; npop = 3; }
+    else { n1 = 1; npop = 1; }
+}
+
+static int l2_make_sub(mglc_l2d *h, int rank, int device, L2Sub **out) {
+    L2Sub *S = new L2Sub();
+    memset(S, 0, sizeof *S);
+    S->device = device;
+    S->coords[0] = rank / h->dims[1]; S->coords[1] = rank % h->dims[1];
+    const int gn[2] = {h->d.total_nx, h->d.total_ny};
+    for (int d = 0; d < 2; ++d) {
+        if (gn[d] < h->dims[d]) { set_error("mglc_l2d_create: fewer cells than ranks along dim %d", d); delete S; return MGLC_E_INVALID; }
+        mglc_decompose_1d(gn[d], S->coords[d], h->dims[d], &S->n[d], &S->start[d]);
+    }
+    const int c0 = S->coords[0], c1 = S->coords[1];
+    S->nbr[0] = l2_cart_rank(h->dims, c0 + 1, c1); S->nbr[1] = l2_cart_rank(h->dims, c0 - 1, c1);
+    S->nbr[2] = l2_cart_rank(h->dims, c0, c1 + 1); S->nbr[3] = l2_cart_rank(h->dims, c0, c1 - 1);
+    for (int a = 5; a < 9; ++a) S->cnr[a - 5] = l2_cart_rank(h->dims, c0 + h_ex9[a], c1 + h_ey9[a]);
+    S->g = make_geom2(S->n[0], S->n[1]);
+    S->g.wall[0] = c0 == h->dims[0] - 1; S->g.wall[1] = c0 == 0;
+    S->g.wall[2] = c1 == h->dims[1] - 1; S->g.wall[3] = c1 == 0;
+    auto fail = [&](int rc) { l2_free_sub(S); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return fail(MGLC_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&S->s, cudaStreamNonBlocking) != cudaSuccess) return fail(MGLC_E_CUDA);
+    if (cudaEventCreateWithFlags(&S->ev_packed, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&S->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&S->ev_t0) != cudaSuccess || cudaEventCreate(&S->ev_t1) != cudaSuccess) return fail(MGLC_E_CUDA);
+    const size_t lat = 9 * (size_t)S->g.sq * sizeof(double), fld = (size_t)S->n[0] * S->n[1] * sizeof(double);
+    struct { double **p; size_t bytes; } bufs[] = {{&S->F, lat}, {&S->P[0], lat}, {&S->P[1], lat}, {&S->rho, fld}, {&S->u, fld}, {&S->v, fld},
+                                                   {&S->up, fld}, {&S->vp, fld}, {&S->lid[0], (size_t)S->n[0] * 8}, {&S->lid[1], (size_t)S->n[0] * 8},
+                                                   {&S->stage, 9 * (size_t)(S->n[0] + 2) * (S->n[1] + 2) * sizeof(double)},
+                                                   {&S->scratch, (size_t)(4 + 2 * L2_CHECK_BLOCKS) * sizeof(double)}};
+    for (auto &b : bufs) {
+        if (cudaMalloc((void **)b.p, b.bytes) != cudaSuccess) { (void)cudaGetLastError(); set_error("mglc_l2d_create: out of device memory"); return fail(MGLC_E_NOMEM); }
+        cudaMemsetAsync(*b.p, 0, b.bytes, S->s);
+    }
+    for (int dir = 0; dir < 8; ++dir) {
+        Msg &M = S->msgs[dir];
+        int n1, npop;
+        l2_msg_dims(S, dir, n1, npop);
+        M.dir = dir;
+        // what I send towards direction `dir` is received from the neighbour on the opposite side
+        const int ox = dir < 4 ? (dir == 0) - (dir == 1) : h_ex9[dir + 1], oy = dir < 4 ? (dir == 2) - (dir == 3) : h_ey9[dir + 1];
+        M.send_to = l2_cart_rank(h->dims, c0 + ox, c1 + oy);
+        M.recv_from = l2_cart_rank(h->dims, c0 - ox, c1 - oy);
+        // face messages span the sender's interior range; both ends share that extent along the face (same coordinate there)
+        M.send_count = M.send_to >= 0 ? (long long)n1 * npop : 0;
+        M.recv_count = M.recv_from >= 0 ? (long long)n1 * npop : 0;
+        if (M.send_count && cudaMalloc((void **)&M.sbuf, M.send_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
+        if (M.recv_count && cudaMalloc((void **)&M.rbuf, M.recv_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
+    }
+    if (cudaStreamSynchronize(S->s) != cudaSuccess) return fail(MGLC_E_CUDA);
+    *out = S;
+    return MGLC_OK;
+}
+
+static int l2_new(mglc_l2d **out, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks) {
+    if (!out || !d || nranks < 1) { set_error("mglc_l2d_create: bad arguments"); return MGLC_E_INVALID; }
+    if (d->total_nx < 1 || d->total_ny < 1 || (d->variant != MGLC_L2D_C && d->variant != MGLC_L2D_F) ||
+        (d->arith != MGLC_ARITH_FAST && d->arith != MGLC_ARITH_STRICT) || !(d->reynolds > 0.0)) {
+        set_error("mglc_l2d_create: bad descriptor (%d x %d, variant %d, arith %d, Re %g)", d->total_nx, d->total_ny, d->variant, d->arith, d->reynolds);
+        return MGLC_E_INVALID;
+    }
+    MGLC_TRY(require_gpu());
+    mglc_l2d *h = new mglc_l2d();
+    h->d = *d; h->nranks = nranks; h->comm = nullptr;
+    if (dims_or_zero && dims_or_zero[0] > 0) { h->dims[0] = dims_or_zero[0]; h->dims[1] = dims_or_zero[1]; }
+    else { int d3[3]; mglc_dims_create_nd(nranks, 2, d3); h->dims[0] = d3[0]; h->dims[1] = d3[1]; }      // main.f90:28
+    if (h->dims[0] * h->dims[1] != nranks) {
+        set_error("mglc_l2d_create: dims %dx%d do not fit %d ranks", h->dims[0], h->dims[1], nranks);
+        delete h;
+        return MGLC_E_INVALID;
+    }
+    // commondata.f90:9,31 == c:96-101 (nu = u_zero*height/Re; tau = 3*nu + 0.5: the same products in the same order)
+    h->tau = d->U0 * (double)d->total_nx / d->reynolds * 3.0 + 0.5;
+    h->p.Snu = 1.0 / h->tau;
+    h->p.Sq = 8.0 * (2.0 * h->tau - 1.0) / (8.0 * h->tau - 1.0);
+    h->p.U0 = d->U0; h->p.rho0 = d->rho0;
+    *out = h;
+    return MGLC_OK;
+}
+
+extern "C" int mglc_l2d_create(mglc_l2d **out, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks, int rank, int device,
+                               mglc_comm *comm_or_null) {
+    if (nranks > 1 && !comm_or_null) { set_error("mglc_l2d_create: %d ranks need a communicator (or use mglc_l2d_create_local)", nranks); return MGLC_E_INVALID; }
+    if (rank < 0 || rank >= nranks) { set_error("mglc_l2d_create: rank=%d of %d", rank, nranks); return MGLC_E_INVALID; }
+    mglc_l2d *h = nullptr;
+    MGLC_TRY(l2_new(&h, d, dims_or_zero, nranks));
+    h->comm = comm_or_null;
+    L2Sub *S = nullptr;
+    int rc = l2_make_sub(h, rank, device, &S);
+    if (rc) { delete h; return rc; }
+    h->subs.push_back(S);
+    *out = h;
+    return MGLC_OK;
+}
+
+extern "C" int mglc_l2d_create_local(mglc_l2d **out, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks,
+                                     const int *devices_or_null) {
+    mglc_l2d *h = nullptr;
+    MGLC_TRY(l2_new(&h, d, dims_or_zero, nranks));
+    for (int r = 0; r < nranks; ++r) {
+        L2Sub *S = nullptr;
+        int rc = l2_make_sub(h, r, devices_or_null ? devices_or_null[r] : 0, &S);
+        if (rc) { mglc_l2d_destroy(h); return rc; }
+        h->subs.push_back(S);
+    }
+    for (L2Sub *a : h->subs)
+        for (L2Sub *b : h->subs)
+            if (a->device != b->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, a->device, b->device);
+                if (can) { cudaSetDevice(a->device); cudaDeviceEnablePeerAccess(b->device, 0); (void)cudaGetLastError(); }
+            }
+    for (L2Sub *S : h->subs) h->ports.push_back(Port{S->device, S->s, S->ev_packed, S->ev_copied, S->msgs, 8});
+    *out = h;
+    return MGLC_OK;
+}
+
+static int l2_sub(mglc_l2d *h, int r, L2Sub **S) {
+    if (!h || r < 0 || r >= (int)h->subs.size()) { set_error("mglc_l2d: bad handle or local index %d", r); return MGLC_E_INVALID; }
+    *S = h->subs[r];
+    return l2_use(*S);
+}
+
+extern "C" int mglc_l2d_nlocal(mglc_l2d *h, int *n) {
+    if (!h || !n) return MGLC_E_INVALID;
+    *n = (int)h->subs.size();
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_info(mglc_l2d *h, int r, int dims[2], int ln[2], int start[2], int coords[2], int nbr[8]) {
+    if (!h || r < 0 || r >= (int)h->subs.size()) return MGLC_E_INVALID;
+    L2Sub *S = h->subs[r];
+    if (dims) memcpy(dims, h->dims, 8);
+    if (ln) memcpy(ln, S->n, 8);
+    if (start) memcpy(start, S->start, 8);
+    if (coords) memcpy(coords, S->coords, 8);
+    if (nbr) { memcpy(nbr, S->nbr, 16); memcpy(nbr + 4, S->cnr, 16); }
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_params(mglc_l2d *h, double *tau, double *Snu, double *Sq) {
+    if (!h) return MGLC_E_INVALID;
+    if (tau) *tau = h->tau;
+    if (Snu) *Snu = h->p.Snu;
+    if (Sq) *Sq = h->p.Sq;
+    return MGLC_OK;
+}
+
+static dim3 l2_grid(const L2Sub *S, int halo = 0) { return dim3((S->n[0] + 2 * halo + 127) / 128, S->n[1] + 2 * halo); }
+
+static int l2_put_lattice(L2Sub *S, const double *host, double *dev, int with_halo) {
+    if (!host) return MGLC_OK;
+    const size_t cells = with_halo ? (size_t)(S->n[0] + 2) * (S->n[1] + 2) : (size_t)S->n[0] * S->n[1];
+    MGLC_CUDA(cudaMemcpyAsync(S->stage, host, 9 * cells * sizeof(double), cudaMemcpyHostToDevice, S->s));
+    k_l2_aos_to_soa<<<l2_grid(S, with_halo), 128, 0, S->s>>>(S->g, S->stage, dev, with_halo);
+    S->launches += 1;
+    MGLC_CUDA(cudaStreamSynchronize(S->s));       // the staging buffer is reused and `host` may be pageable
+    return MGLC_OK;
+}
+static int l2_get_lattice(L2Sub *S, double *host, const double *dev, int with_halo) {
+    if (!host) return MGLC_OK;
+    const size_t cells = with_halo ? (size_t)(S->n[0] + 2) * (S->n[1] + 2) : (size_t)S->n[0] * S->n[1];
+    k_l2_soa_to_aos<<<l2_grid(S, with_halo), 128, 0, S->s>>>(S->g, dev, S->stage, with_halo);
+    S->launches += 1;
+    MGLC_CUDA(cudaMemcpyAsync(host, S->stage, 9 * cells * sizeof(double), cudaMemcpyDeviceToHost, S->s));
+    MGLC_CUDA(cudaStreamSynchronize(S->s));
+    return MGLC_OK;
+}
+
+extern "C" int mglc_l2d_upload(mglc_l2d *h, int r, const double *f, const double *f_post, const double *rho, const double *u,
+                               const double *v) {
+    L2Sub *S;
+    MGLC_TRY(l2_sub(h, r, &S));
+    MGLC_TRY(l2_put_lattice(S, f, S->F, 0));
+    MGLC_TRY(l2_put_lattice(S, f_post, S->P[S->cur], 1));
+    const size_t fld = (size_t)S->n[0] * S->n[1] * sizeof(double);
+    if (rho) MGLC_CUDA(cudaMemcpyAsync(S->rho, rho, fld, cudaMemcpyHostToDevice, S->s));
+    if (u) MGLC_CUDA(cudaMemcpyAsync(S->u, u, fld, cudaMemcpyHostToDevice, S->s));
+    if (v) MGLC_CUDA(cudaMemcpyAsync(S->v, v, fld, cudaMemcpyHostToDevice, S->s));
+    MGLC_CUDA(cudaStreamSynchronize(S->s));
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_download(mglc_l2d *h, int r, double *f, double *f_post, double *rho, double *u, double *v) {
+    L2Sub *S;
+    MGLC_TRY(l2_sub(h, r, &S));
+    MGLC_TRY(l2_get_lattice(S, f, S->F, 0));
+    MGLC_TRY(l2_get_lattice(S, f_post, S->P[S->cur], 1));
+    const size_t fld = (size_t)S->n[0] * S->n[1] * sizeof(double);
+    if (rho) MGLC_CUDA(cudaMemcpyAsync(rho, S->rho, fld, cudaMemcpyDeviceToHost, S->s));
+    if (u) MGLC_CUDA(cudaMemcpyAsync(u, S->u, fld, cudaMemcpyDeviceToHost, S->s));
+    if (v) MGLC_CUDA(cudaMemcpyAsync(v, S->v, fld, cudaMemcpyDeviceToHost, S->s));
+    MGLC_CUDA(cudaStreamSynchronize(S->s));
+    MGLC_CUDA(cudaGetLastError());
+    return MGLC_OK;
+}
+
+extern "C" int mglc_l2d_initial(mglc_l2d *h) {
+    if (!h) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        k_l2_initial<<<l2_grid(S), 128, 0, S->s>>>(S->g, h->p, S->g.wall[2], S->F, S->rho, S->u, S->v, S->up, S->vp);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+
+static int l2_collision(mglc_l2d *h) {
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        S->launches += (h->d.arith == MGLC_ARITH_STRICT ? strict::launch_l2_collision : fast::launch_l2_collision)(
+            S->g, h->p, h->d.variant, S->F, S->rho, S->u, S->v, S->P[S->cur], S->s);
+    }
+    return MGLC_OK;
+}
+
+static int l2_pack(L2Sub *S, cudaStream_t s) {
+    for (int dir = 0; dir < 8; ++dir) {
+        Msg &M = S->msgs[dir];
+        if (!M.send_count) continue;
+        int n1, npop;
+        l2_msg_dims(S, dir, n1, npop);
+        k_l2_pack<<<(unsigned)((M.send_count + 127) / 128), 128, 0, s>>>(S->g, S->P[S->cur], dir, n1, npop, M.sbuf);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+static int l2_unpack(L2Sub *S, cudaStream_t s) {
+    for (int dir = 0; dir < 8; ++dir) {
+        Msg &M = S->msgs[dir];
+        if (!M.recv_count) continue;
+        int n1, npop;
+        l2_msg_dims(S, dir, n1, npop);
+        k_l2_unpack<<<(unsigned)((M.recv_count + 127) / 128), 128, 0, s>>>(S->g, S->P[S->cur], dir, n1, npop, M.rbuf);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+
+// message_passing_sendrecv(), ex_sendrecv.f90:9-78: 12 face + 4 corner Sendrecv become one grouped NCCL operation (or
+// device-to-device copies between the subdomains of one process)
+static int l2_exchange(mglc_l2d *h) {
+    if (h->nranks == 1) return MGLC_OK;
+    if (h->comm) {
+        L2Sub *S = h->subs[0];
+        MGLC_TRY(l2_use(S));
+        MGLC_TRY(l2_pack(S, S->s));
+        MGLC_TRY(halo_nccl_sendrecv(S->msgs, 8, h->comm, S->s));
+        MGLC_TRY(l2_unpack(S, S->s));
+        return MGLC_OK;
+    }
+    return halo_local_exchange(
+        h->ports, [&](int r, cudaStream_t s) { return l2_pack(h->subs[r], s); }, [&](int r, cudaStream_t s) { return l2_unpack(h->subs[r], s); });
+}
+
+extern "C" int mglc_l2d_collision(mglc_l2d *h) { if (!h) return MGLC_E_INVALID; return l2_collision(h); }
+extern "C" int mglc_l2d_exchange(mglc_l2d *h) { if (!h) return MGLC_E_INVALID; return l2_exchange(h); }
+extern "C" int mglc_l2d_streaming(mglc_l2d *h) {
+    if (!h) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        k_l2_streaming<<<l2_grid(S), 128, 0, S->s>>>(S->g, S->P[S->cur], S->F);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_bounceback(mglc_l2d *h) {
+    if (!h) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        const int cells = 2 * S->n[0] + 2 * std::max(S->n[1] - 2, 0);
+        k_l2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p, S->P[S->cur], S->rho, S->F);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_macro(mglc_l2d *h) {
+    if (!h) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        k_l2_macro<<<l2_grid(S), 128, 0, S->s>>>(S->g, S->F, S->rho, S->u, S->v);
+        S->launches += 1;
+    }
+    return MGLC_OK;
+}
+
+// nsteps loop bodies (main.f90:66-82 == c:57-63), rotated by half a step: collision() once, then nsteps-1 times
+// [exchange -> streaming+bounceback+macro+collision in one kernel], then exchange -> streaming+bounceback+macro.  f, f_post
+// (interior + exchanged halos), rho, u, v afterwards are the reference's after the same number of iterations.
+static int l2_step_impl(mglc_l2d *h, int nsteps) {
+    if (nsteps < 0) { set_error("mglc_l2d_step: nsteps=%d", nsteps); return MGLC_E_INVALID; }
+    if (nsteps == 0) return MGLC_OK;
+    const bool strict_build = h->d.arith == MGLC_ARITH_STRICT;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        if (S->g.wall[2]) { k_l2_lid_row<<<(S->n[0] + 127) / 128, 128, 0, S->s>>>(S->g, S->rho, S->lid[0]); S->launches += 1; }
+    }
+    MGLC_TRY(l2_collision(h));
+    int lid = 0;
+    for (int it = 1; it < nsteps; ++it) {
+        MGLC_TRY(l2_exchange(h));
+        for (L2Sub *S : h->subs) {
+            MGLC_TRY(l2_use(S));
+            S->launches += (strict_build ? strict::launch_l2_fused : fast::launch_l2_fused)(S->g, h->p, h->d.variant, S->P[S->cur], S->P[S->cur ^ 1],
+                                                                                            S->lid[lid], S->lid[lid ^ 1], S->s);
+            S->cur ^= 1;
+        }
+        lid ^= 1;
+    }
+    MGLC_TRY(l2_exchange(h));
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        S->launches += strict::launch_l2_stream_macro(S->g, h->p, S->P[S->cur], S->F, S->lid[lid], S->rho, S->u, S->v, S->s);
+    }
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_step(mglc_l2d *h, int nsteps) {
+    if (!h) return MGLC_E_INVALID;
+    MGLC_TRY(l2_step_impl(h, nsteps));
+    for (L2Sub *S : h->subs) { MGLC_TRY(l2_use(S)); MGLC_CUDA(cudaGetLastError()); }
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_step_timed(mglc_l2d *h, int nsteps, float *ms) {
+    if (!h || !ms) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) { MGLC_TRY(l2_use(S)); MGLC_CUDA(cudaStreamSynchronize(S->s)); }
+    for (L2Sub *S : h->subs) { MGLC_TRY(l2_use(S)); MGLC_CUDA(cudaEventRecord(S->ev_t0, S->s)); }
+    MGLC_TRY(l2_step_impl(h, nsteps));
+    for (L2Sub *S : h->subs) { MGLC_TRY(l2_use(S)); MGLC_CUDA(cudaEventRecord(S->ev_t1, S->s)); }
+    float worst = 0.f;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        MGLC_CUDA(cudaEventSynchronize(S->ev_t1));
+        MGLC_CUDA(cudaGetLastError());
+        float t = 0.f;
+        MGLC_CUDA(cudaEventElapsedTime(&t, S->ev_t0, S->ev_t1));
+        worst = std::max(worst, t);
+    }
+    *ms = worst;
+    return MGLC_OK;
+}
+
+// check(): evolution.f90:128-147 (rank sums + 2 MPI_Allreduce) == c:341-363
+extern "C" int mglc_l2d_check(mglc_l2d *h, double *errorU) {
+    if (!h || !errorU) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) {
+        MGLC_TRY(l2_use(S));
+        k_l2_check_partial<<<L2_CHECK_BLOCKS, 256, 0, S->s>>>((long long)S->n[0] * S->n[1], S->u, S->v, S->up, S->vp, S->scratch);
+        k_l2_check_final<<<1, 1, 0, S->s>>>(L2_CHECK_BLOCKS, S->scratch);
+        S->launches += 2;
+    }
+    double t1 = 0.0, t2 = 0.0;
+    for (L2Sub *S : h->subs) {           // rank order, like the Allreduce over emulated ranks in the oracle
+        MGLC_TRY(l2_use(S));
+        if (h->comm && h->nranks > 1) MGLC_NCCL(ncclAllReduce(S->scratch, S->scratch, 2, ncclDouble, ncclSum, h->comm->nccl, S->s));
+        double e[2];
+        MGLC_CUDA(cudaMemcpyAsync(e, S->scratch, sizeof e, cudaMemcpyDeviceToHost, S->s));
+        MGLC_CUDA(cudaStreamSynchronize(S->s));
+        MGLC_CUDA(cudaGetLastError());
+        t1 += e[0]; t2 += e[1];
+    }
+    *errorU = sqrt(t1) / sqrt(t2);
+    return MGLC_OK;
+}
+
+extern "C" int mglc_l2d_launch_count(mglc_l2d *h, long long *n) {
+    if (!h || !n) return MGLC_E_INVALID;
+    long long t = 0;
+    for (L2Sub *S : h->subs) t += S->launches;
+    *n = t;
+    return MGLC_OK;
+}
+extern "C" int mglc_l2d_sync(mglc_l2d *h) {
+    if (!h) return MGLC_E_INVALID;
+    for (L2Sub *S : h->subs) { MGLC_TRY(l2_use(S)); MGLC_CUDA(cudaStreamSynchronize(S->s)); MGLC_CUDA(cudaGetLastError()); }
+    return MGLC_OK;
+}
