@@ -33,6 +33,12 @@ module mglc_iso_c
         real(c_double) :: rho0, rhoSolid, viscosity, radius0, gravity
         real(c_double) :: thresholdWall, stiffWall, thresholdParticle, stiffParticle
     end type mglc_p2d_desc
+    !> mglc_l2d_desc: module commondata of the 2-D lid driver (Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/commondata.f90:4-9)
+    type, bind(C) :: mglc_l2d_desc
+        integer(c_int) :: total_nx, total_ny, variant, arith
+        real(c_double) :: reynolds, U0, rho0
+    end type mglc_l2d_desc
+    integer(c_int), parameter :: MGLC_L2D_C = 0, MGLC_L2D_F = 1
 
     interface
         ! ---- host-only helpers -------------------------------------------------------------------
@@ -320,6 +326,112 @@ module mglc_iso_c
         function mglc_p2d_destroy(h) bind(C, name="mglc_p2d_destroy") result(rc)
             import :: c_int, c_ptr
             type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- 2-D lid driver (Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/main.f90:66-82) ------------------------
+        function mglc_l2d_desc_init(d, variant) bind(C, name="mglc_l2d_desc_init") result(rc)
+            import :: c_int, mglc_l2d_desc
+            type(mglc_l2d_desc), intent(out) :: d
+            integer(c_int), value :: variant
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_create(h, d, dims_or_zero, nranks, rank, device, comm) bind(C, name="mglc_l2d_create") result(rc)
+            import :: c_int, c_ptr, mglc_l2d_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_l2d_desc), intent(in) :: d
+            integer(c_int), intent(in) :: dims_or_zero(2)
+            integer(c_int), value :: nranks, rank, device
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_info(h, r, dims, ln, start, coords, nbr) bind(C, name="mglc_l2d_info") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            integer(c_int), intent(out) :: dims(2), ln(2), start(2), coords(2), nbr(8)
+            integer(c_int) :: rc
+        end function
+        !> f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v(nx,ny) exactly as allocated at initial.f90:30-38
+        function mglc_l2d_upload(h, r, f, f_post, rho, u, v) bind(C, name="mglc_l2d_upload") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(in) :: f(*), f_post(*), rho(*), u(*), v(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_download(h, r, f, f_post, rho, u, v) bind(C, name="mglc_l2d_download") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(out) :: f(*), f_post(*), rho(*), u(*), v(*)
+            integer(c_int) :: rc
+        end function
+        !> nsteps x (collision, message_passing_sendrecv, streaming, bounceback, macro)
+        function mglc_l2d_step(h, nsteps) bind(C, name="mglc_l2d_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_check(h, errorU) bind(C, name="mglc_l2d_check") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_destroy(h) bind(C, name="mglc_l2d_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- in-loop diagnostics on the device and the drivers' on-disk formats ----------------------------------------
+        !> calNuRe(), Buoyancy_driven_cavity/fortran/3d/mpi_blocked/RaNu.F90:13-47
+        function mglc_calNuRe(h, prandtl, NuVolAvg, ReVolAvg) bind(C, name="mglc_calNuRe") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), value :: prandtl
+            real(c_double), intent(out) :: NuVolAvg, ReVolAvg
+            integer(c_int) :: rc
+        end function
+        !> one line of rho|u|v|w|T (field 0..4) along axis through the global 1-based (g1, g2), e.g. getVelocity(), L3/output.f90:334-344
+        function mglc_lbm_download_line(h, field, axis, g1, g2, out, first, count) bind(C, name="mglc_lbm_download_line") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: field, axis, g1, g2
+            real(c_double), intent(out) :: out(*)
+            integer(c_int), intent(out) :: first, count
+            integer(c_int) :: rc
+        end function
+        !> backupData(), Buoyancy_driven_cavity/fortran/3d/seq/bouyancy3d.F90:1011-1029 (path is a C string: trim(name)//c_null_char)
+        function mglc_backup_write(path, u, v, w, T, f, g, nx, ny, nz) bind(C, name="mglc_backup_write") result(rc)
+            import :: c_int, c_char, c_double
+            character(kind=c_char), intent(in) :: path(*)
+            real(c_double), intent(in) :: u(*), v(*), w(*), T(*), f(*), g(*)
+            integer(c_int), value :: nx, ny, nz
+            integer(c_int) :: rc
+        end function
+        !> initial() with loadInitField = 1, seq/bouyancy3d.F90:367-378
+        function mglc_backup_read(path, u, v, w, T, f, g, nx, ny, nz) bind(C, name="mglc_backup_read") result(rc)
+            import :: c_int, c_char, c_double
+            character(kind=c_char), intent(in) :: path(*)
+            real(c_double), intent(out) :: u(*), v(*), w(*), T(*), f(*), g(*)
+            integer(c_int), value :: nx, ny, nz
+            integer(c_int) :: rc
+        end function
+        !> output_Tecplot(), L3/output.f90:175-313
+        function mglc_output_tecplot_lid(path, xp, yp, zp, u, v, w, rho, nx, ny, nz) bind(C, name="mglc_output_tecplot_lid") result(rc)
+            import :: c_int, c_char, c_double
+            character(kind=c_char), intent(in) :: path(*)
+            real(c_double), intent(in) :: xp(*), yp(*), zp(*), u(*), v(*), w(*), rho(*)
+            integer(c_int), value :: nx, ny, nz
+            integer(c_int) :: rc
+        end function
+        !> output_binary(), L3/output.f90:350-367
+        function mglc_output_binary_lid(path, u, v, rho, nx, ny, nz) bind(C, name="mglc_output_binary_lid") result(rc)
+            import :: c_int, c_char, c_double
+            character(kind=c_char), intent(in) :: path(*)
+            real(c_double), intent(in) :: u(*), v(*), rho(*)
+            integer(c_int), value :: nx, ny, nz
             integer(c_int) :: rc
         end function
     end interface
