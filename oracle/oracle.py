@@ -681,3 +681,145 @@ class RefLid2D:
 
     def field_F(self, name):
         return np.asfortranarray(getattr(self, name))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D thermal D2Q9 + D2Q5 (oracle/thermal2d.c): B2 = MPI/Buoyancy_driven_cavity/fortran/2d/mpi_blocked/
+class T2Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("Rayleigh", "Prandtl", "Mach", "Thot", "Tcold", "Tref", "rho0", "lengthUnit", "tauf",
+                                          "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")]
+
+
+T2_FIELDS = {"f": 0, "f_post": 1, "g": 2, "g_post": 3, "rho": 4, "u": 5, "v": 6, "T": 7, "up": 8, "vp": 9, "Tp": 10, "Fx": 11, "Fy": 12}
+T2_ADIABATIC, T2_CONST_HOT, T2_CONST_COLD = 0, 1, 2
+T2_SIDE_HEATED = (T2_CONST_COLD, T2_CONST_HOT, T2_ADIABATIC, T2_ADIABATIC)      # +x, -x, +y, -y   macros.F90:24-27
+T2_RAYLEIGH_BENARD = (T2_ADIABATIC, T2_ADIABATIC, T2_CONST_COLD, T2_CONST_HOT)  # macros.F90:17-20
+
+
+def _t2_lib():
+    L = lib()
+    if not getattr(L, "_t2_ready", False):
+        L.t2_world_create.restype = C.c_void_p
+        L.t2_world_create.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _dp, _ip]
+        L.t2_world_destroy.argtypes = [C.c_void_p]
+        L.t2_world_info.argtypes = [C.c_void_p, _ip, C.POINTER(T2Params), _ip]
+        L.t2_rank_info.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.t2_rank_ptr.restype = _dp
+        L.t2_rank_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for fn in ("t2_initial", "t2_collision", "t2_exchange_f", "t2_streaming", "t2_bounceback", "t2_collisionT", "t2_exchange_g",
+                   "t2_streamingT", "t2_bouncebackT", "t2_macro", "t2_macroT"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+            getattr(L, fn).restype = None
+        L.t2_check.argtypes = [C.c_void_p, _dp, _dp]
+        L.t2_nure_sums.argtypes = [C.c_void_p, _dp]
+        L.t2_step.argtypes = [C.c_void_p, C.c_int]
+        L.t2_derive_params.argtypes = [C.POINTER(T2Params), C.c_int]
+        L.t2_collide_cell.argtypes = [C.POINTER(T2Params), _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.t2_collideT_cell.argtypes = [C.POINTER(T2Params), _dp, C.c_double, C.c_double, C.c_double, _dp]
+        L._t2_ready = True
+    return L
+
+
+def t2_params(total_ny=201, Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0):
+    """module.F90:29-33,67-81 evaluated by the oracle"""
+    p = T2Params(Rayleigh=Rayleigh, Prandtl=Prandtl, Mach=Mach, Thot=Thot, Tcold=Tcold, Tref=Tref, rho0=rho0)
+    _t2_lib().t2_derive_params(C.byref(p), total_ny)
+    return p
+
+
+class Thermal2DRank:
+    def __init__(self, world, r):
+        L = world._lib
+        info = (C.c_int * 14)()
+        L.t2_rank_info(world._h, r, info)
+        self.n, self.coords, self.start = tuple(info[0:2]), tuple(info[2:4]), tuple(info[4:6])
+        self.nbr, self.cnr = tuple(info[6:10]), tuple(info[10:14])
+        nx, ny = self.n
+        shapes = {"f": (9, nx, ny), "f_post": (9, nx + 2, ny + 2), "g": (5, nx, ny), "g_post": (5, nx + 2, ny + 2)}
+        for name, which in T2_FIELDS.items():
+            shape = shapes.get(name, (nx, ny))
+            p = L.t2_rank_ptr(world._h, r, which)
+            setattr(self, name, np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape, order="F"))
+
+
+class Thermal2DWorld:
+    """All P emulated ranks of the 2-D thermal driver in one process."""
+    LEAD = {"f": 9, "f_post": 9, "g": 5, "g_post": 5}
+
+    def __init__(self, total=(201, 201), nprocs=1, dims=None, bcT=None, **params):
+        self._lib = _t2_lib()
+        d = (C.c_int * 2)(*(dims if dims else (0, 0)))
+        pv = dict(Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0)
+        pv.update(params)
+        par = (C.c_double * 7)(*[pv[k] for k in ("Rayleigh", "Prandtl", "Mach", "Thot", "Tcold", "Tref", "rho0")])
+        bc = (C.c_int * 4)(*bcT) if bcT is not None else None
+        self._h = self._lib.t2_world_create(total[0], total[1], nprocs, d, par, bc)
+        self.total, self.nprocs = tuple(total), nprocs
+        self.ranks = [Thermal2DRank(self, r) for r in range(nprocs)]
+        dd, bb = (C.c_int * 2)(), (C.c_int * 4)()
+        self.params = T2Params()
+        self._lib.t2_world_info(self._h, dd, C.byref(self.params), bb)
+        self.dims, self.bcT = tuple(dd), tuple(bb)
+
+    def close(self):
+        if self._h:
+            self.ranks = []
+            self._lib.t2_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self):
+        eu, et = C.c_double(), C.c_double()
+        self._lib.t2_check(self._h, C.byref(eu), C.byref(et))
+        return eu.value, et.value
+
+    def nure_sums(self):
+        out = (C.c_double * 3)()
+        self._lib.t2_nure_sums(self._h, out)
+        return tuple(out)
+
+    def step(self, n=1):
+        self._lib.t2_step(self._h, n)
+
+    def gather(self, name):
+        lead = (self.LEAD[name],) if name in self.LEAD else ()
+        out = np.empty(lead + self.total, order="F")
+        for R in self.ranks:
+            a = getattr(R, name)
+            if name in ("f_post", "g_post"):
+                a = a[:, 1:-1, 1:-1]
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            out[(slice(None),) * len(lead) + sl] = a
+        return out
+
+    def scatter(self, name, glob):
+        lead = 1 if name in self.LEAD else 0
+        for R in self.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            getattr(R, name)[...] = glob[(slice(None),) * lead + sl]
+
+
+for _name, _sub in (("initial", "t2_initial"), ("collision", "t2_collision"), ("message_passing_f", "t2_exchange_f"),
+                    ("streaming", "t2_streaming"), ("bounceback", "t2_bounceback"), ("collisionT", "t2_collisionT"),
+                    ("message_passing_g", "t2_exchange_g"), ("streamingT", "t2_streamingT"), ("bouncebackT", "t2_bouncebackT"),
+                    ("macro", "t2_macro"), ("macroT", "t2_macroT")):
+    setattr(Thermal2DWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))
+
+
+def t2_collide_cell(p, f, rho, u, v, T):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    out, F2 = np.empty(9), np.empty(2)
+    _t2_lib().t2_collide_cell(C.byref(p), f.ctypes.data_as(_dp), rho, u, v, T, out.ctypes.data_as(_dp), F2.ctypes.data_as(_dp))
+    return out, F2
+
+
+def t2_collideT_cell(p, g, u, v, T):
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.empty(5)
+    _t2_lib().t2_collideT_cell(C.byref(p), g.ctypes.data_as(_dp), u, v, T, out.ctypes.data_as(_dp))
+    return out
