@@ -363,6 +363,57 @@ int mglc_l2d_step_timed(mglc_l2d *h, int nsteps, float *ms);
 int mglc_l2d_launch_count(mglc_l2d *h, long long *n);
 int mglc_l2d_sync(mglc_l2d *h);
 
+/* ================= 2-D thermal D2Q9 + D2Q5 driver =================
+ * B2 = MPI/Buoyancy_driven_cavity/fortran/2d/mpi_blocked/ : D2Q9 MRT flow with the Boussinesq force Fy = rho*gBeta*(T-Tref),
+ * D2Q5 MRT temperature; side-heated cell (macros.F90:24-27, shipped) or Rayleigh-Benard cell (macros.F90:17-20).
+ * Arrays cross the boundary in the Fortran program's layout: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), g(0:4,nx,ny),
+ * g_post(0:4,0:nx+1,0:ny+1), rho,u,v,T,Fx,Fy(nx,ny) (initial.F90:177-197).  Handles own one subdomain (mglc_t2d_create) or all
+ * P of them (mglc_t2d_create_local); `r` = index among those owned. */
+typedef struct mglc_t2d mglc_t2d;
+typedef struct mglc_t2d_desc {
+    int total_nx, total_ny;              /* module.F90:26                                    */
+    int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT              */
+    int bcT[4];                          /* +x (right), -x (left), +y (top), -y (bottom): MGLC_BCT_*   macros.F90:16-27 */
+    int reserved;
+    double Rayleigh, Prandtl, Mach;      /* module.F90:31-33                                 */
+    double Thot, Tcold, Tref, rho0;      /* module.F90:67-68                                 */
+} mglc_t2d_desc;
+int mglc_t2d_desc_init(mglc_t2d_desc *d);                               /* the shipped constants (201 x 201, Ra 1e7, side-heated) */
+/* MPI_Dims_create(np,2) + MPI_Cart_create + decompose_1d + MPI_Cart_shift + MPI_Cart_find_corners + allocate -- main.F90:21-43,
+ * initial.F90:177-197; tauf, viscosity, diffusivity, paraA, gBeta, Snu, Sq, Qd, Qnu -- module.F90:69-81; fails with
+ * MGLC_E_INVALID where the reference stops (paraA outside (-4,1), initial.F90:30) */
+int mglc_t2d_create(mglc_t2d **h, const mglc_t2d_desc *d, const int dims_or_zero[2], int nranks, int rank, int device,
+                    mglc_comm *comm_or_null);
+int mglc_t2d_create_local(mglc_t2d **h, const mglc_t2d_desc *d, const int dims_or_zero[2], int nranks, const int *devices_or_null);
+int mglc_t2d_destroy(mglc_t2d *h);
+int mglc_t2d_nlocal(mglc_t2d *h, int *n);
+/* nbr[0..3] = right(+x), left(-x), top(+y), bottom(-y); nbr[4..7] = where populations 5..8 go; -1 = MPI_PROC_NULL */
+int mglc_t2d_info(mglc_t2d *h, int r, int dims[2], int ln[2], int start[2], int coords[2], int nbr[8]);
+/* out = tauf, viscosity, diffusivity, paraA, gBeta, Snu, Sq, Qd, Qnu, lengthUnit */
+int mglc_t2d_params(mglc_t2d *h, double out[10]);
+/* fields = rho, u, v, T, Fx, Fy; NULL (array or entry) = keep / skip */
+int mglc_t2d_upload(mglc_t2d *h, int r, const double *f, const double *f_post, const double *g, const double *g_post,
+                    const double *const fields_or_null[6]);
+int mglc_t2d_download(mglc_t2d *h, int r, double *f, double *f_post, double *g, double *g_post, double *const fields_or_null[6]);
+int mglc_t2d_initial(mglc_t2d *h);      /* initial()            initial.F90:199-335        */
+int mglc_t2d_collision(mglc_t2d *h);    /* collision()          evolution_f.F90:1-84       */
+int mglc_t2d_exchange_f(mglc_t2d *h);   /* message_passing_f()  message_exchange.F90:1-79   */
+int mglc_t2d_streaming(mglc_t2d *h);    /* streaming()          evolution_f.F90:89-108     */
+int mglc_t2d_bounceback(mglc_t2d *h);   /* bounceback()         evolution_f.F90:113-324    */
+int mglc_t2d_collisionT(mglc_t2d *h);   /* collisionT()         evolution_g.F90:1-46       */
+int mglc_t2d_exchange_g(mglc_t2d *h);   /* message_passing_g()  message_exchange.F90:85-118 */
+int mglc_t2d_streamingT(mglc_t2d *h);   /* streamingT()         evolution_g.F90:49-68      */
+int mglc_t2d_bouncebackT(mglc_t2d *h);  /* bouncebackT()        evolution_g.F90:71-159     */
+int mglc_t2d_macro(mglc_t2d *h);        /* macro()              evolution_f.F90:328-342    */
+int mglc_t2d_macroT(mglc_t2d *h);       /* macroT()             evolution_g.F90:163-176    */
+int mglc_t2d_check(mglc_t2d *h, double *errorU, double *errorT);   /* check()   check.F90:1-51 */
+/* calNuRe()'s volume averages: out = angular momentum / N, NuVolAvg, ReVolAvg -- NuRe.F90:27-78 */
+int mglc_t2d_nure(mglc_t2d *h, double out[3]);
+int mglc_t2d_step(mglc_t2d *h, int nsteps);                        /* nsteps loop bodies  main.F90:84-108 */
+int mglc_t2d_step_timed(mglc_t2d *h, int nsteps, float *ms);
+int mglc_t2d_launch_count(mglc_t2d *h, long long *n);
+int mglc_t2d_sync(mglc_t2d *h);
+
 /* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
  * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /
  * the Python gather hand back.  Unformatted files use the gfortran record framing the reference's Makefiles produce:

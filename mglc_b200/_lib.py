@@ -50,6 +50,12 @@ class L2dDesc(C.Structure):
                 ("reynolds", C.c_double), ("U0", C.c_double), ("rho0", C.c_double)]
 
 
+class T2dDesc(C.Structure):
+    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("arith", C.c_int), ("bcT", C.c_int * 4), ("reserved", C.c_int),
+                ("Rayleigh", C.c_double), ("Prandtl", C.c_double), ("Mach", C.c_double), ("Thot", C.c_double), ("Tcold", C.c_double),
+                ("Tref", C.c_double), ("rho0", C.c_double)]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _vp = C.c_void_p
@@ -213,6 +219,32 @@ SIGNATURES = {
     "mglc_l2d_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
     "mglc_l2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_l2d_sync": (C.c_int, [_vp]),
+    "mglc_t2d_desc_init": (C.c_int, [C.POINTER(T2dDesc)]),
+    "mglc_t2d_create": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
+    "mglc_t2d_create_local": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, _ip]),
+    "mglc_t2d_destroy": (C.c_int, [_vp]),
+    "mglc_t2d_nlocal": (C.c_int, [_vp, _ip]),
+    "mglc_t2d_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "mglc_t2d_params": (C.c_int, [_vp, _dp]),
+    "mglc_t2d_upload": (C.c_int, [_vp, C.c_int] + [_vp] * 4 + [_vpp]),
+    "mglc_t2d_download": (C.c_int, [_vp, C.c_int] + [_vp] * 4 + [_vpp]),
+    "mglc_t2d_initial": (C.c_int, [_vp]),
+    "mglc_t2d_collision": (C.c_int, [_vp]),
+    "mglc_t2d_exchange_f": (C.c_int, [_vp]),
+    "mglc_t2d_streaming": (C.c_int, [_vp]),
+    "mglc_t2d_bounceback": (C.c_int, [_vp]),
+    "mglc_t2d_collisionT": (C.c_int, [_vp]),
+    "mglc_t2d_exchange_g": (C.c_int, [_vp]),
+    "mglc_t2d_streamingT": (C.c_int, [_vp]),
+    "mglc_t2d_bouncebackT": (C.c_int, [_vp]),
+    "mglc_t2d_macro": (C.c_int, [_vp]),
+    "mglc_t2d_macroT": (C.c_int, [_vp]),
+    "mglc_t2d_check": (C.c_int, [_vp, _dp, _dp]),
+    "mglc_t2d_nure": (C.c_int, [_vp, _dp]),
+    "mglc_t2d_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_t2d_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_t2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_t2d_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -1,0 +1,305 @@
+"""GPU parity tests of the 2-D thermal D2Q9 + D2Q5 path (libmglc.so through the C ABI) against the CPU oracle (oracle/thermal2d.c,
+pinned bit for bit to the reference's Fortran text by test_oracle_thermal2d.py) and against the committed evaluations of the
+reference's own source (tests/golden/ref_fortran_thermal2d.npz).
+Strict arithmetic: everything bit-exact.  Fast arithmetic: copy-type subroutines, macro()/macroT() and the stored force
+bit-exact, collision()/collisionT()/step() to the north-star tolerance (<= 1e-12 relative L2, <= 1e-10 max pointwise)."""
+import os
+
+import numpy as np
+import pytest
+
+import mglc_b200 as mg
+from mglc_b200.thermal2d import PARAM_NAMES, RAYLEIGH_BENARD, SIDE_HEATED
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "ref_fortran_thermal2d.npz"))
+REL_L2, MAX_ABS = 1e-12, 1e-10
+FIELDS = ("rho", "u", "v", "T")
+
+
+def close_enough(got, want, floor=0.0):
+    d = np.linalg.norm((got - want).ravel()) / max(np.linalg.norm(want.ravel()), floor, 1e-300)
+    return d <= REL_L2 and np.abs(got - want).max() <= MAX_ABS
+
+
+def seeded_state(total, seed):
+    """f, g = perturbed equilibria; rho/u/v/T independent of them: every moment non-trivial"""
+    rng = np.random.default_rng(seed)
+    wd = orc.Thermal2DWorld(total, 1)
+    wd.initial()
+    f = np.asfortranarray(wd.gather("f") * (1.0 + 0.05 * rng.uniform(-1, 1, (9,) + tuple(total))))
+    g = np.asfortranarray(0.2 * (0.5 + rng.uniform(-0.3, 0.3, (5,) + tuple(total))))
+    wd.close()
+    out = dict(f=f, g=g, rho=1.0 + 0.02 * rng.uniform(-1, 1, total), T=rng.uniform(-0.1, 1.1, total))
+    out["u"], out["v"] = (0.05 * rng.uniform(-1, 1, total) for _ in range(2))
+    out["Fx"], out["Fy"] = np.zeros(total), 1e-4 * rng.uniform(-1, 1, total)
+    return {k: np.asfortranarray(a) for k, a in out.items()}
+
+
+def pair(total, nprocs=1, dims=None, bcT=None, strict=True, seed=None, **params):
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=bcT, **params)
+    sim = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, bcT=bcT, strict=strict, **params)
+    assert sim.dims == wd.dims and sim.bcT == wd.bcT
+    for k in PARAM_NAMES:
+        assert sim.params[k] == getattr(wd.params, k), k
+    for r, R in enumerate(wd.ranks):
+        inf = sim.info[r]
+        assert inf["n"] == R.n and inf["start"] == R.start and inf["coords"] == R.coords and inf["nbr"] == R.nbr + R.cnr
+    if seed is None:
+        wd.initial(); sim.initial()
+    else:
+        for k, a in seeded_state(total, seed).items():
+            wd.scatter(k, a); sim.scatter(k, a)
+    return wd, sim
+
+
+def assert_rank_arrays_equal(wd, sim, names, interior_only_post=False):
+    for r, R in enumerate(wd.ranks):
+        for k in names:
+            got, want = sim.download(r, k), getattr(R, k)
+            if k in ("f_post", "g_post") and interior_only_post:
+                got, want = got[:, 1:-1, 1:-1], want[:, 1:-1, 1:-1]
+            assert np.array_equal(got, want), (k, r)
+
+
+def test_parameters_match_the_fortran_text():
+    sim = mg.BuoyancyDrivenCavity2D()
+    assert sim.total == (201, 201) and sim.bcT == SIDE_HEATED
+    assert tuple(sim.params[k] for k in PARAM_NAMES[:9]) == tuple(GOLD["params/201"])
+    sim.close()
+    sim = mg.BuoyancyDrivenCavity2D((64, 64), Rayleigh=1e6)
+    assert tuple(sim.params[k] for k in PARAM_NAMES[:9]) == tuple(GOLD["params/64_ra1e6"])
+    sim.close()
+
+
+@pytest.mark.parametrize("total,bcT", [((201, 201), SIDE_HEATED), ((37, 5), RAYLEIGH_BENARD), ((130, 2), SIDE_HEATED), ((2, 9), (0, 0, 0, 0))])
+def test_initial_bit_exact(total, bcT):
+    for nprocs in (1, 2, 4):
+        if min(total) < 4 and nprocs == 4:
+            continue
+        wd, sim = pair(total, nprocs, bcT=bcT, Thot=0.75, Tcold=-0.25)
+        assert_rank_arrays_equal(wd, sim, ("f", "g", "f_post", "g_post") + FIELDS)
+        wd.close(); sim.close()
+
+
+def test_collisions_on_the_golden_cells_of_the_reference():
+    """the 48 seeded cells whose f_post, g_post, Fx, Fy the reference's own source text produced"""
+    f, g, r = GOLD["cells/f"], GOLD["cells/g"], GOLD["cells/ruvT"]
+    n, nx, ny = len(f), 67, 201                                   # total_ny = 201: the shipped tauf, paraA, gBeta
+    pad = np.arange(nx * ny) % n
+    shp = lambda a: np.asfortranarray(a[pad].reshape(nx, ny, order="F"))
+    for strict in (True, False):
+        sim = mg.BuoyancyDrivenCavity2D((nx, ny), strict=strict)
+        sim.upload(0, f=np.asfortranarray(f[pad].T.reshape(9, nx, ny, order="F")), g=np.asfortranarray(g[pad].T.reshape(5, nx, ny, order="F")),
+                   rho=shp(r[:, 0]), u=shp(r[:, 1]), v=shp(r[:, 2]), T=shp(r[:, 3]))
+        sim.collision(); sim.collisionT()
+        fp = sim.download(0, "f_post")[:, 1:-1, 1:-1].reshape(9, -1, order="F").T
+        gp = sim.download(0, "g_post")[:, 1:-1, 1:-1].reshape(5, -1, order="F").T
+        Fx, Fy = (sim.download(0, k).ravel(order="F") for k in ("Fx", "Fy"))
+        assert np.array_equal(Fx, GOLD["collision/FxFy"][pad, 0]) and np.array_equal(Fy, GOLD["collision/FxFy"][pad, 1])
+        if strict:
+            assert np.array_equal(fp, GOLD["collision/f_post"][pad]) and np.array_equal(gp, GOLD["collisionT/g_post"][pad])
+        else:
+            assert close_enough(fp, GOLD["collision/f_post"][pad]) and close_enough(gp, GOLD["collisionT/g_post"][pad])
+        # macro() / macroT() on the same cells with the golden forces: bit-exact in both builds, including signed zeros
+        F2 = GOLD["cells/FxFy"]
+        sim.upload(0, Fx=shp(F2[:, 0]), Fy=shp(F2[:, 1]))
+        sim.macro(); sim.macroT()
+        got = np.stack([sim.download(0, k).ravel(order="F") for k in ("rho", "u", "v")], axis=1)
+        assert np.array_equal(got, GOLD["macro/ruv"][pad]) and np.array_equal(np.signbit(got), np.signbit(GOLD["macro/ruv"][pad]))
+        assert np.array_equal(sim.download(0, "T").ravel(order="F"), GOLD["macro/T"][pad])
+        sim.close()
+
+
+def test_copy_subroutines_on_the_golden_block_of_the_reference():
+    """streaming / bounceback / streamingT / bouncebackT on the 6 x 5 block the reference's source text was evaluated on"""
+    nx, ny = 6, 5
+    for case in range(5):
+        c = GOLD["field/bb_cases"][case]
+        coords, dims = tuple(int(x) for x in c[:2]), tuple(int(x) for x in c[2:])
+        r = coords[0] * dims[1] + coords[1]
+        for tag, bcT in (("side", SIDE_HEATED), ("rb", RAYLEIGH_BENARD)):
+            sim = mg.BuoyancyDrivenCavity2D((nx * dims[0], ny * dims[1]), nprocs=dims[0] * dims[1], dims=dims, bcT=bcT, strict=True)
+            assert sim.info[r]["n"] == (nx, ny) and sim.info[r]["coords"] == coords
+            sim.upload(r, f_post=GOLD["field/f_post"], g_post=GOLD["field/g_post"])
+            if case == 0:
+                sim.streaming(); sim.streamingT()
+                assert np.array_equal(sim.download(r, "f"), GOLD["field/streaming_f"])
+                assert np.array_equal(sim.download(r, "g"), GOLD["field/streamingT_g"])
+            sim.upload(r, f=GOLD["field/f0"], g=GOLD["field/g0"])
+            sim.bounceback(); sim.bouncebackT()
+            assert np.array_equal(sim.download(r, "f"), GOLD[f"field/bounceback_{case}"]), (case, tag)
+            assert np.array_equal(sim.download(r, "g"), GOLD[f"field/bouncebackT_{tag}_{case}"]), (case, tag)
+            sim.close()
+
+
+@pytest.mark.parametrize("bcT", [SIDE_HEATED, RAYLEIGH_BENARD, (2, 1, 1, 2)])
+@pytest.mark.parametrize("total,nprocs,dims", [((34, 33), 1, None), ((34, 33), 4, None), ((23, 19), 6, None), ((40, 7), 3, (3, 1)), ((9, 31), 3, (1, 3))])
+def test_each_subroutine_bit_exact_strict(bcT, total, nprocs, dims):
+    wd, sim = pair(total, nprocs, dims, bcT=bcT, strict=True, seed=3, Rayleigh=1e6)
+    for R in wd.ranks:                                 # make never-written halo entries recognisable
+        R.f_post[...] = -7.25; R.g_post[...] = 3.5
+    for r in range(nprocs):
+        sim.upload(r, f_post=wd.ranks[r].f_post, g_post=wd.ranks[r].g_post)
+    for it in range(3):
+        wd.collision(); sim.collision()
+        assert_rank_arrays_equal(wd, sim, ("f_post", "Fx", "Fy"))
+        wd.message_passing_f(); sim.message_passing_f()
+        assert_rank_arrays_equal(wd, sim, ("f_post", "g_post"))
+        wd.streaming(); sim.streaming()
+        assert_rank_arrays_equal(wd, sim, ("f",))
+        wd.bounceback(); sim.bounceback()
+        assert_rank_arrays_equal(wd, sim, ("f",))
+        wd.collisionT(); sim.collisionT()
+        assert_rank_arrays_equal(wd, sim, ("g_post",))
+        wd.message_passing_g(); sim.message_passing_g()
+        assert_rank_arrays_equal(wd, sim, ("g_post", "f_post"))
+        wd.streamingT(); sim.streamingT()
+        assert_rank_arrays_equal(wd, sim, ("g",))
+        wd.bouncebackT(); sim.bouncebackT()
+        assert_rank_arrays_equal(wd, sim, ("g",))
+        wd.macro(); sim.macro(); wd.macroT(); sim.macroT()
+        assert_rank_arrays_equal(wd, sim, FIELDS)
+    for _ in range(2):                                  # the second call checks that up, vp, Tp were refreshed identically
+        a, b = sim.check(), wd.check()
+        assert np.isclose(a[0], b[0], rtol=1e-13, atol=0) and np.isclose(a[1], b[1], rtol=1e-13, atol=0)
+    assert np.allclose(sim.calNuRe()[1:], nure_of(wd)[1:], rtol=1e-12, atol=0)
+    assert abs(sim.calNuRe()[0] - nure_of(wd)[0]) < 1e-12
+    wd.close(); sim.close()
+
+
+def nure_of(wd):
+    """calNuRe()'s averages from the oracle's sums, NuRe.F90:31,41,62"""
+    a, b, c = wd.nure_sums()
+    N = float(wd.total[0] * wd.total[1])
+    p = wd.params
+    return a / N, b / N * p.lengthUnit / p.diffusivity + 1.0, np.sqrt(c / N) * p.lengthUnit / p.viscosity
+
+
+@pytest.mark.parametrize("total,nprocs", [((34, 33), 1), ((34, 33), 4)])
+def test_copy_type_subroutines_bit_exact_on_random_lattices(total, nprocs):
+    """exchange / streaming / bounceback move doubles: `==` on every value, random f_post and g_post including the halos"""
+    wd, sim = pair(total, nprocs, strict=False, seed=4)
+    rng = np.random.default_rng(7)
+    for r, R in enumerate(wd.ranks):
+        R.f_post[...] = rng.random(R.f_post.shape); R.g_post[...] = rng.random(R.g_post.shape)
+        sim.upload(r, f_post=R.f_post, g_post=R.g_post)
+    wd.message_passing_f(); sim.message_passing_f(); wd.message_passing_g(); sim.message_passing_g()
+    assert_rank_arrays_equal(wd, sim, ("f_post", "g_post"))
+    wd.streaming(); sim.streaming(); wd.streamingT(); sim.streamingT()
+    assert_rank_arrays_equal(wd, sim, ("f", "g"))
+    wd.bounceback(); sim.bounceback(); wd.bouncebackT(); sim.bouncebackT()
+    assert_rank_arrays_equal(wd, sim, ("f", "g"))
+    wd.macro(); sim.macro(); wd.macroT(); sim.macroT()
+    assert_rank_arrays_equal(wd, sim, FIELDS)
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("bcT", [SIDE_HEATED, RAYLEIGH_BENARD])
+@pytest.mark.parametrize("total,nprocs,dims", [((34, 33), 1, None), ((23, 19), 4, None), ((23, 19), 6, None), ((130, 6), 2, None), ((9, 31), 3, (1, 3))])
+def test_fused_step_strict_is_bit_exact(bcT, total, nprocs, dims):
+    """step(N) = the rotated loop (2 collisions, N-1 fused launches, stream+macro): every array the reference holds afterwards"""
+    wd, sim = pair(total, nprocs, dims, bcT=bcT, strict=True, Rayleigh=1e6)
+    for n in (1, 2, 17):
+        wd.step(n); sim.step(n)
+        assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+        assert_rank_arrays_equal(wd, sim, ("f_post", "g_post"), interior_only_post=True)
+    # the exchanged halo entries too (wall halos are never written by either side: zero in both)
+    assert_rank_arrays_equal(wd, sim, ("f_post", "g_post"))
+    # calls compose with the per-subroutine entry points
+    wd.collision(); sim.collision(); wd.message_passing_f(); sim.message_passing_f()
+    wd.streaming(); sim.streaming(); wd.bounceback(); sim.bounceback()
+    wd.collisionT(); sim.collisionT(); wd.message_passing_g(); sim.message_passing_g()
+    wd.streamingT(); sim.streamingT(); wd.bouncebackT(); sim.bouncebackT()
+    wd.macro(); sim.macro(); wd.macroT(); sim.macroT()
+    wd.step(3); sim.step(3)
+    assert_rank_arrays_equal(wd, sim, ("f", "g", "f_post", "g_post", "Fx", "Fy") + FIELDS)
+    wd.close(); sim.close()
+
+
+def test_wall_halos_are_never_read_by_the_fused_step():
+    wd, sim = pair((31, 17), 4, strict=True)
+    for r in range(4):
+        sim.upload(r, f_post=np.full(sim._shape(r, "f_post"), np.nan), g_post=np.full(sim._shape(r, "g_post"), np.nan))
+    wd.step(20); sim.step(20)
+    assert_rank_arrays_equal(wd, sim, ("f", "g") + FIELDS)
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("bcT,Ra", [(SIDE_HEATED, 1e7), (RAYLEIGH_BENARD, 1e6)])
+def test_shipped_case_fast_within_tolerance(bcT, Ra):
+    """the shipped 201 x 201 grid (Ra = 1e7 side-heated; the Rayleigh-Benard macro set), N in {1, 10, 100, 2000}, fast arithmetic"""
+    wd, sim = pair((201, 201), 1, bcT=bcT, strict=False, Rayleigh=Ra)
+    done = 0
+    for n in (1, 10, 100, 2000):
+        wd.step(n - done); sim.step(n - done); done = n
+        vel = max(np.linalg.norm(wd.gather("u")), np.linalg.norm(wd.gather("v")))
+        for k in FIELDS:
+            # u and v start from rest: measure them against the velocity scale of the flow, not against a near-zero field
+            assert close_enough(sim.gather(k), wd.gather(k), floor=vel if k in ("u", "v") else 0.0), (n, k)
+    a, b = sim.check(), wd.check()
+    assert np.isclose(a[0], b[0], rtol=1e-9) and np.isclose(a[1], b[1], rtol=1e-9)
+    assert np.allclose(sim.calNuRe()[1:], nure_of(wd)[1:], rtol=1e-9)
+    wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (4, None), (6, None), (3, (1, 3)), (4, (4, 1)), (9, None)])
+def test_decomposed_equals_single_subdomain_bit_for_bit(strict, nprocs, dims):
+    """the reference's seq == MPI contract on the device, in both arithmetic builds"""
+    total = (67, 45)
+    one = mg.BuoyancyDrivenCavity2D(total, strict=strict, Rayleigh=1e6)
+    many = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, strict=strict, Rayleigh=1e6)
+    one.initial(); many.initial()
+    one.step(40); many.step(40)
+    for k in ("f", "g", "Fy") + FIELDS:
+        assert np.array_equal(one.gather(k), many.gather(k)), k
+    a, b = one.check(), many.check()
+    assert np.isclose(a[0], b[0], rtol=1e-12) and np.isclose(a[1], b[1], rtol=1e-12)
+    one.close(); many.close()
+
+
+def test_large_lattice_properties():
+    """4096 x 4096 (no oracle run).  Side-heated: total mass constant to rounding, T bounded, four subdomains == one bit for bit.
+    Rayleigh-Benard set: the initial state does not depend on x, so for N steps every column farther than N cells from the side
+    walls runs the same arithmetic on the same inputs (causality): those columns are bit-identical."""
+    total, n = (4096, 4096), 12
+    one = mg.BuoyancyDrivenCavity2D(total, strict=False)
+    many = mg.BuoyancyDrivenCavity2D(total, nprocs=4, strict=False)
+    one.initial(); many.initial()
+    m0 = one.gather("rho").sum()
+    one.step(n); many.step(n)
+    rho, u, v, T = (one.gather(k) for k in FIELDS)
+    assert abs(rho.sum() - m0) / m0 < 1e-13
+    assert np.abs(v).max() > 0.0 and T.min() > -0.01 and T.max() < 1.01
+    for k, a in zip(FIELDS, (rho, u, v, T)):
+        assert np.array_equal(many.gather(k), a), k
+    one.close(); many.close()
+    rb = mg.BuoyancyDrivenCavity2D(total, bcT=RAYLEIGH_BENARD, strict=False)
+    rb.initial()
+    rb.step(n)
+    for k in FIELDS:
+        a = rb.gather(k)
+        mid = a[n + 1:-n - 1, :]
+        assert np.all(mid == mid[0:1, :]), k
+    assert np.abs(rb.gather("v")).max() > 0.0
+    rb.close()
+
+
+def test_error_behaviour():
+    with pytest.raises(mg.MglcError):
+        mg.BuoyancyDrivenCavity2D((8, 8), nprocs=3, dims=(2, 2))
+    with pytest.raises(mg.MglcError):
+        mg.BuoyancyDrivenCavity2D((2, 8), nprocs=4, dims=(4, 1))
+    with pytest.raises(mg.MglcError):
+        mg.BuoyancyDrivenCavity2D((8, 8), bcT=(0, 0, 0, 7))
+    with pytest.raises(mg.MglcError):                       # the reference stops when paraA leaves (-4, 1): initial.F90:30
+        mg.BuoyancyDrivenCavity2D((4001, 4001), Rayleigh=1e3, Mach=0.3)
+    sim = mg.BuoyancyDrivenCavity2D((8, 8))
+    with pytest.raises(mg.MglcError):
+        sim.step(-1)
+    with pytest.raises(ValueError):
+        sim.upload(0, rho=np.zeros((3, 3)))
+    sim.close()
