@@ -228,3 +228,59 @@ def lid2d(args, rank, local_rank, world):
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 144,
                      "cells_per_launch": cells, "note": "whole step(K) call timed: collision + (K-1) fused + stream/macro launches"},
         "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+
+
+def thermal2d(args, rank, local_rank, world):
+    """bench.py --workload thermal2d: the reference's 2-D thermal D2Q9 + D2Q5 driver (Buoyancy_driven_cavity/fortran/2d, SURVEY 8f
+    row 4) on one GPU, lattice far larger than L2 (default 8192 x 8192).  Roofline: 240 B/cell = (9 + 5) loads + (9 + 5) stores of
+    fp64 + the carried force Fy (8 B in, 8 B out) per fused launch.  cpu_baseline: oracle/thermal2d.c on all host threads."""
+    import torch
+
+    import bench as B
+    import mglc_b200 as mg
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "MLUPS", "value": None, "note": "thermal2d bench runs on one GPU"}))
+        return
+    torch.cuda.set_device(local_rank)
+    n = args.size or 8192
+    sim = mg.BuoyancyDrivenCavity2D((n, n), strict=args.arith == "strict", device=local_rank)
+    sim.initial()
+    sim.step(max(args.warmup, 3)); sim.sync()
+    l0 = sim.launch_count()
+    sampler = B.ClockSampler(local_rank); sampler.start()
+    ms = sim.step_timed(args.steps)
+    clocks = sampler.stop()
+    launches = sim.launch_count() - l0
+    eu, et = sim.check()
+    nure = sim.calNuRe()
+    sim.close()
+    cells = n * n
+    peak, peak_src = B.hbm_peak()
+    # a step(K) call is 2 collision launches + (K-1) fused launches + stream/macro; report the whole call against 240 B/cell
+    achieved = 240.0 * cells * args.steps / (ms * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        threads = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+        wd = orc.Thermal2DWorld((2048, 2048), 1)
+        wd.initial(); wd.step(1)
+        t0 = time.perf_counter(); wd.step(2); t1 = (time.perf_counter() - t0) / 2
+        k = max(2, min(200, int(args.cpu_seconds / max(t1, 1e-3))))
+        t0 = time.perf_counter(); wd.step(k); dt = time.perf_counter() - t0
+        wd.close()
+        cpu = {"value": round(2048 * 2048 * k / dt / 1e6, 2), "unit": "MLUPS", "cores": threads, "kind": "port",
+               "sample": f"2048x2048, {k} steps ({dt:.1f} s), oracle/thermal2d.c (-O2, OpenMP over rows, no FMA contraction)"}
+    print(json.dumps({
+        "metric": "MLUPS", "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"buoyancy_driven_cavity_d2q9_d2q5_mrt_{n}x{n}", "Ra": 1e7, "Pr": 0.71, "Ma": 0.1, "bc": "side-heated",
+                   "arith": args.arith, "errorU": eu, "errorT": et, "NuVolAvg": nure[1], "ReVolAvg": nure[2],
+                   "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (14 * cells * 8 / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": f"mglc::{args.arith}::k_t2_fused", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 240,
+                     "cells_per_launch": cells, "note": "whole step(K) call timed: 2 collision + (K-1) fused + stream/macro launches"},
+        "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)

@@ -39,6 +39,12 @@ module mglc_iso_c
         real(c_double) :: reynolds, U0, rho0
     end type mglc_l2d_desc
     integer(c_int), parameter :: MGLC_L2D_C = 0, MGLC_L2D_F = 1
+    !> mglc_t2d_desc: module commondata of the 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/module.F90:26-33,67-68)
+    !> and the boundary macro set of macros.F90:16-27 (bcT = +x, -x, +y, -y)
+    type, bind(C) :: mglc_t2d_desc
+        integer(c_int) :: total_nx, total_ny, arith, bcT(4), reserved
+        real(c_double) :: Rayleigh, Prandtl, Mach, Thot, Tcold, Tref, rho0
+    end type mglc_t2d_desc
 
     interface
         ! ---- host-only helpers -------------------------------------------------------------------
@@ -380,6 +386,72 @@ module mglc_iso_c
             integer(c_int) :: rc
         end function
         function mglc_l2d_destroy(h) bind(C, name="mglc_l2d_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/main.F90:84-108) ---------------------------
+        function mglc_t2d_desc_init(d) bind(C, name="mglc_t2d_desc_init") result(rc)
+            import :: c_int, mglc_t2d_desc
+            type(mglc_t2d_desc), intent(out) :: d
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_create(h, d, dims_or_zero, nranks, rank, device, comm) bind(C, name="mglc_t2d_create") result(rc)
+            import :: c_int, c_ptr, mglc_t2d_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_t2d_desc), intent(in) :: d
+            integer(c_int), intent(in) :: dims_or_zero(2)
+            integer(c_int), value :: nranks, rank, device
+            type(c_ptr), value :: comm
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_info(h, r, dims, ln, start, coords, nbr) bind(C, name="mglc_t2d_info") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            integer(c_int), intent(out) :: dims(2), ln(2), start(2), coords(2), nbr(8)
+            integer(c_int) :: rc
+        end function
+        !> f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), g(0:4,nx,ny), g_post(0:4,0:nx+1,0:ny+1) as allocated at initial.F90:191-194;
+        !> fields = c_loc of rho, u, v, T, Fx, Fy (nx,ny) in that order, c_null_ptr = keep
+        function mglc_t2d_upload(h, r, f, f_post, g, g_post, fields) bind(C, name="mglc_t2d_upload") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(in) :: f(*), f_post(*), g(*), g_post(*)
+            type(c_ptr), intent(in) :: fields(6)
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_download(h, r, f, f_post, g, g_post, fields) bind(C, name="mglc_t2d_download") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: r
+            real(c_double), intent(out) :: f(*), f_post(*), g(*), g_post(*)
+            type(c_ptr), intent(in) :: fields(6)
+            integer(c_int) :: rc
+        end function
+        !> nsteps x (collision, message_passing_f, streaming, bounceback, collisionT, message_passing_g, streamingT, bouncebackT, macro, macroT)
+        function mglc_t2d_step(h, nsteps) bind(C, name="mglc_t2d_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        !> check(), check.F90:1-51
+        function mglc_t2d_check(h, errorU, errorT) bind(C, name="mglc_t2d_check") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU, errorT
+            integer(c_int) :: rc
+        end function
+        !> calNuRe()'s volume averages (angular momentum / N, NuVolAvg, ReVolAvg), NuRe.F90:27-78
+        function mglc_t2d_nure(h, out3) bind(C, name="mglc_t2d_nure") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: out3(3)
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_destroy(h) bind(C, name="mglc_t2d_destroy") result(rc)
             import :: c_int, c_ptr
             type(c_ptr), value :: h
             integer(c_int) :: rc

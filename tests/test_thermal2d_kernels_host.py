@@ -20,9 +20,9 @@ dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 @pytest.fixture(scope="module")
 def shim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("shim") / "t2d_host.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I/usr/local/cuda/include", "-o", out,
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include", "-o", out,
                            os.path.join(ROOT, "tests", "host_shim", "t2d_host.cpp")])
-    S = C.CDLL(out)
+    S = C.CDLL(out)       # -Bsymbolic: libmglc.so (RTLD_GLOBAL) exports host stubs with the kernels' names; bind to the shim's own
     S.shim_t2d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, dp, dp, ip, dp, dp, dp, dp, dp, dp]
     return S
 
