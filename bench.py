@@ -47,7 +47,7 @@ def parse_args():
                    help="multi-GPU halo transport of the fused step: direct = stores into the neighbours' halos over NVLink "
                         "(CUDA IPC), overlap = NCCL exchange beside the interior update, blocking = NCCL exchange, then update; "
                         "auto = direct when the mappings came up, else overlap")
-    p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi", "particles", "lid2d", "thermal2d"],
+    p.add_argument("--workload", default="lid", choices=["lid", "thermal", "jacobi", "particles", "lid2d", "thermal2d", "lid_aa"],
                    help="lid = BASELINE.json's metric (default); thermal / jacobi = the other configs, for profiles/")
     p.add_argument("--size", type=int, default=0, help="per-GPU block edge (weak) / global edge (strong); 0 = the workload's config size")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -216,7 +216,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     thermal = args.workload == "thermal"
     if args.size == 0:
-        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0, "lid2d": 8192, "thermal2d": 8192}[args.workload]
+        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0, "lid2d": 8192, "thermal2d": 8192, "lid_aa": 896}[args.workload]
     if args.workload == "jacobi":
         import bench_jacobi
         bench_jacobi.main(args, rank, local_rank, world)
@@ -232,6 +232,10 @@ def main():
     if args.workload == "thermal2d":
         import bench_jacobi
         bench_jacobi.thermal2d(args, rank, local_rank, world)
+        return
+    if args.workload == "lid_aa":
+        import bench_jacobi
+        bench_jacobi.lid_aa(args, rank, local_rank, world)
         return
     if args.impl == "reference":
         if thermal:

@@ -39,6 +39,11 @@ module mglc_iso_c
         real(c_double) :: reynolds, U0, rho0
     end type mglc_l2d_desc
     integer(c_int), parameter :: MGLC_L2D_C = 0, MGLC_L2D_F = 1
+    !> mglc_aa_desc: the lid driver's constants (L3/commondata.f90:4-9) for the single-lattice (AA-pattern) path
+    type, bind(C) :: mglc_aa_desc
+        integer(c_int) :: n(3), arith, collision, device
+        real(c_double) :: tau, U0, rho0
+    end type mglc_aa_desc
     !> mglc_t2d_desc: module commondata of the 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/module.F90:26-33,67-68)
     !> and the boundary macro set of macros.F90:16-27 (bcT = +x, -x, +y, -y)
     type, bind(C) :: mglc_t2d_desc
@@ -386,6 +391,56 @@ module mglc_iso_c
             integer(c_int) :: rc
         end function
         function mglc_l2d_destroy(h) bind(C, name="mglc_l2d_destroy") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- lid driver on ONE lattice (AA-pattern storage): L3/main.f90:89-97 for the largest single-GPU lattices -----------
+        function mglc_aa_desc_init(d, nx, ny, nz, reynolds, U0, rho0) bind(C, name="mglc_aa_desc_init") result(rc)
+            import :: c_int, c_double, mglc_aa_desc
+            type(mglc_aa_desc), intent(out) :: d
+            integer(c_int), value :: nx, ny, nz
+            real(c_double), value :: reynolds, U0, rho0
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_create(h, d) bind(C, name="mglc_aa_create") result(rc)
+            import :: c_int, c_ptr, mglc_aa_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_aa_desc), intent(in) :: d
+            integer(c_int) :: rc
+        end function
+        !> f(0:18,nx,ny,nz), rho,u,v,w(nx,ny,nz) as allocated at L3/initial.f90:35-44
+        function mglc_aa_upload(h, f, rho, u, v, w) bind(C, name="mglc_aa_upload") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(in) :: f(*), rho(*), u(*), v(*), w(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_step(h, nsteps) bind(C, name="mglc_aa_step") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_check(h, errorU) bind(C, name="mglc_aa_check") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: errorU
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_download_macro(h, rho, u, v, w) bind(C, name="mglc_aa_download_macro") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: rho(*), u(*), v(*), w(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_download_f(h, f) bind(C, name="mglc_aa_download_f") result(rc)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: h
+            real(c_double), intent(out) :: f(*)
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_destroy(h) bind(C, name="mglc_aa_destroy") result(rc)
             import :: c_int, c_ptr
             type(c_ptr), value :: h
             integer(c_int) :: rc

@@ -414,6 +414,35 @@ int mglc_t2d_step_timed(mglc_t2d *h, int nsteps, float *ms);
 int mglc_t2d_launch_count(mglc_t2d *h, long long *n);
 int mglc_t2d_sync(mglc_t2d *h);
 
+/* ================= D3Q19 lid-driven cavity on ONE lattice: AA-pattern storage =================
+ * The loop body of L3/main.f90:89-97 with the arithmetic of mglc_lbm_step (bit-identical to it in MGLC_ARITH_STRICT), updated in
+ * place: 19 x 8 B of lattice per cell instead of 2 x 19 x 8 B, for the largest lattice one GPU can hold (about 1.4x the cells).
+ * One subdomain (all six faces are walls of the global box); the decomposed runs use mglc_lbm_* / mglc_group_*.  The lattice
+ * is only meaningful through these calls (between two streaming steps its populations sit in the opposite slots), so there are
+ * no per-subroutine entry points: f and the fields are uploaded, stepped, checked and downloaded. */
+typedef struct mglc_aa mglc_aa;
+typedef struct mglc_aa_desc {
+    int n[3];                            /* nx, ny, nz                                        L3/commondata.f90:4 */
+    int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT                                  */
+    int collision;                       /* MGLC_MRT_LID | MGLC_BGK                           L3/collision.f90   */
+    int device;
+    double tau, U0, rho0;                /* tauf = U0*total_nx/Re*3 + 0.5                     L3/commondata.f90:6-9 */
+} mglc_aa_desc;
+int mglc_aa_desc_init(mglc_aa_desc *d, int nx, int ny, int nz, double reynolds, double U0, double rho0);
+int mglc_aa_create(mglc_aa **h, const mglc_aa_desc *d);
+int mglc_aa_destroy(mglc_aa *h);
+int mglc_aa_initial(mglc_aa *h);                                        /* initial()   L3/initial.f90:55-73 */
+/* f(0:18,nx,ny,nz), rho,u,v,w(nx,ny,nz); NULL = keep */
+int mglc_aa_upload(mglc_aa *h, const double *f, const double *rho, const double *u, const double *v, const double *w);
+int mglc_aa_step(mglc_aa *h, int nsteps);                               /* nsteps loop bodies  L3/main.f90:89-97 */
+int mglc_aa_step_timed(mglc_aa *h, int nsteps, float *ms);
+int mglc_aa_check(mglc_aa *h, double *errorU);                          /* check()     L3/check.f90:12-34 */
+int mglc_aa_download_macro(mglc_aa *h, double *rho, double *u, double *v, double *w);
+int mglc_aa_download_f(mglc_aa *h, double *f);                          /* f as the reference holds it after the last loop body */
+int mglc_aa_device_bytes(mglc_aa *h, long long *bytes);
+int mglc_aa_launch_count(mglc_aa *h, long long *n);
+int mglc_aa_sync(mglc_aa *h);
+
 /* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
  * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /
  * the Python gather hand back.  Unformatted files use the gfortran record framing the reference's Makefiles produce:

@@ -8,6 +8,7 @@ reference driver's interface; it has no CPU or PyTorch fallback and raises if th
 from . import _lib, formats
 from ._lib import MglcError, lib
 from .jacobi import Jacobi, dims_create_nd
+from .lbm_aa import LidDrivenCavityAA
 from .lid2d import LidDrivenCavity2D
 from .particles import ParticleChannel
 from .thermal2d import BuoyancyDrivenCavity2D
@@ -15,4 +16,4 @@ from .lbm import (BuoyancyDrivenCavity, Communicator, LidDrivenCavity, make_ther
                   halo_plan, make_desc)
 
 __all__ = ["MglcError", "lib", "BuoyancyDrivenCavity", "Communicator", "LidDrivenCavity", "make_thermal_desc", "Subdomain", "cart_neighbors",
-           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "LidDrivenCavity2D", "BuoyancyDrivenCavity2D", "_lib", "formats"]
+           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "LidDrivenCavity2D", "LidDrivenCavityAA", "BuoyancyDrivenCavity2D", "_lib", "formats"]

@@ -56,6 +56,11 @@ class T2dDesc(C.Structure):
                 ("Tref", C.c_double), ("rho0", C.c_double)]
 
 
+class AaDesc(C.Structure):
+    _fields_ = [("n", C.c_int * 3), ("arith", C.c_int), ("collision", C.c_int), ("device", C.c_int),
+                ("tau", C.c_double), ("U0", C.c_double), ("rho0", C.c_double)]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _vp = C.c_void_p
@@ -245,6 +250,19 @@ SIGNATURES = {
     "mglc_t2d_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
     "mglc_t2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_t2d_sync": (C.c_int, [_vp]),
+    "mglc_aa_desc_init": (C.c_int, [C.POINTER(AaDesc), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "mglc_aa_create": (C.c_int, [_vpp, C.POINTER(AaDesc)]),
+    "mglc_aa_destroy": (C.c_int, [_vp]),
+    "mglc_aa_initial": (C.c_int, [_vp]),
+    "mglc_aa_upload": (C.c_int, [_vp] + [_vp] * 5),
+    "mglc_aa_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_aa_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_aa_check": (C.c_int, [_vp, _dp]),
+    "mglc_aa_download_macro": (C.c_int, [_vp] + [_vp] * 4),
+    "mglc_aa_download_f": (C.c_int, [_vp, _vp]),
+    "mglc_aa_device_bytes": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_aa_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mglc_aa_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -1,0 +1,82 @@
+"""Host-side mirror of the reference's D3Q19 lid-driven cavity driver (L3/main.f90) on ONE lattice (AA-pattern storage,
+mglc_aa_* in include/mglc.h): same loop body, same results as LidDrivenCavity, half the lattice memory, one subdomain.
+Arrays cross the boundary in the Fortran program's layout f(0:18,nx,ny,nz), rho,u,v,w(nx,ny,nz), order="F"."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class LidDrivenCavityAA:
+    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0):
+        lib = L.lib()
+        d = L.AaDesc()
+        L.check(lib.mglc_aa_desc_init(C.byref(d), *total, Re, U0, rho0))
+        d.arith = {"fast": L.ARITH_FAST, "strict": L.ARITH_STRICT}[arith]
+        d.collision = {"mrt": L.MRT_LID, "bgk": L.BGK}[collision]
+        d.device = device
+        self.desc, self.total, self.tauf = d, tuple(total), d.tau
+        self._h = C.c_void_p()
+        L.check(lib.mglc_aa_create(C.byref(self._h), C.byref(d)))
+
+    def close(self):
+        if self._h:
+            L.lib().mglc_aa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initial(self):
+        L.check(L.lib().mglc_aa_initial(self._h))
+
+    def step(self, n=1):
+        L.check(L.lib().mglc_aa_step(self._h, n))
+
+    def step_timed(self, n=1):
+        ms = C.c_float()
+        L.check(L.lib().mglc_aa_step_timed(self._h, n, C.byref(ms)))
+        return ms.value
+
+    def check(self):
+        e = C.c_double()
+        L.check(L.lib().mglc_aa_check(self._h, C.byref(e)))
+        return e.value
+
+    def sync(self):
+        L.check(L.lib().mglc_aa_sync(self._h))
+
+    def launch_count(self):
+        n = C.c_longlong()
+        L.check(L.lib().mglc_aa_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def device_bytes(self):
+        n = C.c_longlong()
+        L.check(L.lib().mglc_aa_device_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def upload(self, f=None, rho=None, u=None, v=None, w=None):
+        keep = []
+        for name, a in (("f", f), ("rho", rho), ("u", u), ("v", v), ("w", w)):
+            if a is not None:
+                a = np.asfortranarray(a, dtype=np.float64)
+                want = ((19,) if name == "f" else ()) + self.total
+                if a.shape != want:
+                    raise ValueError(f"{name}: expected shape {want}, got {a.shape}")
+            keep.append(a)
+        L.check(L.lib().mglc_aa_upload(self._h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]))
+
+    def download_macro(self):
+        out = {k: np.empty(self.total, order="F") for k in ("rho", "u", "v", "w")}
+        L.check(L.lib().mglc_aa_download_macro(self._h, *[out[k].ctypes.data_as(C.c_void_p) for k in ("rho", "u", "v", "w")]))
+        return out
+
+    def download_f(self):
+        f = np.empty((19,) + self.total, order="F")
+        L.check(L.lib().mglc_aa_download_f(self._h, f.ctypes.data_as(C.c_void_p)))
+        return f

@@ -1,0 +1,144 @@
+"""CPU-only check of the product's AA-pattern (single-lattice) D3Q19 KERNEL SOURCE and launch schedule against the oracle:
+tests/host_shim/aa_host.cpp compiles mglc_b200/csrc/lbm_aa_kernels.inl + lbm_aa_exact.inl + aa_run() (lbm_aa.cuh) for the host
+and sweeps (blockIdx, threadIdx) sequentially -- exact for these kernels.  Covers the in-place pull/push addressing, the wall
+rule on both sides of an odd launch, both lid terms, every way a run can start and end (either layout), download of f from
+either layout, the BGK operator and both arithmetic builds, before any GPU time is spent.  The GPU tests proper are
+tests/test_aa_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "aa_host.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include",
+                           "-o", out, os.path.join(ROOT, "tests", "host_shim", "aa_host.cpp")])
+    S = C.CDLL(out)       # -Bsymbolic: libmglc.so (RTLD_GLOBAL) exports host stubs with the kernels' names; bind to the shim's own
+    S.aa_shim_create.restype = C.c_void_p
+    S.aa_shim_create.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_int] * 2
+    S.aa_shim_destroy.argtypes = [C.c_void_p]
+    S.aa_shim_upload.argtypes = [C.c_void_p] + [dp] * 5
+    S.aa_shim_layout.argtypes = [C.c_void_p]
+    S.aa_shim_step.restype = C.c_longlong
+    S.aa_shim_step.argtypes = [C.c_void_p, C.c_int]
+    S.aa_shim_download_macro.argtypes = [C.c_void_p] + [dp] * 4
+    S.aa_shim_download_f.argtypes = [C.c_void_p, dp, C.c_longlong]
+    return S
+
+
+class AaSim:
+    def __init__(self, S, wd, strict, bgk=False):
+        self.S, self.total = S, wd.total
+        self.h = S.aa_shim_create(*wd.total, wd.Snu, wd.Sq, wd.U0, wd.rho0, int(bgk), int(strict))
+
+    def upload(self, wd):
+        R = wd.ranks[0]
+        a = [np.asfortranarray(x) for x in (R.f, R.rho, R.u, R.v, R.w)]
+        self.S.aa_shim_upload(self.h, *[x.ctypes.data_as(dp) for x in a])
+
+    def step(self, n):
+        return self.S.aa_shim_step(self.h, n)
+
+    def layout(self):
+        return self.S.aa_shim_layout(self.h)
+
+    def macro(self):
+        out = [np.empty(self.total, order="F") for _ in range(4)]
+        self.S.aa_shim_download_macro(self.h, *[x.ctypes.data_as(dp) for x in out])
+        return dict(zip(("rho", "u", "v", "w"), out))
+
+    def f(self, chunk=97):
+        out = np.empty((19,) + self.total, order="F")
+        self.S.aa_shim_download_f(self.h, out.ctypes.data_as(dp), chunk)
+        return out
+
+    def close(self):
+        self.S.aa_shim_destroy(self.h)
+
+
+def seeded(wd, seed):
+    """perturbed populations and fields that are NOT their moments: the first collision() must use the stored rho,u,v,w"""
+    rng = np.random.default_rng(seed)
+    R = wd.ranks[0]
+    R.f[...] *= 1.0 + 0.05 * rng.uniform(-1, 1, R.f.shape)
+    R.rho[...] = 1.0 + 0.02 * rng.uniform(-1, 1, R.rho.shape)
+    for k in ("u", "v", "w"):
+        getattr(R, k)[...] = 0.05 * rng.uniform(-1, 1, R.rho.shape)
+
+
+SCHEDULES = [[1], [2], [3], [4], [1, 1, 1, 1], [2, 1, 2], [3, 3], [5, 2, 1], [1, 4, 1]]
+
+
+@pytest.mark.parametrize("calls", SCHEDULES)
+@pytest.mark.parametrize("collision", ["mrt", "bgk"])
+def test_strict_build_is_bit_exact_for_every_way_a_run_starts_and_ends(shim, calls, collision):
+    total = (9, 8, 7)
+    wd = orc.LidWorld(total, 1, collision=collision)
+    wd.initial()
+    seeded(wd, 5)
+    sim = AaSim(shim, wd, strict=True, bgk=collision == "bgk")
+    sim.upload(wd)
+    for n in calls:
+        wd.step(n)
+        launches = sim.step(n)
+        assert launches >= n + 1
+        m = sim.macro()
+        for k in ("rho", "u", "v", "w"):
+            assert np.array_equal(m[k], wd.gather(k)), (calls, n, k)
+        assert np.array_equal(sim.f(), wd.gather("f")), (calls, n, "f", sim.layout())
+    sim.close(); wd.close()
+
+
+def test_layouts_alternate_as_documented(shim):
+    wd = orc.LidWorld((5, 4, 6), 1)
+    wd.initial()
+    sim = AaSim(shim, wd, strict=True)
+    sim.upload(wd)
+    assert sim.layout() == 0
+    assert sim.step(1) == 3 and sim.layout() == 1          # lid plane + collision + fields through the pull
+    assert sim.step(1) == 2 and sim.layout() == 0          # odd launch + macro
+    assert sim.step(2) == 4 and sim.layout() == 0          # lid plane + collision + odd + macro
+    assert sim.step(3) == 5 and sim.layout() == 1          # lid plane + collision + odd + even + fields through the pull
+    assert sim.step(4) == 5 and sim.layout() == 1          # odd + even + odd + even + fields through the pull
+    sim.close(); wd.close()
+
+
+def test_lid_driven_start_from_initial_strict(shim):
+    """the reference's own start (rest fluid, moving lid): both lid terms of an odd launch matter from the first step"""
+    total = (11, 10, 9)
+    wd = orc.LidWorld(total, 1)
+    wd.initial()
+    sim = AaSim(shim, wd, strict=True)
+    sim.upload(wd)
+    for n in (1, 6, 13):
+        wd.step(n); sim.step(n)
+        m = sim.macro()
+        for k in ("rho", "u", "v", "w"):
+            assert np.array_equal(m[k], wd.gather(k)), (n, k)
+    assert np.array_equal(sim.f(chunk=1000), wd.gather("f"))
+    sim.close(); wd.close()
+
+
+def test_fast_build_tracks_the_oracle(shim):
+    total = (17, 16, 15)
+    wd = orc.LidWorld(total, 1)
+    wd.initial()
+    sim = AaSim(shim, wd, strict=False)
+    sim.upload(wd)
+    for n in (1, 10, 89):
+        wd.step(n); sim.step(n)
+        m = sim.macro()
+        for k in ("rho", "u", "v", "w"):
+            a, b = m[k], wd.gather(k)
+            rel = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+            assert rel <= 1e-12 and np.abs(a - b).max() <= 1e-10, (n, k, rel)
+    sim.close(); wd.close()
