@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(128) k_aa_macro_post(Geom g, LbmParams p, cons
     if (i > g.nx) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz, c = g.idx(0, i, j, k);
     const AaWalls wf = aa_walls(g, i, j, k);
+    const double *__restrict__ Ain = A;
     double f[19];
     AA_PULL_ALL();
     AA_LID_PULL(rho_lid_in);
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(128) k_aa_gather_f(Geom g, LbmParams p, const 
     const int i = (int)(cell % g.nx) + 1, j = (int)((cell / g.nx) % g.ny) + 1, k = (int)(cell / ((long long)g.nx * g.ny)) + 1;
     const long long sq = g.sq, sy = g.sy, sz = g.sz, c = g.idx(0, i, j, k);
     const AaWalls wf = aa_walls(g, i, j, k);
+    const double *__restrict__ Ain = A;
     double f[19];
     AA_PULL_ALL();
     AA_LID_PULL(rho_lid_in);

@@ -12,6 +12,11 @@
 //                               bounceback() of the NEXT loop body -- so one launch advances two streaming steps.
 // Every location is read and written by exactly one thread (the slot (s, z) is touched only by cell z - e_s, or by z itself at
 // a wall), reads before writes: in place without races.  Either launch moves 19 loads + 19 stores = 304 B per cell.
+// Aliasing note: the even and odd kernels read the lattice through a const __restrict__ alias with __ldg (non-coherent loads,
+// free scheduling: 88-96 registers instead of 90-118).  That is sound here because a thread's stores all depend on all 19 of
+// its loads (every post-collision population is a function of every moment), so no store can be hoisted above a load, and the
+// only thread that ever writes a location during a launch is the one that read it: a stale non-coherent line can only be
+// stale in entries nobody reads again.
 #include "common.cuh"
 
 namespace mglc {
@@ -44,10 +49,10 @@ __device__ __forceinline__ void aa_collide(const double (&f)[19], double rho, do
     {                                                                                                       \
         const bool wall_ = ((dx) == 1 && wf.xm) || ((dx) == -1 && wf.xp) || ((dy) == 1 && wf.ym) ||        \
                            ((dy) == -1 && wf.yp) || ((dz) == 1 && wf.zm) || ((dz) == -1 && wf.zp);         \
-        f[a] = A[wall_ ? (a) * sq + c : (o) * sq + (c - (dz) * sz - (dy) * sy - (dx))];                    \
+        f[a] = __ldg(Ain + (wall_ ? (a) * sq + c : (o) * sq + (c - (dz) * sz - (dy) * sy - (dx))));                    \
     }
 #define AA_PULL_ALL()    \
-    f[0] = A[c];         \
+    f[0] = __ldg(Ain + c); \
     AA_FOR_ALL(AA_PULL)
 #define AA_LID_PULL(rho_lid)                                                                   \
     if (wf.zp) {                                                                               \
@@ -83,13 +88,14 @@ __global__ void __launch_bounds__(128, 4) k_aa_collide0(Geom g, LbmParams p, dou
 
 // NATURAL -> POST: macro() of this loop body and collision() of the next, at the cell
 template <bool BGK>
-__global__ void __launch_bounds__(128, 4) k_aa_even(Geom g, LbmParams p, double *A, double *__restrict__ rho_lid_out) {
+__global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double *__restrict__ A, double *__restrict__ rho_lid_out) {
+    const double *__restrict__ Ain = A;      // see the note on aliasing above
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
     const long long sq = g.sq, c = g.idx(0, i, j, k);
     double f[19], fp[19];
 #pragma unroll
-    for (int a = 0; a < 19; ++a) f[a] = A[a * sq + c];
+    for (int a = 0; a < 19; ++a) f[a] = __ldg(Ain + a * sq + c);
     double rho, u, v, w;
     d3q19_macro(f, rho, u, v, w);
     aa_collide<BGK>(f, rho, u, v, w, p, fp);
@@ -102,7 +108,8 @@ __global__ void __launch_bounds__(128, 4) k_aa_even(Geom g, LbmParams p, double 
 
 // POST -> NATURAL: streaming() + bounceback() + macro() of loop body n, collision() + streaming() + bounceback() of body n+1
 template <bool BGK>
-__global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *A, const double *__restrict__ rho_lid_in) {
+__global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *__restrict__ A, const double *__restrict__ rho_lid_in) {
+    const double *__restrict__ Ain = A;      // see the note on aliasing above
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz, c = g.idx(0, i, j, k);

@@ -691,7 +691,10 @@ class T2Params(C.Structure):
 
 
 T2_FIELDS = {"f": 0, "f_post": 1, "g": 2, "g_post": 3, "rho": 4, "u": 5, "v": 6, "T": 7, "up": 8, "vp": 9, "Tp": 10, "Fx": 11, "Fy": 12}
-T2_ADIABATIC, T2_CONST_HOT, T2_CONST_COLD = 0, 1, 2
+T2_ADIABATIC, T2_CONST_HOT, T2_CONST_COLD, T2_PERIODIC = 0, 1, 2, 3
+T2_MPI, T2_ACC = 0, 1
+# the OpenACC program's shipped set (seq/bouyancy2d_acc.F90:13-22): Rayleigh-Benard cell, vertical walls periodic for f and g
+T2_RB_PERIODIC = (T2_PERIODIC, T2_PERIODIC, T2_CONST_COLD, T2_CONST_HOT)
 T2_SIDE_HEATED = (T2_CONST_COLD, T2_CONST_HOT, T2_ADIABATIC, T2_ADIABATIC)      # +x, -x, +y, -y   macros.F90:24-27
 T2_RAYLEIGH_BENARD = (T2_ADIABATIC, T2_ADIABATIC, T2_CONST_COLD, T2_CONST_HOT)  # macros.F90:17-20
 
@@ -716,13 +719,15 @@ def _t2_lib():
         L.t2_derive_params.argtypes = [C.POINTER(T2Params), C.c_int]
         L.t2_collide_cell.argtypes = [C.POINTER(T2Params), _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
         L.t2_collideT_cell.argtypes = [C.POINTER(T2Params), _dp, C.c_double, C.c_double, C.c_double, _dp]
+        L.t2_collide_cell_v.argtypes = [C.c_int, C.POINTER(T2Params), _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.t2_world_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L._t2_ready = True
     return L
 
 
-def t2_params(total_ny=201, Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0):
-    """module.F90:29-33,67-81 evaluated by the oracle"""
-    p = T2Params(Rayleigh=Rayleigh, Prandtl=Prandtl, Mach=Mach, Thot=Thot, Tcold=Tcold, Tref=Tref, rho0=rho0)
+def t2_params(total_ny=201, Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0, lengthUnit=0.0):
+    """module.F90:29-33,67-81 evaluated by the oracle (lengthUnit = 0: dble(total_ny); the OpenACC program uses dble(nx), acc:57)"""
+    p = T2Params(Rayleigh=Rayleigh, Prandtl=Prandtl, Mach=Mach, Thot=Thot, Tcold=Tcold, Tref=Tref, rho0=rho0, lengthUnit=lengthUnit)
     _t2_lib().t2_derive_params(C.byref(p), total_ny)
     return p
 
@@ -746,7 +751,7 @@ class Thermal2DWorld:
     """All P emulated ranks of the 2-D thermal driver in one process."""
     LEAD = {"f": 9, "f_post": 9, "g": 5, "g_post": 5}
 
-    def __init__(self, total=(201, 201), nprocs=1, dims=None, bcT=None, **params):
+    def __init__(self, total=(201, 201), nprocs=1, dims=None, bcT=None, variant="mpi", lengthUnit=0.0, **params):
         self._lib = _t2_lib()
         d = (C.c_int * 2)(*(dims if dims else (0, 0)))
         pv = dict(Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0)
@@ -754,12 +759,17 @@ class Thermal2DWorld:
         par = (C.c_double * 7)(*[pv[k] for k in ("Rayleigh", "Prandtl", "Mach", "Thot", "Tcold", "Tref", "rho0")])
         bc = (C.c_int * 4)(*bcT) if bcT is not None else None
         self._h = self._lib.t2_world_create(total[0], total[1], nprocs, d, par, bc)
+        self.variant = variant
+        if variant != "mpi" or lengthUnit:
+            self._lib.t2_world_set_variant(self._h, {"mpi": T2_MPI, "acc": T2_ACC}[variant], float(lengthUnit))
         self.total, self.nprocs = tuple(total), nprocs
         self.ranks = [Thermal2DRank(self, r) for r in range(nprocs)]
         dd, bb = (C.c_int * 2)(), (C.c_int * 4)()
         self.params = T2Params()
         self._lib.t2_world_info(self._h, dd, C.byref(self.params), bb)
         self.dims, self.bcT = tuple(dd), tuple(bb)
+        if T2_PERIODIC in self.bcT:
+            assert self.bcT[0] == self.bcT[1] == T2_PERIODIC and self.dims[0] == 1, "periodic vertical walls need bcT[0] = bcT[1] and dims[0] = 1"
 
     def close(self):
         if self._h:
@@ -811,10 +821,11 @@ for _name, _sub in (("initial", "t2_initial"), ("collision", "t2_collision"), ("
     setattr(Thermal2DWorld, _name, (lambda sub: lambda self: getattr(self._lib, sub)(self._h))(_sub))
 
 
-def t2_collide_cell(p, f, rho, u, v, T):
+def t2_collide_cell(p, f, rho, u, v, T, variant="mpi"):
     f = np.ascontiguousarray(f, dtype=np.float64)
     out, F2 = np.empty(9), np.empty(2)
-    _t2_lib().t2_collide_cell(C.byref(p), f.ctypes.data_as(_dp), rho, u, v, T, out.ctypes.data_as(_dp), F2.ctypes.data_as(_dp))
+    _t2_lib().t2_collide_cell_v({"mpi": T2_MPI, "acc": T2_ACC}[variant], C.byref(p), f.ctypes.data_as(_dp), rho, u, v, T,
+                                out.ctypes.data_as(_dp), F2.ctypes.data_as(_dp))
     return out, F2
 
 

@@ -20,7 +20,8 @@
 
 #define Q9 9
 #define Q5 5
-enum { T2_ADIABATIC = 0, T2_CONST_HOT = 1, T2_CONST_COLD = 2 };
+enum { T2_ADIABATIC = 0, T2_CONST_HOT = 1, T2_CONST_COLD = 2, T2_PERIODIC = 3 };
+enum { T2_MPI = 0, T2_ACC = 1 };
 
 /* module.F90:106-109 */
 static const int ex[Q9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
@@ -41,6 +42,8 @@ typedef struct t2_rank {
 typedef struct t2_world {
     int total[2], dims[2], np, itc;
     int bcT[4];          /* +x (right), -x (left), +y (top), -y (bottom) : T2_*   macros.F90:16-27 */
+    int variant;         /* T2_MPI: mpi_blocked/evolution_f.F90 ; T2_ACC: seq/bouyancy2d_acc.F90 (f_post(0) rounded term by term) */
+    int periodic_x;      /* VerticalWallsPeriodicalU + VerticalWallsPeriodicalT (acc:15,22): needs dims[0] == 1 */
     t2_params p;
     double errorU, errorT;
     t2_rank *r;
@@ -54,7 +57,7 @@ typedef struct t2_world {
 
 /* module.F90:29,69-81.  lengthUnit = dble(total_ny); Rayleigh is the single-precision literal 1e7 (exact). */
 void t2_derive_params(t2_params *p, int total_ny) {
-    p->lengthUnit = (double)total_ny;
+    if (!(p->lengthUnit > 0.0)) p->lengthUnit = (double)total_ny;        /* acc:57 uses dble(nx) instead: the caller sets it */
     p->tauf = 0.5 + p->Mach * p->lengthUnit * sqrt(3.0 * p->Prandtl / p->Rayleigh);
     p->viscosity = (p->tauf - 0.5) / 3.0;
     p->diffusivity = p->viscosity / p->Prandtl;
@@ -95,6 +98,8 @@ t2_world *t2_world_create(int tnx, int tny, int np, const int *dims_or_null, con
     memcpy(w->bcT, bcT_or_null ? bcT_or_null : shipped, sizeof w->bcT);
     w->p.Rayleigh = par7[0]; w->p.Prandtl = par7[1]; w->p.Mach = par7[2]; w->p.Thot = par7[3]; w->p.Tcold = par7[4];
     w->p.Tref = par7[5]; w->p.rho0 = par7[6];
+    w->p.lengthUnit = 0.0;
+    w->periodic_x = w->bcT[0] == T2_PERIODIC || w->bcT[1] == T2_PERIODIC;
     t2_derive_params(&w->p, tny);
     w->r = (t2_rank *)calloc((size_t)np, sizeof(t2_rank));
     for (int c0 = 0; c0 < w->dims[0]; ++c0)
@@ -123,6 +128,12 @@ void t2_world_destroy(t2_world *w) {
     }
     free(w->r); free(w);
 }
+/* the OpenACC program's flavour: variant = T2_ACC, lengthUnit = dble(nx) (acc:57); re-derives the parameters */
+void t2_world_set_variant(t2_world *w, int variant, double lengthUnit_or_0) {
+    w->variant = variant;
+    w->p.lengthUnit = lengthUnit_or_0;
+    t2_derive_params(&w->p, w->total[1]);
+}
 void t2_world_info(t2_world *w, int dims[2], t2_params *p, int bcT[4]) {
     dims[0] = w->dims[0]; dims[1] = w->dims[1];
     *p = w->p;
@@ -149,8 +160,10 @@ void t2_initial(t2_world *w) {
     omegaT[0] = (1.0 - p->paraA) / 5.0;
     for (int a = 1; a <= 4; ++a) omegaT[a] = (p->paraA + 4.0) / 20.0;
     w->itc = 0; w->errorU = 100.0; w->errorT = 100.0;
-    const int vertT = w->bcT[0] != T2_ADIABATIC || w->bcT[1] != T2_ADIABATIC;      /* #ifdef VerticalWallsConstT   */
-    const int horT = w->bcT[2] != T2_ADIABATIC || w->bcT[3] != T2_ADIABATIC;       /* #ifdef HorizontalWallsConstT */
+    const int isT[4] = {w->bcT[0] == T2_CONST_HOT || w->bcT[0] == T2_CONST_COLD, w->bcT[1] == T2_CONST_HOT || w->bcT[1] == T2_CONST_COLD,
+                        w->bcT[2] == T2_CONST_HOT || w->bcT[2] == T2_CONST_COLD, w->bcT[3] == T2_CONST_HOT || w->bcT[3] == T2_CONST_COLD};
+    const int vertT = isT[0] || isT[1];                                            /* #ifdef VerticalWallsConstT   */
+    const int horT = isT[2] || isT[3];                                             /* #ifdef HorizontalWallsConstT */
     for (int r = 0; r < w->np; ++r) {
         t2_rank *R = &w->r[r];
         for (int j = 1; j <= R->ny; ++j)
@@ -179,7 +192,12 @@ void t2_initial(t2_world *w) {
 }
 
 /* collision() of one cell: evolution_f.F90:15-78.  out: fp[9], FxFy[2] */
+void t2_collide_cell_v(int variant, const t2_params *p, const double *f, double rho, double u, double v, double T, double *fp, double *FxFy);
 void t2_collide_cell(const t2_params *p, const double *f, double rho, double u, double v, double T, double *fp, double *FxFy) {
+    t2_collide_cell_v(T2_MPI, p, f, rho, u, v, T, fp, FxFy);
+}
+/* variant T2_ACC: seq/bouyancy2d_acc.F90:628-694 -- identical except f_post(0) = m0/9 - m1/9 + m2/9 (acc:679) */
+void t2_collide_cell_v(int variant, const t2_params *p, const double *f, double rho, double u, double v, double T, double *fp, double *FxFy) {
     double m[Q9], meq[Q9], mp[Q9], s[Q9], fs[Q9];
     m[0] = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
     m[1] = -4.0 * f[0] - f[1] - f[2] - f[3] - f[4] + 2.0 * (f[5] + f[6] + f[7] + f[8]);
@@ -212,7 +230,7 @@ void t2_collide_cell(const t2_params *p, const double *f, double rho, double u, 
     fs[7] = (2.0 - s[7]) * (u * Fx - v * Fy);
     fs[8] = (1.0 - 0.5 * s[8]) * (u * Fy + v * Fx);
     for (int a = 0; a < Q9; ++a) mp[a] = m[a] - s[a] * (m[a] - meq[a]) + fs[a];
-    fp[0] = (mp[0] - mp[1] + mp[2]) / 9.0;
+    fp[0] = variant == T2_ACC ? mp[0] / 9.0 - mp[1] / 9.0 + mp[2] / 9.0 : (mp[0] - mp[1] + mp[2]) / 9.0;
     fp[1] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 + mp[3] / 6.0 - mp[4] / 6.0 + mp[7] / 4.0;
     fp[2] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 + mp[5] / 6.0 - mp[6] / 6.0 - mp[7] / 4.0;
     fp[3] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 - mp[3] / 6.0 + mp[4] / 6.0 + mp[7] / 4.0;
@@ -230,7 +248,7 @@ void t2_collision(t2_world *w) {
         for (int j = 1; j <= R->ny; ++j)
             for (int i = 1; i <= R->nx; ++i) {
                 double F2[2];
-                t2_collide_cell(&w->p, &F(R, 0, i, j), S(R, rho, i, j), S(R, u, i, j), S(R, v, i, j), S(R, T, i, j), &FP(R, 0, i, j), F2);
+                t2_collide_cell_v(w->variant, &w->p, &F(R, 0, i, j), S(R, rho, i, j), S(R, u, i, j), S(R, v, i, j), S(R, T, i, j), &FP(R, 0, i, j), F2);
                 S(R, Fx, i, j) = F2[0]; S(R, Fy, i, j) = F2[1];
             }
     }
@@ -329,10 +347,17 @@ void t2_bounceback(t2_world *w) {
     for (int r = 0; r < w->np; ++r) {
         t2_rank *R = &w->r[r];
         const int nx = R->nx, ny = R->ny;
+        if (w->periodic_x) {   /* VerticalWallsPeriodicalU, acc:777-791: the SAME row j of the opposite side, also for the diagonals */
+            for (int j = 1; j <= ny; ++j) {
+                F(R, 1, 1, j) = FP(R, 1, nx, j); F(R, 5, 1, j) = FP(R, 5, nx, j); F(R, 8, 1, j) = FP(R, 8, nx, j);
+                F(R, 3, nx, j) = FP(R, 3, 1, j); F(R, 6, nx, j) = FP(R, 6, 1, j); F(R, 7, nx, j) = FP(R, 7, 1, j);
+            }
+        } else {
         if (R->coords[0] == 0)
             for (int j = 1; j <= ny; ++j) { F(R, 1, 1, j) = FP(R, 3, 1, j); F(R, 5, 1, j) = FP(R, 7, 1, j); F(R, 8, 1, j) = FP(R, 6, 1, j); }
         if (R->coords[0] == w->dims[0] - 1)
             for (int j = 1; j <= ny; ++j) { F(R, 3, nx, j) = FP(R, 1, nx, j); F(R, 6, nx, j) = FP(R, 8, nx, j); F(R, 7, nx, j) = FP(R, 5, nx, j); }
+        }
         if (R->coords[1] == 0)
             for (int i = 1; i <= nx; ++i) { F(R, 2, i, 1) = FP(R, 4, i, 1); F(R, 5, i, 1) = FP(R, 7, i, 1); F(R, 6, i, 1) = FP(R, 8, i, 1); }
         if (R->coords[1] == w->dims[1] - 1)
@@ -354,6 +379,10 @@ void t2_bouncebackT(t2_world *w) {
             const int face = order[q];
             if (!on[face]) continue;
             const int kind = w->bcT[face];
+            if (kind == T2_PERIODIC) {      /* VerticalWallsPeriodicalT, acc:1037-1045 */
+                for (int j = 1; j <= ny; ++j) G(R, in_pop[face], face == 0 ? nx : 1, j) = GP(R, in_pop[face], face == 0 ? 1 : nx, j);
+                continue;
+            }
             const double Tw = kind == T2_CONST_HOT ? p->Thot : p->Tcold;
             const int n = face < 2 ? ny : nx;
             for (int t = 1; t <= n; ++t) {

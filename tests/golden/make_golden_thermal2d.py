@@ -12,6 +12,10 @@ lie (fortran_eval.py: verbatim loop bodies -> Python floats = IEEE binary64, lef
   initial/*       initial.F90:201-212 (weights), :258/:268 (T profile), :278-286 (populations)
   field/*         whole-array subroutines on a seeded 6 x 5 block with one-cell halos: streaming :96-105, bounceback :283-321,
                   streamingT g:56-65, bouncebackT g:79-142 (both macro sets of macros.F90), check.F90:10-30 (the four rank sums)
+  acc/*           the same subroutines of the OpenACC program seq/bouyancy2d_acc.F90 (the reference's only GPU code; population index
+                  last): module constants :91-103, collision :631-695 (f_post(0) rounded term by term), collisionT :879-905, and
+                  streaming :722-743, bounceback :758-822, streamingT :934-954, bouncebackT :968-1046 with its shipped macro
+                  set (periodic vertical walls for f and g, constant-temperature plates)
 Only numbers are stored; run in the authoring container."""
 import os
 import re
@@ -55,6 +59,8 @@ def strip_cpp(text, defined):
         s = line.strip()
         if s.startswith("#ifdef"):
             keep.append(keep[-1] and s.split()[1] in defined)
+        elif s.startswith("#ifndef"):
+            keep.append(keep[-1] and s.split()[1] not in defined)
         elif s.startswith("#endif"):
             keep.pop()
         elif keep[-1]:
@@ -210,6 +216,56 @@ def main():
     ns = run_full(src, {k.lower(): to_full(a, (1, 1)) for k, a in fl.items()}, dict(nx=nx, ny=ny))
     out["field/check_sums"] = np.array([ns["error1"], ns["error2"], ns["error5"], ns["error6"]])
     out["field/check_up_after"] = from_full(ns["up__"], (nx, ny), (1, 1))
+
+    # ---------------- the OpenACC program (seq/bouyancy2d_acc.F90): the reference's only GPU code ----------------
+    # same subroutines with the population index LAST, f(i,j,alpha); reorder the subscripts, then evaluate as above
+    ACC = "/root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/bouyancy2d_acc.F90"
+
+    def acc_text(first, last, defined=()):
+        t = strip_cpp(fe.read_lines(ACC, first, last), set(defined))
+        t = "\n".join(l for l in t.splitlines() if not l.strip().lower().startswith("!$acc"))
+        return re.sub(r"\b(f_post|g_post|f|g)\(([^(),]+),([^(),]+),([^(),]+)\)", r"\1(\4,\2,\3)", t)
+    Pa = acc_params = None
+    # module constants of the OpenACC program: nx = 513, ny = 257, lengthUnit = dble(nx), Ra = 1e5 (acc:55-60,91-103)
+    text = []
+    for line in fe.read_lines(ACC, 91, 103).splitlines():
+        m = re.match(r"\s*real\(kind=8\),\s*parameter\s*::\s*(.*)$", line.split("!")[0].strip())
+        if m:
+            text += fe._split_args(m.group(1))
+    ns = fe.run(fe.translate("\n".join(text)) + "\nout__ = dict(tauf=tauf, viscosity=viscosity, diffusivity=diffusivity, paraa=paraa, gbeta=gbeta, snu=snu, sq=sq, qd=qd, qnu=qnu)",
+                scalars=dict(mach=0.1, lengthunit=513.0, prandtl=0.71, rayleigh=1e5), field_out=["out"])
+    Pa = ns["out"]
+    out["acc/params"] = np.array([Pa[k] for k in ("tauf", "viscosity", "diffusivity", "paraa", "gbeta", "snu", "sq", "qd", "qnu")])
+    sca = dict(snu=Pa["snu"], sq=Pa["sq"], gbeta=Pa["gbeta"], tref=0.0, paraa=Pa["paraa"], qd=Pa["qd"], qnu=Pa["qnu"])
+    la = ["s", "m", "m_post", "meq", "fsource"]
+    src = fe.translate(acc_text(631, 695), cell_arrays=["f", "f_post"], fields=["rho", "u", "v", "T", "Fx", "Fy"], local_arrays=la)
+    res = [fe.run(src, cell_in={"f": c["f"]}, field_in={k: c[k] for k in ("rho", "u", "v", "T")}, scalars=sca, local_arrays=la,
+                  cell_out=["f_post"], field_out=["fx", "fy"]) for c in cells]
+    out["acc/collision_f_post"] = np.array([r["f_post"] for r in res])
+    out["acc/collision_FxFy"] = np.array([[r["fx"], r["fy"]] for r in res])
+    la = ["n", "n_post", "neq", "q"]
+    src = fe.translate(acc_text(879, 905), cell_arrays=["g", "g_post"], fields=["T", "u", "v"], local_arrays=la)
+    res = [fe.run(src, cell_in={"g": c["g"]}, field_in={k: c[k] for k in ("u", "v", "T")}, scalars=sca, local_arrays=la, cell_out=["g_post"])
+           for c in cells]
+    out["acc/collisionT_g_post"] = np.array([r["g_post"] for r in res])
+    # whole-array: streaming, bounceback, streamingT, bouncebackT with the shipped macro set (periodic vertical walls, RB plates)
+    acc_defs = {"HorizontalWallsNoslip", "VerticalWallsPeriodicalU", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsPeriodicalT",
+                "steadyFlow"}
+    full_acc = ["f", "f_post", "g", "g_post", "ex", "ey", "obst"]
+    obst = fe._Arr({(i, j): 0 for i in range(0, nx + 2) for j in range(0, ny + 2)})
+    cm = dict(nx=nx, ny=ny, paraa=Pa["paraa"], thot=1.0, tcold=0.0)
+    src = fe.translate(acc_text(722, 743, acc_defs), full_arrays=full_acc)
+    ns = run_full(src, {"f": fe._Arr(), "f_post": to_full(fp, (0, 0, 0)), "obst": obst}, cm)
+    out["acc/streaming_f"] = from_full(ns["f__"], (9, nx, ny), (0, 1, 1))
+    src = fe.translate(acc_text(758, 822, acc_defs), full_arrays=full_acc)
+    ns = run_full(src, {"f": to_full(f0, (0, 1, 1)), "f_post": to_full(fp, (0, 0, 0)), "obst": obst, **idx}, cm)
+    out["acc/bounceback_f"] = from_full(ns["f__"], (9, nx, ny), (0, 1, 1))
+    src = fe.translate(acc_text(934, 954, acc_defs), full_arrays=full_acc)
+    ns = run_full(src, {"g": fe._Arr(), "g_post": to_full(gp, (0, 0, 0)), "obst": obst}, cm)
+    out["acc/streamingT_g"] = from_full(ns["g__"], (5, nx, ny), (0, 1, 1))
+    src = fe.translate(acc_text(968, 1046, acc_defs), full_arrays=full_acc)
+    ns = run_full(src, {"g": to_full(g0, (0, 1, 1)), "g_post": to_full(gp, (0, 0, 0)), "obst": obst, **idx}, cm)
+    out["acc/bouncebackT_g"] = from_full(ns["g__"], (5, nx, ny), (0, 1, 1))
 
     path = os.path.join(HERE, "ref_fortran_thermal2d.npz")
     np.savez_compressed(path, **out)

@@ -21,6 +21,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
 
 #define MGLC_NS strict
 #define MGLC_STRICT 1
