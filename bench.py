@@ -52,6 +52,9 @@ def parse_args():
     p.add_argument("--size", type=int, default=0, help="per-GPU block edge (weak) / global edge (strong); 0 = the workload's config size")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    p.add_argument("--variant", default="mpi", choices=["mpi", "acc"],
+                   help="thermal2d only: mpi = mpi_blocked/ (side-heated), acc = the OpenACC program seq/bouyancy2d_acc.F90 "
+                        "(Rayleigh-Benard plates, periodic vertical walls; --size 0 = its shipped 513 x 257)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -216,7 +219,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     thermal = args.workload == "thermal"
     if args.size == 0:
-        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0, "lid2d": 8192, "thermal2d": 8192, "lid_aa": 896}[args.workload]
+        args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0, "lid2d": 8192, "thermal2d": 8192 if args.variant == "mpi" else 0, "lid_aa": 896}[args.workload]
     if args.workload == "jacobi":
         import bench_jacobi
         bench_jacobi.main(args, rank, local_rank, world)

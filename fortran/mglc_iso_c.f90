@@ -47,9 +47,10 @@ module mglc_iso_c
     !> mglc_t2d_desc: module commondata of the 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/module.F90:26-33,67-68)
     !> and the boundary macro set of macros.F90:16-27 (bcT = +x, -x, +y, -y)
     type, bind(C) :: mglc_t2d_desc
-        integer(c_int) :: total_nx, total_ny, arith, bcT(4), reserved
-        real(c_double) :: Rayleigh, Prandtl, Mach, Thot, Tcold, Tref, rho0
+        integer(c_int) :: total_nx, total_ny, arith, bcT(4), variant
+        real(c_double) :: Rayleigh, Prandtl, Mach, Thot, Tcold, Tref, rho0, lengthUnit
     end type mglc_t2d_desc
+    integer(c_int), parameter :: MGLC_T2D_MPI = 0, MGLC_T2D_ACC = 1, MGLC_BCT_PERIODIC = 3
 
     interface
         ! ---- host-only helpers -------------------------------------------------------------------
@@ -447,6 +448,12 @@ module mglc_iso_c
         end function
         ! ---- 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/main.F90:84-108) ---------------------------
         function mglc_t2d_desc_init(d) bind(C, name="mglc_t2d_desc_init") result(rc)
+            import :: c_int, mglc_t2d_desc
+            type(mglc_t2d_desc), intent(out) :: d
+            integer(c_int) :: rc
+        end function
+        !> the OpenACC program's shipped constants, seq/bouyancy2d_acc.F90:9-22,55-60
+        function mglc_t2d_desc_init_acc(d) bind(C, name="mglc_t2d_desc_init_acc") result(rc)
             import :: c_int, mglc_t2d_desc
             type(mglc_t2d_desc), intent(out) :: d
             integer(c_int) :: rc

@@ -49,7 +49,8 @@ enum { MGLC_ARITH_FAST = 0, MGLC_ARITH_STRICT = 1 };
 enum { MGLC_TRANSPORT_NONE = 0, MGLC_TRANSPORT_LOCAL = 1, MGLC_TRANSPORT_NCCL = 2 };
 /* thermal wall kinds of bouncebackT() (B3 = MPI/Buoyancy_driven_cavity/fortran/3d/bouyancy3d_mpi.F90:1100-1210):
  * adiabatic g_a = g_post_opp, constant temperature g_a = -g_post_opp + (6+paraA)/21 * Thot|Tcold */
-enum { MGLC_BCT_ADIABATIC = 0, MGLC_BCT_CONST_HOT = 1, MGLC_BCT_CONST_COLD = 2 };
+enum { MGLC_BCT_ADIABATIC = 0, MGLC_BCT_CONST_HOT = 1, MGLC_BCT_CONST_COLD = 2,
+       MGLC_BCT_PERIODIC = 3 /* 2-D thermal driver only: both vertical walls, seq/bouyancy2d_acc.F90:15,22 */ };
 /* fused-kernel variant (MGLC_KERNEL_AUTO picks the fastest validated one) */
 enum { MGLC_KERNEL_AUTO = 0, MGLC_KERNEL_DIRECT = 1, MGLC_KERNEL_TMA = 2 };
 
@@ -373,12 +374,19 @@ typedef struct mglc_t2d mglc_t2d;
 typedef struct mglc_t2d_desc {
     int total_nx, total_ny;              /* module.F90:26                                    */
     int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT              */
-    int bcT[4];                          /* +x (right), -x (left), +y (top), -y (bottom): MGLC_BCT_*   macros.F90:16-27 */
-    int reserved;
+    int bcT[4];                          /* +x (right), -x (left), +y (top), -y (bottom): MGLC_BCT_*   macros.F90:16-27;
+                                            MGLC_BCT_PERIODIC on both vertical walls = VerticalWallsPeriodicalU + ...T of the
+                                            OpenACC program (seq/bouyancy2d_acc.F90:15,22); needs dims[0] == 1 */
+    int variant;                         /* MGLC_T2D_MPI: the mpi_blocked files | MGLC_T2D_ACC: seq/bouyancy2d_acc.F90 (its collision()
+                                            rounds f_post(0) term by term, acc:679) */
     double Rayleigh, Prandtl, Mach;      /* module.F90:31-33                                 */
     double Thot, Tcold, Tref, rho0;      /* module.F90:67-68                                 */
+    double lengthUnit;                   /* 0 = dble(total_ny) (module.F90:29); the OpenACC program uses dble(nx) (acc:57) */
 } mglc_t2d_desc;
+enum { MGLC_T2D_MPI = 0, MGLC_T2D_ACC = 1 };
 int mglc_t2d_desc_init(mglc_t2d_desc *d);                               /* the shipped constants (201 x 201, Ra 1e7, side-heated) */
+/* the OpenACC program as shipped: 513 x 257, Ra 1e5, Rayleigh-Benard plates, periodic vertical walls, lengthUnit = 513 (acc:9-22,55-60) */
+int mglc_t2d_desc_init_acc(mglc_t2d_desc *d);
 /* MPI_Dims_create(np,2) + MPI_Cart_create + decompose_1d + MPI_Cart_shift + MPI_Cart_find_corners + allocate -- main.F90:21-43,
  * initial.F90:177-197; tauf, viscosity, diffusivity, paraA, gBeta, Snu, Sq, Qd, Qnu -- module.F90:69-81; fails with
  * MGLC_E_INVALID where the reference stops (paraA outside (-4,1), initial.F90:30) */

@@ -15,7 +15,8 @@ D3Q19, D3Q19_D3Q7, D2Q9 = 0, 1, 2
 MRT_LID, MRT_THERMAL, BGK = 0, 1, 2
 ARITH_FAST, ARITH_STRICT = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
-BCT_ADIABATIC, BCT_CONST_HOT, BCT_CONST_COLD = 0, 1, 2
+BCT_ADIABATIC, BCT_CONST_HOT, BCT_CONST_COLD, BCT_PERIODIC = 0, 1, 2, 3
+T2D_MPI, T2D_ACC = 0, 1
 L2D_C, L2D_F = 0, 1
 
 
@@ -51,9 +52,9 @@ class L2dDesc(C.Structure):
 
 
 class T2dDesc(C.Structure):
-    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("arith", C.c_int), ("bcT", C.c_int * 4), ("reserved", C.c_int),
+    _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("arith", C.c_int), ("bcT", C.c_int * 4), ("variant", C.c_int),
                 ("Rayleigh", C.c_double), ("Prandtl", C.c_double), ("Mach", C.c_double), ("Thot", C.c_double), ("Tcold", C.c_double),
-                ("Tref", C.c_double), ("rho0", C.c_double)]
+                ("Tref", C.c_double), ("rho0", C.c_double), ("lengthUnit", C.c_double)]
 
 
 class AaDesc(C.Structure):
@@ -225,6 +226,7 @@ SIGNATURES = {
     "mglc_l2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_l2d_sync": (C.c_int, [_vp]),
     "mglc_t2d_desc_init": (C.c_int, [C.POINTER(T2dDesc)]),
+    "mglc_t2d_desc_init_acc": (C.c_int, [C.POINTER(T2dDesc)]),
     "mglc_t2d_create": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
     "mglc_t2d_create_local": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, _ip]),
     "mglc_t2d_destroy": (C.c_int, [_vp]),

@@ -6,6 +6,8 @@
 // through, constant reciprocals, FMA).
 
 // out: fp[9] and the force Fy = rho*gBeta*(T-Tref) (Fx is identically 0, evolution_f.F90:45)
+// acc = true: the OpenACC program's collision() (seq/bouyancy2d_acc.F90:631-695), identical except f_post(0) = m0/9 - m1/9 + m2/9
+template <bool ACC>
 __device__ __forceinline__ void t2_collide(const double (&f)[9], double rho, double u, double v, double T, double Snu, double Sq,
                                            double gBeta, double Tref, double (&fp)[9], double &Fy_out) {
 #ifdef MGLC_STRICT
@@ -42,7 +44,7 @@ __device__ __forceinline__ void t2_collide(const double (&f)[9], double rho, dou
     fs[8] = (1.0 - 0.5 * s[8]) * (u * Fy + v * Fx);
 #pragma unroll
     for (int a = 0; a < 9; ++a) mp[a] = m[a] - s[a] * (m[a] - meq[a]) + fs[a];
-    fp[0] = (mp[0] - mp[1] + mp[2]) / 9.0;
+    fp[0] = ACC ? mp[0] / 9.0 - mp[1] / 9.0 + mp[2] / 9.0 : (mp[0] - mp[1] + mp[2]) / 9.0;
     fp[1] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 + mp[3] / 6.0 - mp[4] / 6.0 + mp[7] / 4.0;
     fp[2] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 + mp[5] / 6.0 - mp[6] / 6.0 - mp[7] / 4.0;
     fp[3] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 - mp[3] / 6.0 + mp[4] / 6.0 + mp[7] / 4.0;

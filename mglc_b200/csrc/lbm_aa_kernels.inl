@@ -114,19 +114,35 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     if (i > g.nx) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz, c = g.idx(0, i, j, k);
     const AaWalls wf = aa_walls(g, i, j, k);
+    // Interior cells (no wall flag: all but the outermost shell) take straight-line paths: every address is the cell index plus
+    // a block-uniform offset, no per-population wall test and no 64-bit select -- half the instructions of the general path.
+    const bool shell = wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
     double f[19], fp[19];
-    AA_PULL_ALL();
-    AA_LID_PULL(rho_lid_in);
+    if (!shell) {
+        f[0] = __ldg(Ain + c);
+#define AA_PULL_IN(a, o, dx, dy, dz) f[a] = __ldg(Ain + ((o) * sq + (c - (dz) * sz - (dy) * sy - (dx))));
+        AA_FOR_ALL(AA_PULL_IN)
+#undef AA_PULL_IN
+    } else {
+        AA_PULL_ALL();
+        AA_LID_PULL(rho_lid_in);
+    }
     double rho, u, v, w;
     d3q19_macro(f, rho, u, v, w);
     aa_collide<BGK>(f, rho, u, v, w, p, fp);
-    if (wf.zp) {      // the lid term of body n+1 uses the rho this macro() just produced: f(14) = f_post(11) - rho/6*U0, f(13) = f_post(12) - rho/6*(-U0)
-        const double r6 = __ddiv_rn(rho, 6.0);
-        fp[11] = __dsub_rn(fp[11], __dmul_rn(r6, p.U0));
-        fp[12] = __dsub_rn(fp[12], __dmul_rn(r6, -p.U0));
-    }
     A[c] = fp[0];
-    AA_FOR_ALL(AA_PUSH)
+    if (!shell) {
+#define AA_PUSH_IN(a, o, dx, dy, dz) A[(a) * sq + (c + (dz) * sz + (dy) * sy + (dx))] = fp[a];
+        AA_FOR_ALL(AA_PUSH_IN)
+#undef AA_PUSH_IN
+    } else {
+        if (wf.zp) {  // the lid term of body n+1 uses the rho this macro() just produced: f(14) = f_post(11) - rho/6*U0, f(13) = f_post(12) - rho/6*(-U0)
+            const double r6 = __ddiv_rn(rho, 6.0);
+            fp[11] = __dsub_rn(fp[11], __dmul_rn(r6, p.U0));
+            fp[12] = __dsub_rn(fp[12], __dmul_rn(r6, -p.U0));
+        }
+        AA_FOR_ALL(AA_PUSH)
+    }
 }
 
 #ifndef MGLC_HOST_SHIM

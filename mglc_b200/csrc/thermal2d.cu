@@ -62,6 +62,17 @@ extern "C" int mglc_t2d_desc_init(mglc_t2d_desc *d) {
     d->bcT[2] = d->bcT[3] = MGLC_BCT_ADIABATIC;
     d->Rayleigh = 1e7; d->Prandtl = 0.71; d->Mach = 0.1;                        // module.F90:31-33
     d->Thot = 1.0; d->Tcold = 0.0; d->Tref = 0.0; d->rho0 = 1.0;                // module.F90:67-68
+    d->variant = MGLC_T2D_MPI; d->lengthUnit = 0.0;                             // lengthUnit = dble(total_ny), module.F90:29
+    return MGLC_OK;
+}
+// the OpenACC program as shipped, seq/bouyancy2d_acc.F90 (the reference's only GPU code)
+extern "C" int mglc_t2d_desc_init_acc(mglc_t2d_desc *d) {
+    MGLC_TRY(mglc_t2d_desc_init(d));
+    d->total_nx = 513; d->total_ny = 257;                                       // acc:55
+    d->bcT[0] = d->bcT[1] = MGLC_BCT_PERIODIC;                                  // acc:15,22: VerticalWallsPeriodicalU / ...T
+    d->bcT[2] = MGLC_BCT_CONST_COLD; d->bcT[3] = MGLC_BCT_CONST_HOT;            // acc:19-20: RayleighBenardCell, HorizontalWallsConstT
+    d->Rayleigh = 1e5;                                                          // acc:59
+    d->variant = MGLC_T2D_ACC; d->lengthUnit = 513.0;                           // acc:57: lengthUnit = dble(nx)
     return MGLC_OK;
 }
 
@@ -114,7 +125,7 @@ static int t2_make_sub(mglc_t2d *h, int rank, int device, T2Sub **out) {
     S->nbr[2] = t2_cart_rank(h->dims, c0, c1 + 1); S->nbr[3] = t2_cart_rank(h->dims, c0, c1 - 1);
     for (int a = 5; a < 9; ++a) S->cnr[a - 5] = t2_cart_rank(h->dims, c0 + h_t2_ex[a], c1 + h_t2_ey[a]);
     S->g = make_geom2(S->n[0], S->n[1]);
-    S->g.wall[0] = c0 == h->dims[0] - 1; S->g.wall[1] = c0 == 0;
+    S->g.wall[0] = c0 == h->dims[0] - 1 && !h->p.perx; S->g.wall[1] = c0 == 0 && !h->p.perx;
     S->g.wall[2] = c1 == h->dims[1] - 1; S->g.wall[3] = c1 == 0;
     auto fail = [&](int rc) { t2_free_sub(S); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return fail(MGLC_E_CUDA); }
@@ -163,7 +174,16 @@ static int t2_new(mglc_t2d **out, const mglc_t2d_desc *d, const int dims_or_zero
         return MGLC_E_INVALID;
     }
     for (int f = 0; f < 4; ++f)
-        if (d->bcT[f] < MGLC_BCT_ADIABATIC || d->bcT[f] > MGLC_BCT_CONST_COLD) { set_error("mglc_t2d_create: bcT[%d]=%d", f, d->bcT[f]); return MGLC_E_INVALID; }
+        if (d->bcT[f] < MGLC_BCT_ADIABATIC || d->bcT[f] > MGLC_BCT_PERIODIC) { set_error("mglc_t2d_create: bcT[%d]=%d", f, d->bcT[f]); return MGLC_E_INVALID; }
+    const bool perx = d->bcT[0] == MGLC_BCT_PERIODIC || d->bcT[1] == MGLC_BCT_PERIODIC;
+    if ((perx && d->bcT[0] != d->bcT[1]) || d->bcT[2] == MGLC_BCT_PERIODIC || d->bcT[3] == MGLC_BCT_PERIODIC) {
+        set_error("mglc_t2d_create: MGLC_BCT_PERIODIC applies to both vertical walls together (seq/bouyancy2d_acc.F90:15,22)");
+        return MGLC_E_INVALID;
+    }
+    if ((d->variant != MGLC_T2D_MPI && d->variant != MGLC_T2D_ACC) || d->lengthUnit < 0.0) {
+        set_error("mglc_t2d_create: variant=%d lengthUnit=%g", d->variant, d->lengthUnit);
+        return MGLC_E_INVALID;
+    }
     MGLC_TRY(require_gpu());
     mglc_t2d *h = new mglc_t2d();
     h->d = *d; h->nranks = nranks; h->comm = nullptr;
@@ -174,8 +194,13 @@ static int t2_new(mglc_t2d **out, const mglc_t2d_desc *d, const int dims_or_zero
         delete h;
         return MGLC_E_INVALID;
     }
+    if (perx && h->dims[0] != 1) {
+        set_error("mglc_t2d_create: periodic vertical walls need an undivided x direction (dims %dx%d); split along y only", h->dims[0], h->dims[1]);
+        delete h;
+        return MGLC_E_INVALID;
+    }
     // module.F90:29,69-81 -- the same products in the same order
-    h->lengthUnit = (double)d->total_ny;
+    h->lengthUnit = d->lengthUnit > 0.0 ? d->lengthUnit : (double)d->total_ny;
     h->tauf = 0.5 + d->Mach * h->lengthUnit * sqrt(3.0 * d->Prandtl / d->Rayleigh);
     h->viscosity = (h->tauf - 0.5) / 3.0;
     h->diffusivity = h->viscosity / d->Prandtl;
@@ -193,8 +218,9 @@ static int t2_new(mglc_t2d **out, const mglc_t2d_desc *d, const int dims_or_zero
         delete h;
         return MGLC_E_INVALID;
     }
+    p.perx = perx; p.variant = d->variant;
     for (int f = 0; f < 4; ++f) {
-        p.bcT[f] = d->bcT[f];
+        p.bcT[f] = d->bcT[f] == MGLC_BCT_PERIODIC ? 0 : d->bcT[f];
         p.wallT[f] = (4.0 + p.paraA) / 10.0 * (d->bcT[f] == MGLC_BCT_CONST_HOT ? d->Thot : d->Tcold);    // evolution_g.F90:100,107,132,139
     }
     *out = h;
@@ -322,8 +348,8 @@ extern "C" int mglc_t2d_download(mglc_t2d *h, int r, double *f, double *f_post, 
 extern "C" int mglc_t2d_initial(mglc_t2d *h) {
     if (!h) return MGLC_E_INVALID;
     // #ifdef VerticalWallsConstT: T linear in x (initial.F90:252-261); #ifdef HorizontalWallsConstT: linear in y, applied after (:262-271)
-    const bool vertT = h->d.bcT[0] != MGLC_BCT_ADIABATIC || h->d.bcT[1] != MGLC_BCT_ADIABATIC;
-    const bool horT = h->d.bcT[2] != MGLC_BCT_ADIABATIC || h->d.bcT[3] != MGLC_BCT_ADIABATIC;
+    auto constT = [&](int f) { return h->d.bcT[f] == MGLC_BCT_CONST_HOT || h->d.bcT[f] == MGLC_BCT_CONST_COLD; };
+    const bool vertT = constT(0) || constT(1), horT = constT(2) || constT(3);
     const int profile = horT ? 2 : vertT ? 1 : 0;
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
@@ -422,7 +448,7 @@ extern "C" int mglc_t2d_bounceback(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         const int cells = 2 * S->n[0] + 2 * std::max(S->n[1] - 2, 0);
-        k_t2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, S->P[S->cur], S->F);
+        k_t2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p.perx, S->P[S->cur], S->F);
         S->launches += 1;
     }
     return MGLC_OK;

@@ -8,7 +8,9 @@ namespace mglc {
 struct T2Params {
     double Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, rho0, Thot, Tcold;   // module.F90:67-81
     double wallT[4];     // (4+paraA)/10 * T_wall per side (+x, -x, +y, -y), evolution_g.F90:99-140; used when bcT[side] != 0
-    int bcT[4];          // MGLC_BCT_ADIABATIC or a constant-temperature kind
+    int bcT[4];          // MGLC_BCT_ADIABATIC or a constant-temperature kind (0 for a periodic side)
+    int perx;            // 1 = vertical walls periodic for f and g (seq/bouyancy2d_acc.F90:777-791, 1037-1045); the subdomain spans x
+    int variant;         // MGLC_T2D_MPI | MGLC_T2D_ACC (collision() rounds f_post(0) term by term, acc:679)
 };
 
 // Fy is updated in place by the fused kernel (a cell reads and writes only its own entry); Fx is identically 0 after any

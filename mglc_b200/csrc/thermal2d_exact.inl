@@ -60,10 +60,15 @@ __device__ __forceinline__ bool t2_ring_cell(const Geom2 &g, int t, int &i, int 
 }
 
 // bounceback(): evolution_f.F90:283-321 (left, right, bottom, top; all half-way bounce-back)
-__global__ void __launch_bounds__(128) k_t2_bounceback(Geom2 g, const double *__restrict__ Fpost, double *__restrict__ F) {
+__global__ void __launch_bounds__(128) k_t2_bounceback(Geom2 g, int perx, const double *__restrict__ Fpost, double *__restrict__ F) {
     int i, j;
     if (!t2_ring_cell(g, blockIdx.x * blockDim.x + threadIdx.x, i, j)) return;
     const long long c = g.idx(0, i, j), sq = g.sq;
+    if (perx) {   // VerticalWallsPeriodicalU, seq/bouyancy2d_acc.F90:777-791 (before the horizontal walls, like the reference)
+        const long long wrap = g.nx - 1;
+        if (i == 1) { F[1 * sq + c] = Fpost[1 * sq + c + wrap]; F[5 * sq + c] = Fpost[5 * sq + c + wrap]; F[8 * sq + c] = Fpost[8 * sq + c + wrap]; }
+        if (i == g.nx) { F[3 * sq + c] = Fpost[3 * sq + c - wrap]; F[6 * sq + c] = Fpost[6 * sq + c - wrap]; F[7 * sq + c] = Fpost[7 * sq + c - wrap]; }
+    }
     if (g.wall[1] && i == 1) { F[1 * sq + c] = Fpost[3 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[8 * sq + c] = Fpost[6 * sq + c]; }
     if (g.wall[0] && i == g.nx) { F[3 * sq + c] = Fpost[1 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; F[7 * sq + c] = Fpost[5 * sq + c]; }
     if (g.wall[3] && j == 1) { F[2 * sq + c] = Fpost[4 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; }
@@ -75,6 +80,10 @@ __global__ void __launch_bounds__(128) k_t2_bouncebackT(Geom2 g, T2Params p, con
     int i, j;
     if (!t2_ring_cell(g, blockIdx.x * blockDim.x + threadIdx.x, i, j)) return;
     const long long c = g.idx(0, i, j), sq = g.sq;
+    if (p.perx) {   // VerticalWallsPeriodicalT, seq/bouyancy2d_acc.F90:1037-1045
+        if (i == 1) G[1 * sq + c] = Gpost[1 * sq + c + (g.nx - 1)];
+        if (i == g.nx) G[3 * sq + c] = Gpost[3 * sq + c - (g.nx - 1)];
+    }
     if (g.wall[3] && j == 1) G[2 * sq + c] = p.bcT[3] ? -Gpost[4 * sq + c] + p.wallT[3] : Gpost[4 * sq + c];
     if (g.wall[2] && j == g.ny) G[4 * sq + c] = p.bcT[2] ? -Gpost[2 * sq + c] + p.wallT[2] : Gpost[2 * sq + c];
     if (g.wall[1] && i == 1) G[1 * sq + c] = p.bcT[1] ? -Gpost[3 * sq + c] + p.wallT[1] : Gpost[3 * sq + c];

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(128) k_t2_collision(Geom2 g, T2Params p, const
     double f[9], fp[9], fy;
 #pragma unroll
     for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
-    t2_collide(f, rho[m], u[m], v[m], T[m], p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
+    if (p.variant) t2_collide<true>(f, rho[m], u[m], v[m], T[m], p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
+    else t2_collide<false>(f, rho[m], u[m], v[m], T[m], p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
 #pragma unroll
     for (int a = 0; a < 9; ++a) Fpost[a * g.sq + c] = fp[a];
     Fx[m] = 0.0; Fy[m] = fy;
@@ -55,23 +56,29 @@ __device__ __forceinline__ void t2_pull_macro(const Geom2 &g, const T2Params &p,
                                               double &rho, double &u, double &v, double &T) {
     const long long c = g.idx(0, i, j), sy = g.sy, sq = g.sq;
     const bool xp = g.wall[0] && i == g.nx, xm = g.wall[1] && i == 1, yp = g.wall[2] && j == g.ny, ym = g.wall[3] && j == 1;
+    // periodic vertical walls (acc:777-791): a population entering through x takes the SAME population from the SAME row of
+    // the opposite column (also the diagonal ones); the horizontal walls are processed afterwards and win in the corner cells
+    const bool pxm = p.perx && i == 1, pxp = p.perx && i == g.nx;
+    const long long wrap = g.nx - 1;
 #define T2_PULL(a, o, dx, dy)                                                                                       \
     {                                                                                                               \
         const bool wall_ = ((dx) == 1 && xm) || ((dx) == -1 && xp) || ((dy) == 1 && ym) || ((dy) == -1 && yp);     \
-        f[a] = __ldg(Fin + (wall_ ? (o) * sq + c : (a) * sq + (c - (dy) * sy - (dx))));                             \
+        const bool per_ = ((dx) == 1 && pxm) || ((dx) == -1 && pxp);                                                \
+        f[a] = __ldg(Fin + (wall_ ? (o) * sq + c : per_ ? (a) * sq + (c + (dx) * wrap) : (a) * sq + (c - (dy) * sy - (dx)))); \
     }
     f[0] = __ldg(Fin + c);
     T2_PULL(1, 3, 1, 0) T2_PULL(2, 4, 0, 1) T2_PULL(3, 1, -1, 0) T2_PULL(4, 2, 0, -1)
     T2_PULL(5, 7, 1, 1) T2_PULL(6, 8, -1, 1) T2_PULL(7, 5, -1, -1) T2_PULL(8, 6, 1, -1)
 #undef T2_PULL
     // side: 0 = +x wall (population 3 comes off it), 1 = -x (1), 2 = +y (4), 3 = -y (2)
-#define T2_PULLG(a, o, off, hit, side)                                                                              \
+#define T2_PULLG(a, o, off, hit, side, per, pwrap)                                                                  \
     {                                                                                                               \
-        const double raw_ = __ldg(Gin + ((hit) ? (o) * sq + c : (a) * sq + (c - (off))));                           \
+        const double raw_ = __ldg(Gin + ((hit) ? (o) * sq + c : (per) ? (a) * sq + (c + (pwrap)) : (a) * sq + (c - (off)))); \
         gg[a] = ((hit) && p.bcT[side]) ? __dadd_rn(-raw_, p.wallT[side]) : raw_;                                    \
     }
     gg[0] = __ldg(Gin + c);
-    T2_PULLG(1, 3, 1, xm, 1) T2_PULLG(2, 4, sy, ym, 3) T2_PULLG(3, 1, -1, xp, 0) T2_PULLG(4, 2, -sy, yp, 2)
+    T2_PULLG(1, 3, 1, xm, 1, pxm, wrap) T2_PULLG(2, 4, sy, ym, 3, false, 0) T2_PULLG(3, 1, -1, xp, 0, pxp, -wrap)
+    T2_PULLG(4, 2, -sy, yp, 2, false, 0)
 #undef T2_PULLG
     t2_macro_cell(f, gg, 0.0, Fy, rho, u, v, T);
 }
@@ -83,7 +90,8 @@ __global__ void __launch_bounds__(128) k_t2_fused(Geom2 g, T2Params p, const dou
     const long long c = g.idx(0, i, j), m = g.cell(i, j);
     double f[9], gg[5], fp[9], gp[5], rho, u, v, T, fy;
     t2_pull_macro(g, p, Fin, Gin, Fy[m], i, j, f, gg, rho, u, v, T);
-    t2_collide(f, rho, u, v, T, p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
+    if (p.variant) t2_collide<true>(f, rho, u, v, T, p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
+    else t2_collide<false>(f, rho, u, v, T, p.Snu, p.Sq, p.gBeta, p.Tref, fp, fy);
     t2_collideT(gg, u, v, T, p.Qd, p.Qnu, p.paraA, gp);
 #pragma unroll
     for (int a = 0; a < 9; ++a) Fout[a * g.sq + c] = fp[a];

@@ -10,6 +10,7 @@ from . import _lib as L
 
 SIDE_HEATED = (L.BCT_CONST_COLD, L.BCT_CONST_HOT, L.BCT_ADIABATIC, L.BCT_ADIABATIC)      # +x, -x, +y, -y   macros.F90:24-27
 RAYLEIGH_BENARD = (L.BCT_ADIABATIC, L.BCT_ADIABATIC, L.BCT_CONST_COLD, L.BCT_CONST_HOT)  # macros.F90:17-20
+RB_PERIODIC = (L.BCT_PERIODIC, L.BCT_PERIODIC, L.BCT_CONST_COLD, L.BCT_CONST_HOT)        # seq/bouyancy2d_acc.F90:13-22 (the OpenACC program)
 PARAM_NAMES = ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu", "lengthUnit")
 
 
@@ -18,10 +19,17 @@ class BuoyancyDrivenCavity2D:
     _LATTICES = ("f", "f_post", "g", "g_post")
     _FIELDS = ("rho", "u", "v", "T", "Fx", "Fy")
 
-    def __init__(self, total=None, nprocs=1, dims=None, bcT=None, strict=False, devices=None, comm=None, device=0, **params):
+    def __init__(self, total=None, nprocs=1, dims=None, bcT=None, strict=False, devices=None, comm=None, device=0, variant="mpi",
+                 lengthUnit=None, **params):
+        """variant "mpi": mpi_blocked/ (201 x 201, Ra 1e7, side-heated); "acc": the OpenACC program seq/bouyancy2d_acc.F90
+        (513 x 257, Ra 1e5, Rayleigh-Benard plates, periodic vertical walls, lengthUnit = nx) -- each with its shipped defaults"""
         lib = L.lib()
         d = L.T2dDesc()
-        L.check(lib.mglc_t2d_desc_init(C.byref(d)))
+        L.check((lib.mglc_t2d_desc_init_acc if variant == "acc" else lib.mglc_t2d_desc_init)(C.byref(d)))
+        if variant == "acc" and total is not None and lengthUnit is None:
+            lengthUnit = float(total[0])              # acc:57: lengthUnit = dble(nx)
+        if lengthUnit is not None:
+            d.lengthUnit = lengthUnit
         if total is not None:
             d.total_nx, d.total_ny = total
         if bcT is not None:
@@ -31,7 +39,7 @@ class BuoyancyDrivenCavity2D:
                 raise TypeError(f"unknown parameter {k}")
             setattr(d, k, v)
         d.arith = L.ARITH_STRICT if strict else L.ARITH_FAST
-        self.desc, self.total, self.bcT = d, (d.total_nx, d.total_ny), tuple(d.bcT)
+        self.desc, self.total, self.bcT, self.variant = d, (d.total_nx, d.total_ny), tuple(d.bcT), variant
         dz = (C.c_int * 2)(*(dims if dims else (0, 0)))
         self._h = C.c_void_p()
         if comm is not None:

@@ -60,7 +60,7 @@ void to_aos(const Geom2 &g, int nq, const std::vector<double> &P, double *aos) {
 }  // namespace
 
 extern "C" {
-// par = Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, rho0, Thot, Tcold ; wallT[4], bcT[4], wall[4] as in T2Params / Geom2.
+// par = Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, rho0, Thot, Tcold, perx, variant ; wallT[4], bcT[4], wall[4] as in T2Params / Geom2.
 // mode 0: k_t2_fused         f_post, g_post (halo'd, in) -> f_post_out, g_post_out (halo'd, interior written), Fy in place
 // mode 1: k_t2_stream_macro  f_post, g_post -> f_out, g_out (halo'd arrays, interior written), rho,u,v,T (nx*ny each, in fields4)
 // mode 2: k_t2_collision + k_t2_collisionT: f_post/g_post hold f/g (halo'd arrays, interior used), fields4 = rho,u,v,T in;
@@ -71,7 +71,7 @@ int shim_t2d(int mode, int strict_build, int nx, int ny, const int *wall, const 
     for (int q = 0; q < 4; ++q) g.wall[q] = wall[q];
     T2Params p{};
     p.Snu = par[0]; p.Sq = par[1]; p.Qd = par[2]; p.Qnu = par[3]; p.paraA = par[4]; p.gBeta = par[5]; p.Tref = par[6]; p.rho0 = par[7];
-    p.Thot = par[8]; p.Tcold = par[9];
+    p.Thot = par[8]; p.Tcold = par[9]; p.perx = (int)par[10]; p.variant = (int)par[11];
     for (int q = 0; q < 4; ++q) { p.wallT[q] = wallT[q]; p.bcT[q] = bcT[q]; }
     std::vector<double> Fi, Gi, Fo((size_t)9 * g.sq, 0.0), Go((size_t)5 * g.sq, 0.0);
     to_soa(g, 9, fin, Fi); to_soa(g, 5, gin, Gi);
@@ -132,7 +132,7 @@ void *shim_sub_create(int nx, int ny, const int *wall, const double *par, const 
     T2Params &p = S->p;
     p = T2Params{};
     p.Snu = par[0]; p.Sq = par[1]; p.Qd = par[2]; p.Qnu = par[3]; p.paraA = par[4]; p.gBeta = par[5]; p.Tref = par[6]; p.rho0 = par[7];
-    p.Thot = par[8]; p.Tcold = par[9];
+    p.Thot = par[8]; p.Tcold = par[9]; p.perx = (int)par[10]; p.variant = (int)par[11];
     for (int q = 0; q < 4; ++q) { p.wallT[q] = wallT[q]; p.bcT[q] = bcT[q]; }
     S->F.assign((size_t)9 * S->g.sq, 0.0); S->P.assign((size_t)9 * S->g.sq, 0.0);
     S->G.assign((size_t)5 * S->g.sq, 0.0); S->Q.assign((size_t)5 * S->g.sq, 0.0);
@@ -177,7 +177,7 @@ int shim_sub_op(void *h, int op, int a0, int a1, int a2) {
             std::fill(S->P.begin(), S->P.end(), 0.0); std::fill(S->Q.begin(), S->Q.end(), 0.0); break;
     case 1: sweep_grid(gx, g.ny, 128, [&] { k_t2_streaming(g, 9, S->P.data(), S->F.data()); }); break;
     case 2: sweep_grid(gx, g.ny, 128, [&] { k_t2_streaming(g, 5, S->Q.data(), S->G.data()); }); break;
-    case 3: sweep_grid(ring, 1, 128, [&] { k_t2_bounceback(g, S->P.data(), S->F.data()); }); break;
+    case 3: sweep_grid(ring, 1, 128, [&] { k_t2_bounceback(g, S->p.perx, S->P.data(), S->F.data()); }); break;
     case 4: sweep_grid(ring, 1, 128, [&] { k_t2_bouncebackT(g, S->p, S->Q.data(), S->G.data()); }); break;
     case 5: sweep_grid(gx, g.ny, 128, [&] { k_t2_macro(g, S->F.data(), Fx, Fy, rho, u, v); }); break;
     case 6: sweep_grid(gx, g.ny, 128, [&] { k_t2_macroT(g, S->G.data(), T); }); break;

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import mglc_b200 as mg
-from mglc_b200.thermal2d import PARAM_NAMES, RAYLEIGH_BENARD, SIDE_HEATED
+from mglc_b200.thermal2d import PARAM_NAMES, RAYLEIGH_BENARD, RB_PERIODIC, SIDE_HEATED
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -38,9 +38,10 @@ def seeded_state(total, seed):
     return {k: np.asfortranarray(a) for k, a in out.items()}
 
 
-def pair(total, nprocs=1, dims=None, bcT=None, strict=True, seed=None, **params):
-    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=bcT, **params)
-    sim = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, bcT=bcT, strict=strict, **params)
+def pair(total, nprocs=1, dims=None, bcT=None, strict=True, seed=None, variant="mpi", **params):
+    lu = float(total[0]) if variant == "acc" else 0.0                 # the OpenACC program's lengthUnit = dble(nx), acc:57
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=bcT, variant=variant, lengthUnit=lu, **params)
+    sim = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, bcT=bcT, strict=strict, variant=variant, **params)
     assert sim.dims == wd.dims and sim.bcT == wd.bcT
     for k in PARAM_NAMES:
         assert sim.params[k] == getattr(wd.params, k), k
@@ -269,6 +270,70 @@ def test_decomposed_equals_single_subdomain_bit_for_bit(strict, nprocs, dims):
     one.close(); many.close()
 
 
+# ---------------- the OpenACC program (seq/bouyancy2d_acc.F90): periodic vertical walls, its own rounding of f_post(0) ----------------
+def test_acc_shipped_constants_and_golden_cells():
+    sim = mg.BuoyancyDrivenCavity2D(variant="acc", strict=True)
+    assert sim.total == (513, 257) and sim.bcT == RB_PERIODIC and sim.params["lengthUnit"] == 513.0
+    assert tuple(sim.params[k] for k in PARAM_NAMES[:9]) == tuple(GOLD["acc/params"])
+    f, g, r = GOLD["cells/f"], GOLD["cells/g"], GOLD["cells/ruvT"]
+    n, (nx, ny) = len(f), sim.total
+    pad = np.arange(nx * ny) % n
+    shp = lambda a: np.asfortranarray(a[pad].reshape(nx, ny, order="F"))
+    sim.upload(0, f=np.asfortranarray(f[pad].T.reshape(9, nx, ny, order="F")), g=np.asfortranarray(g[pad].T.reshape(5, nx, ny, order="F")),
+               rho=shp(r[:, 0]), u=shp(r[:, 1]), v=shp(r[:, 2]), T=shp(r[:, 3]))
+    sim.collision(); sim.collisionT()
+    fp = sim.download(0, "f_post")[:, 1:-1, 1:-1].reshape(9, -1, order="F").T
+    gp = sim.download(0, "g_post")[:, 1:-1, 1:-1].reshape(5, -1, order="F").T
+    assert np.array_equal(fp, GOLD["acc/collision_f_post"][pad]) and np.array_equal(gp, GOLD["acc/collisionT_g_post"][pad])
+    assert not np.array_equal(fp, GOLD["collision/f_post"][pad])          # not the MPI program's bits
+    sim.close()
+
+
+def test_acc_periodic_walls_on_the_golden_block():
+    nx, ny = 6, 5
+    sim = mg.BuoyancyDrivenCavity2D((nx, ny), variant="acc", lengthUnit=513.0, strict=True, Rayleigh=1e5)
+    assert sim.params["paraA"] == GOLD["acc/params"][3]
+    sim.upload(0, f_post=GOLD["field/f_post"], g_post=GOLD["field/g_post"])
+    sim.streaming(); sim.streamingT()
+    assert np.array_equal(sim.download(0, "f"), GOLD["acc/streaming_f"]) and np.array_equal(sim.download(0, "g"), GOLD["acc/streamingT_g"])
+    sim.upload(0, f=GOLD["field/f0"], g=GOLD["field/g0"])
+    sim.bounceback(); sim.bouncebackT()
+    assert np.array_equal(sim.download(0, "f"), GOLD["acc/bounceback_f"]) and np.array_equal(sim.download(0, "g"), GOLD["acc/bouncebackT_g"])
+    sim.close()
+
+
+@pytest.mark.parametrize("total,nprocs,dims", [((34, 33), 1, None), ((23, 19), 3, (1, 3)), ((130, 6), 2, (1, 2)), ((513, 257), 1, None)])
+def test_acc_fused_step_strict_is_bit_exact(total, nprocs, dims):
+    """the OpenACC program's loop (acc:165-187) through the fused kernel, split along y only (x must stay whole to wrap)"""
+    wd, sim = pair(total, nprocs, dims, bcT=RB_PERIODIC, strict=True, variant="acc", Rayleigh=1e5)
+    for n in (1, 2, 17):
+        wd.step(n); sim.step(n)
+        assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+        assert_rank_arrays_equal(wd, sim, ("f_post", "g_post"), interior_only_post=True)
+    wd.collision(); sim.collision(); wd.message_passing_f(); sim.message_passing_f()
+    wd.streaming(); sim.streaming(); wd.bounceback(); sim.bounceback()
+    wd.collisionT(); sim.collisionT(); wd.message_passing_g(); sim.message_passing_g()
+    wd.streamingT(); sim.streamingT(); wd.bouncebackT(); sim.bouncebackT()
+    wd.macro(); sim.macro(); wd.macroT(); sim.macroT()
+    assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+    wd.step(3); sim.step(3)
+    assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+    wd.close(); sim.close()
+
+
+def test_acc_shipped_case_fast_within_tolerance():
+    """513 x 257, Ra = 1e5, N in {1, 10, 100, 1000}: the OpenACC program's own configuration in the throughput arithmetic"""
+    wd, sim = pair((513, 257), 1, bcT=RB_PERIODIC, strict=False, variant="acc", Rayleigh=1e5)
+    done = 0
+    for n in (1, 10, 100, 1000):
+        wd.step(n - done); sim.step(n - done); done = n
+        for k in FIELDS:
+            assert close_enough(sim.gather(k), wd.gather(k), floor=velocity_floor(wd) if k in ("u", "v") else 0.0), (n, k)
+    a, b = sim.check(), wd.check()
+    assert np.isclose(a[0], b[0], rtol=1e-9) and np.isclose(a[1], b[1], rtol=1e-9)
+    wd.close(); sim.close()
+
+
 def test_large_lattice_properties():
     """4096 x 4096 (no oracle run).  Side-heated: total mass constant to rounding, T bounded, four subdomains == one bit for bit.
     Rayleigh-Benard set: the initial state does not depend on x, so for N steps every column farther than N cells from the side
@@ -303,6 +368,10 @@ def test_error_behaviour():
         mg.BuoyancyDrivenCavity2D((2, 8), nprocs=4, dims=(4, 1))
     with pytest.raises(mg.MglcError):
         mg.BuoyancyDrivenCavity2D((8, 8), bcT=(0, 0, 0, 7))
+    with pytest.raises(mg.MglcError):                       # periodic vertical walls cannot be split along x
+        mg.BuoyancyDrivenCavity2D((16, 16), nprocs=2, dims=(2, 1), bcT=RB_PERIODIC)
+    with pytest.raises(mg.MglcError):                       # ... and come in pairs
+        mg.BuoyancyDrivenCavity2D((16, 16), bcT=(3, 0, 2, 1))
     with pytest.raises(mg.MglcError):                       # the reference stops when paraA leaves (-4, 1): initial.F90:30
         mg.BuoyancyDrivenCavity2D((4001, 4001), Rayleigh=1e3, Mach=0.3)
     sim = mg.BuoyancyDrivenCavity2D((8, 8))

@@ -30,10 +30,7 @@ def shim(tmp_path_factory):
 def run_shim(S, w, R, mode, strict, fin, gin, Fy, fields=None):
     p = w.params
     nx, ny = R.n
-    wall = (C.c_int * 4)(R.coords[0] == w.dims[0] - 1, R.coords[0] == 0, R.coords[1] == w.dims[1] - 1, R.coords[1] == 0)
-    par = (C.c_double * 10)(p.Snu, p.Sq, p.Qd, p.Qnu, p.paraA, p.gBeta, p.Tref, p.rho0, p.Thot, p.Tcold)
-    wallT = (C.c_double * 4)(*[(4.0 + p.paraA) / 10.0 * (p.Thot if k == orc.T2_CONST_HOT else p.Tcold) for k in w.bcT])
-    bcT = (C.c_int * 4)(*w.bcT)
+    wall, par, wallT, bcT = shim_params(w, R)
     fin, gin = np.asfortranarray(fin), np.asfortranarray(gin)
     fout, gout = np.zeros((9, nx + 2, ny + 2), order="F"), np.zeros((5, nx + 2, ny + 2), order="F")
     Fy = np.asfortranarray(Fy.copy())
@@ -44,6 +41,17 @@ def run_shim(S, w, R, mode, strict, fin, gin, Fy, fields=None):
     return fout, gout, Fy, [fl[q].reshape((nx, ny), order="F") for q in range(4)]
 
 
+def shim_params(w, R):
+    """Geom2.wall, T2Params as thermal2d.cu fills them (periodic vertical sides are not walls and carry no thermal kind)"""
+    p = w.params
+    perx = orc.T2_PERIODIC in w.bcT
+    wall = (C.c_int * 4)(R.coords[0] == w.dims[0] - 1 and not perx, R.coords[0] == 0 and not perx, R.coords[1] == w.dims[1] - 1, R.coords[1] == 0)
+    par = (C.c_double * 12)(p.Snu, p.Sq, p.Qd, p.Qnu, p.paraA, p.gBeta, p.Tref, p.rho0, p.Thot, p.Tcold, float(perx), float(w.variant == "acc"))
+    wallT = (C.c_double * 4)(*[(4.0 + p.paraA) / 10.0 * (p.Thot if k == orc.T2_CONST_HOT else p.Tcold) for k in w.bcT])
+    bcT = (C.c_int * 4)(*[0 if k == orc.T2_PERIODIC else k for k in w.bcT])
+    return wall, par, wallT, bcT
+
+
 def padded(a):
     """interior array (q, nx, ny) -> halo'd (q, nx+2, ny+2) with NaN halos (the kernels must not read them)"""
     out = np.full((a.shape[0], a.shape[1] + 2, a.shape[2] + 2), np.nan, order="F")
@@ -51,14 +59,21 @@ def padded(a):
     return out
 
 
-CASES = [((1, 1), orc.T2_SIDE_HEATED), ((2, 2), orc.T2_SIDE_HEATED), ((3, 3), orc.T2_RAYLEIGH_BENARD), ((1, 3), (2, 1, 1, 2)), ((3, 1), (0, 0, 0, 0))]
+CASES = [((1, 1), orc.T2_SIDE_HEATED), ((2, 2), orc.T2_SIDE_HEATED), ((3, 3), orc.T2_RAYLEIGH_BENARD), ((1, 3), (2, 1, 1, 2)), ((3, 1), (0, 0, 0, 0)),
+         ((1, 1), orc.T2_RB_PERIODIC), ((1, 3), orc.T2_RB_PERIODIC)]      # the OpenACC program's set: periodic vertical walls, acc arithmetic
+
+
+def world_for(total, dims, bcT, **kw):
+    acc = orc.T2_PERIODIC in bcT
+    return orc.Thermal2DWorld(total, nprocs=dims[0] * dims[1], dims=dims, bcT=bcT, variant="acc" if acc else "mpi",
+                              lengthUnit=float(total[0]) if acc else 0.0, **kw)
 
 
 @pytest.mark.parametrize("dims,bcT", CASES)
 @pytest.mark.parametrize("strict", [True, False])
 def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, strict):
     """k_t2_fused on every rank == streaming .. macroT of this step + collision/collisionT of the next (oracle), wall halos poisoned"""
-    w = orc.Thermal2DWorld((23, 19), nprocs=dims[0] * dims[1], dims=dims, bcT=bcT, Rayleigh=1e6)
+    w = world_for((23, 19), dims, bcT, Rayleigh=1e6)
     w.initial()
     w.step(30)
     w.collision(); w.message_passing_f(); w.collisionT(); w.message_passing_g()          # rotated-loop state: halos valid
@@ -66,7 +81,7 @@ def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, strict)
     for R in w.ranks:
         fp, gp = R.f_post.copy(), R.g_post.copy()
         # poison the halo entries no message fills (physical walls and the unused corners): the kernel must never read them
-        if R.coords[0] == 0: fp[:, 0, :] = gp[:, 0, :] = np.nan
+        if R.coords[0] == 0: fp[:, 0, :] = gp[:, 0, :] = np.nan                   # (periodic sides: the wrap reads column nx, never the halo)
         if R.coords[0] == dims[0] - 1: fp[:, -1, :] = gp[:, -1, :] = np.nan
         if R.coords[1] == 0: fp[:, :, 0] = gp[:, :, 0] = np.nan
         if R.coords[1] == dims[1] - 1: fp[:, :, -1] = gp[:, :, -1] = np.nan
@@ -148,12 +163,8 @@ class ShimWorld:
         S.shim_sub_op.argtypes = [C.c_void_p] + [C.c_int] * 4
         S.shim_sub_pack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
         S.shim_sub_unpack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
-        p = w.params
-        par = (C.c_double * 10)(p.Snu, p.Sq, p.Qd, p.Qnu, p.paraA, p.gBeta, p.Tref, p.rho0, p.Thot, p.Tcold)
-        wallT = (C.c_double * 4)(*[(4.0 + p.paraA) / 10.0 * (p.Thot if k == orc.T2_CONST_HOT else p.Tcold) for k in w.bcT])
-        bcT = (C.c_int * 4)(*w.bcT)
         for R in w.ranks:
-            wall = (C.c_int * 4)(R.coords[0] == w.dims[0] - 1, R.coords[0] == 0, R.coords[1] == w.dims[1] - 1, R.coords[1] == 0)
+            wall, par, wallT, bcT = shim_params(w, R)
             self.subs.append(S.shim_sub_create(R.n[0], R.n[1], wall, par, wallT, bcT))
 
     def close(self):
@@ -181,8 +192,8 @@ class ShimWorld:
 
     def initial(self):
         w = self.w
-        vert = w.bcT[0] != 0 or w.bcT[1] != 0
-        hor = w.bcT[2] != 0 or w.bcT[3] != 0
+        isT = [k in (orc.T2_CONST_HOT, orc.T2_CONST_COLD) for k in w.bcT]
+        vert, hor = isT[0] or isT[1], isT[2] or isT[3]
         profile = 2 if hor else 1 if vert else 0
         for h, R in zip(self.subs, w.ranks):
             axis = 1 if profile == 2 else 0
@@ -215,7 +226,7 @@ class ShimWorld:
 @pytest.mark.parametrize("dims,bcT", CASES + [((2, 3), (2, 1, 1, 2))])
 def test_exact_kernel_sources_follow_the_oracle_subroutine_by_subroutine(shim, dims, bcT):
     total = (23, 19)
-    w = orc.Thermal2DWorld(total, nprocs=dims[0] * dims[1], dims=dims, bcT=bcT, Rayleigh=1e6, Thot=0.75, Tcold=-0.25)
+    w = world_for(total, dims, bcT, Rayleigh=1e6, Thot=0.75, Tcold=-0.25)
     sw = ShimWorld(shim, w)
     P = range(w.nprocs)
 
