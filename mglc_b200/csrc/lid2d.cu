@@ -195,7 +195,13 @@ struct L2Sub {
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
     Msg msgs[8];
     long long launches;
+    cudaGraphExec_t gexec[2];      // L2_GRAPH_STEPS fused launches starting from cur = 0 / 1 (small single-subdomain lattices)
 };
+
+// The shipped 200 x 200 / 201 x 201 lattices fit the L2 and are bounded by kernel-launch latency, not by HBM: such runs replay
+// the fused launches as CUDA graphs of L2_GRAPH_STEPS kernels (an even count: the ping-pong and lid-row indices return).
+constexpr int L2_GRAPH_STEPS = 64;
+constexpr long long L2_GRAPH_MAX_CELLS = 1LL << 22;
 
 }  // namespace
 
@@ -230,6 +236,7 @@ static void l2_free_sub(L2Sub *S) {
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
     cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (cudaGraphExec_t e : S->gexec) if (e) cudaGraphExecDestroy(e);
     if (S->s) cudaStreamDestroy(S->s);
     (void)cudaGetLastError();
     delete S;
@@ -544,8 +551,31 @@ static int l2_step_impl(mglc_l2d *h, int nsteps) {
         if (S->g.wall[2]) { k_l2_lid_row<<<(S->n[0] + 127) / 128, 128, 0, S->s>>>(S->g, S->rho, S->lid[0]); S->launches += 1; }
     }
     MGLC_TRY(l2_collision(h));
-    int lid = 0;
-    for (int it = 1; it < nsteps; ++it) {
+    int lid = 0, it = 1;
+    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= L2_GRAPH_MAX_CELLS) {
+        L2Sub *S = h->subs[0];
+        MGLC_TRY(l2_use(S));
+        auto fused = strict_build ? strict::launch_l2_fused : fast::launch_l2_fused;
+        // every run starts with lid = 0, so a graph is determined by the ping-pong index it starts from
+        while (nsteps - it >= L2_GRAPH_STEPS) {
+            cudaGraphExec_t &ge = S->gexec[S->cur];
+            if (!ge) {
+                cudaGraph_t gr = nullptr;
+                MGLC_CUDA(cudaStreamBeginCapture(S->s, cudaStreamCaptureModeRelaxed));
+                int c = S->cur, l = 0;
+                for (int q = 0; q < L2_GRAPH_STEPS; ++q, c ^= 1, l ^= 1) fused(S->g, h->p, h->d.variant, S->P[c], S->P[c ^ 1], S->lid[l], S->lid[l ^ 1], S->s);
+                const cudaError_t ce = cudaStreamEndCapture(S->s, &gr);
+                if (ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); (void)cudaGetLastError(); set_error("mglc_l2d_step: graph capture failed: %s", cudaGetErrorString(ce)); return MGLC_E_CUDA; }
+                const cudaError_t ie = cudaGraphInstantiate(&ge, gr, 0);
+                cudaGraphDestroy(gr);
+                if (ie != cudaSuccess) { ge = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return MGLC_E_CUDA; }
+            }
+            MGLC_CUDA(cudaGraphLaunch(ge, S->s));
+            S->launches += L2_GRAPH_STEPS;
+            it += L2_GRAPH_STEPS;
+        }
+    }
+    for (; it < nsteps; ++it) {
         MGLC_TRY(l2_exchange(h));
         for (L2Sub *S : h->subs) {
             MGLC_TRY(l2_use(S));

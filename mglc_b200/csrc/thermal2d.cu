@@ -39,7 +39,13 @@ struct T2Sub {
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
     Msg msgs[T2_NMSG];
     long long launches;
+    cudaGraphExec_t gexec[2];      // T2_GRAPH_STEPS fused launches starting from cur = 0 / 1 (small single-subdomain lattices)
 };
+
+// A lattice that fits the L2 (the shipped 201 x 201 and 513 x 257 cases) is bounded by kernel-launch latency, not by HBM:
+// such runs replay the fused launches as CUDA graphs of T2_GRAPH_STEPS kernels (an even count: the ping-pong index returns).
+constexpr int T2_GRAPH_STEPS = 64;
+constexpr long long T2_GRAPH_MAX_CELLS = 1LL << 22;
 
 }  // namespace
 
@@ -88,6 +94,7 @@ static void t2_free_sub(T2Sub *S) {
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
     cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (cudaGraphExec_t e : S->gexec) if (e) cudaGraphExecDestroy(e);
     if (S->s) cudaStreamDestroy(S->s);
     (void)cudaGetLastError();
     delete S;
@@ -492,7 +499,30 @@ static int t2_step_impl(mglc_t2d *h, int nsteps) {
     const bool strict_build = h->d.arith == MGLC_ARITH_STRICT;
     MGLC_TRY(t2_collision(h));
     MGLC_TRY(t2_collisionT(h));
-    for (int it = 1; it < nsteps; ++it) {
+    int it = 1;
+    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= T2_GRAPH_MAX_CELLS) {
+        T2Sub *S = h->subs[0];
+        MGLC_TRY(t2_use(S));
+        auto fused = strict_build ? strict::launch_t2_fused : fast::launch_t2_fused;
+        while (nsteps - it >= T2_GRAPH_STEPS) {
+            cudaGraphExec_t &ge = S->gexec[S->cur];
+            if (!ge) {
+                cudaGraph_t gr = nullptr;
+                MGLC_CUDA(cudaStreamBeginCapture(S->s, cudaStreamCaptureModeRelaxed));
+                int c = S->cur;
+                for (int q = 0; q < T2_GRAPH_STEPS; ++q, c ^= 1) fused(S->g, h->p, S->P[c], S->P[c ^ 1], S->Q[c], S->Q[c ^ 1], S->Fy, S->s);
+                const cudaError_t ce = cudaStreamEndCapture(S->s, &gr);
+                if (ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); (void)cudaGetLastError(); set_error("mglc_t2d_step: graph capture failed: %s", cudaGetErrorString(ce)); return MGLC_E_CUDA; }
+                const cudaError_t ie = cudaGraphInstantiate(&ge, gr, 0);
+                cudaGraphDestroy(gr);
+                if (ie != cudaSuccess) { ge = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return MGLC_E_CUDA; }
+            }
+            MGLC_CUDA(cudaGraphLaunch(ge, S->s));
+            S->launches += T2_GRAPH_STEPS;
+            it += T2_GRAPH_STEPS;
+        }
+    }
+    for (; it < nsteps; ++it) {
         MGLC_TRY(t2_exchange(h, 3));
         for (T2Sub *S : h->subs) {
             MGLC_TRY(t2_use(S));

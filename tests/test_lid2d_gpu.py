@@ -149,6 +149,17 @@ def test_fused_step_strict_is_bit_exact(variant, total, nprocs, dims):
     wd.close(); sim.close()
 
 
+@pytest.mark.parametrize("variant", ["c", "f"])
+def test_graph_replayed_steps_strict_are_bit_exact(variant):
+    """a single small subdomain replays its fused launches as CUDA graphs of 64 kernels (the lid-row side buffers alternate
+    inside the graph): 1 + 2 x 64 + 7 steps, then 64 + 1 more from the other ping-pong index, bit for bit"""
+    wd, sim = pair((45, 38), 1, variant=variant, strict=True)
+    for n in (136, 65):
+        wd.step(n); sim.step(n)
+        assert_rank_arrays_equal(wd, sim, ("f", "rho", "u", "v"))
+    wd.close(); sim.close()
+
+
 def test_wall_halos_are_never_read_by_the_fused_step():
     wd, sim = pair((31, 17), 4, strict=True)
     for r in range(4):

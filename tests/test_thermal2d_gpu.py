@@ -220,6 +220,19 @@ def test_fused_step_strict_is_bit_exact(bcT, total, nprocs, dims):
     wd.close(); sim.close()
 
 
+@pytest.mark.parametrize("variant,bcT", [("mpi", SIDE_HEATED), ("acc", RB_PERIODIC)])
+def test_graph_replayed_steps_strict_are_bit_exact(variant, bcT):
+    """a single small subdomain replays its fused launches as CUDA graphs of 64 kernels: 1 + 2 x 64 + 7 steps, then 64 + 1 more
+    (the second call starts from the other ping-pong index), bit for bit"""
+    wd, sim = pair((45, 38), 1, bcT=bcT, strict=True, variant=variant, Rayleigh=1e5)
+    for n in (136, 65):
+        l0 = sim.launch_count()
+        wd.step(n); sim.step(n)
+        assert sim.launch_count() - l0 == 2 + (n - 1) + 1          # kernels, whether launched directly or from a graph
+        assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+    wd.close(); sim.close()
+
+
 def test_wall_halos_are_never_read_by_the_fused_step():
     wd, sim = pair((31, 17), 4, strict=True)
     for r in range(4):
