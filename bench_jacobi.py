@@ -179,6 +179,11 @@ def lid2d(args, rank, local_rank, world):
     sim = mg.LidDrivenCavity2D((n, n), variant="f", strict=args.arith == "strict", device=local_rank)
     sim.initial()
     sim.step(max(args.warmup, 3)); sim.sync()
+    if n * n <= (1 << 20):
+        # an L2-resident lattice replays its fused launches from CUDA graphs of 64 kernels, one per ping-pong index: have both
+        # instantiated before the timed region, and time enough steps for a stable figure
+        sim.step(66); sim.step(66); sim.sync()
+        args.steps = max(args.steps, 4000)
     l0 = sim.launch_count()
     sampler = B.ClockSampler(local_rank); sampler.start()
     ms = sim.step_timed(args.steps)
@@ -223,8 +228,9 @@ def lid2d(args, rank, local_rank, world):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"lid_driven_cavity_d2q9_mrt_{n}x{n}", "Re": 1000.0, "U0": 0.1, "arith": args.arith, "errorU": err,
-                   "l2": "lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (9 * cells * 8 / 1e9)},
-        "roofline": {"bound": "hbm", "kernel": f"mglc::{args.arith}::k_l2_fused", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                   "l2": ("lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (9 * cells * 8 / 1e9)) if cells > (1 << 22) else
+                         ("lattice (2 x %.1f MB) is L2-resident: the rate is not an HBM figure; fused launches replayed from CUDA graphs" % (9 * cells * 8 / 1e6))},
+        "roofline": {"bound": "hbm" if cells > (1 << 22) else "launch latency / L2", "kernel": f"mglc::{args.arith}::k_l2_fused", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 144,
                      "cells_per_launch": cells, "note": "whole step(K) call timed: collision + (K-1) fused + stream/macro launches"},
         "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
@@ -259,10 +265,13 @@ def thermal2d(args, rank, local_rank, world):
         # the large lattices run Ra = 1e9
         Ra = 1e7 if n <= 4096 else 1e9
         sim = mg.BuoyancyDrivenCavity2D((n, n), strict=args.arith == "strict", device=local_rank, Rayleigh=Ra)
-    if nx * ny < 4_000_000:
-        args.steps = max(args.steps, 2000)        # an L2-resident lattice: enough steps for a stable time
     sim.initial()
     sim.step(max(args.warmup, 3)); sim.sync()
+    if nx * ny <= (1 << 20):
+        # an L2-resident lattice replays its fused launches from CUDA graphs of 64 kernels, one per ping-pong index: have both
+        # instantiated before the timed region, and time enough steps for a stable figure
+        sim.step(66); sim.step(66); sim.sync()
+        args.steps = max(args.steps, 4000)
     l0 = sim.launch_count()
     sampler = B.ClockSampler(local_rank); sampler.start()
     ms = sim.step_timed(args.steps)

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -201,7 +202,12 @@ struct L2Sub {
 // The shipped 200 x 200 / 201 x 201 lattices fit the L2 and are bounded by kernel-launch latency, not by HBM: such runs replay
 // the fused launches as CUDA graphs of L2_GRAPH_STEPS kernels (an even count: the ping-pong and lid-row indices return).
 constexpr int L2_GRAPH_STEPS = 64;
-constexpr long long L2_GRAPH_MAX_CELLS = 1LL << 22;
+// largest lattice (cells) that is replayed from graphs; MGLC_2D_GRAPH_CELLS overrides it (0 = never), for A/B measurements
+static long long l2_graph_max_cells() {
+    static long long v = -1;
+    if (v < 0) { v = 1LL << 20; if (const char *e = getenv("MGLC_2D_GRAPH_CELLS")) v = std::max(0LL, atoll(e)); }
+    return v;
+}
 
 }  // namespace
 
@@ -552,7 +558,7 @@ static int l2_step_impl(mglc_l2d *h, int nsteps) {
     }
     MGLC_TRY(l2_collision(h));
     int lid = 0, it = 1;
-    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= L2_GRAPH_MAX_CELLS) {
+    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= l2_graph_max_cells()) {
         L2Sub *S = h->subs[0];
         MGLC_TRY(l2_use(S));
         auto fused = strict_build ? strict::launch_l2_fused : fast::launch_l2_fused;

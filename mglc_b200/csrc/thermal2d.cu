@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -45,7 +46,12 @@ struct T2Sub {
 // A lattice that fits the L2 (the shipped 201 x 201 and 513 x 257 cases) is bounded by kernel-launch latency, not by HBM:
 // such runs replay the fused launches as CUDA graphs of T2_GRAPH_STEPS kernels (an even count: the ping-pong index returns).
 constexpr int T2_GRAPH_STEPS = 64;
-constexpr long long T2_GRAPH_MAX_CELLS = 1LL << 22;
+// largest lattice (cells) that is replayed from graphs; MGLC_2D_GRAPH_CELLS overrides it (0 = never), for A/B measurements
+static long long t2_graph_max_cells() {
+    static long long v = -1;
+    if (v < 0) { v = 1LL << 20; if (const char *e = getenv("MGLC_2D_GRAPH_CELLS")) v = std::max(0LL, atoll(e)); }
+    return v;
+}
 
 }  // namespace
 
@@ -500,7 +506,7 @@ static int t2_step_impl(mglc_t2d *h, int nsteps) {
     MGLC_TRY(t2_collision(h));
     MGLC_TRY(t2_collisionT(h));
     int it = 1;
-    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= T2_GRAPH_MAX_CELLS) {
+    if (h->nranks == 1 && (long long)h->subs[0]->n[0] * h->subs[0]->n[1] <= t2_graph_max_cells()) {
         T2Sub *S = h->subs[0];
         MGLC_TRY(t2_use(S));
         auto fused = strict_build ? strict::launch_t2_fused : fast::launch_t2_fused;
