@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
 // (plus one row above and one below the strip per plane), x neighbours come from the adjacent lanes by shuffle
 // (warp-edge lanes read them), z neighbours from the marching registers: per cell one DRAM read, one write and
 // about 2/JRY extra L2 reads.
-constexpr int JTX = 128, JRY = 4;
-template <bool HAS_F>
-__global__ void __launch_bounds__(JTX, 8) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
-                                                     double *__restrict__ B, int k_lo, int k_hi, int kch) {
+constexpr int JTX = 128;
+template <bool HAS_F, int JRY>
+__global__ void __launch_bounds__(JTX, JRY <= 4 ? 8 : 4) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
+                                                                   double *__restrict__ B, int k_lo, int k_hi, int kch) {
     const int i = 1 + blockIdx.x * JTX + threadIdx.x;
     const int j0 = 1 + blockIdx.y * JRY;
     const int k0 = k_lo + blockIdx.z * kch;
@@ -125,6 +125,14 @@ __global__ void __launch_bounds__(JTX, 8) k_jacobi3d(Geom g, const double *__res
 
 // planes a CTA marches: short chunks keep the last wave of CTAs small (the sweep of a 512^3 block lasts only
 // ~0.4 ms, so a partly filled last wave costs several per cent), long chunks re-read fewer start-up planes
+// rows a thread owns (4 or 8): more rows re-read fewer y-neighbour rows from the L2 but need more registers -- measured on
+// B200 at 512^3 (profiles/r1k_jacobi_register_blocking_sweep.json): 4 rows 0.371 ms/sweep, 8 rows 0.580 ms (127 registers halve
+// the resident warps; the sweep is bound by loads in flight, not by L2 traffic), so 4 stays the default
+static int jacobi_jry() {
+    static int v = 0;
+    if (!v) { v = 4; if (const char *e = getenv("MGLC_JACOBI_JRY")) v = atoi(e) == 8 ? 8 : 4; }
+    return v;
+}
 static int jacobi_kch(int nz) {
     static int v = 0;
     if (!v) { v = 8; if (const char *e = getenv("MGLC_JACOBI_KCH")) v = std::max(1, atoi(e)); }
@@ -442,10 +450,16 @@ static int jac_sweep(mglc_jacobi *h) {
             else k_jacobi2d<false><<<grid, 128, 0, S->s>>>(S->g, A, nullptr, B);
         } else {
             const int kch = jacobi_kch(S->n[2]);
+            const int JRY = jacobi_jry();
             const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JRY - 1) / JRY, (S->n[2] + kch - 1) / kch);
             const dim3 block(JTX);
-            if (S->f) k_jacobi3d<true><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2], kch);
-            else k_jacobi3d<false><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2], kch);
+            if (JRY == 8) {
+                if (S->f) k_jacobi3d<true, 8><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2], kch);
+                else k_jacobi3d<false, 8><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2], kch);
+            } else {
+                if (S->f) k_jacobi3d<true, 4><<<grid, block, 0, S->s>>>(S->g, A, S->f, B, 1, S->n[2], kch);
+                else k_jacobi3d<false, 4><<<grid, block, 0, S->s>>>(S->g, A, nullptr, B, 1, S->n[2], kch);
+            }
         }
         S->launches += 1;
         S->cur ^= 1;
