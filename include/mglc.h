@@ -123,6 +123,10 @@ int mglc_thermal_desc_init(mglc_lbm_desc *d, const int gn[3], const int dims_or_
                            double rayleigh, double prandtl, double mach, double ekman);
 /* the 18 messages of one message_passing_sendrecv() for this subdomain, in the reference's order */
 int mglc_halo_plan(const mglc_lbm_desc *d, mglc_halo_msg msgs[18], int *nmsgs);
+/* the 2-D drivers' messages for the rank at `rank` (= c0*dims[1] + c1): 0..3 f faces (+x,-x,+y,-y; 3 populations), 4..7 the corner
+ * population 5..8 crosses (1 value), 8..11 the thermal driver's g faces (1 population) -- 2d_revised/mpi_blocked/ex_sendrecv.f90:9-78,
+ * Buoyancy_driven_cavity/fortran/2d/mpi_blocked/message_exchange.F90:1-118; buffer layout [slot][t] over the sender's interior range */
+int mglc_halo_plan_2d(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg msgs[12], int *nmsgs);
 /* relaxation rates Snu, Sq -- L3/commondata.f90:42 */
 int mglc_relaxation_rates(double tau, double *Snu, double *Sq);
 

@@ -13,7 +13,7 @@ from .lid2d import LidDrivenCavity2D
 from .particles import ParticleChannel
 from .thermal2d import BuoyancyDrivenCavity2D
 from .lbm import (BuoyancyDrivenCavity, Communicator, LidDrivenCavity, make_thermal_desc, Subdomain, cart_neighbors, decompose_1d, dims_create,
-                  halo_plan, make_desc)
+                  halo_plan, halo_plan_2d, make_desc)
 
 __all__ = ["MglcError", "lib", "BuoyancyDrivenCavity", "Communicator", "LidDrivenCavity", "make_thermal_desc", "Subdomain", "cart_neighbors",
-           "decompose_1d", "dims_create", "halo_plan", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "LidDrivenCavity2D", "LidDrivenCavityAA", "BuoyancyDrivenCavity2D", "_lib", "formats"]
+           "decompose_1d", "dims_create", "halo_plan", "halo_plan_2d", "make_desc", "Jacobi", "dims_create_nd", "ParticleChannel", "LidDrivenCavity2D", "LidDrivenCavityAA", "BuoyancyDrivenCavity2D", "_lib", "formats"]

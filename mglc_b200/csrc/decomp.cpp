@@ -194,4 +194,37 @@ int mglc_halo_plan(const mglc_lbm_desc *d, mglc_halo_msg msgs[18], int *nmsgs) {
     return MGLC_OK;
 }
 
+// The 2-D drivers' messages (Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/ex_sendrecv.f90:9-78 and
+// Buoyancy_driven_cavity/fortran/2d/mpi_blocked/message_exchange.F90:1-118) for the rank at `rank` of a dims[0] x dims[1] grid
+// (rank = c0*dims[1] + c1): msgs 0..3 = f faces to right(+x), left(-x), top(+y), bottom(-y), three populations over the interior
+// range; 4..7 = the corner population 5..8 crosses, one value; 8..11 = the thermal driver's g faces, one population each.
+int mglc_halo_plan_2d(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg msgs[12], int *nmsgs) {
+    if (!dims || !msgs || !nmsgs || dims[0] < 1 || dims[1] < 1 || rank < 0 || rank >= dims[0] * dims[1]) return MGLC_E_INVALID;
+    static const int ex9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    static const int face_pops[4][3] = {{1, 5, 8}, {3, 6, 7}, {2, 5, 6}, {4, 7, 8}}, face_popg[4] = {1, 3, 2, 4};
+    const int c0 = rank / dims[1], c1 = rank % dims[1];
+    int n[2], start;
+    mglc_decompose_1d(total_nx, c0, dims[0], &n[0], &start);
+    mglc_decompose_1d(total_ny, c1, dims[1], &n[1], &start);
+    auto cart = [&](int a, int b) { return (a < 0 || a >= dims[0] || b < 0 || b >= dims[1]) ? -1 : a * dims[1] + b; };
+    for (int dir = 0; dir < 12; ++dir) {
+        mglc_halo_msg &m = msgs[dir];
+        const int d = dir >= 8 ? dir - 8 : dir;
+        const int ox = d < 4 ? (d == 0) - (d == 1) : ex9[d + 1], oy = d < 4 ? (d == 2) - (d == 3) : ey9[d + 1];
+        const int n1 = d < 4 ? ((d >> 1) == 0 ? n[1] : n[0]) : 1;
+        m.dir = dir;
+        m.npop = d < 4 ? (dir >= 8 ? 1 : 3) : 1;
+        m.send_to = cart(c0 + ox, c1 + oy);
+        m.recv_from = cart(c0 - ox, c1 - oy);          // what travels in +x arrives from my -x neighbour
+        m.send_count = m.send_to >= 0 ? n1 * m.npop : 0;
+        m.recv_count = m.recv_from >= 0 ? n1 * m.npop : 0;      // the extent along a face is shared by both sides of a Cartesian cut
+        for (int q = 0; q < 5; ++q) m.pops[q] = -1;
+        if (dir >= 8) m.pops[0] = face_popg[d];
+        else if (d < 4) for (int q = 0; q < 3; ++q) m.pops[q] = face_pops[d][q];
+        else m.pops[0] = d + 1;
+    }
+    *nmsgs = 12;
+    return MGLC_OK;
+}
+
 }  // extern "C"

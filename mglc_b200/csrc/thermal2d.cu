@@ -173,6 +173,17 @@ static int t2_make_sub(mglc_t2d *h, int rank, int device, T2Sub **out) {
         if (M.send_count && cudaMalloc((void **)&M.sbuf, M.send_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
         if (M.recv_count && cudaMalloc((void **)&M.rbuf, M.recv_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
     }
+    {   // the message table must be the one the host-only plan publishes (mglc_halo_plan_2d, checked on the CPU against the oracle)
+        mglc_halo_msg plan[12];
+        int np = 0;
+        if (mglc_halo_plan_2d(gn[0], gn[1], h->dims, rank, plan, &np) != MGLC_OK) return fail(MGLC_E_INVALID);
+        for (int dir = 0; dir < T2_NMSG; ++dir)
+            if (plan[dir].send_to != S->msgs[dir].send_to || plan[dir].recv_from != S->msgs[dir].recv_from ||
+                plan[dir].send_count != S->msgs[dir].send_count || plan[dir].recv_count != S->msgs[dir].recv_count) {
+                set_error("mglc_t2d_create: message %d differs from mglc_halo_plan_2d", dir);
+                return fail(MGLC_E_STATE);
+            }
+    }
     if (cudaStreamSynchronize(S->s) != cudaSuccess) return fail(MGLC_E_CUDA);
     *out = S;
     return MGLC_OK;

@@ -94,6 +94,15 @@ def halo_plan(desc):
                  recv_count=m.recv_count, pops=[p for p in m.pops if p >= 0]) for m in msgs[:n.value]]
 
 
+def halo_plan_2d(total, dims, rank):
+    """The 12 messages of the 2-D drivers for the rank at `rank` of a dims[0] x dims[1] grid (host-only, no GPU needed)"""
+    msgs = (L.HaloMsg * 12)()
+    n = C.c_int()
+    L.check(L.lib().mglc_halo_plan_2d(total[0], total[1], (C.c_int * 2)(*dims), rank, msgs, C.byref(n)))
+    return [dict(dir=m.dir, send_to=m.send_to, recv_from=m.recv_from, npop=m.npop, send_count=m.send_count,
+                 recv_count=m.recv_count, pops=[p for p in m.pops if p >= 0]) for m in msgs[:n.value]]
+
+
 class Communicator:
     """NCCL communicator for the one-process-per-GPU mode (replaces MPI_Cart_create, L3/main.f90:25).
 
