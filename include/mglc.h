@@ -475,6 +475,13 @@ int mglc_output_binary_thermal(const char *path, const double *u, const double *
 int mglc_backup_write(const char *path, const double *u, const double *v, const double *w, const double *T,
                       const double *f, const double *g, int nx, int ny, int nz);
 int mglc_backup_read(const char *path, double *u, double *v, double *w, double *T, double *f, double *g, int nx, int ny, int nz);
+/* the 2-D thermal driver: output_binary() records u, v, T -- Buoyancy_driven_cavity/fortran/2d/mpi_blocked/output.F90:192-217;
+ * backupData() records f, g, u, v, T as the driver stores them -- output.F90:381-401 (f(0:8,nx,ny)), seq/bouyancy2d_acc.F90:1158-1189
+ * (f(nx,ny,0:8)); mglc_backup_read_2d = initial() with loadInitField = 1 */
+int mglc_output_binary_thermal2d(const char *path, const double *u, const double *v, const double *T, int nx, int ny);
+int mglc_backup_write_2d(const char *path, const double *f, const double *g, const double *u, const double *v, const double *T,
+                         int nx, int ny);
+int mglc_backup_read_2d(const char *path, double *f, double *g, double *u, double *v, double *T, int nx, int ny);
 /* xp(0:total_n+1): 0, i - 0.5, total_n -- L3/initial.f90:18-31, B3:459-472 */
 int mglc_grid_coords(int total_n, double *xp);
 /* output_Tecplot(): "#!TDV101", one ordered zone, POINT packing, 7 float variables X Y Z U V W Pressure(= rho/3)

@@ -205,6 +205,9 @@ SIGNATURES = {
     "mglc_p2d_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_p2d_sync": (C.c_int, [_vp]),
     # 2-D D2Q9 lid-driven cavity
+    "mglc_output_binary_thermal2d": (C.c_int, [C.c_char_p, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "mglc_backup_write_2d": (C.c_int, [C.c_char_p] + [_vp] * 5 + [C.c_int, C.c_int]),
+    "mglc_backup_read_2d": (C.c_int, [C.c_char_p] + [_vp] * 5 + [C.c_int, C.c_int]),
     "mglc_halo_plan_2d": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.POINTER(HaloMsg), _ip]),
     "mglc_l2d_desc_init": (C.c_int, [C.POINTER(L2dDesc), C.c_int]),
     "mglc_l2d_create": (C.c_int, [_vpp, C.POINTER(L2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),

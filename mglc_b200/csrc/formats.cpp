@@ -118,6 +118,33 @@ extern "C" int mglc_backup_write(const char *path, const double *u, const double
     const long long bytes[6] = {b, b, b, b, 19 * b, 7 * b};
     return mglc_unformatted_write(path, 6, rec, bytes, 0);
 }
+// ---- the 2-D thermal driver (B2 = Buoyancy_driven_cavity/fortran/2d) ----
+// output_binary(): records u, v, T -- mpi_blocked/output.F90:192-217
+extern "C" int mglc_output_binary_thermal2d(const char *path, const double *u, const double *v, const double *T, int nx, int ny) {
+    if (!u || !v || !T || nx < 1 || ny < 1) { set_error("mglc_output_binary_thermal2d: bad arguments"); return MGLC_E_INVALID; }
+    const long long b = 8LL * nx * ny;
+    const void *rec[3] = {u, v, T};
+    const long long bytes[3] = {b, b, b};
+    return mglc_unformatted_write(path, 3, rec, bytes, 0);
+}
+// backupData(): records f, g, u, v, T -- mpi_blocked/output.F90:381-401 (f(0:8,nx,ny), population index fastest) and
+// seq/bouyancy2d_acc.F90:1158-1189 (f(nx,ny,0:8), population index slowest): the records hold the arrays as the driver
+// stores them, so the same call serves both; mglc_backup_read_2d = initial() with loadInitField = 1 (initial.F90:291-301)
+extern "C" int mglc_backup_write_2d(const char *path, const double *f, const double *g, const double *u, const double *v,
+                                    const double *T, int nx, int ny) {
+    if (!f || !g || !u || !v || !T || nx < 1 || ny < 1) { set_error("mglc_backup_write_2d: bad arguments"); return MGLC_E_INVALID; }
+    const long long b = 8LL * nx * ny;
+    const void *rec[5] = {f, g, u, v, T};
+    const long long bytes[5] = {9 * b, 5 * b, b, b, b};
+    return mglc_unformatted_write(path, 5, rec, bytes, 0);
+}
+extern "C" int mglc_backup_read_2d(const char *path, double *f, double *g, double *u, double *v, double *T, int nx, int ny) {
+    if (!f || !g || !u || !v || !T || nx < 1 || ny < 1) { set_error("mglc_backup_read_2d: bad arguments"); return MGLC_E_INVALID; }
+    const long long b = 8LL * nx * ny;
+    void *rec[5] = {f, g, u, v, T};
+    const long long bytes[5] = {9 * b, 5 * b, b, b, b};
+    return mglc_unformatted_read(path, 5, rec, bytes);
+}
 // initial() with loadInitField = 1: B3/seq/bouyancy3d.F90:367-378
 extern "C" int mglc_backup_read(const char *path, double *u, double *v, double *w, double *T, double *f, double *g, int nx, int ny,
                                 int nz) {

@@ -88,6 +88,32 @@ def backup_read(path, n):
     return out
 
 
+def output_binary_thermal2d(path, u, v, T):
+    """output_binary() of the 2-D thermal driver, mpi_blocked/output.F90:192-217: records u, v, T"""
+    u = _f(u); v = _f(v, u.shape); T = _f(T, u.shape)
+    L.check(L.lib().mglc_output_binary_thermal2d(_path(path), _p(u), _p(v), _p(T), *u.shape))
+
+
+def backup_write_2d(path, f, g, u, v, T):
+    """backupData() of the 2-D thermal driver: records f, g, u, v, T as the driver stores them (f (9,nx,ny) for the MPI program,
+    (nx,ny,9) for the OpenACC one) -- mpi_blocked/output.F90:381-401, seq/bouyancy2d_acc.F90:1158-1189"""
+    u = _f(u); n = u.shape
+    v = _f(v, n); T = _f(T, n); f = _f(f); g = _f(g)
+    if f.size != 9 * u.size or g.size != 5 * u.size:
+        raise ValueError("f / g do not hold 9 / 5 populations per node")
+    L.check(L.lib().mglc_backup_write_2d(_path(path), _p(f), _p(g), _p(u), _p(v), _p(T), *n))
+
+
+def backup_read_2d(path, n, population_last=False):
+    """initial() with loadInitField = 1 -> dict(f, g, u, v, T); population_last: the OpenACC program's f(nx,ny,0:8)"""
+    n = tuple(n)
+    out = {k: np.empty(n, order="F") for k in ("u", "v", "T")}
+    out["f"] = np.empty(n + (9,) if population_last else (9,) + n, order="F")
+    out["g"] = np.empty(n + (5,) if population_last else (5,) + n, order="F")
+    L.check(L.lib().mglc_backup_read_2d(_path(path), *[_p(out[k]) for k in ("f", "g", "u", "v", "T")], *n))
+    return out
+
+
 def output_tecplot_lid(path, u, v, w, rho):
     """output_Tecplot(), L3/output.f90:175-313 (X Y Z U V W Pressure = rho/3, all float, POINT packing)"""
     u = _f(u); n = u.shape

@@ -50,6 +50,14 @@ def backup_data(u, v, w, T, f, g):
     return b"".join(fortran_record(_col(a)) for a in (u, v, w, T, f, g))   # seq:1021-1026
 
 
+def output_binary_thermal2d(u, v, T):
+    return b"".join(fortran_record(_col(a)) for a in (u, v, T))               # B2 mpi_blocked/output.F90:211-213
+
+
+def backup_data_2d(f, g, u, v, T):
+    return b"".join(fortran_record(_col(a)) for a in (f, g, u, v, T))         # output.F90:397-401 ; acc:1177-1181
+
+
 def grid_coords(n):
     xp = np.empty(n + 2)
     xp[0] = 0.0

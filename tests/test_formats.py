@@ -131,3 +131,30 @@ def test_format_errors_are_reported_not_thrown(tmp_path):
     assert "cannot open" in str(e.value)
     with pytest.raises(mg.MglcError):
         F.output_filename(99, 1)
+
+
+def test_thermal2d_files(tmp_path):
+    """the 2-D thermal driver's output_binary() (u, v, T) and backupData() (f, g, u, v, T), in the MPI program's layout
+    f(0:8,nx,ny) and the OpenACC program's f(nx,ny,0:8) -- mpi_blocked/output.F90:192-217, 381-401; seq/bouyancy2d_acc.F90:1158-1189"""
+    n = (7, 5)
+    u, v, T = fields(n, 11, 3)
+    p = tmp_path / "buoyancyCavity-2000.bin"
+    F.output_binary_thermal2d(p, u, v, T)
+    assert p.read_bytes() == OF.output_binary_thermal2d(u, v, T)
+    with FortranFile(str(p), "r") as ff:
+        for a in (u, v, T):
+            assert np.array_equal(ff.read_reals(np.float64).reshape(n, order="F"), a)
+    for last in (False, True):
+        f = fields(n + (9,) if last else (9,) + n, 12, 1)[0]
+        g = fields(n + (5,) if last else (5,) + n, 13, 1)[0]
+        q = tmp_path / f"backupFile-{int(last)}.bin"
+        F.backup_write_2d(q, f, g, u, v, T)
+        assert q.read_bytes() == OF.backup_data_2d(f, g, u, v, T)
+        b = F.backup_read_2d(q, n, population_last=last)
+        for k, a in zip(("f", "g", "u", "v", "T"), (f, g, u, v, T)):
+            assert np.array_equal(b[k], a), (last, k)
+        with FortranFile(str(q), "r") as ff:
+            for a in (f, g, u, v, T):
+                assert np.array_equal(ff.read_reals(np.float64).reshape(a.shape, order="F"), a)
+    with pytest.raises(mg.MglcError):
+        F.backup_read_2d(q, (7, 6))
