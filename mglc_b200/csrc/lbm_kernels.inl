@@ -10,11 +10,12 @@
 // macro() (L3/macro.f90) of step n and collision() (L3/collision.f90) of step n+1, so a step costs
 // one read and one write of the 19 populations: 304 B/cell.
 #include "common.cuh"
-#include "d3q19_mrt.inl"
-#include "d3q19_thermal.inl"
 
 namespace mglc {
 namespace MGLC_NS {
+
+#include "d3q19_mrt.inl"
+#include "d3q19_thermal.inl"
 
 // Pull the 19 populations that arrive at cell c (c = linear index of the cell in population 0), with
 // bounceback() (L3/bounce_back.f90:6-83) folded in as the unified boundary rule:
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128) k_stream_macro(Geom g, LbmParams p, const
     rho_o[m] = rho; u_o[m] = u; v_o[m] = v; w_o[m] = w;
 }
 
+#ifndef MGLC_HOST_SHIM   // tests/host_shim/lbm_host.cpp runs the kernels above on the CPU and has no <<< >>>
 static inline dim3 grid_for(int nxs, int nys, int nzs, int tx) { return dim3((nxs + tx - 1) / tx, nys, nzs); }
 
 int launch_collision(const Geom &g, const LbmParams &p, const double *F, const double *rho, const double *u,
@@ -216,6 +218,7 @@ int launch_stream_macro(const Geom &g, const LbmParams &p, const double *Fin, do
     k_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, p, Fin, F, rho_lid_in, rho, u, v, w);
     return 1;
 }
+#endif
 
 #include "thermal_kernels.inl"
 

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(128) k_th_stream_macro(Geom g, ThermalParams t
     T_o[m] = d3q7_temperature(gq);
 }
 
+#ifndef MGLC_HOST_SHIM
 int launch_th_collision(const Geom &g, const ThermalParams &tp, const double *F, const double *rho, const double *u,
                         const double *v, const double *w, const double *T, double *Fpost, double *Fc, cudaStream_t s) {
     k_th_collision<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, tp, F, rho, u, v, w, T, Fpost, Fc);
@@ -150,3 +151,4 @@ int launch_th_stream_macro(const Geom &g, const ThermalParams &tp, const double 
     k_th_stream_macro<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, tp, Fin, F, Gin, G, Fc_in, rho, u, v, w, T);
     return 1;
 }
+#endif
