@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(128) k_l2_stream_macro(Geom2 g, L2Params p, co
     rho[m] = r; u[m] = uu; v[m] = vv;
 }
 
+#ifndef MGLC_HOST_SHIM   // tests/host_shim/l2d_host.cpp runs the kernels above on the CPU and has no <<< >>>
 int launch_l2_collision(const Geom2 &g, const L2Params &p, int variant, const double *F, const double *rho, const double *u,
                         const double *v, double *Fpost, cudaStream_t s) {
     const dim3 grid((g.nx + 127) / 128, g.ny);
@@ -187,6 +188,7 @@ int launch_l2_fused(const Geom2 &g, const L2Params &p, int variant, const double
     else k_l2_fused<1><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
     return 1;
 }
+#endif
 
 }  // namespace MGLC_NS
 }  // namespace mglc
