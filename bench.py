@@ -221,24 +221,24 @@ def main():
     if args.size == 0:
         args.size = {"lid": 768, "thermal": 512 if world == 1 else 256, "jacobi": 512, "particles": 0, "lid2d": 8192, "thermal2d": 8192 if args.variant == "mpi" else 0, "lid_aa": 896}[args.workload]
     if args.workload == "jacobi":
-        import bench_jacobi
-        bench_jacobi.main(args, rank, local_rank, world)
+        import bench_workloads
+        bench_workloads.jacobi(args, rank, local_rank, world)
         return
     if args.workload == "particles":
-        import bench_jacobi
-        bench_jacobi.particles(args, rank, local_rank, world)
+        import bench_workloads
+        bench_workloads.particles(args, rank, local_rank, world)
         return
     if args.workload == "lid2d":
-        import bench_jacobi
-        bench_jacobi.lid2d(args, rank, local_rank, world)
+        import bench_workloads
+        bench_workloads.lid2d(args, rank, local_rank, world)
         return
     if args.workload == "thermal2d":
-        import bench_jacobi
-        bench_jacobi.thermal2d(args, rank, local_rank, world)
+        import bench_workloads
+        bench_workloads.thermal2d(args, rank, local_rank, world)
         return
     if args.workload == "lid_aa":
-        import bench_jacobi
-        bench_jacobi.lid_aa(args, rank, local_rank, world)
+        import bench_workloads
+        bench_workloads.lid_aa(args, rank, local_rank, world)
         return
     if args.impl == "reference":
         if thermal:

@@ -1,7 +1,9 @@
-"""bench.py --workload jacobi: BASELINE.json config 2 (3-D Jacobi, 512^3 per GPU block, halo exchange over
-NCCL at N > 1).  One step = one exchange_message + one jacobi sweep (LAP:94-103).  Prints ONE JSON line in the
-shape of bench.py's; the metric is million cell updates per second, algorithmic traffic 16 B/cell (one read,
-one write; the source term is identically zero in the reference problem and is not read)."""
+"""The secondary workloads of bench.py (`--workload jacobi | particles | lid2d | thermal2d | lid_aa`); the headline lid and the
+3-D thermal workloads live in bench.py itself.  Every function prints ONE JSON line in the shape of bench.py's.
+
+jacobi: BASELINE.json config 2 (3-D Jacobi, 512^3 per GPU block, halo exchange over NCCL at N > 1).  One step = one
+exchange_message + one jacobi sweep (LAP:94-103); the metric is million cell updates per second, algorithmic traffic 16 B/cell
+(one read, one write; the source term is identically zero in the reference problem and is not read)."""
 import ctypes as C
 import json
 import os
@@ -10,7 +12,7 @@ import tempfile
 import time
 
 
-def main(args, rank, local_rank, world):
+def jacobi(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
