@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGLC_VERSION 102
+#define MGLC_VERSION 103
 
 /* ---- status codes ---- */
 #define MGLC_OK          0
