@@ -518,6 +518,181 @@ module mglc_iso_c
             type(c_ptr), value :: h
             integer(c_int) :: rc
         end function
+        ! ---- one call per reference subroutine (Laplace driver, jacobi2d_mpi.f90:94-112): handle in, status out ----
+        function mglc_jacobi_init(h) bind(C, name="mglc_jacobi_init") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_exchange(h) bind(C, name="mglc_jacobi_exchange") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_sweep(h) bind(C, name="mglc_jacobi_sweep") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_jacobi_sync(h) bind(C, name="mglc_jacobi_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- one call per reference subroutine (particle driver, case4/mpi_particle/main.F90:37-71): handle in, status out ----
+        function mglc_p2d_collision(h) bind(C, name="mglc_p2d_collision") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_send_all_fp(h) bind(C, name="mglc_p2d_send_all_fp") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_streaming(h) bind(C, name="mglc_p2d_streaming") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_bounceback(h) bind(C, name="mglc_p2d_bounceback") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_macro(h) bind(C, name="mglc_p2d_macro") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_calforce(h) bind(C, name="mglc_p2d_calforce") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_send_all_f(h) bind(C, name="mglc_p2d_send_all_f") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_update_center(h) bind(C, name="mglc_p2d_update_center") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_p2d_sync(h) bind(C, name="mglc_p2d_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- one call per reference subroutine (2-D lid driver, 2d_revised/mpi_blocked/main.f90:66-82): handle in, status out ----
+        function mglc_l2d_initial(h) bind(C, name="mglc_l2d_initial") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_collision(h) bind(C, name="mglc_l2d_collision") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_exchange(h) bind(C, name="mglc_l2d_exchange") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_streaming(h) bind(C, name="mglc_l2d_streaming") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_bounceback(h) bind(C, name="mglc_l2d_bounceback") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_macro(h) bind(C, name="mglc_l2d_macro") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_l2d_sync(h) bind(C, name="mglc_l2d_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- one call per reference subroutine (2-D thermal driver, Buoyancy_driven_cavity/fortran/2d/mpi_blocked/main.F90:84-108): handle in, status out ----
+        function mglc_t2d_initial(h) bind(C, name="mglc_t2d_initial") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_collision(h) bind(C, name="mglc_t2d_collision") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_exchange_f(h) bind(C, name="mglc_t2d_exchange_f") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_streaming(h) bind(C, name="mglc_t2d_streaming") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_bounceback(h) bind(C, name="mglc_t2d_bounceback") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_collisionT(h) bind(C, name="mglc_t2d_collisionT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_exchange_g(h) bind(C, name="mglc_t2d_exchange_g") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_streamingT(h) bind(C, name="mglc_t2d_streamingT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_bouncebackT(h) bind(C, name="mglc_t2d_bouncebackT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_macro(h) bind(C, name="mglc_t2d_macro") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_macroT(h) bind(C, name="mglc_t2d_macroT") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_t2d_sync(h) bind(C, name="mglc_t2d_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        ! ---- one call per reference subroutine (lid driver on one lattice): handle in, status out ----
+        function mglc_aa_initial(h) bind(C, name="mglc_aa_initial") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
+        function mglc_aa_sync(h) bind(C, name="mglc_aa_sync") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int) :: rc
+        end function
         ! ---- in-loop diagnostics on the device and the drivers' on-disk formats ----------------------------------------
         !> calNuRe(), Buoyancy_driven_cavity/fortran/3d/mpi_blocked/RaNu.F90:13-47
         function mglc_calNuRe(h, prandtl, NuVolAvg, ReVolAvg) bind(C, name="mglc_calNuRe") result(rc)
