@@ -192,6 +192,10 @@ def run_reference(args, rank):
     cal.close()
     rate = n * n * 8 / t1
     nz = int(max(8, min(n, rate * 90.0 / max(1, args.steps + args.warmup) / (n * n))))
+    # ... and keep the slab inside the host memory: f + halo'd f_post + seven fields ~ 400 B per cell
+    avail = host_mem_available()
+    if avail:
+        nz = int(max(8, min(nz, 0.5 * avail / (400.0 * n * n))))
     wd = orc.LidWorld((n, n, nz), 1, native=native)
     wd.initial()
     wd.step(args.warmup)
