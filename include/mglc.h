@@ -127,6 +127,10 @@ int mglc_halo_plan(const mglc_lbm_desc *d, mglc_halo_msg msgs[18], int *nmsgs);
  * population 5..8 crosses (1 value), 8..11 the thermal driver's g faces (1 population) -- 2d_revised/mpi_blocked/ex_sendrecv.f90:9-78,
  * Buoyancy_driven_cavity/fortran/2d/mpi_blocked/message_exchange.F90:1-118; buffer layout [slot][t] over the sender's interior range */
 int mglc_halo_plan_2d(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg msgs[12], int *nmsgs);
+/* the message tables the 2-D CUDA drivers build for themselves at create time (host-only views, for the CPU suite: they must
+ * equal the plan above; `pops` is not filled) */
+int mglc_l2d_msg_table(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg out[8]);
+int mglc_t2d_msg_table(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg out[12]);
 /* relaxation rates Snu, Sq -- L3/commondata.f90:42 */
 int mglc_relaxation_rates(double tau, double *Snu, double *Sq);
 

@@ -209,6 +209,8 @@ SIGNATURES = {
     "mglc_backup_write_2d": (C.c_int, [C.c_char_p] + [_vp] * 5 + [C.c_int, C.c_int]),
     "mglc_backup_read_2d": (C.c_int, [C.c_char_p] + [_vp] * 5 + [C.c_int, C.c_int]),
     "mglc_halo_plan_2d": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.POINTER(HaloMsg), _ip]),
+    "mglc_l2d_msg_table": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.POINTER(HaloMsg)]),
+    "mglc_t2d_msg_table": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int, C.POINTER(HaloMsg)]),
     "mglc_l2d_desc_init": (C.c_int, [C.POINTER(L2dDesc), C.c_int]),
     "mglc_l2d_create": (C.c_int, [_vpp, C.POINTER(L2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
     "mglc_l2d_create_local": (C.c_int, [_vpp, C.POINTER(L2dDesc), _ip, C.c_int, _ip]),

@@ -264,6 +264,39 @@ static void l2_msg_dims(const L2Sub *S, int dir, int &n1, int &npop) {
     else { n1 = 1; npop = 1; }
 }
 
+// the 8 messages of message_passing_sendrecv() (ex_sendrecv.f90:9-78) for the block at (c0, c1) with interior size n: pure host
+// logic, also reachable without a GPU through mglc_l2d_msg_table (the CPU suite compares it with mglc_halo_plan_2d)
+static void l2_build_msgs(const int dims[2], const int n[2], int c0, int c1, Msg msgs[8]) {
+    for (int dir = 0; dir < 8; ++dir) {
+        Msg &M = msgs[dir];
+        const int n1 = dir < 4 ? ((dir >> 1) == 0 ? n[1] : n[0]) : 1, npop = dir < 4 ? 3 : 1;
+        M.dir = dir;
+        // what I send towards direction `dir` is received from the neighbour on the opposite side
+        const int ox = dir < 4 ? (dir == 0) - (dir == 1) : h_ex9[dir + 1], oy = dir < 4 ? (dir == 2) - (dir == 3) : h_ey9[dir + 1];
+        M.send_to = l2_cart_rank(dims, c0 + ox, c1 + oy);
+        M.recv_from = l2_cart_rank(dims, c0 - ox, c1 - oy);
+        // face messages span the sender's interior range; both ends share that extent along the face (same coordinate there)
+        M.send_count = M.send_to >= 0 ? (long long)n1 * npop : 0;
+        M.recv_count = M.recv_from >= 0 ? (long long)n1 * npop : 0;
+    }
+}
+extern "C" int mglc_l2d_msg_table(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg out[8]) {
+    if (!dims || !out || dims[0] < 1 || dims[1] < 1 || rank < 0 || rank >= dims[0] * dims[1]) return MGLC_E_INVALID;
+    const int c0 = rank / dims[1], c1 = rank % dims[1];
+    int n[2], start;
+    mglc_decompose_1d(total_nx, c0, dims[0], &n[0], &start);
+    mglc_decompose_1d(total_ny, c1, dims[1], &n[1], &start);
+    Msg msgs[8];
+    memset(msgs, 0, sizeof msgs);
+    l2_build_msgs(dims, n, c0, c1, msgs);
+    for (int d = 0; d < 8; ++d) {
+        memset(&out[d], 0, sizeof out[d]);
+        out[d].dir = msgs[d].dir; out[d].send_to = msgs[d].send_to; out[d].recv_from = msgs[d].recv_from;
+        out[d].send_count = (int)msgs[d].send_count; out[d].recv_count = (int)msgs[d].recv_count; out[d].npop = d < 4 ? 3 : 1;
+    }
+    return MGLC_OK;
+}
+
 static int l2_make_sub(mglc_l2d *h, int rank, int device, L2Sub **out) {
     L2Sub *S = new L2Sub();
     memset(S, 0, sizeof *S);
@@ -296,18 +329,9 @@ static int l2_make_sub(mglc_l2d *h, int rank, int device, L2Sub **out) {
         if (cudaMalloc((void **)b.p, b.bytes) != cudaSuccess) { (void)cudaGetLastError(); set_error("mglc_l2d_create: out of device memory"); return fail(MGLC_E_NOMEM); }
         cudaMemsetAsync(*b.p, 0, b.bytes, S->s);
     }
+    l2_build_msgs(h->dims, S->n, c0, c1, S->msgs);
     for (int dir = 0; dir < 8; ++dir) {
         Msg &M = S->msgs[dir];
-        int n1, npop;
-        l2_msg_dims(S, dir, n1, npop);
-        M.dir = dir;
-        // what I send towards direction `dir` is received from the neighbour on the opposite side
-        const int ox = dir < 4 ? (dir == 0) - (dir == 1) : h_ex9[dir + 1], oy = dir < 4 ? (dir == 2) - (dir == 3) : h_ey9[dir + 1];
-        M.send_to = l2_cart_rank(h->dims, c0 + ox, c1 + oy);
-        M.recv_from = l2_cart_rank(h->dims, c0 - ox, c1 - oy);
-        // face messages span the sender's interior range; both ends share that extent along the face (same coordinate there)
-        M.send_count = M.send_to >= 0 ? (long long)n1 * npop : 0;
-        M.recv_count = M.recv_from >= 0 ? (long long)n1 * npop : 0;
         if (M.send_count && cudaMalloc((void **)&M.sbuf, M.send_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
         if (M.recv_count && cudaMalloc((void **)&M.rbuf, M.recv_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
     }

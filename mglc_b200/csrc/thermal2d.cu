@@ -123,6 +123,41 @@ static void t2_msg_dims(const T2Sub *S, int dir, int &n1, int &npop) {
     else { n1 = 1; npop = 1; }
 }
 
+// the 12 messages of message_passing_f() + message_passing_g() (message_exchange.F90:1-118) for the block at (c0, c1) with interior
+// size n: pure host logic, also reachable without a GPU through mglc_t2d_msg_table (the CPU suite compares it with mglc_halo_plan_2d)
+static void t2_build_msgs(const int dims[2], const int n[2], int c0, int c1, Msg msgs[T2_NMSG]) {
+    for (int dir = 0; dir < T2_NMSG; ++dir) {
+        Msg &M = msgs[dir];
+        const int d = dir >= 8 ? dir - 8 : dir;
+        const int n1 = d < 4 ? ((d >> 1) == 0 ? n[1] : n[0]) : 1, npop = d < 4 ? (dir >= 8 ? 1 : 3) : 1;
+        M.dir = dir;
+        // what I send towards direction `dir` is received from the neighbour on the opposite side
+        const int ox = d < 4 ? (d == 0) - (d == 1) : h_t2_ex[d + 1], oy = d < 4 ? (d == 2) - (d == 3) : h_t2_ey[d + 1];
+        M.send_to = t2_cart_rank(dims, c0 + ox, c1 + oy);
+        M.recv_from = t2_cart_rank(dims, c0 - ox, c1 - oy);
+        // face messages span the sender's interior range; both ends share that extent along the face (same coordinate there)
+        M.send_count = M.send_to >= 0 ? (long long)n1 * npop : 0;
+        M.recv_count = M.recv_from >= 0 ? (long long)n1 * npop : 0;
+    }
+}
+extern "C" int mglc_t2d_msg_table(int total_nx, int total_ny, const int dims[2], int rank, mglc_halo_msg out[12]) {
+    if (!dims || !out || dims[0] < 1 || dims[1] < 1 || rank < 0 || rank >= dims[0] * dims[1]) return MGLC_E_INVALID;
+    const int c0 = rank / dims[1], c1 = rank % dims[1];
+    int n[2], start;
+    mglc_decompose_1d(total_nx, c0, dims[0], &n[0], &start);
+    mglc_decompose_1d(total_ny, c1, dims[1], &n[1], &start);
+    Msg msgs[T2_NMSG];
+    memset(msgs, 0, sizeof msgs);
+    t2_build_msgs(dims, n, c0, c1, msgs);
+    for (int d = 0; d < T2_NMSG; ++d) {
+        memset(&out[d], 0, sizeof out[d]);
+        out[d].dir = msgs[d].dir; out[d].send_to = msgs[d].send_to; out[d].recv_from = msgs[d].recv_from;
+        out[d].send_count = (int)msgs[d].send_count; out[d].recv_count = (int)msgs[d].recv_count;
+        out[d].npop = (d >= 8 || (d >= 4 && d < 8)) ? 1 : 3;
+    }
+    return MGLC_OK;
+}
+
 static int t2_make_sub(mglc_t2d *h, int rank, int device, T2Sub **out) {
     T2Sub *S = new T2Sub();
     memset(S, 0, sizeof *S);
@@ -157,19 +192,9 @@ static int t2_make_sub(mglc_t2d *h, int rank, int device, T2Sub **out) {
         if (cudaMalloc((void **)b.p, b.bytes) != cudaSuccess) { (void)cudaGetLastError(); set_error("mglc_t2d_create: out of device memory"); return fail(MGLC_E_NOMEM); }
         cudaMemsetAsync(*b.p, 0, b.bytes, S->s);       // f_post = g_post = 0, initial.F90:334-335
     }
+    t2_build_msgs(h->dims, S->n, c0, c1, S->msgs);
     for (int dir = 0; dir < T2_NMSG; ++dir) {
         Msg &M = S->msgs[dir];
-        int n1, npop;
-        t2_msg_dims(S, dir, n1, npop);
-        M.dir = dir;
-        const int d = dir >= 8 ? dir - 8 : dir;
-        // what I send towards direction `dir` is received from the neighbour on the opposite side
-        const int ox = d < 4 ? (d == 0) - (d == 1) : h_t2_ex[d + 1], oy = d < 4 ? (d == 2) - (d == 3) : h_t2_ey[d + 1];
-        M.send_to = t2_cart_rank(h->dims, c0 + ox, c1 + oy);
-        M.recv_from = t2_cart_rank(h->dims, c0 - ox, c1 - oy);
-        // face messages span the sender's interior range; both ends share that extent along the face (same coordinate there)
-        M.send_count = M.send_to >= 0 ? (long long)n1 * npop : 0;
-        M.recv_count = M.recv_from >= 0 ? (long long)n1 * npop : 0;
         if (M.send_count && cudaMalloc((void **)&M.sbuf, M.send_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
         if (M.recv_count && cudaMalloc((void **)&M.rbuf, M.recv_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
     }

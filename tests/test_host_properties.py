@@ -82,3 +82,24 @@ def test_halo_plan_2d_is_pairwise_consistent_and_matches_the_oracle_topology(d0,
         want = [3 * n[1], 3 * n[1], 3 * n[0], 3 * n[0], 1, 1, 1, 1, n[1], n[1], n[0], n[0]]
         assert [m["send_count"] for m in plan] == [w if m["send_to"] >= 0 else 0 for w, m in zip(want, plan)]
     wd.close()
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(1, 6), st.integers(1, 6), st.integers(6, 300), st.integers(6, 300))
+def test_the_cuda_drivers_own_message_tables_equal_the_published_plan(d0, d1, nx, ny):
+    """mglc_l2d_create / mglc_t2d_create refuse to start when their message table differs from mglc_halo_plan_2d; the same
+    host code that builds those tables is reachable without a GPU (mglc_l2d_msg_table / mglc_t2d_msg_table), so the CPU suite
+    can show that the refusal can never trigger"""
+    import ctypes as C
+    from mglc_b200 import _lib as L
+    lib = L.lib()
+    dims = (C.c_int * 2)(d0, d1)
+    for rank in range(d0 * d1):
+        plan = mg.halo_plan_2d((nx, ny), (d0, d1), rank)
+        for fn, n in ((lib.mglc_l2d_msg_table, 8), (lib.mglc_t2d_msg_table, 12)):
+            out = (L.HaloMsg * 12)()
+            L.check(fn(nx, ny, dims, rank, out))
+            for k in range(n):
+                m, q = out[k], plan[k]
+                assert (m.dir, m.send_to, m.recv_from, m.send_count, m.recv_count, m.npop) == \
+                       (q["dir"], q["send_to"], q["recv_from"], q["send_count"], q["recv_count"], q["npop"]), (fn.__name__, rank, k)
