@@ -378,3 +378,43 @@ def test_bgk_run_decomposition_invariant_and_mass_conserving(nprocs):
     assert abs(one.gather("f").sum() - m0) < 1e-10
     assert np.isfinite(one.gather("f")).all()
     one.close(); many.close()
+
+
+# ---------------- whole-array subroutines against the reference's own text (make_golden_lid3d_fields.py) ----------------
+FGOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_lid3d_fields.npz"))
+
+
+def test_streaming_whole_array_matches_the_fortran_text():
+    wd = orc.LidWorld((5, 4, 3), 1)
+    R = wd.ranks[0]
+    R.f_post[...] = FGOLD["f_post"]
+    wd.streaming()
+    assert np.array_equal(R.f, FGOLD["streaming_f"])
+    wd.close()
+
+
+@pytest.mark.parametrize("case", range(13))
+def test_bounceback_whole_array_matches_the_fortran_text(case):
+    """the single rank, an interior block, three mixed positions and the eight corner blocks of a 3 x 3 x 3 grid: which walls a block owns, the later
+    wall winning on edges and corners, the lid term with the previous macro()'s rho -- L3/bounce_back.f90:6-83"""
+    c = FGOLD["bb_cases"][case]
+    coords, dims = tuple(int(x) for x in c[:3]), tuple(int(x) for x in c[3:])
+    total = (5 * dims[0], 4 * dims[1], 3 * dims[2])
+    wd = orc.LidWorld(total, dims[0] * dims[1] * dims[2], dims=dims)
+    R = next(Q for Q in wd.ranks if Q.coords == coords)
+    assert R.n == (5, 4, 3)
+    R.f_post[...] = FGOLD["f_post"]; R.f[...] = FGOLD["f0"]; R.rho[...] = FGOLD["rho"]
+    wd.bounceback()
+    assert np.array_equal(R.f, FGOLD[f"bounceback_{case}"])
+    wd.close()
+
+
+def test_check_sums_match_the_fortran_text():
+    wd = orc.LidWorld((5, 4, 3), 1)
+    R = wd.ranks[0]
+    for k in ("u", "v", "w", "up", "vp"):
+        getattr(R, k)[...] = FGOLD[f"check_{k}"]
+    e1, e2 = FGOLD["check_sums"]
+    assert wd.check() == np.sqrt(e1) / np.sqrt(e2)
+    assert np.array_equal(R.up, R.u) and np.array_equal(R.wp, R.w)
+    wd.close()

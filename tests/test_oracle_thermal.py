@@ -157,3 +157,50 @@ def test_check_matches_numpy():
     assert np.isclose(eu, np.sqrt(((u2 - u) ** 2 + (v2 - v) ** 2 + (w2 - w) ** 2).sum()) / np.sqrt((u2 ** 2 + v2 ** 2 + w2 ** 2).sum()), rtol=1e-12)
     assert np.isclose(et, np.abs(T2 - T).sum() / np.abs(T2).sum(), rtol=1e-12)
     wd.close()
+
+
+# ---------------- whole-array subroutines against the reference's own text (make_golden_thermal3d_fields.py) ----------------
+import os as _os  # noqa: E402
+
+FGOLD = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "ref_fortran_thermal3d_fields.npz"))
+BC_SETS = {"cavity": None, "rb": (0, 0, 0, 0, 2, 1)}          # +x,-x,+y,-y,+z,-z: the shipped benchmark cavity; RB plates (bottom hot)
+
+
+def test_streamingT_whole_array_matches_the_fortran_text():
+    wd = orc.ThermalWorld((5, 4, 3), 1)
+    R = wd.ranks[0]
+    R.g_post[...] = FGOLD["g_post"]
+    wd.streamingT()
+    assert np.array_equal(R.g, FGOLD["streamingT_g"])
+    wd.close()
+
+
+@pytest.mark.parametrize("case", range(13))
+def test_bounceback_and_bouncebackT_whole_array_match_the_fortran_text(case):
+    """B3:900-980 and B3:1106-1207 with the benchmark-cavity and the RB-convection macro sets, for the single rank, an interior
+    block, three mixed positions and the eight corner blocks of a 3 x 3 x 3 process grid"""
+    c = FGOLD["bb_cases"][case]
+    coords, dims = tuple(int(x) for x in c[:3]), tuple(int(x) for x in c[3:])
+    total = (5 * dims[0], 4 * dims[1], 3 * dims[2])
+    for tag, bcT in BC_SETS.items():
+        wd = orc.ThermalWorld(total, dims[0] * dims[1] * dims[2], dims=dims, bcT=bcT)
+        assert wd.p.paraA == FGOLD[f"paraA_{case}"][0]
+        R = next(Q for Q in wd.ranks if Q.coords == coords)
+        assert R.n == (5, 4, 3)
+        R.f_post[...] = FGOLD["f_post"]; R.f[...] = FGOLD["f0"]; R.g_post[...] = FGOLD["g_post"]; R.g[...] = FGOLD["g0"]
+        wd.bounceback(); wd.bouncebackT()
+        assert np.array_equal(R.f, FGOLD[f"bounceback_{case}"]), (case, tag)
+        assert np.array_equal(R.g, FGOLD[f"bouncebackT_{tag}_{case}"]), (case, tag)
+        wd.close()
+
+
+def test_check_sums_match_the_fortran_text():
+    wd = orc.ThermalWorld((5, 4, 3), 1)
+    R = wd.ranks[0]
+    for k in ("u", "v", "w", "up", "vp", "wp", "T", "Tp"):
+        getattr(R, k)[...] = FGOLD[f"check_{k}"]
+    e1, e2, e5, e6 = FGOLD["check_sums"]
+    eu, et = wd.check()
+    assert eu == np.sqrt(e1) / np.sqrt(e2) and et == e5 / e6
+    assert np.array_equal(R.Tp, R.T) and np.array_equal(R.wp, R.w)
+    wd.close()
