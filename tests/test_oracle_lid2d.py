@@ -149,3 +149,41 @@ def test_mass_is_conserved_and_walls_never_leak_halo_values():
     rho = wd.gather("rho")
     assert np.isfinite(rho).all() and abs(rho.sum() - m0) / m0 < 1e-13
     wd.close()
+
+
+# ---------------- the Fortran program's whole-array subroutines against its own text (make_golden_lid2d_fields.py) ----------------
+FGOLD = np.load(os.path.join(HERE, "golden", "ref_fortran_lid2d_fields.npz"))
+
+
+def test_fortran_streaming_whole_array():
+    wd = orc.Lid2DWorld((6, 5), 1, variant="f")
+    R = wd.ranks[0]
+    R.f_post[...] = FGOLD["f_post"]
+    wd.streaming()
+    assert np.array_equal(R.f, FGOLD["streaming_f"])
+    wd.close()
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_fortran_bounceback_whole_array(case):
+    """bounceback.f90:7-42 for the single rank, the interior block, the four corner blocks and the top-middle block of a 3 x 3
+    grid: which walls a block owns, the moving top wall winning in the corners, the lid term with the previous macro()'s rho"""
+    c = FGOLD["bb_cases"][case]
+    coords, dims = tuple(int(x) for x in c[:2]), tuple(int(x) for x in c[2:])
+    wd = orc.Lid2DWorld((6 * dims[0], 5 * dims[1]), dims[0] * dims[1], dims, variant="f")
+    R = next(Q for Q in wd.ranks if Q.coords == coords)
+    assert R.n == (6, 5)
+    R.f_post[...] = FGOLD["f_post"]; R.f[...] = FGOLD["f0"]; R.rho[...] = FGOLD["rho"]
+    wd.bounceback()
+    assert np.array_equal(R.f, FGOLD[f"bounceback_{case}"])
+    wd.close()
+
+
+def test_fortran_check_sums():
+    wd = orc.Lid2DWorld((6, 5), 1, variant="f")
+    R = wd.ranks[0]
+    for k in ("u", "v", "up", "vp"):
+        getattr(R, k)[...] = FGOLD[f"check_{k}"]
+    e1, e2 = FGOLD["check_sums"]
+    assert wd.check() == np.sqrt(e1) / np.sqrt(e2)
+    wd.close()
