@@ -124,3 +124,30 @@ def test_check_diff_is_max_abs_change_and_updates_previous():
     assert wd.check_diff() == np.abs(a).max()     # A_p was the all-zero interior of init()
     assert wd.check_diff() == 0.0
     wd.close()
+
+
+# ---------------- the Fortran program's text (make_golden_jacobi_fortran.py) ----------------
+FGOLD = np.load(os.path.join(HERE, "golden", "ref_fortran_jacobi.npz"))
+
+
+def test_fortran_jacobi_check_diff_and_init_match_the_text():
+    """jacobi2d_mpi.f90:176-180 with a non-zero source term, check_diff :193-198, init :151-165 for a rank that owns the top
+    boundary and one that does not"""
+    wd = orc.JacobiWorld((7, 6), 1)
+    wd.init()
+    assert np.array_equal(wd.array(0, "A"), FGOLD["init_A_0"])
+    wd.array(0, "A")[...] = FGOLD["A"]; wd.array(0, "f")[...] = FGOLD["f"]
+    wd.jacobi()
+    assert np.array_equal(wd.array(0, "A")[1:-1, 1:-1], FGOLD["A_new_interior"])        # the roles of A and A_new swapped
+    wd.close()
+    wd = orc.JacobiWorld((7, 6), 1)
+    wd.init()
+    wd.array(0, "A")[...] = FGOLD["A"]; wd.array(0, "A_p")[...] = FGOLD["A_p"]
+    assert wd.check_diff() == FGOLD["check_diff"][0]
+    wd.close()
+    wd = orc.JacobiWorld((14, 12), 4, dims=(2, 2))
+    wd.init()
+    for r, inf in enumerate(wd.info):
+        want = FGOLD["init_A_1"] if inf["coords"][1] == 1 else FGOLD["init_A_2"]
+        assert np.array_equal(wd.array(r, "A"), want) and np.array_equal(wd.array(r, "A_new"), want), inf
+    wd.close()
