@@ -12,7 +12,9 @@
  * periodic wrap followed by boundary() (c:262-313) == pull streaming from halo'd f_post followed by bounceback().
  * L2F (variant L2_F) differs from L2C only in the rounding of collision() (grouped sums, per-term divisions,
  * meq(8) = rho*u*v instead of u*v) and in check(); it is pinned through the Fortran-text evaluator
- * (tests/golden/make_golden_lid2d.py) and the seq == MPI contract (P ranks == 1 rank).
+ * (tests/golden/make_golden_lid2d.py: collision, macro, feq per cell; make_golden_lid2d_fields.py: streaming,
+ * bounceback for the block positions that change the owned walls, the check() sums as whole arrays) and the
+ * seq == MPI contract (P ranks == 1 rank).
  *
  * Layout is L2F's: column-major, population index fastest: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v,up,vp(nx,ny)
  * (initial.f90:30-38); tests transpose when they compare with the C program's f[NX][NY][9], rho[NX][NY].

@@ -4,12 +4,20 @@
  * "L3" below).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this; the product (mglc_b200/, libmglc.so) never does.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden vectors or fixtures for this
- * path and its Fortran+MPI sources cannot be compiled in this image (no gfortran / mpif90).  This
- * restatement is pinned instead by analytic known answers (tests/test_oracle_lid.py: M^-1 M = I,
- * M feq = meq, rest equilibrium fixed point, delta-population transport, mass conservation, no NaN
- * leaking from poisoned wall halos) and by the reference's implicit seq == MPI contract
- * (decomposition invariance, bit for bit).
+ * PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path and its Fortran+MPI
+ * sources cannot be compiled in this image (no gfortran / mpif90), so the restatement is pinned to the
+ * reference's own SOURCE TEXT: tests/golden/fortran_eval.py machine-evaluates the Fortran statements where
+ * they lie under /root/reference and the generators commit the numbers --
+ *   per cell     collision.f90:20-189, macro.f90:13-22, initial.f90:66-70  (make_golden_fortran.py ->
+ *                ref_fortran_kernels.npz)
+ *   whole array  streaming.f90:8-20, bounce_back.f90:6-83 for every wall combination a block can own (the
+ *                later wall winning on edges, the lid term with the previous rho), check.f90:9-19
+ *                (make_golden_lid3d_fields.py -> ref_fortran_lid3d_fields.npz)
+ * -- and tests/test_oracle_lid.py requires this file to reproduce them bit for bit.  On top: analytic known
+ * answers (M^-1 M = I, M feq = meq, rest equilibrium fixed point, delta-population transport, mass
+ * conservation, no NaN leaking from poisoned wall halos) and the reference's implicit seq == MPI contract
+ * (decomposition invariance, bit for bit).  The exchange (ex_sendrecv.f90) is MPI calls and cannot be
+ * evaluated; it is checked by construction tests and, across real processes, by tests/test_gloo_multiprocess.py.
  *
  * Layout is the reference's: Fortran column-major, AoS with the population index fastest,
  *   f     (0:18, 1:nx,   1:ny,   1:nz  )      L3/initial.f90:43

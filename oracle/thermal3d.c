@@ -8,8 +8,11 @@
  * PARITY PIN: the Fortran+MPI program cannot be built in this image.  The per-cell arithmetic restated
  * here (collision + forcing, macro, collisionT, both equilibria, the module parameters) is checked bit for
  * bit against vectors obtained by machine-evaluating the reference's own source text
- * (tests/golden/make_golden_fortran.py -> tests/golden/ref_fortran_kernels.npz); streaming, boundary rules
- * and the exchange are pure copies checked by construction tests (tests/test_oracle_thermal.py).
+ * (tests/golden/make_golden_fortran.py -> tests/golden/ref_fortran_kernels.npz); the copy-type subroutines are
+ * pinned the same way as whole arrays (make_golden_thermal3d_fields.py -> ref_fortran_thermal3d_fields.npz:
+ * streamingT B3:1081-1094, bounceback B3:900-980, bouncebackT B3:1106-1207 with the benchmark-cavity and the
+ * RB-convection macro sets for 13 block positions, the check() sums B3:1242-1264); the exchange is MPI calls and is
+ * checked by construction tests (tests/test_oracle_thermal.py).
  *
  * Layout is the reference's (B3:483-492): f(0:18,nx,ny,nz), f_post(0:18,0:nx+1,0:ny+1,0:nz+1),
  * g(0:6,nx,ny,nz), g_post(0:6,0:nx+1,...), rho,u,v,w,T,Fx,Fy,Fz,up,vp,wp,Tp (nx,ny,nz), column-major.
