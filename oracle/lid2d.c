@@ -1,8 +1,9 @@
 /*
  * oracle/lid2d.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's 2-D D2Q9 MRT lid-driven
- * cavity, in its two shipped forms:
+ * cavity, in its three shipped forms:
  *   L2C  MPI/Lid_driven_cavity/c/lid_driven_cavity.c                      (plain C, one domain, 200 x 200)
  *   L2F  MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/ (.f90)   (Fortran + MPI, 2-D Cartesian blocks, 201 x 201)
+ *   L2I  MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90  (sequential, incompressible model, 257 x 257)
  * Only tests/ and __graft_entry__.smoke() may load this; the product never does.
  *
  * PARITY PIN: L2C is the one LBM program of the reference this image can compile.  oracle/Makefile `ref` builds it
@@ -15,6 +16,11 @@
  * (tests/golden/make_golden_lid2d.py: collision, macro, feq per cell; make_golden_lid2d_fields.py: streaming,
  * bounceback for the block positions that change the owned walls, the check() sums as whole arrays) and the
  * seq == MPI contract (P ranks == 1 rank).
+ * L2I (variant L2_I) is L2F with the incompressible equilibrium: meq without the rho factors (inc:195-202), u, v = the
+ * momentum sums undivided (inc:307-308), the lid term without rho (inc:291-292), initial() with rho = 0 and f = omega*(...)
+ * (inc:137,160; so the first collision() relaxes towards meq(1) = 3|u|^2, meq(2) = -3|u|^2), and check() as a ratio of
+ * sums of dsqrt (inc:327-335).  Pinned through the same evaluator (make_golden_lid2d_incomp.py: every subroutine as whole
+ * arrays).  The program is sequential; on P ranks the restatement exchanges halos as L2F does (P ranks == 1 rank).
  *
  * Layout is L2F's: column-major, population index fastest: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v,up,vp(nx,ny)
  * (initial.f90:30-38); tests transpose when they compare with the C program's f[NX][NY][9], rho[NX][NY].
@@ -25,7 +31,7 @@
 #include <string.h>
 
 #define Q9 9
-enum { L2_C = 0, L2_F = 1 };
+enum { L2_C = 0, L2_F = 1, L2_I = 2 };
 
 /* commondata.f90:25-27 == c:24-25 */
 static const int ex[Q9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
@@ -125,7 +131,8 @@ void l2_initial(l2_world *w) {
         l2_rank *R = &w->r[r];
         for (int j = 1; j <= R->ny; ++j)
             for (int i = 1; i <= R->nx; ++i) {
-                S(R, rho, i, j) = w->rho0; S(R, u, i, j) = 0.0; S(R, v, i, j) = 0.0; S(R, up, i, j) = 0.0; S(R, vp, i, j) = 0.0;
+                S(R, rho, i, j) = w->variant == L2_I ? 0.0 : w->rho0;      /* inc:137 */
+                S(R, u, i, j) = 0.0; S(R, v, i, j) = 0.0; S(R, up, i, j) = 0.0; S(R, vp, i, j) = 0.0;
             }
         if (R->coords[1] == w->dims[1] - 1)
             for (int i = 1; i <= R->nx; ++i) S(R, u, i, R->ny) = w->U0;
@@ -134,13 +141,14 @@ void l2_initial(l2_world *w) {
                 double us2 = S(R, u, i, j) * S(R, u, i, j) + S(R, v, i, j) * S(R, v, i, j);
                 for (int a = 0; a < Q9; ++a) {
                     double un = S(R, u, i, j) * (double)ex[a] + S(R, v, i, j) * (double)ey[a];
-                    F(R, a, i, j) = S(R, rho, i, j) * omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
+                    if (w->variant == L2_I) F(R, a, i, j) = omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);      /* inc:160 */
+                    else F(R, a, i, j) = S(R, rho, i, j) * omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
                 }
             }
     }
 }
 
-/* collision() of one cell.  variant L2_C: c:186-255 ; variant L2_F: evolution.f90:15-70 */
+/* collision() of one cell.  variant L2_C: c:186-255 ; variant L2_F: evolution.f90:15-70 ; variant L2_I: inc:183-233 */
 void l2_collide_cell(int variant, const double *f, double rho, double u, double v, double Snu, double Sq, double *fp) {
     double m[Q9], meq[Q9], mp[Q9];
     const double s[Q9] = {0.0, Snu, Snu, 0.0, Sq, 0.0, Sq, Snu, Snu};
@@ -184,14 +192,25 @@ void l2_collide_cell(int variant, const double *f, double rho, double u, double 
         m[7] = f[1] - f[2] + f[3] - f[4];
         m[8] = f[5] - f[6] + f[7] - f[8];
         meq[0] = rho;
-        meq[1] = rho * (-2.0 + 3.0 * (u * u + v * v));
-        meq[2] = rho * (1.0 - 3.0 * (u * u + v * v));
-        meq[3] = rho * u;
-        meq[4] = -rho * u;
-        meq[5] = rho * v;
-        meq[6] = -rho * v;
-        meq[7] = rho * (u * u - v * v);
-        meq[8] = rho * (u * v);
+        if (variant == L2_I) {                           /* inc:194-202 */
+            meq[1] = -2.0 * rho + 3.0 * (u * u + v * v);
+            meq[2] = rho - 3.0 * (u * u + v * v);
+            meq[3] = u;
+            meq[4] = -u;
+            meq[5] = v;
+            meq[6] = -v;
+            meq[7] = u * u - v * v;
+            meq[8] = u * v;
+        } else {
+            meq[1] = rho * (-2.0 + 3.0 * (u * u + v * v));
+            meq[2] = rho * (1.0 - 3.0 * (u * u + v * v));
+            meq[3] = rho * u;
+            meq[4] = -rho * u;
+            meq[5] = rho * v;
+            meq[6] = -rho * v;
+            meq[7] = rho * (u * u - v * v);
+            meq[8] = rho * (u * v);
+        }
         for (int a = 0; a < Q9; ++a) mp[a] = m[a] - s[a] * (m[a] - meq[a]);
         fp[0] = (mp[0] - mp[1] + mp[2]) / 9.0;
         fp[1] = mp[0] / 9.0 - mp[1] / 36.0 - mp[2] / 18.0 + mp[3] / 6.0 - mp[4] / 6.0 + mp[7] * 0.25;
@@ -260,8 +279,13 @@ void l2_bounceback(l2_world *w) {
         if (R->coords[1] == w->dims[1] - 1)
             for (int i = 1; i <= nx; ++i) {
                 F(R, 4, i, ny) = FP(R, 2, i, ny);
-                F(R, 7, i, ny) = FP(R, 5, i, ny) - S(R, rho, i, ny) * (w->U0) / 6.0;
-                F(R, 8, i, ny) = FP(R, 6, i, ny) - S(R, rho, i, ny) * (-w->U0) / 6.0;
+                if (w->variant == L2_I) {                /* inc:291-292 */
+                    F(R, 7, i, ny) = FP(R, 5, i, ny) - (w->U0) / 6.0;
+                    F(R, 8, i, ny) = FP(R, 6, i, ny) - (-w->U0) / 6.0;
+                } else {
+                    F(R, 7, i, ny) = FP(R, 5, i, ny) - S(R, rho, i, ny) * (w->U0) / 6.0;
+                    F(R, 8, i, ny) = FP(R, 6, i, ny) - S(R, rho, i, ny) * (-w->U0) / 6.0;
+                }
             }
     }
 }
@@ -275,14 +299,19 @@ void l2_macro(l2_world *w) {
                 const double *f = &F(R, 0, i, j);
                 double rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
                 S(R, rho, i, j) = rho;
-                S(R, u, i, j) = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / rho;
-                S(R, v, i, j) = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / rho;
+                if (w->variant == L2_I) {                /* inc:307-308 */
+                    S(R, u, i, j) = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]);
+                    S(R, v, i, j) = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]);
+                } else {
+                    S(R, u, i, j) = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / rho;
+                    S(R, v, i, j) = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / rho;
+                }
             }
     }
 }
 
 /* check(): L2F evolution.f90:128-147 (rank sums, then Allreduce in rank order); L2C c:341-363 (pow(.,2), grouped add,
- * cells in i-outer / j-inner order, pow(.,0.5)) */
+ * cells in i-outer / j-inner order, pow(.,0.5)); L2I inc:316-341 (sums of dsqrt, errorU = error1/error2) */
 double l2_check(l2_world *w) {
     double t1 = 0.0, t2 = 0.0;
     for (int r = 0; r < w->np; ++r) {
@@ -293,6 +322,13 @@ double l2_check(l2_world *w) {
                 for (int j = 1; j <= R->ny; ++j) {
                     e1 += pow(S(R, u, i, j) - S(R, up, i, j), 2) + pow(S(R, v, i, j) - S(R, vp, i, j), 2);
                     e2 += pow(S(R, u, i, j), 2) + pow(S(R, v, i, j), 2);
+                    S(R, up, i, j) = S(R, u, i, j); S(R, vp, i, j) = S(R, v, i, j);
+                }
+        } else if (w->variant == L2_I) {                 /* inc:325-332 */
+            for (int j = 1; j <= R->ny; ++j)
+                for (int i = 1; i <= R->nx; ++i) {
+                    e1 = e1 + sqrt((S(R, u, i, j) - S(R, up, i, j)) * (S(R, u, i, j) - S(R, up, i, j)) + (S(R, v, i, j) - S(R, vp, i, j)) * (S(R, v, i, j) - S(R, vp, i, j)));
+                    e2 = e2 + sqrt(S(R, u, i, j) * S(R, u, i, j) + S(R, v, i, j) * S(R, v, i, j));
                     S(R, up, i, j) = S(R, u, i, j); S(R, vp, i, j) = S(R, v, i, j);
                 }
         } else {
@@ -306,7 +342,7 @@ double l2_check(l2_world *w) {
         }
         t1 += e1; t2 += e2;
     }
-    w->errorU = w->variant == L2_C ? pow(t1, 0.5) / pow(t2, 0.5) : sqrt(t1) / sqrt(t2);
+    w->errorU = w->variant == L2_C ? pow(t1, 0.5) / pow(t2, 0.5) : w->variant == L2_I ? t1 / t2 : sqrt(t1) / sqrt(t2);   /* inc:335 */
     return w->errorU;
 }
 

@@ -187,3 +187,84 @@ def test_fortran_check_sums():
     e1, e2 = FGOLD["check_sums"]
     assert wd.check() == np.sqrt(e1) / np.sqrt(e2)
     wd.close()
+
+
+# ---------------- the incompressible sequential program (variant "i") against its own text (make_golden_lid2d_incomp.py) ----------------
+IGOLD = np.load(os.path.join(HERE, "golden", "ref_fortran_lid2d_incomp.npz"))
+
+
+def _incomp_world(nprocs=1, dims=None):
+    nx, ny = (int(x) for x in IGOLD["shape"])
+    wd = orc.Lid2DWorld((nx, ny), nprocs, dims, variant="i")
+    assert (wd.tauf, wd.Snu, wd.Sq) == tuple(IGOLD["params"])
+    return wd
+
+
+def test_incompressible_subroutines_whole_array():
+    """lid-driven_cavity_incompress.f90: collision :181-236, streaming :249-259, bounceback :270-293, macro :304-310,
+    check :322-335 on seeded arrays, bit for bit"""
+    wd = _incomp_world()
+    R = wd.ranks[0]
+
+    def load():
+        R.f[...] = IGOLD["in/f0"]; R.f_post[...] = IGOLD["in/f_post"]
+        for k in ("rho", "u", "v", "up", "vp"):
+            getattr(R, k)[...] = IGOLD["in/" + k]
+
+    load(); wd.collision()
+    assert np.array_equal(R.f_post[:, 1:-1, 1:-1], IGOLD["collision/f_post"])
+    load(); wd.streaming()
+    assert np.array_equal(R.f, IGOLD["streaming/f"])
+    load(); wd.bounceback()
+    assert np.array_equal(R.f, IGOLD["bounceback/f"])
+    load(); wd.macro()
+    assert np.array_equal(np.stack([R.rho, R.u, R.v]), IGOLD["macro/ruv"])
+    load()
+    e1, e2, eu = IGOLD["check/e1_e2_errorU"]
+    assert wd.check() == eu == e1 / e2
+    assert np.array_equal(R.up, IGOLD["in/u"]) and np.array_equal(R.vp, IGOLD["in/v"])
+    wd.close()
+
+
+def test_incompressible_differs_from_the_compressible_program():
+    """the variant is not a relabelling: same inputs, different f_post / u / lid populations"""
+    a, b = _incomp_world(), orc.Lid2DWorld(tuple(int(x) for x in IGOLD["shape"]), 1, variant="f")
+    for wd in (a, b):
+        R = wd.ranks[0]
+        R.f[...] = IGOLD["in/f0"]; R.f_post[...] = IGOLD["in/f_post"]
+        for k in ("rho", "u", "v"):
+            getattr(R, k)[...] = IGOLD["in/" + k]
+        wd.collision()
+    assert not np.array_equal(a.ranks[0].f_post, b.ranks[0].f_post)
+    for wd in (a, b):
+        wd.ranks[0].f_post[...] = IGOLD["in/f_post"]
+        wd.bounceback(); wd.macro()
+    assert not np.array_equal(a.ranks[0].f[7, :, -1], b.ranks[0].f[7, :, -1])
+    assert np.array_equal(a.ranks[0].rho[:, :-1], b.ranks[0].rho[:, :-1]) and not np.array_equal(a.ranks[0].u[:, :-1], b.ranks[0].u[:, :-1])
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (4, (2, 2)), (6, (3, 2))])
+def test_incompressible_program_run(nprocs, dims):
+    """initial() (rho = 0 until the first macro(): the first collision() relaxes towards meq(1) = 3|u|^2) and 1, 2, 20, 25
+    iterations of the program's loop with check() after 20 and 25; on P emulated ranks the halo exchange of the MPI program
+    makes the blocks reproduce the sequential program bit for bit"""
+    wd = _incomp_world(nprocs, dims)
+    wd.initial()
+    assert np.array_equal(wd.gather("f"), IGOLD["run0/f"])
+    assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v")]), IGOLD["run0/ruv"])
+    assert not wd.gather("rho").any()
+    done = 0
+    for n in (1, 2, 20):
+        wd.step(n - done); done = n
+        assert np.array_equal(wd.gather("f"), IGOLD[f"run{n}/f"]), n
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v")]), IGOLD[f"run{n}/ruv"]), n
+    e = wd.check()
+    if nprocs == 1:
+        assert e == IGOLD["run20/check"][2]
+    else:
+        assert abs(e - IGOLD["run20/check"][2]) <= 1e-14 * abs(e)        # rank sums add in a different order
+    wd.step(5)
+    e = wd.check()
+    assert abs(e - IGOLD["run25/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
+    wd.close()
