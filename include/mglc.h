@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGLC_VERSION 103
+#define MGLC_VERSION 104
 
 /* ---- status codes ---- */
 #define MGLC_OK          0
@@ -331,18 +331,22 @@ int mglc_p2d_launch_count(mglc_p2d *h, long long *n);
 int mglc_p2d_sync(mglc_p2d *h);
 
 /* ================= 2-D D2Q9 lid-driven cavity =================
- * The reference ships it twice: L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c (plain C, one domain, 200 x 200) and
+ * The reference ships it as L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c (plain C, one domain, 200 x 200) and
  * L2F = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/ (Fortran + MPI, 2-D Cartesian blocks, 201 x 201).  They differ only
  * in the rounding of collision() (L2C: (...)/36.0 and meq(8) = u*v, c:186-255; L2F: per-term divisions and meq(8) = rho*u*v,
- * evolution.f90:15-70) and in check(); `variant` picks the one to reproduce.  Host arrays are L2F's, column-major:
+ * evolution.f90:15-70) and in check(); `variant` picks the one to reproduce.  A third program,
+ * L2I = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (sequential, 257 x 257), is L2F with the
+ * incompressible equilibrium: meq without the rho factors (L2I:195-202), u, v = the undivided momentum sums (L2I:307-308), the lid
+ * term -(+-U0)/6 without rho (L2I:291-292), initial() leaving rho = 0 and f = omega*(...) (L2I:137,160), check() = ratio of the
+ * sums of dsqrt (L2I:327-335); MGLC_L2D_INCOMP reproduces it and decomposes like L2F.  Host arrays are L2F's, column-major:
  * f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v(nx,ny) (initial.f90:30-38); L2C's f[NX][NY][9] is the same memory read as
  * (0:8,ny,nx), i.e. the caller transposes x and y.  A handle owns ONE subdomain (one process per GPU, halos over NCCL) or
  * all P of them (mglc_l2d_create_local); `r` = index among those owned. */
-enum { MGLC_L2D_C = 0, MGLC_L2D_F = 1 };
+enum { MGLC_L2D_C = 0, MGLC_L2D_F = 1, MGLC_L2D_INCOMP = 2 };
 typedef struct mglc_l2d mglc_l2d;
 typedef struct mglc_l2d_desc {
     int total_nx, total_ny;              /* commondata.f90:4 ; c:9-10                       */
-    int variant;                         /* MGLC_L2D_C | MGLC_L2D_F                         */
+    int variant;                         /* MGLC_L2D_C | MGLC_L2D_F | MGLC_L2D_INCOMP       */
     int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT             */
     double reynolds, U0, rho0;           /* 1000, 0.1, 1    commondata.f90:6-8 ; c:15-17    */
 } mglc_l2d_desc;

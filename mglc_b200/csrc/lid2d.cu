@@ -1,7 +1,10 @@
 // lid2d.cu -- the reference's 2-D D2Q9 MRT lid-driven cavity behind the mglc_l2d_* entry points of mglc.h:
 //   L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c                      (plain C, one domain, 200 x 200)
 //   L2F = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/*.f90     (Fortran + MPI, 2-D Cartesian blocks, 201 x 201)
-// The two programs differ only in the rounding of collision() and in check(); `variant` selects which one is reproduced.
+//   L2I = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (sequential, incompressible model, 257 x 257)
+// L2C and L2F differ only in the rounding of collision() and in check(); L2I is L2F with the incompressible equilibrium (no rho
+// factors in meq, u and v undivided, the lid term without rho, rho = 0 before the first macro(), check() as a ratio of sums of
+// square roots); `variant` selects which program is reproduced.  L2I decomposes like L2F (same halo messages).
 // This file holds the strict build of the collision / fused kernels (-fmad=false), the copy-type subroutines (streaming,
 // bounceback, macro, initial, check, halo pack/unpack, layout transposes) and the host side; lid2d_fast.cu is the
 // throughput build of the same kernel source.
@@ -21,163 +24,7 @@ using namespace mglc;
 
 namespace {
 
-// commondata.f90:25-27 == c:24-25
-__constant__ int c_ex9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
-__constant__ int c_ey9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-const int h_ex9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
-const int h_ey9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-// populations leaving through each side, ascending = tag order of ex_sendrecv.f90:9-45 (to right, left, top, bottom)
-__constant__ int c_face_pops9[4][3] = {{1, 5, 8}, {3, 6, 7}, {2, 5, 6}, {4, 7, 8}};
-
-// initial(): initial.f90:40-66 == c:123-151
-__global__ void __launch_bounds__(128) k_l2_initial(Geom2 g, L2Params p, int lid, double *__restrict__ F, double *__restrict__ rho,
-                                                    double *__restrict__ u, double *__restrict__ v, double *__restrict__ up,
-                                                    double *__restrict__ vp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
-    if (i > g.nx) return;
-    const double omega[9] = {4.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
-    const long long c = g.idx(0, i, j), m = g.cell(i, j);
-    const double r = p.rho0, uu = (lid && j == g.ny) ? p.U0 : 0.0, vv = 0.0;
-    rho[m] = r; u[m] = uu; v[m] = vv; up[m] = 0.0; vp[m] = 0.0;
-    const double us2 = uu * uu + vv * vv;
-#pragma unroll
-    for (int a = 0; a < 9; ++a) {
-        const double un = uu * (double)c_ex9[a] + vv * (double)c_ey9[a];
-        F[a * g.sq + c] = r * omega[a] * (1.0 + 3.0 * un + 4.5 * un * un - 1.5 * us2);
-    }
-}
-
-// streaming(): evolution.f90:80-97 (pull from the halo'd f_post; wall halos are read as they are, like the reference)
-__global__ void __launch_bounds__(128) k_l2_streaming(Geom2 g, const double *__restrict__ Fpost, double *__restrict__ F) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
-    if (i > g.nx) return;
-    const long long c = g.idx(0, i, j);
-#pragma unroll
-    for (int a = 0; a < 9; ++a) F[a * g.sq + c] = Fpost[a * g.sq + c - c_ey9[a] * g.sy - c_ex9[a]];
-}
-
-// bounceback(): bounceback.f90:7-40 == boundary(), c:286-313.  One thread per wall cell applies left, right, bottom, top in
-// the reference's order, so the later wall wins in the corners exactly as in the sequential loops.
-__global__ void __launch_bounds__(128) k_l2_bounceback(Geom2 g, L2Params p, const double *__restrict__ Fpost,
-                                                       const double *__restrict__ rho, double *__restrict__ F) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int i, j;
-    if (t < g.nx) { i = t + 1; j = 1; }
-    else if (t < 2 * g.nx) { i = t - g.nx + 1; j = g.ny; if (g.ny == 1) return; }
-    else if (t < 2 * g.nx + (g.ny - 2)) { i = 1; j = t - 2 * g.nx + 2; }
-    else if (t < 2 * g.nx + 2 * (g.ny - 2)) { i = g.nx; j = t - 2 * g.nx - (g.ny - 2) + 2; if (g.nx == 1) return; }
-    else return;
-    const long long c = g.idx(0, i, j), sq = g.sq;
-    if (g.wall[1] && i == 1) { F[1 * sq + c] = Fpost[3 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[8 * sq + c] = Fpost[6 * sq + c]; }
-    if (g.wall[0] && i == g.nx) { F[3 * sq + c] = Fpost[1 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; F[7 * sq + c] = Fpost[5 * sq + c]; }
-    if (g.wall[3] && j == 1) { F[2 * sq + c] = Fpost[4 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; }
-    if (g.wall[2] && j == g.ny) {
-        const double r = rho[g.cell(i, j)];
-        F[4 * sq + c] = Fpost[2 * sq + c];
-        F[7 * sq + c] = Fpost[5 * sq + c] - r * p.U0 / 6.0;
-        F[8 * sq + c] = Fpost[6 * sq + c] - r * (-p.U0) / 6.0;
-    }
-}
-
-// macro(): evolution.f90:105-113 == c:321-336
-__global__ void __launch_bounds__(128) k_l2_macro(Geom2 g, const double *__restrict__ F, double *__restrict__ rho,
-                                                  double *__restrict__ u, double *__restrict__ v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
-    if (i > g.nx) return;
-    const long long c = g.idx(0, i, j), m = g.cell(i, j);
-    double f[9];
-#pragma unroll
-    for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
-    const double r = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
-    rho[m] = r;
-    u[m] = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / r;
-    v[m] = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / r;
-}
-
-// the lid row of rho, kept beside the rotated loop (the lid term uses rho of the previous macro(), bounceback.f90:35-36)
-__global__ void k_l2_lid_row(Geom2 g, const double *__restrict__ rho, double *__restrict__ lid) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i <= g.nx) lid[i - 1] = rho[g.cell(i, g.ny)];
-}
-
-// check(): evolution.f90:128-147 == c:341-363: error1 = sum (du^2 + dv^2), error2 = sum (u^2 + v^2); up, vp <- u, v
-constexpr int L2_CHECK_BLOCKS = 296;   // fixed: reproducible summation order
-__global__ void __launch_bounds__(256) k_l2_check_partial(long long n, const double *__restrict__ u, const double *__restrict__ v,
-                                                          double *__restrict__ up, double *__restrict__ vp, double *__restrict__ part) {
-    double e1 = 0.0, e2 = 0.0;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-        const double a = u[q], b = v[q];
-        const double da = a - up[q], db = b - vp[q];
-        e1 += da * da + db * db;
-        e2 += a * a + b * b;
-        up[q] = a; vp[q] = b;
-    }
-    __shared__ double s1[256], s2[256];
-    s1[threadIdx.x] = e1; s2[threadIdx.x] = e2;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { part[2 + 2 * blockIdx.x] = s1[0]; part[3 + 2 * blockIdx.x] = s2[0]; }
-}
-__global__ void k_l2_check_final(int nblocks, double *__restrict__ part) {
-    double e1 = 0.0, e2 = 0.0;
-    for (int b = 0; b < nblocks; ++b) { e1 += part[2 + 2 * b]; e2 += part[3 + 2 * b]; }
-    part[0] = e1; part[1] = e2;
-}
-
-// halo messages of message_passing_sendrecv(), ex_sendrecv.f90:9-78: dir 0..3 = to right(+x), left(-x), top(+y), bottom(-y), three
-// populations over the interior range, buffer [slot][t]; dir 4..7 = the corner population 5..8 crosses, one value.
-__device__ __forceinline__ void l2_msg_cell(const Geom2 &g, int dir, int ghost, int t, int &i, int &j) {
-    if (dir < 4) {
-        const int axis = dir >> 1, plus = !(dir & 1);
-        const int nfix = axis == 0 ? g.nx : g.ny;
-        const int fix = ghost ? (plus ? 0 : nfix + 1) : (plus ? nfix : 1);
-        i = axis == 0 ? fix : 1 + t;
-        j = axis == 1 ? fix : 1 + t;
-    } else {
-        const int a = dir + 1, px = c_ex9[a] > 0, py = c_ey9[a] > 0;
-        i = ghost ? (px ? 0 : g.nx + 1) : (px ? g.nx : 1);
-        j = ghost ? (py ? 0 : g.ny + 1) : (py ? g.ny : 1);
-    }
-}
-__global__ void k_l2_pack(Geom2 g, const double *__restrict__ Fpost, int dir, int n1, int npop, double *__restrict__ buf) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n1 * npop) return;
-    int i, j;
-    l2_msg_cell(g, dir, 0, t % n1, i, j);
-    const int a = dir < 4 ? c_face_pops9[dir][t / n1] : dir + 1;
-    buf[t] = Fpost[g.idx(a, i, j)];
-}
-__global__ void k_l2_unpack(Geom2 g, double *__restrict__ Fpost, int dir, int n1, int npop, const double *__restrict__ buf) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n1 * npop) return;
-    int i, j;
-    l2_msg_cell(g, dir, 1, t % n1, i, j);
-    const int a = dir < 4 ? c_face_pops9[dir][t / n1] : dir + 1;
-    Fpost[g.idx(a, i, j)] = buf[t];
-}
-
-// reference layout (population index fastest; with_halo: (0:8,0:nx+1,0:ny+1), else (0:8,nx,ny)) <-> SoA rows
-__global__ void __launch_bounds__(128) k_l2_aos_to_soa(Geom2 g, const double *__restrict__ aos, double *__restrict__ F, int with_halo) {
-    const int w = with_halo ? g.nx + 2 : g.nx, hgt = with_halo ? g.ny + 2 : g.ny;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w || y >= hgt) return;
-    const int i = with_halo ? x : x + 1, j = with_halo ? y : y + 1;
-    const long long src = 9LL * (x + (long long)w * y), c = g.idx(0, i, j);
-#pragma unroll
-    for (int a = 0; a < 9; ++a) F[a * g.sq + c] = aos[src + a];
-}
-__global__ void __launch_bounds__(128) k_l2_soa_to_aos(Geom2 g, const double *__restrict__ F, double *__restrict__ aos, int with_halo) {
-    const int w = with_halo ? g.nx + 2 : g.nx, hgt = with_halo ? g.ny + 2 : g.ny;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w || y >= hgt) return;
-    const int i = with_halo ? x : x + 1, j = with_halo ? y : y + 1;
-    const long long dst = 9LL * (x + (long long)w * y), c = g.idx(0, i, j);
-#pragma unroll
-    for (int a = 0; a < 9; ++a) aos[dst + a] = F[a * g.sq + c];
-}
+#include "lid2d_exact.inl"
 
 struct L2Sub {
     int n[2], coords[2], start[2];
@@ -222,10 +69,10 @@ struct mglc_l2d {
 };
 
 extern "C" int mglc_l2d_desc_init(mglc_l2d_desc *d, int variant) {
-    if (!d || (variant != MGLC_L2D_C && variant != MGLC_L2D_F)) { set_error("mglc_l2d_desc_init: variant=%d", variant); return MGLC_E_INVALID; }
+    if (!d || (variant != MGLC_L2D_C && variant != MGLC_L2D_F && variant != MGLC_L2D_INCOMP)) { set_error("mglc_l2d_desc_init: variant=%d", variant); return MGLC_E_INVALID; }
     memset(d, 0, sizeof *d);
     d->variant = variant;
-    d->total_nx = d->total_ny = variant == MGLC_L2D_C ? 200 : 201;      // c:9-10 ; commondata.f90:4
+    d->total_nx = d->total_ny = variant == MGLC_L2D_C ? 200 : variant == MGLC_L2D_F ? 201 : 257;      // c:9-10 ; commondata.f90:4 ; L2I:7
     d->arith = MGLC_ARITH_FAST;
     d->reynolds = 1000.0; d->U0 = 0.1; d->rho0 = 1.0;                   // c:15-17 ; commondata.f90:6-8
     return MGLC_OK;
@@ -353,7 +200,7 @@ static int l2_make_sub(mglc_l2d *h, int rank, int device, L2Sub **out) {
 
 static int l2_new(mglc_l2d **out, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks) {
     if (!out || !d || nranks < 1) { set_error("mglc_l2d_create: bad arguments"); return MGLC_E_INVALID; }
-    if (d->total_nx < 1 || d->total_ny < 1 || (d->variant != MGLC_L2D_C && d->variant != MGLC_L2D_F) ||
+    if (d->total_nx < 1 || d->total_ny < 1 || (d->variant != MGLC_L2D_C && d->variant != MGLC_L2D_F && d->variant != MGLC_L2D_INCOMP) ||
         (d->arith != MGLC_ARITH_FAST && d->arith != MGLC_ARITH_STRICT) || !(d->reynolds > 0.0)) {
         set_error("mglc_l2d_create: bad descriptor (%d x %d, variant %d, arith %d, Re %g)", d->total_nx, d->total_ny, d->variant, d->arith, d->reynolds);
         return MGLC_E_INVALID;
@@ -495,7 +342,8 @@ extern "C" int mglc_l2d_initial(mglc_l2d *h) {
     if (!h) return MGLC_E_INVALID;
     for (L2Sub *S : h->subs) {
         MGLC_TRY(l2_use(S));
-        k_l2_initial<<<l2_grid(S), 128, 0, S->s>>>(S->g, h->p, S->g.wall[2], S->F, S->rho, S->u, S->v, S->up, S->vp);
+        if (h->d.variant == MGLC_L2D_INCOMP) k_l2_initial<true><<<l2_grid(S), 128, 0, S->s>>>(S->g, h->p, S->g.wall[2], S->F, S->rho, S->u, S->v, S->up, S->vp);
+        else k_l2_initial<false><<<l2_grid(S), 128, 0, S->s>>>(S->g, h->p, S->g.wall[2], S->F, S->rho, S->u, S->v, S->up, S->vp);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -565,7 +413,8 @@ extern "C" int mglc_l2d_bounceback(mglc_l2d *h) {
     for (L2Sub *S : h->subs) {
         MGLC_TRY(l2_use(S));
         const int cells = 2 * S->n[0] + 2 * std::max(S->n[1] - 2, 0);
-        k_l2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p, S->P[S->cur], S->rho, S->F);
+        if (h->d.variant == MGLC_L2D_INCOMP) k_l2_bounceback<true><<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p, S->P[S->cur], S->rho, S->F);
+        else k_l2_bounceback<false><<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p, S->P[S->cur], S->rho, S->F);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -574,7 +423,8 @@ extern "C" int mglc_l2d_macro(mglc_l2d *h) {
     if (!h) return MGLC_E_INVALID;
     for (L2Sub *S : h->subs) {
         MGLC_TRY(l2_use(S));
-        k_l2_macro<<<l2_grid(S), 128, 0, S->s>>>(S->g, S->F, S->rho, S->u, S->v);
+        if (h->d.variant == MGLC_L2D_INCOMP) k_l2_macro<true><<<l2_grid(S), 128, 0, S->s>>>(S->g, S->F, S->rho, S->u, S->v);
+        else k_l2_macro<false><<<l2_grid(S), 128, 0, S->s>>>(S->g, S->F, S->rho, S->u, S->v);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -629,7 +479,7 @@ static int l2_step_impl(mglc_l2d *h, int nsteps) {
     MGLC_TRY(l2_exchange(h));
     for (L2Sub *S : h->subs) {
         MGLC_TRY(l2_use(S));
-        S->launches += strict::launch_l2_stream_macro(S->g, h->p, S->P[S->cur], S->F, S->lid[lid], S->rho, S->u, S->v, S->s);
+        S->launches += strict::launch_l2_stream_macro(S->g, h->p, h->d.variant, S->P[S->cur], S->F, S->lid[lid], S->rho, S->u, S->v, S->s);
     }
     return MGLC_OK;
 }
@@ -658,12 +508,13 @@ extern "C" int mglc_l2d_step_timed(mglc_l2d *h, int nsteps, float *ms) {
     return MGLC_OK;
 }
 
-// check(): evolution.f90:128-147 (rank sums + 2 MPI_Allreduce) == c:341-363
+// check(): evolution.f90:128-147 (rank sums + 2 MPI_Allreduce) == c:341-363; L2I:316-340
 extern "C" int mglc_l2d_check(mglc_l2d *h, double *errorU) {
     if (!h || !errorU) return MGLC_E_INVALID;
     for (L2Sub *S : h->subs) {
         MGLC_TRY(l2_use(S));
-        k_l2_check_partial<<<L2_CHECK_BLOCKS, 256, 0, S->s>>>((long long)S->n[0] * S->n[1], S->u, S->v, S->up, S->vp, S->scratch);
+        if (h->d.variant == MGLC_L2D_INCOMP) k_l2_check_partial<true><<<L2_CHECK_BLOCKS, 256, 0, S->s>>>((long long)S->n[0] * S->n[1], S->u, S->v, S->up, S->vp, S->scratch);
+        else k_l2_check_partial<false><<<L2_CHECK_BLOCKS, 256, 0, S->s>>>((long long)S->n[0] * S->n[1], S->u, S->v, S->up, S->vp, S->scratch);
         k_l2_check_final<<<1, 1, 0, S->s>>>(L2_CHECK_BLOCKS, S->scratch);
         S->launches += 2;
     }
@@ -677,7 +528,7 @@ extern "C" int mglc_l2d_check(mglc_l2d *h, double *errorU) {
         MGLC_CUDA(cudaGetLastError());
         t1 += e[0]; t2 += e[1];
     }
-    *errorU = sqrt(t1) / sqrt(t2);
+    *errorU = h->d.variant == MGLC_L2D_INCOMP ? t1 / t2 : sqrt(t1) / sqrt(t2);      // L2I:335
     return MGLC_OK;
 }
 

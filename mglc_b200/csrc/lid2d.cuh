@@ -27,8 +27,8 @@ struct L2Params { double Snu, Sq, U0, rho0; };
                             const double *v, double *Fpost, cudaStream_t s);                                                   \
     int launch_l2_fused(const Geom2 &g, const L2Params &p, int variant, const double *Fin, double *Fout, const double *lid_in,   \
                         double *lid_out, cudaStream_t s);                                                                      \
-    int launch_l2_stream_macro(const Geom2 &g, const L2Params &p, const double *Fin, double *F, const double *lid_in,          \
-                               double *rho, double *u, double *v, cudaStream_t s);
+    int launch_l2_stream_macro(const Geom2 &g, const L2Params &p, int variant, const double *Fin, double *F,                  \
+                               const double *lid_in, double *rho, double *u, double *v, cudaStream_t s);
 namespace strict { MGLC_DECLARE_L2_LAUNCHERS }
 namespace fast { MGLC_DECLARE_L2_LAUNCHERS }
 

@@ -1,6 +1,7 @@
 // lid2d_kernels.inl -- 2-D D2Q9 MRT lid-driven cavity kernels; compiled twice (lid2d.cu: namespace strict, -fmad=false;
 // lid2d_fast.cu: namespace fast, -fmad=true).
 //   L2C = MPI/Lid_driven_cavity/c/lid_driven_cavity.c            L2F = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/
+//   L2I = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (the incompressible model, sequential)
 // Device layout: SoA F[a][j][x], one-cell halo ring, rows padded like the 3-D lattice (interior cell i = 1 at x-index OX,
 // pitch a multiple of 16 doubles): thread <-> cell, threadIdx.x along x, every warp store 128-byte aligned.
 // The fused kernel is the reference loop body rotated by half a step (like k_fused of the 3-D path): streaming() + bounceback()
@@ -11,7 +12,8 @@ namespace mglc {
 namespace MGLC_NS {
 
 // collision() of one cell.  VARIANT 0: L2C c:186-255 (meq(8) = u*v, the inverse as (...)/36.0);
-// VARIANT 1: L2F evolution.f90:16-66 (grouped sums, per-term divisions, meq(8) = rho*(u*v)).
+// VARIANT 1: L2F evolution.f90:16-66 (grouped sums, per-term divisions, meq(8) = rho*(u*v));
+// VARIANT 2: L2I:184-233 (the sums and divisions of L2F, the equilibrium without the rho factors, L2I:195-202).
 template <int VARIANT>
 __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, double u, double v, double Snu, double Sq,
                                              double (&fp)[9]) {
@@ -34,14 +36,25 @@ __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, d
     m[7] = f[1] - f[2] + f[3] - f[4];
     m[8] = f[5] - f[6] + f[7] - f[8];
     meq[0] = rho;
-    meq[1] = rho * (-2.0 + 3.0 * (u * u + v * v));
-    meq[2] = rho * (1.0 - 3.0 * (u * u + v * v));
-    meq[3] = rho * u;
-    meq[4] = -(rho * u);
-    meq[5] = rho * v;
-    meq[6] = -(rho * v);
-    meq[7] = rho * (u * u - v * v);
-    meq[8] = VARIANT == 0 ? u * v : rho * (u * v);
+    if (VARIANT == 2) {
+        meq[1] = -2.0 * rho + 3.0 * (u * u + v * v);
+        meq[2] = rho - 3.0 * (u * u + v * v);
+        meq[3] = u;
+        meq[4] = -u;
+        meq[5] = v;
+        meq[6] = -v;
+        meq[7] = u * u - v * v;
+        meq[8] = u * v;
+    } else {
+        meq[1] = rho * (-2.0 + 3.0 * (u * u + v * v));
+        meq[2] = rho * (1.0 - 3.0 * (u * u + v * v));
+        meq[3] = rho * u;
+        meq[4] = -(rho * u);
+        meq[5] = rho * v;
+        meq[6] = -(rho * v);
+        meq[7] = rho * (u * u - v * v);
+        meq[8] = VARIANT == 0 ? u * v : rho * (u * v);
+    }
 #pragma unroll
     for (int a = 0; a < 9; ++a) mp[a] = m[a] - s[a] * (m[a] - meq[a]);
     if (VARIANT == 0) {
@@ -75,12 +88,12 @@ __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, d
     const double m3 = ax + dx, m4 = dx - 2.0 * ax, m5 = ay + dy, m6 = dy - 2.0 * ay;
     const double m7 = (f[1] + f[3]) - (f[2] + f[4]), m8 = (f[5] + f[7]) - (f[6] + f[8]);
     const double uu = u * u, vv = v * v, q3 = 3.0 * (uu + vv);
-    const double p1 = m1 - Snu * (m1 - rho * (q3 - 2.0));
-    const double p2 = m2 - Snu * (m2 - rho * (1.0 - q3));
-    const double p4 = m4 - Sq * (m4 + rho * u);
-    const double p6 = m6 - Sq * (m6 + rho * v);
-    const double p7 = m7 - Snu * (m7 - rho * (uu - vv));
-    const double p8 = m8 - Snu * (m8 - (VARIANT == 0 ? u * v : rho * (u * v)));
+    const double p1 = m1 - Snu * (m1 - (VARIANT == 2 ? q3 - 2.0 * rho : rho * (q3 - 2.0)));
+    const double p2 = m2 - Snu * (m2 - (VARIANT == 2 ? rho - q3 : rho * (1.0 - q3)));
+    const double p4 = m4 - Sq * (m4 + (VARIANT == 2 ? u : rho * u));
+    const double p6 = m6 - Sq * (m6 + (VARIANT == 2 ? v : rho * v));
+    const double p7 = m7 - Snu * (m7 - (VARIANT == 2 ? uu - vv : rho * (uu - vv)));
+    const double p8 = m8 - Snu * (m8 - (VARIANT == 1 ? rho * (u * v) : u * v));
     constexpr double r9 = 1.0 / 9.0, r36 = 1.0 / 36.0, r6 = 1.0 / 6.0, r12 = 1.0 / 12.0;
     fp[0] = (m0 - p1 + p2) * r9;
     const double ca = (4.0 * m0 - p1 - 2.0 * p2) * r36, cd = (4.0 * m0 + 2.0 * p1 + p2) * r36;
@@ -115,7 +128,8 @@ __global__ void __launch_bounds__(128) k_l2_collision(Geom2 g, L2Params p, const
 // also get - rho*(+U0)/6 / - rho*(-U0)/6 with rho of the previous macro() (bounceback.f90:34-36 == c:310-312), and because
 // the top wall is processed last the lid term also holds in the two top corners.  Wall halos are never read.
 // streaming() + bounceback() of one cell, then macro() (evolution.f90:105-107 == c:321-336; adds and IEEE divisions only:
-// identical in both builds)
+// identical in both builds).  INC = L2I: the lid term is -(+-U0)/6 without rho (L2I:291-292) and u, v stay undivided (L2I:307-308).
+template <bool INC>
 __device__ __forceinline__ void l2_pull_macro(const Geom2 &g, const L2Params &p, const double *__restrict__ Fin,
                                               const double *__restrict__ rho_lid_in, int i, int j, double (&f)[9], double &rho,
                                               double &u, double &v) {
@@ -131,13 +145,23 @@ __device__ __forceinline__ void l2_pull_macro(const Geom2 &g, const L2Params &p,
     L2_PULL(5, 7, 1, 1) L2_PULL(6, 8, -1, 1) L2_PULL(7, 5, -1, -1) L2_PULL(8, 6, 1, -1)
 #undef L2_PULL
     if (yp) {   // explicit _rn intrinsics: the fast build must not contract this
-        const double r = rho_lid_in[i - 1];
-        f[7] = __dsub_rn(f[7], __ddiv_rn(__dmul_rn(r, p.U0), 6.0));
-        f[8] = __dsub_rn(f[8], __ddiv_rn(__dmul_rn(r, -p.U0), 6.0));
+        if (INC) {
+            f[7] = __dsub_rn(f[7], __ddiv_rn(p.U0, 6.0));
+            f[8] = __dsub_rn(f[8], __ddiv_rn(-p.U0, 6.0));
+        } else {
+            const double r = rho_lid_in[i - 1];
+            f[7] = __dsub_rn(f[7], __ddiv_rn(__dmul_rn(r, p.U0), 6.0));
+            f[8] = __dsub_rn(f[8], __ddiv_rn(__dmul_rn(r, -p.U0), 6.0));
+        }
     }
     rho = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(f[0], f[1]), f[2]), f[3]), f[4]), f[5]), f[6]), f[7]), f[8]);
-    u = __ddiv_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dsub_rn(f[1], f[3]), f[5]), f[6]), f[7]), f[8]), rho);
-    v = __ddiv_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(f[2], f[4]), f[5]), f[6]), f[7]), f[8]), rho);
+    if (INC) {
+        u = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dsub_rn(f[1], f[3]), f[5]), f[6]), f[7]), f[8]);
+        v = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(f[2], f[4]), f[5]), f[6]), f[7]), f[8]);
+    } else {
+        u = __ddiv_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dsub_rn(f[1], f[3]), f[5]), f[6]), f[7]), f[8]), rho);
+        v = __ddiv_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(f[2], f[4]), f[5]), f[6]), f[7]), f[8]), rho);
+    }
 }
 
 template <int VARIANT>
@@ -146,7 +170,7 @@ __global__ void __launch_bounds__(128) k_l2_fused(Geom2 g, L2Params p, const dou
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
     if (i > g.nx) return;
     double f[9], fp[9], rho, u, v;
-    l2_pull_macro(g, p, Fin, rho_lid_in, i, j, f, rho, u, v);
+    l2_pull_macro<VARIANT == 2>(g, p, Fin, rho_lid_in, i, j, f, rho, u, v);
     if (g.wall[2] && j == g.ny) rho_lid_out[i - 1] = rho;
     d2q9_collide<VARIANT>(f, rho, u, v, p.Snu, p.Sq, fp);
     const long long c = g.idx(0, i, j);
@@ -155,13 +179,14 @@ __global__ void __launch_bounds__(128) k_l2_fused(Geom2 g, L2Params p, const dou
 }
 
 // epilogue of a fused run: streaming() + bounceback() + macro() -> F (pre-collision) and the fields
+template <bool INC>
 __global__ void __launch_bounds__(128) k_l2_stream_macro(Geom2 g, L2Params p, const double *__restrict__ Fin, double *__restrict__ F,
                                                          const double *__restrict__ rho_lid_in, double *__restrict__ rho,
                                                          double *__restrict__ u, double *__restrict__ v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
     if (i > g.nx) return;
     double f[9], r, uu, vv;
-    l2_pull_macro(g, p, Fin, rho_lid_in, i, j, f, r, uu, vv);
+    l2_pull_macro<INC>(g, p, Fin, rho_lid_in, i, j, f, r, uu, vv);
     const long long c = g.idx(0, i, j), m = g.cell(i, j);
 #pragma unroll
     for (int a = 0; a < 9; ++a) F[a * g.sq + c] = f[a];
@@ -173,19 +198,23 @@ int launch_l2_collision(const Geom2 &g, const L2Params &p, int variant, const do
                         const double *v, double *Fpost, cudaStream_t s) {
     const dim3 grid((g.nx + 127) / 128, g.ny);
     if (variant == 0) k_l2_collision<0><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
-    else k_l2_collision<1><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
+    else if (variant == 1) k_l2_collision<1><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
+    else k_l2_collision<2><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
     return 1;
 }
-int launch_l2_stream_macro(const Geom2 &g, const L2Params &p, const double *Fin, double *F, const double *lid_in, double *rho,
-                           double *u, double *v, cudaStream_t s) {
-    k_l2_stream_macro<<<dim3((g.nx + 127) / 128, g.ny), 128, 0, s>>>(g, p, Fin, F, lid_in, rho, u, v);
+int launch_l2_stream_macro(const Geom2 &g, const L2Params &p, int variant, const double *Fin, double *F, const double *lid_in,
+                           double *rho, double *u, double *v, cudaStream_t s) {
+    const dim3 grid((g.nx + 127) / 128, g.ny);
+    if (variant == 2) k_l2_stream_macro<true><<<grid, 128, 0, s>>>(g, p, Fin, F, lid_in, rho, u, v);
+    else k_l2_stream_macro<false><<<grid, 128, 0, s>>>(g, p, Fin, F, lid_in, rho, u, v);
     return 1;
 }
 int launch_l2_fused(const Geom2 &g, const L2Params &p, int variant, const double *Fin, double *Fout, const double *lid_in,
                     double *lid_out, cudaStream_t s) {
     const dim3 grid((g.nx + 127) / 128, g.ny);
     if (variant == 0) k_l2_fused<0><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
-    else k_l2_fused<1><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
+    else if (variant == 1) k_l2_fused<1><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
+    else k_l2_fused<2><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
     return 1;
 }
 #endif

@@ -1,5 +1,7 @@
 """Host-side mirror of the reference's 2-D lid-driven cavity drivers over libmglc.so:
-  variant "c" = MPI/Lid_driven_cavity/c/lid_driven_cavity.c, variant "f" = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/.
+  variant "c" = MPI/Lid_driven_cavity/c/lid_driven_cavity.c, variant "f" = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/,
+  variant "i" = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (the incompressible model: rho = 0 until the
+  first macro(), u and v are the undivided momentum sums, check() is a ratio of sums of square roots).
 Method names follow the reference subroutines (initial / collision / message_passing_sendrecv / streaming / bounceback / macro /
 check); arrays cross the boundary as numpy arrays in the Fortran program's layout f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1),
 rho,u,v(nx,ny), order="F"."""
@@ -9,7 +11,7 @@ import numpy as np
 
 from . import _lib as L
 
-VARIANTS = {"c": L.L2D_C, "f": L.L2D_F}
+VARIANTS = {"c": L.L2D_C, "f": L.L2D_F, "i": L.L2D_INCOMP}
 
 
 class LidDrivenCavity2D:
