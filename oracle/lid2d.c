@@ -21,6 +21,9 @@
  * (inc:137,160; so the first collision() relaxes towards meq(1) = 3|u|^2, meq(2) = -3|u|^2), and check() as a ratio of
  * sums of dsqrt (inc:327-335).  Pinned through the same evaluator (make_golden_lid2d_incomp.py: every subroutine as whole
  * arrays).  The program is sequential; on P ranks the restatement exchanges halos as L2F does (P ranks == 1 rank).
+ * L2S (variant L2_S) is L2C with its own model switch set to SRT (c:13-14, collision c:160-176: single-relaxation-time BGK,
+ * f_post = f - 1.0/tau*(f - feq)); pinned live and through committed outputs to the same program compiled with that switch
+ * (oracle/_ref/liblid2d_srt_ref.so; make_golden_lid2d_srt.py).
  *
  * Layout is L2F's: column-major, population index fastest: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v,up,vp(nx,ny)
  * (initial.f90:30-38); tests transpose when they compare with the C program's f[NX][NY][9], rho[NX][NY].
@@ -31,7 +34,8 @@
 #include <string.h>
 
 #define Q9 9
-enum { L2_C = 0, L2_F = 1, L2_I = 2 };
+enum { L2_C = 0, L2_F = 1, L2_I = 2, L2_S = 3 };
+#define IS_C(v) ((v) == L2_C || (v) == L2_S)
 
 /* commondata.f90:25-27 == c:24-25 */
 static const int ex[Q9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
@@ -148,10 +152,20 @@ void l2_initial(l2_world *w) {
     }
 }
 
-/* collision() of one cell.  variant L2_C: c:186-255 ; variant L2_F: evolution.f90:15-70 ; variant L2_I: inc:183-233 */
+/* collision() of one cell.  variant L2_S: c:160-176 ; variant L2_C: c:186-255 ; variant L2_F: evolution.f90:15-70 ; variant L2_I: inc:183-233 */
 void l2_collide_cell(int variant, const double *f, double rho, double u, double v, double Snu, double Sq, double *fp) {
     double m[Q9], meq[Q9], mp[Q9];
     const double s[Q9] = {0.0, Snu, Snu, 0.0, Sq, 0.0, Sq, Snu, Snu};
+    if (variant == L2_S) {                               /* c:160-176; 1.0/tau is s_nu (c:99) */
+        static const double omega[Q9] = {4.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
+        double u2 = u * u + v * v;
+        for (int a = 0; a < Q9; ++a) {
+            double ue = u * (double)ex[a] + v * (double)ey[a];
+            double feq = rho * omega[a] * (1.0 + 3.0 * ue + 4.5 * ue * ue - 1.5 * u2);
+            fp[a] = f[a] - Snu * (f[a] - feq);
+        }
+        return;
+    }
     if (variant == L2_C) {
         m[0] = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
         m[1] = -4 * f[0] - f[1] - f[2] - f[3] - f[4] + 2 * f[5] + 2 * f[6] + 2 * f[7] + 2 * f[8];
@@ -317,7 +331,7 @@ double l2_check(l2_world *w) {
     for (int r = 0; r < w->np; ++r) {
         l2_rank *R = &w->r[r];
         double e1 = 0.0, e2 = 0.0;
-        if (w->variant == L2_C) {
+        if (IS_C(w->variant)) {
             for (int i = 1; i <= R->nx; ++i)
                 for (int j = 1; j <= R->ny; ++j) {
                     e1 += pow(S(R, u, i, j) - S(R, up, i, j), 2) + pow(S(R, v, i, j) - S(R, vp, i, j), 2);
@@ -342,7 +356,7 @@ double l2_check(l2_world *w) {
         }
         t1 += e1; t2 += e2;
     }
-    w->errorU = w->variant == L2_C ? pow(t1, 0.5) / pow(t2, 0.5) : w->variant == L2_I ? t1 / t2 : sqrt(t1) / sqrt(t2);   /* inc:335 */
+    w->errorU = IS_C(w->variant) ? pow(t1, 0.5) / pow(t2, 0.5) : w->variant == L2_I ? t1 / t2 : sqrt(t1) / sqrt(t2);   /* inc:335 */
     return w->errorU;
 }
 

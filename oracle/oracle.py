@@ -547,9 +547,10 @@ for _name, _sub in (("initial", "p2_initial"), ("collision", "p2_collision"), ("
 # ---------------------------------------------------------------------------------------------------------
 # 2-D D2Q9 lid-driven cavity (oracle/lid2d.c): variant "c" = MPI/Lid_driven_cavity/c/lid_driven_cavity.c,
 # variant "f" = MPI/Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked,
-# variant "i" = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (incompressible equilibrium)
+# variant "i" = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (incompressible equilibrium),
+# variant "s" = the C program with its model switch set to SRT (c:13-14, c:160-176: BGK)
 L2_FIELDS = {"f": 0, "f_post": 1, "rho": 2, "u": 3, "v": 4, "up": 5, "vp": 6}
-L2_VARIANTS = {"c": 0, "f": 1, "i": 2}
+L2_VARIANTS = {"c": 0, "f": 1, "i": 2, "s": 3}
 
 
 def _l2_lib():

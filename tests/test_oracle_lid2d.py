@@ -268,3 +268,76 @@ def test_incompressible_program_run(nprocs, dims):
     e = wd.check()
     assert abs(e - IGOLD["run25/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
     wd.close()
+
+
+# ---------------- the C program with its model switch set to SRT / BGK (variant "s"; make_golden_lid2d_srt.py) ----------------
+SGOLD = np.load(os.path.join(HERE, "golden", "ref_lid2d_srt.npz"))
+SRT_SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "liblid2d_srt_ref.so")
+
+
+def test_srt_collision_cells_bit_exact():
+    """c:160-176 on the seeded cells, as the compiled program (model = SRT) computed them"""
+    f, ruv = GOLD["cells/f"], GOLD["cells/ruv"]
+    _, snu, sq = SGOLD["params"]
+    assert tuple(SGOLD["params"]) == tuple(GOLD["c/params"])
+    for k in range(len(f)):
+        assert np.array_equal(orc.l2_collide_cell("s", f[k], *ruv[k], snu, sq), SGOLD["collision_f_post"][k]), k
+    assert not np.array_equal(SGOLD["collision_f_post"], GOLD["c/collision_f_post"])
+
+
+def test_srt_run_matches_committed_reference_outputs():
+    wd = orc.Lid2DWorld((200, 200), variant="s")
+    wd.initial()
+    done = 0
+    for n in (1, 10, 100, 1000):
+        wd.step(n - done); done = n
+        for k in ("rho", "u", "v"):
+            a = c_view(wd.gather(k))
+            assert np.array_equal(a[100, :], SGOLD[f"run{n}/{k}_col100"]), (n, k)
+            assert np.array_equal(a[:, 199], SGOLD[f"run{n}/{k}_row199"]), (n, k)
+            assert np.array_equal(a[:, 0], SGOLD[f"run{n}/{k}_row0"]), (n, k)
+            assert np.array_equal(a[::4, ::4], SGOLD[f"run{n}/{k}_stride4"]), (n, k)
+            assert np.array_equal(np.array([a.sum(), np.abs(a).sum(), (a * a).sum()]), SGOLD[f"run{n}/{k}_sum"]), (n, k)
+        f = c_view(wd.gather("f"))
+        assert np.array_equal(f[:3, :3, :], SGOLD[f"run{n}/f_corner"]) and np.array_equal(f[-3:, -3:, :], SGOLD[f"run{n}/f_topright"])
+    assert wd.check() == SGOLD["check_1000"][0]
+    wd.step(100)
+    assert wd.check() == SGOLD["check_1100"][0]
+    wd.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SRT_SO), reason="oracle/_ref/liblid2d_srt_ref.so not built (make -C oracle ref)")
+def test_srt_live_against_the_compiled_reference(tmp_path, monkeypatch):
+    """the reference program compiled with model = SRT: every array after each of its own subroutines, seeded input"""
+    monkeypatch.chdir(tmp_path)
+    ref = orc.RefLid2D(SRT_SO)
+    ref.lib.initial()
+    wd = orc.Lid2DWorld((200, 200), variant="s")
+    wd.initial()
+    assert np.array_equal(ref.f_F(), wd.gather("f"))
+    rng = np.random.default_rng(6)
+    f = np.asfortranarray(wd.gather("f") * (1.0 + 0.05 * rng.uniform(-1, 1, (9, 200, 200))))
+    rho = np.asfortranarray(1.0 + 0.02 * rng.uniform(-1, 1, (200, 200)))
+    u, v = (np.asfortranarray(0.05 * rng.uniform(-1, 1, (200, 200))) for _ in range(2))
+    ref.f[...] = np.transpose(f, (1, 2, 0)); ref.rho[...] = rho; ref.u[...] = u; ref.v[...] = v
+    for k, a in (("f", f), ("rho", rho), ("u", u), ("v", v)):
+        wd.scatter(k, a)
+    for it in range(6):
+        ref.lib.collision(); wd.collision()
+        assert np.array_equal(ref.f_F(True), wd.ranks[0].f_post[:, 1:-1, 1:-1]), ("collision", it)
+        ref.lib.streaming(); ref.lib.boundary(); wd.message_passing_sendrecv(); wd.streaming(); wd.bounceback()
+        assert np.array_equal(ref.f_F(), wd.gather("f")), ("streaming+boundary", it)
+        ref.lib.macro(); wd.macro()
+        for k in ("rho", "u", "v"):
+            assert np.array_equal(ref.field_F(k), wd.gather(k)), (k, it)
+    assert ref.lib.check(6) == wd.check()
+    wd.close()
+
+
+def test_srt_decomposed_equals_one_rank():
+    one, many = orc.Lid2DWorld((31, 23), 1, variant="s"), orc.Lid2DWorld((31, 23), 6, variant="s")
+    for wd in (one, many):
+        wd.initial(); wd.step(40)
+    for k in ("f", "rho", "u", "v"):
+        assert np.array_equal(one.gather(k), many.gather(k)), k
+    one.close(); many.close()
