@@ -38,7 +38,7 @@ module mglc_iso_c
         integer(c_int) :: total_nx, total_ny, variant, arith
         real(c_double) :: reynolds, U0, rho0
     end type mglc_l2d_desc
-    integer(c_int), parameter :: MGLC_L2D_C = 0, MGLC_L2D_F = 1, MGLC_L2D_INCOMP = 2
+    integer(c_int), parameter :: MGLC_L2D_C = 0, MGLC_L2D_F = 1, MGLC_L2D_INCOMP = 2, MGLC_L2D_C_SRT = 3
     !> mglc_aa_desc: the lid driver's constants (L3/commondata.f90:4-9) for the single-lattice (AA-pattern) path
     type, bind(C) :: mglc_aa_desc
         integer(c_int) :: n(3), arith, collision, device

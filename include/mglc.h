@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGLC_VERSION 104
+#define MGLC_VERSION 105
 
 /* ---- status codes ---- */
 #define MGLC_OK          0
@@ -338,15 +338,16 @@ int mglc_p2d_sync(mglc_p2d *h);
  * L2I = MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90 (sequential, 257 x 257), is L2F with the
  * incompressible equilibrium: meq without the rho factors (L2I:195-202), u, v = the undivided momentum sums (L2I:307-308), the lid
  * term -(+-U0)/6 without rho (L2I:291-292), initial() leaving rho = 0 and f = omega*(...) (L2I:137,160), check() = ratio of the
- * sums of dsqrt (L2I:327-335); MGLC_L2D_INCOMP reproduces it and decomposes like L2F.  Host arrays are L2F's, column-major:
+ * sums of dsqrt (L2I:327-335); MGLC_L2D_INCOMP reproduces it and decomposes like L2F.  MGLC_L2D_C_SRT is L2C with its own model
+ * switch set to SRT (c:13-14): the single-relaxation-time collision c:160-176, the rest as L2C.  Host arrays are L2F's, column-major:
  * f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), rho,u,v(nx,ny) (initial.f90:30-38); L2C's f[NX][NY][9] is the same memory read as
  * (0:8,ny,nx), i.e. the caller transposes x and y.  A handle owns ONE subdomain (one process per GPU, halos over NCCL) or
  * all P of them (mglc_l2d_create_local); `r` = index among those owned. */
-enum { MGLC_L2D_C = 0, MGLC_L2D_F = 1, MGLC_L2D_INCOMP = 2 };
+enum { MGLC_L2D_C = 0, MGLC_L2D_F = 1, MGLC_L2D_INCOMP = 2, MGLC_L2D_C_SRT = 3 };
 typedef struct mglc_l2d mglc_l2d;
 typedef struct mglc_l2d_desc {
     int total_nx, total_ny;              /* commondata.f90:4 ; c:9-10                       */
-    int variant;                         /* MGLC_L2D_C | MGLC_L2D_F | MGLC_L2D_INCOMP       */
+    int variant;                         /* MGLC_L2D_C | MGLC_L2D_F | MGLC_L2D_INCOMP | MGLC_L2D_C_SRT */
     int arith;                           /* MGLC_ARITH_FAST | MGLC_ARITH_STRICT             */
     double reynolds, U0, rho0;           /* 1000, 0.1, 1    commondata.f90:6-8 ; c:15-17    */
 } mglc_l2d_desc;

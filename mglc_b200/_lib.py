@@ -17,7 +17,7 @@ ARITH_FAST, ARITH_STRICT = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 BCT_ADIABATIC, BCT_CONST_HOT, BCT_CONST_COLD, BCT_PERIODIC = 0, 1, 2, 3
 T2D_MPI, T2D_ACC = 0, 1
-L2D_C, L2D_F, L2D_INCOMP = 0, 1, 2
+L2D_C, L2D_F, L2D_INCOMP, L2D_C_SRT = 0, 1, 2, 3
 
 
 class MglcError(RuntimeError):

@@ -5,6 +5,7 @@
 // L2C and L2F differ only in the rounding of collision() and in check(); L2I is L2F with the incompressible equilibrium (no rho
 // factors in meq, u and v undivided, the lid term without rho, rho = 0 before the first macro(), check() as a ratio of sums of
 // square roots); `variant` selects which program is reproduced.  L2I decomposes like L2F (same halo messages).
+// MGLC_L2D_C_SRT is L2C with its own model switch set to SRT (c:13-14): BGK collision c:160-176, everything else as L2C.
 // This file holds the strict build of the collision / fused kernels (-fmad=false), the copy-type subroutines (streaming,
 // bounceback, macro, initial, check, halo pack/unpack, layout transposes) and the host side; lid2d_fast.cu is the
 // throughput build of the same kernel source.
@@ -69,10 +70,10 @@ struct mglc_l2d {
 };
 
 extern "C" int mglc_l2d_desc_init(mglc_l2d_desc *d, int variant) {
-    if (!d || (variant != MGLC_L2D_C && variant != MGLC_L2D_F && variant != MGLC_L2D_INCOMP)) { set_error("mglc_l2d_desc_init: variant=%d", variant); return MGLC_E_INVALID; }
+    if (!d || variant < MGLC_L2D_C || variant > MGLC_L2D_C_SRT) { set_error("mglc_l2d_desc_init: variant=%d", variant); return MGLC_E_INVALID; }
     memset(d, 0, sizeof *d);
     d->variant = variant;
-    d->total_nx = d->total_ny = variant == MGLC_L2D_C ? 200 : variant == MGLC_L2D_F ? 201 : 257;      // c:9-10 ; commondata.f90:4 ; L2I:7
+    d->total_nx = d->total_ny = variant == MGLC_L2D_F ? 201 : variant == MGLC_L2D_INCOMP ? 257 : 200;      // c:9-10 ; commondata.f90:4 ; L2I:7
     d->arith = MGLC_ARITH_FAST;
     d->reynolds = 1000.0; d->U0 = 0.1; d->rho0 = 1.0;                   // c:15-17 ; commondata.f90:6-8
     return MGLC_OK;
@@ -200,7 +201,7 @@ static int l2_make_sub(mglc_l2d *h, int rank, int device, L2Sub **out) {
 
 static int l2_new(mglc_l2d **out, const mglc_l2d_desc *d, const int dims_or_zero[2], int nranks) {
     if (!out || !d || nranks < 1) { set_error("mglc_l2d_create: bad arguments"); return MGLC_E_INVALID; }
-    if (d->total_nx < 1 || d->total_ny < 1 || (d->variant != MGLC_L2D_C && d->variant != MGLC_L2D_F && d->variant != MGLC_L2D_INCOMP) ||
+    if (d->total_nx < 1 || d->total_ny < 1 || d->variant < MGLC_L2D_C || d->variant > MGLC_L2D_C_SRT ||
         (d->arith != MGLC_ARITH_FAST && d->arith != MGLC_ARITH_STRICT) || !(d->reynolds > 0.0)) {
         set_error("mglc_l2d_create: bad descriptor (%d x %d, variant %d, arith %d, Re %g)", d->total_nx, d->total_ny, d->variant, d->arith, d->reynolds);
         return MGLC_E_INVALID;

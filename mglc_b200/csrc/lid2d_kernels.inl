@@ -13,10 +13,33 @@ namespace MGLC_NS {
 
 // collision() of one cell.  VARIANT 0: L2C c:186-255 (meq(8) = u*v, the inverse as (...)/36.0);
 // VARIANT 1: L2F evolution.f90:16-66 (grouped sums, per-term divisions, meq(8) = rho*(u*v));
-// VARIANT 2: L2I:184-233 (the sums and divisions of L2F, the equilibrium without the rho factors, L2I:195-202).
+// VARIANT 2: L2I:184-233 (the sums and divisions of L2F, the equilibrium without the rho factors, L2I:195-202);
+// VARIANT 3: L2C with its model switch set to SRT (c:13-14), c:160-176: f_post = f - 1.0/tau*(f - feq), 1.0/tau = Snu (c:98).
 template <int VARIANT>
 __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, double u, double v, double Snu, double Sq,
                                              double (&fp)[9]) {
+    if (VARIANT == 3) {
+        const double omega[9] = {4.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
+        const double ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, ey[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};      // c:25-26 (doubles there too)
+#ifdef MGLC_STRICT
+        const double u2 = u * u + v * v;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const double ue = u * ex[a] + v * ey[a];
+            const double feq = rho * omega[a] * (1.0 + 3.0 * ue + 4.5 * ue * ue - 1.5 * u2);
+            fp[a] = f[a] - Snu * (f[a] - feq);
+        }
+#else
+        const double base = 1.0 - 1.5 * (u * u + v * v);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const double ue = u * ex[a] + v * ey[a];
+            const double feq = (rho * omega[a]) * (base + ue * (3.0 + 4.5 * ue));
+            fp[a] = f[a] + Snu * (feq - f[a]);
+        }
+#endif
+        return;
+    }
 #ifdef MGLC_STRICT
     double m[9], meq[9], mp[9];
     const double s[9] = {0.0, Snu, Snu, 0.0, Sq, 0.0, Sq, Snu, Snu};
@@ -199,7 +222,8 @@ int launch_l2_collision(const Geom2 &g, const L2Params &p, int variant, const do
     const dim3 grid((g.nx + 127) / 128, g.ny);
     if (variant == 0) k_l2_collision<0><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
     else if (variant == 1) k_l2_collision<1><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
-    else k_l2_collision<2><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
+    else if (variant == 2) k_l2_collision<2><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
+    else k_l2_collision<3><<<grid, 128, 0, s>>>(g, p, F, rho, u, v, Fpost);
     return 1;
 }
 int launch_l2_stream_macro(const Geom2 &g, const L2Params &p, int variant, const double *Fin, double *F, const double *lid_in,
@@ -214,7 +238,8 @@ int launch_l2_fused(const Geom2 &g, const L2Params &p, int variant, const double
     const dim3 grid((g.nx + 127) / 128, g.ny);
     if (variant == 0) k_l2_fused<0><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
     else if (variant == 1) k_l2_fused<1><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
-    else k_l2_fused<2><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
+    else if (variant == 2) k_l2_fused<2><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
+    else k_l2_fused<3><<<grid, 128, 0, s>>>(g, p, Fin, Fout, lid_in, lid_out);
     return 1;
 }
 #endif

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib as L
 
-VARIANTS = {"c": L.L2D_C, "f": L.L2D_F, "i": L.L2D_INCOMP}
+VARIANTS = {"c": L.L2D_C, "f": L.L2D_F, "i": L.L2D_INCOMP, "s": L.L2D_C_SRT}
 
 
 class LidDrivenCavity2D:

@@ -1,5 +1,5 @@
 // Test-only shim: the product's 2-D lid-driven cavity kernels (mglc_b200/csrc/lid2d_kernels.inl: k_l2_collision, k_l2_fused,
-// k_l2_stream_macro, all three programs' arithmetic; lid2d_exact.inl: k_l2_initial, k_l2_streaming, k_l2_bounceback, k_l2_macro)
+// k_l2_stream_macro, all four arithmetics; lid2d_exact.inl: k_l2_initial, k_l2_streaming, k_l2_bounceback, k_l2_macro)
 // compiled for the HOST and run thread by thread, so the CPU-only suite can check
 // the pull addressing, the wall rule and the lid term (incl. the two top corners) against the oracle without a GPU.  No shared
 // memory, no synchronisation: a sequential sweep over (blockIdx, threadIdx) is an exact emulation.  Never linked into the product.
@@ -62,7 +62,7 @@ extern "C" {
 // mode 0: k_l2_fused         f_post (halo'd) + lid_in -> f_post_out (halo'd, interior written), lid_out
 // mode 1: k_l2_stream_macro  f_post + lid_in -> f_out (halo'd array, interior written), fields3 = rho,u,v
 // mode 2: k_l2_collision     fin holds f (halo'd array, interior used), fields3 = rho,u,v in -> f_post_out
-// modes 3..6: the per-subroutine kernels initial / streaming / bounceback / macro (see below); variant 0 = L2C, 1 = L2F, 2 = L2I
+// modes 3..6: the per-subroutine kernels initial / streaming / bounceback / macro (see below); variant 0 = L2C, 1 = L2F, 2 = L2I, 3 = L2C with model = SRT
 int shim_l2d(int mode, int strict_build, int variant, int nx, int ny, const int *wall, double Snu, double Sq, double U0, double rho0,
              const double *fin, const double *lid_in, double *fout, double *lid_out, double *fields3) {
     Geom2 g = make_geom2(nx, ny);
@@ -78,7 +78,8 @@ int shim_l2d(int mode, int strict_build, int variant, int nx, int ny, const int 
     {                                                                               \
         if (variant == 0) sweep(g, [&] { NS::KERNEL<0>(__VA_ARGS__); });            \
         else if (variant == 1) sweep(g, [&] { NS::KERNEL<1>(__VA_ARGS__); });       \
-        else sweep(g, [&] { NS::KERNEL<2>(__VA_ARGS__); });                         \
+        else if (variant == 2) sweep(g, [&] { NS::KERNEL<2>(__VA_ARGS__); });       \
+        else sweep(g, [&] { NS::KERNEL<3>(__VA_ARGS__); });                         \
     }
     const bool inc = variant == 2;
     if (mode == 0) {

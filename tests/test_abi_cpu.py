@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mglc.h but not exported by libmglc.so"
     assert set(names) == set(L.SIGNATURES), set(names) ^ set(L.SIGNATURES)
-    assert mg.lib().mglc_version() == 104
+    assert mg.lib().mglc_version() == 105
 
 
 def test_no_cpu_fallback_without_gpu():
