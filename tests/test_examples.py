@@ -1,4 +1,6 @@
-"""examples/lid2d_driver.c: a plain-C driver that binds libmglc.so through include/mglc.h alone, in the role of the reference's
+"""examples/*.c: plain-C drivers that bind libmglc.so through include/mglc.h alone (CPU: they compile as C99 with -Wall -Werror
+and fail loudly without a device; the GPU run of laplace2d_driver.c is in test_zz_examples_laplace_gpu.py).
+examples/lid2d_driver.c: a plain-C driver that binds libmglc.so through include/mglc.h alone, in the role of the reference's
 own C program (MPI/Lid_driven_cavity/c/lid_driven_cavity.c).  CPU: it compiles as C99 against the header and fails loudly
 without a device.  GPU: after 2000 iterations in strict arithmetic its `flow_binary` is byte-identical to the file the reference
 program writes (SHA-256 committed in tests/golden/ref_lid2d.npz by make_golden_lid2d.py, from the reference's own run)."""
@@ -13,11 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_lid2d.npz"))
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "lid2d_driver")
+def build(tmp_path, name="lid2d_driver"):
+    exe = str(tmp_path / name)
     lib = os.path.join(ROOT, "mglc_b200")
     subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "lid2d_driver.c"), "-L", lib, "-lmglc", f"-Wl,-rpath,{lib}", "-o", exe])
+                           os.path.join(ROOT, "examples", name + ".c"), "-L", lib, "-lmglc", f"-Wl,-rpath,{lib}", "-o", exe])
     return exe
 
 
@@ -35,6 +37,17 @@ def test_c_driver_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_p
         pytest.skip("a CUDA device is present: the run itself is covered by the gpu test")
     r = subprocess.run([exe, "10"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "no CUDA device" in r.stderr and not (tmp_path / "flow_binary").exists()
+
+
+def test_laplace_driver_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/laplace2d_driver.c, in the role of the reference's MPI/Laplace/c/laplace2d.c"""
+    exe = build(tmp_path, "laplace2d_driver")
+    r = subprocess.run([exe, "2", "2"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 2 and "interior" in r.stderr
+    if _has_gpu():
+        pytest.skip("a CUDA device is present: the run itself is covered by the gpu test")
+    r = subprocess.run([exe, "64", "48", "10", "dump.bin"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and not r.stdout and not (tmp_path / "dump.bin").exists()
 
 
 @pytest.mark.gpu
