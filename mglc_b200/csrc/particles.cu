@@ -236,6 +236,9 @@ __global__ void k_p_fluid_sum_final(int nblocks, double *__restrict__ part) {
 
 // ---- streaming + bounceback + bounceback_particle + macro + the link sums of calForce, one node per thread ---
 // STAGES selects which of the reference's subroutines the launch performs (all of them in the fused step).
+// ps_in and ps_sum are two views of ONE particle-state table (the host passes S->ps twice): the kernel reads only the rows
+// PX_/PY_/PRAD_/POM_/PU_/PV_ through ps_in and writes only the rows PSX_/PSY_/PST_ through ps_sum, so no object is accessed
+// through both pointers and the __restrict__ qualifiers hold (same for k_p_links below).
 template <int STAGES>
 __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__restrict__ ps_in, double *__restrict__ ps_sum,
                                                   const double *__restrict__ Fp, double *__restrict__ F,
