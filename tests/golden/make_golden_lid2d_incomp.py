@@ -1,5 +1,8 @@
 """Generates tests/golden/ref_fortran_lid2d_incomp.npz -- golden vectors of the reference's sequential INCOMPRESSIBLE 2-D
-lid-driven cavity program (variant "i"), machine-evaluated from its own source text (fortran_eval.py) as whole arrays:
+lid-driven cavity program (variant "i") -- and tests/golden/ref_fortran_lid2d_seq.npz -- the same vectors of its sequential
+COMPRESSIBLE sibling seq/lid-driven_cavity.f90 (line-aligned with the incompressible file; its subroutines are also those of
+2d_old/lid-driven_cavity.f90), which variant "f" must reproduce -- machine-evaluated from the source text (fortran_eval.py)
+as whole arrays:
 
   L2I = /root/reference/MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity_incompress.f90
   initial      L2I:143-163   (u = U0 on the lid row, omega, f = omega*(...): no rho factor; rho stays 0, L2I:137)
@@ -26,12 +29,12 @@ EY = [0, 0, 1, 0, -1, 1, 1, -1, -1]
 FULL = ["f", "f_post", "rho", "u", "v", "up", "vp", "ex", "ey", "omega", "un", "uwall", "s", "m", "m_post", "meq"]
 
 
-def main():
+def main(L2I=L2I, name="ref_fortran_lid2d_incomp.npz", rho_init=0.0):
     rng = np.random.default_rng(20310)
     nx, ny, U0, Re = 8, 7, 0.1, 1000.0
     tau = U0 * float(nx) / Re * 3.0 + 0.5                             # L2I:11
     snu, sq = 1.0 / tau, 8.0 * (2.0 * tau - 1.0) / (8.0 * tau - 1.0)   # L2I:33
-    sc = dict(nx=nx, ny=ny, u0=U0, snu=snu, sq=sq, itc=0)
+    sc = dict(nx=nx, ny=ny, u0=U0, snu=snu, sq=sq, itc=0, rho0=1.0)
     out = {"params": np.array([tau, snu, sq]), "shape": np.array([nx, ny])}
     tr = lambda a, b: fe.translate(fe.read_lines(L2I, a, b), full_arrays=FULL)
     src = {"initial": tr(143, 163), "collision": tr(181, 236), "streaming": tr(249, 259), "bounceback": tr(270, 293),
@@ -51,7 +54,7 @@ def main():
     out["collision/f_post"] = from_full(ns["f_post__"], (9, nx, ny), F3)
     ns = run_full(src["streaming"], {**tables(), "f": fe._Arr(), "f_post": to_full(fp, H3)}, sc)
     out["streaming/f"] = from_full(ns["f__"], (9, nx, ny), F3)
-    ns = run_full(src["bounceback"], {**tables(), "f": to_full(f0, F3), "f_post": to_full(fp, H3)}, sc)
+    ns = run_full(src["bounceback"], {**tables(), "f": to_full(f0, F3), "f_post": to_full(fp, H3), "rho": to_full(rho, S2)}, sc)
     out["bounceback/f"] = from_full(ns["f__"], (9, nx, ny), F3)
     ns = run_full(src["macro"], {**tables(), "f": to_full(f0, F3), "rho": fe._Arr(), "u": fe._Arr(), "v": fe._Arr()}, sc)
     out["macro/ruv"] = np.stack([from_full(ns[k + "__"], (nx, ny), S2) for k in ("rho", "u", "v")])
@@ -59,8 +62,8 @@ def main():
     out["check/e1_e2_errorU"] = np.array([ns["error1"], ns["error2"], ns["erroru"]])
 
     # ---------------- the program's own run ----------------
-    zeros = lambda: to_full(np.zeros((nx, ny)), S2)                  # L2I:137-141: rho = u = v = up = vp = 0
-    st = {**tables(), "f": fe._Arr(), "f_post": to_full(np.zeros((9, nx + 2, ny + 2)), H3), "rho": zeros(), "u": zeros(),
+    zeros = lambda: to_full(np.zeros((nx, ny)), S2)                  # L2I:137-141: rho = u = v = up = vp = 0 (seq: rho = rho0)
+    st = {**tables(), "f": fe._Arr(), "f_post": to_full(np.zeros((9, nx + 2, ny + 2)), H3), "rho": to_full(np.full((nx, ny), rho_init), S2), "u": zeros(),
           "v": zeros(), "up": zeros(), "vp": zeros()}
     names = list(st)
 
@@ -89,10 +92,11 @@ def main():
     ns = call("check")
     out["run25/check"] = np.array([ns["error1"], ns["error2"], ns["erroru"]])
 
-    path = os.path.join(HERE, "ref_fortran_lid2d_incomp.npz")
+    path = os.path.join(HERE, name)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
     main()
+    main("/root/reference/MPI/Lid_driven_cavity/fortran/2d/seq/lid-driven_cavity.f90", "ref_fortran_lid2d_seq.npz", rho_init=1.0)

@@ -341,3 +341,47 @@ def test_srt_decomposed_equals_one_rank():
     for k in ("f", "rho", "u", "v"):
         assert np.array_equal(one.gather(k), many.gather(k)), k
     one.close(); many.close()
+
+
+# ---------------- the compressible sequential program against variant "f" (make_golden_lid2d_incomp.py, second output) ----------------
+QGOLD = np.load(os.path.join(HERE, "golden", "ref_fortran_lid2d_seq.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (4, (2, 2)), (6, (2, 3))])
+def test_variant_f_reproduces_the_sequential_fortran_program(nprocs, dims):
+    """seq/lid-driven_cavity.f90 (= the subroutines of 2d_old/lid-driven_cavity.f90) evaluated from its text: every subroutine
+    on seeded arrays and the program's loop for 25 iterations.  The MPI program's restatement (variant "f"), on 1, 4 and 6
+    emulated ranks, reproduces the sequential program bit for bit: the reference's seq == MPI contract, from its own text."""
+    nx, ny = (int(x) for x in QGOLD["shape"])
+    wd = orc.Lid2DWorld((nx, ny), nprocs, dims, variant="f")
+    assert (wd.tauf, wd.Snu, wd.Sq) == tuple(QGOLD["params"])
+    if nprocs == 1:
+        R = wd.ranks[0]
+
+        def load():
+            R.f[...] = QGOLD["in/f0"]; R.f_post[...] = QGOLD["in/f_post"]
+            for k in ("rho", "u", "v", "up", "vp"):
+                getattr(R, k)[...] = QGOLD["in/" + k]
+
+        load(); wd.collision()
+        assert np.array_equal(R.f_post[:, 1:-1, 1:-1], QGOLD["collision/f_post"])
+        load(); wd.streaming()
+        assert np.array_equal(R.f, QGOLD["streaming/f"])
+        load(); wd.bounceback()
+        assert np.array_equal(R.f, QGOLD["bounceback/f"])
+        load(); wd.macro()
+        assert np.array_equal(np.stack([R.rho, R.u, R.v]), QGOLD["macro/ruv"])
+        load()
+        e1, e2, eu = QGOLD["check/e1_e2_errorU"]
+        assert wd.check() == eu == np.sqrt(e1) / np.sqrt(e2)
+    wd.initial()
+    assert np.array_equal(wd.gather("f"), QGOLD["run0/f"])
+    assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v")]), QGOLD["run0/ruv"])
+    done = 0
+    for n in (1, 2, 20):
+        wd.step(n - done); done = n
+        assert np.array_equal(wd.gather("f"), QGOLD[f"run{n}/f"]), n
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v")]), QGOLD[f"run{n}/ruv"]), n
+    e = wd.check()
+    assert abs(e - QGOLD["run20/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
+    wd.close()
