@@ -13,6 +13,9 @@
  *   whole array  streaming.f90:8-20, bounce_back.f90:6-83 for every wall combination a block can own (the
  *                later wall winning on edges, the lid term with the previous rho), check.f90:9-19
  *                (make_golden_lid3d_fields.py -> ref_fortran_lid3d_fields.npz)
+ *   whole run    the SEQUENTIAL program 3d/seq/lid_driven_cavity_3d.f90 evaluated as a whole on 6 x 5 x 4: initial()
+ *                and its loop for 1, 2, 12, 14 iterations with check() (make_golden_lid3d_seq_run.py ->
+ *                ref_fortran_lid3d_seq_run.npz); this file reproduces f, f_post, rho, u, v, w on 1..8 emulated ranks
  * -- and tests/test_oracle_lid.py requires this file to reproduce them bit for bit.  On top: analytic known
  * answers (M^-1 M = I, M feq = meq, rest equilibrium fixed point, delta-population transport, mass
  * conservation, no NaN leaking from poisoned wall halos) and the reference's implicit seq == MPI contract

@@ -418,3 +418,34 @@ def test_check_sums_match_the_fortran_text():
     assert wd.check() == np.sqrt(e1) / np.sqrt(e2)
     assert np.array_equal(R.up, R.u) and np.array_equal(R.wp, R.w)
     wd.close()
+
+
+# ---------------- the sequential program's own run, from its text (make_golden_lid3d_seq_run.py) ----------------
+SGOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_lid3d_seq_run.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, None), (8, (2, 2, 2)), (6, (3, 1, 2))])
+def test_oracle_reproduces_the_sequential_programs_run(nprocs, dims):
+    """3d/seq/lid_driven_cavity_3d.f90 evaluated from its text on 6 x 5 x 4: initial() and its loop (collision, streaming,
+    bounceback, macro) for 1, 2, 12 and 14 iterations, check() after 12 and 14.  The restatement of the MPI program reproduces
+    f, the interior of f_post, rho, u, v, w bit for bit on 1, 2, 4, 6 and 8 emulated ranks (the reference's seq == MPI contract)."""
+    total = tuple(int(x) for x in SGOLD["shape"])
+    wd = orc.LidWorld(total, nprocs, dims=dims)
+    assert (wd.tauf, wd.Snu, wd.Sq) == tuple(SGOLD["params"])
+    wd.initial()
+    fields = lambda: np.stack([wd.gather(k) for k in ("rho", "u", "v", "w")])
+    assert np.array_equal(wd.gather("f"), SGOLD["run0/f"]) and np.array_equal(fields(), SGOLD["run0/ruvw"])
+    done = 0
+    for n in (1, 2, 12):
+        wd.step(n - done); done = n
+        assert np.array_equal(wd.gather("f"), SGOLD[f"run{n}/f"]), n
+        assert np.array_equal(fields(), SGOLD[f"run{n}/ruvw"]), n
+        if nprocs == 1:
+            assert np.array_equal(wd.ranks[0].f_post[:, 1:-1, 1:-1, 1:-1], SGOLD[f"run{n}/f_post"]), n
+    e = wd.check()
+    assert abs(e - SGOLD["run12/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
+    wd.step(2)
+    e = wd.check()
+    assert abs(e - SGOLD["run14/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
+    assert np.array_equal(wd.gather("f"), SGOLD["run14/f"]) and np.array_equal(fields(), SGOLD["run14/ruvw"])
+    wd.close()
