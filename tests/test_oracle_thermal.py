@@ -204,3 +204,40 @@ def test_check_sums_match_the_fortran_text():
     assert eu == np.sqrt(e1) / np.sqrt(e2) and et == e5 / e6
     assert np.array_equal(R.Tp, R.T) and np.array_equal(R.wp, R.w)
     wd.close()
+
+
+# ---------------- the sequential program's own run, from its text (make_golden_thermal3d_seq_run.py) ----------------
+SRUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal3d_seq_run.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, None), (8, (2, 2, 2)), (6, (3, 1, 2))])
+def test_oracle_reproduces_the_sequential_thermal_programs_run(nprocs, dims):
+    """3d/seq/bouyancy3d.F90 with its shipped macro set, evaluated from its text on 6 x 5 x 4: parameters, initial() and its loop
+    (collision, streaming, bounceback, collisionT, streamingT, bouncebackT, macro, macroT) for 1, 2, 10 and 12 iterations, check()
+    after 10 and 12.  The restatement of the MPI program reproduces f, g, rho, u, v, w, T and the force fields bit for bit on
+    1, 2, 4, 6 and 8 emulated ranks (the reference's seq == MPI contract, from the sequential program's own text)."""
+    total = tuple(int(x) for x in SRUN["shape"])
+    wd = orc.ThermalWorld(total, nprocs, dims=dims)
+    names_p = ("tauf", "viscosity", "diffusivity", "omegaRatating", "paraA", "gBeta1", "gBeta", "Snu", "Sq", "Qd", "Qnu")
+    assert tuple(getattr(wd.p, k) for k in names_p) == tuple(SRUN["params"])
+    wd.initial()
+
+    def same(tag):
+        assert np.array_equal(wd.gather("f"), SRUN[tag + "/f"]), tag
+        assert np.array_equal(wd.gather("g"), SRUN[tag + "/g"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v", "w", "T")]), SRUN[tag + "/ruvwT"]), tag
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 10):
+        wd.step(n - done); done = n
+        same(f"run{n}")
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("Fx", "Fy", "Fz")]), SRUN[f"run{n}/F"]), n
+    eu, et = wd.check()
+    tol = 0 if nprocs == 1 else 1e-14
+    assert abs(eu - SRUN["run10/check"][0]) <= tol * abs(eu) and abs(et - SRUN["run10/check"][1]) <= tol * abs(et)
+    wd.step(2)
+    eu, et = wd.check()
+    assert abs(eu - SRUN["run12/check"][0]) <= tol * abs(eu) and abs(et - SRUN["run12/check"][1]) <= tol * abs(et)
+    same("run12")
+    wd.close()
