@@ -9,6 +9,9 @@
  * bounceback(), bouncebackT(), streaming(), streamingT(), the initial() loops and check()'s sums from B2's files
  * (fortran_eval.py) on seeded inputs, and tests/test_oracle_thermal2d.py requires this file to reproduce those numbers
  * bit for bit; on top: the reference's seq == MPI contract (P emulated ranks == 1 rank, bit for bit) and analytic pins.
+ * Whole run: the sequential side-heated program seq/steady.F90 is evaluated from its text on 9 x 7 -- parameters, initial() and
+ * its loop for 1, 2, 20, 25 iterations with check() (make_golden_thermal2d_seq_run.py) -- and this file (variant T2_MPI,
+ * side-heated walls) reproduces its f, g, rho, u, v, T, Fx, Fy bit for bit on 1..6 emulated ranks.
  *
  * Layout is B2's: column-major, population index fastest: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), g(0:4,nx,ny),
  * g_post(0:4,0:nx+1,0:ny+1), rho,u,v,T,up,vp,Tp,Fx,Fy(nx,ny)  (initial.F90:177-197).

@@ -1,0 +1,95 @@
+"""Generates tests/golden/ref_fortran_thermal2d_seq_run.npz -- the reference's SEQUENTIAL 2-D buoyancy-driven cavity program
+seq/steady.F90 (side-heated cell, its shipped macro set :7-31) run from its own source text (fortran_eval.py, whole arrays) on a
+9 x 7 lattice:
+
+  S2 = /root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/steady.F90
+  parameters   S2:56-62, :79, :87, :96-110, :118-120 (nx, ny replaced by 9, 7; odd sizes keep the integer divisions of :87 exact)
+  initial      S2:446-457 (weights), :466-481 (wall velocities, all 0 at shearReynolds = 0), :507-516 (T linear in x),
+               :545-557 (populations); the whole-array assignments (:443-444, :461-463, :597-603) are applied by this script
+  collision    S2:638-709      streaming   S2:726-737      bounceback   S2:754-897 (incl. the four corners :863-897)
+  collisionT   S2:958-990      streamingT  S2:1007-1019    bouncebackT  S2:1036-1131
+  macro        S2:927-939      macroT      S2:1146-1152    check        S2:1168-1193
+its loop (S2:189-207: collision, streaming, bounceback, collisionT, streamingT, bouncebackT, macro, macroT) for 1, 2 and 20
+iterations with check() after 20 and 25.  INTEGRATION.md maps this file onto MGLC_T2D_MPI with the side-heated set: the
+restatement of the MPI program (oracle/thermal2d.c) must reproduce this run on 1 and on several emulated ranks.  Only numbers are
+stored; run in the authoring container."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import fortran_eval as fe  # noqa: E402
+from make_golden_fortran import eval_parameters  # noqa: E402
+from make_golden_thermal2d import arr, from_full, run_full, strip_cpp, to_full  # noqa: E402
+
+S2 = "/root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/steady.F90"
+DEFS = {"steadyFlow", "HorizontalWallsNoslip", "VerticalWallsNoslip", "SideHeatedCell", "HorizontalWallsAdiabatic", "VerticalWallsConstT"}
+EX = [0, 1, 0, -1, 0, 1, -1, -1, 1]     # S2:132-133
+EY = [0, 0, 1, 0, -1, 1, 1, -1, -1]
+FULL = ["f", "f_post", "g", "g_post", "rho", "u", "v", "t", "up", "vp", "tp", "fx", "fy", "ex", "ey", "omega", "omegat", "un", "s", "m",
+        "m_post", "meq", "fsource", "n", "n_post", "neq", "q", "obst"]
+
+
+def main():
+    nx, ny = 9, 7
+    text = "\n".join(fe.read_lines(S2, a, b) for a, b in ((56, 62), (79, 79), (87, 87), (96, 110), (118, 120)))
+    text = text.replace("nx=201, ny=201", f"nx={nx}, ny={ny}")
+    P = eval_parameters(text)
+    assert (P["nx"], P["ny"], P["lengthunit"], P["u0"]) == (nx, ny, float(ny), 0.0)
+    names_p = ("tauf", "viscosity", "diffusivity", "paraa", "gbeta", "snu", "sq", "qd", "qnu")
+    out = {"params": np.array([P[k] for k in names_p]), "shape": np.array([nx, ny])}
+    sc = {k: v for k, v in P.items()}
+    sc.update(itc=0)
+    tr = lambda a, b: fe.translate(strip_cpp(fe.read_lines(S2, a, b), DEFS), full_arrays=FULL)
+    src = {"weights": tr(446, 457), "initU": tr(466, 481), "initT": tr(507, 516), "initial": tr(545, 557), "collision": tr(638, 709),
+           "streaming": tr(726, 737), "bounceback": tr(754, 897), "macro": tr(927, 939), "collisionT": tr(958, 990),
+           "streamingT": tr(1007, 1019), "bouncebackT": tr(1036, 1131), "macroT": tr(1146, 1152), "check": tr(1168, 1193)}
+    F3, H3, S = (0, 1, 1), (0, 0, 0), (1, 1)
+    field = lambda value: to_full(np.full((nx, ny), value), S)
+    st = {k: fe._Arr() for k in ("omega", "omegat", "un", "s", "m", "m_post", "meq", "fsource", "n", "n_post", "neq", "q", "f", "g")}
+    st.update(ex=arr(EX), ey=arr(EY), rho=field(P["rho0"]), obst=fe._Arr({(i, j): 0 for i in range(nx + 2) for j in range(ny + 2)}),   # S2:443-444
+              f_post=to_full(np.zeros((9, nx + 2, ny + 2)), H3), g_post=to_full(np.zeros((5, nx + 2, ny + 2)), H3),                  # :602-603
+              **{k: field(0.0) for k in ("u", "v", "t", "up", "vp", "tp", "fx", "fy")})                                             # :461-463, :597-600
+    names = list(st)
+
+    def call(sub):
+        ns = run_full(src[sub], st, sc)
+        for k in names:
+            st[k] = ns[k + "__"]
+        return ns
+
+    def step():
+        for sub in ("collision", "streaming", "bounceback", "collisionT", "streamingT", "bouncebackT", "macro", "macroT"):   # S2:189-207
+            call(sub)
+
+    def snap(tag):
+        out[tag + "/f"] = from_full(st["f"], (9, nx, ny), F3)
+        out[tag + "/g"] = from_full(st["g"], (5, nx, ny), F3)
+        out[tag + "/ruvT"] = np.stack([from_full(st[k], (nx, ny), S) for k in ("rho", "u", "v", "t")])
+        out[tag + "/F"] = np.stack([from_full(st[k], (nx, ny), S) for k in ("fx", "fy")])
+
+    for sub in ("weights", "initU", "initT", "initial"):
+        call(sub)
+    snap("run0")
+    done = 0
+    for n in (1, 2, 20):
+        for _ in range(n - done):
+            step()
+        done = n
+        snap(f"run{n}")
+    ns = call("check")
+    out["run20/check"] = np.array([ns["erroru"], ns["errort"]])
+    for _ in range(5):
+        step()
+    ns = call("check")
+    out["run25/check"] = np.array([ns["erroru"], ns["errort"]])
+    snap("run25")
+    path = os.path.join(HERE, "ref_fortran_thermal2d_seq_run.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

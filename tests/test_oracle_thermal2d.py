@@ -318,3 +318,39 @@ def test_acc_periodic_run_splits_along_y_bit_exactly():
     T = one.gather("T")
     assert np.all(T[2:-2, :] == T[2:3, :]) or not np.all(T == T[0:1, :])
     one.close(); many.close()
+
+
+# ---------------- the sequential side-heated program's own run, from its text (make_golden_thermal2d_seq_run.py) ----------------
+SRUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_seq_run.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, (2, 2)), (6, (3, 2)), (3, (1, 3))])
+def test_oracle_reproduces_the_sequential_side_heated_programs_run(nprocs, dims):
+    """seq/steady.F90 with its shipped macro set (side-heated cell, no-slip walls at rest), evaluated from its text on 9 x 7:
+    parameters, initial() (T linear in x) and its loop of eight subroutines for 1, 2, 20 and 25 iterations, check() after 20 and
+    25 -- including its separate corner statements in bounceback().  The restatement of the MPI program (variant "mpi", the
+    side-heated set: the row INTEGRATION.md maps this file to) reproduces f, g, rho, u, v, T, Fx, Fy bit for bit on 1 to 6 ranks."""
+    total = tuple(int(x) for x in SRUN["shape"])
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=orc.T2_SIDE_HEATED, variant="mpi")
+    assert tuple(getattr(wd.params, k) for k in ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")) == tuple(SRUN["params"])
+    wd.initial()
+
+    def same(tag):
+        assert np.array_equal(wd.gather("f"), SRUN[tag + "/f"]), tag
+        assert np.array_equal(wd.gather("g"), SRUN[tag + "/g"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v", "T")]), SRUN[tag + "/ruvT"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("Fx", "Fy")]), SRUN[tag + "/F"]), tag
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 20):
+        wd.step(n - done); done = n
+        same(f"run{n}")
+    tol = 0 if nprocs == 1 else 1e-14
+    eu, et = wd.check()
+    assert abs(eu - SRUN["run20/check"][0]) <= tol * abs(eu) and abs(et - SRUN["run20/check"][1]) <= tol * abs(et)
+    wd.step(5)
+    eu, et = wd.check()
+    assert abs(eu - SRUN["run25/check"][0]) <= tol * abs(eu) and abs(et - SRUN["run25/check"][1]) <= tol * abs(et)
+    same("run25")
+    wd.close()
