@@ -11,7 +11,9 @@
  * bit for bit; on top: the reference's seq == MPI contract (P emulated ranks == 1 rank, bit for bit) and analytic pins.
  * Whole run: the sequential side-heated program seq/steady.F90 is evaluated from its text on 9 x 7 -- parameters, initial() and
  * its loop for 1, 2, 20, 25 iterations with check() (make_golden_thermal2d_seq_run.py) -- and this file (variant T2_MPI,
- * side-heated walls) reproduces its f, g, rho, u, v, T, Fx, Fy bit for bit on 1..6 emulated ranks.
+ * side-heated walls) reproduces its f, g, rho, u, v, T, Fx, Fy bit for bit on 1..6 emulated ranks.  The OpenACC program
+ * seq/bouyancy2d_acc.F90 is evaluated the same way (periodic vertical walls, Rayleigh-Benard plates, lengthUnit = nx) and
+ * variant T2_ACC reproduces that run bit for bit on 1..3 ranks stacked along y (ref_fortran_thermal2d_acc_run.npz).
  *
  * Layout is B2's: column-major, population index fastest: f(0:8,nx,ny), f_post(0:8,0:nx+1,0:ny+1), g(0:4,nx,ny),
  * g_post(0:4,0:nx+1,0:ny+1), rho,u,v,T,up,vp,Tp,Fx,Fy(nx,ny)  (initial.F90:177-197).

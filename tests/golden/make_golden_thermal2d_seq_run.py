@@ -11,9 +11,19 @@ seq/steady.F90 (side-heated cell, its shipped macro set :7-31) run from its own 
   macro        S2:927-939      macroT      S2:1146-1152    check        S2:1168-1193
 its loop (S2:189-207: collision, streaming, bounceback, collisionT, streamingT, bouncebackT, macro, macroT) for 1, 2 and 20
 iterations with check() after 20 and 25.  INTEGRATION.md maps this file onto MGLC_T2D_MPI with the side-heated set: the
-restatement of the MPI program (oracle/thermal2d.c) must reproduce this run on 1 and on several emulated ranks.  Only numbers are
-stored; run in the authoring container."""
+restatement of the MPI program (oracle/thermal2d.c) must reproduce this run on 1 and on several emulated ranks.
+
+A second output, tests/golden/ref_fortran_thermal2d_acc_run.npz, is the same whole run of the OpenACC program
+  ACC = /root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/bouyancy2d_acc.F90
+(Rayleigh-Benard plates, vertical walls periodic for f and g, lengthUnit = dble(nx), arrays indexed f(i,j,alpha): rewritten to
+(alpha,i,j) before evaluation; `!$acc` lines dropped):
+  parameters ACC:55-61, :90-103   initial ACC:419-430, :511-520 (T linear in y), :532-544
+  collision ACC:624-707   streaming ACC:722-743   bounceback ACC:758-822   macro ACC:836-849
+  collisionT ACC:869-919  streamingT ACC:934-953  bouncebackT ACC:968-1046 macroT ACC:1060-1071   check ACC:1087-1113
+which variant "acc" of the oracle with the periodic Rayleigh-Benard set must reproduce (one rank, or ranks stacked along y).
+Only numbers are stored; run in the authoring container."""
 import os
+import re
 import sys
 
 import numpy as np
@@ -32,20 +42,40 @@ FULL = ["f", "f_post", "g", "g_post", "rho", "u", "v", "t", "up", "vp", "tp", "f
         "m_post", "meq", "fsource", "n", "n_post", "neq", "q", "obst"]
 
 
-def main():
+ACC = "/root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/bouyancy2d_acc.F90"
+ACC_DEFS = {"steadyFlow", "HorizontalWallsNoslip", "VerticalWallsPeriodicalU", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsPeriodicalT"}
+STEADY = dict(path=S2, defs=DEFS, name="ref_fortran_thermal2d_seq_run.npz", param_lines=((56, 62), (79, 79), (87, 87), (96, 110), (118, 120)),
+              size_text="nx=201, ny=201", reorder=False,
+              ranges={"weights": (446, 457), "initU": (466, 481), "initT": (507, 516), "initial": (545, 557), "collision": (638, 709),
+                      "streaming": (726, 737), "bounceback": (754, 897), "macro": (927, 939), "collisionT": (958, 990),
+                      "streamingT": (1007, 1019), "bouncebackT": (1036, 1131), "macroT": (1146, 1152), "check": (1168, 1193)})
+ACCRUN = dict(path=ACC, defs=ACC_DEFS, name="ref_fortran_thermal2d_acc_run.npz", param_lines=((55, 61), (90, 103)),
+              size_text="nx=513, ny=257", reorder=True,
+              ranges={"weights": (419, 430), "initT": (511, 520), "initial": (532, 544), "collision": (624, 707), "streaming": (722, 743),
+                      "bounceback": (758, 822), "macro": (836, 849), "collisionT": (869, 919), "streamingT": (934, 953),
+                      "bouncebackT": (968, 1046), "macroT": (1060, 1071), "check": (1087, 1113)})
+
+
+def main(cfg=STEADY):
     nx, ny = 9, 7
-    text = "\n".join(fe.read_lines(S2, a, b) for a, b in ((56, 62), (79, 79), (87, 87), (96, 110), (118, 120)))
-    text = text.replace("nx=201, ny=201", f"nx={nx}, ny={ny}")
+    S2, DEFS = cfg["path"], cfg["defs"]
+    text = "\n".join(fe.read_lines(S2, a, b) for a, b in cfg["param_lines"])
+    assert cfg["size_text"] in text
+    text = text.replace(cfg["size_text"], f"nx={nx}, ny={ny}")
     P = eval_parameters(text)
-    assert (P["nx"], P["ny"], P["lengthunit"], P["u0"]) == (nx, ny, float(ny), 0.0)
+    P.setdefault("rho0", 1.0)                  # ACC:416 `rho = 1.0d0`
+    assert (P["nx"], P["ny"], P["lengthunit"], P.get("u0", 0.0)) == (nx, ny, float(nx if cfg["reorder"] else ny), 0.0)
     names_p = ("tauf", "viscosity", "diffusivity", "paraa", "gbeta", "snu", "sq", "qd", "qnu")
     out = {"params": np.array([P[k] for k in names_p]), "shape": np.array([nx, ny])}
     sc = {k: v for k, v in P.items()}
     sc.update(itc=0)
-    tr = lambda a, b: fe.translate(strip_cpp(fe.read_lines(S2, a, b), DEFS), full_arrays=FULL)
-    src = {"weights": tr(446, 457), "initU": tr(466, 481), "initT": tr(507, 516), "initial": tr(545, 557), "collision": tr(638, 709),
-           "streaming": tr(726, 737), "bounceback": tr(754, 897), "macro": tr(927, 939), "collisionT": tr(958, 990),
-           "streamingT": tr(1007, 1019), "bouncebackT": tr(1036, 1131), "macroT": tr(1146, 1152), "check": tr(1168, 1193)}
+    def tr(a, b):
+        t = strip_cpp(fe.read_lines(S2, a, b), DEFS)
+        t = "\n".join(l for l in t.splitlines() if not l.strip().lower().startswith("!$acc"))
+        if cfg["reorder"]:                      # f(i,j,alpha) -> f(alpha,i,j)
+            t = re.sub(r"\b(f_post|g_post|f|g)\(([^(),]+),([^(),]+),([^(),]+)\)", r"\1(\4,\2,\3)", t)
+        return fe.translate(t, full_arrays=FULL)
+    src = {k: tr(*r) for k, r in cfg["ranges"].items()}
     F3, H3, S = (0, 1, 1), (0, 0, 0), (1, 1)
     field = lambda value: to_full(np.full((nx, ny), value), S)
     st = {k: fe._Arr() for k in ("omega", "omegat", "un", "s", "m", "m_post", "meq", "fsource", "n", "n_post", "neq", "q", "f", "g")}
@@ -71,7 +101,8 @@ def main():
         out[tag + "/F"] = np.stack([from_full(st[k], (nx, ny), S) for k in ("fx", "fy")])
 
     for sub in ("weights", "initU", "initT", "initial"):
-        call(sub)
+        if sub in src:
+            call(sub)
     snap("run0")
     done = 0
     for n in (1, 2, 20):
@@ -86,10 +117,11 @@ def main():
     ns = call("check")
     out["run25/check"] = np.array([ns["erroru"], ns["errort"]])
     snap("run25")
-    path = os.path.join(HERE, "ref_fortran_thermal2d_seq_run.npz")
+    path = os.path.join(HERE, cfg["name"])
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    main(STEADY)
+    main(ACCRUN)

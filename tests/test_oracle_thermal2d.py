@@ -354,3 +354,38 @@ def test_oracle_reproduces_the_sequential_side_heated_programs_run(nprocs, dims)
     assert abs(eu - SRUN["run25/check"][0]) <= tol * abs(eu) and abs(et - SRUN["run25/check"][1]) <= tol * abs(et)
     same("run25")
     wd.close()
+
+
+ARUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_acc_run.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, (1, 2)), (3, (1, 3))])
+def test_oracle_reproduces_the_openacc_programs_run(nprocs, dims):
+    """seq/bouyancy2d_acc.F90 (the reference's only GPU code) with its shipped macro set -- Rayleigh-Benard plates, vertical walls
+    periodic for f and g with its same-row rule, lengthUnit = dble(nx), f_post(0) rounded term by term -- evaluated from its
+    text as a whole program on 9 x 7: parameters, initial() (T linear in y), 25 iterations of its eight subroutines, check().
+    Variant "acc" of the restatement reproduces f, g, rho, u, v, T, Fx, Fy bit for bit on one rank and on ranks stacked along y."""
+    total = tuple(int(x) for x in ARUN["shape"])
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=orc.T2_RB_PERIODIC, variant="acc", lengthUnit=float(total[0]), Rayleigh=1e5)
+    assert tuple(getattr(wd.params, k) for k in ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")) == tuple(ARUN["params"])
+    wd.initial()
+
+    def same(tag):
+        assert np.array_equal(wd.gather("f"), ARUN[tag + "/f"]), tag
+        assert np.array_equal(wd.gather("g"), ARUN[tag + "/g"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v", "T")]), ARUN[tag + "/ruvT"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("Fx", "Fy")]), ARUN[tag + "/F"]), tag
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 20):
+        wd.step(n - done); done = n
+        same(f"run{n}")
+    tol = 0 if nprocs == 1 else 1e-14
+    eu, et = wd.check()
+    assert abs(eu - ARUN["run20/check"][0]) <= tol * abs(eu) and abs(et - ARUN["run20/check"][1]) <= tol * abs(et)
+    wd.step(5)
+    eu, et = wd.check()
+    assert abs(eu - ARUN["run25/check"][0]) <= tol * abs(eu) and abs(et - ARUN["run25/check"][1]) <= tol * abs(et)
+    same("run25")
+    wd.close()
