@@ -9,7 +9,11 @@
  * here is checked bit for bit against vectors obtained by machine-evaluating the reference's own source text
  * (tests/golden/make_golden_particles.py); copies (streaming, wall bounce-back, exchanges, mask rebuild) by
  * construction tests.  The reference seeds its 64 particle positions with compiler-specific random_number
- * (P4/initial.F90:52-75), so positions are an INPUT here.
+ * (P4/initial.F90:52-75), so positions are an INPUT here.  Whole run: the program's text is evaluated as a whole on one
+ * rank (56 x 72, two particles: initial() and 30 iterations of collision, streaming, bounceback, bounceback_particle with
+ * calQ called as written, macro, calForce, updateCenter incl. mask rebuild and refill, then check();
+ * make_golden_particles_run.py -> ref_fortran_particles_run.npz) and this file reproduces every population incl. the ghost
+ * layers, rho, u, v, the solid mask, rhoAvg and the particle state bit for bit.
  *
  * Layout is the reference's (P4/freeall.F90:13-17): f(0:8,-2:nx+3,-2:ny+3), f_post(0:8,-1:nx+2,-1:ny+2),
  * obst/obstNew(0:nx+1,0:ny+1) integer, rho,u,v,up,vp(nx,ny); column-major.  Left-to-right expressions,

@@ -262,3 +262,42 @@ def test_product_calQ_matches_oracle_on_random_and_grazing_links(calq_shim):
         if checked > 40000:
             break
     assert checked > 20000 and grazing > 200
+
+
+# ---------------- the program's own run on one rank, from its text (make_golden_particles_run.py) ----------------
+PRUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_particles_run.npz"))
+
+
+def test_oracle_reproduces_the_particle_programs_run():
+    """case4/mpi_particle evaluated from its text as a whole program on one rank (56 x 72, two particles 3.5 cells apart):
+    initial() and 1, 2, 30 iterations of collision, streaming, bounceback, bounceback_particle (with calQ called as written),
+    macro, calForce, updateCenter (mask rebuild, refill), then check().  The restatement reproduces every population incl. the
+    ghost layers, rho, u, v, the solid mask, rhoAvg and the particle state bit for bit."""
+    nx, ny, N = (int(x) for x in PRUN["shape"])
+    x, y = PRUN["positions"]
+    wd = orc.ParticleWorld(x, y, nprocs=1, total_nx=nx, total_ny=ny)
+    names_p = ("Pi", "radius0", "rho0", "rhoSolid", "viscosity", "tauf", "Snu", "Sq", "gravity", "thresholdWall", "stiffWall",
+               "thresholdParticle", "stiffParticle")
+    assert tuple(getattr(wd.p, k) for k in names_p) == tuple(PRUN["params"])
+    wd.initial()
+    R = wd.ranks[0]
+    keys = ("xCenter", "yCenter", "Uc", "Vc", "rationalOmega", "wallTotalForceX", "wallTotalForceY", "totalTorque", "xCenterOld", "yCenterOld")
+
+    def same(tag, forces=True):
+        assert np.array_equal(R.f, PRUN[tag + "/f"]), tag
+        assert np.array_equal(R.f_post, PRUN[tag + "/f_post"]), tag
+        assert np.array_equal(np.stack([R.rho, R.u, R.v]), PRUN[tag + "/ruv"]), tag
+        assert np.array_equal(R.obst, PRUN[tag + "/obst"]), tag
+        got = np.stack([getattr(wd, k) for k in keys])
+        assert np.array_equal(got, PRUN[tag + "/particles"]), (tag, got - PRUN[tag + "/particles"])
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 30):
+        wd.step(n - done); done = n
+        same(f"run{n}")
+        assert wd.info()["rhoAvg"] == PRUN[f"run{n}/rhoAvg"][0]
+    assert PRUN["run30/particles"][5].any() and PRUN["run30/obst"].sum() > 500      # forces act; the particles are on the lattice
+    assert (PRUN["run30/obst"] != PRUN["run0/obst"]).any()                            # nodes were uncovered / covered: refill ran
+    assert wd.check() == PRUN["run30/check"][2]
+    wd.close()
