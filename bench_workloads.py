@@ -178,7 +178,9 @@ def lid2d(args, rank, local_rank, world):
         return
     torch.cuda.set_device(local_rank)
     n = args.size or 8192
-    sim = mg.LidDrivenCavity2D((n, n), variant="f", strict=args.arith == "strict", device=local_rank)
+    # MGLC_BENCH_L2D_VARIANT = c | f | i | s picks another of the reference's programs (default: the Fortran + MPI one)
+    l2d_variant = os.environ.get("MGLC_BENCH_L2D_VARIANT", "f")
+    sim = mg.LidDrivenCavity2D((n, n), variant=l2d_variant, strict=args.arith == "strict", device=local_rank)
     sim.initial()
     sim.step(max(args.warmup, 3)); sim.sync()
     if n * n <= (1 << 20):
@@ -229,7 +231,7 @@ def lid2d(args, rank, local_rank, world):
         "metric": "MLUPS", "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lid_driven_cavity_d2q9_mrt_{n}x{n}", "Re": 1000.0, "U0": 0.1, "arith": args.arith, "errorU": err,
+        "config": {"workload": f"lid_driven_cavity_d2q9_mrt_{n}x{n}" + ("" if l2d_variant == "f" else f"_variant_{l2d_variant}"), "Re": 1000.0, "U0": 0.1, "arith": args.arith, "errorU": err,
                    "l2": ("lattice (2 x %.1f GB) far exceeds the 126 MB L2; no flush needed" % (9 * cells * 8 / 1e9)) if cells > (1 << 22) else
                          ("lattice (2 x %.1f MB) is L2-resident: the rate is not an HBM figure; fused launches replayed from CUDA graphs" % (9 * cells * 8 / 1e6))},
         "roofline": {"bound": "hbm" if cells > (1 << 22) else "launch latency / L2", "kernel": f"mglc::{args.arith}::k_l2_fused", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

@@ -16,3 +16,5 @@ for v in ("i", "s"):
         s = mg.LidDrivenCavity2D((67, 45), variant=v, strict=strict, Re=100.0); s.initial(); s.step(140); print(v, strict, s.check()); s.close()
 PY
 (timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python $O/mc.py > $O/memcheck.log 2>&1; echo memcheck rc=$?); tail -4 $O/memcheck.log
+# 4. bench lines of the new 2-D lid variants (8192^2, HBM-bound like the others)
+for v in i s; do (MGLC_BENCH_L2D_VARIANT=$v timeout 200 python bench.py --workload lid2d --steps 50 --warmup 5 --no-cpu > $O/bench_lid2d_8192_variant_$v.json 2> $O/b_$v.err; echo bench $v rc=$?); tail -1 $O/bench_lid2d_8192_variant_$v.json | cut -c1-300; done
