@@ -73,3 +73,38 @@ def test_derived_types_mirror_the_c_structs():
         return n
     for struct in ("mglc_lbm_desc", "mglc_p2d_desc", "mglc_l2d_desc", "mglc_t2d_desc", "mglc_aa_desc"):
         assert c_fields(struct) == f_fields(struct), (struct, c_fields(struct), f_fields(struct))
+
+
+def c_constants():
+    """MGLC_* integer constants of include/mglc.h: #define NAME value and enum { NAME = value, NAME, ... } (implicit values count up)"""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mglc.h")).read(), flags=re.S)
+    vals = {}
+    for m in re.finditer(r"#define\s+(MGLC_[A-Z0-9_]+)\s+\(?(-?\d+)\)?\s*$", src, flags=re.M):
+        vals[m.group(1)] = int(m.group(2))
+    for m in re.finditer(r"enum\s*\w*\s*\{([^}]*)\}", src):
+        nxt = 0
+        for item in m.group(1).split(","):
+            item = item.strip()
+            if not item:
+                continue
+            name, _, v = (s.strip() for s in item.partition("="))
+            nxt = int(v, 0) if v else nxt
+            vals[name] = nxt
+            nxt += 1
+    return vals
+
+
+def test_fortran_constants_equal_the_c_header():
+    c = c_constants()
+    src = open(os.path.join(ROOT, "fortran", "mglc_iso_c.f90")).read()
+    src = "\n".join(l.split("!")[0] for l in src.splitlines())
+    seen = 0
+    for m in re.finditer(r"integer\(c_int\),\s*parameter\s*::\s*(.*)", src):
+        for item in m.group(1).split(","):
+            name, _, v = (s.strip() for s in item.partition("="))
+            assert name in c, f"{name} is not a constant of include/mglc.h"
+            assert c[name] == int(v), (name, c[name], v)
+            seen += 1
+    assert seen >= 15
+    for must in ("MGLC_L2D_C", "MGLC_L2D_F", "MGLC_L2D_INCOMP", "MGLC_L2D_C_SRT", "MGLC_T2D_MPI", "MGLC_T2D_ACC", "MGLC_BCT_PERIODIC"):
+        assert re.search(r"\b%s\b" % must, src), must
