@@ -7,7 +7,8 @@
  * (tests/test_examples_gpu.py compares its SHA-256 with the committed hash of the reference's own file).
  *
  *   gcc -std=c99 -O2 -Iinclude examples/lid2d_driver.c -Lmglc_b200 -lmglc -Wl,-rpath,$PWD/mglc_b200 -o lid2d_driver
- *   ./lid2d_driver [max_iterations = 2000] [strict = 1] [output = flow_binary]
+ *   ./lid2d_driver [max_iterations = 2000] [strict = 1] [output = flow_binary] [model = 2]
+ * model follows the program's own switch (c:13-14): 2 = MRT (its shipped setting), 1 = SRT / BGK.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,10 +28,15 @@ int main(int argc, char **argv) {
     const int itc_max = argc > 1 ? atoi(argv[1]) : 2000;
     const int strict = argc > 2 ? atoi(argv[2]) : 1;
     const char *out = argc > 3 ? argv[3] : "flow_binary";
+    const int model = argc > 4 ? atoi(argv[4]) : 2;        /* c:13-14: const int SRT = 1, MRT = 2; const int model = 2; */
+    if (model != 1 && model != 2) {
+        fprintf(stderr, "lid2d_driver: model must be 1 (SRT) or 2 (MRT)\n");
+        return 2;
+    }
     const double eps = 1e-6;
 
     mglc_l2d_desc d;
-    CHECK(mglc_l2d_desc_init(&d, MGLC_L2D_C));             /* 200 x 200, Re = 1000, u_zero = 0.1, rho_zero = 1 */
+    CHECK(mglc_l2d_desc_init(&d, model == 1 ? MGLC_L2D_C_SRT : MGLC_L2D_C));   /* 200 x 200, Re = 1000, u_zero = 0.1, rho_zero = 1 */
     d.arith = strict ? MGLC_ARITH_STRICT : MGLC_ARITH_FAST;
     const int NX = d.total_nx, NY = d.total_ny;
     const double height = (double)NX;

@@ -48,6 +48,15 @@ def main():
     out["check_1000"] = np.array([ref.lib.check(1000)])
     ref.step(100)
     out["check_1100"] = np.array([ref.lib.check(1100)])
+    # the program's own output file after 2000 iterations (what examples/lid2d_driver.c must write with model = 1)
+    ref.lib.initial()
+    ref.step(2000)
+    ref.lib.output_binary()
+    raw = open("flow_binary", "rb").read()
+    import hashlib
+    out["output_binary_len"] = np.array([len(raw)])
+    out["output_binary_sha256"] = np.frombuffer(hashlib.sha256(raw).digest(), dtype=np.uint8)
+    out["run2000/u_sum"] = np.array([ref.u.sum(), np.abs(ref.u).sum()])
     os.chdir(cwd)
     path = os.path.join(HERE, "ref_lid2d_srt.npz")
     np.savez_compressed(path, **out)

@@ -33,10 +33,14 @@ def _has_gpu():
 
 def test_c_driver_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
     exe = build(tmp_path)
+    r = subprocess.run([exe, "10", "1", "flow_binary", "3"], capture_output=True, text=True, cwd=tmp_path)      # c:13: SRT = 1, MRT = 2
+    assert r.returncode == 2 and "model" in r.stderr
     if _has_gpu():
         pytest.skip("a CUDA device is present: the run itself is covered by the gpu test")
     r = subprocess.run([exe, "10"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "no CUDA device" in r.stderr and not (tmp_path / "flow_binary").exists()
+    r = subprocess.run([exe, "10", "1", "flow_binary", "1"], capture_output=True, text=True, cwd=tmp_path)      # model = SRT
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
 def test_laplace_driver_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):

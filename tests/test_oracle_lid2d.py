@@ -385,3 +385,25 @@ def test_variant_f_reproduces_the_sequential_fortran_program(nprocs, dims):
     e = wd.check()
     assert abs(e - QGOLD["run20/check"][2]) <= (0 if nprocs == 1 else 1e-14 * abs(e))
     wd.close()
+
+
+def _flow_binary_bytes(wd):
+    """the bytes of the C program's output_binary() (c:428-457: x, y, rho, u, v as double[NX][NY]) from an oracle world"""
+    nx, ny = wd.total
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    x, y = i * (float(nx) / (nx - 1)), j * (float(nx) / (ny - 1))
+    return b"".join(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in (x, y, c_view(wd.gather("rho")), c_view(wd.gather("u")), c_view(wd.gather("v"))))
+
+
+@pytest.mark.parametrize("variant,gold", [("c", "c/"), ("s", "")])
+def test_output_file_of_the_c_program_after_2000_iterations(variant, gold):
+    """the SHA-256 of the file the compiled reference program wrote (MRT and SRT builds) == the same bytes assembled from the
+    restatement's fields: what examples/lid2d_driver.c must reproduce on the GPU with model = 2 / model = 1"""
+    import hashlib
+    G = GOLD if variant == "c" else SGOLD
+    wd = orc.Lid2DWorld((200, 200), variant=variant)
+    wd.initial(); wd.step(2000)
+    raw = _flow_binary_bytes(wd)
+    assert len(raw) == int(G[gold + "output_binary_len"][0])
+    assert hashlib.sha256(raw).digest() == G[gold + "output_binary_sha256"].tobytes()
+    wd.close()

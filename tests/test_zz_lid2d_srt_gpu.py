@@ -160,3 +160,19 @@ def test_decomposed_equals_single_subdomain_bit_for_bit(strict, nprocs, dims):
     for k in ("f", "rho", "u", "v"):
         assert np.array_equal(one.gather(k), many.gather(k)), k
     one.close(); many.close()
+
+
+def test_c_driver_with_the_srt_switch_writes_the_reference_programs_file(tmp_path):
+    """examples/lid2d_driver.c with model = 1 (the program's own SRT switch, c:13-14): after 2000 iterations in strict
+    arithmetic its flow_binary has the SHA-256 of the file the reference program compiled with that switch wrote"""
+    import hashlib
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe, lib = str(tmp_path / "lid2d_driver"), os.path.join(root, "mglc_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "lid2d_driver.c"), "-L", lib, "-lmglc", f"-Wl,-rpath,{lib}", "-o", exe])
+    r = subprocess.run([exe, "2000", "1", "flow_binary", "1"], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = (tmp_path / "flow_binary").read_bytes()
+    assert len(raw) == int(SGOLD["output_binary_len"][0])
+    assert hashlib.sha256(raw).digest() == SGOLD["output_binary_sha256"].tobytes()
