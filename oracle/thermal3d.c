@@ -13,7 +13,7 @@
  * streamingT B3:1081-1094, bounceback B3:900-980, bouncebackT B3:1106-1207 with the benchmark-cavity and the
  * RB-convection macro sets for 13 block positions, the check() sums B3:1242-1264); the exchange is MPI calls and is
  * checked by construction tests (tests/test_oracle_thermal.py).  Whole run: the SEQUENTIAL program 3d/seq/bouyancy3d.F90 with its
- * shipped macro set is evaluated from its text on 6 x 5 x 4 -- parameters, initial() and the driver loop for 1, 2, 10, 12
+ * shipped macro set (and again with its RB-convection set) is evaluated from its text on 6 x 5 x 4 -- parameters, initial() and the driver loop for 1, 2, 10, 12
  * iterations with check() (make_golden_thermal3d_seq_run.py -> ref_fortran_thermal3d_seq_run.npz) -- and this file reproduces its
  * f, g, rho, u, v, w, T, Fx, Fy, Fz bit for bit on 1..8 emulated ranks.
  *

@@ -4,13 +4,14 @@ walls, benchmarkCavity: back/front adiabatic, left/right constant T, plates adia
 
   B3S = /root/reference/MPI/Buoyancy_driven_cavity/fortran/3d/seq/bouyancy3d.F90
   parameters   B3S:10-28, :54-55 (nx, ny, nz replaced by 6, 5, 4)
-  initial      B3S:291-302 (weights), :316-325 (T on the constant-T walls), :350-364 (populations); the whole-array assignments
+  initial      B3S:291-302 (weights), :316-347 (T on the constant-T walls of the macro set), :350-364 (populations); the whole-array assignments
                (:289, :307-310, :386-392) are applied by this script
   collision    B3S:415-624     streaming   B3S:639-652     bounceback   B3S:664-723
   collisionT   B3S:767-809     streamingT  B3S:824-837     bouncebackT  B3S:849-919
   macro        B3S:736-750     macroT      B3S:931-937     check        B3S:950-976
 its loop (B3S:117-133: collision, streaming, bounceback, collisionT, streamingT, bouncebackT, macro, macroT) for 1, 2 and 10
-iterations with check() after 10 and 12.  The restatement of the MPI program (oracle/thermal3d.c) must reproduce this run on 1
+iterations with check() after 10 and 12; a second file holds the same run with the program's other macro set (RBconvection:
+plates at constant temperature, side walls adiabatic).  The restatement of the MPI program (oracle/thermal3d.c) must reproduce this run on 1
 and on several emulated ranks.  Only numbers are stored; run in the authoring container."""
 import os
 import sys
@@ -29,7 +30,10 @@ FULL = ["f", "f_post", "g", "g_post", "rho", "u", "v", "w", "t", "up", "vp", "wp
         "omega", "omegat", "un", "unt", "s", "m", "m_post", "meq", "fsource", "n", "n_post", "neq", "q"]
 
 
-def main():
+DEFS_RB = {"noslipWalls", "RBconvection", "BackFrontWallsAdiabatic", "LeftRightWallsAdiabatic", "TopBottomPlatesConstT"}   # B3S:74-79
+
+
+def main(DEFS=DEFS, name="ref_fortran_thermal3d_seq_run.npz"):
     nx, ny, nz = 6, 5, 4
     text = fe.read_lines(B3S, 10, 28).replace("nx=51, ny=nx, nz=nx", f"nx={nx}, ny={ny}, nz={nz}") + "\n" + fe.read_lines(B3S, 54, 55)
     P = eval_parameters(text)
@@ -38,7 +42,7 @@ def main():
     out = {"params": np.array([P[k] for k in names_p]), "shape": np.array([nx, ny, nz])}
     sc = dict(nx=nx, ny=ny, nz=nz, itc=0, **{k: P[k] for k in names_p}, thot=P["thot"], tcold=P["tcold"], tref=P["tref"])
     tr = lambda a, b: fe.translate(strip_cpp(fe.read_lines(B3S, a, b), DEFS), full_arrays=FULL)
-    src = {"weights": tr(291, 302), "initT": tr(316, 325), "initial": tr(350, 364), "collision": tr(415, 624), "streaming": tr(639, 652),
+    src = {"weights": tr(291, 302), "initT": tr(316, 347), "initial": tr(350, 364), "collision": tr(415, 624), "streaming": tr(639, 652),
            "bounceback": tr(664, 723), "macro": tr(736, 750), "collisionT": tr(767, 809), "streamingT": tr(824, 837),
            "bouncebackT": tr(849, 919), "macroT": tr(931, 937), "check": tr(950, 976)}
     F4, H4, S3 = (0, 1, 1, 1), (0, 0, 0, 0), (1, 1, 1)
@@ -79,10 +83,11 @@ def main():
     ns = call("check")
     out["run12/check"] = np.array([ns["erroru"], ns["errort"]])
     snap("run12")
-    path = os.path.join(HERE, "ref_fortran_thermal3d_seq_run.npz")
+    path = os.path.join(HERE, name)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
     main()
+    main(DEFS_RB, "ref_fortran_thermal3d_seq_run_rb.npz")       # the program's other macro set (RB convection, B3S:74-79)

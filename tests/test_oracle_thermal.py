@@ -210,14 +210,19 @@ def test_check_sums_match_the_fortran_text():
 SRUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal3d_seq_run.npz"))
 
 
+SRUN_RB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal3d_seq_run_rb.npz"))
+
+
+@pytest.mark.parametrize("macro_set", ["cavity", "rb"])
 @pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, None), (8, (2, 2, 2)), (6, (3, 1, 2))])
-def test_oracle_reproduces_the_sequential_thermal_programs_run(nprocs, dims):
+def test_oracle_reproduces_the_sequential_thermal_programs_run(nprocs, dims, macro_set):
     """3d/seq/bouyancy3d.F90 with its shipped macro set, evaluated from its text on 6 x 5 x 4: parameters, initial() and its loop
     (collision, streaming, bounceback, collisionT, streamingT, bouncebackT, macro, macroT) for 1, 2, 10 and 12 iterations, check()
     after 10 and 12.  The restatement of the MPI program reproduces f, g, rho, u, v, w, T and the force fields bit for bit on
     1, 2, 4, 6 and 8 emulated ranks (the reference's seq == MPI contract, from the sequential program's own text)."""
+    SRUN = SRUN_RB if macro_set == "rb" else globals()["SRUN"]          # the program's two macro sets (seq:74-85)
     total = tuple(int(x) for x in SRUN["shape"])
-    wd = orc.ThermalWorld(total, nprocs, dims=dims)
+    wd = orc.ThermalWorld(total, nprocs, dims=dims, bcT=BC_SETS[macro_set])
     names_p = ("tauf", "viscosity", "diffusivity", "omegaRatating", "paraA", "gBeta1", "gBeta", "Snu", "Sq", "Qd", "Qnu")
     assert tuple(getattr(wd.p, k) for k in names_p) == tuple(SRUN["params"])
     wd.initial()
