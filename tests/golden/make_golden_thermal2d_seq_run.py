@@ -49,6 +49,10 @@ STEADY = dict(path=S2, defs=DEFS, name="ref_fortran_thermal2d_seq_run.npz", para
               ranges={"weights": (446, 457), "initU": (466, 481), "initT": (507, 516), "initial": (545, 557), "collision": (638, 709),
                       "streaming": (726, 737), "bounceback": (754, 897), "macro": (927, 939), "collisionT": (958, 990),
                       "streamingT": (1007, 1019), "bouncebackT": (1036, 1131), "macroT": (1146, 1152), "check": (1168, 1193)})
+# the same program with its other temperature macro set switched on (S2:22-24 instead of :29-31): Rayleigh-Benard plates
+STEADY_RB = dict(STEADY, name="ref_fortran_thermal2d_seq_run_rb.npz",
+                 defs={"steadyFlow", "HorizontalWallsNoslip", "VerticalWallsNoslip", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsAdiabatic"},
+                 ranges=dict(STEADY["ranges"], initT=(507, 526)))
 ACCRUN = dict(path=ACC, defs=ACC_DEFS, name="ref_fortran_thermal2d_acc_run.npz", param_lines=((55, 61), (90, 103)),
               size_text="nx=513, ny=257", reorder=True,
               ranges={"weights": (419, 430), "initT": (511, 520), "initial": (532, 544), "collision": (624, 707), "streaming": (722, 743),
@@ -124,4 +128,5 @@ def main(cfg=STEADY):
 
 if __name__ == "__main__":
     main(STEADY)
+    main(STEADY_RB)
     main(ACCRUN)

@@ -324,14 +324,20 @@ def test_acc_periodic_run_splits_along_y_bit_exactly():
 SRUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_seq_run.npz"))
 
 
+SRUN_RB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_seq_run_rb.npz"))
+
+
+@pytest.mark.parametrize("macro_set", ["side_heated", "rb"])
 @pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, (2, 2)), (6, (3, 2)), (3, (1, 3))])
-def test_oracle_reproduces_the_sequential_side_heated_programs_run(nprocs, dims):
+def test_oracle_reproduces_the_sequential_side_heated_programs_run(nprocs, dims, macro_set):
     """seq/steady.F90 with its shipped macro set (side-heated cell, no-slip walls at rest), evaluated from its text on 9 x 7:
     parameters, initial() (T linear in x) and its loop of eight subroutines for 1, 2, 20 and 25 iterations, check() after 20 and
     25 -- including its separate corner statements in bounceback().  The restatement of the MPI program (variant "mpi", the
     side-heated set: the row INTEGRATION.md maps this file to) reproduces f, g, rho, u, v, T, Fx, Fy bit for bit on 1 to 6 ranks."""
+    # "rb": the same file with its Rayleigh-Benard macro set (steady.F90:22-24) switched on instead of the side-heated one
+    SRUN = SRUN_RB if macro_set == "rb" else globals()["SRUN"]
     total = tuple(int(x) for x in SRUN["shape"])
-    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=orc.T2_SIDE_HEATED, variant="mpi")
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=orc.T2_RAYLEIGH_BENARD if macro_set == "rb" else orc.T2_SIDE_HEATED, variant="mpi")
     assert tuple(getattr(wd.params, k) for k in ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")) == tuple(SRUN["params"])
     wd.initial()
 
