@@ -7,7 +7,8 @@
  * MPI/Laplace/c/laplace2d.c (functions jacobi() and swap(), built from the source where it lies into
  * oracle/_ref/liblaplace2d_ref.so by `make -C oracle ref`), and against the Fortran program's own text
  * (jacobi LAP:176-180 with a source term, check_diff LAP:193-198, init LAP:151-165, machine-evaluated by
- * tests/golden/make_golden_jacobi_fortran.py), see tests/test_oracle_jacobi.py.  The 3-D
+ * tests/golden/make_golden_jacobi_fortran.py; and the program's loop LAP:91-112 as a whole: 300 iterations of two sweeps with
+ * check_diff every 100, reproduced on 1, 4 and 6 emulated ranks), see tests/test_oracle_jacobi.py.  The 3-D
  * mode has no reference (LAP is 2-D only; BASELINE.json config 2 asks for 512^3): it is defined here
  * as the same update with the six face neighbours, summed x-,x+,y-,y+,z-,z+ then + f, times the
  * compile-time constant 1/6 -- the 2-D mode is its nz = 1 special case with 0.25.

@@ -5,6 +5,7 @@ from the REFERENCE's own source text (fortran_eval.py):
   init        LAP:151-165  (A = A_new = f = 0, the top halo row = 1 on the ranks that own the top boundary)
   jacobi      LAP:176-180  (A_new = 0.25*(A(i-1,j)+A(i+1,j)+A(i,j-1)+A(i,j+1)+f(i,j)); the literal 0.25 is single precision, exact)
   check_diff  LAP:193-198  (max |A_p - A| over the interior)
+  run         LAP:91-112   (the program's loop on one rank: 300 iterations = 150 x two sweeps, check_diff every 100)
 Only numbers are stored; run in the authoring container."""
 import os
 import sys
@@ -38,6 +39,27 @@ def main():
         ns = run_full(fe.translate(fe.read_lines(LAP, 151, 165), full_arrays=full),
                       {"a": fe._Arr(), "a_new": fe._Arr(), "f": fe._Arr(), "coords": arr(co, 1), "dims": arr(di, 1)}, sc)
         out[f"init_A_{k}"] = from_full(ns["a__"], (nx + 2, ny + 2), (0, 0))
+    # ---- the program's own loop (LAP:91-112) on one rank: init, then per iteration two sweeps (A -> A_new -> A, the halo
+    # exchange has no neighbours), check_diff + A_p = A every 100 iterations ----
+    rx, ry = 9, 7
+    init = fe.translate(fe.read_lines(LAP, 151, 165), full_arrays=full)
+    sweep = fe.translate(fe.read_lines(LAP, 176, 180), full_arrays=full)
+    diff = fe.translate(fe.read_lines(LAP, 193, 198), full_arrays=full)
+    scr = dict(nx=rx, ny=ry, max=max)
+    ns = run_full(init, {"a": fe._Arr(), "a_new": fe._Arr(), "f": fe._Arr(), "coords": arr((0, 0), 1), "dims": arr((1, 1), 1)}, scr)
+    A_, An_, f_ = ns["a__"], ns["a_new__"], ns["f__"]
+    Ap_ = fe._Arr(A_)                                                                    # LAP:93
+    itc, errs = 0, []
+    while itc < 300:
+        itc += 2                                                                         # LAP:95
+        An_ = run_full(sweep, {"a": A_, "a_new": An_, "f": f_}, scr)["a_new__"]           # jacobi(A, A_new, f), LAP:99
+        A_ = run_full(sweep, {"a": An_, "a_new": A_, "f": f_}, scr)["a_new__"]            # jacobi(A_new, A, f), LAP:103
+        if itc % 100 == 0:                                                               # LAP:105-107
+            errs.append(run_full(diff, {"a": A_, "a_p": Ap_}, scr)["error"])
+            Ap_ = fe._Arr(A_)                                                            # LAP:200
+            out[f"run/A_{itc}"] = from_full(A_, (rx + 2, ry + 2), (0, 0))
+    out["run/shape"] = np.array([rx, ry])
+    out["run/errors"] = np.array(errs)
     path = os.path.join(HERE, "ref_fortran_jacobi.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

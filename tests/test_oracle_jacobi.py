@@ -151,3 +151,18 @@ def test_fortran_jacobi_check_diff_and_init_match_the_text():
         want = FGOLD["init_A_1"] if inf["coords"][1] == 1 else FGOLD["init_A_2"]
         assert np.array_equal(wd.array(r, "A"), want) and np.array_equal(wd.array(r, "A_new"), want), inf
     wd.close()
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (4, None), (6, (3, 2))])
+def test_oracle_reproduces_the_fortran_programs_loop(nprocs, dims):
+    """jacobi2d_mpi.f90:91-112 evaluated from its text on one rank (9 x 7): init, 300 iterations (two sweeps per loop body),
+    check_diff every 100 -- bit for bit, also on 4 and 6 emulated ranks"""
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_jacobi.npz"))
+    total = tuple(int(x) for x in G["run/shape"])
+    wd = orc.JacobiWorld(total, nprocs, dims)
+    wd.init()
+    for k, itc in enumerate((100, 200, 300)):
+        wd.step(100)
+        assert wd.check_diff() == G["run/errors"][k]
+        assert np.array_equal(wd.gather(), G[f"run/A_{itc}"][1:-1, 1:-1]), itc
+    wd.close()
