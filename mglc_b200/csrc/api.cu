@@ -309,7 +309,10 @@ static int install_peers(mglc_lbm *h, const PeerView *view /* [19], valid where 
         h->sync.signal[d] = view[d].flags + opp_dir(d);     // the neighbour sees me in the opposite direction
         h->sync.wait[d] = h->flags + d;
     }
-    for (int b = 0; b < 2; ++b) MGLC_CUDA(cudaMemcpy(h->pt_dev[b], &pt[b], sizeof(PeerTable), cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2; ++b) {
+        pt[b].err = h->d_err;
+        MGLC_CUDA(cudaMemcpy(h->pt_dev[b], &pt[b], sizeof(PeerTable), cudaMemcpyHostToDevice));
+    }
     h->direct = 1;
     return MGLC_OK;
 }
@@ -415,18 +418,23 @@ extern "C" int mglc_lbm_launch_count(mglc_lbm *h, long long *n) {
     *n = h->launches;
     return MGLC_OK;
 }
+// The neighbour barrier of the direct-halo path reports through a sticky device word (k_halo_wait).  Every entry point
+// that hands results to the caller reads it once its stream has drained: a run whose neighbours fell out of step never
+// comes back as MGLC_OK.
+static int direct_status(mglc_lbm *h) {
+    if (!h->direct || h->group) return MGLC_OK;
+    int e = 0;
+    MGLC_CUDA(cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e & 1) { set_error("direct halo path: a neighbour did not reach the barrier within %.0f s (MGLC_HALO_TIMEOUT_S; ranks out of step?); the lattice was left untouched from that step on", halo_timeout_seconds()); return MGLC_E_STATE; }
+    if (e & 2) { set_error("direct halo path: a neighbour wrote the other ping-pong lattice (calls between mglc_lbm_step must be made by every rank)"); return MGLC_E_STATE; }
+    return MGLC_OK;
+}
 extern "C" int mglc_lbm_sync(mglc_lbm *h) {
     MGLC_TRY(use(h));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s_comm));
     MGLC_CUDA(cudaGetLastError());
-    if (h->direct) {
-        int e = 0;
-        MGLC_CUDA(cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
-        if (e & 1) { set_error("direct halo path: a neighbour did not reach the barrier within 20 s (ranks out of step?)"); return MGLC_E_STATE; }
-        if (e & 2) { set_error("direct halo path: a neighbour wrote the other ping-pong lattice (calls between mglc_lbm_step must be made by every rank)"); return MGLC_E_STATE; }
-    }
-    return MGLC_OK;
+    return direct_status(h);
 }
 
 static int canonicalise(mglc_lbm *h);
@@ -491,23 +499,36 @@ extern "C" int mglc_lbm_download_macro(mglc_lbm *h, double *rho, double *u, doub
     MGLC_TRY(copy_field(h, v, h->v, false));
     MGLC_TRY(copy_field(h, w, h->w, false));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
-    return MGLC_OK;
+    return direct_status(h);
 }
 extern "C" int mglc_lbm_download_f(mglc_lbm *h, double *f) {
     MGLC_TRY(use(h));
     MGLC_TRY(canonicalise(h));
     if (!f) return MGLC_E_INVALID;
-    return transfer_lattice(h, f, F_(h), 0, false);
+    MGLC_TRY(transfer_lattice(h, f, F_(h), 0, false));
+    return direct_status(h);
 }
 extern "C" int mglc_lbm_download_fpost(mglc_lbm *h, double *f_post) {
     MGLC_TRY(use(h));
     MGLC_TRY(canonicalise(h));
     if (!f_post) return MGLC_E_INVALID;
-    return transfer_lattice(h, f_post, Fpost_(h), 1, false);
+    MGLC_TRY(transfer_lattice(h, f_post, Fpost_(h), 1, false));
+    return direct_status(h);
 }
 
 // ---- single-subdomain building blocks ---------------------------------------------------------------------
+// before a subdomain is re-initialised: the neighbours' stores into my halos (direct path) or the exchange on s_comm
+// (overlapped path) that a previous step() left in flight must have landed, or they would hit the fresh lattice
+static int drain_halos(mglc_lbm *h) {
+    if (h->direct_valid) MGLC_TRY(wait_direct(h));
+    if (h->halo_inflight) {
+        MGLC_CUDA(cudaStreamWaitEvent(h->s, h->ev_halo, 0));
+        h->halo_inflight = 0;
+    }
+    return MGLC_OK;
+}
 static int do_initial(mglc_lbm *h) {
+    MGLC_TRY(drain_halos(h));
     h->rotated = 0;
     h->lid_next = h->lid_last_in = h->rho + (long long)h->g.nx * h->g.ny * (h->g.nz - 1);
     if (h->thermal) {
@@ -859,7 +880,7 @@ static int check_impl(mglc_lbm *h, double *errorU, double *errorT) {
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     *errorU = sqrt(e[0]) / sqrt(e[1]);
     if (errorT) *errorT = e[2] / e[3];
-    return MGLC_OK;
+    return direct_status(h);
 }
 extern "C" int mglc_check(mglc_lbm *h, double *errorU) {
     MGLC_TRY(use(h));
@@ -899,7 +920,7 @@ extern "C" int mglc_calNuRe(mglc_lbm *h, double prandtl, double *NuVolAvg, doubl
     MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     nure_from_sums(h, prandtl, e, NuVolAvg, ReVolAvg);
-    return MGLC_OK;
+    return direct_status(h);
 }
 // one line of a macroscopic field along `axis` through the global 1-based indices (g1, g2) of the other two axes (ascending
 // axis order), e.g. u(nxHalf, nyHalf, :) of getVelocity(), L3/output.f90:334-344, without a full-field download.
@@ -921,7 +942,7 @@ extern "C" int mglc_lbm_download_line(mglc_lbm *h, int field, int axis, int g1, 
                                 cudaMemcpyDeviceToHost, h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     *count = n;
-    return MGLC_OK;
+    return direct_status(h);
 }
 extern "C" int mglc_lbm_upload_thermal(mglc_lbm *h, const double *g, const double *T, const double *Fx, const double *Fy,
                                        const double *Fz) {
@@ -948,7 +969,7 @@ extern "C" int mglc_lbm_download_thermal(mglc_lbm *h, double *g, double *T, doub
     MGLC_TRY(copy_field(h, Fy, Fc + ncell(h), false));
     MGLC_TRY(copy_field(h, Fz, Fc + 2 * ncell(h), false));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
-    return MGLC_OK;
+    return direct_status(h);
 }
 extern "C" int mglc_lbm_upload_gpost(mglc_lbm *h, const double *g_post) {
     MGLC_TRY(use(h));
@@ -962,7 +983,8 @@ extern "C" int mglc_lbm_download_gpost(mglc_lbm *h, double *g_post) {
     MGLC_TRY(need_thermal(h, "mglc_lbm_download_gpost"));
     MGLC_TRY(canonicalise(h));
     if (!g_post) return MGLC_E_INVALID;
-    return transfer_lattice(h, g_post, Gpost_(h), 1, false, QT);
+    MGLC_TRY(transfer_lattice(h, g_post, Gpost_(h), 1, false, QT));
+    return direct_status(h);
 }
 
 // nsteps iterations of: collision, exchange, streaming, bounceback, macro  (L3/main.f90:85-97).
@@ -1006,7 +1028,7 @@ extern "C" int mglc_lbm_step_timed(mglc_lbm *h, int nsteps, float *ms) {
     MGLC_CUDA(cudaEventSynchronize(h->ev_t1));
     MGLC_CUDA(cudaGetLastError());
     MGLC_CUDA(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
-    return MGLC_OK;
+    return direct_status(h);
 }
 // 1 (default) = overlap the halo exchange with the interior update when the handle has neighbours and a
 // communicator; 0 = exchange, then update (what the blocking reference driver does, L3/main.f90:89-93)
@@ -1139,7 +1161,11 @@ static int group_exchange(mglc_group *g, int which = MSG_ALL) {
         [&](int r, cudaStream_t s) { return do_unpack(g->r[r], s); });
 }
 
-extern "C" int mglc_group_initial(mglc_group *g) { GROUP_EACH(g, do_initial); }
+extern "C" int mglc_group_initial(mglc_group *g) {
+    if (!g) return MGLC_E_INVALID;
+    FOR_RANKS(g, h) { MGLC_TRY(use(h)); MGLC_TRY(drain_halos(h)); }      // every member, before any member starts over
+    GROUP_EACH(g, do_initial);
+}
 extern "C" int mglc_group_collision(mglc_group *g) { GROUP_EACH(g, do_collision); }
 extern "C" int mglc_group_exchange(mglc_group *g) {
     if (!g) return MGLC_E_INVALID;

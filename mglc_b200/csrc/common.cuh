@@ -52,6 +52,10 @@ struct PeerTable {
     double *G[6];              // thermal: its g_post lattice
     long long sy[19], sz[19], sq[19];
     int n[19][3];              // the neighbour's interior size
+    // sticky error word of the neighbour barrier (k_halo_wait): once set, a launch with direct halo stores does
+    // nothing at all -- it neither reads halos a neighbour has not written nor overwrites halos a neighbour may
+    // still be reading; the host reports MGLC_E_STATE at every point where it synchronises
+    const int *err;
 };
 
 // the flag words of the neighbour barrier that goes with PeerTable: signal[d] = my slot in the memory of the
@@ -168,6 +172,7 @@ int launch_nure(const Geom &g, const double *u, const double *v, const double *w
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
 int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s);
 int launch_halo_wait(const SyncTable &t, unsigned long long epoch, int *err, cudaStream_t s);
+double halo_timeout_seconds();
 int check_scratch_doubles();
 void msg_dims(const Geom &g, int dir, int &n1, int &n2, int &npop);
 

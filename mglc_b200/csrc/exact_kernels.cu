@@ -1,6 +1,8 @@
 // exact_kernels.cu -- kernels whose results are bit-defined (copies, order-preserving sums, IEEE
 // divisions): initial(), streaming(), bounceback(), macro(), check() reductions, halo pack/unpack and the AoS<->SoA transposes of upload/download.
 // Built with -fmad=false so nothing is contracted; see lbm_kernels.inl for the collision kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "d3q19_mrt.inl"
 #include "d3q19_thermal.inl"
@@ -502,8 +504,11 @@ int launch_nure(const Geom &g, const double *u, const double *v, const double *w
 // ---- neighbour barrier of the direct-halo path --------------------------------------------------------------------
 // After a fused launch that stored into the neighbours' halos, every subdomain raises its epoch in a flag word that
 // lives in each neighbour's memory (signal); before anything reads its own halos it waits until all neighbours have
-// raised theirs (wait).  Kernel completion orders the halo stores before the flag store on the same stream; the wait
-// gives up after ~20 s and sets *err instead of hanging the device.
+// raised theirs (wait).  Kernel completion orders the halo stores before the flag store on the same stream.  Like
+// MPI_Waitall (lid3_mpi_nonblock.f90:1229) the wait lasts as long as the slowest neighbour's host takes to issue its
+// launch; it is bounded (MGLC_HALO_TIMEOUT_S, default 600 s) only so that ranks that really fell out of step cannot hang
+// the device for ever.  Running out of time does NOT let the stream carry on: *err becomes sticky, every later launch
+// with direct halo stores returns at once (PeerTable::err) and the host reports MGLC_E_STATE.
 __global__ void k_halo_signal(SyncTable t, unsigned long long epoch /* the word, see k_halo_wait */) {
     const int d = threadIdx.x;
     if (d < 19 && (t.mask >> d & 1u)) {
@@ -512,7 +517,7 @@ __global__ void k_halo_signal(SyncTable t, unsigned long long epoch /* the word,
     }
 }
 // word = 2 * epoch + ping-pong index of the lattice the launch wrote: neighbours out of step on the index are reported
-__global__ void k_halo_wait(SyncTable t, unsigned long long word, int *err) {
+__global__ void k_halo_wait(SyncTable t, unsigned long long word, int *err, unsigned long long timeout_ns) {
     const int d = threadIdx.x;
     if (d < 19 && (t.mask >> d & 1u)) {
         unsigned long long t0, seen;
@@ -520,19 +525,27 @@ __global__ void k_halo_wait(SyncTable t, unsigned long long word, int *err) {
         while (((seen = *(volatile unsigned long long *)t.wait[d]) >> 1) < (word >> 1)) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 20000000000ull) { atomicOr(err, 1); break; }
+            if (now - t0 > timeout_ns || *(volatile int *)err) { atomicOr(err, 1); break; }
             __nanosleep(200);
         }
         if ((seen >> 1) == (word >> 1) && ((seen ^ word) & 1ull)) atomicOr(err, 2);
         __threadfence_system();
     }
 }
+double halo_timeout_seconds() {
+    static double v = -1.0;
+    if (v < 0.0) {
+        v = 600.0;
+        if (const char *e = getenv("MGLC_HALO_TIMEOUT_S")) { const double q = atof(e); if (q > 0.0) v = q; }
+    }
+    return v;
+}
 int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s) {
     k_halo_signal<<<1, 32, 0, s>>>(t, epoch);
     return 1;
 }
 int launch_halo_wait(const SyncTable &t, unsigned long long word, int *err, cudaStream_t s) {
-    k_halo_wait<<<1, 32, 0, s>>>(t, word, err);
+    k_halo_wait<<<1, 32, 0, s>>>(t, word, err, (unsigned long long)(halo_timeout_seconds() * 1e9));
     return 1;
 }
 

@@ -8,9 +8,16 @@
 //   k_jacobi3d   A_new = (1/6) * (x- + x+ + y- + y+ + z- + z+ + f); register blocking: a thread marches along z with
 //                the z-1 / z / z+1 values of 4 consecutive rows in registers, x neighbours by warp shuffle, so a
 //                cell costs one DRAM read and one write (16 B, 24 B with a source term)
+//   k_jacobi3d_tma   the same update as a persistent TMA pipeline (the default in 3-D): one CTA per SM marches tiles of
+//                128 x 16 cells along z; a producer thread streams the (130 x 18) halo'd planes into a ring of shared-memory
+//                stages with cp.async.bulk.tensor (completion on mbarriers), 16 consumer warps keep z-1 / z / z+1 of their
+//                4 cells in registers and take the x / y neighbours from the stage; the loads in flight no longer depend
+//                on registers or occupancy
 //   k_face_pack / k_face_unpack   replace the contiguous-row and MPI_Type_vector column messages of
 //                exchange_message (LAP:223-254)
 //   k_absdiff_max   check_diff (LAP:185-204)
+#include <cuda.h>      // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, libcuda is not linked)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -36,6 +43,8 @@ struct JacSub {
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
     Msg msgs[6];
     long long launches;
+    CUtensorMap tmap[2]; // 3-D tiled maps of A[0], A[1] (box 130 x 18 x 1 doubles) for k_jacobi3d_tma
+    int tma_ok;
 };
 
 __device__ __forceinline__ void face_cell(const Geom &g, int face, int ghost, int t1, int t2, int &i, int &j, int &k) {
@@ -123,6 +132,167 @@ __global__ void __launch_bounds__(JTX, JRY <= 4 ? 8 : 4) k_jacobi3d(Geom g, cons
     }
 }
 
+// ---- the TMA pipeline --------------------------------------------------------------------------------------------------
+// Tile = TBX x TBY cells of one z plane; a stage holds the tile with its one-cell x / y rim: (TBX+2) x (TBY+2) doubles, dense.
+// Work = tiles x planes, cut into z slabs of `slab` planes; inside a slab the tile-planes (tile-major, z-minor) are dealt to
+// the CTAs as equal contiguous ranges, so every CTA streams the same number of planes (no last-wave tail) and all CTAs stay
+// within one slab of each other in z: the rims a tile shares with its neighbours are read from DRAM once and hit the L2 after.
+constexpr int TBX = 128, TBY = 16, TRY = 4;                 // tile, rows per consumer thread
+constexpr int TMA_CONSUMERS = TBX * (TBY / TRY);            // 512 threads = 16 warps
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32;             // + the producer warp
+constexpr int TSX = TBX + 2, TSY = TBY + 2;
+constexpr int TMA_STAGE_BYTES = ((TSX * TSY * 8 + 127) / 128) * 128;
+constexpr int tma_smem(int stages) { return stages * TMA_STAGE_BYTES + 2 * stages * 8 + 128; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_plane(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// the ranges of (tile, k) a CTA owns, slab after slab; producer and consumers walk the same sequence
+struct TmaWalk {
+    int ntiles, nz, slab, k_lo;
+    long long pos, end;        // tile-planes of the current slab still to do: [pos, end)
+    int s, hs;                 // slab index, its height
+    __device__ void init(int ntiles_, int k_lo_, int k_hi_, int slab_) {
+        ntiles = ntiles_; k_lo = k_lo_; nz = k_hi_ - k_lo_ + 1; slab = slab_; s = -1; pos = end = 0;
+    }
+    // next segment: tile t, planes ka..kb (inclusive); false when the CTA is done
+    __device__ bool next(int &t, int &ka, int &kb) {
+        while (pos >= end) {
+            if (++s >= (nz + slab - 1) / slab) return false;
+            hs = min(slab, nz - s * slab);
+            const long long w = (long long)ntiles * hs;
+            pos = w * blockIdx.x / gridDim.x;
+            end = w * (blockIdx.x + 1) / gridDim.x;
+        }
+        t = (int)(pos / hs);
+        const int z0 = (int)(pos - (long long)t * hs);
+        const int z1 = (int)min((long long)hs, z0 + (end - pos));
+        ka = k_lo + s * slab + z0;
+        kb = k_lo + s * slab + z1 - 1;
+        pos += z1 - z0;
+        return true;
+    }
+};
+
+// TMA_STAGES = 10 with one CTA per SM (169 KB of planes in flight), or 5 with two CTAs per SM
+template <bool HAS_F, int TMA_STAGES>
+__global__ void __launch_bounds__(TMA_THREADS, TMA_STAGES > 5 ? 1 : 2) k_jacobi3d_tma(const __grid_constant__ CUtensorMap mapA, Geom g,
+                                                                 const double *__restrict__ f, double *__restrict__ B,
+                                                                 int k_lo, int k_hi, int slab) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *base = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t *full = (uint64_t *)(base + TMA_STAGES * TMA_STAGE_BYTES), *empty = full + TMA_STAGES;
+    const int tiles_x = (g.nx + TBX - 1) / TBX, tiles_y = (g.ny + TBY - 1) / TBY;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < TMA_STAGES; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    TmaWalk wk;
+    wk.init(tiles_x * tiles_y, k_lo, k_hi, slab);
+    int t, ka, kb;
+    unsigned n = 0;                                            // running plane counter: stage = n % STAGES
+    if (threadIdx.x >= TMA_CONSUMERS) {
+        // ---- producer: one thread streams planes ka-1 .. kb+1 of every segment into the ring
+        if (threadIdx.x == TMA_CONSUMERS) {
+            while (wk.next(t, ka, kb)) {
+                const int x0 = (t % tiles_x) * TBX + OX - 1, y0 = (t / tiles_x) * TBY;      // halo cell (i0-1, j0-1)
+                for (int k = ka - 1; k <= kb + 1; ++k, ++n) {
+                    const unsigned st = n % TMA_STAGES, ph = (n / TMA_STAGES) & 1u;
+                    mbar_wait(empty + st, ph ^ 1u);
+                    mbar_expect_tx(full + st, TSX * TSY * 8);
+                    tma_load_plane(base + st * TMA_STAGE_BYTES, &mapA, full + st, x0, y0, k);
+                }
+            }
+        }
+        return;
+    }
+    // ---- consumers: thread = one x column, TRY consecutive rows
+    const int lx = threadIdx.x % TBX, rg = threadIdx.x / TBX;
+    const int so = (rg * TRY + 1) * TSX + lx + 1;              // my first cell inside a stage
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    while (wk.next(t, ka, kb)) {
+        const int i = 1 + (t % tiles_x) * TBX + lx, j0 = 1 + (t / tiles_x) * TBY + rg * TRY;
+        const bool active = i <= g.nx;
+        long long c = g.idx(0, min(i, g.nx), min(j0, g.ny + 1), ka);
+        double below[TRY], cen[TRY], up[TRY];
+        {   // plane ka-1: only my own cells, then the stage is free again
+            const unsigned st = n % TMA_STAGES, ph = (n / TMA_STAGES) & 1u;
+            mbar_wait(full + st, ph);
+            const double *S = (const double *)(base + st * TMA_STAGE_BYTES);
+#pragma unroll
+            for (int r = 0; r < TRY; ++r) below[r] = S[so + r * TSX];
+            __syncwarp();
+            if (lane0) mbar_arrive(empty + st);
+            ++n;
+        }
+        {   // plane ka
+            const unsigned st = n % TMA_STAGES, ph = (n / TMA_STAGES) & 1u;
+            mbar_wait(full + st, ph);
+            const double *S = (const double *)(base + st * TMA_STAGE_BYTES);
+#pragma unroll
+            for (int r = 0; r < TRY; ++r) cen[r] = S[so + r * TSX];
+        }
+        for (int k = ka; k <= kb; ++k) {
+            const unsigned st = n % TMA_STAGES;                                           // holds plane k (already waited for)
+            const unsigned su = (n + 1) % TMA_STAGES, pu = ((n + 1) / TMA_STAGES) & 1u;   // plane k+1
+            const double *S = (const double *)(base + st * TMA_STAGE_BYTES);
+            const double *U = (const double *)(base + su * TMA_STAGE_BYTES);
+            mbar_wait(full + su, pu);
+#pragma unroll
+            for (int r = 0; r < TRY; ++r) up[r] = U[so + r * TSX];
+            const double ym = S[so - TSX], yp = S[so + TRY * TSX];
+#pragma unroll
+            for (int r = 0; r < TRY; ++r) {
+                double s = S[so + r * TSX - 1] + S[so + r * TSX + 1];
+                s += (r == 0) ? ym : cen[r - 1];
+                s += (r == TRY - 1) ? yp : cen[r + 1];
+                s += below[r];
+                s += up[r];
+                const long long cr = c + (long long)r * g.sy;
+                if (active && j0 + r <= g.ny) {
+                    s += HAS_F ? f[cr] : 0.0;
+                    B[cr] = (1.0 / 6.0) * s;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < TRY; ++r) { below[r] = cen[r]; cen[r] = up[r]; }
+            __syncwarp();
+            if (lane0) mbar_arrive(empty + st);                // plane k is no longer needed by this warp
+            ++n;
+            c += g.sz;
+        }
+        // plane kb+1 was only read as `up`
+        __syncwarp();
+        if (lane0) mbar_arrive(empty + (n % TMA_STAGES));
+        ++n;
+    }
+}
+
 // planes a CTA marches: short chunks keep the last wave of CTAs small (the sweep of a 512^3 block lasts only
 // ~0.4 ms, so a partly filled last wave costs several per cent), long chunks re-read fewer start-up planes
 // rows a thread owns (4 or 8): more rows re-read fewer y-neighbour rows from the L2 but need more registers -- measured on
@@ -192,6 +362,64 @@ extern "C" int mglc_dims_create_nd(int nranks, int ndim, int dims[3]) {
 
 static int jac_use(JacSub *S) { MGLC_CUDA(cudaSetDevice(S->device)); return MGLC_OK; }
 
+// 3-D tiled tensor maps over the padded arrays for k_jacobi3d_tma: dims (px, py, pz) doubles, box (TBX+2, TBY+2, 1), no
+// swizzle (the stage is read row-wise by consecutive lanes: conflict-free as it is), out-of-bounds = 0 (tiles overhanging
+// the block; those cells are never stored).  cuTensorMapEncodeTiled is looked up in the driver at run time.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+static void jac_make_tmaps(JacSub *S) {
+    S->tma_ok = 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return;
+    const cuuint64_t dims[3] = {(cuuint64_t)S->g.px, (cuuint64_t)S->g.py, (cuuint64_t)S->g.pz};
+    const cuuint64_t strides[2] = {(cuuint64_t)S->g.sy * 8, (cuuint64_t)S->g.sz * 8};
+    const cuuint32_t box[3] = {TSX, TSY, 1}, estr[3] = {1, 1, 1};
+    for (int b = 0; b < 2; ++b)
+        if (enc(&S->tmap[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, S->A[b], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+    if (cudaFuncSetAttribute(k_jacobi3d_tma<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(10)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_jacobi3d_tma<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(10)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_jacobi3d_tma<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(5)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_jacobi3d_tma<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(5)) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    S->tma_ok = 1;
+}
+static int jacobi_tma_ctas() {            // CTAs per SM of the TMA pipeline: 1 (10 stages) or 2 (5 stages each)
+    static int v = 0;
+    if (!v) { v = 1; if (const char *e = getenv("MGLC_JACOBI_TMA_CTAS")) v = atoi(e) == 2 ? 2 : 1; }
+    return v;
+}
+// MGLC_JACOBI_KERNEL=reg keeps the register-blocked LDG kernel (k_jacobi3d); default: the TMA pipeline
+static bool jacobi_use_tma() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MGLC_JACOBI_KERNEL"); v = !(e && !strcmp(e, "reg")); }
+    return v != 0;
+}
+static int jacobi_slab(int nz) {
+    static int v = 0;
+    if (!v) { v = 64; if (const char *e = getenv("MGLC_JACOBI_SLAB")) v = std::max(1, atoi(e)); }
+    return std::min(v, nz);
+}
+static int sm_count(int device) {
+    static int n[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (!n[device]) { cudaDeviceGetAttribute(&n[device], cudaDevAttrMultiProcessorCount, device); if (n[device] <= 0) n[device] = 148; }
+    return n[device];
+}
+
 static void jac_free_sub(JacSub *S) {
     if (!S) return;
     cudaSetDevice(S->device);
@@ -256,6 +484,7 @@ static int jac_make_sub(mglc_jacobi *h, int rank, int device, JacSub **out) {
         if (M.recv_count && cudaMalloc((void **)&M.rbuf, M.recv_count * sizeof(double)) != cudaSuccess) return fail(MGLC_E_NOMEM);
     }
     if (cudaStreamSynchronize(S->s) != cudaSuccess) return fail(MGLC_E_CUDA);
+    if (h->ndim == 3) jac_make_tmaps(S);
     *out = S;
     return MGLC_OK;
 }
@@ -448,6 +677,15 @@ static int jac_sweep(mglc_jacobi *h) {
             const dim3 grid((S->n[0] + 127) / 128, S->n[1]);
             if (S->f) k_jacobi2d<true><<<grid, 128, 0, S->s>>>(S->g, A, S->f, B);
             else k_jacobi2d<false><<<grid, 128, 0, S->s>>>(S->g, A, nullptr, B);
+        } else if (S->tma_ok && jacobi_use_tma()) {
+            const int tiles = ((S->n[0] + TBX - 1) / TBX) * ((S->n[1] + TBY - 1) / TBY);
+            const int slab = jacobi_slab(S->n[2]);
+            const int per_sm = jacobi_tma_ctas();
+            const int grid = (int)std::min<long long>((long long)sm_count(S->device) * per_sm, (long long)tiles * slab);
+#define MGLC_JAC_TMA(HASF, NST, FPTR) k_jacobi3d_tma<HASF, NST><<<grid, TMA_THREADS, tma_smem(NST), S->s>>>(S->tmap[S->cur], S->g, FPTR, B, 1, S->n[2], slab)
+            if (per_sm == 2) { if (S->f) MGLC_JAC_TMA(true, 5, S->f); else MGLC_JAC_TMA(false, 5, nullptr); }
+            else { if (S->f) MGLC_JAC_TMA(true, 10, S->f); else MGLC_JAC_TMA(false, 10, nullptr); }
+#undef MGLC_JAC_TMA
         } else {
             const int kch = jacobi_kch(S->n[2]);
             const int JRY = jacobi_jry();

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
     if (i > i1 || j > j1) return;
+    if (PEER && pt->err && *pt->err) return;      // the neighbour barrier failed: touch nothing (see PeerTable::err)
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k), m = g.cell(i, j, k);
     const long long n = (long long)g.nx * g.ny * g.nz;

@@ -33,8 +33,23 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define Q 19
+
+/* Thread count of every OpenMP loop in this library, set and read back by bench.py's CPU legs: a launcher such as
+ * torch.distributed.run exports OMP_NUM_THREADS=1, and the environment is only read when the OpenMP runtime starts. */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* D3Q19 velocity set, L3/commondata.f90:32-40 */
 static const int ex[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};

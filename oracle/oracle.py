@@ -49,7 +49,20 @@ def load(native=False):
     lib.orc_collide_cell.argtypes = [_dp] + [C.c_double] * 6 + [_dp]
     lib.orc_collide_cell_bgk.argtypes = [_dp] + [C.c_double] * 5 + [_dp]
     lib.orc_world_set_bgk.argtypes = [C.c_void_p, C.c_int]
+    lib.orc_set_threads.argtypes = [C.c_int]
+    lib.orc_set_threads.restype = C.c_int
     return lib
+
+
+def set_threads(n=0, native=False):
+    """Run the oracle's OpenMP loops on n threads (0 = every core this process may use) and return the count the OpenMP
+    runtime reports afterwards -- the number bench.py prints as `cores`.  Overrides an inherited OMP_NUM_THREADS=1."""
+    if n <= 0:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    return int((load(native) if native else lib()).orc_set_threads(n))
 
 
 _LIB = None
