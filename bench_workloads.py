@@ -12,42 +12,62 @@ import tempfile
 import time
 
 
+def jacobi_config(n, dims, gn, cells_local):
+    return {"workload": f"jacobi3d_7pt_{n}^3_per_gpu", "global_grid": list(gn), "decomposition": "x".join(map(str, dims)),
+            "l2": "two %.1f GB arrays per GPU exceed the 126 MB L2; no flush needed" % (cells_local * 8 / 1e9)}
+
+
+def jacobi_reference(args, rank, world):
+    """--impl reference --workload jacobi: the CPU restatement of jacobi2d_mpi.f90's loop in 3-D (oracle/jacobi.c, OpenMP) on a
+    bounded slab of one block, all host threads"""
+    if rank != 0:
+        return
+    import bench as B
+    from oracle import oracle as orc
+    threads = orc.set_threads(0)
+    n = args.size
+    dims = B.dims_create(world)
+    gn = tuple(n * d for d in dims) if args.scaling == "weak" else (n, n, n)
+    per = [n, n, n] if args.scaling == "weak" else [n // d for d in dims]
+    nz = max(8, min(per[2], 64))
+    wd = orc.JacobiWorld((per[0], per[1], nz), 1)
+    wd.init(); wd.step(max(1, args.warmup))
+    t0 = time.perf_counter(); wd.step(args.steps); dt = time.perf_counter() - t0
+    wd.close()
+    v = per[0] * per[1] * nz * args.steps / dt / 1e6
+    sample = f"{per[0]}x{per[1]}x{nz} slab of one block per iteration, {args.steps} iterations in {dt:.1f} s, oracle/jacobi.c on {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mcells/s", "value": round(v, 1), "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": jacobi_config(n, dims, gn, per[0] * per[1] * per[2]),
+        "cpu_baseline": {"value": round(v, 1), "unit": "Mcells/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 1), "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
 def jacobi(args, rank, local_rank, world):
+    if args.impl == "reference":
+        return jacobi_reference(args, rank, max(world, args.gpus))
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
     import bench as B
     import mglc_b200 as mg
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; mglc_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    D = B.Dist(rank, local_rank, world)
     n = args.size
     dims = mg.dims_create_nd(world, 3)
     gn = tuple(n * d for d in dims) if args.scaling == "weak" else (n, n, n)
-    comm = None
-    if world > 1:
-        def bcast(b):
-            box = [b]
-            dist.broadcast_object_list(box, src=0)
-            return box[0]
-        comm = mg.Communicator(world, rank, local_rank, bcast)
+    comm = D.communicator(mg)
+    parity = None
+    if world > 1 and not args.no_parity:
+        sys.path.insert(0, os.path.join(B.ROOT, "tests", "dist"))
+        import parity_suite as ps
+        parity = ps.jacobi(comm, rank, world)
+        if D.max(1.0 if (rank == 0 and ps.failed(parity)) else 0.0) > 0:
+            if rank == 0:
+                print(json.dumps({"metric": "Mcells/s", "value": None, "n_gpus": world, "parity": parity,
+                                  "error": "decomposed run does not match the oracle; nothing was timed"}), flush=True)
+            comm.close(); D.close()
+            sys.exit(3)
     sim = mg.Jacobi(gn, comm=comm) if comm else mg.Jacobi(gn, device=local_rank)
     cells_local = int(np.prod(sim.info[0]["n"]))
     cells_total = int(np.prod(gn))
@@ -58,109 +78,217 @@ def jacobi(args, rank, local_rank, world):
     if rank == 0:
         sampler.start()
     l0 = sim.launch_count()
-    barrier()
-    ms = reduce_max(sim.step_timed(args.steps))
-    barrier()
+    D.barrier()
+    ms = D.max(sim.step_timed(args.steps))
+    D.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = sim.launch_count() - l0
+    launches = D.sum(float(sim.launch_count() - l0))
     value = cells_total * args.steps / (ms * 1e-3) / 1e6
     peak, peak_src = B.hbm_peak()
     achieved = 16 * cells_local * args.steps / (ms * 1e-3) / 1e9
+    kernel = "k_jacobi3d<0,4>" if os.environ.get("MGLC_JACOBI_KERNEL") == "reg" else "k_jacobi3d_tma"
+    tr = B.ncu_traffic(kernel, cells_local)
     # end to end: host arrays in, `steps` iterations, check_diff, host array out
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         A = sim.download(0)
-        barrier()
+        D.barrier()
         t0 = time.perf_counter()
         sim.upload(0, A=A, A_new=A)
         sim.step(args.steps)
         err = sim.check_diff()
         A = sim.download(0)
-        barrier()
-        dt = time.perf_counter() - t0
-        e2e = {"value": round(cells_total * args.steps / dt / 1e6, 1), "unit": "Mcells/s", "h2d_bytes_per_step": int(2 * A.nbytes / args.steps),
-               "d2h_bytes_per_step": int(A.nbytes / args.steps), "seconds": round(dt, 3), "check_diff": err,
+        D.barrier()
+        dt = D.max(time.perf_counter() - t0)
+        e2e = {"value": round(cells_total * args.steps / dt / 1e6, 1), "unit": "Mcells/s", "h2d_bytes_per_step": int(2 * A.nbytes * world / args.steps),
+               "d2h_bytes_per_step": int(A.nbytes * world / args.steps), "seconds": round(dt, 3), "check_diff": err,
                "region": f"upload A, A_new (pageable host) + {args.steps} iterations + check_diff + download A"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as orc
-        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+        threads = orc.set_threads(0)
         wd = orc.JacobiWorld((256, 256, 256), 1)
         wd.init()
         wd.step(2)
         t0 = time.perf_counter(); wd.step(40); dt = time.perf_counter() - t0
-        cpu = {"value": round(256 ** 3 * 40 / dt / 1e6, 1), "unit": "Mcells/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": round(256 ** 3 * 40 / dt / 1e6, 1), "unit": "Mcells/s", "cores": threads, "kind": "port",
                "sample": f"256^3 x 40 iterations ({dt:.1f} s), oracle/jacobi.c (-O2, OpenMP)"}
         wd.close()
+    halo = sim.halo_mode() if hasattr(sim, "halo_mode") else None
     sim.close()
     if rank == 0:
-        print(json.dumps({
+        out = {
             "metric": "Mcells/s", "value": round(value, 1), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"jacobi3d_7pt_{n}^3_per_gpu", "global_grid": list(gn), "decomposition": "x".join(map(str, dims)),
-                       "l2": "two %.1f GB arrays exceed the 126 MB L2; no flush needed" % (cells_local * 8 / 1e9)},
-            "roofline": {"bound": "hbm", "kernel": "k_jacobi3d", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 16,
+            "config": jacobi_config(n, dims, gn, cells_local),
+            "detail": {"kernel": kernel, "halo_exchange": halo},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "bytes_per_cell": 16, "cells_per_launch": cells_local, "traffic_source": (tr or {}).get("source"),
                          "note": "whole step (exchange + sweep) timed, not the kernel alone"},
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches)}
+        if parity is not None:
+            out["parity"] = parity
+        print(json.dumps(out), flush=True)
     if comm:
         comm.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
+
+
+def particle_raster(nx, ny, seed=11):
+    """the reference's seeding (P4/initial.F90:49-75: a raster with 50 nodes between centres, each centre moved by up to +-10),
+    extended over a lattice of any size; the jitter comes from our own seeded generator (random_number is compiler-specific)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    gx, gy = np.meshgrid(np.arange(25.0, nx - 20, 50.0), np.arange(25.0, ny - 20, 50.0), indexing="ij")
+    xs = (gx + (rng.random(gx.shape) - 0.5) * 20).ravel(order="F")
+    ys = (gy + (rng.random(gy.shape) - 0.5) * 20).ravel(order="F")
+    return xs, ys
+
+
+def particles_config(edge, world, total, nparticles):
+    return {"workload": f"micro_particles_d2q9_{edge}x{edge}_per_gpu" if edge else "micro_particles_d2q9_201x801_64_particles",
+            "global_lattice": list(total), "decomposition": f"1x{world}" if edge else "1x1", "particles": int(nparticles),
+            "radius": 10.0, "seeding": "50-node raster, +-10 jitter (P4/initial.F90:49-75)",
+            "l2": ("lattice (2 x %.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (9 * edge * edge * 8 / 1e9)) if edge else
+                  "state is L2-resident by design of the reference problem (161k nodes)"}
+
+
+def particles_reference(args, rank, world):
+    """--impl reference --workload particles: oracle/particles2d.c (the restated P4 loop body) on a bounded lattice with the same
+    particle density; one thread for the particle loops, OpenMP for the node sweeps"""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    threads = orc.set_threads(0)
+    edge = args.size
+    total = (edge, edge * world) if edge else (201, 801)
+    nx, ny = (601, 1201) if edge else (201, 801)
+    xs, ys = particle_raster(nx, ny)
+    if not edge:
+        xs, ys = xs[:64], ys[:64]
+    wd = orc.ParticleWorld(xs, ys, nprocs=1, total_nx=nx, total_ny=ny)
+    wd.initial(); wd.step(max(1, args.warmup))
+    t0 = time.perf_counter(); wd.step(args.steps); dt = time.perf_counter() - t0
+    wd.close()
+    v = nx * ny * args.steps / dt / 1e6
+    npart = len(particle_raster(*total)[0]) if edge else 64
+    sample = f"{nx}x{ny} nodes, {len(xs)} particles (same density), {args.steps} steps in {dt:.1f} s, oracle/particles2d.c on {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "MLUPS", "value": round(v, 2), "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": particles_config(edge, world, total, npart),
+        "cpu_baseline": {"value": round(v, 2), "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 2), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def particles(args, rank, local_rank, world):
-    """bench.py --workload particles: the reference's shipped particle problem (201 x 801 nodes, 64 particles, D2Q9;
-    BASELINE.json config 5 in the reference's own 2-D form).  The whole state is L2-resident (1.4 MB per population
-    set), so a step is bounded by kernel-launch latency, not HBM: the line reports MLUPS and microseconds per step."""
+    """bench.py --workload particles: BASELINE.json config 5 in the reference's own 2-D form (P4/main.F90:35-73).
+    --size 0 (one GPU): the shipped problem, 201 x 801 nodes and 64 particles -- L2-resident, bounded by launch latency.
+    --size E: an E x E block per GPU (default 8192: 67 M nodes, 26 732 particles per GPU on the reference's raster), blocks
+    stacked along y (1 x N, what MPI_Dims_create_2d picks for this shape), particles crossing the block boundaries, halos and
+    the three per-step reductions over NCCL.  Roofline: 144 B/node of populations + 8 B of mask = 152 B/node/step."""
+    if args.impl == "reference":
+        return particles_reference(args, rank, max(world, args.gpus))
     import numpy as np
-    import torch
 
     import bench as B
     import mglc_b200 as mg
 
-    if world > 1:
-        if rank == 0:
-            print(json.dumps({"metric": "MLUPS", "value": None, "note": "particles bench runs on one GPU (161k nodes)"}))
-        return
-    torch.cuda.set_device(local_rank)
-    rng = np.random.default_rng(11)
-    xs, ys, tx, ty = [], [], 25.0, 25.0
-    for _ in range(64):
-        xs.append(tx + (rng.random() - 0.5) * 20); ys.append(ty + (rng.random() - 0.5) * 20)
-        tx += 50.0
-        if tx > 200.0:
-            tx, ty = 25.0, ty + 50.0
-    sim = mg.ParticleChannel(xs, ys, device=local_rank)
+    D = B.Dist(rank, local_rank, world)
+    comm = D.communicator(mg)
+    edge = args.size if (args.size or world == 1) else 8192
+    parity = None
+    if world > 1 and not args.no_parity:
+        sys.path.insert(0, os.path.join(B.ROOT, "tests", "dist"))
+        import parity_suite as ps
+        parity = ps.particles(comm, rank, world)
+        if D.max(1.0 if (rank == 0 and ps.failed(parity)) else 0.0) > 0:
+            if rank == 0:
+                print(json.dumps({"metric": "MLUPS", "value": None, "n_gpus": world, "parity": parity,
+                                  "error": "decomposed run does not match the oracle; nothing was timed"}), flush=True)
+            comm.close(); D.close()
+            sys.exit(3)
+    if edge:
+        total = (edge, edge * world)
+        xs, ys = particle_raster(*total)
+    else:
+        total = (201, 801)
+        xs, ys = particle_raster(*total)
+        xs, ys = xs[:64], ys[:64]
+    kw = dict(total_nx=total[0], total_ny=total[1])
+    sim = mg.ParticleChannel(xs, ys, comm=comm, dims=(1, world), **kw) if comm else mg.ParticleChannel(xs, ys, device=local_rank, **kw)
     sim.initial()
-    steps = max(args.steps, 200)
+    steps = args.steps if edge else max(args.steps, 200)
     sim.step(max(args.warmup, 3)); sim.sync()
     l0 = sim.launch_count()
-    sampler = B.ClockSampler(local_rank); sampler.start()
-    ms = sim.step_timed(steps)
-    clocks = sampler.stop()
+    sampler = B.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    D.barrier()
+    ms = D.max(sim.step_timed(steps))
+    D.barrier()
+    clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - l0
-    cells = 201 * 801
-    cpu = None
-    if not args.no_cpu:
-        from oracle import oracle as orc
-        wd = orc.ParticleWorld(xs, ys, nprocs=1)
-        wd.initial(); wd.step(2)
-        t0 = time.perf_counter(); wd.step(40); dt = time.perf_counter() - t0
-        cpu = {"value": round(cells * 40 / dt / 1e6, 2), "unit": "MLUPS", "cores": 1, "kind": "port",
-               "sample": f"201x801, 64 particles, 40 steps ({dt:.1f} s), oracle/particles2d.c"}
-        wd.close()
-    flags = sim.error_flags()
+    cells = total[0] * total[1]
+    cells_local = int(np.prod(sim.info[0]["n"]))
+    flags = int(D.max(float(sim.error_flags())))
+    # end to end: the host arrays of a restart (f, f_post, rho, u, v, obst) in, K steps, fields and particle state out
+    e2e = None
+    if not args.no_e2e and edge:
+        st = sim.download(0)
+        D.barrier()
+        t0 = time.perf_counter()
+        sim.upload(0, **st)
+        sim.step(steps)
+        out = sim.download(0, ("rho", "u", "v"))
+        pstate = sim.particles()
+        D.barrier()
+        dt = D.max(time.perf_counter() - t0)
+        up = sum(a.nbytes for a in st.values()); down = sum(a.nbytes for a in out.values()) + 8 * 8 * len(xs)
+        e2e = {"value": round(cells * steps / dt / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": int(up * world / steps),
+               "d2h_bytes_per_step": int(down * world / steps), "seconds": round(dt, 3), "mean_yCenter": float(pstate["yCenter"].mean()),
+               "region": f"upload f,f_post,rho,u,v,obst (pageable host) + {steps} steps + download rho,u,v + particle state"}
+    p = sim.particles()
     sim.close()
-    print(json.dumps({
-        "metric": "MLUPS", "value": round(cells * steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": "micro_particles_d2q9_201x801_64_particles", "error_flags": flags,
-                                                         "l2": "state is L2-resident by design of the reference problem (161k nodes)"},
-        "roofline": {"bound": "launch latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
-                     "launches_per_step": round(launches / steps, 2), "us_per_step": round(ms / steps * 1e3, 2)},
-        "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+    peak, peak_src = B.hbm_peak()
+    achieved = 152.0 * cells_local * steps / (ms * 1e-3) / 1e9
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        threads = orc.set_threads(0)
+        cn = (601, 1201) if edge else (201, 801)
+        cx, cy = particle_raster(*cn)
+        if not edge:
+            cx, cy = cx[:64], cy[:64]
+        wd = orc.ParticleWorld(cx, cy, nprocs=1, total_nx=cn[0], total_ny=cn[1])
+        wd.initial(); wd.step(2)
+        t0 = time.perf_counter(); wd.step(20); dt = time.perf_counter() - t0
+        cpu = {"value": round(cn[0] * cn[1] * 20 / dt / 1e6, 2), "unit": "MLUPS", "cores": threads, "kind": "port",
+               "sample": f"{cn[0]}x{cn[1]} nodes, {len(cx)} particles (same density), 20 steps ({dt:.1f} s), oracle/particles2d.c"}
+        wd.close()
+    if rank == 0:
+        out = {
+            "metric": "MLUPS", "value": round(cells * steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": particles_config(edge, world, total, len(xs)),
+            "detail": {"error_flags": flags, "launches_per_step": round(launches / steps, 2), "mean_settling_velocity": float(p["Vc"].mean()),
+                       "collectives_per_step": 0 if world == 1 else 3,
+                       "collectives": "rhoAvg sums (2 doubles) -> link force sums (3 x N doubles) -> rhoAvg sums (2 doubles): each needs the previous one's result"},
+            "roofline": ({"bound": "hbm", "kernel": "k_p_collision_sum + k_p_update + k_p_links + k_p_mask_sum + k_p_refill", "achieved": round(achieved, 1),
+                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 152,
+                          "cells_per_launch": cells_local, "note": "whole step timed; the reference's two persistent lattices f and f_post are each read and written once per step by two node sweeps"}
+                         if edge else
+                         {"bound": "launch latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                          "launches_per_step": round(launches / steps, 2), "us_per_step": round(ms / steps * 1e3, 2)}),
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches)}
+        if parity is not None:
+            out["parity"] = parity
+        print(json.dumps(out), flush=True)
+    if comm:
+        comm.close()
+    D.close()
 
 
 def lid2d(args, rank, local_rank, world):

@@ -43,7 +43,8 @@ struct JacSub {
     cudaEvent_t ev_packed, ev_copied, ev_t0, ev_t1;
     Msg msgs[6];
     long long launches;
-    CUtensorMap tmap[2]; // 3-D tiled maps of A[0], A[1] (box 130 x 18 x 1 doubles) for k_jacobi3d_tma
+    CUtensorMap tmap[2]; // 3-D tiled maps of A[0], A[1] (box TSX x TSY x 1 doubles) for k_jacobi3d_tma
+    CUtensorMap *tmap_dev; // the same two maps in device memory (MGLC_JACOBI_TMAP=global)
     int tma_ok;
 };
 
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(JTX, JRY <= 4 ? 8 : 4) k_jacobi3d(Geom g, cons
 constexpr int TBX = 128, TBY = 16, TRY = 4;                 // tile, rows per consumer thread
 constexpr int TMA_CONSUMERS = TBX * (TBY / TRY);            // 512 threads = 16 warps
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;             // + the producer warp
-constexpr int TSX = TBX + 2, TSY = TBY + 2;
+// XH = x rim of a stage in cells: 2 makes the first column of every box (x index OX - 2 + 128 t) start on a 16-byte boundary
+constexpr int TMA_XH = 2;
+constexpr int TSX = TBX + 2 * TMA_XH, TSY = TBY + 2;
 constexpr int TMA_STAGE_BYTES = ((TSX * TSY * 8 + 127) / 128) * 128;
 constexpr int tma_smem(int stages) { return stages * TMA_STAGE_BYTES + 2 * stages * 8 + 128; }
 
@@ -199,9 +202,11 @@ struct TmaWalk {
 
 // TMA_STAGES = 10 with one CTA per SM (169 KB of planes in flight), or 5 with two CTAs per SM
 template <bool HAS_F, int TMA_STAGES>
-__global__ void __launch_bounds__(TMA_THREADS, TMA_STAGES > 5 ? 1 : 2) k_jacobi3d_tma(const __grid_constant__ CUtensorMap mapA, Geom g,
+__global__ void __launch_bounds__(TMA_THREADS, TMA_STAGES > 5 ? 1 : 2) k_jacobi3d_tma(const __grid_constant__ CUtensorMap mapP,
+                                                                 const CUtensorMap *__restrict__ mapG, Geom g,
                                                                  const double *__restrict__ f, double *__restrict__ B,
                                                                  int k_lo, int k_hi, int slab) {
+    const CUtensorMap *map = mapG ? mapG : &mapP;              // descriptor in global memory, or the kernel parameter
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *base = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint64_t *full = (uint64_t *)(base + TMA_STAGES * TMA_STAGE_BYTES), *empty = full + TMA_STAGES;
@@ -220,12 +225,12 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_STAGES > 5 ? 1 : 2) k_jacobi3
         // ---- producer: one thread streams planes ka-1 .. kb+1 of every segment into the ring
         if (threadIdx.x == TMA_CONSUMERS) {
             while (wk.next(t, ka, kb)) {
-                const int x0 = (t % tiles_x) * TBX + OX - 1, y0 = (t / tiles_x) * TBY;      // halo cell (i0-1, j0-1)
+                const int x0 = (t % tiles_x) * TBX + OX - TMA_XH, y0 = (t / tiles_x) * TBY;      // cell (i0 - XH, j0 - 1)
                 for (int k = ka - 1; k <= kb + 1; ++k, ++n) {
                     const unsigned st = n % TMA_STAGES, ph = (n / TMA_STAGES) & 1u;
                     mbar_wait(empty + st, ph ^ 1u);
                     mbar_expect_tx(full + st, TSX * TSY * 8);
-                    tma_load_plane(base + st * TMA_STAGE_BYTES, &mapA, full + st, x0, y0, k);
+                    tma_load_plane(base + st * TMA_STAGE_BYTES, map, full + st, x0, y0, k);
                 }
             }
         }
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_STAGES > 5 ? 1 : 2) k_jacobi3
     }
     // ---- consumers: thread = one x column, TRY consecutive rows
     const int lx = threadIdx.x % TBX, rg = threadIdx.x / TBX;
-    const int so = (rg * TRY + 1) * TSX + lx + 1;              // my first cell inside a stage
+    const int so = (rg * TRY + 1) * TSX + lx + TMA_XH;         // my first cell inside a stage
     const bool lane0 = (threadIdx.x & 31) == 0;
     while (wk.next(t, ka, kb)) {
         const int i = 1 + (t % tiles_x) * TBX + lx, j0 = 1 + (t / tiles_x) * TBY + rg * TRY;
@@ -388,29 +393,37 @@ static void jac_make_tmaps(JacSub *S) {
     const cuuint64_t dims[3] = {(cuuint64_t)S->g.px, (cuuint64_t)S->g.py, (cuuint64_t)S->g.pz};
     const cuuint64_t strides[2] = {(cuuint64_t)S->g.sy * 8, (cuuint64_t)S->g.sz * 8};
     const cuuint32_t box[3] = {TSX, TSY, 1}, estr[3] = {1, 1, 1};
+    // no L2 promotion: with 256-byte promotion the rows of a box (1056 B, starting 112 B into a line) pull in more DRAM sectors
+    // than the SMs ever request (ncu, 512^3: 1.44 GB read from DRAM for 1.37 GB delivered; profiles/r2c_*)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (const char *e = getenv("MGLC_JACOBI_TMA_L2PROMO")) {
+        const int v = atoi(e);
+        promo = v >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : v >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : promo;
+    }
     for (int b = 0; b < 2; ++b)
         if (enc(&S->tmap[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, S->A[b], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
     if (cudaFuncSetAttribute(k_jacobi3d_tma<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(10)) != cudaSuccess ||
         cudaFuncSetAttribute(k_jacobi3d_tma<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(10)) != cudaSuccess ||
         cudaFuncSetAttribute(k_jacobi3d_tma<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(5)) != cudaSuccess ||
         cudaFuncSetAttribute(k_jacobi3d_tma<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem(5)) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    if (cudaMalloc((void **)&S->tmap_dev, 2 * sizeof(CUtensorMap)) != cudaSuccess ||
+        cudaMemcpy(S->tmap_dev, S->tmap, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) { (void)cudaGetLastError(); return; }
     S->tma_ok = 1;
 }
 static int jacobi_tma_ctas() {            // CTAs per SM of the TMA pipeline: 1 (10 stages) or 2 (5 stages each)
-    static int v = 0;
-    if (!v) { v = 1; if (const char *e = getenv("MGLC_JACOBI_TMA_CTAS")) v = atoi(e) == 2 ? 2 : 1; }
-    return v;
+    const char *e = getenv("MGLC_JACOBI_TMA_CTAS");
+    return e && atoi(e) == 2 ? 2 : 1;
 }
 // MGLC_JACOBI_KERNEL=reg keeps the register-blocked LDG kernel (k_jacobi3d); default: the TMA pipeline
+// (the three switches are read at every sweep, so a test or a tuning sweep can flip them inside one process)
 static bool jacobi_use_tma() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("MGLC_JACOBI_KERNEL"); v = !(e && !strcmp(e, "reg")); }
-    return v != 0;
+    const char *e = getenv("MGLC_JACOBI_KERNEL");
+    return !(e && !strcmp(e, "reg"));
 }
 static int jacobi_slab(int nz) {
-    static int v = 0;
-    if (!v) { v = 64; if (const char *e = getenv("MGLC_JACOBI_SLAB")) v = std::max(1, atoi(e)); }
+    int v = 64;
+    if (const char *e = getenv("MGLC_JACOBI_SLAB")) v = std::max(1, atoi(e));
     return std::min(v, nz);
 }
 static int sm_count(int device) {
@@ -426,6 +439,7 @@ static void jac_free_sub(JacSub *S) {
     if (S->s) cudaStreamSynchronize(S->s);
     double *bufs[] = {S->A[0], S->A[1], S->f, S->A_p, S->scratch};
     for (double *p : bufs) cudaFree(p);
+    cudaFree(S->tmap_dev);
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
     cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -682,7 +696,9 @@ static int jac_sweep(mglc_jacobi *h) {
             const int slab = jacobi_slab(S->n[2]);
             const int per_sm = jacobi_tma_ctas();
             const int grid = (int)std::min<long long>((long long)sm_count(S->device) * per_sm, (long long)tiles * slab);
-#define MGLC_JAC_TMA(HASF, NST, FPTR) k_jacobi3d_tma<HASF, NST><<<grid, TMA_THREADS, tma_smem(NST), S->s>>>(S->tmap[S->cur], S->g, FPTR, B, 1, S->n[2], slab)
+            const char *where = getenv("MGLC_JACOBI_TMAP");
+            const CUtensorMap *gmap = (where && !strcmp(where, "global")) ? S->tmap_dev + S->cur : nullptr;
+#define MGLC_JAC_TMA(HASF, NST, FPTR) k_jacobi3d_tma<HASF, NST><<<grid, TMA_THREADS, tma_smem(NST), S->s>>>(S->tmap[S->cur], gmap, S->g, FPTR, B, 1, S->n[2], slab)
             if (per_sm == 2) { if (S->f) MGLC_JAC_TMA(true, 5, S->f); else MGLC_JAC_TMA(false, 5, nullptr); }
             else { if (S->f) MGLC_JAC_TMA(true, 10, S->f); else MGLC_JAC_TMA(false, 10, nullptr); }
 #undef MGLC_JAC_TMA

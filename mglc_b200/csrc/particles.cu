@@ -53,11 +53,78 @@ enum { PX_ = 0, PY_, PU_, PV_, POM_, PRAD_, PINERTIA_, PXO_, PYO_, PUO_, PVO_, P
 // PFX/PFY/PTQ = wallTotalForceX/Y, totalTorque; PSX/PSY/PST = this rank's link sums before the Allreduce
 
 enum { ST_STREAM = 1, ST_WALLBB = 2, ST_PBB = 4, ST_MACRO = 8, ST_FORCE = 16, ST_COUNT = 32 };
-enum { ERR_CALQ = 1, ERR_Q = 2, ERR_OWNER = 4, ERR_INTERPENETRATION = 8, ERR_WALL = 16, ERR_REFILL = 32 };
+enum { ERR_CALQ = 1, ERR_Q = 2, ERR_OWNER = 4, ERR_INTERPENETRATION = 8, ERR_WALL = 16, ERR_REFILL = 32, ERR_BINS = 64 };
 
 __device__ __forceinline__ bool inside(const G2 &g, int i, int j, double xc, double yc, double rad) {
     const double dx = (double)(i + g.i_start) - xc, dy = (double)(j + g.j_start) - yc;
     return (dx * dx + dy * dy) <= rad * rad;
+}
+
+// ---- particle bins ----------------------------------------------------------------------------------------------
+// The reference finds "the particle that covers this node" and "the particles close to this particle" by looping over all
+// cNumMax = 64 of them (P4/particle_update.F90:84-100, P4/particle_force.F90:100-130).  That loop is kept for small counts;
+// beyond PB_MIN_PARTICLES the same questions are answered from a uniform grid of bins over the GLOBAL lattice: bin (bx, by)
+// lists the particles whose centre lies in [bx*B, (bx+1)*B) x [by*B, (by+1)*B), with B >= 2*rmax + thresholdParticle (so every
+// spring partner of a particle sits in the 3 x 3 bins around its own) and B >= rmax + 2 (so the particle covering a node, by its
+// old or its new centre, sits in the 3 x 3 bins around the node's).  The answers do not depend on the order inside a bin:
+// mask tests are an OR, and the spring sums and the refill run over the candidates in ascending particle index -- the
+// reference's loop order -- so results stay bit-identical to the full loop.
+constexpr int PB_CAP = 8;              // centres per bin: non-overlapping discs with 2*r + threshold <= B leave room for 5
+constexpr int PB_MIN_PARTICLES = 257;  // below this the full loops run (MGLC_P2D_BINS=1 forces the bins: tests)
+struct PB {
+    int B, nbx, nby;                   // B == 0: no bins (small particle counts)
+    double rmax;
+    int *cnt, *list;
+    __device__ int bin(int bx, int by) const { return by * nbx + bx; }
+    __device__ int bx_of(double x) const { return min(nbx - 1, max(0, (int)floor(x / (double)B))); }
+    __device__ int by_of(double y) const { return min(nby - 1, max(0, (int)floor(y / (double)B))); }
+};
+__global__ void k_p_bins_fill(PB b, P2 p, const double *__restrict__ ps, int *__restrict__ err) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.N) return;
+    const int q = b.bin(b.bx_of(ps[PX_ * p.N + c]), b.by_of(ps[PY_ * p.N + c]));
+    const int slot = atomicAdd(&b.cnt[q], 1);
+    if (slot < PB_CAP) b.list[q * PB_CAP + slot] = c;
+    else atomicOr(err, ERR_BINS);
+}
+// The particles that can cover a node of the row segment gi_lo..gi_hi of global row gj (old or new centre: one node of
+// slack), collected by the whole block into list[0..*nlist) (shared memory, room for 128).  All threads must call.
+__device__ void block_candidates(const PB &b, int gi_lo, int gi_hi, int gj, int *list, int *nlist) {
+    if (threadIdx.x == 0) *nlist = 0;
+    __syncthreads();
+    const double reach = b.rmax + 2.0;
+    const int bx0 = b.bx_of((double)gi_lo - reach), bx1 = b.bx_of((double)gi_hi + reach);
+    const int by0 = b.by_of((double)gj - reach), by1 = b.by_of((double)gj + reach);
+    const int w = bx1 - bx0 + 1, nb = w * (by1 - by0 + 1);
+    for (int q = threadIdx.x; q < nb * PB_CAP; q += blockDim.x) {
+        const int bi = b.bin(bx0 + (q / PB_CAP) % w, by0 + (q / PB_CAP) / w), slot = q % PB_CAP;
+        if (slot < min(b.cnt[bi], PB_CAP)) {
+            const int pos = atomicAdd(nlist, 1);
+            if (pos < 128) list[pos] = b.list[bi * PB_CAP + slot];
+        }
+    }
+    __syncthreads();
+}
+// is global node (gi, gj) inside a particle?  list/nlist from block_candidates (nlist > 128: scan the bins instead)
+__device__ __forceinline__ int covered(const PB &b, const G2 &g, int N, const double *__restrict__ ps, int i, int j, const int *list, int nlist) {
+    int solid = 0;
+    if (nlist <= 128) {
+        for (int q = 0; q < nlist; ++q) {
+            const int c = list[q];
+            if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+        }
+    } else {
+        const int bx = b.bx_of((double)(i + g.i_start)), by = b.by_of((double)(j + g.j_start));
+        for (int yy = max(0, by - 1); yy <= min(b.nby - 1, by + 1); ++yy)
+            for (int xx = max(0, bx - 1); xx <= min(b.nbx - 1, bx + 1); ++xx) {
+                const int bi = b.bin(xx, yy);
+                for (int q = 0; q < min(b.cnt[bi], PB_CAP); ++q) {
+                    const int c = b.list[bi * PB_CAP + q];
+                    if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+                }
+            }
+    }
+    return solid;
 }
 
 #include "p2d_calq.inl"
@@ -100,15 +167,21 @@ __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, d
 }
 
 // ---- initial(), P4/initial.F90:79-199 (positions come from the caller) -----------------------------------------
-__global__ void k_p_initial(G2 g, P2 p, const double *__restrict__ ps, double *__restrict__ F, double *__restrict__ Fp,
+__global__ void __launch_bounds__(128) k_p_initial(G2 g, P2 p, PB b, const double *__restrict__ ps, double *__restrict__ F, double *__restrict__ Fp,
                             int *__restrict__ obst, int *__restrict__ obstNew, double *__restrict__ rho, double *__restrict__ u,
                             double *__restrict__ v, double *__restrict__ up, double *__restrict__ vp) {
+    __shared__ int list[128];
+    __shared__ int nlist;
     const int i = -2 + (int)(blockIdx.x * blockDim.x + threadIdx.x), j = -2 + (int)blockIdx.y;
+    if (b.B) block_candidates(b, -2 + (int)(blockIdx.x * blockDim.x) + g.i_start, -2 + (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + g.i_start,
+                              j + g.j_start, list, &nlist);
     if (i > g.nx + 3) return;
     const bool interior = i >= 1 && i <= g.nx && j >= 1 && j <= g.ny;
     const bool ring12 = !interior && i >= -1 && i <= g.nx + 2 && j >= -1 && j <= g.ny + 2;
     int solid = 0;
     if (i >= 0 && i <= g.nx + 1 && j >= 0 && j <= g.ny + 1) {
+        if (b.B) solid = covered(b, g, p.N, ps, i, j, list, nlist);
+        else
         for (int c = 0; c < p.N; ++c)
             if (inside(g, i, j, ps[PX_ * p.N + c], ps[PY_ * p.N + c], ps[PRAD_ * p.N + c])) solid = 1;
     }
@@ -426,6 +499,10 @@ __global__ void __launch_bounds__(LK_T) k_p_links(G2 g, P2 p, const double *__re
     const int lj0 = max(1, (int)floor(yc - rad) - 1 - g.j_start), lj1 = min(g.ny, (int)ceil(yc + rad) + 1 - g.j_start);
     const int bw = li1 - li0 + 1, bh = lj1 - lj0 + 1;
     const int nnodes = (bw > 0 && bh > 0) ? bw * bh : 0;
+    if (nnodes == 0) {                   // the particle does not reach this subdomain (most of them, on a decomposed lattice)
+        if (t == 0) { ps_sum[PSX_ * N + cn] = 0.0; ps_sum[PSY_ * N + cn] = 0.0; ps_sum[PST_ * N + cn] = 0.0; }
+        return;
+    }
     double lfx = 0.0, lfy = 0.0, ltq = 0.0;
     // one link: bisection, bounce-back, momentum exchange, and macro() when it was the node's last
     auto do_link = [&](int e) {
@@ -569,6 +646,59 @@ __global__ void k_p_particles(P2 p, double *ps, const double *__restrict__ rhoAv
     }
 }
 
+// PT_FORCES for any number of particles: one thread per particle, spring partners from the 3 x 3 bins around its own (every
+// particle within 2*rmax + thresholdParticle lies there).  The contributing partners (a handful) are added in ascending
+// index, which is the reference's loop order, so the sums round exactly like the full loop of k_p_particles.
+__global__ void __launch_bounds__(64) k_p_forces_binned(PB b, P2 p, double *ps, const double *__restrict__ rhoAvgPart, int *__restrict__ err) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, N = p.N;
+    if (c >= N) return;
+    const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
+    const double rad = ps[PRAD_ * N + c], xc = ps[PX_ * N + c], yc = ps[PY_ * N + c];
+    double forceScale = p.Pi * (rad * rad) * (p.rhoSolid - rhoAvg) * p.gravity / p.stiffParticle;
+    constexpr int MAXP = 12;
+    int pid[MAXP];
+    double ptx[MAXP], pty[MAXP];
+    int np_ = 0;
+    const int bx = b.bx_of(xc), by = b.by_of(yc);
+    for (int yy = max(0, by - 1); yy <= min(b.nby - 1, by + 1); ++yy)
+        for (int xx = max(0, bx - 1); xx <= min(b.nbx - 1, bx + 1); ++xx) {
+            const int bi = b.bin(xx, yy);
+            for (int q = 0; q < min(b.cnt[bi], PB_CAP); ++q) {
+                const int c2 = b.list[bi * PB_CAP + q];
+                if (c2 == c) continue;
+                const double x2 = ps[PX_ * N + c2], y2 = ps[PY_ * N + c2], r2 = ps[PRAD_ * N + c2];
+                const double dij = sqrt((xc - x2) * (xc - x2) + (yc - y2) * (yc - y2));
+                if (dij >= (rad + r2 + p.thresholdParticle)) {
+                } else if (dij >= (rad + r2)) {
+                    const double t = (dij - rad - r2 - p.thresholdParticle) / p.thresholdParticle;
+                    if (np_ < MAXP) { pid[np_] = c2; ptx[np_] = forceScale * (t * t) * (xc - x2) / dij; pty[np_] = forceScale * (t * t) * (yc - y2) / dij; ++np_; }
+                    else atomicOr(err, ERR_BINS);
+                } else atomicOr(err, ERR_INTERPENETRATION);
+            }
+        }
+    double Fxij = 0.0, Fyij = 0.0;
+    for (int prev = -1, k = 0; k < np_; ++k) {          // ascending partner index
+        int best = -1;
+        for (int q = 0; q < np_; ++q) if (pid[q] > prev && (best < 0 || pid[q] < pid[best])) best = q;
+        Fxij = Fxij + ptx[best]; Fyij = Fyij + pty[best];
+        prev = pid[best];
+    }
+    double Fwx = 0.0, Fwy = 0.0;
+    forceScale = p.Pi * (rad * rad) * (p.rhoSolid - p.rho0) * p.gravity / p.stiffWall;
+    double dw = yc - rad - 1.0;
+    if (dw < 0) atomicOr(err, ERR_WALL);
+    else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwy = Fwy + forceScale * (t * t); }
+    dw = xc - rad - 1.0;
+    if (dw < 0) atomicOr(err, ERR_WALL);
+    else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwx = Fwx + forceScale * (t * t); }
+    dw = (double)p.total_nx - xc - rad;
+    if (dw < 0) atomicOr(err, ERR_WALL);
+    else if (dw < p.thresholdWall) { const double t = (dw - p.thresholdWall) / p.thresholdWall; Fwx = Fwx - forceScale * (t * t); }
+    ps[PFX_ * N + c] = ps[PSX_ * N + c] + Fxij + Fwx;
+    ps[PFY_ * N + c] = ps[PSY_ * N + c] - (p.rhoSolid - rhoAvg) * p.Pi * (p.radius0 * p.radius0) * p.gravity + Fyij + Fwy;
+    ps[PTQ_ * N + c] = ps[PST_ * N + c];
+}
+
 // Fused-step form of the two passes above for one block: a warp per particle evaluates the pair terms of the spring
 // force 32 at a time and adds them in ascending order of the partner index (the reference's loop order, so the sums
 // round identically); after a barrier the kinematics run one particle per thread.
@@ -637,11 +767,17 @@ __global__ void __launch_bounds__(1024) k_p_particles_block(P2 p, double *ps, co
 
 // updateCenter, P4/particle_update.F90:80-103: rebuild the mask from the new centres (rim included), reset the
 // macroscopic fields of solid nodes
-__global__ void __launch_bounds__(128) k_p_mask(G2 g, P2 p, const double *__restrict__ ps, int *__restrict__ obstNew,
+__global__ void __launch_bounds__(128) k_p_mask(G2 g, P2 p, PB b, const double *__restrict__ ps, int *__restrict__ obstNew,
                                                 double *__restrict__ rho, double *__restrict__ u, double *__restrict__ v) {
+    __shared__ int list[128];
+    __shared__ int nlist;
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), j = (int)blockIdx.y;
+    if (b.B) block_candidates(b, (int)(blockIdx.x * blockDim.x) + g.i_start, (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + g.i_start,
+                              j + g.j_start, list, &nlist);
     if (i > g.nx + 1) return;
     int solid = 0;
+    if (b.B) solid = covered(b, g, p.N, ps, i, j, list, nlist);
+    else
     for (int c = 0; c < p.N; ++c)
         if (inside(g, i, j, ps[PX_ * p.N + c], ps[PY_ * p.N + c], ps[PRAD_ * p.N + c])) solid = 1;
     obstNew[g.idx(0, i, j)] = solid;
@@ -656,7 +792,7 @@ __global__ void __launch_bounds__(128) k_p_mask(G2 g, P2 p, const double *__rest
 // (P4/particle_update.F90:105-120: rho over the nodes that are fluid in obstNew, after the reset above), (b) the check that
 // k_p_links consumed every link the node kernel counted (a link into a solid node no particle owns: ERR_OWNER).
 // A block first collects the particles whose extent reaches its row segment, then tests its nodes against those only.
-__global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, const double *__restrict__ ps, const int *__restrict__ obst,
+__global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, PB b, const double *__restrict__ ps, const int *__restrict__ obst,
                                                     int *__restrict__ obstNew, double *__restrict__ rho, double *__restrict__ u,
                                                     double *__restrict__ v, const int *__restrict__ nlinks, int *__restrict__ err,
                                                     double *__restrict__ partials, unsigned *__restrict__ ticket,
@@ -668,6 +804,8 @@ __global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, const double *__
     __syncthreads();
     const double gj = (double)(j + g.j_start), gi_lo = (double)((int)(blockIdx.x * blockDim.x) + g.i_start),
                  gi_hi = gi_lo + (double)(blockDim.x - 1);
+    if (b.B) block_candidates(b, (int)gi_lo, (int)gi_hi, j + g.j_start, list, &nlist);
+    else
     for (int c = threadIdx.x; c < N; c += blockDim.x) {
         const double xc = ps[PX_ * N + c], yc = ps[PY_ * N + c], rad = ps[PRAD_ * N + c];
         // conservative: one node of slack on every side of the particle's bounding box
@@ -680,7 +818,8 @@ __global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, const double *__
     double sr = 0.0, sc = 0.0;
     if (i <= g.nx + 1) {
         int solid = 0;
-        if (nlist <= 128) {
+        if (b.B) solid = covered(b, g, N, ps, i, j, list, nlist);
+        else if (nlist <= 128) {
             for (int q = 0; q < nlist; ++q) {
                 const int c = list[q];
                 if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
@@ -702,7 +841,7 @@ __global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, const double *__
 
 // updateCenter, P4/particle_update.F90:122-203: a solid node that became fluid is refilled by 3-point extrapolation
 // along the lattice direction closest to the outward normal, its momentum moments reset to the wall velocity
-__global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, const double *__restrict__ ps, const int *__restrict__ obst,
+__global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, PB b, const double *__restrict__ ps, const int *__restrict__ obst,
                                                   const int *__restrict__ obstNew, double *__restrict__ F, double *__restrict__ rho,
                                                   double *__restrict__ u, double *__restrict__ v, const double *__restrict__ rhoAvgPart,
                                                   int *__restrict__ err) {
@@ -713,8 +852,8 @@ __global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, const double *__re
     const int N = p.N;
     const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
     int found = 0;
-    for (int cn = 0; cn < N; ++cn) {
-        if (!inside(g, i, j, ps[PXO_ * N + cn], ps[PYO_ * N + cn], ps[PRAD_ * N + cn])) continue;
+    // the refill from particle cn (whose OLD extent covered the node), P4/particle_update.F90:130-200
+    auto refill_from = [&](int cn) {
         found = 1;
         const double xc = ps[PX_ * N + cn], yc = ps[PY_ * N + cn];
         const double dx = (double)(i + g.i_start) - xc, dy = (double)(j + g.j_start) - yc;
@@ -724,7 +863,7 @@ __global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, const double *__re
             const double tempNormal = (dx * (double)c9x[a] + dy * (double)c9y[a]) / sqrt(dx * dx + dy * dy);
             if (tempNormal > outNormal) { outNormal = tempNormal; ec = a; }
         }
-        if (ec == 0) { atomicOr(err, ERR_REFILL); continue; }
+        if (ec == 0) { atomicOr(err, ERR_REFILL); return; }
         const long long s1 = c9y[ec] * (long long)g.px + c9x[ec];
         double f[9], m[9];
 #pragma unroll
@@ -755,6 +894,27 @@ __global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, const double *__re
         rho[mm] = r;
         u[mm] = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / r;
         v[mm] = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / r;
+    };
+    if (!b.B) {
+        for (int cn = 0; cn < N; ++cn)
+            if (inside(g, i, j, ps[PXO_ * N + cn], ps[PYO_ * N + cn], ps[PRAD_ * N + cn])) refill_from(cn);
+    } else {
+        // candidates from the 3 x 3 bins around the node, taken in ascending particle index (the reference's loop order)
+        const int bx = b.bx_of((double)(i + g.i_start)), by = b.by_of((double)(j + g.j_start));
+        for (int prev = -1;;) {
+            int next = N;
+            for (int yy = max(0, by - 1); yy <= min(b.nby - 1, by + 1); ++yy)
+                for (int xx = max(0, bx - 1); xx <= min(b.nbx - 1, bx + 1); ++xx) {
+                    const int bi = b.bin(xx, yy);
+                    for (int q = 0; q < min(b.cnt[bi], PB_CAP); ++q) {
+                        const int cn = b.list[bi * PB_CAP + q];
+                        if (cn > prev && cn < next && inside(g, i, j, ps[PXO_ * N + cn], ps[PYO_ * N + cn], ps[PRAD_ * N + cn])) next = cn;
+                    }
+                }
+            if (next == N) break;
+            refill_from(next);
+            prev = next;
+        }
     }
     if (!found) atomicOr(err, ERR_REFILL);
 }
@@ -826,7 +986,7 @@ struct Sub {
     int *nlinks;                     // fused step: links into solid nodes still to be bounced back, per interior node
     double *gpart;                   // fused step: per-block partial sums of grid_sum2 (2 per block)
     unsigned *ticket;                // [0] collision+sum launch, [1] mask+sum launch
-    int launches_per_step;
+    int launches_per_step, no_graph;
     int *obst0;                      // the allocation obst pointed to at create time (graph parity)
     cudaGraphExec_t gexec[2];        // one captured step per obst/obstNew parity (single-subdomain handles)
     cudaStream_t s;
@@ -834,6 +994,7 @@ struct Sub {
     Msg msgs[16];                    // 0..7 f_post (depth 2), 8..15 f (depth 3)
     int org[16][6];                  // per message: send i0,j0, recv i0,j0, ni, nj
     long long launches;
+    PB bins;                         // particle bins (B == 0: not in use)
 };
 
 }  // namespace
@@ -886,6 +1047,7 @@ static void p_free_sub(Sub *S) {
     for (double *b : bufs) cudaFree(b);
     cudaFree(S->obst); cudaFree(S->obstNew); cudaFree(S->err); cudaFree(S->istage);
     cudaFree(S->nlinks); cudaFree(S->gpart); cudaFree(S->ticket);
+    cudaFree(S->bins.cnt); cudaFree(S->bins.list);
     for (cudaGraphExec_t e : S->gexec) if (e) cudaGraphExecDestroy(e);
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
     cudaEvent_t evs[] = {S->ev_packed, S->ev_copied, S->ev_t0, S->ev_t1};
@@ -1054,13 +1216,48 @@ extern "C" int mglc_p2d_info(mglc_p2d *h, int r, int dims[2], int ln[2], int sta
     return MGLC_OK;
 }
 
+// ---- particle bins (see PB): sized from the radii whenever they are set, refilled whenever the centres move ---------------
+static int p_setup_bins(mglc_p2d *h) {
+    const int N = h->p.N;
+    const bool want = N >= PB_MIN_PARTICLES || (N > 0 && getenv("MGLC_P2D_BINS") != nullptr);
+    double rmax = 0.0;
+    for (int c = 0; c < N; ++c) rmax = std::max(rmax, h->host_ps[(size_t)PRAD_ * N + c]);
+    int B = 16;
+    while ((double)B < std::max(2.0 * rmax + h->p.thresholdParticle, rmax + 2.0)) B *= 2;
+    P_EACH(h, S) {
+        MGLC_TRY(p_use(S));
+        PB &b = S->bins;
+        const int nbx = h->p.total_nx / B + 2, nby = h->p.total_ny / B + 2;
+        if (want && b.B == B && b.nbx == nbx && b.nby == nby) { b.rmax = rmax; continue; }
+        MGLC_CUDA(cudaStreamSynchronize(S->s));
+        cudaFree(b.cnt); cudaFree(b.list);
+        b = PB{};
+        for (cudaGraphExec_t &e : S->gexec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }      // captured with the old bins
+        if (!want) continue;
+        b.B = B; b.nbx = nbx; b.nby = nby; b.rmax = rmax;
+        MGLC_CUDA(cudaMalloc((void **)&b.cnt, (size_t)nbx * nby * sizeof(int)));
+        MGLC_CUDA(cudaMalloc((void **)&b.list, (size_t)nbx * nby * PB_CAP * sizeof(int)));
+    }
+    return MGLC_OK;
+}
+static int p_fill_bins(mglc_p2d *h, Sub *S) {
+    const PB &b = S->bins;
+    if (!b.B) return MGLC_OK;
+    MGLC_CUDA(cudaMemsetAsync(b.cnt, 0, (size_t)b.nbx * b.nby * sizeof(int), S->s));
+    k_p_bins_fill<<<(h->p.N + 127) / 128, 128, 0, S->s>>>(b, h->p, S->ps, S->err);
+    S->launches += 1;
+    return MGLC_OK;
+}
+
 // ---- particle state (replicated on every subdomain, like the reference's module arrays) ------------------------------
 static int p_push_particles(mglc_p2d *h) {
     const int N = h->p.N;
     if (N == 0) return MGLC_OK;
+    MGLC_TRY(p_setup_bins(h));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
         MGLC_CUDA(cudaMemcpyAsync(S->ps, h->host_ps.data(), (size_t)PFIELDS_ * N * sizeof(double), cudaMemcpyHostToDevice, S->s));
+        MGLC_TRY(p_fill_bins(h, S));
         MGLC_CUDA(cudaStreamSynchronize(S->s));
     }
     return MGLC_OK;
@@ -1189,7 +1386,7 @@ extern "C" int mglc_p2d_initial(mglc_p2d *h) {
     MGLC_TRY(p_push_particles(h));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_initial<<<dim3((S->nx + 6 + 127) / 128, S->ny + 6), 128, 0, S->s>>>(S->g, h->p, S->ps, S->F, S->Fp, S->obst, S->obstNew, S->rho,
+        k_p_initial<<<dim3((S->nx + 6 + 127) / 128, S->ny + 6), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->F, S->Fp, S->obst, S->obstNew, S->rho,
                                                                               S->u, S->v, S->up, S->vp);
         MGLC_CUDA(cudaMemsetAsync(S->err, 0, sizeof(int), S->s));
         S->launches += 1;
@@ -1339,9 +1536,11 @@ static int p_force_tail(mglc_p2d *h, int what) {
         // two launches when both are asked for: the force pass reads every particle's position, the advance pass moves them
         for (int pass : {PT_FORCES, PT_ADVANCE}) {
             if (!(what & pass)) continue;
-            k_p_particles<<<(N + 63) / 64, 64, 0, S->s>>>(h->p, S->ps, S->part, pass, S->err);
+            if (pass == PT_FORCES && S->bins.B) k_p_forces_binned<<<(N + 63) / 64, 64, 0, S->s>>>(S->bins, h->p, S->ps, S->part, S->err);
+            else k_p_particles<<<(N + 63) / 64, 64, 0, S->s>>>(h->p, S->ps, S->part, pass, S->err);
             S->launches += 1;
         }
+        if (what & PT_ADVANCE) MGLC_TRY(p_fill_bins(h, S));      // the centres moved
     }
     return MGLC_OK;
 }
@@ -1354,13 +1553,13 @@ extern "C" int mglc_p2d_calforce(mglc_p2d *h) {
 static int p_mask_refill(mglc_p2d *h) {
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_mask<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obstNew, S->rho, S->u, S->v);
+        k_p_mask<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obstNew, S->rho, S->u, S->v);
         S->launches += 1;
     }
     MGLC_TRY(p_fluid_average(h, true));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
+        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
         S->launches += 1;
         std::swap(S->obst, S->obstNew);      // obst = obstNew, P4/particle_update.F90:206 (obstNew is rebuilt from scratch next time)
     }
@@ -1440,7 +1639,7 @@ static int p_enqueue_step(mglc_p2d *h) {
         }
     }
     if (N) {
-        if (h->nranks > 1) MGLC_TRY(p_force_tail(h, PT_FORCES | PT_ADVANCE));      // Allreduce of the link sums + the two passes
+        if (h->nranks > 1 || h->subs[0]->bins.B) MGLC_TRY(p_force_tail(h, PT_FORCES | PT_ADVANCE));      // Allreduce of the link sums + the two passes
         else {
             Sub *S = h->subs[0];
             k_p_particles_block<<<1, std::min(1024, 32 * N), 0, S->s>>>(h->p, S->ps, S->part, S->err);
@@ -1450,14 +1649,14 @@ static int p_enqueue_step(mglc_p2d *h) {
     MGLC_TRY(p_exchange(h, 1));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_mask_sum<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obst, S->obstNew, S->rho, S->u, S->v,
+        k_p_mask_sum<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->rho, S->u, S->v,
                                                                                S->nlinks, S->err, S->gpart, S->ticket + 1, S->part);
         S->launches += 1;
     }
     MGLC_TRY(p_reduce_part(h));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
+        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
         S->launches += 1;
         std::swap(S->obst, S->obstNew);      // obst = obstNew, P4/particle_update.F90:206
     }
@@ -1482,23 +1681,34 @@ static int p_step_legacy(mglc_p2d *h) {
 static int p_step_impl(mglc_p2d *h, int nsteps) {
     if (nsteps < 0) return MGLC_E_INVALID;
     static const bool legacy = getenv("MGLC_P2D_LEGACY") != nullptr, nograph = getenv("MGLC_P2D_NOGRAPH") != nullptr;
-    const bool graph = !legacy && !nograph && h->nranks == 1 && h->subs.size() == 1;
+    // one subdomain per process: alone, or one rank of a communicator (the NCCL send/recv and all-reduces of the step are
+    // captured with the kernels; every rank replays the same sequence)
+    const bool graph = !legacy && !nograph && h->subs.size() == 1 && (h->nranks == 1 || h->comm) && !h->subs[0]->no_graph;
     for (int it = 0; it < nsteps; ++it) {
         if (legacy) { MGLC_TRY(p_step_legacy(h)); continue; }
-        if (!graph) { MGLC_TRY(p_enqueue_step(h)); continue; }
         Sub *S = h->subs[0];
+        if (!graph || S->no_graph) { MGLC_TRY(p_enqueue_step(h)); continue; }
         MGLC_TRY(p_use(S));
         const int par = S->obst == S->obst0 ? 0 : 1;
         if (!S->gexec[par]) {
             const long long l0 = S->launches;
+            int *o0 = S->obst, *o1 = S->obstNew;
             cudaGraph_t gr = nullptr;
             MGLC_CUDA(cudaStreamBeginCapture(S->s, cudaStreamCaptureModeRelaxed));
             const int rc = p_enqueue_step(h);                 // swaps obst / obstNew like an executed step
             const cudaError_t ce = cudaStreamEndCapture(S->s, &gr);
-            if (rc || ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); set_error("mglc_p2d_step: graph capture failed"); return rc ? rc : MGLC_E_CUDA; }
-            const cudaError_t ie = cudaGraphInstantiate(&S->gexec[par], gr, 0);
-            cudaGraphDestroy(gr);
-            if (ie != cudaSuccess) { S->gexec[par] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return MGLC_E_CUDA; }
+            cudaError_t ie = cudaErrorUnknown;
+            if (!rc && ce == cudaSuccess) ie = cudaGraphInstantiate(&S->gexec[par], gr, 0);
+            if (gr) cudaGraphDestroy(gr);
+            if (rc || ce != cudaSuccess || ie != cudaSuccess) {
+                // nothing ran: put the host-side state back and run this handle without graphs from now on
+                (void)cudaGetLastError();
+                S->gexec[par] = nullptr;
+                S->obst = o0; S->obstNew = o1; S->launches = l0;
+                S->no_graph = 1;
+                MGLC_TRY(p_enqueue_step(h));
+                continue;
+            }
             S->launches_per_step = (int)(S->launches - l0);
         } else {
             std::swap(S->obst, S->obstNew);

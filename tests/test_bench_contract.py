@@ -32,6 +32,28 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert j["e2e"] == {"value": j["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_uses_every_core_under_a_launcher_and_names_the_product_arms_config():
+    """torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arm must still run on all the cores it reports, and
+    its `config` must be the N-GPU product arm's (same keys: workload, global_lattice, decomposition, ...)."""
+    import bench as B
+    r = bench("--impl", "reference", "--gpus", "8", "--size", "32", "--steps", "2", "--warmup", "1",
+              env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "8", "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == j["detail"]["omp_threads"]
+    assert j["config"]["global_lattice"] == [64, 64, 64] and j["config"]["decomposition"] == "2x2x2" and j["n_gpus"] == 8
+
+    class A:
+        size, scaling, dims = 32, "weak", ""
+    dims, per_gpu, gn = B.lattice_for(A, 8)
+    assert j["config"] == B.lattice_config(A, False, dims, per_gpu, gn)
+    assert [B.dims_create(n) for n in (1, 2, 4, 8, 12, 6)] == [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 2, 2), (3, 2, 1)]
+    r = bench("--impl", "reference", "--workload", "jacobi", "--gpus", "4", "--size", "24", "--steps", "2", "--warmup", "1", env={"OMP_NUM_THREADS": "1"})
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["impl"] == "reference" and j["metric"] == "Mcells/s" and j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert j["config"]["decomposition"] == "2x2x1" and j["config"]["global_grid"] == [48, 48, 24]
+
+
 def test_reference_arm_is_silent_on_other_ranks():
     r = bench("--impl", "reference", "--gpus", "2", "--size", "32", "--steps", "2", "--warmup", "1",
               env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})

@@ -62,6 +62,22 @@ def test_sweep_bit_exact(total, with_f):
     wd.close(); sim.close()
 
 
+@pytest.mark.parametrize("kernel,ctas,slab", [("tma", 1, 64), ("tma", 2, 64), ("tma", 1, 5), ("tma", 2, 1), ("reg", 1, 64)])
+@pytest.mark.parametrize("total,with_f", [((131, 17, 9), True), ((260, 35, 70), False), ((128, 16, 3), True), ((5, 4, 3), False)])
+def test_3d_sweep_kernels_bit_exact(total, with_f, kernel, ctas, slab, monkeypatch):
+    """Both 3-D sweep kernels -- the TMA pipeline (persistent CTAs, 128 x 16 tiles, any slab height, one or two CTAs per SM) and
+    the register-blocked LDG kernel -- on blocks that do not divide into tiles: every cell, several sweeps, bit for bit."""
+    monkeypatch.setenv("MGLC_JACOBI_KERNEL", kernel)
+    monkeypatch.setenv("MGLC_JACOBI_TMA_CTAS", str(ctas))
+    monkeypatch.setenv("MGLC_JACOBI_SLAB", str(slab))
+    wd, sim = orc.JacobiWorld(total, 1), mg.Jacobi(total)
+    load_random(wd, sim, total, 5, with_f)
+    for _ in range(3):
+        wd.jacobi(); sim.jacobi()
+        assert np.array_equal(sim.download(0), wd.array(0))
+    wd.close(); sim.close()
+
+
 @pytest.mark.parametrize("total,nprocs,dims", [((37, 23), 2, None), ((37, 23), 6, None), ((37, 23), 3, (1, 3)),
                                                ((17, 13, 11), 2, None), ((17, 13, 11), 8, None),
                                                ((17, 13, 11), 12, None), ((17, 13, 11), 3, (1, 1, 3))])

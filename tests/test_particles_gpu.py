@@ -280,3 +280,67 @@ def test_shipped_configuration_64_particles():
         assert np.allclose(p[k], getattr(wd, k), rtol=1e-12, atol=1e-12), k
     assert p["yCenter"].mean() < np.mean(ys) - 0.3 and sim.launch_count() > 0        # they sediment
     wd.close(); sim.close()
+
+
+@pytest.mark.parametrize("nprocs", [1, 8])
+def test_particle_bins_give_the_same_run_as_the_full_loops(nprocs, monkeypatch):
+    """Large particle counts answer 'which particle covers this node' / 'which particles are close' from a grid of bins
+    (PB in particles.cu) instead of the reference's loops over all particles.  Forced on for the shipped 64-particle case
+    (MGLC_P2D_BINS=1), every kernel that uses them (initial, mask rebuild, refill, spring forces) must reproduce the full-loop
+    run bit for bit -- fields, mask, populations and particle state -- and both must match the oracle."""
+    xs, ys = shipped_layout(seed=3)
+    runs = []
+    for bins in (False, True):
+        if bins:
+            monkeypatch.setenv("MGLC_P2D_BINS", "1")
+        sim = mg.ParticleChannel(xs, ys, nprocs=nprocs)
+        sim.initial(); sim.step(60)
+        assert sim.error_flags() == 0
+        runs.append(sim)
+    monkeypatch.delenv("MGLC_P2D_BINS")
+    a, b = runs
+    for k in ("f", "f_post", "rho", "u", "v", "obst"):
+        assert np.array_equal(a.gather(k), b.gather(k)), k
+    pa, pb = a.particles(), b.particles()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k
+    wd = orc.ParticleWorld(xs, ys, nprocs=1)
+    wd.initial(); wd.step(60)
+    for k in ("rho", "u", "v"):
+        x, y = b.gather(k), wd.gather(k)
+        fl = velocity_floor(wd) if k != "rho" else 0.0
+        assert rel_l2(x, y, fl) <= REL_L2 and np.abs(x - y).max() <= MAX_ABS, k
+    assert np.array_equal(b.gather("obst"), wd.gather("obst"))
+    for s_ in runs:
+        s_.close()
+    wd.close()
+
+
+def test_thousands_of_particles_on_a_lattice_larger_than_l2_conserve_and_settle():
+    """Config 5 at scale (no oracle run fits: properties only): 2048 x 4096 nodes, 3 321 particles of the reference's radius on
+    its 50-node raster.  Mean fluid density stays put, no error flag is raised, the particles sediment, and two
+    subdomains reproduce one."""
+    nx, ny = 2048, 4096
+    rng = np.random.default_rng(17)
+    gx, gy = np.meshgrid(np.arange(25.0, nx - 20, 50.0), np.arange(25.0, ny - 20, 50.0), indexing="ij")
+    xs = (gx + (rng.random(gx.shape) - 0.5) * 20).ravel(); ys = (gy + (rng.random(gy.shape) - 0.5) * 20).ravel()
+    assert xs.size > 3000
+    sims = [mg.ParticleChannel(xs, ys, nprocs=n, total_nx=nx, total_ny=ny) for n in (1, 2)]
+    for sim in sims:
+        sim.initial()
+    rho0 = sims[0].gather("rho"); fluid0 = sims[0].gather("obst") == 0
+    for sim in sims:
+        sim.step(40)
+        assert sim.error_flags() == 0
+    a, b = sims
+    for k in ("rho", "u", "v"):
+        x, y = b.gather(k), a.gather(k)
+        assert rel_l2(x, y, 0.02 * np.sqrt(nx * ny) if k != "rho" else 0.0) <= REL_L2 and np.abs(x - y).max() <= MAX_ABS, k
+    assert np.array_equal(a.gather("obst"), b.gather("obst"))
+    p = a.particles()
+    assert np.median(p["Vc"]) < 0.0 and p["yCenter"].mean() < ys.mean()       # (the bottom row feels the wall spring and may rise)
+    fluid = a.gather("obst") == 0
+    m0, m1 = rho0[fluid0].sum(), a.gather("rho")[fluid].sum()
+    assert abs(m1 / fluid.sum() - m0 / fluid0.sum()) < 1e-6          # mean fluid density: refill and moving walls exchange O(1e-7)
+    for sim in sims:
+        sim.close()
