@@ -485,6 +485,7 @@ def main():
         e2e = run_e2e(args, D, sim, sub, lib, L, cells_local, cells_total, thermal)
 
     sim.close()
+    D.barrier()          # a lattice mapped by the neighbours (CUDA IPC) is only returned to the driver once they have closed it too
 
     # ---- strong scaling in the same invocation (N > 1, default weak run): the config-3 lattice split over the GPUs ----
     strong = None

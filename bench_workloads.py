@@ -86,7 +86,7 @@ def jacobi(args, rank, local_rank, world):
     value = cells_total * args.steps / (ms * 1e-3) / 1e6
     peak, peak_src = B.hbm_peak()
     achieved = 16 * cells_local * args.steps / (ms * 1e-3) / 1e9
-    kernel = "k_jacobi3d<0,4>" if os.environ.get("MGLC_JACOBI_KERNEL") == "reg" else "k_jacobi3d_tma"
+    kernel = "k_jacobi3d_tma" if os.environ.get("MGLC_JACOBI_KERNEL") == "tma" else "k_jacobi3d<0,4>"
     tr = B.ncu_traffic(kernel, cells_local)
     # end to end: host arrays in, `steps` iterations, check_diff, host array out
     e2e = None

@@ -273,6 +273,14 @@ int mglc_jacobi_step_timed(mglc_jacobi *h, int nits, float *ms);
 int mglc_jacobi_check_diff(mglc_jacobi *h, double *error_max);   /* check_diff + Allreduce(MAX)  LAP:105-107,185-204 */
 int mglc_jacobi_launch_count(mglc_jacobi *h, long long *n);
 int mglc_jacobi_sync(mglc_jacobi *h);
+/* Halo transport of mglc_jacobi_step on several subdomains.  1 (default when the neighbours' arrays could be mapped: peer
+ * pointers inside one process, CUDA IPC between processes): the sweep stores its boundary values straight into the
+ * neighbours' ghost layers of A_new -- the values exchange_message() (LAP:223-254) would bring before the next sweep -- so the
+ * transfer rides along with the sweep (the reference's own overlap of exchange and interior, jacobi2d_mpi_nonblock.f90:167-218,
+ * taken to its end).  0: exchange_message, then sweep, as LAP:94-103 is written.  After mglc_jacobi_step in mode 1 the ghost
+ * layers of A are already the neighbours' new boundary values; interior cells are identical in both modes. */
+int mglc_jacobi_set_halo(mglc_jacobi *h, int mode);
+int mglc_jacobi_direct_halo(mglc_jacobi *h, int *available);
 
 /* ================= particle-laden D2Q9 path (MPI/Micro_particles/fortran/case4/mpi_particle/, "P4") =================
  * Host arrays are the reference's (P4/freeall.F90:13-17): f(0:8,-2:nx+3,-2:ny+3), f_post(0:8,-1:nx+2,-1:ny+2),

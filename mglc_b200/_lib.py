@@ -173,6 +173,8 @@ SIGNATURES = {
     "mglc_jacobi_check_diff": (C.c_int, [_vp, _dp]),
     "mglc_jacobi_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_jacobi_sync": (C.c_int, [_vp]),
+    "mglc_jacobi_set_halo": (C.c_int, [_vp, C.c_int]),
+    "mglc_jacobi_direct_halo": (C.c_int, [_vp, _ip]),
     # particle-laden D2Q9 path
     "mglc_p2d_desc_init": (C.c_int, [C.POINTER(P2dDesc), C.c_int]),
     "mglc_p2d_dims_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip]),
@@ -276,6 +278,21 @@ SIGNATURES = {
 _lib = None
 
 
+def _preload_nccl():
+    """libmglc.so needs libnccl.so.2.  A process that imports torch afterwards needs the NCCL torch was built against (bundled
+    as nvidia/nccl/lib/libnccl.so.2, newer than the system's); the dynamic loader keeps whichever libnccl.so.2 came first, so
+    the bundled one is loaded first when it exists -- libmglc.so only uses entry points every 2.x release has."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def lib():
     """Load libmglc.so (once).  Fails loudly when the CUDA extension has not been built."""
     global _lib
@@ -284,6 +301,7 @@ def lib():
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C mglc_b200/csrc`).  mglc_b200 has no CPU/PyTorch fallback.")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch

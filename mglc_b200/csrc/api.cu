@@ -585,21 +585,23 @@ static void select_msgs(mglc_lbm *h, int which) {
     for (int m = 0; m < h->nmsgs; ++m) h->msgs[m].skip = !(((h->msgs[m].dir >= 20) ? MSG_G : MSG_F) & which);
 }
 static int do_pack(mglc_lbm *h, cudaStream_t s) {
+    MsgBatch mb{};
     for (int m = 0; m < h->nmsgs; ++m) {
         const Msg &M = h->msgs[m];
         if (!M.send_count || M.skip) continue;
-        h->launches += (M.dir >= 20) ? launch_pack_g(h->g, Gpost_(h), M.dir - 20, M.sbuf, s)
-                                     : launch_pack(h->g, Fpost_(h), M.dir, M.sbuf, s);
+        mb.dir[mb.n] = M.dir; mb.buf[mb.n] = M.sbuf; ++mb.n;
     }
+    h->launches += launch_pack_all(h->g, mb, Fpost_(h), h->thermal ? Gpost_(h) : nullptr, false, s);
     return MGLC_OK;
 }
 static int do_unpack(mglc_lbm *h, cudaStream_t s) {
+    MsgBatch mb{};
     for (int m = 0; m < h->nmsgs; ++m) {
         const Msg &M = h->msgs[m];
         if (!M.recv_count || M.skip) continue;
-        h->launches += (M.dir >= 20) ? launch_unpack_g(h->g, Gpost_(h), M.dir - 20, M.rbuf, s)
-                                     : launch_unpack(h->g, Fpost_(h), M.dir, M.rbuf, s);
+        mb.dir[mb.n] = M.dir; mb.buf[mb.n] = M.rbuf; ++mb.n;
     }
+    h->launches += launch_pack_all(h->g, mb, Fpost_(h), h->thermal ? Gpost_(h) : nullptr, true, s);
     return MGLC_OK;
 }
 // message_passing_sendrecv() for a handle that owns a communicator (one process per GPU)

@@ -169,6 +169,9 @@ int launch_th_check(const Geom &g, const double *u, const double *v, const doubl
 int launch_pack_g(const Geom &g, const double *Gpost, int face, double *buf, cudaStream_t s);
 int launch_unpack_g(const Geom &g, double *Gpost, int face, const double *buf, cudaStream_t s);
 int launch_nure(const Geom &g, const double *u, const double *v, const double *w, const double *T, double *part, cudaStream_t s);
+// one launch that packs (or unpacks) every message of an exchange: dir 0..18 = f messages, 20 + face = g messages
+struct MsgBatch { int n; int dir[24]; double *buf[24]; };
+int launch_pack_all(const Geom &g, const MsgBatch &mb, double *Fpost, double *Gpost, bool unpack, cudaStream_t s);
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
 int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s);
 int launch_halo_wait(const SyncTable &t, unsigned long long epoch, int *err, cudaStream_t s);

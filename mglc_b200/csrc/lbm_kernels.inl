@@ -73,6 +73,10 @@ __device__ __forceinline__ long long peer_cell(const PeerTable *__restrict__ pt,
     }
 #define MGLC_PEER_EDGE(A, EX, EY, EZ)                                                        \
     if (pm & (1u << (A))) pt->F[A][(A) * pt->sq[A] + peer_cell<EX, EY, EZ>(pt, A, i, j, k)] = fp[A];
+// does the CTA whose first cell is (ib, jb, k) contain a cell on a face of the subdomain?  (block-uniform)
+__device__ __forceinline__ bool peer_cta_on_face(const Geom &g, int ib, int jb, int k) {
+    return (k == 1) | (k == g.nz) | (jb == 1) | (jb + (int)blockDim.y - 1 >= g.ny) | (ib == 1) | (ib + (int)blockDim.x - 1 >= g.nx);
+}
 // the outgoing populations of a boundary cell, in the message sets of message_passing_sendrecv()
 __device__ __forceinline__ void peer_store_f(const PeerTable *__restrict__ pt, const Geom &g, int i, int j, int k,
                                              const double (&fp)[19]) {
@@ -161,7 +165,11 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     collide<BGK>(f, rho, u, v, w, p, fp);
 #pragma unroll
     for (int a = 0; a < 19; ++a) Fout[a * sq + c] = fp[a];
-    if (PEER) peer_store_f(pt, g, i, j, k, fp);
+    // Only CTAs that touch a face of the subdomain have anything to send; the test is uniform across the CTA, so the
+    // interior (all but ~1 % of the CTAs at 768^3) skips the message code in a handful of instructions (ncu, 2 GPUs:
+    // the per-thread face tests cost 5.7 % more instructions than k_fused<..., false>, profiles/r2d_*).
+    if (PEER && peer_cta_on_face(g, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k))
+        peer_store_f(pt, g, i, j, k, fp);
     // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
     // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro()); it goes to the other
     // side buffer so that the plane this launch read stays intact for canonicalise()

@@ -87,14 +87,14 @@ __global__ void k_p_bins_fill(PB b, P2 p, const double *__restrict__ ps, int *__
     if (slot < PB_CAP) b.list[q * PB_CAP + slot] = c;
     else atomicOr(err, ERR_BINS);
 }
-// The particles that can cover a node of the row segment gi_lo..gi_hi of global row gj (old or new centre: one node of
-// slack), collected by the whole block into list[0..*nlist) (shared memory, room for 128).  All threads must call.
-__device__ void block_candidates(const PB &b, int gi_lo, int gi_hi, int gj, int *list, int *nlist) {
+// The particles that can cover a node of the row segment gi_lo..gi_hi of the global rows gj_lo..gj_hi (old or new centre: one
+// node of slack), collected by the whole block into list[0..*nlist) (shared memory, room for 128).  All threads must call.
+__device__ void block_candidates(const PB &b, int gi_lo, int gi_hi, int gj_lo, int gj_hi, int *list, int *nlist) {
     if (threadIdx.x == 0) *nlist = 0;
     __syncthreads();
     const double reach = b.rmax + 2.0;
     const int bx0 = b.bx_of((double)gi_lo - reach), bx1 = b.bx_of((double)gi_hi + reach);
-    const int by0 = b.by_of((double)gj - reach), by1 = b.by_of((double)gj + reach);
+    const int by0 = b.by_of((double)gj_lo - reach), by1 = b.by_of((double)gj_hi + reach);
     const int w = bx1 - bx0 + 1, nb = w * (by1 - by0 + 1);
     for (int q = threadIdx.x; q < nb * PB_CAP; q += blockDim.x) {
         const int bi = b.bin(bx0 + (q / PB_CAP) % w, by0 + (q / PB_CAP) / w), slot = q % PB_CAP;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_p_initial(G2 g, P2 p, PB b, const doubl
     __shared__ int nlist;
     const int i = -2 + (int)(blockIdx.x * blockDim.x + threadIdx.x), j = -2 + (int)blockIdx.y;
     if (b.B) block_candidates(b, -2 + (int)(blockIdx.x * blockDim.x) + g.i_start, -2 + (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + g.i_start,
-                              j + g.j_start, list, &nlist);
+                              j + g.j_start, j + g.j_start, list, &nlist);
     if (i > g.nx + 3) return;
     const bool interior = i >= 1 && i <= g.nx && j >= 1 && j <= g.ny;
     const bool ring12 = !interior && i >= -1 && i <= g.nx + 2 && j >= -1 && j <= g.ny + 2;
@@ -248,19 +248,24 @@ __global__ void __launch_bounds__(128) k_p_collision_sum(G2 g, P2 p, const doubl
                                                          const double *__restrict__ u, const double *__restrict__ v,
                                                          const int *__restrict__ obst, double *__restrict__ Fp,
                                                          double *__restrict__ partials, unsigned *__restrict__ ticket,
-                                                         double *__restrict__ out) {
-    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+                                                         double *__restrict__ out, int *__restrict__ rcount) {
+    // a block walks rows blockIdx.y+1, +gridDim.y, ...: the number of block partials stays bounded on large lattices (the block
+    // that adds them up at the end is a serial tail), one row per block on the reference's own sizes
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (rcount && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *rcount = 0;      // the step's refill list starts empty
     double sr = 0.0, sc = 0.0;
-    if (i <= g.nx && obst[g.idx(0, i, j)] == 0) {
-        const long long c = g.idx(0, i, j), m = g.cell(i, j);
-        double f[9], fp[9];
+    for (int j = 1 + blockIdx.y; j <= g.ny; j += gridDim.y) {
+        if (i <= g.nx && obst[g.idx(0, i, j)] == 0) {
+            const long long c = g.idx(0, i, j), m = g.cell(i, j);
+            double f[9], fp[9];
 #pragma unroll
-        for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
-        const double r = rho[m];
-        d2q9_collide(f, r, u[m], v[m], p.Snu, p.Sq, fp);
+            for (int a = 0; a < 9; ++a) f[a] = F[a * g.sq + c];
+            const double r = rho[m];
+            d2q9_collide(f, r, u[m], v[m], p.Snu, p.Sq, fp);
 #pragma unroll
-        for (int a = 0; a < 9; ++a) Fp[a * g.sq + c] = fp[a];
-        sr = r; sc = 1.0;
+            for (int a = 0; a < 9; ++a) Fp[a * g.sq + c] = fp[a];
+            sr += r; sc += 1.0;
+        }
     }
     grid_sum2(sr, sc, partials, ticket, out);
 }
@@ -338,10 +343,20 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
     // streaming(), P4/fluid.F90:97-108: every interior node, skipped when the upstream node is solid
     if (in_range) {
         if (STAGES & ST_STREAM) {
+            // all nine upstream masks and populations are requested before any is used (the 3-node rim makes every address
+            // valid); a population whose upstream node is solid is then replaced by the node's old value -- rare, so that
+            // second load stays conditional
+            int ob[9];
+            double fu[9];
 #pragma unroll
             for (int a = 0; a < 9; ++a) {
                 const long long up_ = c - c9y[a] * (long long)g.px - c9x[a];
-                if (obst[up_] == 0) { f[a] = Fp[a * g.sq + up_]; F[a * g.sq + c] = f[a]; }
+                ob[a] = obst[up_];
+                fu[a] = Fp[a * g.sq + up_];
+            }
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+                if (ob[a] == 0) { f[a] = fu[a]; F[a * g.sq + c] = f[a]; }
                 else f[a] = F[a * g.sq + c];
             }
         } else {
@@ -773,7 +788,7 @@ __global__ void __launch_bounds__(128) k_p_mask(G2 g, P2 p, PB b, const double *
     __shared__ int nlist;
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), j = (int)blockIdx.y;
     if (b.B) block_candidates(b, (int)(blockIdx.x * blockDim.x) + g.i_start, (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + g.i_start,
-                              j + g.j_start, list, &nlist);
+                              j + g.j_start, j + g.j_start, list, &nlist);
     if (i > g.nx + 1) return;
     int solid = 0;
     if (b.B) solid = covered(b, g, p.N, ps, i, j, list, nlist);
@@ -796,44 +811,57 @@ __global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, PB b, const doub
                                                     int *__restrict__ obstNew, double *__restrict__ rho, double *__restrict__ u,
                                                     double *__restrict__ v, const int *__restrict__ nlinks, int *__restrict__ err,
                                                     double *__restrict__ partials, unsigned *__restrict__ ticket,
-                                                    double *__restrict__ out) {
+                                                    double *__restrict__ out, int *__restrict__ rlist, int *__restrict__ rcount, int rcap) {
     __shared__ int list[128];
     __shared__ int nlist;
-    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), j = (int)blockIdx.y, N = p.N;
-    if (threadIdx.x == 0) nlist = 0;
-    __syncthreads();
-    const double gj = (double)(j + g.j_start), gi_lo = (double)((int)(blockIdx.x * blockDim.x) + g.i_start),
-                 gi_hi = gi_lo + (double)(blockDim.x - 1);
-    if (b.B) block_candidates(b, (int)gi_lo, (int)gi_hi, j + g.j_start, list, &nlist);
-    else
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        const double xc = ps[PX_ * N + c], yc = ps[PY_ * N + c], rad = ps[PRAD_ * N + c];
-        // conservative: one node of slack on every side of the particle's bounding box
-        if (fabs(gj - yc) <= rad + 1.0 && xc + rad + 1.0 >= gi_lo && xc - rad - 1.0 <= gi_hi) {
-            const int pos = atomicAdd(&nlist, 1);
-            if (pos < 128) list[pos] = c;
-        }
-    }
-    __syncthreads();
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x), N = p.N;
+    const double gi_lo = (double)((int)(blockIdx.x * blockDim.x) + g.i_start), gi_hi = gi_lo + (double)(blockDim.x - 1);
     double sr = 0.0, sc = 0.0;
-    if (i <= g.nx + 1) {
-        int solid = 0;
-        if (b.B) solid = covered(b, g, N, ps, i, j, list, nlist);
-        else if (nlist <= 128) {
-            for (int q = 0; q < nlist; ++q) {
-                const int c = list[q];
-                if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+    // a block owns a band of consecutive rows (one row on the reference's own sizes); with bins the particles that can reach
+    // the band are collected once for all its rows
+    const int band = (g.ny + 2 + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int jb0 = (int)blockIdx.y * band, jb1 = min(g.ny + 1, jb0 + band - 1);
+    if (b.B) block_candidates(b, (int)gi_lo, (int)gi_hi, jb0 + g.j_start, jb1 + g.j_start, list, &nlist);
+    for (int j = jb0; j <= jb1; ++j) {
+        if (!b.B) {
+            __syncthreads();                                                   // the previous row's list has been read
+            if (threadIdx.x == 0) nlist = 0;
+            __syncthreads();
+            const double gj = (double)(j + g.j_start);
+            for (int c = threadIdx.x; c < N; c += blockDim.x) {
+                const double xc = ps[PX_ * N + c], yc = ps[PY_ * N + c], rad = ps[PRAD_ * N + c];
+                // conservative: one node of slack on every side of the particle's bounding box
+                if (fabs(gj - yc) <= rad + 1.0 && xc + rad + 1.0 >= gi_lo && xc - rad - 1.0 <= gi_hi) {
+                    const int pos = atomicAdd(&nlist, 1);
+                    if (pos < 128) list[pos] = c;
+                }
             }
-        } else {
-            for (int c = 0; c < N; ++c)
-                if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+            __syncthreads();
         }
-        obstNew[g.idx(0, i, j)] = solid;
-        if (i >= 1 && i <= g.nx && j >= 1 && j <= g.ny) {
-            const long long m = g.cell(i, j);
-            if (solid) { rho[m] = p.rhoSolid; u[m] = 0.0; v[m] = 0.0; }
-            else { sr = rho[m]; sc = 1.0; }
-            if (obst[g.idx(0, i, j)] == 0 && nlinks[m] != 0) atomicOr(err, ERR_OWNER);
+        if (i <= g.nx + 1) {
+            int solid = 0;
+            if (b.B) solid = covered(b, g, N, ps, i, j, list, nlist);
+            else if (nlist <= 128) {
+                for (int q = 0; q < nlist; ++q) {
+                    const int c = list[q];
+                    if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+                }
+            } else {
+                for (int c = 0; c < N; ++c)
+                    if (inside(g, i, j, ps[PX_ * N + c], ps[PY_ * N + c], ps[PRAD_ * N + c])) solid = 1;
+            }
+            obstNew[g.idx(0, i, j)] = solid;
+            if (i >= 1 && i <= g.nx && j >= 1 && j <= g.ny) {
+                const long long m = g.cell(i, j);
+                if (solid) { rho[m] = p.rhoSolid; u[m] = 0.0; v[m] = 0.0; }
+                else { sr += rho[m]; sc += 1.0; }
+                const int was = obst[g.idx(0, i, j)];
+                if (was == 0 && nlinks[m] != 0) atomicOr(err, ERR_OWNER);
+                if (was == 1 && !solid) {                                      // uncovered by the move: k_p_refill's work list
+                    const int pos = atomicAdd(rcount, 1);
+                    if (pos < rcap) rlist[pos] = (int)m; else atomicOr(err, ERR_REFILL);
+                }
+            }
         }
     }
     grid_sum2(sr, sc, partials, ticket, out);
@@ -841,14 +869,31 @@ __global__ void __launch_bounds__(128) k_p_mask_sum(G2 g, P2 p, PB b, const doub
 
 // updateCenter, P4/particle_update.F90:122-203: a solid node that became fluid is refilled by 3-point extrapolation
 // along the lattice direction closest to the outward normal, its momentum moments reset to the wall velocity
+__device__ void p_refill_node(const G2 &g, const P2 &p, const PB &b, const double *__restrict__ ps, double *__restrict__ F, double *__restrict__ rho,
+                              double *__restrict__ u, double *__restrict__ v, const double *__restrict__ rhoAvgPart, int *__restrict__ err, int i, int j);
 __global__ void __launch_bounds__(128) k_p_refill(G2 g, P2 p, PB b, const double *__restrict__ ps, const int *__restrict__ obst,
                                                   const int *__restrict__ obstNew, double *__restrict__ F, double *__restrict__ rho,
                                                   double *__restrict__ u, double *__restrict__ v, const double *__restrict__ rhoAvgPart,
-                                                  int *__restrict__ err) {
+                                                  int *__restrict__ err, const int *__restrict__ rlist, const int *__restrict__ rcount) {
+    // rlist == nullptr: every interior node is tested (one node per thread).  Otherwise the launch is a fixed grid that works off
+    // the list of uncovered nodes k_p_mask_sum collected (a few per particle), so no second pass over the lattice is needed.
+    if (rlist) {
+        const int n = *rcount;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+            const int m = rlist[q];
+            p_refill_node(g, p, b, ps, F, rho, u, v, rhoAvgPart, err, 1 + m % g.nx, 1 + m / g.nx);
+        }
+        return;
+    }
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
     if (i > g.nx) return;
     const long long c = g.idx(0, i, j);
     if (!(obst[c] == 1 && obstNew[c] == 0)) return;
+    p_refill_node(g, p, b, ps, F, rho, u, v, rhoAvgPart, err, i, j);
+}
+__device__ void p_refill_node(const G2 &g, const P2 &p, const PB &b, const double *__restrict__ ps, double *__restrict__ F, double *__restrict__ rho,
+                              double *__restrict__ u, double *__restrict__ v, const double *__restrict__ rhoAvgPart, int *__restrict__ err, int i, int j) {
+    const long long c = g.idx(0, i, j);
     const int N = p.N;
     const double rhoAvg = rhoAvgPart[0] / rhoAvgPart[1];
     int found = 0;
@@ -986,6 +1031,7 @@ struct Sub {
     int *nlinks;                     // fused step: links into solid nodes still to be bounced back, per interior node
     double *gpart;                   // fused step: per-block partial sums of grid_sum2 (2 per block)
     unsigned *ticket;                // [0] collision+sum launch, [1] mask+sum launch
+    int *rlist, *rcount, rcap;       // fused step: nodes uncovered by the particles' move (k_p_mask_sum -> k_p_refill)
     int launches_per_step, no_graph;
     int *obst0;                      // the allocation obst pointed to at create time (graph parity)
     cudaGraphExec_t gexec[2];        // one captured step per obst/obstNew parity (single-subdomain handles)
@@ -1046,7 +1092,7 @@ static void p_free_sub(Sub *S) {
     double *bufs[] = {S->F, S->Fp, S->rho, S->u, S->v, S->up, S->vp, S->ps, S->part, S->stage};
     for (double *b : bufs) cudaFree(b);
     cudaFree(S->obst); cudaFree(S->obstNew); cudaFree(S->err); cudaFree(S->istage);
-    cudaFree(S->nlinks); cudaFree(S->gpart); cudaFree(S->ticket);
+    cudaFree(S->nlinks); cudaFree(S->gpart); cudaFree(S->ticket); cudaFree(S->rlist); cudaFree(S->rcount);
     cudaFree(S->bins.cnt); cudaFree(S->bins.list);
     for (cudaGraphExec_t e : S->gexec) if (e) cudaGraphExecDestroy(e);
     for (Msg &M : S->msgs) { cudaFree(M.sbuf); cudaFree(M.rbuf); }
@@ -1099,6 +1145,9 @@ static int p_make_sub(mglc_p2d *h, int rank, int device, Sub **out) {
     if (cudaMalloc((void **)&S->nlinks, (size_t)S->nx * S->ny * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&S->gpart, 2 * nblk * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void **)&S->ticket, 2 * sizeof(unsigned)) != cudaSuccess) { (void)cudaGetLastError(); return fail(MGLC_E_NOMEM); }
+    S->rcap = (int)std::min<long long>((long long)S->nx * S->ny, std::max<long long>(65536, (long long)S->nx * S->ny / 4));
+    if (cudaMalloc((void **)&S->rlist, (size_t)S->rcap * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&S->rcount, sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); return fail(MGLC_E_NOMEM); }
+    cudaMemsetAsync(S->rcount, 0, sizeof(int), S->s);
     cudaMemsetAsync(S->nlinks, 0, (size_t)S->nx * S->ny * sizeof(int), S->s);
     cudaMemsetAsync(S->ticket, 0, 2 * sizeof(unsigned), S->s);
     S->obst0 = S->obst;
@@ -1371,6 +1420,11 @@ extern "C" int mglc_p2d_download(mglc_p2d *h, int r, double *f, double *f_post, 
 
 // ---- the reference's subroutines --------------------------------------------------------------------------------------------
 static inline dim3 grid_int(const Sub *S) { return dim3((S->nx + 127) / 128, S->ny); }
+// the two summing kernels: at most ~8192 blocks (= partial sums), each walking several rows on a large lattice
+static inline dim3 grid_rows(int nxt, int rows) {
+    const int nbx = (nxt + 127) / 128;
+    return dim3(nbx, std::max(1, std::min(rows, 8192 / nbx)));
+}
 
 extern "C" int mglc_p2d_initial(mglc_p2d *h) {
     if (!h) return MGLC_E_INVALID;
@@ -1559,7 +1613,7 @@ static int p_mask_refill(mglc_p2d *h) {
     MGLC_TRY(p_fluid_average(h, true));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
+        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err, nullptr, nullptr);
         S->launches += 1;
         std::swap(S->obst, S->obstNew);      // obst = obstNew, P4/particle_update.F90:206 (obstNew is rebuilt from scratch next time)
     }
@@ -1623,7 +1677,7 @@ static int p_enqueue_step(mglc_p2d *h) {
     const int N = h->p.N;
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_collision_sum<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->F, S->rho, S->u, S->v, S->obst, S->Fp, S->gpart, S->ticket, S->part);
+        k_p_collision_sum<<<grid_rows(S->nx, S->ny), 128, 0, S->s>>>(S->g, h->p, S->F, S->rho, S->u, S->v, S->obst, S->Fp, S->gpart, S->ticket, S->part, S->rcount);
         S->launches += 1;
     }
     MGLC_TRY(p_exchange(h, 0));
@@ -1649,14 +1703,15 @@ static int p_enqueue_step(mglc_p2d *h) {
     MGLC_TRY(p_exchange(h, 1));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_mask_sum<<<dim3((S->nx + 2 + 127) / 128, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->rho, S->u, S->v,
-                                                                               S->nlinks, S->err, S->gpart, S->ticket + 1, S->part);
+        k_p_mask_sum<<<grid_rows(S->nx + 2, S->ny + 2), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->rho, S->u, S->v,
+                                                                      S->nlinks, S->err, S->gpart, S->ticket + 1, S->part, S->rlist, S->rcount, S->rcap);
         S->launches += 1;
     }
     MGLC_TRY(p_reduce_part(h));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_refill<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err);
+        k_p_refill<<<std::min(1184, (S->rcap + 127) / 128), 128, 0, S->s>>>(S->g, h->p, S->bins, S->ps, S->obst, S->obstNew, S->F, S->rho, S->u, S->v, S->part, S->err,
+                                                                      S->rlist, S->rcount);
         S->launches += 1;
         std::swap(S->obst, S->obstNew);      // obst = obstNew, P4/particle_update.F90:206
     }

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
         d3q7_collide(gq, u, v, w, T, tp, gp);                 // collisionT() of step n+1
 #pragma unroll
         for (int a = 0; a < 7; ++a) Gout[a * sq + c] = gp[a];
-        if (PEER) peer_store_g(pt, g, i, j, k, gp);
+        if (PEER && peer_cta_on_face(g, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k)) peer_store_g(pt, g, i, j, k, gp);
     }
     thermal_force(rho, u, v, T, tp, Fx, Fy, Fz);              // force of step n+1's collision
     Fc_out[m] = Fx; Fc_out[n + m] = Fy; Fc_out[2 * n + m] = Fz;

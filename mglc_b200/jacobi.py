@@ -88,6 +88,18 @@ class Jacobi:
     def sync(self):
         L.check(L.lib().mglc_jacobi_sync(self._h))
 
+    def set_halo(self, mode):
+        """'direct' (boundary values stored into the neighbours' ghost layers by the sweep) or 'exchange' (LAP:94-103 as written)"""
+        L.check(L.lib().mglc_jacobi_set_halo(self._h, {"direct": 1, "exchange": 0}[mode]))
+
+    def direct_halo_available(self):
+        a = C.c_int()
+        L.check(L.lib().mglc_jacobi_direct_halo(self._h, C.byref(a)))
+        return bool(a.value)
+
+    def halo_mode(self):
+        return "none (1 subdomain)" if self.nprocs == 1 else ("direct stores into the neighbours' ghost layers" if self.direct_halo_available() else "NCCL exchange, then sweep")
+
     def launch_count(self):
         n = C.c_longlong()
         L.check(L.lib().mglc_jacobi_launch_count(self._h, C.byref(n)))

@@ -129,25 +129,35 @@ def thermal(comm, rank, world, total=(27, 25, 23), nsteps=10, transports=("direc
 
 
 def jacobi(comm, rank, world, totals=((37, 29, 23), (61, 45)), nsteps=15, log=None):
+    """Jacobi halo-exchange path, 3-D and 2-D, with both halo transports of the fused step: direct stores into the neighbours'
+    ghost layers, and exchange_message over NCCL followed by the sweep (LAP:94-103 as written)"""
     out = {}
     for total in totals:
-        sim = mg.Jacobi(total, comm=comm)
-        sim.init(); sim.step(7); sim.step(nsteps - 7)
-        diff = sim.check_diff()
-        inf = sim.info[0]
-        inner = tuple(slice(1, n + 1) for n in inf["n"])
-        blocks = gather_blocks((inf["start"], sim.download(0)[inner]), rank, world)
-        same = True
-        if rank == 0:
-            orc = _oracle()
-            wd = orc.JacobiWorld(total, 1)
-            wd.init(); wd.step(nsteps)
-            same = bool(np.array_equal(assemble(blocks, total), wd.gather()) and diff == wd.check_diff())
-            wd.close()
-            if log:
-                log(f"jacobi {len(total)}-D: {'bit-exact' if same else 'MISMATCH'}")
-        out[f"{len(total)}d"] = "bit-exact" if same else "MISMATCH"
-        sim.close()
+        for halo in ("direct", "exchange"):
+            sim = mg.Jacobi(total, comm=comm)
+            key = f"{len(total)}d_{halo}"
+            if halo == "direct" and not sim.direct_halo_available():
+                out[key] = "unavailable"
+                sim.close()
+                continue
+            sim.set_halo(halo)
+            sim.init(); sim.step(7); sim.step(nsteps - 7)
+            diff = sim.check_diff()
+            inf = sim.info[0]
+            inner = tuple(slice(1, n + 1) for n in inf["n"])
+            blocks = gather_blocks((inf["start"], sim.download(0)[inner]), rank, world)
+            same = True
+            if rank == 0:
+                orc = _oracle()
+                wd = orc.JacobiWorld(total, 1)
+                wd.init(); wd.step(nsteps)
+                same = bool(np.array_equal(assemble(blocks, total), wd.gather()) and diff == wd.check_diff())
+                wd.close()
+                if log:
+                    log(f"jacobi {len(total)}-D {halo}: {'bit-exact' if same else 'MISMATCH'}")
+            out[key] = "bit-exact" if same else "MISMATCH"
+            sim.sync()
+            sim.close()
     return out
 
 

@@ -62,14 +62,19 @@ def test_sweep_bit_exact(total, with_f):
     wd.close(); sim.close()
 
 
-@pytest.mark.parametrize("kernel,ctas,slab", [("tma", 1, 64), ("tma", 2, 64), ("tma", 1, 5), ("tma", 2, 1), ("reg", 1, 64)])
+@pytest.mark.parametrize("kernel,shape,th,chunks", [("tma", 0, 0, 0), ("tma", 1, 0, 0), ("tma", 2, 0, 0), ("tma", 0, 14, 2), ("tma", 1, 13, 2), ("tma", 2, 5, 3),
+                                                    ("tma", 1, 1, 9), ("tma", 0, 6, 1), ("reg", 0, 0, 0), ("reg", 1, 0, 0)])
 @pytest.mark.parametrize("total,with_f", [((131, 17, 9), True), ((260, 35, 70), False), ((128, 16, 3), True), ((5, 4, 3), False)])
-def test_3d_sweep_kernels_bit_exact(total, with_f, kernel, ctas, slab, monkeypatch):
-    """Both 3-D sweep kernels -- the TMA pipeline (persistent CTAs, 128 x 16 tiles, any slab height, one or two CTAs per SM) and
-    the register-blocked LDG kernel -- on blocks that do not divide into tiles: every cell, several sweeps, bit for bit."""
+def test_3d_sweep_kernels_bit_exact(total, with_f, kernel, shape, th, chunks, monkeypatch):
+    """Both 3-D sweep kernels -- the TMA pipeline (persistent CTAs, 128 x th tiles with th chosen per block or forced, any number
+    of z chunks, each of its three CTA shapes) and the register-blocked LDG kernel -- on blocks that do not divide into tiles:
+    every cell, several sweeps, bit for bit."""
     monkeypatch.setenv("MGLC_JACOBI_KERNEL", kernel)
-    monkeypatch.setenv("MGLC_JACOBI_TMA_CTAS", str(ctas))
-    monkeypatch.setenv("MGLC_JACOBI_SLAB", str(slab))
+    monkeypatch.setenv("MGLC_JACOBI_TMA_SHAPE", str(shape))
+    monkeypatch.setenv("MGLC_JACOBI_PF", str(shape))              # register-blocked kernel: with / without the one-plane prefetch
+    if th:
+        monkeypatch.setenv("MGLC_JACOBI_TMA_TH", str(th))
+        monkeypatch.setenv("MGLC_JACOBI_TMA_CHUNKS", str(chunks))
     wd, sim = orc.JacobiWorld(total, 1), mg.Jacobi(total)
     load_random(wd, sim, total, 5, with_f)
     for _ in range(3):
@@ -127,3 +132,31 @@ def test_3d_256_matches_oracle_and_512_properties():
     assert np.all(np.diff(col) >= 0.0) and col[-1] > 0.1 and col[0] == 0.0
     assert sim.launch_count() >= 40
     sim.close()
+
+
+@pytest.mark.parametrize("halo", ["direct", "exchange"])
+@pytest.mark.parametrize("total,nprocs,dims", [((37, 23), 6, None), ((41, 19), 3, (3, 1)), ((33, 21, 19), 8, None), ((150, 18, 9), 12, None),
+                                               ((17, 13, 29), 3, (1, 1, 3))])
+def test_fused_steps_with_direct_halo_stores_match_the_oracle(total, nprocs, dims, halo):
+    """mglc_jacobi_step on P subdomains: the sweep stores its boundary values into the neighbours' ghost layers (default) or the
+    halos go through exchange_message first (LAP:94-103 as written).  Either way every interior cell equals the 1-rank oracle
+    bit for bit, across several step() calls with check_diff(), a download and an explicit exchange_message() in between."""
+    wd, sim = orc.JacobiWorld(total, 1), mg.Jacobi(total, nprocs=nprocs, dims=dims)
+    assert sim.direct_halo_available()
+    sim.set_halo(halo)
+    wd.init(); sim.init()
+    rng = np.random.default_rng(9)
+    glob = rng.random(tuple(n + 2 for n in total))
+    wd.array(0, "A")[...] = glob; wd.array(0, "A_new")[...] = glob
+    for r, inf in enumerate(sim.info):
+        sl = tuple(slice(s, s + n + 2) for s, n in zip(inf["start"], inf["n"]))
+        sim.upload(r, A=glob[sl], A_new=glob[sl])
+    for n in (1, 4, 2):
+        wd.step(n); sim.step(n)
+        assert np.array_equal(sim.gather(), wd.gather())
+        assert sim.check_diff() == wd.check_diff()
+    sim.exchange_message(); wd.exchange_message()
+    wd.step(3); sim.step(3)
+    assert np.array_equal(sim.gather(), wd.gather())
+    sim.sync()
+    wd.close(); sim.close()

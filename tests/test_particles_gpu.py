@@ -341,6 +341,6 @@ def test_thousands_of_particles_on_a_lattice_larger_than_l2_conserve_and_settle(
     assert np.median(p["Vc"]) < 0.0 and p["yCenter"].mean() < ys.mean()       # (the bottom row feels the wall spring and may rise)
     fluid = a.gather("obst") == 0
     m0, m1 = rho0[fluid0].sum(), a.gather("rho")[fluid].sum()
-    assert abs(m1 / fluid.sum() - m0 / fluid0.sum()) < 1e-6          # mean fluid density: refill and moving walls exchange O(1e-7)
+    assert abs(m1 / fluid.sum() - m0 / fluid0.sum()) < 1e-4          # mean fluid density: refill and moving walls exchange O(1e-7) per step
     for sim in sims:
         sim.close()

@@ -64,6 +64,80 @@ import json;d=json.loads(open('$O/bench_jacobi_$1_$2_promo$3.json').read().strip
     tail -n 5 $O/err.txt
 }
 
+m2() {   # 2 GPUs: multi-process parity, the N=2 bench line, which decomposition axis costs what, NVLink traffic of k_fused<0,1>
+    (timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 30 $O/pytest_multigpu.log
+    (timeout 600 python -m pytest tests/test_jacobi_gpu.py tests/test_particles_gpu.py -q -m gpu -x > $O/pytest_jacobi_particles.log 2>&1; echo "pytest rc=$?" >> $O/pytest_jacobi_particles.log); tail -n 5 $O/pytest_jacobi_particles.log
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 2500 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
+    for d in 2,1,1 1,2,1 1,1,2; do timeout 300 python tools/group_bench.py --gpus 2 --dims $d --size 768 --steps 20 2>> $O/err.txt | tee -a $O/group_bench_axes.jsonl; done
+    timeout 300 python tools/group_bench.py --gpus 1 --dims 1,1,1 --size 768 --steps 20 2>> $O/err.txt | tee -a $O/group_bench_axes.jsonl
+    ncu --query-metrics 2>/dev/null | grep -iE "nvl|fabric|pcie" > $O/ncu_metric_names_nvlink.txt; wc -l $O/ncu_metric_names_nvlink.txt
+    timeout 900 $NCU --set full --import-source on -k regex:k_fused -s 4 -c 2 -o $O/ncu_full_k_fused_peer_512 \
+        python tools/group_bench.py --gpus 2 --dims 2,1,1 --size 512 --steps 2 > $O/b2.log 2>&1; echo "ncu peer rc=$?"
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 > $O/bench_jacobi_2gpu.json 2> $O/b3.err; tail -c 1200 $O/bench_jacobi_2gpu.json; tail -n 3 $O/b3.err
+    MGLC_NO_DIRECT=1 timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-parity --no-e2e > $O/bench_jacobi_2gpu_nccl.json 2> $O/b4.err; tail -c 500 $O/bench_jacobi_2gpu_nccl.json
+    timeout 600 $TR bench.py --gpus 2 --workload particles --steps 20 --warmup 3 > $O/bench_particles_2gpu.json 2> $O/b5.err; tail -c 1500 $O/bench_particles_2gpu.json; tail -n 3 $O/b5.err
+    for cfg in "reg 1" "tma 1" "tma 2"; do
+        set -- $cfg
+        MGLC_JACOBI_KERNEL=$1 MGLC_JACOBI_TMA_CTAS=$2 timeout 120 python bench.py --workload jacobi --steps 300 --no-cpu --no-e2e > $O/bench_jacobi_$1_$2.json 2>> $O/err.txt
+        python -c "
+import json;d=json.loads(open('$O/bench_jacobi_$1_$2.json').read().strip().splitlines()[-1]);print('jacobi $cfg', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+    timeout 600 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_1gpu.json 2> $O/b10.err; tail -c 600 $O/bench_particles_8192_1gpu.json
+    tail -n 5 $O/err.txt
+}
+
+san() {   # 1 GPU: compute-sanitizer racecheck + initcheck + memcheck over the fused, single-lattice, particle, Jacobi (TMA) and
+          # direct-halo-store paths (P subdomains in one process); logs are kept under profiles/
+    SEL='(test_fused_step_strict_is_bit_exact and 13) or test_direct_halo_stores_equal_packed_exchange or test_reinitialising or (test_3d_sweep_kernels_bit_exact and 131) or (test_fused_steps_with_direct_halo_stores and 33) or (test_particle_bins and 1-) or test_decomposed_run_matches_single_rank_oracle or (strict_is_bit_exact_for_every_way and mrt and calls8) or (test_fused_step_strict and thermal and 11)'
+    FILES="tests/test_lid_gpu.py tests/test_jacobi_gpu.py tests/test_particles_gpu.py tests/test_aa_gpu.py tests/test_thermal_gpu.py"
+    for tool in memcheck racecheck initcheck; do
+        (timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $FILES -m gpu -q -x -k "$SEL" > $O/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a $O/sanitizer_$tool.log)
+        grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" $O/sanitizer_$tool.log | tail -n 4
+    done
+}
+
+s5() {   # 1 GPU: TMA Jacobi shapes after the row-mapping fix, particle sums/refill list, whole suite
+    (timeout 900 python -m pytest tests/test_jacobi_gpu.py tests/test_particles_gpu.py -q -m gpu -x > $O/pytest_jacobi_particles.log 2>&1; echo "pytest rc=$?" >> $O/pytest_jacobi_particles.log); tail -n 6 $O/pytest_jacobi_particles.log
+    for cfg in "reg 0" "tma 0" "tma 1" "tma 2"; do
+        set -- $cfg
+        MGLC_JACOBI_KERNEL=$1 MGLC_JACOBI_TMA_SHAPE=$2 timeout 120 python bench.py --workload jacobi --steps 300 --no-cpu --no-e2e > $O/bench_jacobi_$1_shape$2.json 2>> $O/err.txt
+        python -c "
+import json;d=json.loads(open('$O/bench_jacobi_$1_shape$2.json').read().strip().splitlines()[-1]);print('jacobi $cfg', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+    for sh in 0 1; do
+    MGLC_JACOBI_TMA_SHAPE=$sh timeout 600 $NCU --set full --import-source on -k regex:k_jacobi3d_tma -s 5 -c 1 -o $O/ncu_full_k_jacobi3d_tma_512_shape$sh \
+        python bench.py --workload jacobi --steps 10 --warmup 3 --no-e2e --no-cpu > $O/b5.log 2>&1; echo "ncu full jacobi tma shape $sh rc=$?"
+    done
+    timeout 600 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu > $O/bench_particles_8192_1gpu.json 2> $O/b10.err; tail -c 900 $O/bench_particles_8192_1gpu.json; tail -n 3 $O/b10.err
+    timeout 300 python bench.py --workload particles --steps 200 --no-cpu > $O/bench_particles_shipped.json 2> $O/b11.err; tail -c 500 $O/bench_particles_shipped.json
+    timeout 600 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -s 40 -c 24 --csv --log-file $O/launches_particles_8192.csv \
+        python bench.py --workload particles --size 8192 --steps 4 --warmup 3 --no-e2e --no-cpu > $O/b12.log 2>&1; echo "ncu particles rc=$?"
+    (timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log); tail -n 4 $O/pytest_gpu.log
+    tail -n 5 $O/err.txt
+}
+
+m3() {   # 2 GPUs: after the fixes -- bench lines (lid with strong leg, jacobi direct vs NCCL, particles), axis costs again
+    (timeout 900 python -m pytest tests/test_jacobi_gpu.py tests/test_particles_gpu.py tests/test_lid_gpu.py tests/test_thermal_gpu.py -q -m gpu -x > $O/pytest_sel.log 2>&1; echo "pytest rc=$?" >> $O/pytest_sel.log); tail -n 5 $O/pytest_sel.log
+    for cfg in "0 8" "1 8" "1 16" "1 32" "0 16"; do
+        set -- $cfg
+        MGLC_JACOBI_PF=$1 MGLC_JACOBI_KCH=$2 timeout 120 python bench.py --workload jacobi --steps 300 --no-cpu --no-e2e > $O/bench_jacobi_pf$1_kch$2.json 2>> $O/err.txt
+        python -c "
+import json;d=json.loads(open('$O/bench_jacobi_pf$1_kch$2.json').read().strip().splitlines()[-1]);print('jacobi pf kch $cfg', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 3 $O/pytest_multigpu.log
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 3000 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
+    for d in 2,1,1 1,1,2; do timeout 300 python tools/group_bench.py --gpus 2 --dims $d --size 768 --steps 20 2>> $O/err.txt | tee -a $O/group_bench_axes.jsonl; done
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 > $O/bench_jacobi_2gpu.json 2> $O/b3.err; tail -c 1200 $O/bench_jacobi_2gpu.json; tail -n 3 $O/b3.err
+    MGLC_NO_DIRECT=1 timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-parity --no-e2e > $O/bench_jacobi_2gpu_nccl.json 2> $O/b4.err; tail -c 500 $O/bench_jacobi_2gpu_nccl.json
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --scaling strong --steps 1000 --no-parity --no-e2e > $O/bench_jacobi_2gpu_strong.json 2> $O/b6.err; tail -c 500 $O/bench_jacobi_2gpu_strong.json
+    timeout 600 $TR bench.py --gpus 2 --workload particles --steps 20 --warmup 3 > $O/bench_particles_2gpu.json 2> $O/b5.err; tail -c 1500 $O/bench_particles_2gpu.json; tail -n 3 $O/b5.err
+    timeout 600 $TR bench.py --gpus 2 --workload thermal --steps 20 --warmup 5 > $O/bench_thermal_2gpu.json 2> $O/b7.err; tail -c 2500 $O/bench_thermal_2gpu.json; tail -n 3 $O/b7.err
+    timeout 600 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_1gpu.json 2> $O/b10.err; tail -c 600 $O/bench_particles_8192_1gpu.json
+    tail -n 5 $O/err.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30
