@@ -427,7 +427,7 @@ static int direct_status(mglc_lbm *h) {
     if (!h->direct || h->group) return MGLC_OK;
     int e = 0;
     MGLC_CUDA(cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
-    if (e & 1) { set_error("direct halo path: a neighbour did not reach the barrier within %.0f s (MGLC_HALO_TIMEOUT_S; ranks out of step?); the lattice was left untouched from that step on", halo_timeout_seconds()); return MGLC_E_STATE; }
+    if (e & 1) { set_error("direct halo path: a neighbour did not reach the barrier within %.0f s (MGLC_HALO_TIMEOUT_S; ranks out of step?); nothing was stored into a neighbour from that step on and this subdomain's fields are invalid", halo_timeout_seconds()); return MGLC_E_STATE; }
     if (e & 2) { set_error("direct halo path: a neighbour wrote the other ping-pong lattice (calls between mglc_lbm_step must be made by every rank)"); return MGLC_E_STATE; }
     return MGLC_OK;
 }

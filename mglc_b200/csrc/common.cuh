@@ -52,9 +52,9 @@ struct PeerTable {
     double *G[6];              // thermal: its g_post lattice
     long long sy[19], sz[19], sq[19];
     int n[19][3];              // the neighbour's interior size
-    // sticky error word of the neighbour barrier (k_halo_wait): once set, a launch with direct halo stores does
-    // nothing at all -- it neither reads halos a neighbour has not written nor overwrites halos a neighbour may
-    // still be reading; the host reports MGLC_E_STATE at every point where it synchronises
+    // sticky error word of the neighbour barrier (k_halo_wait): once set, a launch stores nothing into a neighbour any
+    // more (it may still be reading those halos); the subdomain's own numbers are meaningless from then on and the host
+    // reports MGLC_E_STATE at every point where it synchronises, so such a run never comes back as MGLC_OK
     const int *err;
 };
 

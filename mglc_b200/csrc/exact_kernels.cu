@@ -540,8 +540,8 @@ int launch_nure(const Geom &g, const double *u, const double *v, const double *w
 // raised theirs (wait).  Kernel completion orders the halo stores before the flag store on the same stream.  Like
 // MPI_Waitall (lid3_mpi_nonblock.f90:1229) the wait lasts as long as the slowest neighbour's host takes to issue its
 // launch; it is bounded (MGLC_HALO_TIMEOUT_S, default 600 s) only so that ranks that really fell out of step cannot hang
-// the device for ever.  Running out of time does NOT let the stream carry on: *err becomes sticky, every later launch
-// with direct halo stores returns at once (PeerTable::err) and the host reports MGLC_E_STATE.
+// the device for ever.  Running out of time does NOT go unnoticed: *err becomes sticky, no later launch stores into a
+// neighbour's halos (PeerTable::err) and the host reports MGLC_E_STATE at every point where it synchronises.
 __global__ void k_halo_signal(SyncTable t, unsigned long long epoch /* the word, see k_halo_wait */) {
     const int d = threadIdx.x;
     if (d < 19 && (t.mask >> d & 1u)) {

@@ -27,6 +27,9 @@ struct File {
     FILE *fp;
     explicit File(const char *path, const char *mode) : fp(path ? fopen(path, mode) : nullptr) {}
     ~File() { if (fp) fclose(fp); }
+    // the success path of every writer ends here: data still sitting in the stdio buffer reaches the file (or the error is
+    // reported: ENOSPC, quota, NFS) before MGLC_OK goes back to the caller
+    bool close() { FILE *q = fp; fp = nullptr; return q == nullptr || fclose(q) == 0; }
     bool put(const void *p, size_t n) { return n == 0 || fwrite(p, 1, n, fp) == n; }
     bool get(void *p, size_t n) { return n == 0 || fread(p, 1, n, fp) == n; }
 };
@@ -62,6 +65,10 @@ int read_record(File &f, void *data, long long bytes) {
     if (got != bytes) { set_error("unformatted read: record holds %lld bytes, %lld expected", got, bytes); return MGLC_E_INVALID; }
     return MGLC_OK;
 }
+int close_failed(const char *what, const char *path) {
+    set_error("%s: closing '%s' failed (file may be truncated): %s", what, path ? path : "(null)", strerror(errno));
+    return MGLC_E_INVALID;
+}
 int open_failed(const char *what, const char *path) {
     set_error("%s: cannot open '%s': %s", what, path ? path : "(null)", strerror(errno));
     return MGLC_E_INVALID;
@@ -79,6 +86,7 @@ extern "C" int mglc_unformatted_write(const char *path, int nrecords, const void
         if (bytes[r] < 0 || (bytes[r] && !records[r])) { set_error("mglc_unformatted_write: record %d", r); return MGLC_E_INVALID; }
         if (!write_record(f, records[r], bytes[r], max_sub)) { set_error("mglc_unformatted_write: write to '%s' failed", path); return MGLC_E_INVALID; }
     }
+    if (!f.close()) return close_failed("mglc_unformatted_write", path);
     return MGLC_OK;
 }
 extern "C" int mglc_unformatted_read(const char *path, int nrecords, void *const *records, const long long *bytes) {
@@ -206,6 +214,7 @@ static int tecplot_write(const char *path, const double *xp, const double *yp, c
             }
             if (!f.put(row.data(), row.size() * sizeof(float))) { set_error("mglc_output_tecplot: write to '%s' failed", path); return MGLC_E_INVALID; }
         }
+    if (!f.close()) return close_failed("mglc_output_tecplot", path);
     return MGLC_OK;
 }
 extern "C" int mglc_output_tecplot_lid(const char *path, const double *xp, const double *yp, const double *zp, const double *u,

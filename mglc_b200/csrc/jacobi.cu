@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
                                                   double *__restrict__ B, JacPeers P) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
     if (i > g.nx) return;
-    if (PEER && *P.err) return;
+    const bool on_face = PEER && ((blockIdx.x == 0) | (blockIdx.x == gridDim.x - 1) | (j == 1) | (j == g.ny)) && *P.err == 0;
     const long long c = g.idx(0, i, j, 1);
     double s = A[c - 1] + A[c + 1];
     s += A[c - g.sy];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restri
     s += HAS_F ? f[c] : 0.0;
     const double val = 0.25 * s;
     B[c] = val;
-    if (PEER) jac_peer_store(P, g, i, j, 1, val);
+    if (PEER && on_face) jac_peer_store(P, g, i, j, 1, val);
 }
 
 // Register blocking, no barriers: a thread owns JRY consecutive rows of one x column and marches `kch` planes along
@@ -132,11 +132,14 @@ constexpr int JTX = 128;
 template <bool HAS_F, int JRY, bool PEER, bool PF>
 __global__ void __launch_bounds__(JTX, JRY <= 4 ? (PF ? 7 : 8) : 4) k_jacobi3d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
                                                                    double *__restrict__ B, int k_lo, int k_hi, int kch, JacPeers P) {
-    if (PEER && *P.err) return;
     const int i = 1 + blockIdx.x * JTX + threadIdx.x;
     const int j0 = 1 + blockIdx.y * JRY;
     const int k0 = k_lo + blockIdx.z * kch;
     const int k1 = min(k0 + kch - 1, k_hi);
+    // only CTAs that touch a face of the block have boundary values to hand over (block-uniform test: the interior skips the
+    // address arithmetic of the six possible messages); after a failed barrier nothing is stored into a neighbour
+    const bool on_face = PEER && ((blockIdx.x == 0) | (blockIdx.x == gridDim.x - 1) | (j0 == 1) | (j0 + JRY - 1 >= g.ny) | (k0 == 1) | (k1 == g.nz)) &&
+                         *P.err == 0;
     const int lane = threadIdx.x & 31;
     const bool active = i <= g.nx;
     const bool edge_m = lane == 0, edge_p = lane == 31 || i >= g.nx;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(JTX, JRY <= 4 ? (PF ? 7 : 8) : 4) k_jacobi3d(G
             if (active && j0 + r <= g.ny) {
                 const double val = (1.0 / 6.0) * s;
                 B[c + row[r]] = val;
-                if (PEER) jac_peer_store(P, g, i, j0 + r, k, val);
+                if (PEER && on_face) jac_peer_store(P, g, i, j0 + r, k, val);
             }
         }
 #pragma unroll
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(TBX * NRG + 32, CTAS) k_jacobi3d_tma(const __g
                                                                  const double *__restrict__ f, double *__restrict__ B,
                                                                  int k_lo, int k_hi, int th, int nchunks, JacPeers P) {
     constexpr int CONSUMERS = TBX * NRG;
-    if (PEER && *P.err) return;
+    const bool peers_ok = PEER && *P.err == 0;                 // after a failed barrier nothing is stored into a neighbour
     const CUtensorMap *map = mapG ? mapG : &mapP;              // descriptor in global memory, or the kernel parameter
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *base = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -291,6 +294,8 @@ __global__ void __launch_bounds__(TBX * NRG + 32, CTAS) k_jacobi3d_tma(const __g
         const int t = q % ntiles, ka = k_lo + (q / ntiles) * H, kb = min(k_hi, ka + H - 1);
         const int i = 1 + (t % tiles_x) * TBX + lx, j0 = 1 + (t / tiles_x) * th + rg * TRY;
         const bool active = i <= g.nx;
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        const bool on_face = peers_ok && ((tx == 0) | (tx == tiles_x - 1) | (ty == 0) | (ty == tiles_y - 1) | (ka == 1) | (kb == g.nz));
         long long c = g.idx(0, min(i, g.nx), min(j0, g.ny + 1), ka);
         double below[TRY], cen[TRY], up[TRY];
         {   // plane ka-1: only my own cells, then the stage is free again
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(TBX * NRG + 32, CTAS) k_jacobi3d_tma(const __g
                     s += HAS_F ? f[cr] : 0.0;
                     const double val = (1.0 / 6.0) * s;
                     B[cr] = val;
-                    if (PEER) jac_peer_store(P, g, i, j0 + r, k, val);
+                    if (PEER && on_face) jac_peer_store(P, g, i, j0 + r, k, val);
                 }
             }
 #pragma unroll
@@ -953,7 +958,7 @@ static int jac_sweep(mglc_jacobi *h, bool peers = false) {
             const dim3 grid((S->n[0] + JTX - 1) / JTX, (S->n[1] + JRY - 1) / JRY, (S->n[2] + kch - 1) / kch);
             const dim3 block(JTX);
             const char *pfe = getenv("MGLC_JACOBI_PF");
-            const bool pf = pfe ? atoi(pfe) != 0 : true;
+            const bool pf = pfe ? atoi(pfe) != 0 : false;       // measured on B200 at 512^3: 0.408 ms with the prefetch, 0.367 ms without (7 instead of 8 CTAs per SM)
 #define MGLC_JAC_REG(HASF, ROWS, PEER_, FPTR) do { if (pf) k_jacobi3d<HASF, ROWS, PEER_, true><<<grid, block, 0, S->s>>>(S->g, A, FPTR, B, 1, S->n[2], kch, P); \
                                                    else k_jacobi3d<HASF, ROWS, PEER_, false><<<grid, block, 0, S->s>>>(S->g, A, FPTR, B, 1, S->n[2], kch, P); } while (0)
             if (JRY == 8) {

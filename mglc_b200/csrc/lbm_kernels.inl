@@ -74,8 +74,13 @@ __device__ __forceinline__ long long peer_cell(const PeerTable *__restrict__ pt,
 #define MGLC_PEER_EDGE(A, EX, EY, EZ)                                                        \
     if (pm & (1u << (A))) pt->F[A][(A) * pt->sq[A] + peer_cell<EX, EY, EZ>(pt, A, i, j, k)] = fp[A];
 // does the CTA whose first cell is (ib, jb, k) contain a cell on a face of the subdomain?  (block-uniform)
-__device__ __forceinline__ bool peer_cta_on_face(const Geom &g, int ib, int jb, int k) {
-    return (k == 1) | (k == g.nz) | (jb == 1) | (jb + (int)blockDim.y - 1 >= g.ny) | (ib == 1) | (ib + (int)blockDim.x - 1 >= g.nx);
+// ... and is the neighbour barrier intact?  After a time-out (PeerTable::err) nothing is stored into a neighbour any more:
+// the step goes on computing on this subdomain's own stale halos, and the host reports MGLC_E_STATE at every synchronisation.
+// Testing the word here -- by the ~1 % of CTAs on a face, after their arithmetic -- keeps two dependent loads off the
+// start of every thread (they cost 1 % of the step there: 21.71 instead of 21.52 ms at 768^3 on 2 GPUs).
+__device__ __forceinline__ bool peer_cta_on_face(const Geom &g, const PeerTable *__restrict__ pt, int ib, int jb, int k) {
+    const bool face = (k == 1) | (k == g.nz) | (jb == 1) | (jb + (int)blockDim.y - 1 >= g.ny) | (ib == 1) | (ib + (int)blockDim.x - 1 >= g.nx);
+    return face && !(pt->err && *pt->err);
 }
 // the outgoing populations of a boundary cell, in the message sets of message_passing_sendrecv()
 __device__ __forceinline__ void peer_store_f(const PeerTable *__restrict__ pt, const Geom &g, int i, int j, int k,
@@ -153,7 +158,6 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
     if (i > i1 || j > j1) return;
-    if (PEER && pt->err && *pt->err) return;      // the neighbour barrier failed: touch nothing (see PeerTable::err)
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k);
     const WallFlags wf = wall_flags(g, i, j, k);
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(128, 4) k_fused(Geom g, LbmParams p, const dou
     // Only CTAs that touch a face of the subdomain have anything to send; the test is uniform across the CTA, so the
     // interior (all but ~1 % of the CTAs at 768^3) skips the message code in a handful of instructions (ncu, 2 GPUs:
     // the per-thread face tests cost 5.7 % more instructions than k_fused<..., false>, profiles/r2d_*).
-    if (PEER && peer_cta_on_face(g, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k))
+    if (PEER && peer_cta_on_face(g, pt, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k))
         peer_store_f(pt, g, i, j, k, fp);
     // the moving-lid bounce-back of the NEXT step needs this step's rho on the lid plane
     // (L3/bounce_back.f90:77-78 reads rho(i,j,nz) left by the previous macro()); it goes to the other

@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
     if (i > i1 || j > j1) return;
-    if (PEER && pt->err && *pt->err) return;      // the neighbour barrier failed: touch nothing (see PeerTable::err)
     const long long sq = g.sq, sy = g.sy, sz = g.sz;
     const long long c = g.idx(0, i, j, k), m = g.cell(i, j, k);
     const long long n = (long long)g.nx * g.ny * g.nz;
@@ -87,7 +86,7 @@ __global__ void __launch_bounds__(128, 3) k_th_fused(Geom g, ThermalParams tp, c
         d3q7_collide(gq, u, v, w, T, tp, gp);                 // collisionT() of step n+1
 #pragma unroll
         for (int a = 0; a < 7; ++a) Gout[a * sq + c] = gp[a];
-        if (PEER && peer_cta_on_face(g, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k)) peer_store_g(pt, g, i, j, k, gp);
+        if (PEER && peer_cta_on_face(g, pt, i0 + (int)(blockIdx.x * blockDim.x), j0 + (int)(blockIdx.y * blockDim.y), k)) peer_store_g(pt, g, i, j, k, gp);
     }
     thermal_force(rho, u, v, T, tp, Fx, Fy, Fz);              // force of step n+1's collision
     Fc_out[m] = Fx; Fc_out[n + m] = Fy; Fc_out[2 * n + m] = Fz;

@@ -20,6 +20,55 @@ import math
 import re
 
 
+# ---- guarded evaluation ---------------------------------------------------------------------------------------------
+# The text that reaches eval()/exec() below is produced from files under /root/reference -- untrusted content.  The
+# translated source is therefore parsed first and rejected unless it consists of plain arithmetic, indexing, assignments,
+# loops and calls to the whitelisted names in its namespace: no attribute access, no imports, no lambdas, no dunder names,
+# and it runs without Python's builtins.
+import ast as _ast
+
+_ALLOWED_NODES = (
+    _ast.Module, _ast.Expression, _ast.Expr, _ast.Assign, _ast.AugAssign, _ast.For, _ast.While, _ast.If, _ast.IfExp, _ast.Break,
+    _ast.Continue, _ast.Pass, _ast.BinOp, _ast.UnaryOp, _ast.BoolOp, _ast.Compare, _ast.Call, _ast.Name, _ast.Constant,
+    _ast.Subscript, _ast.Tuple, _ast.List, _ast.Load, _ast.Store, _ast.Slice, _ast.Add, _ast.Sub, _ast.Mult, _ast.Div, _ast.FloorDiv,
+    _ast.Mod, _ast.Pow, _ast.USub, _ast.UAdd, _ast.Not, _ast.And, _ast.Or, _ast.Eq, _ast.NotEq, _ast.Lt, _ast.LtE, _ast.Gt, _ast.GtE,
+    _ast.FunctionDef, _ast.arguments, _ast.arg, _ast.Return, _ast.keyword, _ast.Global, _ast.Nonlocal, _ast.Raise)
+
+
+def _checked(src, mode, what):
+    tree = _ast.parse(src, what, mode)
+    for node in _ast.walk(tree):
+        if not isinstance(node, _ALLOWED_NODES):
+            raise ValueError(f"{what}: refusing to evaluate reference-derived source containing {type(node).__name__}")
+        if isinstance(node, _ast.Name) and node.id.startswith("_"):
+            raise ValueError(f"{what}: refusing the name {node.id!r}")
+        if isinstance(node, _ast.Call) and not isinstance(node.func, _ast.Name):
+            raise ValueError(f"{what}: only calls to plain names are allowed")
+    return compile(tree, what, mode)
+
+
+# the only builtins translated source gets: pure functions and the exception the translation of `stop` raises
+_SAFE_BUILTINS = {"dict": dict, "range": range, "abs": abs, "min": min, "max": max, "float": float, "int": int, "len": len,
+                  "RuntimeError": RuntimeError}
+
+
+def safe_eval(expr, ns=None, what="<reference expression>"):
+    ns = ns if ns is not None else {}
+    ns.setdefault("__builtins__", dict(_SAFE_BUILTINS))
+    return eval(_checked(expr.strip(), "eval", what), ns)
+
+
+def safe_compile(src, what="<reference source>"):
+    """checked once, executed many times (safe_exec accepts the result)"""
+    return _checked(src, "exec", what)
+
+
+def safe_exec(src, ns, what="<reference source>"):
+    ns.setdefault("__builtins__", dict(_SAFE_BUILTINS))
+    exec(_checked(src, "exec", what) if isinstance(src, str) else src, ns)
+
+
+
 def _logical_lines(text):
     out, cur = [], ""
     for raw in text.splitlines():
@@ -127,10 +176,10 @@ def _powers(s):
         m = re.match(r"\s*(\d+\.?\d*|\(.*?\))", s[k + 2:])
         expo = m.group(1)
         rest = s[k + 2 + m.end():]
-        if float(eval(expo)) == 2.0:
+        if float(safe_eval(expo)) == 2.0:
             s = left[:o] + f"square__({base})" + rest
         else:
-            s = left[:o] + f"pow({base}, {float(eval(expo))})" + rest
+            s = left[:o] + f"pow({base}, {float(safe_eval(expo))})" + rest
     return s
 
 
@@ -226,7 +275,7 @@ def run(py_src, cell_in=None, field_in=None, scalars=None, local_arrays=(), cell
         ns.setdefault(name.lower() + "__", _Arr())
     for name, val in (scalars or {}).items():
         ns[name.lower()] = val
-    exec(compile(py_src, "<reference loop body>", "exec"), ns)
+    safe_exec(py_src, ns, "<reference loop body>")
     out = {}
     for name in cell_out:
         a = ns[name.lower() + "__"]

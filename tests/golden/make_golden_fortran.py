@@ -42,7 +42,7 @@ def eval_parameters(text, known=None):
         rhs = rhs.replace("dsqrt", "sqrt").replace("dble", "float")
         for item in fe._split_args(rhs):
             name, expr = item.split("=", 1)
-            ns[name.strip()] = eval(expr, ns)
+            ns[name.strip()] = fe.safe_eval(expr, ns)
     return {k: v for k, v in ns.items() if isinstance(v, (int, float))}
 
 

@@ -38,7 +38,7 @@ def eval_parameters(text):
         rhs = fe._expr(fe._numbers(line.split("::", 1)[1]), ([], [], [], []))
         for item in fe._split_args(rhs):
             name, expr = item.split("=", 1)
-            ns[name.strip()] = eval(expr, ns)
+            ns[name.strip()] = fe.safe_eval(expr, ns)
     return {k: v for k, v in ns.items() if isinstance(v, (int, float))}
 
 

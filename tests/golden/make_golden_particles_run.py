@@ -70,7 +70,7 @@ def main():
         "refill": tr("particle_update.F90", 126, 203), "check": tr("fluid.F90", 195, 209),
     }
     calq_src = fe.translate(fe.read_lines(P4 + "/particle_bounceback.F90", 112, 139), full_arrays=["xcenter", "ycenter", "radius", "ex", "ey"])
-    calq_code = compile(calq_src, "<calQ>", "exec")
+    calq_code = fe.safe_compile(calq_src, "<calQ>")
 
     zeros = lambda keys: fe._Arr({k: 0.0 for k in keys})
     cells = [(i, j) for i in range(1, nx + 1) for j in range(1, ny + 1)]
@@ -97,7 +97,7 @@ def main():
         ns = {"sqrt": math.sqrt, "abs": abs, "float": float, "int": int, "range": range, **fn, "epsradius": sc["epsradius"],
               "xcenter__": st["xcenter"], "ycenter__": st["ycenter"], "radius__": st["radius"], "ex__": st["ex"], "ey__": st["ey"],
               "cnum": cnum, "i": i, "j": j, "alpha": alpha}
-        exec(calq_code, ns)
+        fe.safe_exec(calq_code, ns, "<calQ>")
         return ns["x0"], ns["y0"], ns["q"]
 
     def call(sub, **scalars):
@@ -107,7 +107,7 @@ def main():
         ns.update(scalars)
         for k in names:
             ns[k + "__"] = st[k]
-        exec(compile(src[sub], "<" + sub + ">", "exec"), ns)
+        fe.safe_exec(src[sub], ns, "<" + sub + ">")
         for k in names:
             st[k] = ns[k + "__"]
         return ns

@@ -97,7 +97,7 @@ def run_full(src, arrays, scalars):
     ns.update(scalars)
     for k, v in arrays.items():
         ns[k + "__"] = v
-    exec(compile(src, "<reference subroutine>", "exec"), ns)
+    fe.safe_exec(src, ns, "<reference subroutine>")
     return ns
 
 
