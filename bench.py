@@ -40,9 +40,10 @@ BYTES_PER_CELL = 304          # D3Q19 fp64 pull scheme: 19 x 8 B read + 19 x 8 B
 BYTES_PER_CELL_THERMAL = 464  # (19 + 7) x 16 B + the carried force Fx,Fy,Fz in and out (48 B); SURVEY 8d quotes 416 without it
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 HALO_NAMES = {"direct": "fused kernel stores outgoing populations into the neighbours' halos over NVLink (CUDA IPC) + flag barrier",
+              "push": "plain fused kernel, then one launch that copies the outgoing populations into the neighbours' halos over NVLink (CUDA IPC) + flag barrier",
               "overlap": "NCCL send/recv on a second stream, overlapped with the interior update",
               "blocking": "NCCL send/recv, blocking before the update"}
-HALO_MODE = {"direct": 2, "overlap": 1, "blocking": 0}
+HALO_MODE = {"direct": 2, "push": 3, "overlap": 1, "blocking": 0}
 
 
 def parse_args():
@@ -52,7 +53,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="mglc", choices=["mglc", "reference"])
     p.add_argument("--no-overlap", action="store_true", help="same as --halo blocking")
-    p.add_argument("--halo", default="auto", choices=["auto", "direct", "overlap", "blocking"],
+    p.add_argument("--halo", default="auto", choices=["auto", "direct", "push", "overlap", "blocking"],
                    help="multi-GPU halo transport of the fused step: direct = stores into the neighbours' halos over NVLink "
                         "(CUDA IPC), overlap = NCCL exchange beside the interior update, blocking = NCCL exchange, then update; "
                         "auto = direct when the mappings came up, else overlap")
@@ -340,7 +341,7 @@ def run_parity(D, comm, thermal_too=True):
     if thermal_too:
         flat["thermal_27x25x23_10_steps"] = out["thermal"]
     # the headline keys the driver's record is read for
-    for name, key in (("direct", "direct"), ("nccl_overlap", "nccl_overlap"), ("nccl_blocking", "nccl_blocking")):
+    for name, key in (("direct", "direct"), ("push", "push"), ("nccl_overlap", "nccl_overlap"), ("nccl_blocking", "nccl_blocking")):
         verdicts = [v[key] for v in out.values() if key in v]
         flat[name] = "MISMATCH" if "MISMATCH" in verdicts else ("unavailable" if "unavailable" in verdicts else "bit-exact")
     return flat, bad
@@ -469,8 +470,8 @@ def main():
     transports = None
     if world > 1 and not args.no_extras and not args.dims:
         transports = {args.halo: {"value": round(value, 1), "ms_per_step": round(ms / args.steps, 4)}}
-        for name in ("direct", "blocking", "overlap"):
-            if name == args.halo or (name == "direct" and not avail.value):
+        for name in ("direct", "push", "blocking", "overlap"):
+            if name == args.halo or (name in ("direct", "push") and not avail.value):
                 continue
             L.check(lib.mglc_lbm_set_overlap(sub._h, HALO_MODE[name]))
             sim.step(3); sim.sync()

@@ -32,6 +32,8 @@ module mglc_iso_c
         integer(c_int) :: total_nx, total_ny, nparticles, reserved
         real(c_double) :: rho0, rhoSolid, viscosity, radius0, gravity
         real(c_double) :: thresholdWall, stiffWall, thresholdParticle, stiffParticle
+        real(c_double) :: Uwall, Uframe            ! case1/mpi_complete options: moving walls (fluid.F90:123-171); 0 = case4
+        integer(c_int) :: bb_linear, moving_walls  ! linear-interpolated bounce-back (particle_bounceback.F90:66-76)
     end type mglc_p2d_desc
     !> mglc_l2d_desc: module commondata of the 2-D lid driver (Lid_driven_cavity/fortran/2d/2d_revised/mpi_blocked/commondata.f90:4-9)
     type, bind(C) :: mglc_l2d_desc

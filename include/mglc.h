@@ -208,7 +208,10 @@ int mglc_lbm_set_profiling(mglc_lbm *h, int on);
  *      interior update, the schedule of collision_with_message_exchange, lid3_mpi_nonblock.f90:1108-1230.
  *      Default otherwise.
  *   0  blocking exchange, then update: message_passing_sendrecv() as the blocking driver does it, L3/main.f90:89-93.
- * With mode 2 every call that leaves the fused loop (upload, download, the per-subroutine entry points) must be made
+ *   3  halo push: the plain fused kernel, then ONE small launch that copies every outgoing message (same sets) from the
+ *      boundary cells straight into the neighbours' halo cells over the same mappings as mode 2 -- no send buffers, no NCCL,
+ *      no unpack, and no message code inside the update kernel.
+ * With modes 2 and 3 every call that leaves the fused loop (upload, download, the per-subroutine entry points) must be made
  * by all ranks between the same two mglc_lbm_step calls, like the reference's subroutines; a rank out of step is
  * reported by mglc_lbm_sync / mglc_check as MGLC_E_STATE instead of hanging. */
 int mglc_lbm_set_overlap(mglc_lbm *h, int mode);
@@ -297,6 +300,12 @@ typedef struct mglc_p2d_desc {           /* module commondata, P4/commondata.F90
     double radius0;                      /* 10                                             */
     double gravity;                      /* 980 * t0^2 / l0                                */
     double thresholdWall, stiffWall, thresholdParticle, stiffParticle;
+    /* options taken from the reference's other particle scenario, MPI/Micro_particles/fortran/case1/mpi_complete; all 0 (as
+     * mglc_p2d_desc_init leaves them) = case4 */
+    double Uwall;                        /* top wall moves with +Uwall, bottom wall with -Uwall (case1/.../fluid.F90:123-171)   */
+    double Uframe;                       /* U0 of the `movingFrame` build of that file; 0 = `stationaryFrame`                     */
+    int bb_linear;                       /* 1: linear-interpolated bounce-back (case1/.../particle_bounceback.F90:66-76)         */
+    int moving_walls;                    /* 1: apply the moving-wall terms                                                       */
 } mglc_p2d_desc;
 int mglc_p2d_desc_init(mglc_p2d_desc *d, int nparticles);            /* the shipped constants */
 /* MPI_Dims_create_2d -- P4/mpi_starts.F90:160-180 (smallest halo message wins) */

@@ -43,7 +43,8 @@ class HaloMsg(C.Structure):
 class P2dDesc(C.Structure):
     _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("nparticles", C.c_int), ("reserved", C.c_int)] + \
                [(n, C.c_double) for n in ("rho0", "rhoSolid", "viscosity", "radius0", "gravity", "thresholdWall", "stiffWall",
-                                          "thresholdParticle", "stiffParticle")]
+                                          "thresholdParticle", "stiffParticle", "Uwall", "Uframe")] + \
+               [("bb_linear", C.c_int), ("moving_walls", C.c_int)]
 
 
 class L2dDesc(C.Structure):

@@ -738,7 +738,11 @@ static int do_fused_direct(mglc_lbm *h) {
     FusedIO io;
     MGLC_TRY(fused_begin(h, io));
     const PeerTable *pt = h->pt_dev[h->cur];                 // io.Fout == buf[cur]: the neighbours write the same parity
-    if (h->thermal)
+    if (h->overlap == 3) {
+        // push after: the plain fused kernel, then one small launch that copies the messages into the neighbours' halos
+        MGLC_TRY(launch_fused_box(h, io, box));
+        h->launches += launch_push_halos(h->g, pt, io.Fout, h->thermal ? io.Gout : nullptr, h->s);
+    } else if (h->thermal)
         h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt)
                                   : fast::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt);
     else
@@ -1023,7 +1027,7 @@ static int step_impl(mglc_lbm *h, int nsteps) {
         MGLC_TRY(do_collision(h));
         if (h->thermal) MGLC_TRY(do_collisionT(h));
     }
-    const bool direct = h->overlap == 2 && h->direct && h->has_neighbors && h->comm;
+    const bool direct = (h->overlap == 2 || h->overlap == 3) && h->direct && h->has_neighbors && h->comm;
     const bool overlapped = h->overlap == 1 && h->has_neighbors && h->comm;
     for (int it = 0; it < nsteps; ++it) {
         if (h->direct_valid) MGLC_TRY(wait_direct(h));            // the neighbours' launches stored the halos of step it
@@ -1060,8 +1064,8 @@ extern "C" int mglc_lbm_step_timed(mglc_lbm *h, int nsteps, float *ms) {
 extern "C" int mglc_lbm_set_overlap(mglc_lbm *h, int on) {
     MGLC_TRY(use(h));
     MGLC_TRY(canonicalise(h));
-    if (on < 0 || on > 2) { set_error("mglc_lbm_set_overlap: mode %d (0 blocking, 1 overlapped exchange, 2 direct halo stores)", on); return MGLC_E_INVALID; }
-    if (on == 2 && !h->direct && h->has_neighbors) { set_error("mglc_lbm_set_overlap: the neighbours' lattices are not mapped on this GPU"); return MGLC_E_STATE; }
+    if (on < 0 || on > 3) { set_error("mglc_lbm_set_overlap: mode %d (0 blocking, 1 overlapped exchange, 2 direct halo stores, 3 halo push after the update)", on); return MGLC_E_INVALID; }
+    if (on >= 2 && !h->direct && h->has_neighbors) { set_error("mglc_lbm_set_overlap: the neighbours' lattices are not mapped on this GPU"); return MGLC_E_STATE; }
     h->overlap = on;
     return MGLC_OK;
 }
@@ -1261,7 +1265,7 @@ static int group_step_impl(mglc_group *g, int nsteps) {
         MGLC_TRY(use(h));
         if (!h->rotated) { MGLC_TRY(do_collision(h)); if (h->thermal) MGLC_TRY(do_collisionT(h)); }
     }
-    const bool direct = g->r[0]->direct && g->r[0]->overlap == 2 && g->r.size() > 1;
+    const bool direct = g->r[0]->direct && g->r[0]->overlap >= 2 && g->r.size() > 1;
     for (int it = 0; it < nsteps; ++it) {
         bool all_valid = true;
         FOR_RANKS(g, h) all_valid = all_valid && h->direct_valid;

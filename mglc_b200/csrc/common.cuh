@@ -172,6 +172,7 @@ int launch_nure(const Geom &g, const double *u, const double *v, const double *w
 // one launch that packs (or unpacks) every message of an exchange: dir 0..18 = f messages, 20 + face = g messages
 struct MsgBatch { int n; int dir[24]; double *buf[24]; };
 int launch_pack_all(const Geom &g, const MsgBatch &mb, double *Fpost, double *Gpost, bool unpack, cudaStream_t s);
+int launch_push_halos(const Geom &g, const PeerTable *pt_dev, const double *F, const double *G, cudaStream_t s);
 int launch_fill(double *p, long long n, double value, cudaStream_t s);
 int launch_halo_signal(const SyncTable &t, unsigned long long epoch, cudaStream_t s);
 int launch_halo_wait(const SyncTable &t, unsigned long long epoch, int *err, cudaStream_t s);

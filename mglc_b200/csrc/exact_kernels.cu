@@ -266,6 +266,43 @@ int launch_pack_all(const Geom &g, const MsgBatch &mb, double *Fpost, double *Gp
     return 1;
 }
 
+// ---- halo push (transport 3): after a fused launch WITHOUT in-kernel peer stores, one launch copies the outgoing
+// populations of every face / edge message (the sets of ex_sendrecv.f90:12-123, + the g population per face for thermal
+// lattices) from this subdomain's boundary cells straight into the neighbours' halo cells over NVLink.  No send buffer, no
+// NCCL, no unpack; the neighbour barrier (k_halo_signal / k_halo_wait) orders it like the in-kernel stores.
+__global__ void k_push_halos(Geom g, const PeerTable *__restrict__ pt, const double *__restrict__ F, const double *__restrict__ G) {
+    const int m = blockIdx.y;                       // 0..18: f message in direction m (6 = none); 19..24: g message of face m - 19
+    const bool isg = m >= 19;
+    const int d = isg ? m - 19 : m;
+    if (d == 6 || !(pt->mask >> d & 1u) || (isg && !G)) return;
+    if (pt->err && *pt->err) return;                // the barrier failed: nothing goes into a neighbour any more
+    int n1, n2, npop;
+    if (d < 6) { const int axis = d >> 1; n1 = (axis == 0) ? g.ny : g.nx; n2 = (axis == 2) ? g.ny : g.nz; npop = isg ? 1 : 5; }
+    else { n1 = (c_ex[d] == 0) ? g.nx : (c_ey[d] == 0 ? g.ny : g.nz); n2 = 1; npop = 1; }
+    const int e[3] = {d < 6 ? (d >> 1 == 0 ? 1 - 2 * (d & 1) : 0) : c_ex[d], d < 6 ? (d >> 1 == 1 ? 1 - 2 * (d & 1) : 0) : c_ey[d],
+                      d < 6 ? (d >> 1 == 2 ? 1 - 2 * (d & 1) : 0) : c_ez[d]};
+    const long long per = (long long)n1 * n2, psy = pt->sy[d], psz = pt->sz[d], psq = pt->sq[d];
+    double *P = isg ? pt->G[d] : pt->F[d];
+    const double *src = isg ? G : F;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per * npop; t += (long long)gridDim.x * blockDim.x) {
+        const int slot = (int)(t / per), r = (int)(t % per);
+        int i, j, k;
+        msg_cell(g, d, 0, r % n1, r / n1, i, j, k);
+        const int a = isg ? d + 1 : (d < 6 ? c_face_pops[d][slot] : d);
+        // the neighbour's halo cell: layer 0 / n'+1 along the axes the message crosses, my own index along the others
+        const int ii = e[0] > 0 ? 0 : (e[0] < 0 ? pt->n[d][0] + 1 : i);
+        const int jj = e[1] > 0 ? 0 : (e[1] < 0 ? pt->n[d][1] + 1 : j);
+        const int kk = e[2] > 0 ? 0 : (e[2] < 0 ? pt->n[d][2] + 1 : k);
+        P[a * psq + kk * psz + jj * psy + (ii + OX - 1)] = src[g.idx(a, i, j, k)];
+    }
+}
+int launch_push_halos(const Geom &g, const PeerTable *pt_dev, const double *F, const double *G, cudaStream_t s) {
+    const long long face = (long long)std::max(g.nx, g.ny) * std::max(g.ny, g.nz) * 5;
+    const dim3 grid((unsigned)std::min<long long>(512, (face + 255) / 256), G ? 25 : 19);
+    k_push_halos<<<grid, 256, 0, s>>>(g, pt_dev, F, G);
+    return 1;
+}
+
 // ---- AoS (reference: population index fastest) <-> SoA transposes ----------------------------------
 // A block moves TILE consecutive cells (linear reference order) through shared memory so that both the
 // AoS side (19*TILE contiguous doubles) and the SoA side (TILE contiguous cells per population) coalesce.

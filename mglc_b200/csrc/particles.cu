@@ -46,6 +46,9 @@ struct G2 {
 struct P2 {              // module commondata, P4/commondata.F90
     int N, total_nx, total_ny;
     double rho0, rhoSolid, Snu, Sq, gravity, thresholdWall, stiffWall, thresholdParticle, stiffParticle, radius0, Pi;
+    // options taken from the reference's other particle scenario (case1/mpi_complete, "P1"); all zero = P4
+    double Uwall, Uframe;        // moving top (+Uwall) / bottom (-Uwall) walls seen from a frame moving with Uframe, P1/fluid.F90:127-169
+    int bb_linear, moving_walls; // linear-interpolated bounce-back on the particles, P1/particle_bounceback.F90:66-76
 };
 
 // particle state, N doubles each, one device buffer
@@ -130,6 +133,25 @@ __device__ __forceinline__ int covered(const PB &b, const G2 &g, int N, const do
 #include "p2d_calq.inl"
 __device__ __forceinline__ int calQ(double xc, double yc, double rad, double i, double j, int alpha, double &x0, double &y0, double &q) {
     return calQ_link(xc, yc, rad, i, j, (double)c9x[alpha], (double)c9y[alpha], x0, y0, q);
+}
+
+// moving top / bottom walls, P1/fluid.F90:130-145 (with Uframe = 0: the `stationaryFrame` lines :151-168); fp5..fp8 = f_post of the node
+__device__ __forceinline__ void p1_moving_walls(const G2 &g, const P2 &p, int j, double fp5, double fp6, double fp7, double fp8, double (&f)[9]) {
+    if (g.wall[2] && j == 1) { f[5] = fp7 + (-p.Uwall - p.Uframe) / 6.0; f[6] = fp8 - (-p.Uwall - p.Uframe) / 6.0; }
+    if (g.wall[3] && j == g.ny) { f[7] = fp5 - (p.Uwall - p.Uframe) / 6.0; f[8] = fp6 + (p.Uwall - p.Uframe) / 6.0; }
+}
+// interpolated bounce-back of one link: quadratic (P4/particle_bounceback.F90:65-75) or linear (P1/particle_bounceback.F90:67-75).
+// fp0 = f_post(alpha, x), fp1 = f_post(alpha, x - e), fp2 = f_post(alpha, x - 2e), fr0 = f_post(r, x), fr1 = f_post(r, x - e); wall =
+// ex(r) (Uc + temp1) + ey(r) (Vc + temp2).  fp2 / fr1 are only read by the quadratic form (passed as pointers to stay lazy).
+__device__ __forceinline__ double pbb_value(int linear, double q, double omega, double rhoAvg, double fp0, double fp1, const double *fp2,
+                                            double fr0, const double *fr1, double wall) {
+    if (linear) {
+        if (q < 0.5) return 2.0 * q * fp0 + (1.0 - 2.0 * q) * fp1 + 6.0 * omega * rhoAvg * wall;
+        return 0.5 / q * fp0 + (1.0 - 0.50 / q) * fr0 + 3.0 * omega * rhoAvg / q * wall;
+    }
+    if (q < 0.5) return q * (1.0 + 2.0 * q) * fp0 + (1.0 - 4.0 * q * q) * fp1 - q * (1.0 - 2.0 * q) * (*fp2) + 6.0 * omega * rhoAvg * wall;
+    return fp0 / q / (1.0 + 2.0 * q) + fr0 * (2.0 * q - 1.0) / q - (*fr1) * (2.0 * q - 1.0) / (2.0 * q + 1.0)
+         + 6.0 * omega * rhoAvg / q / (1.0 + 2.0 * q) * wall;
 }
 
 __device__ __forceinline__ void d2q9_collide(const double (&f)[9], double rho, double u, double v, double Snu, double Sq, double (&fp)[9]) {
@@ -343,20 +365,10 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
     // streaming(), P4/fluid.F90:97-108: every interior node, skipped when the upstream node is solid
     if (in_range) {
         if (STAGES & ST_STREAM) {
-            // all nine upstream masks and populations are requested before any is used (the 3-node rim makes every address
-            // valid); a population whose upstream node is solid is then replaced by the node's old value -- rare, so that
-            // second load stays conditional
-            int ob[9];
-            double fu[9];
 #pragma unroll
             for (int a = 0; a < 9; ++a) {
                 const long long up_ = c - c9y[a] * (long long)g.px - c9x[a];
-                ob[a] = obst[up_];
-                fu[a] = Fp[a * g.sq + up_];
-            }
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                if (ob[a] == 0) { f[a] = fu[a]; F[a * g.sq + c] = f[a]; }
+                if (obst[up_] == 0) { f[a] = Fp[a * g.sq + up_]; F[a * g.sq + c] = f[a]; }
                 else f[a] = F[a * g.sq + c];
             }
         } else {
@@ -369,6 +381,8 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
             if (g.wall[1] && i == g.nx) { f[3] = Fp[1 * g.sq + c]; f[6] = Fp[8 * g.sq + c]; f[7] = Fp[5 * g.sq + c]; }
             if (g.wall[2] && j == 1) { f[2] = Fp[4 * g.sq + c]; f[5] = Fp[7 * g.sq + c]; f[6] = Fp[8 * g.sq + c]; }
             if (g.wall[3] && j == g.ny) { f[4] = Fp[2 * g.sq + c]; f[7] = Fp[5 * g.sq + c]; f[8] = Fp[6 * g.sq + c]; }
+            if (p.moving_walls && ((g.wall[2] && j == 1) || (g.wall[3] && j == g.ny)))
+                p1_moving_walls(g, p, j, Fp[5 * g.sq + c], Fp[6 * g.sq + c], Fp[7 * g.sq + c], Fp[8 * g.sq + c], f);
             if ((g.wall[0] && i == 1) || (g.wall[1] && i == g.nx) || (g.wall[2] && j == 1) || (g.wall[3] && j == g.ny)) {
 #pragma unroll
                 for (int a = 1; a < 9; ++a) F[a * g.sq + c] = f[a];
@@ -399,16 +413,9 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
                     const double omega = a < 5 ? 1.0 / 9.0 : 1.0 / 36.0;
                     const double fp0 = Fp[a * g.sq + c];
                     const long long c1 = c - c9y[a] * (long long)g.px - c9x[a];
-                    double val;
-                    if (q < 0.5) {
-                        const long long c2 = c1 - c9y[a] * (long long)g.px - c9x[a];
-                        val = q * (1.0 + 2.0 * q) * fp0 + (1.0 - 4.0 * q * q) * Fp[a * g.sq + c1] - q * (1.0 - 2.0 * q) * Fp[a * g.sq + c2]
-                            + 6.0 * omega * rhoAvg * (exr * (Uc + temp1) + eyr * (Vc + temp2));
-                    } else {
-                        val = fp0 / q / (1.0 + 2.0 * q) + Fp[ra * g.sq + c] * (2.0 * q - 1.0) / q
-                            - Fp[ra * g.sq + c1] * (2.0 * q - 1.0) / (2.0 * q + 1.0)
-                            + 6.0 * omega * rhoAvg / q / (1.0 + 2.0 * q) * (exr * (Uc + temp1) + eyr * (Vc + temp2));
-                    }
+                    const long long c2 = c1 - c9y[a] * (long long)g.px - c9x[a];
+                    const double val = pbb_value(p.bb_linear, q, omega, rhoAvg, fp0, Fp[a * g.sq + c1], Fp + (a * g.sq + c2), Fp[ra * g.sq + c],
+                                                 Fp + (ra * g.sq + c1), exr * (Uc + temp1) + eyr * (Vc + temp2));
                     f[ra] = val;
                     F[ra * g.sq + c] = val;
                 }
@@ -489,6 +496,51 @@ __global__ void __launch_bounds__(128) k_p_update(G2 g, P2 p, const double *__re
 }
 
 
+// ---- fused step: the node pass (streaming + bounceback + macro + link count) laid out for bandwidth ------------------
+// Same result as k_p_update<STREAM | WALLBB | MACRO | COUNT>, node for node and bit for bit.  The nine masks around the node
+// are loaded once (the upstream node of population a is the downstream node of its opposite, so they also give the link
+// count), then the nine populations are loaded in one batch through selected addresses: f_post of the upstream node, or --
+// where that node is solid and streaming() leaves f untouched (P4/fluid.F90:97-108) -- the node's own old f.  No load waits
+// for a mask test in between, and every population is stored (an untouched one is stored back unchanged).
+__global__ void __launch_bounds__(128) k_p_node(G2 g, P2 p, const double *Fp, double *F, const int *__restrict__ obst, double *__restrict__ rho,
+                                                double *__restrict__ u, double *__restrict__ v, int *__restrict__ nlinks) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+    if (i > g.nx) return;
+    const long long c = g.idx(0, i, j);
+    int ob[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) ob[a] = obst[c - c9y[a] * (long long)g.px - c9x[a]];
+    const bool fluid = ob[0] == 0;
+    int nl = 0;
+    if (fluid) {
+#pragma unroll
+        for (int a = 1; a < 9; ++a) nl += ob[c9r[a]] == 1;          // obst(x + e_a) = the upstream mask of the opposite direction
+    }
+    nlinks[g.cell(i, j)] = nl;
+    double f[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        const double *src = ob[a] == 0 ? Fp + (a * g.sq + c - c9y[a] * (long long)g.px - c9x[a]) : F + (a * g.sq + c);
+        f[a] = *src;
+    }
+    // bounceback(), P4/fluid.F90:115-161 (left, right, bottom, top: later walls overwrite the corners)
+    if (g.wall[0] && i == 1) { f[1] = Fp[3 * g.sq + c]; f[5] = Fp[7 * g.sq + c]; f[8] = Fp[6 * g.sq + c]; }
+    if (g.wall[1] && i == g.nx) { f[3] = Fp[1 * g.sq + c]; f[6] = Fp[8 * g.sq + c]; f[7] = Fp[5 * g.sq + c]; }
+    if (g.wall[2] && j == 1) { f[2] = Fp[4 * g.sq + c]; f[5] = Fp[7 * g.sq + c]; f[6] = Fp[8 * g.sq + c]; }
+    if (g.wall[3] && j == g.ny) { f[4] = Fp[2 * g.sq + c]; f[7] = Fp[5 * g.sq + c]; f[8] = Fp[6 * g.sq + c]; }
+    if (p.moving_walls && ((g.wall[2] && j == 1) || (g.wall[3] && j == g.ny)))
+        p1_moving_walls(g, p, j, Fp[5 * g.sq + c], Fp[6 * g.sq + c], Fp[7 * g.sq + c], Fp[8 * g.sq + c], f);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) F[a * g.sq + c] = f[a];
+    if (fluid) {                                                     // macro(), P4/fluid.F90:164-184
+        const double r = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
+        const long long m = g.cell(i, j);
+        rho[m] = r;
+        u[m] = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / r;
+        v[m] = (f[2] - f[4] + f[5] + f[6] - f[7] - f[8]) / r;
+    }
+}
+
 // ---- fused step: bounceback_particle() + the link sums of calForce(), one block per particle ------------------------
 // The node kernel (k_p_update<STREAM|WALLBB|MACRO|COUNT>) leaves in nlinks the number of links of every fluid node that
 // end in a solid node.  Here block cn scans the bounding box of particle cn for those links (fluid node -> node inside
@@ -534,16 +586,9 @@ __global__ void __launch_bounds__(LK_T) k_p_links(G2 g, P2 p, const double *__re
             const double omega = a < 5 ? 1.0 / 9.0 : 1.0 / 36.0;
             const double fp0 = Fp[a * g.sq + c];
             const long long c1 = c - c9y[a] * (long long)g.px - c9x[a];
-            double val;
-            if (q < 0.5) {                       // P4/particle_bounceback.F90:66-69
-                const long long c2 = c1 - c9y[a] * (long long)g.px - c9x[a];
-                val = q * (1.0 + 2.0 * q) * fp0 + (1.0 - 4.0 * q * q) * Fp[a * g.sq + c1] - q * (1.0 - 2.0 * q) * Fp[a * g.sq + c2]
-                    + 6.0 * omega * rhoAvg * (exr * (Uc + temp1) + eyr * (Vc + temp2));
-            } else {                             // :71-74
-                val = fp0 / q / (1.0 + 2.0 * q) + Fp[ra * g.sq + c] * (2.0 * q - 1.0) / q
-                    - Fp[ra * g.sq + c1] * (2.0 * q - 1.0) / (2.0 * q + 1.0)
-                    + 6.0 * omega * rhoAvg / q / (1.0 + 2.0 * q) * (exr * (Uc + temp1) + eyr * (Vc + temp2));
-            }
+            const long long c2 = c1 - c9y[a] * (long long)g.px - c9x[a];
+            const double val = pbb_value(p.bb_linear, q, omega, rhoAvg, fp0, Fp[a * g.sq + c1], Fp + (a * g.sq + c2), Fp[ra * g.sq + c],
+                                         Fp + (ra * g.sq + c1), exr * (Uc + temp1) + eyr * (Vc + temp2));
             F[ra * g.sq + c] = val;
             // momentum exchange over the link, P4/particle_force.F90:60-62, with the node's final f(r(alpha)) = val
             const double tfx = ((double)c9x[a] - Uc - temp1) * fp0 - (exr - Uc - temp1) * val;
@@ -1201,6 +1246,7 @@ static int p_new(mglc_p2d **out, const mglc_p2d_desc *d, const int dims_or_zero[
     p.N = d->nparticles; p.total_nx = d->total_nx; p.total_ny = d->total_ny;
     p.rho0 = d->rho0; p.rhoSolid = d->rhoSolid; p.gravity = d->gravity; p.thresholdWall = d->thresholdWall; p.stiffWall = d->stiffWall;
     p.thresholdParticle = d->thresholdParticle; p.stiffParticle = d->stiffParticle; p.radius0 = d->radius0;
+    p.Uwall = d->Uwall; p.Uframe = d->Uframe; p.bb_linear = d->bb_linear != 0; p.moving_walls = d->moving_walls != 0;
     p.Pi = 4.0 * atan(1.0);                                          // P4/commondata.F90:3
     const double tauf = 3.0 * d->viscosity + 0.5;                    // :33-34
     p.Snu = 1.0 / tauf;
@@ -1684,8 +1730,11 @@ static int p_enqueue_step(mglc_p2d *h) {
     MGLC_TRY(p_reduce_part(h));
     P_EACH(h, S) {
         MGLC_TRY(p_use(S));
-        k_p_update<ST_STREAM | ST_WALLBB | ST_MACRO | ST_COUNT><<<grid_int(S), 128, 0, S->s>>>(
-            S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->part, S->err, S->nlinks);
+        static const bool generic_node_kernel = getenv("MGLC_P2D_NODE") && atoi(getenv("MGLC_P2D_NODE")) == 0;      // A/B runs
+        if (generic_node_kernel)
+            k_p_update<ST_STREAM | ST_WALLBB | ST_MACRO | ST_COUNT><<<grid_int(S), 128, 0, S->s>>>(
+                S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->part, S->err, S->nlinks);
+        else k_p_node<<<grid_int(S), 128, 0, S->s>>>(S->g, h->p, S->Fp, S->F, S->obst, S->rho, S->u, S->v, S->nlinks);
         S->launches += 1;
         if (N) {
             k_p_links<<<N, LK_T, 0, S->s>>>(S->g, h->p, S->ps, S->ps, S->Fp, S->F, S->obst, S->nlinks, S->rho, S->u, S->v, S->part, S->err);

@@ -408,7 +408,8 @@ for _name, _sub in (("initial", "th_initial"), ("collision", "th_collision"), ("
 class P2Params(C.Structure):
     _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("N", C.c_int)] + \
                [(n, C.c_double) for n in ("rho0", "rhoSolid", "viscosity", "tauf", "Snu", "Sq", "gravity", "thresholdWall",
-                                          "stiffWall", "thresholdParticle", "stiffParticle", "radius0", "Pi")]
+                                          "stiffWall", "thresholdParticle", "stiffParticle", "radius0", "Pi", "Uwall", "Uframe")] + \
+               [("bb_linear", C.c_int), ("moving_walls", C.c_int)]
 
 
 P2_FIELDS = {"f": 0, "f_post": 1, "rho": 2, "u": 3, "v": 4, "up": 5, "vp": 6}

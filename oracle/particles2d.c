@@ -33,6 +33,11 @@ typedef struct p2_params {
     int total_nx, total_ny, N;
     double rho0, rhoSolid, viscosity, tauf, Snu, Sq, gravity, thresholdWall, stiffWall, thresholdParticle,
            stiffParticle, radius0, Pi;
+    /* options of the reference's other particle scenario, MPI/Micro_particles/fortran/case1/mpi_complete ("P1"): 0 / 0.0 = P4 */
+    double Uwall;        /* top wall moves with +Uwall, bottom wall with -Uwall along x (P1/fluid.F90:123-171)          */
+    double Uframe;       /* U0 of the `movingFrame` build: the walls' velocities are seen from a frame moving with U0    */
+    int bb_linear;       /* 1: linear-interpolated bounce-back on the particles (`#ifdef linear`, P1/particle_bounceback.F90:66-76) */
+    int moving_walls;    /* 1: apply the wall terms above                                                                 */
 } p2_params;
 
 typedef struct p2_rank {
@@ -69,6 +74,7 @@ void p2_default_params(p2_params *p) {
     p->tauf = 3.0 * p->viscosity + 0.5;
     p->Snu = 1.0 / p->tauf;
     p->Sq = 8.0 * (2.0 * p->tauf - 1.0) / (8.0 * p->tauf - 1.0);
+    p->Uwall = 0.0; p->Uframe = 0.0; p->bb_linear = 0; p->moving_walls = 0;
 }
 
 /* MPI_Dims_create_2d, P4/mpi_starts.F90:160-180: the factorisation with the smallest halo message, in
@@ -331,6 +337,21 @@ void p2_bounceback(p2_world *w) {
             for (int i = 1; i <= nx; ++i) { FI(R, 2, i, 1) = FP(R, 4, i, 1); FI(R, 5, i, 1) = FP(R, 7, i, 1); FI(R, 6, i, 1) = FP(R, 8, i, 1); }
         if (R->coords[1] == w->dims[1] - 1)
             for (int i = 1; i <= nx; ++i) { FI(R, 4, i, ny) = FP(R, 2, i, ny); FI(R, 7, i, ny) = FP(R, 5, i, ny); FI(R, 8, i, ny) = FP(R, 6, i, ny); }
+        if (w->p.moving_walls) {
+            /* moving top / bottom walls, P1/fluid.F90:127-145 (`movingFrame`; with U0 = 0 these are the `stationaryFrame` lines
+             * :149-167 bit for bit, since -Uwall - 0 = -Uwall) */
+            const double Uw = w->p.Uwall, U0 = w->p.Uframe;
+            if (R->coords[1] == 0)
+                for (int i = 1; i <= nx; ++i) {
+                    FI(R, 5, i, 1) = FP(R, 7, i, 1) + (-Uw - U0) / 6.0;
+                    FI(R, 6, i, 1) = FP(R, 8, i, 1) - (-Uw - U0) / 6.0;
+                }
+            if (R->coords[1] == w->dims[1] - 1)
+                for (int i = 1; i <= nx; ++i) {
+                    FI(R, 7, i, ny) = FP(R, 5, i, ny) - (Uw - U0) / 6.0;
+                    FI(R, 8, i, ny) = FP(R, 6, i, ny) + (Uw - U0) / 6.0;
+                }
+        }
     }
 }
 
@@ -382,6 +403,18 @@ void p2_bb_link(p2_world *w, p2_rank *R, int i, int j, int alpha, int c) {
     const double temp2 = (x0 - w->xCenter[c]) * w->rOmega[c];
     const int ra = rr[alpha];
     const double Uc = w->Uc[c], Vc = w->Vc[c], rhoAvg = w->rhoAvg, om = w->omega[alpha];
+    if (w->p.bb_linear) {                        /* P1/particle_bounceback.F90:66-76 */
+        if (q < 0.5) {
+            FI(R, ra, i, j) = 2.0 * q * FP(R, alpha, i, j)
+                            + (1.0 - 2.0 * q) * FP(R, alpha, i - ex[alpha], j - ey[alpha])
+                            + 6.0 * om * rhoAvg * (ex[ra] * (Uc + temp1) + ey[ra] * (Vc + temp2));
+        } else if (q >= 0.5) {
+            FI(R, ra, i, j) = 0.5 / q * FP(R, alpha, i, j)
+                            + (1.0 - 0.50 / q) * FP(R, ra, i, j)
+                            + 3.0 * om * rhoAvg / q * (ex[ra] * (Uc + temp1) + ey[ra] * (Vc + temp2));
+        }
+        return;
+    }
     if (q < 0.5) {
         FI(R, ra, i, j) = q * (1.0 + 2.0 * q) * FP(R, alpha, i, j)
                         + (1.0 - 4.0 * q * q) * FP(R, alpha, i - ex[alpha], j - ey[alpha])

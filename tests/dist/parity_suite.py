@@ -5,8 +5,9 @@ Every rank steps its own subdomain through libmglc.so in STRICT arithmetic; rank
 the single-rank CPU oracle (test infrastructure: the oracle is the checker here, never the thing measured).  The verdict of a
 case is "bit-exact", "MISMATCH" or "unavailable" (direct halo stores need the CUDA IPC mappings of an NVLink box).
 
-Transports of the fused step (mglc_lbm_set_overlap): 2 = direct stores into the neighbours' halos, 1 = overlapped NCCL
-exchange (lid3_mpi_nonblock.f90:1108-1230), 0 = blocking NCCL exchange (L3/ex_sendrecv.f90:12-123)."""
+Transports of the fused step (mglc_lbm_set_overlap): 2 = direct stores into the neighbours' halos from inside the update
+kernel, 3 = the same stores from one small launch after it ("push"), 1 = overlapped NCCL exchange
+(lid3_mpi_nonblock.f90:1108-1230), 0 = blocking NCCL exchange (L3/ex_sendrecv.f90:12-123)."""
 import ctypes as C
 import os
 
@@ -16,7 +17,7 @@ import torch.distributed as dist
 import mglc_b200 as mg
 from mglc_b200 import _lib as L
 
-TRANSPORTS = {"direct": 2, "nccl_overlap": 1, "nccl_blocking": 0}
+TRANSPORTS = {"direct": 2, "push": 3, "nccl_overlap": 1, "nccl_blocking": 0}
 
 
 def gather_blocks(block, rank, world):
@@ -45,7 +46,7 @@ def _direct_available(sim):
     return bool(avail.value)
 
 
-def lid(comm, rank, world, total=(41, 37, 35), nsteps=12, transports=("direct", "nccl_overlap", "nccl_blocking"),
+def lid(comm, rank, world, total=(41, 37, 35), nsteps=12, transports=("direct", "push", "nccl_overlap", "nccl_blocking"),
         reinit=True, log=None):
     """3-D lid-driven cavity, uneven blocks.  Per transport: step(5); step(n-5) (the rotated state carries the in-flight halos
     across the two calls) and, with reinit, step(3); initial(); step(n) (stale halo state after re-initialising)."""
@@ -60,7 +61,7 @@ def lid(comm, rank, world, total=(41, 37, 35), nsteps=12, transports=("direct", 
         wd.close()
     for name in transports:
         sim = mg.LidDrivenCavity(total, comm=comm, arith="strict")
-        if name == "direct" and not _direct_available(sim):
+        if name in ("direct", "push") and not _direct_available(sim):
             out[name] = "unavailable"
             sim.close()
             continue
@@ -94,7 +95,7 @@ def lid(comm, rank, world, total=(41, 37, 35), nsteps=12, transports=("direct", 
     return out
 
 
-def thermal(comm, rank, world, total=(27, 25, 23), nsteps=10, transports=("direct", "nccl_overlap", "nccl_blocking"), log=None):
+def thermal(comm, rank, world, total=(27, 25, 23), nsteps=10, transports=("direct", "push", "nccl_overlap", "nccl_blocking"), log=None):
     """3-D thermal cavity (f + g exchange), uneven blocks"""
     out = {}
     ref = None
@@ -106,7 +107,7 @@ def thermal(comm, rank, world, total=(27, 25, 23), nsteps=10, transports=("direc
         wd.close()
     for name in transports:
         sim = mg.BuoyancyDrivenCavity(total, comm=comm, arith="strict")
-        if name == "direct" and not _direct_available(sim):
+        if name in ("direct", "push") and not _direct_available(sim):
             out[name] = "unavailable"
             sim.close()
             continue

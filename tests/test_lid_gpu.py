@@ -351,6 +351,25 @@ def test_direct_halo_stores_equal_packed_exchange(nprocs, dims, monkeypatch):
     wd.close()
 
 
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (8, None), (12, None), (3, (1, 3, 1))])
+def test_halo_push_after_the_update_equals_the_oracle(nprocs, dims):
+    """Transport 3: the plain fused kernel followed by one launch that copies every outgoing face / edge message straight into the
+    neighbours' halo cells.  Strict arithmetic: bit-identical to the 1-rank oracle, f_post halos included in what the next step
+    reads, across two step() calls and a re-initialisation."""
+    total, nsteps = (23, 19, 17), 9
+    sim = gpu_world(total, nprocs=nprocs, dims=dims, seed=21, arith="strict")
+    for R in sim.ranks:
+        mg._lib.check(mg._lib.lib().mglc_lbm_set_overlap(R._h, 3))
+    wd = oracle_world(total, seed=21)
+    sim.step(4); sim.step(nsteps - 4); wd.step(nsteps)
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    for k in ("rho", "u", "v", "w"):
+        assert np.array_equal(sim.gather_macro()[k], wd.gather(k)), k
+    sim.step(3); wd.step(3)
+    assert np.array_equal(sim.gather("f"), wd.gather("f"))
+    sim.close(); wd.close()
+
+
 def test_direct_halo_survives_a_member_leaving_the_fused_loop_alone():
     """One subdomain of a group is downloaded on its own between two step() calls (its ping-pong parity flips);
     the next step() must bring the others into line instead of storing halos into the wrong lattice."""

@@ -301,3 +301,49 @@ def test_oracle_reproduces_the_particle_programs_run():
     assert (PRUN["run30/obst"] != PRUN["run0/obst"]).any()                            # nodes were uncovered / covered: refill ran
     assert wd.check() == PRUN["run30/check"][2]
     wd.close()
+
+
+# ---- the options taken from the reference's other particle scenario (case1/mpi_complete, "P1") ---------------------------
+GOLD1 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_particles_case1.npz"))
+
+
+def test_linear_interpolated_bounceback_matches_case1_source():
+    """bb_linear = 1: P1/particle_bounceback.F90:67-75 (`#ifdef linear`), with calQ as that file writes it, bit for bit"""
+    xc, yc, rad, Uc, Vc, om, rhoAvg = GOLD1["link/particle"]
+    wd = orc.ParticleWorld([xc], [yc], radius=[rad], total_nx=140, total_ny=90, bb_linear=1)
+    wd.initial()
+    wd.Uc[0], wd.Vc[0], wd.rationalOmega[0] = Uc, Vc, om
+    wd._lib.p2_set_rhoAvg(wd._h, float(rhoAvg))
+    R = wd.ranks[0]
+    for n, (i, j, a) in enumerate(GOLD1["link/ija"]):
+        i, j, a = int(i), int(j), int(a)
+        q, x0, y0 = C.c_double(), C.c_double(), C.c_double()
+        assert wd._lib.p2_calQ(wd._h, 0, float(i), float(j), a, C.byref(x0), C.byref(y0), C.byref(q)) == 0
+        assert (q.value, x0.value, y0.value) == tuple(GOLD1["link/q_x0_y0"][n]), n
+        for s in range(2):
+            R.f_post[:, i - s * orc.EX9[a] + 1, j - s * orc.EY9[a] + 1] = GOLD1["link/fpost_0_1"][n, s]
+        wd._lib.p2_bb_link_r(wd._h, 0, i, j, a, 0)
+        assert R.f[orc.OPP9[a], i + 2, j + 2] == GOLD1["link/bb_linear"][n], n
+    wd.close()
+
+
+@pytest.mark.parametrize("frame", ["moving", "stationary"])
+def test_moving_walls_match_case1_source(frame):
+    """moving_walls = 1: P1/fluid.F90:130-145 (`movingFrame`, walls seen from a frame moving with U0) and :151-168
+    (`stationaryFrame` = the same expressions with U0 = 0), bit for bit on a seeded row of nodes along either wall"""
+    nx, ny, Uwall, U0 = GOLD1["walls/params"]
+    nx, ny = int(nx), int(ny)
+    wd = orc.ParticleWorld([], [], total_nx=nx, total_ny=ny, moving_walls=1, Uwall=float(Uwall), Uframe=float(U0) if frame == "moving" else 0.0)
+    wd.initial()
+    R = wd.ranks[0]
+    for row, j in enumerate((1, ny)):
+        R.f_post[:, 2:nx + 2, j + 1] = GOLD1[f"walls/{frame}/f_post"][row].T
+    wd.bounceback()
+    want = GOLD1[f"walls/{frame}/f"]
+    for row, j in enumerate((1, ny)):
+        got = R.f[:, 3:nx + 3, j + 2].T
+        pops = (2, 5, 6) if j == 1 else (4, 7, 8)
+        inner = slice(1, nx - 1)                 # the reference scenario has no side walls; ours overwrite 5/8 and 6/7 in the two corner nodes
+        for b in pops:
+            assert np.array_equal(got[inner, b], want[row][inner, b]), (frame, j, b)
+    wd.close()

@@ -344,3 +344,37 @@ def test_thousands_of_particles_on_a_lattice_larger_than_l2_conserve_and_settle(
     assert abs(m1 / fluid.sum() - m0 / fluid0.sum()) < 1e-4          # mean fluid density: refill and moving walls exchange O(1e-7) per step
     for sim in sims:
         sim.close()
+
+
+@pytest.mark.parametrize("nprocs", [1, 4])
+@pytest.mark.parametrize("opts", [dict(bb_linear=1), dict(moving_walls=1, Uwall=0.05), dict(bb_linear=1, moving_walls=1, Uwall=0.05, Uframe=0.01)])
+def test_case1_options_linear_bounceback_and_moving_walls(opts, nprocs):
+    """The two options taken from the reference's other particle scenario (case1/mpi_complete): linear-interpolated bounce-back
+    (particle_bounceback.F90:66-76) and moving top / bottom walls (fluid.F90:123-171).  The oracle is pinned to that Fortran text
+    (tests/test_oracle_particles.py); here the CUDA path -- per-subroutine entry points and the fused step, one and four
+    subdomains -- must follow the oracle within the north-star tolerance."""
+    params = dict(SMALL, **opts)
+    wd = orc.ParticleWorld(PX, PY, nprocs=1, **params)
+    sim = mg.ParticleChannel(PX, PY, nprocs=nprocs, **params)
+    wd.initial(); sim.initial()
+    if nprocs == 1:                                           # one loop body through the per-subroutine entry points, exact pieces
+        wd.collision(); sim.collision(); wd.send_all_fp(); sim.send_all_fp(); wd.streaming(); sim.streaming()
+        wd.bounceback(); sim.bounceback()
+        assert_fields(sim, wd, ("f",))
+        wd.bounceback_particle(); sim.bounceback_particle()
+        assert_fields(sim, wd, ("f",), exact=False, atol=1e-16)
+        wd.initial(); sim.initial()
+    wd.step(60); sim.step(60)
+    assert sim.error_flags() == 0
+    for k in ("rho", "u", "v"):
+        a, b = sim.gather(k), wd.gather(k)
+        fl = velocity_floor(wd) if k != "rho" else 0.0
+        assert rel_l2(a, b, fl) <= REL_L2 and np.abs(a - b).max() <= MAX_ABS, (k, rel_l2(a, b, fl), np.abs(a - b).max())
+    p = sim.particles()
+    for k in ("xCenter", "yCenter", "Uc", "Vc", "rationalOmega"):
+        assert np.allclose(p[k], getattr(wd, k), rtol=1e-12, atol=1e-12), k
+    # the options do change the run: compare with the plain case-4 run
+    base = orc.ParticleWorld(PX, PY, nprocs=1, **SMALL)
+    base.initial(); base.step(60)
+    assert np.abs(base.gather("u") - wd.gather("u")).max() > 1e-9
+    base.close(); wd.close(); sim.close()

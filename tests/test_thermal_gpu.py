@@ -201,6 +201,20 @@ def test_decomposition_invariance_and_exchange_bit_exact(nprocs, dims):
     one.close(); many.close()
 
 
+@pytest.mark.parametrize("nprocs,dims", [(2, None), (8, None), (3, (1, 1, 3))])
+def test_halo_push_after_the_update_thermal(nprocs, dims):
+    """Transport 3 (one launch after the fused kernel copies the f messages and the g population of every face into the
+    neighbours' halos): bit-identical to one subdomain, across two step() calls."""
+    total = (13, 11, 9)
+    one, _ = worlds(total, 1, seed=9)
+    _, many = worlds(total, nprocs, dims, seed=9)
+    for R in many.ranks:
+        mg._lib.check(mg._lib.lib().mglc_lbm_set_overlap(R._h, 3))
+    one.step(12); many.step(5); many.step(7)
+    assert_state_equal(many, one)
+    one.close(); many.close()
+
+
 def test_config4_51cubed_2x2x2_fast_matches_oracle():
     total = (51, 51, 51)
     wd, sim = worlds(total, 8, arith="fast")

@@ -138,6 +138,37 @@ import json;d=json.loads(open('$O/bench_jacobi_pf$1_kch$2.json').read().strip().
     tail -n 5 $O/err.txt
 }
 
+s6() {   # 1 GPU: where the particle step at scale spends its time; Jacobi default again; the whole suite
+    timeout 600 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -s 40 -c 24 --csv --log-file $O/launches_particles_8192.csv \
+        python bench.py --workload particles --size 8192 --steps 4 --warmup 3 --no-e2e --no-cpu > $O/b12.log 2>&1; echo "ncu particles rc=$?"
+    timeout 600 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_1gpu.json 2> $O/b10.err; tail -c 600 $O/bench_particles_8192_1gpu.json
+    timeout 300 python bench.py --workload jacobi --steps 300 --no-cpu > $O/bench_jacobi_512.json 2>> $O/err.txt; tail -c 700 $O/bench_jacobi_512.json
+    (timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log); tail -n 4 $O/pytest_gpu.log
+    tail -n 5 $O/err.txt
+}
+
+m4() {   # 2 GPUs: particle node kernel A/B, lid weak after the barrier-word move, Jacobi direct vs NCCL after the face flag
+    (timeout 900 python -m pytest tests/test_particles_gpu.py tests/test_jacobi_gpu.py -q -m gpu -x > $O/pytest_sel.log 2>&1; echo "pytest rc=$?" >> $O/pytest_sel.log); tail -n 5 $O/pytest_sel.log
+    for v in 1 0; do
+        MGLC_P2D_NODE=$v timeout 600 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_1gpu_node$v.json 2> $O/b10.err
+        python -c "
+import json;d=json.loads(open('$O/bench_particles_8192_1gpu_node$v.json').read().strip().splitlines()[-1]);print('particles node=$v', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+    timeout 600 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -s 40 -c 24 --csv --log-file $O/launches_particles_8192.csv \
+        python bench.py --workload particles --size 8192 --steps 4 --warmup 3 --no-e2e --no-cpu > $O/b12.log 2>&1; echo "ncu particles rc=$?"
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 3 $O/pytest_multigpu.log
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 1800 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
+    for d in 2,1,1 1,1,2; do timeout 300 python tools/group_bench.py --gpus 2 --dims $d --size 768 --steps 20 2>> $O/err.txt | tee -a $O/group_bench_axes.jsonl; done
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-e2e > $O/bench_jacobi_2gpu.json 2> $O/b3.err; tail -c 700 $O/bench_jacobi_2gpu.json; tail -n 3 $O/b3.err
+    MGLC_NO_DIRECT=1 timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-parity --no-e2e > $O/bench_jacobi_2gpu_nccl.json 2> $O/b4.err; tail -c 400 $O/bench_jacobi_2gpu_nccl.json
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --scaling strong --steps 1000 --no-parity --no-e2e > $O/bench_jacobi_2gpu_strong.json 2> $O/b6.err; tail -c 400 $O/bench_jacobi_2gpu_strong.json
+    timeout 600 $TR bench.py --gpus 2 --workload particles --steps 20 --warmup 3 --no-e2e > $O/bench_particles_2gpu.json 2> $O/b5.err; tail -c 900 $O/bench_particles_2gpu.json; tail -n 3 $O/b5.err
+    timeout 600 $NCU --set full --import-source on -k regex:k_fused -s 4 -c 1 -o $O/ncu_full_k_fused_peer_512 \
+        python tools/group_bench.py --gpus 2 --dims 2,1,1 --size 512 --steps 2 > $O/b2.log 2>&1; echo "ncu peer rc=$?"
+    tail -n 5 $O/err.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30
