@@ -178,8 +178,11 @@ def dims_create(nranks):
 
 
 def lattice_for(args, world):
-    """(dims, per-GPU block, global lattice) of a run: weak = one size^3 block per GPU, strong = size^3 split over the GPUs"""
-    dims = tuple(int(x) for x in args.dims.split(",")) if args.dims else dims_create(world)
+    """(dims, per-GPU block, global lattice) of a run: weak = one size^3 block per GPU, strong = size^3 split over the GPUs.
+    The process grid has the factors MPI_Dims_create gives the reference (L3/main.f90:24), assigned z first, then y, then x:
+    1x1x2, 1x2x2, 2x2x2.  Rows are contiguous along x on the device, so a z or y face is a block of whole rows while an x face
+    is one double per row; with fewer than 8 subdomains the faces that have to move are the cheap ones.  --dims overrides."""
+    dims = tuple(int(x) for x in args.dims.split(",")) if args.dims else tuple(sorted(dims_create(world)))
     n = args.size
     per_gpu = [n, n, n] if args.scaling == "weak" else [n // d for d in dims]
     gn = tuple(p * d for p, d in zip(per_gpu, dims))
@@ -405,9 +408,7 @@ def main():
     Driver = mg.BuoyancyDrivenCavity if thermal else mg.LidDrivenCavity
 
     def make_sim(total):
-        kw = dict(arith=args.arith, device=local_rank)
-        if args.dims:
-            kw["dims"] = dims
+        kw = dict(arith=args.arith, device=local_rank, dims=dims)
         return Driver(total, comm=comm, **kw) if comm else Driver(total, **kw)
 
     sim = make_sim(gn)
@@ -416,8 +417,10 @@ def main():
         args.halo = "blocking"
     avail = C.c_int()
     L.check(lib.mglc_lbm_direct_halo(sub._h, C.byref(avail)))
-    if args.halo == "auto":
-        args.halo = "direct" if avail.value else "overlap"
+    if args.halo == "auto":                 # what the library picked for this block size (push for large blocks, in-kernel stores for small ones)
+        mode = C.c_int()
+        L.check(lib.mglc_lbm_get_overlap(sub._h, C.byref(mode)))
+        args.halo = {v: k for k, v in HALO_MODE.items()}[mode.value] if avail.value else "overlap"
     if world > 1:
         L.check(lib.mglc_lbm_set_overlap(sub._h, HALO_MODE[args.halo]))
     cells_local = int(np.prod(sub.n))
@@ -468,7 +471,7 @@ def main():
 
     # ---- the other halo transports on the same lattice (N > 1) ----
     transports = None
-    if world > 1 and not args.no_extras and not args.dims:
+    if world > 1 and not args.no_extras:
         transports = {args.halo: {"value": round(value, 1), "ms_per_step": round(ms / args.steps, 4)}}
         for name in ("direct", "push", "blocking", "overlap"):
             if name == args.halo or (name in ("direct", "push") and not avail.value):
@@ -490,16 +493,21 @@ def main():
 
     # ---- strong scaling in the same invocation (N > 1, default weak run): the config-3 lattice split over the GPUs ----
     strong = None
-    if world > 1 and args.scaling == "weak" and not args.no_extras and not args.dims:
+    if world > 1 and args.scaling == "weak" and not args.no_extras:
         gs = (args.size,) * 3 if not thermal else (512,) * 3
         sim2 = make_sim(gs)
-        if avail.value:
+        if avail.value and args.halo in ("direct", "push"):
+            mode = C.c_int()
+            L.check(lib.mglc_lbm_get_overlap(sim2.ranks[0]._h, C.byref(mode)))
+            strong_halo = {v: k for k, v in HALO_MODE.items()}[mode.value]
+        else:
             L.check(lib.mglc_lbm_set_overlap(sim2.ranks[0]._h, HALO_MODE[args.halo]))
+            strong_halo = args.halo
         sim2.initial()
         sim2.step(max(args.warmup, 3)); sim2.sync()
         cs = int(np.prod(gs))
         v, m = time_steps(D, sim2, args.steps, cs)
-        strong = {"global_lattice": list(gs), "per_gpu": list(sim2.ranks[0].n), "halo": args.halo,
+        strong = {"global_lattice": list(gs), "per_gpu": list(sim2.ranks[0].n), "halo": strong_halo,
                   "value": round(v, 1), "unit": "MLUPS", "ms_per_step": round(m, 4), "steps": args.steps,
                   "note": "same lattice as the N=1 line of this bench: speed-up = value / the N=1 value"}
         sim2.close()

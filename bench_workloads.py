@@ -26,7 +26,7 @@ def jacobi_reference(args, rank, world):
     from oracle import oracle as orc
     threads = orc.set_threads(0)
     n = args.size
-    dims = B.dims_create(world)
+    dims = tuple(sorted(B.dims_create(world)))           # z first, as bench.lattice_for
     gn = tuple(n * d for d in dims) if args.scaling == "weak" else (n, n, n)
     per = [n, n, n] if args.scaling == "weak" else [n // d for d in dims]
     nz = max(8, min(per[2], 64))
@@ -54,7 +54,7 @@ def jacobi(args, rank, local_rank, world):
 
     D = B.Dist(rank, local_rank, world)
     n = args.size
-    dims = mg.dims_create_nd(world, 3)
+    dims = tuple(sorted(mg.dims_create_nd(world, 3)))    # MPI_Dims_create's factors, assigned z first (see bench.lattice_for)
     gn = tuple(n * d for d in dims) if args.scaling == "weak" else (n, n, n)
     comm = D.communicator(mg)
     parity = None
@@ -68,7 +68,7 @@ def jacobi(args, rank, local_rank, world):
                                   "error": "decomposed run does not match the oracle; nothing was timed"}), flush=True)
             comm.close(); D.close()
             sys.exit(3)
-    sim = mg.Jacobi(gn, comm=comm) if comm else mg.Jacobi(gn, device=local_rank)
+    sim = mg.Jacobi(gn, comm=comm, dims=dims) if comm else mg.Jacobi(gn, device=local_rank)
     cells_local = int(np.prod(sim.info[0]["n"]))
     cells_total = int(np.prod(gn))
     sim.init()

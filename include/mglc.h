@@ -215,6 +215,7 @@ int mglc_lbm_set_profiling(mglc_lbm *h, int on);
  * by all ranks between the same two mglc_lbm_step calls, like the reference's subroutines; a rank out of step is
  * reported by mglc_lbm_sync / mglc_check as MGLC_E_STATE instead of hanging. */
 int mglc_lbm_set_overlap(mglc_lbm *h, int mode);
+int mglc_lbm_get_overlap(mglc_lbm *h, int *mode);   /* the transport in use (the library picks 3 for large blocks, 2 for small ones) */
 /* 1 if the direct-halo mappings of mode 2 are established for this handle */
 int mglc_lbm_direct_halo(mglc_lbm *h, int *available);
 int mglc_lbm_kernel_time(mglc_lbm *h, float *fused_ms, long long *fused_launches);

@@ -106,6 +106,7 @@ SIGNATURES = {
     "mglc_lbm_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "mglc_lbm_set_profiling": (C.c_int, [_vp, C.c_int]),
     "mglc_lbm_set_overlap": (C.c_int, [_vp, C.c_int]),
+    "mglc_lbm_get_overlap": (C.c_int, [_vp, _ip]),
     "mglc_lbm_direct_halo": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "mglc_host_alloc": (C.c_int, [_vpp, C.c_size_t]),
     "mglc_host_free": (C.c_int, [_vp]),

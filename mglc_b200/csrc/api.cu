@@ -62,6 +62,11 @@ struct mglc_lbm {
     unsigned long long *flags, epoch;
     int parity_sent;                     // ping-pong index of the lattice my last direct launch wrote (neighbours must agree)
     int *d_err;
+    // halo push: staging of the x-face messages I RECEIVE, [lattice parity][message 0 / 1][xs_count doubles] (PeerTable::XS);
+    // xs_pending: my neighbours' pushes of the current epoch went there and still have to be scattered into my halo columns
+    double *xstage;
+    long long xs_count;
+    int xs_pending;
     int nbr_rank[19];                    // rank at coords + e_d, -1 = none
     cudaEvent_t ev_done[2];              // group mode: my direct launch of epoch e is recorded in ev_done[e & 1]
     std::vector<void *> *ipc_opened;     // comm mode: mappings to close on destroy
@@ -165,7 +170,7 @@ extern "C" int mglc_lbm_destroy(mglc_lbm *h) {
     if (h->direct && h->direct_valid && h->s) wait_direct(h);      // neighbours may still be storing into my halos
     cudaDeviceSynchronize();
     if (h->ipc_opened) { for (void *q : *h->ipc_opened) cudaIpcCloseMemHandle(q); delete h->ipc_opened; }
-    cudaFree(h->pt_dev[0]); cudaFree(h->pt_dev[1]); cudaFree(h->flags); cudaFree(h->d_err);
+    cudaFree(h->pt_dev[0]); cudaFree(h->pt_dev[1]); cudaFree(h->flags); cudaFree(h->d_err); cudaFree(h->xstage);
     for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
     double *fields[] = {h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->stage, h->rho_lid[0], h->rho_lid[1],
@@ -281,6 +286,10 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
     if (cudaMalloc((void **)&h->flags, 32 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc((void **)&h->d_err, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&h->pt_dev[0], sizeof(PeerTable)) != cudaSuccess || cudaMalloc((void **)&h->pt_dev[1], sizeof(PeerTable)) != cudaSuccess)
         return fail(MGLC_E_NOMEM);
+    if (h->nbr_rank[0] >= 0 || h->nbr_rank[1] >= 0) {
+        h->xs_count = (long long)(h->thermal ? 6 : 5) * h->g.ny * h->g.nz;
+        if ((rc = dmalloc(h, &h->xstage, 4 * h->xs_count))) return fail(rc);
+    }
     cudaMemsetAsync(h->flags, 0, 32 * sizeof(unsigned long long), h->s);
     cudaMemsetAsync(h->d_err, 0, sizeof(int), h->s);
     for (cudaEvent_t &e : h->ev_done) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(MGLC_E_CUDA);
@@ -289,9 +298,18 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
     return MGLC_OK;
 }
 
+// Which of the two NVLink transports a handle starts with once its neighbours are mapped.  Measured on 2 B200s (768^3 blocks,
+// profiles/r2g_*): the push after the update costs 0.05 ms per step for a y or z face and 0.24 ms for an x face, the stores from
+// inside the update kernel 0.2 and 0.57 ms; on 256^3 blocks (thermal, config 4) the in-kernel stores are 0.8 % ahead because
+// the two extra launches of the push weigh more.  MGLC_HALO_MODE=2|3 overrides.
+static int default_direct_mode(const mglc_lbm *h) {
+    if (const char *e = getenv("MGLC_HALO_MODE")) { const int v = atoi(e); if (v == 2 || v == 3) return v; }
+    return (long long)h->g.nx * h->g.ny * h->g.nz >= (1LL << 26) ? 3 : 2;
+}
+
 // ---- direct halo stores: wiring ------------------------------------------------------------------------------
 static inline int opp_dir(int d) { return d < 6 ? (d ^ 1) : h_opp[d]; }
-struct PeerView { double *buf[2], *gbuf[2]; unsigned long long *flags; int ln[3]; };
+struct PeerView { double *buf[2], *gbuf[2], *xstage; unsigned long long *flags; int ln[3]; };
 // fill pt_dev[0..1] and sync from the neighbours' lattices as seen from this GPU
 static int install_peers(mglc_lbm *h, const PeerView *view /* [19], valid where nbr_rank >= 0 */) {
     PeerTable pt[2];
@@ -306,6 +324,9 @@ static int install_peers(mglc_lbm *h, const PeerView *view /* [19], valid where 
             if (d < 6) pt[b].G[d] = view[d].gbuf[b];
             pt[b].sy[d] = pg.sy; pt[b].sz[d] = pg.sz; pt[b].sq[d] = pg.sq;
             pt[b].n[d][0] = pg.nx; pt[b].n[d][1] = pg.ny; pt[b].n[d][2] = pg.nz;
+            // my +x message lands in the +x neighbour's staging of message 0, my -x message in the -x neighbour's of message 1
+            // (an x neighbour has my ny, nz, hence my xs_count)
+            if (d < 2 && view[d].xstage) pt[b].XS[d] = view[d].xstage + (b * 2 + d) * h->xs_count;
         }
         h->sync.mask |= 1u << d;
         h->sync.signal[d] = view[d].flags + opp_dir(d);     // the neighbour sees me in the opposite direction
@@ -320,7 +341,7 @@ static int install_peers(mglc_lbm *h, const PeerView *view /* [19], valid where 
 }
 // one process per GPU: exchange CUDA IPC handles of the lattices and the barrier words through the communicator,
 // map the neighbours' allocations (peer access over NVLink) and agree collectively on whether the path is usable
-struct IpcRecord { cudaIpcMemHandle_t buf[2], gbuf[2], flags; int ln[3]; int thermal; };
+struct IpcRecord { cudaIpcMemHandle_t buf[2], gbuf[2], flags, xstage; int ln[3]; int thermal, has_xstage; };
 static int setup_direct_ipc(mglc_lbm *h) {
     if (!h->comm || h->nranks < 2 || getenv("MGLC_NO_DIRECT")) return MGLC_OK;
     const int P = h->nranks;
@@ -334,6 +355,7 @@ static int setup_direct_ipc(mglc_lbm *h) {
         if (h->thermal) ok &= cudaIpcGetMemHandle(&mine.gbuf[b], h->gbuf[b]) == cudaSuccess;
     }
     ok &= cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
+    if (h->xstage) { ok &= cudaIpcGetMemHandle(&mine.xstage, h->xstage) == cudaSuccess; mine.has_xstage = 1; }
     (void)cudaGetLastError();
     for (int q = 0; q < 3; ++q) mine.ln[q] = h->d.ln[q];
     mine.thermal = h->thermal;
@@ -366,6 +388,7 @@ static int setup_direct_ipc(mglc_lbm *h) {
                 if (h->thermal && ok) ok &= open(all[r].gbuf[b], (void **)&v.gbuf[b]);
             }
             if (ok) ok &= open(all[r].flags, (void **)&v.flags);
+            if (ok && all[r].has_xstage) ok &= open(all[r].xstage, (void **)&v.xstage);
             if (ok) {           // the mapping must start at the neighbour's own pointer, not at some enclosing block
                 unsigned long long seen = 0;
                 ok &= cudaMemcpy(&seen, v.flags + 31, sizeof seen, cudaMemcpyDeviceToHost) == cudaSuccess &&
@@ -387,7 +410,7 @@ static int setup_direct_ipc(mglc_lbm *h) {
     cudaFree(dev_ok);
     if (!ok) return MGLC_OK;                     // stay on the NCCL transport
     MGLC_TRY(install_peers(h, view));
-    h->overlap = 2;
+    h->overlap = default_direct_mode(h);
     return MGLC_OK;
 }
 
@@ -742,6 +765,7 @@ static int do_fused_direct(mglc_lbm *h) {
         // push after: the plain fused kernel, then one small launch that copies the messages into the neighbours' halos
         MGLC_TRY(launch_fused_box(h, io, box));
         h->launches += launch_push_halos(h->g, pt, io.Fout, h->thermal ? io.Gout : nullptr, h->s);
+        h->xs_pending = h->xstage != nullptr;                // my x neighbours do the same: their x faces arrive in my staging
     } else if (h->thermal)
         h->launches += strict_(h) ? strict::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt)
                                   : fast::launch_th_fused(h->g, h->tp, io.Fin, io.Fout, io.Gin, io.Gout, io.Fc_in, io.Fc_out, box, h->s, pt);
@@ -769,6 +793,21 @@ static int wait_direct(mglc_lbm *h) {
         }
     } else h->launches += launch_halo_wait(h->sync, h->epoch * 2 + (unsigned long long)h->parity_sent, h->d_err, h->s);
     h->direct_valid = 0;
+    if (h->xs_pending) {
+        // halo push: the x-face messages of the lattice written last sit in my staging; scatter them into its halo columns
+        // (message 0 came from the -x neighbour, message 1 from the +x neighbour)
+        const int b = h->parity_sent;
+        const long long per = (long long)h->g.ny * h->g.nz;
+        MsgBatch mb{};
+        for (int d = 0; d < 2; ++d) {
+            if (h->nbr_rank[d ^ 1] < 0) continue;
+            double *st = h->xstage + (b * 2 + d) * h->xs_count;
+            mb.dir[mb.n] = d; mb.buf[mb.n] = st; ++mb.n;
+            if (h->thermal) { mb.dir[mb.n] = 20 + d; mb.buf[mb.n] = st + 5 * per; ++mb.n; }
+        }
+        h->launches += launch_pack_all(h->g, mb, h->buf[b], h->thermal ? h->gbuf[b] : nullptr, true, h->s);
+        h->xs_pending = 0;
+    }
     return MGLC_OK;
 }
 // Overlapped step (the schedule of L3nb collision_with_message_exchange, :1108-1230): the cells next to a
@@ -1069,6 +1108,11 @@ extern "C" int mglc_lbm_set_overlap(mglc_lbm *h, int on) {
     h->overlap = on;
     return MGLC_OK;
 }
+extern "C" int mglc_lbm_get_overlap(mglc_lbm *h, int *mode) {
+    if (!h || !mode) return MGLC_E_INVALID;
+    *mode = h->overlap;
+    return MGLC_OK;
+}
 extern "C" int mglc_lbm_direct_halo(mglc_lbm *h, int *available) {
     if (!h || !available) return MGLC_E_INVALID;
     *available = h->direct;
@@ -1155,12 +1199,13 @@ extern "C" int mglc_group_create(mglc_group **out, const mglc_lbm_desc *gd, int 
                 mglc_lbm *n = g->r[h->nbr_rank[dd]];
                 for (int b = 0; b < 2; ++b) { view[dd].buf[b] = n->buf[b]; view[dd].gbuf[b] = n->gbuf[b]; }
                 view[dd].flags = n->flags;
+                view[dd].xstage = n->xstage;
                 for (int q = 0; q < 3; ++q) view[dd].ln[q] = n->d.ln[q];
             }
             int rc = use(h);
             if (!rc) rc = install_peers(h, view);
             if (rc) { mglc_group_destroy(g); return rc; }
-            h->overlap = 2;
+            h->overlap = default_direct_mode(h);
         }
     *out = g;
     return MGLC_OK;

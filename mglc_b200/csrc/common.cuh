@@ -52,6 +52,13 @@ struct PeerTable {
     double *G[6];              // thermal: its g_post lattice
     long long sy[19], sz[19], sq[19];
     int n[19][3];              // the neighbour's interior size
+    // halo push (transport 3) only: where the two x-face messages go instead of the neighbour's halo column.  A halo column is
+    // one double every `sy` doubles, and 8-byte remote stores scattered like that cost ~2 ns each over NVLink (2.9 M of them per
+    // x face at 768^3: 5.6 ms, against 0.01 ms for a contiguous y or z face, profiles/r2g_*).  So the x faces are written
+    // contiguously -- [slot][k][j], the layout of the NCCL messages -- into a staging area in the neighbour's memory, and the
+    // neighbour scatters them into its own halo column after the barrier (local stores).  XS[d] = staging of face message d
+    // (0: +x, 1: -x) for the lattice this table belongs to, nullptr = store into the halo column as usual.
+    double *XS[2];
     // sticky error word of the neighbour barrier (k_halo_wait): once set, a launch stores nothing into a neighbour any
     // more (it may still be reading those halos); the subdomain's own numbers are meaningless from then on and the host
     // reports MGLC_E_STATE at every point where it synchronises, so such a run never comes back as MGLC_OK

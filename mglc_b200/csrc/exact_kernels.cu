@@ -284,11 +284,13 @@ __global__ void k_push_halos(Geom g, const PeerTable *__restrict__ pt, const dou
     const long long per = (long long)n1 * n2, psy = pt->sy[d], psz = pt->sz[d], psq = pt->sq[d];
     double *P = isg ? pt->G[d] : pt->F[d];
     const double *src = isg ? G : F;
+    double *xs = d < 2 ? pt->XS[d] : nullptr;       // x faces: contiguous staging in the neighbour's memory (PeerTable::XS)
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per * npop; t += (long long)gridDim.x * blockDim.x) {
         const int slot = (int)(t / per), r = (int)(t % per);
         int i, j, k;
         msg_cell(g, d, 0, r % n1, r / n1, i, j, k);
         const int a = isg ? d + 1 : (d < 6 ? c_face_pops[d][slot] : d);
+        if (xs) { xs[(isg ? 5 * per : 0) + t] = src[g.idx(a, i, j, k)]; continue; }
         // the neighbour's halo cell: layer 0 / n'+1 along the axes the message crosses, my own index along the others
         const int ii = e[0] > 0 ? 0 : (e[0] < 0 ? pt->n[d][0] + 1 : i);
         const int jj = e[1] > 0 ? 0 : (e[1] < 0 ? pt->n[d][1] + 1 : j);

@@ -105,6 +105,25 @@ __device__ __forceinline__ void jac_peer_store(const JacPeers &P, const Geom &g,
     if (k == 1 && (pm & 32u)) jac_remote_store(P.B[5] + ((P.n[5] + 1) * P.sz[5] + j * P.sy[5] + (i + OX - 1)), val);
 }
 
+// The hand-over as its own small launch after the sweep: the six boundary faces of A_new go into the neighbours' ghost layers
+// (blockIdx.y = face).  In-kernel stores (PEER = true below) turned the sweep's inner loop into mostly address arithmetic --
+// with 4 CTAs across x half of all CTAs touch an x face -- and cost 0.24 ms of a 0.37 ms sweep; this launch moves the same
+// 12.6 MB at 512^3 in a few microseconds (profiles/r2f_*).
+__global__ void __launch_bounds__(256) k_jac_push(Geom g, int ndim, const double *__restrict__ B, JacPeers P) {
+    const int face = blockIdx.y;
+    if (!(P.mask >> face & 1u) || *P.err) return;
+    const int axis = face >> 1;
+    const int n1 = (axis == 0) ? g.ny : g.nx, n2 = (ndim == 2) ? 1 : ((axis == 2) ? g.ny : g.nz);
+    const int nfix = (axis == 0) ? g.nx : (axis == 1 ? g.ny : g.nz), fix = (face & 1) ? 1 : nfix;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)n1 * n2; t += (long long)gridDim.x * blockDim.x) {
+        const int t1 = 1 + (int)(t % n1), t2 = 1 + (int)(t / n1);
+        const int i = (axis == 0) ? fix : t1;
+        const int j = (axis == 1) ? fix : (axis == 0 ? t1 : t2);
+        const int k = (ndim == 2) ? 1 : ((axis == 2) ? fix : t2);
+        jac_peer_store(P, g, i, j, k, B[g.idx(0, i, j, k)]);
+    }
+}
+
 template <bool HAS_F, bool PEER>
 __global__ void __launch_bounds__(128) k_jacobi2d(Geom g, const double *__restrict__ A, const double *__restrict__ f,
                                                   double *__restrict__ B, JacPeers P) {
@@ -937,7 +956,9 @@ static int jac_sweep(mglc_jacobi *h, bool peers = false) {
         const double *A = S->A[S->cur];
         double *B = S->A[S->cur ^ 1];
         const JacPeers P = jac_peers(h, S, peers);
-        const bool peer = P.mask != 0;
+        // default: the plain sweep, then k_jac_push; MGLC_JACOBI_PEER_IN_KERNEL=1 stores from inside the sweep instead
+        static const bool in_kernel = getenv("MGLC_JACOBI_PEER_IN_KERNEL") != nullptr;
+        const bool peer = P.mask != 0 && in_kernel;
         if (h->ndim == 2) {
             const dim3 grid((S->n[0] + 127) / 128, S->n[1]);
             if (peer) { if (S->f) k_jacobi2d<true, true><<<grid, 128, 0, S->s>>>(S->g, A, S->f, B, P); else k_jacobi2d<false, true><<<grid, 128, 0, S->s>>>(S->g, A, nullptr, B, P); }
@@ -971,6 +992,12 @@ static int jac_sweep(mglc_jacobi *h, bool peers = false) {
 #undef MGLC_JAC_REG
         }
         S->launches += 1;
+        if (P.mask && !peer) {
+            // a corner/edge cell belongs to two or three faces: jac_peer_store sends it to each of them, as the sweep would
+            const long long cells = (long long)std::max(S->n[0], S->n[1]) * (h->ndim == 2 ? 1 : std::max(S->n[1], S->n[2]));
+            k_jac_push<<<dim3((unsigned)std::min<long long>(256, (cells + 255) / 256), 2 * h->ndim), 256, 0, S->s>>>(S->g, h->ndim, B, P);
+            S->launches += 1;
+        }
         if (P.mask) {
             const int parity = S->cur ^ 1;                         // of the array just written
             S->epoch += 1;

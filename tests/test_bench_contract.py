@@ -51,7 +51,7 @@ def test_reference_arm_uses_every_core_under_a_launcher_and_names_the_product_ar
     r = bench("--impl", "reference", "--workload", "jacobi", "--gpus", "4", "--size", "24", "--steps", "2", "--warmup", "1", env={"OMP_NUM_THREADS": "1"})
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
     assert j["impl"] == "reference" and j["metric"] == "Mcells/s" and j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
-    assert j["config"]["decomposition"] == "2x2x1" and j["config"]["global_grid"] == [48, 48, 24]
+    assert j["config"]["decomposition"] == "1x2x2" and j["config"]["global_grid"] == [24, 48, 48]
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -87,12 +87,20 @@ import json;d=json.loads(open('$O/bench_jacobi_$1_$2.json').read().strip().split
     tail -n 5 $O/err.txt
 }
 
+jk() {    # 1 GPU: planes per CTA of the register-blocked Jacobi sweep (r1 only tried 8 / 16 / 32)
+    for kch in 4 6 8 12; do
+        MGLC_JACOBI_KCH=$kch timeout 120 python bench.py --workload jacobi --steps 300 --no-cpu --no-e2e > $O/bench_jacobi_kch$kch.json 2>> $O/err.txt
+        python -c "
+import json;d=json.loads(open('$O/bench_jacobi_kch$kch.json').read().strip().splitlines()[-1]);print('jacobi kch $kch', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+}
 san() {   # 1 GPU: compute-sanitizer racecheck + initcheck + memcheck over the fused, single-lattice, particle, Jacobi (TMA) and
           # direct-halo-store paths (P subdomains in one process); logs are kept under profiles/
-    SEL='(test_fused_step_strict_is_bit_exact and 13) or test_direct_halo_stores_equal_packed_exchange or test_reinitialising or (test_3d_sweep_kernels_bit_exact and 131) or (test_fused_steps_with_direct_halo_stores and 33) or (test_particle_bins and 1-) or test_decomposed_run_matches_single_rank_oracle or (strict_is_bit_exact_for_every_way and mrt and calls8) or (test_fused_step_strict and thermal and 11)'
+    SEL='(test_fused_step_strict_is_bit_exact and total0-1) or (test_direct_halo_stores_equal_packed_exchange and 2-None) or (test_halo_push_after_the_update and 2-None) or (test_reinitialising and False) or (test_3d_sweep_kernels_bit_exact and total0 and tma-0-0-0) or (test_3d_sweep_kernels_bit_exact and total0 and reg-0) or (test_fused_steps_with_direct_halo_stores and total2 and direct) or (test_decomposed_run_matches_single_rank_oracle and 2-dims0) or (strict_is_bit_exact_for_every_way and mrt and calls8) or (test_case1_options and opts2 and 4)'
     FILES="tests/test_lid_gpu.py tests/test_jacobi_gpu.py tests/test_particles_gpu.py tests/test_aa_gpu.py tests/test_thermal_gpu.py"
+    jk
     for tool in memcheck racecheck initcheck; do
-        (timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $FILES -m gpu -q -x -k "$SEL" > $O/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a $O/sanitizer_$tool.log)
+        (timeout 420 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $FILES -m gpu -q -x -k "$SEL" > $O/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a $O/sanitizer_$tool.log)
         grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" $O/sanitizer_$tool.log | tail -n 4
     done
 }
@@ -167,6 +175,39 @@ import json;d=json.loads(open('$O/bench_particles_8192_1gpu_node$v.json').read()
     timeout 600 $NCU --set full --import-source on -k regex:k_fused -s 4 -c 1 -o $O/ncu_full_k_fused_peer_512 \
         python tools/group_bench.py --gpus 2 --dims 2,1,1 --size 512 --steps 2 > $O/b2.log 2>&1; echo "ncu peer rc=$?"
     tail -n 5 $O/err.txt
+}
+
+m5() {   # 2 GPUs: halo push (lid, thermal, Jacobi) against the in-kernel stores and NCCL; case1 particle options; NVLink bytes
+    (timeout 900 python -m pytest tests/test_particles_gpu.py tests/test_jacobi_gpu.py tests/test_lid_gpu.py tests/test_thermal_gpu.py -q -m gpu -x > $O/pytest_sel.log 2>&1; echo "pytest rc=$?" >> $O/pytest_sel.log); tail -n 5 $O/pytest_sel.log
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 3 $O/pytest_multigpu.log
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 1500 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e --no-parity --dims 1,1,2 --halo push > $O/bench_lid_2gpu_z_push.json 2> $O/b1z.err; tail -c 400 $O/bench_lid_2gpu_z_push.json
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e --no-parity --dims 1,1,2 --halo direct > $O/bench_lid_2gpu_z_direct.json 2> $O/b1z.err; tail -c 400 $O/bench_lid_2gpu_z_direct.json
+    timeout 600 $TR bench.py --gpus 2 --workload thermal --steps 20 --warmup 5 --no-e2e --no-parity > $O/bench_thermal_2gpu.json 2> $O/b7.err; tail -c 900 $O/bench_thermal_2gpu.json
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-e2e > $O/bench_jacobi_2gpu.json 2> $O/b3.err; tail -c 700 $O/bench_jacobi_2gpu.json; tail -n 3 $O/b3.err
+    MGLC_NO_DIRECT=1 timeout 600 $TR bench.py --gpus 2 --workload jacobi --steps 300 --no-parity --no-e2e > $O/bench_jacobi_2gpu_nccl.json 2> $O/b4.err; tail -c 400 $O/bench_jacobi_2gpu_nccl.json
+    timeout 600 $TR bench.py --gpus 2 --workload jacobi --scaling strong --steps 1000 --no-parity --no-e2e > $O/bench_jacobi_2gpu_strong.json 2> $O/b6.err; tail -c 400 $O/bench_jacobi_2gpu_strong.json
+    timeout 600 $NCU --metrics gpu__time_duration.sum,nvltx__bytes.sum,nvlrx__bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum -k regex:"k_fused|k_push" -s 6 -c 6 --csv --log-file $O/ncu_nvlink_k_fused_peer_768.csv \
+        python tools/group_bench.py --gpus 2 --dims 2,1,1 --size 768 --steps 2 > $O/b2.log 2>&1; echo "ncu nvlink rc=$?"; tail -n 8 $O/ncu_nvlink_k_fused_peer_768.csv | cut -c1-60,200-
+    tail -n 5 $O/err.txt 2>/dev/null
+}
+
+m6() {   # 2 GPUs: halo push with staged x faces
+    (timeout 900 python -m pytest tests/test_lid_gpu.py tests/test_thermal_gpu.py -q -m gpu -x > $O/pytest_sel.log 2>&1; echo "pytest rc=$?" >> $O/pytest_sel.log); tail -n 5 $O/pytest_sel.log
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 3 $O/pytest_multigpu.log
+    for d in 2,1,1 1,2,1 1,1,2; do for hm in push direct; do
+        timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e --no-parity --dims $d --halo $hm > $O/bench_lid_2gpu_${d//,/}_$hm.json 2> $O/b1z.err
+        python -c "
+import json;d=json.loads(open('$O/bench_lid_2gpu_${d//,/}_$hm.json').read().strip().splitlines()[-1]);print('lid dims $d $hm', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done; done
+    for hm in push direct; do
+        timeout 600 $TR bench.py --gpus 2 --workload thermal --steps 20 --warmup 5 --no-e2e --no-parity --dims 2,1,1 --halo $hm > $O/bench_thermal_2gpu_211_$hm.json 2> $O/b7.err
+        python -c "
+import json;d=json.loads(open('$O/bench_thermal_2gpu_211_$hm.json').read().strip().splitlines()[-1]);print('thermal dims 2,1,1 $hm', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+    timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 2500 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
 }
 
 "$S"
