@@ -210,6 +210,16 @@ import json;d=json.loads(open('$O/bench_thermal_2gpu_211_$hm.json').read().strip
     timeout 900 $TR bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_lid_2gpu.json 2> $O/b1.err; tail -c 2500 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err
 }
 
+m8() {   # 8 GPUs: the driver's own N = 8 line (parity + weak + transports + e2e + strong), then configs 2, 4, 5
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
+    python tools/probe_host.py --gpus 0 --gib 1 2>&1 | head -3 > $O/probe_host_8gpu_box.txt
+    ( time timeout 900 $TR bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_lid_8gpu.json 2> $O/b1.err ) 2> $O/time_lid.txt; tail -c 3500 $O/bench_lid_8gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time_lid.txt
+    timeout 300 $TR bench.py --gpus 8 --workload jacobi --steps 300 --no-e2e > $O/bench_jacobi_8gpu_weak.json 2> $O/b3.err; tail -c 600 $O/bench_jacobi_8gpu_weak.json; tail -n 2 $O/b3.err
+    timeout 300 $TR bench.py --gpus 8 --workload jacobi --scaling strong --steps 1000 --no-parity --no-e2e > $O/bench_jacobi_8gpu_strong.json 2> $O/b6.err; tail -c 400 $O/bench_jacobi_8gpu_strong.json
+    timeout 400 $TR bench.py --gpus 8 --workload thermal --steps 20 --warmup 5 --no-e2e > $O/bench_thermal_8gpu.json 2> $O/b7.err; tail -c 1500 $O/bench_thermal_8gpu.json; tail -n 2 $O/b7.err
+    timeout 400 $TR bench.py --gpus 8 --workload particles --steps 10 --warmup 3 --no-e2e > $O/bench_particles_8gpu.json 2> $O/b5.err; tail -c 1000 $O/bench_particles_8gpu.json; tail -n 2 $O/b5.err
+}
+
 "$S"
 clk
 ls -la $O | tail -30
