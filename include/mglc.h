@@ -456,7 +456,10 @@ int mglc_t2d_sync(mglc_t2d *h);
 /* ================= D3Q19 lid-driven cavity on ONE lattice: AA-pattern storage =================
  * The loop body of L3/main.f90:89-97 with the arithmetic of mglc_lbm_step (bit-identical to it in MGLC_ARITH_STRICT), updated in
  * place: 19 x 8 B of lattice per cell instead of 2 x 19 x 8 B, for the largest lattice one GPU can hold (about 1.4x the cells).
- * One subdomain (all six faces are walls of the global box); the decomposed runs use mglc_lbm_* / mglc_group_*.  The lattice
+ * mglc_aa_create: one subdomain (all six faces are walls of the global box).  mglc_aa_group_create: the blocks of
+ * mpi_starts/decompose_1d (L3/main.f90:33-63, 247-263) inside one process, on one or several devices that can address each
+ * other: no halo message is packed, every launch stores what the neighbouring blocks need straight into their lattices and
+ * the launches of neighbours are ordered by events (one neighbour barrier per launch).  The lattice
  * is only meaningful through these calls (between two streaming steps its populations sit in the opposite slots), so there are
  * no per-subroutine entry points: f and the fields are uploaded, stepped, checked and downloaded. */
 typedef struct mglc_aa mglc_aa;
@@ -481,6 +484,23 @@ int mglc_aa_download_f(mglc_aa *h, double *f);                          /* f as 
 int mglc_aa_device_bytes(mglc_aa *h, long long *bytes);
 int mglc_aa_launch_count(mglc_aa *h, long long *n);
 int mglc_aa_sync(mglc_aa *h);
+int mglc_aa_get_block(mglc_aa *h, int *ln, int *start);                 /* local size, 0-based global offset of a block */
+/* decomposed: gd->n = the GLOBAL lattice (total_nx, total_ny, total_nz), tau from mglc_aa_desc_init with the global nx.
+ * dims = {0,..} or NULL: MPI_Dims_create's factors (mglc_dims_create); devices = NULL: gd->device for every block.
+ * Blocks are numbered like MPI_Cart_create's ranks (row-major, mglc_cart_rank).  On a block handle (mglc_aa_group_rank) the
+ * per-block calls are mglc_aa_upload (NATURAL layout only), mglc_aa_download_macro / _download_f, mglc_aa_get_block,
+ * mglc_aa_device_bytes, mglc_aa_launch_count; initial / step / check go through the group (else MGLC_E_STATE). */
+typedef struct mglc_aa_group mglc_aa_group;
+int mglc_aa_group_create(mglc_aa_group **g, const mglc_aa_desc *gd, int nranks, const int *dims, const int *devices);
+int mglc_aa_group_destroy(mglc_aa_group *g);
+int mglc_aa_group_size(mglc_aa_group *g, int *n);
+int mglc_aa_group_dims(mglc_aa_group *g, int *dims);
+int mglc_aa_group_rank(mglc_aa_group *g, int r, mglc_aa **h);
+int mglc_aa_group_initial(mglc_aa_group *g);
+int mglc_aa_group_step(mglc_aa_group *g, int nsteps);
+int mglc_aa_group_step_timed(mglc_aa_group *g, int nsteps, float *ms);   /* longest block stream, ms */
+int mglc_aa_group_check(mglc_aa_group *g, double *errorU);
+int mglc_aa_group_sync(mglc_aa_group *g);
 
 /* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
  * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /

@@ -275,6 +275,17 @@ SIGNATURES = {
     "mglc_aa_device_bytes": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_aa_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "mglc_aa_sync": (C.c_int, [_vp]),
+    "mglc_aa_get_block": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mglc_aa_group_create": (C.c_int, [_vpp, C.POINTER(AaDesc), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mglc_aa_group_destroy": (C.c_int, [_vp]),
+    "mglc_aa_group_size": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "mglc_aa_group_dims": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "mglc_aa_group_rank": (C.c_int, [_vp, C.c_int, _vpp]),
+    "mglc_aa_group_initial": (C.c_int, [_vp]),
+    "mglc_aa_group_step": (C.c_int, [_vp, C.c_int]),
+    "mglc_aa_group_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "mglc_aa_group_check": (C.c_int, [_vp, _dp]),
+    "mglc_aa_group_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -298,13 +298,14 @@ static int create_impl(mglc_lbm **out, const mglc_lbm_desc *d, mglc_comm *comm) 
     return MGLC_OK;
 }
 
-// Which of the two NVLink transports a handle starts with once its neighbours are mapped.  Measured on 2 B200s (768^3 blocks,
-// profiles/r2g_*): the push after the update costs 0.05 ms per step for a y or z face and 0.24 ms for an x face, the stores from
-// inside the update kernel 0.2 and 0.57 ms; on 256^3 blocks (thermal, config 4) the in-kernel stores are 0.8 % ahead because
-// the two extra launches of the push weigh more.  MGLC_HALO_MODE=2|3 overrides.
+// Which of the two NVLink transports a handle starts with once its neighbours are mapped.  Measured on 2 and 8 B200s (768^3
+// blocks, profiles/r2g_*, r2m_*): the push after the update costs 0.05 ms per step for a y or z face and 0.24 ms for an x face,
+// the stores from inside the update kernel 0.2 and 0.57 ms (8 GPUs, 2x2x2: 21.50 against 22.33 ms); on 256^3 blocks (thermal,
+// config 4) the in-kernel stores are 1 % ahead because the two extra launches of the push weigh more than the stores.  Both
+// costs scale with the surface, the launches do not: the switch sits between 256^3 and 384^3.  MGLC_HALO_MODE=2|3 overrides.
 static int default_direct_mode(const mglc_lbm *h) {
     if (const char *e = getenv("MGLC_HALO_MODE")) { const int v = atoi(e); if (v == 2 || v == 3) return v; }
-    return (long long)h->g.nx * h->g.ny * h->g.nz >= (1LL << 26) ? 3 : 2;
+    return (long long)h->g.nx * h->g.ny * h->g.nz >= (1LL << 25) ? 3 : 2;
 }
 
 // ---- direct halo stores: wiring ------------------------------------------------------------------------------

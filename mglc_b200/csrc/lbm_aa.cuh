@@ -4,10 +4,13 @@
 
 namespace mglc {
 #define MGLC_DECLARE_AA_LAUNCHERS                                                                                              \
+    /* peers (a PeerTable on the HOST, passed by value) != nullptr: a decomposed lattice, neighbours mapped */               \
     int launch_aa_collide0(const Geom &g, const LbmParams &p, double *A, const double *rho, const double *u, const double *v, \
-                           const double *w, cudaStream_t s);                                                                  \
-    int launch_aa_even(const Geom &g, const LbmParams &p, double *A, double *rho_lid_out, cudaStream_t s);                    \
-    int launch_aa_odd(const Geom &g, const LbmParams &p, double *A, const double *rho_lid_in, cudaStream_t s);
+                           const double *w, cudaStream_t s, const PeerTable *peers = nullptr);                                \
+    int launch_aa_even(const Geom &g, const LbmParams &p, double *A, double *rho_lid_out, cudaStream_t s,                     \
+                       const PeerTable *peers = nullptr);                                                                     \
+    int launch_aa_odd(const Geom &g, const LbmParams &p, double *A, const double *rho_lid_in, cudaStream_t s,                 \
+                      const PeerTable *peers = nullptr);
 namespace strict { MGLC_DECLARE_AA_LAUNCHERS }
 namespace fast { MGLC_DECLARE_AA_LAUNCHERS }
 

@@ -17,6 +17,17 @@
 // its loads (every post-collision population is a function of every moment), so no store can be hoisted above a load, and the
 // only thread that ever writes a location during a launch is the one that read it: a stale non-coherent line can only be
 // stale in entries nobody reads again.
+// Decomposed lattices (PEER = true, the neighbours' lattices mapped: peer pointers or CUDA IPC; the PeerTable of common.cuh is a
+// kernel parameter here, read from the constant bank, so every global load of these kernels is a lattice load).  The two
+// exchanges of a decomposed AA run ride along with the launches, like the halo stores of k_fused<..., PEER>:
+//   * a launch that PARKS (k_aa_collide0, k_aa_even) also stores the parked populations of its boundary cells into the
+//     neighbour's halo cells, same slot opp(a) -- the message sets of ex_sendrecv.f90:12-123 (5 per face, 1 per edge) -- so the
+//     next odd launch over there can pull them;
+//   * the odd launch PUSHES f_post_a(x) to x + e_a; where that cell belongs to a neighbour the store goes straight into the
+//     neighbour's own cell (slot a), so no halo layer has to be sent back.
+// Nobody reads a location that another subdomain writes during the same launch: (a, y) of a boundary cell y is pulled by the
+// cell x = y - e_a across the face -- from x's own halo copy -- and pushed by that same cell; y's owner only touches it in the
+// next launch.  The launches of neighbouring subdomains are ordered by the neighbour barrier (events / flag words).
 #include "common.cuh"
 
 namespace mglc {
@@ -69,11 +80,74 @@ __device__ __forceinline__ void aa_collide(const double (&f)[19], double rho, do
         A[out_ ? (o) * sq + c : (a) * sq + (c + (dz) * sz + (dy) * sy + (dx))] = fp[a];                    \
     }
 
+// ---- decomposed lattices: where the parked populations of a boundary cell also go, and where a push across a face lands ----
+// halo cell of the neighbour in direction (EX,EY,EZ) that mirrors cell (i,j,k) (as peer_cell in lbm_kernels.inl)
+template <int EX, int EY, int EZ>
+__device__ __forceinline__ long long aa_peer_halo(const PeerTable &pt, int D, int i, int j, int k) {
+    const int ii = EX > 0 ? 0 : (EX < 0 ? pt.n[D][0] + 1 : i);
+    const int jj = EY > 0 ? 0 : (EY < 0 ? pt.n[D][1] + 1 : j);
+    const int kk = EZ > 0 ? 0 : (EZ < 0 ? pt.n[D][2] + 1 : k);
+    return kk * pt.sz[D] + jj * pt.sy[D] + (ii + OX - 1);
+}
+// population a of a face message is parked in slot opp(a)
+#define AA_PARK_FACE(D, EX, EY, EZ, a0, o0, a1, o1, a2, o2, a3, o3, a4, o4)                                   \
+    if (pm & (1u << (D))) {                                                                                   \
+        double *P = pt.F[D];                                                                                 \
+        const long long hc = aa_peer_halo<EX, EY, EZ>(pt, D, i, j, k), q = pt.sq[D];                         \
+        P[(o0) * q + hc] = fp[a0]; P[(o1) * q + hc] = fp[a1]; P[(o2) * q + hc] = fp[a2];                      \
+        P[(o3) * q + hc] = fp[a3]; P[(o4) * q + hc] = fp[a4];                                                 \
+    }
+#define AA_PARK_EDGE(A, O, EX, EY, EZ)                                                                       \
+    if (pm & (1u << (A))) pt.F[A][(O) * pt.sq[A] + aa_peer_halo<EX, EY, EZ>(pt, A, i, j, k)] = fp[A];
+__device__ __forceinline__ void aa_peer_park(const PeerTable &pt, const Geom &g, int i, int j, int k, const double (&fp)[19]) {
+    const unsigned pm = pt.mask;
+    const bool xp = i == g.nx, xm = i == 1, yp = j == g.ny, ym = j == 1, zp = k == g.nz, zm = k == 1;
+    if (!(xp | xm | yp | ym | zp | zm)) return;
+    if (xp) AA_PARK_FACE(0, 1, 0, 0, 1, 2, 7, 10, 9, 8, 11, 14, 13, 12)
+    if (xm) AA_PARK_FACE(1, -1, 0, 0, 2, 1, 8, 9, 10, 7, 12, 13, 14, 11)
+    if (yp) AA_PARK_FACE(2, 0, 1, 0, 3, 4, 7, 10, 8, 9, 15, 18, 17, 16)
+    if (ym) AA_PARK_FACE(3, 0, -1, 0, 4, 3, 9, 8, 10, 7, 16, 17, 18, 15)
+    if (zp) AA_PARK_FACE(4, 0, 0, 1, 5, 6, 11, 14, 12, 13, 15, 18, 16, 17)
+    if (zm) AA_PARK_FACE(5, 0, 0, -1, 6, 5, 13, 12, 14, 11, 17, 16, 18, 15)
+    if (xp && yp) AA_PARK_EDGE(7, 10, 1, 1, 0)
+    if (xm && yp) AA_PARK_EDGE(8, 9, -1, 1, 0)
+    if (xp && ym) AA_PARK_EDGE(9, 8, 1, -1, 0)
+    if (xm && ym) AA_PARK_EDGE(10, 7, -1, -1, 0)
+    if (xp && zp) AA_PARK_EDGE(11, 14, 1, 0, 1)
+    if (xm && zp) AA_PARK_EDGE(12, 13, -1, 0, 1)
+    if (xp && zm) AA_PARK_EDGE(13, 12, 1, 0, -1)
+    if (xm && zm) AA_PARK_EDGE(14, 11, -1, 0, -1)
+    if (yp && zp) AA_PARK_EDGE(15, 18, 0, 1, 1)
+    if (ym && zp) AA_PARK_EDGE(16, 17, 0, -1, 1)
+    if (yp && zm) AA_PARK_EDGE(17, 16, 0, 1, -1)
+    if (ym && zm) AA_PARK_EDGE(18, 15, 0, -1, -1)
+}
+// push of population a = (dx,dy,dz) from cell (i,j,k) of a decomposed lattice: beyond a wall of the global box it comes back as
+// opp(a) of the cell (bounceback(), as AA_PUSH); beyond a face shared with a neighbour it is stored into that neighbour's own
+// cell -- the face neighbour if one component leaves the block, the edge neighbour (direction = a itself) if two do
+#define AA_PUSH_PEER(a, o, dx, dy, dz)                                                                                  \
+    {                                                                                                                   \
+        const bool out_ = ((dx) == 1 && wf.xp) || ((dx) == -1 && wf.xm) || ((dy) == 1 && wf.yp) ||                     \
+                          ((dy) == -1 && wf.ym) || ((dz) == 1 && wf.zp) || ((dz) == -1 && wf.zm);                      \
+        const bool bx = ((dx) == 1 && i == g.nx) || ((dx) == -1 && i == 1);                                            \
+        const bool by = ((dy) == 1 && j == g.ny) || ((dy) == -1 && j == 1);                                            \
+        const bool bz = ((dz) == 1 && k == g.nz) || ((dz) == -1 && k == 1);                                            \
+        if (out_) A[(o) * sq + c] = fp[a];                                                                             \
+        else if (!(bx | by | bz)) A[(a) * sq + (c + (dz) * sz + (dy) * sy + (dx))] = fp[a];                            \
+        else {                                                                                                          \
+            const int D = (int)bx + (int)by + (int)bz == 2 ? (a) : bx ? ((dx) > 0 ? 0 : 1) : by ? ((dy) > 0 ? 2 : 3) : ((dz) > 0 ? 4 : 5); \
+            const int ii = bx ? ((dx) > 0 ? 1 : pt.n[D][0]) : i + (dx);                                               \
+            const int jj = by ? ((dy) > 0 ? 1 : pt.n[D][1]) : j + (dy);                                               \
+            const int kk = bz ? ((dz) > 0 ? 1 : pt.n[D][2]) : k + (dz);                                               \
+            pt.F[D][(a) * pt.sq[D] + kk * pt.sz[D] + jj * pt.sy[D] + (ii + OX - 1)] = fp[a];                       \
+        }                                                                                                               \
+    }
+
 // prologue: collision() with the stored rho,u,v,w (what the reference does with the fields initial() or the caller left)
-template <bool BGK>
+template <bool BGK, bool PEER>
 __global__ void __launch_bounds__(128, 4) k_aa_collide0(Geom g, LbmParams p, double *A, const double *__restrict__ rho,
                                                         const double *__restrict__ u, const double *__restrict__ v,
-                                                        const double *__restrict__ w) {
+                                                        const double *__restrict__ w, const __grid_constant__ PeerTable pt) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
     const long long sq = g.sq, c = g.idx(0, i, j, k), m = g.cell(i, j, k);
@@ -84,11 +158,13 @@ __global__ void __launch_bounds__(128, 4) k_aa_collide0(Geom g, LbmParams p, dou
     A[c] = fp[0];
 #define AA_PARK(a, o, dx, dy, dz) A[(o) * sq + c] = fp[a];
     AA_FOR_ALL(AA_PARK)
+    if (PEER) aa_peer_park(pt, g, i, j, k, fp);
 }
 
 // NATURAL -> POST: macro() of this loop body and collision() of the next, at the cell
-template <bool BGK>
-__global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double *__restrict__ A, double *__restrict__ rho_lid_out) {
+template <bool BGK, bool PEER>
+__global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double *__restrict__ A, double *__restrict__ rho_lid_out,
+                                                    const __grid_constant__ PeerTable pt) {
     const double *__restrict__ Ain = A;      // see the note on aliasing above
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
@@ -102,13 +178,15 @@ __global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double 
     A[c] = fp[0];
     AA_FOR_ALL(AA_PARK)
 #undef AA_PARK
+    if (PEER) aa_peer_park(pt, g, i, j, k, fp);
     // the moving-lid bounce-back of the next streaming step needs this macro()'s rho on the lid plane (bounce_back.f90:77-78)
     if (g.lid && k == g.nz) rho_lid_out[(i - 1) + (long long)g.nx * (j - 1)] = rho;
 }
 
 // POST -> NATURAL: streaming() + bounceback() + macro() of loop body n, collision() + streaming() + bounceback() of body n+1
-template <bool BGK>
-__global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *__restrict__ A, const double *__restrict__ rho_lid_in) {
+template <bool BGK, bool PEER>
+__global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *__restrict__ A, const double *__restrict__ rho_lid_in,
+                                                   const __grid_constant__ PeerTable pt) {
     const double *__restrict__ Ain = A;      // see the note on aliasing above
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
@@ -116,7 +194,9 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     const AaWalls wf = aa_walls(g, i, j, k);
     // Interior cells (no wall flag: all but the outermost shell) take straight-line paths: every address is the cell index plus
     // a block-uniform offset, no per-population wall test and no 64-bit select -- half the instructions of the general path.
-    const bool shell = wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
+    // (a decomposed block: every cell on a face of the block takes the general path, its pushes may leave the block)
+    const bool shell = PEER ? (i == 1) | (i == g.nx) | (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz)
+                            : wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
     double f[19], fp[19];
     if (!shell) {
         f[0] = __ldg(Ain + c);
@@ -141,28 +221,33 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
             fp[11] = __dsub_rn(fp[11], __dmul_rn(r6, p.U0));
             fp[12] = __dsub_rn(fp[12], __dmul_rn(r6, -p.U0));
         }
-        AA_FOR_ALL(AA_PUSH)
+        if (PEER) { AA_FOR_ALL(AA_PUSH_PEER) }
+        else { AA_FOR_ALL(AA_PUSH) }
     }
 }
 
 #ifndef MGLC_HOST_SHIM
+static const PeerTable aa_no_peers = {};
 static inline dim3 aa_grid(const Geom &g) { return dim3((g.nx + 127) / 128, g.ny, g.nz); }
+#define MGLC_AA_LAUNCH(K, ...)                                                                          \
+    do {                                                                                                \
+        if (pt) { if (p.bgk) K<true, true><<<aa_grid(g), 128, 0, s>>>(__VA_ARGS__, *pt); else K<false, true><<<aa_grid(g), 128, 0, s>>>(__VA_ARGS__, *pt); } \
+        else { if (p.bgk) K<true, false><<<aa_grid(g), 128, 0, s>>>(__VA_ARGS__, aa_no_peers); else K<false, false><<<aa_grid(g), 128, 0, s>>>(__VA_ARGS__, aa_no_peers); } \
+    } while (0)
 int launch_aa_collide0(const Geom &g, const LbmParams &p, double *A, const double *rho, const double *u, const double *v, const double *w,
-                       cudaStream_t s) {
-    if (p.bgk) k_aa_collide0<true><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho, u, v, w);
-    else k_aa_collide0<false><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho, u, v, w);
+                       cudaStream_t s, const PeerTable *pt) {
+    MGLC_AA_LAUNCH(k_aa_collide0, g, p, A, rho, u, v, w);
     return 1;
 }
-int launch_aa_even(const Geom &g, const LbmParams &p, double *A, double *rho_lid_out, cudaStream_t s) {
-    if (p.bgk) k_aa_even<true><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho_lid_out);
-    else k_aa_even<false><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho_lid_out);
+int launch_aa_even(const Geom &g, const LbmParams &p, double *A, double *rho_lid_out, cudaStream_t s, const PeerTable *pt) {
+    MGLC_AA_LAUNCH(k_aa_even, g, p, A, rho_lid_out);
     return 1;
 }
-int launch_aa_odd(const Geom &g, const LbmParams &p, double *A, const double *rho_lid_in, cudaStream_t s) {
-    if (p.bgk) k_aa_odd<true><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho_lid_in);
-    else k_aa_odd<false><<<aa_grid(g), 128, 0, s>>>(g, p, A, rho_lid_in);
+int launch_aa_odd(const Geom &g, const LbmParams &p, double *A, const double *rho_lid_in, cudaStream_t s, const PeerTable *pt) {
+    MGLC_AA_LAUNCH(k_aa_odd, g, p, A, rho_lid_in);
     return 1;
 }
+#undef MGLC_AA_LAUNCH
 #endif
 
 }  // namespace MGLC_NS

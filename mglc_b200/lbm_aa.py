@@ -1,5 +1,7 @@
 """Host-side mirror of the reference's D3Q19 lid-driven cavity driver (L3/main.f90) on ONE lattice (AA-pattern storage,
-mglc_aa_* in include/mglc.h): same loop body, same results as LidDrivenCavity, half the lattice memory, one subdomain.
+mglc_aa_* in include/mglc.h): same loop body, same results as LidDrivenCavity, half the lattice memory.  One subdomain, or
+(nranks > 1) the blocks of mpi_starts/decompose_1d (L3/main.f90:33-63) inside this process on devices that can address each
+other (mglc_aa_group_*): the global arrays are scattered to / gathered from the blocks here.
 Arrays cross the boundary in the Fortran program's layout f(0:18,nx,ny,nz), rho,u,v,w(nx,ny,nz), order="F"."""
 import ctypes as C
 
@@ -9,7 +11,12 @@ from . import _lib as L
 
 
 class LidDrivenCavityAA:
-    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0):
+    def __new__(cls, total, *args, nranks=1, **kw):
+        if cls is LidDrivenCavityAA and nranks > 1:
+            return super().__new__(LidDrivenCavityAAGroup)
+        return super().__new__(cls)
+
+    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0, nranks=1):
         lib = L.lib()
         d = L.AaDesc()
         L.check(lib.mglc_aa_desc_init(C.byref(d), *total, Re, U0, rho0))
@@ -79,4 +86,103 @@ class LidDrivenCavityAA:
     def download_f(self):
         f = np.empty((19,) + self.total, order="F")
         L.check(L.lib().mglc_aa_download_f(self._h, f.ctypes.data_as(C.c_void_p)))
+        return f
+
+
+class _Block:
+    """per-block view of a group member (download / upload in the block's own shape)"""
+
+    def __init__(self, h):
+        self._h = h
+        ln, st = (C.c_int * 3)(), (C.c_int * 3)()
+        L.check(L.lib().mglc_aa_get_block(h, ln, st))
+        self.n, self.start, self.total = tuple(ln), tuple(st), tuple(ln)
+
+    upload = LidDrivenCavityAA.upload
+    download_macro = LidDrivenCavityAA.download_macro
+    download_f = LidDrivenCavityAA.download_f
+    launch_count = LidDrivenCavityAA.launch_count
+    device_bytes = LidDrivenCavityAA.device_bytes
+
+    @property
+    def slices(self):
+        return tuple(slice(s, s + n) for s, n in zip(self.start, self.n))
+
+
+class LidDrivenCavityAAGroup(LidDrivenCavityAA):
+    """LidDrivenCavityAA(total, nranks=P, dims=None, devices=None): P blocks in this process, total = the GLOBAL lattice"""
+
+    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0, nranks=2, dims=None, devices=None):
+        lib = L.lib()
+        d = L.AaDesc()
+        L.check(lib.mglc_aa_desc_init(C.byref(d), *total, Re, U0, rho0))
+        d.arith = {"fast": L.ARITH_FAST, "strict": L.ARITH_STRICT}[arith]
+        d.collision = {"mrt": L.MRT_LID, "bgk": L.BGK}[collision]
+        d.device = device
+        self.desc, self.total, self.tauf = d, tuple(total), d.tau
+        self._h = None
+        self._g = C.c_void_p()
+        cd = (C.c_int * 3)(*dims) if dims else None
+        dev = (C.c_int * nranks)(*devices) if devices is not None else None
+        L.check(lib.mglc_aa_group_create(C.byref(self._g), C.byref(d), nranks, cd, dev))
+        got = (C.c_int * 3)()
+        L.check(lib.mglc_aa_group_dims(self._g, got))
+        self.dims = tuple(got)
+        self.blocks = []
+        for r in range(nranks):
+            h = C.c_void_p()
+            L.check(lib.mglc_aa_group_rank(self._g, r, C.byref(h)))
+            self.blocks.append(_Block(h))
+
+    def close(self):
+        if self._g:
+            L.lib().mglc_aa_group_destroy(self._g)
+            self._g = None
+
+    def initial(self):
+        L.check(L.lib().mglc_aa_group_initial(self._g))
+
+    def step(self, n=1):
+        L.check(L.lib().mglc_aa_group_step(self._g, n))
+
+    def step_timed(self, n=1):
+        ms = C.c_float()
+        L.check(L.lib().mglc_aa_group_step_timed(self._g, n, C.byref(ms)))
+        return ms.value
+
+    def check(self):
+        e = C.c_double()
+        L.check(L.lib().mglc_aa_group_check(self._g, C.byref(e)))
+        return e.value
+
+    def sync(self):
+        L.check(L.lib().mglc_aa_group_sync(self._g))
+
+    def launch_count(self):
+        return sum(b.launch_count() for b in self.blocks)
+
+    def device_bytes(self):
+        return sum(b.device_bytes() for b in self.blocks)
+
+    def upload(self, f=None, rho=None, u=None, v=None, w=None):
+        self.sync()
+        for b in self.blocks:
+            part = [None if a is None else np.asfortranarray(np.asarray(a)[((slice(None),) if i == 0 else ()) + b.slices])
+                    for i, a in enumerate((f, rho, u, v, w))]
+            b.upload(*part)
+
+    def download_macro(self):
+        self.sync()
+        out = {k: np.empty(self.total, order="F") for k in ("rho", "u", "v", "w")}
+        for b in self.blocks:
+            m = b.download_macro()
+            for k in out:
+                out[k][b.slices] = m[k]
+        return out
+
+    def download_f(self):
+        self.sync()
+        f = np.empty((19,) + self.total, order="F")
+        for b in self.blocks:
+            f[(slice(None),) + b.slices] = b.download_f()
         return f

@@ -137,3 +137,85 @@ def test_error_behaviour():
     with pytest.raises(mg.MglcError):
         sim.upload(rho=np.ones((8, 8, 8)))            # fields alone cannot be replaced in that state
     sim.close()
+
+
+# ---- decomposed lattices: blocks in one process storing into each other (mglc_aa_group_*) --------------------------------------
+@pytest.mark.parametrize("nranks,dims,total", [(2, None, (34, 9, 7)), (4, None, (21, 18, 17)), (8, None, (19, 18, 17)),
+                                               (12, (2, 2, 3), (15, 14, 13)), (3, (3, 1, 1), (3, 5, 4)), (6, (1, 2, 3), (130, 7, 9))])
+@pytest.mark.parametrize("collision", ["mrt", "bgk"])
+def test_group_blocks_strict_bit_exact(nranks, dims, total, collision):
+    """uneven blocks (down to one cell thick) on one device: every way a run starts and ends, f from either layout, check()"""
+    wd = orc.LidWorld(total, 1, collision=collision)
+    wd.initial()
+    seeded(wd, 7)
+    sim = mg.LidDrivenCavityAA(total, arith="strict", collision=collision, nranks=nranks, dims=dims)
+    assert len(sim.blocks) == nranks and sim.tauf == wd.tauf
+    R = wd.ranks[0]
+    sim.upload(R.f, R.rho, R.u, R.v, R.w)
+    for n in (1, 2, 1, 3, 5):
+        wd.step(n); sim.step(n)
+        m = sim.download_macro()
+        for k in FIELDS:
+            assert np.array_equal(m[k], wd.gather(k)), (nranks, n, k)
+        assert np.array_equal(sim.download_f(), wd.gather("f")), (nranks, n)
+    assert np.isclose(sim.check(), wd.check(), rtol=1e-13, atol=0)
+    sim.close(); wd.close()
+
+
+def test_group_from_initial_and_reinitialised():
+    """the reference's own start on 2x2x2 blocks; initial() again in the middle of a run starts over (no stale parked halos)"""
+    total = (33, 31, 30)
+    wd = orc.LidWorld(total, 1)
+    wd.initial(); wd.step(25)
+    sim = mg.LidDrivenCavityAA(total, arith="strict", nranks=8)
+    sim.initial(); sim.step(3)
+    sim.initial(); sim.step(24); sim.step(1)
+    m = sim.download_macro()
+    for k in FIELDS:
+        assert np.array_equal(m[k], wd.gather(k)), k
+    assert np.array_equal(sim.download_f(), wd.gather("f"))
+    assert sim.launch_count() > 0
+    sim.close(); wd.close()
+
+
+def test_group_fast_equals_one_block_fast():
+    """fast arithmetic: the decomposed run does the same per-cell arithmetic as the one-block run -- identical results"""
+    total = (40, 37, 35)
+    one = mg.LidDrivenCavityAA(total, arith="fast")
+    grp = mg.LidDrivenCavityAA(total, arith="fast", nranks=4)
+    one.initial(); grp.initial()
+    one.step(60); grp.step(60)
+    a, b = one.download_macro(), grp.download_macro()
+    for k in FIELDS:
+        assert np.array_equal(a[k], b[k]), k
+    one.close(); grp.close()
+
+
+def test_group_member_calls_are_refused():
+    import ctypes as C
+    from mglc_b200 import _lib as L
+    sim = mg.LidDrivenCavityAA((12, 11, 10), nranks=2)
+    h = sim.blocks[0]._h
+    assert L.lib().mglc_aa_step(h, 1) == L.E_STATE
+    assert L.lib().mglc_aa_initial(h) == L.E_STATE
+    e = C.c_double()
+    assert L.lib().mglc_aa_check(h, C.byref(e)) == L.E_STATE
+    sim.initial(); sim.step(1)                          # POST layout now: a block upload is refused
+    with pytest.raises(L.MglcError):
+        sim.blocks[0].upload(rho=np.ones(sim.blocks[0].n, order="F"))
+    sim.close()
+
+
+def test_group_on_two_devices_if_present():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one device")
+    total = (48, 33, 31)
+    wd = orc.LidWorld(total, 1)
+    wd.initial(); wd.step(20)
+    sim = mg.LidDrivenCavityAA(total, arith="strict", nranks=2, devices=[0, 1])
+    sim.initial(); sim.step(20)
+    m = sim.download_macro()
+    for k in FIELDS:
+        assert np.array_equal(m[k], wd.gather(k)), k
+    sim.close(); wd.close()

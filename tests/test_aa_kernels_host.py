@@ -32,6 +32,11 @@ def shim(tmp_path_factory):
     S.aa_shim_step.argtypes = [C.c_void_p, C.c_int]
     S.aa_shim_download_macro.argtypes = [C.c_void_p] + [dp] * 4
     S.aa_shim_download_f.argtypes = [C.c_void_p, dp, C.c_longlong]
+    S.aa_shim_create_block.restype = C.c_void_p
+    S.aa_shim_create_block.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int] + [C.c_double] * 4 + [C.c_int] * 2
+    S.aa_shim_set_peers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    S.aa_shim_world_step.restype = C.c_longlong
+    S.aa_shim_world_step.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     return S
 
 
@@ -142,3 +147,113 @@ def test_fast_build_tracks_the_oracle(shim):
             rel = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
             assert rel <= 1e-12 and np.abs(a - b).max() <= 1e-10, (n, k, rel)
     sim.close(); wd.close()
+
+
+# ---- decomposed lattices: the PEER build of the same kernels, blocks wired to each other's lattices ---------------------------
+# direction d of a message (ex_sendrecv.f90:12-123): faces 0..5 = +x,-x,+y,-y,+z,-z, edges 7..18 = the population crossing it
+EX = [0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0]
+EY = [0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1]
+EZ = [0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1]
+FACE = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+
+
+class AaWorld:
+    """the blocks of the oracle world wd (nprocs > 1, same decomposition), each an in-place lattice of the host shim"""
+
+    def __init__(self, S, wd, strict, bgk=False):
+        self.S, self.wd = S, wd
+        self.dims = tuple(wd.dims)
+        self.subs = []
+        for R in wd.ranks:
+            co = R.coords
+            wall = (C.c_int * 6)(*[int(co[q // 2] == (self.dims[q // 2] - 1 if q % 2 == 0 else 0)) for q in range(6)])
+            self.subs.append(S.aa_shim_create_block(*R.n, wall, wall[4], wd.Snu, wd.Sq, wd.U0, wd.rho0, int(bgk), int(strict)))
+        rank_of = {tuple(R.coords): r for r, R in enumerate(wd.ranks)}
+        for r, R in enumerate(wd.ranks):
+            nbr = (C.c_void_p * 19)()
+            for d in range(19):
+                if d == 6:
+                    continue
+                e = FACE[d] if d < 6 else (EX[d], EY[d], EZ[d])
+                other = rank_of.get(tuple(c + x for c, x in zip(R.coords, e)))
+                nbr[d] = self.subs[other] if other is not None else None
+            S.aa_shim_set_peers(self.subs[r], nbr)
+        self.arr = (C.c_void_p * len(self.subs))(*self.subs)
+
+    def upload(self):
+        for h, R in zip(self.subs, self.wd.ranks):
+            a = [np.asfortranarray(x) for x in (R.f, R.rho, R.u, R.v, R.w)]
+            self.S.aa_shim_upload(h, *[x.ctypes.data_as(dp) for x in a])
+
+    def step(self, n, order=0):
+        return self.S.aa_shim_world_step(self.arr, len(self.subs), n, order)
+
+    def gather(self, what, chunk=97):
+        lead = (19,) if what == "f" else ()
+        glob = np.empty(lead + tuple(self.wd.total), order="F")
+        for h, R in zip(self.subs, self.wd.ranks):
+            n = tuple(R.n)
+            if what == "f":
+                out = np.empty((19,) + n, order="F")
+                self.S.aa_shim_download_f(h, out.ctypes.data_as(dp), chunk)
+            else:
+                m = [np.empty(n, order="F") for _ in range(4)]
+                self.S.aa_shim_download_macro(h, *[x.ctypes.data_as(dp) for x in m])
+                out = m[("rho", "u", "v", "w").index(what)]
+            sl = tuple(slice(s, s + k) for s, k in zip(R.start, n))
+            glob[(slice(None),) * len(lead) + sl] = out
+        return glob
+
+    def close(self):
+        for h in self.subs:
+            self.S.aa_shim_destroy(h)
+
+
+def seeded_world(wd, seed):
+    rng = np.random.default_rng(seed)
+    for R in wd.ranks:
+        R.f[...] *= 1.0 + 0.05 * rng.uniform(-1, 1, R.f.shape)
+        R.rho[...] = 1.0 + 0.02 * rng.uniform(-1, 1, R.rho.shape)
+        for k in ("u", "v", "w"):
+            getattr(R, k)[...] = 0.05 * rng.uniform(-1, 1, R.rho.shape)
+
+
+@pytest.mark.parametrize("nprocs,total", [(2, (7, 6, 9)), (4, (7, 9, 8)), (8, (9, 8, 7)), (12, (9, 7, 10)), (3, (5, 4, 3))])
+@pytest.mark.parametrize("order", [0, 1])
+def test_decomposed_blocks_store_into_each_other_bit_exact(shim, nprocs, total, order):
+    """P blocks (uneven, down to one cell thick), every launch storing into the neighbours: equal to the single-rank oracle
+    whichever block of a launch runs first -- nothing a launch writes into a neighbour is read over there in the same launch"""
+    ref = orc.LidWorld(total, 1)
+    ref.initial()
+    wd = orc.LidWorld(total, nprocs)            # only its decomposition and its state at upload time are used
+    wd.initial()
+    seeded_world(wd, 11)
+    for k in ("rho", "u", "v", "w", "f"):       # the same perturbed state on the single-rank oracle
+        getattr(ref.ranks[0], k)[...] = wd.gather(k)
+    sim = AaWorld(shim, wd, strict=True)
+    sim.upload()
+    for n in (1, 2, 3, 5):
+        ref.step(n)
+        sim.step(n, order)
+        for k in ("rho", "u", "v", "w", "f"):
+            assert np.array_equal(sim.gather(k), ref.gather(k)), (nprocs, n, k)
+    sim.close(); wd.close(); ref.close()
+
+
+def test_decomposed_blocks_bgk_and_fast_build(shim):
+    total = (10, 9, 8)
+    for collision, strict in (("bgk", True), ("mrt", False)):
+        ref = orc.LidWorld(total, 1, collision=collision)
+        ref.initial()
+        wd = orc.LidWorld(total, 4, collision=collision)
+        wd.initial()
+        sim = AaWorld(shim, wd, strict=strict, bgk=collision == "bgk")
+        sim.upload()
+        ref.step(21); sim.step(21)
+        for k in ("rho", "u", "v", "w"):
+            a, b = sim.gather(k), ref.gather(k)
+            if strict:
+                assert np.array_equal(a, b), (collision, k)
+            else:
+                assert np.abs(a - b).max() <= 1e-13, (collision, k)
+        sim.close(); wd.close(); ref.close()

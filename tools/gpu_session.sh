@@ -220,6 +220,22 @@ m8() {   # 8 GPUs: the driver's own N = 8 line (parity + weak + transports + e2e
     timeout 400 $TR bench.py --gpus 8 --workload particles --steps 10 --warmup 3 --no-e2e > $O/bench_particles_8gpu.json 2> $O/b5.err; tail -c 1000 $O/bench_particles_8gpu.json; tail -n 2 $O/b5.err
 }
 
+m9() {   # 2 GPUs: single-lattice (AA) blocks storing into each other; push vs direct at 384^3 blocks
+    (timeout 900 python -m pytest tests/test_aa_gpu.py -q -m gpu -x > $O/pytest_aa.log 2>&1; echo "pytest rc=$?" >> $O/pytest_aa.log); tail -n 5 $O/pytest_aa.log
+    for d in 2,1,1 1,2,1 1,1,2; do
+        timeout 300 python tools/group_bench.py --aa --gpus 2 --dims $d --size 768 --steps 20 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    done
+    timeout 300 python tools/group_bench.py --aa --gpus 1 --dims 1,1,1 --size 768 --steps 20 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    timeout 300 python tools/group_bench.py --aa --gpus 2 --dims 1,1,2 --size 896 --steps 10 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    for d in 2,1,1 1,1,2; do for hm in push direct; do
+        timeout 300 $TR bench.py --gpus 2 --size 384 --steps 40 --warmup 5 --no-e2e --no-parity --no-cpu --no-extras --dims $d --halo $hm > $O/bench_lid384_2gpu_${d//,/}_$hm.json 2> $O/b1z.err
+        python -c "
+import json;d=json.loads(open('$O/bench_lid384_2gpu_${d//,/}_$hm.json').read().strip().splitlines()[-1]);print('lid 384 dims $d $hm', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done; done
+    tail -n 5 $O/err.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30
