@@ -445,51 +445,73 @@ def thermal2d(args, rank, local_rank, world):
 
 
 def lid_aa(args, rank, local_rank, world):
-    """bench.py --workload lid_aa: the D3Q19 lid-driven cavity on ONE lattice (AA-pattern storage) at a size the
-    two-lattice path cannot hold on one B200 (default 896^3 = 1.59x the cells of 768^3; 114 GB of lattice + 23 GB of fields).
-    Roofline: 304 B/cell per launch, as for the ping-pong kernel."""
+    """bench.py --workload lid_aa: the D3Q19 lid-driven cavity on ONE lattice per block (AA-pattern storage) at a
+    size the two-lattice path cannot hold on a B200 (default 896^3 per GPU = 1.59x the cells of 768^3; 114 GB of lattice +
+    23 GB of fields).  N > 1: one block per GPU (weak), the blocks store into each other's lattices (mglc_aa_create_comm), parity
+    against the oracle in the same run.  Roofline: 304 B/cell per launch, as for the two-lattice kernel."""
     import torch
 
     import bench as B
     import mglc_b200 as mg
 
-    if world > 1:
-        if rank == 0:
-            print(json.dumps({"metric": "MLUPS", "value": None, "note": "lid_aa bench runs on one GPU (the AA path is single-subdomain)"}))
-        return
-    torch.cuda.set_device(local_rank)
+    D = B.Dist(rank, local_rank, world)
+    comm = D.communicator(mg)
     n = args.size or 896
-    free, _ = torch.cuda.mem_get_info()
+    free = D.min(float(torch.cuda.mem_get_info()[0]))
     reduced = False
     need = lambda e: 19 * (((e + 17 + 15) // 16) * 16) * (e + 2) ** 2 * 8 + 4 * e ** 3 * 8 + (1 << 28)
     while need(n) > free and n > 64:
         n -= 64; reduced = True
-    sim = mg.LidDrivenCavityAA((n, n, n), arith=args.arith, device=local_rank)
+    dims = tuple(int(x) for x in args.dims.split(",")) if args.dims else tuple(sorted(B.dims_create(world)))
+    gn = tuple(n * d for d in dims)
+    parity = None
+    if comm is not None and not args.no_parity:
+        sys.path.insert(0, os.path.join(B.ROOT, "tests", "dist"))
+        import parity_suite as ps
+        parity = ps.lid_aa(comm, rank, world)
+        if D.max(1.0 if (rank == 0 and ps.failed(parity)) else 0.0) > 0:
+            if rank == 0:
+                print(json.dumps({"metric": "MLUPS", "value": None, "parity": parity, "error": "parity mismatch against the oracle"}), flush=True)
+            comm.close(); D.close()
+            sys.exit(3)
+        parity = dict(parity, case="lid 41x37x35, 12 steps, strict, vs oracle/lid3d.c on one emulated rank")
+    sim = mg.LidDrivenCavityAA(gn, arith=args.arith, comm=comm, dims=dims) if comm else mg.LidDrivenCavityAA(gn, arith=args.arith, device=local_rank)
     sim.initial()
     sim.step(max(args.warmup, 3)); sim.sync()
     l0 = sim.launch_count()
     sampler = B.ClockSampler(local_rank); sampler.start()
-    ms = sim.step_timed(args.steps)
+    D.barrier()
+    ms = D.max(sim.step_timed(args.steps))
+    D.barrier()
     clocks = sampler.stop()
-    launches = sim.launch_count() - l0
+    launches = D.sum(float(sim.launch_count() - l0))
     nbytes = sim.device_bytes()
     m = sim.download_macro()
-    mass = float(m["rho"].sum()) / n ** 3
-    umax = float(abs(m["u"]).max())
+    cells_local = n ** 3
+    mass = D.sum(float(m["rho"].sum())) / (cells_local * world)
+    umax = D.max(float(abs(m["u"]).max()))
     sim.close()
-    cells = n ** 3
+    D.barrier()
+    if comm:
+        comm.close()
+    cells = cells_local * world
     peak, peak_src = B.hbm_peak()
-    achieved = 304.0 * cells * args.steps / (ms * 1e-3) / 1e9
-    print(json.dumps({
-        "metric": "MLUPS", "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lid_driven_cavity_d3q19_mrt_{n}x{n}x{n}_single_lattice", "Re": 1000.0, "U0": 0.1, "arith": args.arith,
-                   "storage": "SoA fp64, ONE lattice updated in place (AA pattern)", "device_bytes": nbytes, "reduced_to_fit": reduced,
-                   "mean_rho": mass, "max_u": umax,
-                   "l2": "lattice (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (19 * cells * 8 / 1e9)},
-        "roofline": {"bound": "hbm", "kernel": f"mglc::{args.arith}::k_aa_odd / k_aa_even", "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 304,
-                     "cells_per_launch": cells,
-                     "note": "whole step(K) call timed: the launches alternate k_aa_odd / k_aa_even, plus collision and macro at its ends"},
-        "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+    achieved = 304.0 * cells_local * args.steps / (ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "MLUPS", "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"lid_driven_cavity_d3q19_mrt_{n}x{n}x{n}_per_gpu_single_lattice", "global_lattice": list(gn),
+                       "decomposition": "x".join(map(str, dims)), "Re": 1000.0, "U0": 0.1, "arith": args.arith,
+                       "storage": "SoA fp64, ONE lattice per block updated in place (AA pattern)", "device_bytes_per_gpu": nbytes,
+                       "reduced_to_fit": reduced, "mean_rho": mass, "max_u": umax,
+                       "halo": None if world == 1 else "none packed: every launch stores into the neighbours' lattices (CUDA IPC), one flag barrier per launch",
+                       "l2": "lattice (%.1f GB per GPU) far exceeds the 126 MB L2; no flush needed" % (19 * cells_local * 8 / 1e9)},
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": f"mglc::{args.arith}::k_aa_odd / k_aa_even", "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_cell": 304,
+                         "cells_per_launch": cells_local,
+                         "note": "per GPU; whole step(K) call timed: the launches alternate k_aa_odd / k_aa_even, plus collision and macro at its ends"},
+            "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": int(launches)}), flush=True)
+    D.close()

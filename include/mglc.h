@@ -501,6 +501,11 @@ int mglc_aa_group_step(mglc_aa_group *g, int nsteps);
 int mglc_aa_group_step_timed(mglc_aa_group *g, int nsteps, float *ms);   /* longest block stream, ms */
 int mglc_aa_group_check(mglc_aa_group *g, double *errorU);
 int mglc_aa_group_sync(mglc_aa_group *g);
+/* decomposed, one process per block (collective over the communicator; gd->n = the GLOBAL lattice).  The handle is this rank's
+ * block: mglc_aa_initial / _step / _step_timed / _check (all-reduced) / _upload / _download_* are then collective calls made by
+ * every rank, as the reference's subroutines are.  The neighbours' lattices are mapped through CUDA IPC; where that is not
+ * possible (no NVLink / peer access) creation fails with MGLC_E_STATE: this path has no message transport. */
+int mglc_aa_create_comm(mglc_aa **h, const mglc_aa_desc *gd, mglc_comm *comm, const int *dims);
 
 /* ================= on-disk formats of the drivers' output()/backupData() (host-only) =================
  * All arrays are the reference's global (gathered) arrays, column-major (nx,ny,nz) -- what mglc_lbm_download_macro /

@@ -286,6 +286,7 @@ SIGNATURES = {
     "mglc_aa_group_step_timed": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
     "mglc_aa_group_check": (C.c_int, [_vp, _dp]),
     "mglc_aa_group_sync": (C.c_int, [_vp]),
+    "mglc_aa_create_comm": (C.c_int, [_vpp, C.POINTER(AaDesc), _vp, C.POINTER(C.c_int)]),
 }
 
 _lib = None

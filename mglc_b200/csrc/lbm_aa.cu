@@ -44,7 +44,15 @@ struct mglc_aa {
     struct mglc_aa_group *group;
     int rank, coords[3], dims[3], start[3], nbr[19];
     PeerTable peers;                 // peers.mask != 0: passed to the PEER build of the kernels
-    cudaEvent_t ev_done[2];          // this block's launch of epoch e has finished: ev_done[e & 1]
+    cudaEvent_t ev_done[2];          // group: this block's launch of epoch e has finished: ev_done[e & 1]
+    // one process per block (mglc_aa_create_comm): the neighbours' lattices are CUDA IPC mappings, launches are ordered by the
+    // flag words of k_halo_signal / k_halo_wait (word = 2 x the number of launches the block has finished)
+    mglc_comm *comm;
+    unsigned long long *flags;
+    int *d_err;
+    SyncTable sync;
+    long long epoch;
+    std::vector<void *> *ipc_opened;
 };
 struct mglc_aa_group {
     std::vector<mglc_aa *> m;
@@ -58,6 +66,14 @@ static inline long long aa_ncell(const mglc_aa *h) { return (long long)h->g.nx *
 static int aa_use(mglc_aa *h) {
     if (!h) { set_error("mglc_aa: null handle"); return MGLC_E_INVALID; }
     MGLC_CUDA(cudaSetDevice(h->d.device));
+    return MGLC_OK;
+}
+// the barrier's sticky error word (k_halo_wait): a run whose neighbours fell out of step never comes back as MGLC_OK
+static int aa_comm_status(mglc_aa *h) {
+    if (!h->comm || !h->d_err) return MGLC_OK;
+    int e = 0;
+    MGLC_CUDA(cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e) { set_error("mglc_aa: a neighbour did not reach the barrier within %.0f s (MGLC_HALO_TIMEOUT_S; ranks out of step?)", halo_timeout_seconds()); return MGLC_E_STATE; }
     return MGLC_OK;
 }
 static int aa_malloc(mglc_aa *h, double **p, long long count) {
@@ -84,7 +100,14 @@ extern "C" int mglc_aa_desc_init(mglc_aa_desc *d, int nx, int ny, int nz, double
 extern "C" int mglc_aa_destroy(mglc_aa *h) {
     if (!h) return MGLC_OK;
     cudaSetDevice(h->d.device);
+    if (h->comm && h->sync.mask && h->s && h->epoch > 0) {
+        // the neighbours may still be storing into this block: wait for their last launch (bounded by the barrier's timeout)
+        int e = 0;
+        if (cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost) == cudaSuccess && !e) launch_halo_wait(h->sync, (unsigned long long)h->epoch * 2, h->d_err, h->s);
+    }
     if (h->s) cudaStreamSynchronize(h->s);
+    if (h->ipc_opened) { for (void *p : *h->ipc_opened) cudaIpcCloseMemHandle(p); delete h->ipc_opened; }
+    cudaFree(h->flags); cudaFree(h->d_err);
     double *bufs[] = {h->A, h->rho, h->u, h->v, h->w, h->up, h->vp, h->wp, h->lid, h->scratch, h->stage};
     for (double *p : bufs) cudaFree(p);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -156,12 +179,16 @@ extern "C" int mglc_aa_sync(mglc_aa *h) {
     MGLC_TRY(aa_use(h));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaGetLastError());
-    return MGLC_OK;
+    return aa_comm_status(h);
 }
 
 // make this block's stream wait for the last launch of each neighbour (what they stored into this block is complete, and
 // they have finished reading what the next launch of this block will overwrite in them)
 static int aa_wait_neighbours(mglc_aa *h) {
+    if (h->comm) {
+        if (h->sync.mask && h->epoch > 0) h->launches += launch_halo_wait(h->sync, (unsigned long long)h->epoch * 2, h->d_err, h->s);
+        return MGLC_OK;
+    }
     mglc_aa_group *G = h->group;
     if (!G || G->epoch == 0) return MGLC_OK;
     for (int d = 0; d < 19; ++d) {
@@ -183,6 +210,7 @@ static int aa_ensure_stage(mglc_aa *h) {
 // initial(): L3/initial.f90:55-73 (rho = rho0, u = U0 on the lid plane, f = feq)
 static int aa_initial_impl(mglc_aa *h) {
     MGLC_TRY(aa_use(h));
+    if (h->comm) MGLC_TRY(aa_wait_neighbours(h));      // their last launch may still be storing into this block
     h->launches += launch_initial(h->g, h->p, h->A, h->rho, h->u, h->v, h->w, h->s);
     if (h->up) {
         const size_t b = (size_t)aa_ncell(h) * sizeof(double);
@@ -202,6 +230,7 @@ extern "C" int mglc_aa_initial(mglc_aa *h) {
 extern "C" int mglc_aa_upload(mglc_aa *h, const double *f, const double *rho, const double *u, const double *v, const double *w) {
     MGLC_TRY(aa_use(h));
     if (h->group && h->layout != AA_NATURAL) { set_error("mglc_aa_upload: the group is between two streaming steps"); return MGLC_E_STATE; }
+    if (h->comm) MGLC_TRY(aa_wait_neighbours(h));
     if (h->layout != AA_NATURAL && !f) { set_error("mglc_aa_upload: the lattice is between two streaming steps; upload f as well"); return MGLC_E_STATE; }
     if (f) {
         MGLC_TRY(aa_ensure_stage(h));
@@ -231,7 +260,7 @@ extern "C" int mglc_aa_download_macro(mglc_aa *h, double *rho, double *u, double
         if (dst[q]) MGLC_CUDA(cudaMemcpyAsync(dst[q], src[q], b, cudaMemcpyDeviceToHost, h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaGetLastError());
-    return MGLC_OK;
+    return aa_comm_status(h);
 }
 
 // f as the reference holds it after the last loop body (pre-collision): a transposed copy in the NATURAL layout, a gather
@@ -253,7 +282,7 @@ extern "C" int mglc_aa_download_f(mglc_aa *h, double *f) {
     }
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaGetLastError());
-    return MGLC_OK;
+    return aa_comm_status(h);
 }
 
 // one launch of the schedule aa_run() (lbm_aa.cuh) on one block
@@ -278,7 +307,18 @@ static long long aa_launch_op(mglc_aa *h, AaOp op) {
 // after the same number of loop bodies.
 static int aa_step_impl(mglc_aa *h, int nsteps) {
     if (nsteps < 0) { set_error("mglc_aa_step: nsteps=%d", nsteps); return MGLC_E_INVALID; }
-    h->launches += aa_run(h->layout, nsteps, [&](AaOp op) -> long long { return aa_launch_op(h, op); });
+    if (!h->comm || !h->sync.mask) {
+        h->launches += aa_run(h->layout, nsteps, [&](AaOp op) -> long long { return aa_launch_op(h, op); });
+        return MGLC_OK;
+    }
+    // one process per block: every launch is one epoch of the neighbour barrier (all ranks run the same schedule)
+    h->launches += aa_run(h->layout, nsteps, [&](AaOp op) -> long long {
+        long long n = 0;
+        if (h->epoch > 0) n += launch_halo_wait(h->sync, (unsigned long long)h->epoch * 2, h->d_err, h->s);
+        n += aa_launch_op(h, op);
+        ++h->epoch;
+        return n + launch_halo_signal(h->sync, (unsigned long long)h->epoch * 2, h->s);
+    });
     return MGLC_OK;
 }
 extern "C" int mglc_aa_step(mglc_aa *h, int nsteps) {
@@ -299,7 +339,7 @@ extern "C" int mglc_aa_step_timed(mglc_aa *h, int nsteps, float *ms) {
     MGLC_CUDA(cudaEventSynchronize(h->ev_t1));
     MGLC_CUDA(cudaGetLastError());
     MGLC_CUDA(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
-    return MGLC_OK;
+    return aa_comm_status(h);
 }
 
 // check(): L3/check.f90:12-34 (up, vp, wp are allocated on first use: 24 B/cell that a run without residual checks keeps free)
@@ -312,10 +352,11 @@ static int aa_check_partial(mglc_aa *h, double (&e)[2]) {
         MGLC_CUDA(cudaMemsetAsync(h->wp, 0, (size_t)n * 8, h->s));          // up = vp = wp = 0, L3/initial.f90:50-52
     }
     h->launches += launch_check(h->g, h->u, h->v, h->w, h->up, h->vp, h->wp, h->scratch, h->s);
+    if (h->comm && h->comm->nranks > 1) MGLC_NCCL(ncclAllReduce(h->scratch, h->scratch, 2, ncclDouble, ncclSum, h->comm->nccl, h->s));   // check.f90:27-28
     MGLC_CUDA(cudaMemcpyAsync(e, h->scratch, sizeof e, cudaMemcpyDeviceToHost, h->s));
     MGLC_CUDA(cudaStreamSynchronize(h->s));
     MGLC_CUDA(cudaGetLastError());
-    return MGLC_OK;
+    return aa_comm_status(h);
 }
 extern "C" int mglc_aa_check(mglc_aa *h, double *errorU) {
     if (!errorU) return MGLC_E_INVALID;
@@ -484,5 +525,130 @@ extern "C" int mglc_aa_group_sync(mglc_aa_group *G) {
     if (!G) return MGLC_E_INVALID;
     for (mglc_aa *h : G->m) { MGLC_TRY(aa_use(h)); MGLC_CUDA(cudaStreamSynchronize(h->s)); }
     MGLC_CUDA(cudaGetLastError());
+    return MGLC_OK;
+}
+
+// ================= a decomposed lattice, one process per block (torchrun / mpirun) =================
+// The same kernels and the same launch-by-launch schedule as the group above; the neighbours' lattices are CUDA IPC mappings
+// (exchanged once through the communicator), the launches are ordered by the flag words of k_halo_signal / k_halo_wait.
+// There is no message transport to fall back to on this path: without IPC peer mappings creation fails.
+namespace {
+struct AaIpcRecord { cudaIpcMemHandle_t A, flags; int ln[3]; };
+}
+extern "C" int mglc_aa_create_comm(mglc_aa **out, const mglc_aa_desc *gd, mglc_comm *comm, const int *dims_or_null) {
+    if (!out || !gd || !comm) { set_error("mglc_aa_create_comm: null argument"); return MGLC_E_INVALID; }
+    const int P = comm->nranks, r = comm->rank;
+    int dims[3] = {0, 0, 0};
+    if (dims_or_null && dims_or_null[0] > 0) for (int q = 0; q < 3; ++q) dims[q] = dims_or_null[q];
+    else mglc_dims_create(P, dims);
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[0] * dims[1] * dims[2] != P) {
+        set_error("mglc_aa_create_comm: dims %dx%dx%d do not multiply to %d ranks", dims[0], dims[1], dims[2], P);
+        return MGLC_E_INVALID;
+    }
+    mglc_aa_desc d = *gd;
+    int coords[3], start[3], wall[6];
+    mglc_cart_coords(dims, r, coords);
+    for (int q = 0; q < 3; ++q) {
+        MGLC_TRY(mglc_decompose_1d(gd->n[q], coords[q], dims[q], &d.n[q], &start[q]));
+        wall[2 * q] = coords[q] == dims[q] - 1;
+        wall[2 * q + 1] = coords[q] == 0;
+    }
+    d.device = comm->device;
+    mglc_aa *h = nullptr;
+    MGLC_TRY(aa_create_impl(&h, &d, wall, wall[4]));
+    auto fail = [&](int rc) { mglc_aa_destroy(h); return rc; };
+    h->comm = comm; h->rank = r;
+    for (int q = 0; q < 3; ++q) { h->coords[q] = coords[q]; h->dims[q] = dims[q]; h->start[q] = start[q]; }
+    for (int dd = 0; dd < 19; ++dd) {
+        if (dd == 6) continue;
+        const int e[3] = {dd < 6 ? (dd >> 1 == 0 ? 1 - 2 * (dd & 1) : 0) : h_ex[dd], dd < 6 ? (dd >> 1 == 1 ? 1 - 2 * (dd & 1) : 0) : h_ey[dd],
+                          dd < 6 ? (dd >> 1 == 2 ? 1 - 2 * (dd & 1) : 0) : h_ez[dd]};
+        const int c[3] = {coords[0] + e[0], coords[1] + e[1], coords[2] + e[2]};
+        mglc_cart_rank(dims, c, &h->nbr[dd]);
+    }
+    if (cudaMalloc((void **)&h->flags, 32 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc((void **)&h->d_err, sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->flags, 0, 32 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) return fail(MGLC_E_NOMEM);
+    if (P == 1) { *out = h; return MGLC_OK; }
+    // exchange the IPC handles of the lattices and the barrier words (collective)
+    AaIpcRecord mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = 1;
+    const unsigned long long magic = 0x6d67616100000000ull + (unsigned long long)r;
+    ok &= cudaMemcpy(h->flags + 31, &magic, sizeof magic, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaIpcGetMemHandle(&mine.A, h->A) == cudaSuccess;
+    ok &= cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
+    (void)cudaGetLastError();
+    mine.ln[0] = h->g.nx; mine.ln[1] = h->g.ny; mine.ln[2] = h->g.nz;
+    char *dev_all = nullptr;
+    std::vector<AaIpcRecord> all(P);
+    {
+        int rc = MGLC_OK;
+        auto step = [&]() -> int {
+            MGLC_CUDA(cudaMalloc((void **)&dev_all, (size_t)(P + 1) * sizeof(AaIpcRecord)));
+            MGLC_CUDA(cudaMemcpy(dev_all + (size_t)P * sizeof(AaIpcRecord), &mine, sizeof mine, cudaMemcpyHostToDevice));
+            MGLC_NCCL(ncclAllGather(dev_all + (size_t)P * sizeof(AaIpcRecord), dev_all, sizeof(AaIpcRecord), ncclChar, comm->nccl, h->s));
+            MGLC_CUDA(cudaMemcpyAsync(all.data(), dev_all, (size_t)P * sizeof(AaIpcRecord), cudaMemcpyDeviceToHost, h->s));
+            MGLC_CUDA(cudaStreamSynchronize(h->s));
+            return MGLC_OK;
+        };
+        rc = step();
+        cudaFree(dev_all);
+        if (rc) return fail(rc);
+    }
+    h->ipc_opened = new std::vector<void *>();
+    struct View { double *A; unsigned long long *flags; };
+    std::vector<View> by_rank(P, View{nullptr, nullptr});
+    std::vector<char> have(P, 0);
+    auto open = [&](const cudaIpcMemHandle_t &hd, void **p) {
+        if (cudaIpcOpenMemHandle(p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); *p = nullptr; return 0; }
+        h->ipc_opened->push_back(*p);
+        return 1;
+    };
+    memset(&h->peers, 0, sizeof h->peers);
+    memset(&h->sync, 0, sizeof h->sync);
+    for (int dd = 0; dd < 19 && ok; ++dd) {
+        const int n = h->nbr[dd];
+        if (dd == 6 || n < 0) continue;
+        if (!have[n]) {
+            ok &= open(all[n].A, (void **)&by_rank[n].A);
+            if (ok) ok &= open(all[n].flags, (void **)&by_rank[n].flags);
+            if (ok) {           // the mapping must start at the neighbour's own pointer, not at some enclosing block
+                unsigned long long seen = 0;
+                ok &= cudaMemcpy(&seen, by_rank[n].flags + 31, sizeof seen, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                      seen == 0x6d67616100000000ull + (unsigned long long)n;
+                (void)cudaGetLastError();
+            }
+            have[n] = 1;
+        }
+        if (!ok) break;
+        const Geom pg = make_geom(all[n].ln[0], all[n].ln[1], all[n].ln[2]);
+        h->peers.mask |= 1u << dd;
+        h->peers.F[dd] = by_rank[n].A; h->peers.sy[dd] = pg.sy; h->peers.sz[dd] = pg.sz; h->peers.sq[dd] = pg.sq;
+        h->peers.n[dd][0] = pg.nx; h->peers.n[dd][1] = pg.ny; h->peers.n[dd][2] = pg.nz;
+        h->sync.mask |= 1u << dd;
+        h->sync.signal[dd] = by_rank[n].flags + (dd < 6 ? (dd ^ 1) : h_opp[dd]);     // the neighbour sees me in the opposite direction
+        h->sync.wait[dd] = h->flags + dd;
+    }
+    // collective verdict: everybody or nobody
+    {
+        int *dev_ok = nullptr, rc = MGLC_OK;
+        auto step = [&]() -> int {
+            MGLC_CUDA(cudaMalloc((void **)&dev_ok, sizeof(int)));
+            MGLC_CUDA(cudaMemcpy(dev_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
+            MGLC_NCCL(ncclAllReduce(dev_ok, dev_ok, 1, ncclInt, ncclMin, comm->nccl, h->s));
+            MGLC_CUDA(cudaMemcpyAsync(&ok, dev_ok, sizeof ok, cudaMemcpyDeviceToHost, h->s));
+            MGLC_CUDA(cudaStreamSynchronize(h->s));
+            return MGLC_OK;
+        };
+        rc = step();
+        cudaFree(dev_ok);
+        if (rc) return fail(rc);
+    }
+    if (!ok) {
+        h->sync.mask = 0;      // nothing to wait for in destroy
+        set_error("mglc_aa_create_comm: the neighbours' lattices cannot be mapped (CUDA IPC / peer access); the single-lattice path has no message transport -- use mglc_lbm_create");
+        return fail(MGLC_E_STATE);
+    }
+    *out = h;
     return MGLC_OK;
 }

@@ -194,9 +194,14 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     const AaWalls wf = aa_walls(g, i, j, k);
     // Interior cells (no wall flag: all but the outermost shell) take straight-line paths: every address is the cell index plus
     // a block-uniform offset, no per-population wall test and no 64-bit select -- half the instructions of the general path.
-    // (a decomposed block: every cell on a face of the block takes the general path, its pushes may leave the block)
-    const bool shell = PEER ? (i == 1) | (i == g.nx) | (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz)
-                            : wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
+    // A decomposed block: a cell on a face shared with a neighbour takes the peer path (its pushes may leave the block); a cell
+    // that only touches walls of the global box takes the same general path as in a one-block run.  (The x-face lanes make
+    // one warp in twelve run two paths at 768 cells per row: the peer path is kept off them wherever x is not split.)
+    const bool on_face = (i == 1) | (i == g.nx) | (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz);
+    const bool at_wall = wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
+    const bool peer_cell = PEER && ((i == g.nx && !g.wall[0]) | (i == 1 && !g.wall[1]) | (j == g.ny && !g.wall[2]) |
+                                    (j == 1 && !g.wall[3]) | (k == g.nz && !g.wall[4]) | (k == 1 && !g.wall[5]));
+    const bool shell = PEER ? on_face : at_wall;
     double f[19], fp[19];
     if (!shell) {
         f[0] = __ldg(Ain + c);
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
             fp[11] = __dsub_rn(fp[11], __dmul_rn(r6, p.U0));
             fp[12] = __dsub_rn(fp[12], __dmul_rn(r6, -p.U0));
         }
-        if (PEER) { AA_FOR_ALL(AA_PUSH_PEER) }
+        if (PEER && peer_cell) { AA_FOR_ALL(AA_PUSH_PEER) }
         else { AA_FOR_ALL(AA_PUSH) }
     }
 }

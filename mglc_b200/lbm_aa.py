@@ -11,12 +11,16 @@ from . import _lib as L
 
 
 class LidDrivenCavityAA:
+    """LidDrivenCavityAA(total): one subdomain.  LidDrivenCavityAA(total, nranks=P, dims=None, devices=None): P blocks in this
+    process.  LidDrivenCavityAA(total, comm=Communicator(...), dims=None): this process holds one block of the global lattice
+    `total` (one process per GPU); every method is then a collective call, arrays are the block's (self.n, self.start)."""
+
     def __new__(cls, total, *args, nranks=1, **kw):
         if cls is LidDrivenCavityAA and nranks > 1:
             return super().__new__(LidDrivenCavityAAGroup)
         return super().__new__(cls)
 
-    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0, nranks=1):
+    def __init__(self, total, Re=1000.0, U0=0.1, rho0=1.0, arith="fast", collision="mrt", device=0, nranks=1, comm=None, dims=None):
         lib = L.lib()
         d = L.AaDesc()
         L.check(lib.mglc_aa_desc_init(C.byref(d), *total, Re, U0, rho0))
@@ -25,7 +29,16 @@ class LidDrivenCavityAA:
         d.device = device
         self.desc, self.total, self.tauf = d, tuple(total), d.tau
         self._h = C.c_void_p()
-        L.check(lib.mglc_aa_create(C.byref(self._h), C.byref(d)))
+        self.global_total, self.start, self._comm = tuple(total), (0, 0, 0), comm
+        if comm is None:
+            L.check(lib.mglc_aa_create(C.byref(self._h), C.byref(d)))
+        else:
+            cd = (C.c_int * 3)(*dims) if dims else None
+            L.check(lib.mglc_aa_create_comm(C.byref(self._h), C.byref(d), comm._h, cd))
+            ln, st = (C.c_int * 3)(), (C.c_int * 3)()
+            L.check(lib.mglc_aa_get_block(self._h, ln, st))
+            self.total, self.start = tuple(ln), tuple(st)       # the arrays of this rank are its block's
+        self.n = self.total
 
     def close(self):
         if self._h:

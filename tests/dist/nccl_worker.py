@@ -31,16 +31,13 @@ def main():
             print(msg, flush=True)
 
     comm = mg.Communicator(world, rank, local, bcast)
-    verdicts = {
-        "lid": ps.lid(comm, rank, world, log=log),
-        "thermal": ps.thermal(comm, rank, world, log=log),
-        "jacobi": ps.jacobi(comm, rank, world, log=log),
-        "particles": ps.particles(comm, rank, world, log=log),
-        "drivers_2d": ps.drivers_2d(comm, rank, world, log=log),
-    }
+    only = [c for c in os.environ.get("MGLC_PARITY_ONLY", "").split(",") if c]       # e.g. lid_aa,jacobi while developing
+    verdicts = {name: getattr(ps, name)(comm, rank, world, log=log)
+                for name in ("lid", "lid_aa", "thermal", "jacobi", "particles", "drivers_2d") if not only or name in only}
     ok = not ps.failed(verdicts)
     # on an NVLink box the CUDA IPC mappings of the direct path must come up (unless they were switched off on purpose)
-    if rank == 0 and verdicts["lid"].get("direct") == "unavailable" and not os.environ.get("MGLC_NO_DIRECT"):
+    if rank == 0 and not os.environ.get("MGLC_NO_DIRECT") and \
+            (verdicts.get("lid", {}).get("direct") == "unavailable" or verdicts.get("lid_aa", {}).get("single_lattice") == "unavailable"):
         ok = False
     comm.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

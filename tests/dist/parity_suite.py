@@ -95,6 +95,51 @@ def lid(comm, rank, world, total=(41, 37, 35), nsteps=12, transports=("direct", 
     return out
 
 
+def lid_aa(comm, rank, world, total=(41, 37, 35), nsteps=12, log=None):
+    """the same cavity on ONE lattice per block (AA-pattern storage, mglc_aa_create_comm): the blocks store into each other's
+    lattices through the CUDA IPC mappings, one neighbour barrier per launch.  step(5); step(n-5) crosses both layouts; then
+    initial() again in the middle of a run, as for the two-lattice transports"""
+    ref = None
+    if rank == 0:
+        orc = _oracle()
+        wd = orc.LidWorld(total, 1)
+        wd.initial(); wd.step(nsteps)
+        ref = {k: wd.gather(k) for k in ("rho", "u", "v", "w", "f")}
+        ref["errorU"] = wd.check()
+        wd.close()
+    try:
+        sim = mg.LidDrivenCavityAA(total, comm=comm, arith="strict")
+    except L.MglcError as e:           # collective verdict inside the library: every rank raises or none does
+        if log:
+            log(f"lid_aa: unavailable ({e})")
+        return {"single_lattice": "unavailable"}
+    same = True
+    for scenario in ("split", "reinit"):
+        sim.initial()
+        if scenario == "split":
+            sim.step(5); sim.step(nsteps - 5)
+        else:
+            sim.step(3); sim.initial(); sim.step(nsteps)
+        m = sim.download_macro()
+        blocks = {k: gather_blocks((sim.start, m[k]), rank, world) for k in ("rho", "u", "v", "w")}
+        fb = gather_blocks((sim.start, sim.download_f()), rank, world)
+        err = sim.check()
+        if rank == 0:
+            for k in blocks:
+                ok = np.array_equal(assemble(blocks[k], total), ref[k])
+                same &= ok
+                if log:
+                    log(f"lid_aa {scenario} {k}: {'bit-exact' if ok else 'MISMATCH'}")
+            ok = np.array_equal(assemble(fb, total, (19,)), ref["f"])
+            same &= ok
+            if scenario == "split":
+                same &= bool(np.isclose(err, ref["errorU"], rtol=1e-12))
+            if log:
+                log(f"lid_aa {scenario} f: {'bit-exact' if ok else 'MISMATCH'}; errorU {err} vs {ref['errorU']}")
+    sim.close()
+    return {"single_lattice": "bit-exact" if same else "MISMATCH"}
+
+
 def thermal(comm, rank, world, total=(27, 25, 23), nsteps=10, transports=("direct", "push", "nccl_overlap", "nccl_blocking"), log=None):
     """3-D thermal cavity (f + g exchange), uneven blocks"""
     out = {}

@@ -236,6 +236,21 @@ import json;d=json.loads(open('$O/bench_lid384_2gpu_${d//,/}_$hm.json').read().s
     tail -n 5 $O/err.txt
 }
 
+m10() {   # 2 GPUs: single-lattice blocks, one process per GPU (IPC + flag barrier per launch); NVLink counters of the push
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (MGLC_PARITY_ONLY=lid_aa timeout 300 $TR tests/dist/nccl_worker.py > $O/nccl_worker_lid_aa.log 2>&1; echo "worker rc=$?" >> $O/nccl_worker_lid_aa.log); tail -n 6 $O/nccl_worker_lid_aa.log
+    for d in 1,1,2 2,1,1; do
+        timeout 300 $TR bench.py --gpus 2 --workload lid_aa --size 768 --steps 20 --warmup 3 --dims $d > $O/bench_lid_aa_2gpu_${d//,/}.json 2> $O/b1.err; tail -c 1800 $O/bench_lid_aa_2gpu_${d//,/}.json; tail -n 3 $O/b1.err
+    done
+    timeout 300 python tools/group_bench.py --aa --gpus 2 --dims 1,1,2 --size 768 --steps 20 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    timeout 300 python tools/group_bench.py --aa --gpus 2 --dims 2,1,1 --size 768 --steps 20 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    timeout 300 python tools/group_bench.py --aa --gpus 1 --dims 1,1,1 --size 768 --steps 20 >> $O/aa_group_2gpu.jsonl 2>> $O/err.txt; tail -n 1 $O/aa_group_2gpu.jsonl
+    ncu --query-metrics 2>/dev/null | grep -i "nvl" | head -40 > $O/ncu_nvlink_metrics.txt; wc -l $O/ncu_nvlink_metrics.txt; head -12 $O/ncu_nvlink_metrics.txt
+    MGLC_HALO_MODE=3 timeout 300 $NCU --metrics nvltx__bytes.sum,nvlrx__bytes.sum,gpu__time_duration.sum -k regex:k_push_halos -s 4 -c 4 --csv --log-file $O/ncu_nvlink_push_halos.csv \
+        python tools/group_bench.py --gpus 2 --dims 1,1,2 --size 512 --steps 4 > $O/b2.log 2>&1; echo "ncu nvlink rc=$?"; tail -n 6 $O/ncu_nvlink_push_halos.csv
+    tail -n 5 $O/err.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30

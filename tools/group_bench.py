@@ -23,7 +23,8 @@ def main():
     dims = tuple(int(x) for x in a.dims.split(",")) if a.dims else mg.dims_create(a.gpus)
     total = tuple(a.size * d for d in dims)
     if a.aa:
-        sim = mg.LidDrivenCavityAA(total, nranks=a.gpus, dims=dims, devices=list(range(a.gpus)), arith="fast")
+        sim = mg.LidDrivenCavityAA(total, nranks=a.gpus, dims=dims, devices=list(range(a.gpus)), arith="fast") if a.gpus > 1 \
+            else mg.LidDrivenCavityAA(total, arith="fast")
     else:
         Driver = mg.BuoyancyDrivenCavity if a.thermal else mg.LidDrivenCavity
         sim = Driver(total, nprocs=a.gpus, dims=dims, devices=list(range(a.gpus)), arith="fast")
