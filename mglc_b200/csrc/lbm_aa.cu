@@ -455,7 +455,7 @@ extern "C" int mglc_aa_group_rank(mglc_aa_group *G, int r, mglc_aa **h) {
 extern "C" int mglc_aa_get_block(mglc_aa *h, int *ln, int *start) {
     if (!h || !ln || !start) return MGLC_E_INVALID;
     ln[0] = h->g.nx; ln[1] = h->g.ny; ln[2] = h->g.nz;
-    for (int q = 0; q < 3; ++q) start[q] = h->group ? h->start[q] : 0;
+    for (int q = 0; q < 3; ++q) start[q] = (h->group || h->comm) ? h->start[q] : 0;
     return MGLC_OK;
 }
 extern "C" int mglc_aa_group_initial(mglc_aa_group *G) {

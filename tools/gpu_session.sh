@@ -251,6 +251,14 @@ m10() {   # 2 GPUs: single-lattice blocks, one process per GPU (IPC + flag barri
     tail -n 5 $O/err.txt
 }
 
+m11() {   # 2 GPUs: single-lattice blocks, one process per GPU, after the block-offset fix
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (MGLC_PARITY_ONLY=lid_aa timeout 300 $TR tests/dist/nccl_worker.py > $O/nccl_worker_lid_aa.log 2>&1; echo "worker rc=$?" >> $O/nccl_worker_lid_aa.log); tail -n 6 $O/nccl_worker_lid_aa.log
+    for d in 1,1,2 2,1,1; do
+        timeout 300 $TR bench.py --gpus 2 --workload lid_aa --size 768 --steps 20 --warmup 3 --dims $d > $O/bench_lid_aa_2gpu_${d//,/}.json 2> $O/b1.err; tail -c 1800 $O/bench_lid_aa_2gpu_${d//,/}.json; tail -n 3 $O/b1.err
+    done
+}
+
 "$S"
 clk
 ls -la $O | tail -30
