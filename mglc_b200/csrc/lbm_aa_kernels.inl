@@ -46,6 +46,10 @@ __device__ __forceinline__ void aa_collide(const double (&f)[19], double rho, do
     if (BGK) d3q19_collide_bgk(f, rho, u, v, w, p.Snu, fp);
     else d3q19_collide(f, rho, u, v, w, p.Snu, p.Sq, fp);
 }
+// Cache hints and occupancy were measured on the two bulk kernels (640^3, 100 steps, profiles/r2q_aa_memop_640.txt): loads as
+// ld.global.lu / .cs 1.9 % slower than .nc, stores as st.global.cs / .wt 9-11 % slower than plain stores (the L2 merges the 19
+// store streams into full lines before writing back), 6 CTAs/SM (80 registers) 5.9 % slower, 4 CTAs/SM (no spill in
+// k_aa_even) 1 % slower.  So: non-coherent loads, plain stores, 5 CTAs/SM.
 // (a, opp(a), ex, ey, ez) of L3/commondata.f90:32-40
 #define AA_FOR_ALL(X)                                                                                                   \
     X(1, 2, 1, 0, 0)    X(2, 1, -1, 0, 0)   X(3, 4, 0, 1, 0)    X(4, 3, 0, -1, 0)   X(5, 6, 0, 0, 1)    X(6, 5, 0, 0, -1)   \
@@ -192,22 +196,36 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     if (i > g.nx) return;
     const long long sq = g.sq, sy = g.sy, sz = g.sz, c = g.idx(0, i, j, k);
     const AaWalls wf = aa_walls(g, i, j, k);
-    // Interior cells (no wall flag: all but the outermost shell) take straight-line paths: every address is the cell index plus
-    // a block-uniform offset, no per-population wall test and no 64-bit select -- half the instructions of the general path.
-    // A decomposed block: a cell on a face shared with a neighbour takes the peer path (its pushes may leave the block); a cell
-    // that only touches walls of the global box takes the same general path as in a one-block run.  (The x-face lanes make
-    // one warp in twelve run two paths at 768 cells per row: the peer path is kept off them wherever x is not split.)
-    const bool on_face = (i == 1) | (i == g.nx) | (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz);
-    const bool at_wall = wf.xp | wf.xm | wf.yp | wf.ym | wf.zp | wf.zm;
+    // Three paths, chosen per WARP (j, k are block-uniform, and whether a warp holds the first or the last cell of a row follows
+    // from its first index), so that no warp runs two of them:
+    //   0  interior: every address is the cell index plus a block-uniform offset, no wall test, no 64-bit select;
+    //   1  the row is interior in y and z, the warp holds an x wall: the ten populations with an x component choose between
+    //      the neighbour and the bounce-back slot of the cell itself (one select per address); the other nine as path 0.
+    //      (Per-lane branching here made one warp in twelve run path 0 AND the general path: 0.5 ms of a 22.4 ms step.)
+    //   2  general: rows on a y or z face of the block, and -- decomposed blocks -- warps holding a cell of an x face shared
+    //      with a neighbour; a cell on a shared face pushes through AA_PUSH_PEER, any other cell as in a one-block run.
+    const int i0 = 1 + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+    const bool warp_lo = i0 == 1, warp_hi = (g.nx >= i0) & (g.nx - i0 < 32);
+    const bool yz_face = (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz);
+    const bool x_shared = PEER && ((warp_lo && !g.wall[1]) | (warp_hi && !g.wall[0]));
+    const int path = (yz_face | x_shared) ? 2 : ((warp_lo | warp_hi) ? 1 : 0);
     const bool peer_cell = PEER && ((i == g.nx && !g.wall[0]) | (i == 1 && !g.wall[1]) | (j == g.ny && !g.wall[2]) |
                                     (j == 1 && !g.wall[3]) | (k == g.nz && !g.wall[4]) | (k == 1 && !g.wall[5]));
-    const bool shell = PEER ? on_face : at_wall;
     double f[19], fp[19];
-    if (!shell) {
+    if (path == 0) {
         f[0] = __ldg(Ain + c);
 #define AA_PULL_IN(a, o, dx, dy, dz) f[a] = __ldg(Ain + ((o) * sq + (c - (dz) * sz - (dy) * sy - (dx))));
         AA_FOR_ALL(AA_PULL_IN)
 #undef AA_PULL_IN
+    } else if (path == 1) {
+        f[0] = __ldg(Ain + c);
+#define AA_PULL_X(a, o, dx, dy, dz)                                                                                  \
+    {                                                                                                                \
+        const bool wall_ = ((dx) == 1 && wf.xm) || ((dx) == -1 && wf.xp);                                           \
+        f[a] = __ldg(Ain + (wall_ ? (a) * sq + c : (o) * sq + (c - (dz) * sz - (dy) * sy - (dx))));                  \
+    }
+        AA_FOR_ALL(AA_PULL_X)
+#undef AA_PULL_X
     } else {
         AA_PULL_ALL();
         AA_LID_PULL(rho_lid_in);
@@ -216,10 +234,18 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     d3q19_macro(f, rho, u, v, w);
     aa_collide<BGK>(f, rho, u, v, w, p, fp);
     A[c] = fp[0];
-    if (!shell) {
+    if (path == 0) {
 #define AA_PUSH_IN(a, o, dx, dy, dz) A[(a) * sq + (c + (dz) * sz + (dy) * sy + (dx))] = fp[a];
         AA_FOR_ALL(AA_PUSH_IN)
 #undef AA_PUSH_IN
+    } else if (path == 1) {
+#define AA_PUSH_X(a, o, dx, dy, dz)                                                                                  \
+    {                                                                                                                \
+        const bool out_ = ((dx) == 1 && wf.xp) || ((dx) == -1 && wf.xm);                                            \
+        A[out_ ? (o) * sq + c : (a) * sq + (c + (dz) * sz + (dy) * sy + (dx))] = fp[a];                             \
+    }
+        AA_FOR_ALL(AA_PUSH_X)
+#undef AA_PUSH_X
     } else {
         if (wf.zp) {  // the lid term of body n+1 uses the rho this macro() just produced: f(14) = f_post(11) - rho/6*U0, f(13) = f_post(12) - rho/6*(-U0)
             const double r6 = __ddiv_rn(rho, 6.0);

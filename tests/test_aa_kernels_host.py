@@ -257,3 +257,32 @@ def test_decomposed_blocks_bgk_and_fast_build(shim):
             else:
                 assert np.abs(a - b).max() <= 1e-13, (collision, k)
         sim.close(); wd.close(); ref.close()
+
+
+@pytest.mark.parametrize("nx", [31, 32, 33, 64, 65, 70, 129])
+def test_rows_of_one_to_five_warps_strict(shim, nx):
+    """the odd launch picks its path per warp from the warp's first x index: rows where the first and the last cell share a warp,
+    sit in neighbouring warps, or have interior warps between them; one block and two blocks split along x"""
+    total = (nx, 4, 3)
+    wd = orc.LidWorld(total, 1)
+    wd.initial()
+    seeded(wd, nx)
+    sim = AaSim(shim, wd, strict=True)
+    sim.upload(wd)
+    w2 = orc.LidWorld(total, 2, dims=(2, 1, 1))
+    w2.initial()
+    for k in ("rho", "u", "v", "w", "f"):
+        full = wd.gather(k)
+        for R in w2.ranks:
+            sl = tuple(slice(s, s + n) for s, n in zip(R.start, R.n))
+            getattr(R, k)[...] = full[(slice(None),) + sl] if k == "f" else full[sl]
+    two = AaWorld(shim, w2, strict=True)
+    two.upload()
+    for n in (2, 3):
+        wd.step(n); sim.step(n); two.step(n)
+        for k in ("rho", "u", "v", "w"):
+            assert np.array_equal(sim.macro()[k], wd.gather(k)), (nx, n, k)
+            assert np.array_equal(two.gather(k), wd.gather(k)), (nx, n, k, "two blocks")
+        assert np.array_equal(sim.f(), wd.gather("f")), (nx, n)
+        assert np.array_equal(two.gather("f"), wd.gather("f")), (nx, n, "two blocks")
+    sim.close(); two.close(); wd.close(); w2.close()

@@ -259,6 +259,24 @@ m11() {   # 2 GPUs: single-lattice blocks, one process per GPU, after the block-
     done
 }
 
+s7() {   # 1 GPU: the single-lattice kernels after the per-warp path choice of the odd launch
+    (timeout 600 python -m pytest tests/test_aa_gpu.py -q -m gpu -x > $O/pytest_aa.log 2>&1; echo "pytest rc=$?" >> $O/pytest_aa.log); tail -n 3 $O/pytest_aa.log
+    timeout 300 python bench.py --workload lid_aa --size 768 --steps 20 --warmup 3 > $O/bench_lid_aa_768.json 2> $O/b1.err; tail -c 900 $O/bench_lid_aa_768.json; tail -n 3 $O/b1.err
+    timeout 300 python bench.py --workload lid_aa --steps 20 --warmup 3 > $O/bench_lid_aa_896.json 2> $O/b1.err; tail -c 900 $O/bench_lid_aa_896.json; tail -n 3 $O/b1.err
+    timeout 300 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:k_aa -c 14 --csv --log-file $O/launches_lid_aa_768.csv \
+        python bench.py --workload lid_aa --size 768 --steps 4 --warmup 3 > $O/b2.log 2>&1; echo "ncu launches rc=$?"
+    timeout 300 $NCU --set full --import-source on -k regex:k_aa_even -s 1 -c 1 -o $O/ncu_full_k_aa_even_512 python bench.py --workload lid_aa --size 512 --steps 4 --warmup 3 > $O/b3.log 2>&1; echo "ncu even rc=$?"
+    timeout 300 $NCU --set full --import-source on -k regex:k_aa_odd -s 1 -c 1 -o $O/ncu_full_k_aa_odd_512 python bench.py --workload lid_aa --size 512 --steps 4 --warmup 3 > $O/b4.log 2>&1; echo "ncu odd rc=$?"
+}
+
+s8() {   # 1 GPU: cache hints and occupancy of the single-lattice kernels (MGLC_AA_MEMOP: load = &3, store = >>2&3, 16 / 32 = launch bounds)
+    for m in 0 1 2 4 5 8 9 16 32 0; do
+        MGLC_AA_MEMOP=$m timeout 200 python bench.py --workload lid_aa --size 640 --steps 100 --warmup 3 > $O/bench_lid_aa_640_memop$m.json 2> $O/b1.err
+        python -c "
+import json;d=json.loads(open('$O/bench_lid_aa_640_memop$m.json').read().strip().splitlines()[-1]);print('memop $m', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    done
+}
+
 "$S"
 clk
 ls -la $O | tail -30
