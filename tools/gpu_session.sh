@@ -277,6 +277,15 @@ import json;d=json.loads(open('$O/bench_lid_aa_640_memop$m.json').read().strip()
     done
 }
 
+m12() {   # 8 GPUs: single-lattice blocks of 960^3 (2x2x2: 1920^3 = 7.08 G cells; the two-lattice path cannot hold a 960^3 block)
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
+    ( time timeout 420 $TR bench.py --gpus 8 --workload lid_aa --size 960 --steps 10 --warmup 3 > $O/bench_lid_aa_8gpu_960.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 1900 $O/bench_lid_aa_8gpu_960.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
+}
+m13() {   # 4 GPUs: parity and the weak-scaling line at N = 4 (1x2x2); e2e / transports / strong left to the round-end run (GPU budget)
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517"
+    ( time timeout 240 $TR bench.py --gpus 4 --steps 20 --warmup 5 --no-e2e --no-extras > $O/bench_lid_4gpu.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 3500 $O/bench_lid_4gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30
