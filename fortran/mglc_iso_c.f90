@@ -51,6 +51,10 @@ module mglc_iso_c
     type, bind(C) :: mglc_t2d_desc
         integer(c_int) :: total_nx, total_ny, arith, bcT(4), variant
         real(c_double) :: Rayleigh, Prandtl, Mach, Thot, Tcold, Tref, rho0, lengthUnit
+        !> the sheared Rayleigh-Benard programs (seq/R_B_2d.F90:118-120, :1086-1106): UwallTopLeft, TopRight, BottomLeft,
+        !> BottomRight, LeftTop, LeftBottom, RightTop, RightBottom; cornersT = 1: its bouncebackT() corner cells
+        real(c_double) :: Uwall(8)
+        integer(c_int) :: cornersT
     end type mglc_t2d_desc
     integer(c_int), parameter :: MGLC_T2D_MPI = 0, MGLC_T2D_ACC = 1, MGLC_BCT_PERIODIC = 3
 
@@ -450,6 +454,12 @@ module mglc_iso_c
         end function
         ! ---- 2-D thermal driver (Buoyancy_driven_cavity/fortran/2d/mpi_blocked/main.F90:84-108) ---------------------------
         function mglc_t2d_desc_init(d) bind(C, name="mglc_t2d_desc_init") result(rc)
+            import :: c_int, mglc_t2d_desc
+            type(mglc_t2d_desc), intent(out) :: d
+            integer(c_int) :: rc
+        end function
+        !> seq/R_B_2d.F90 as shipped: Rayleigh-Benard plates, Pr = 5.3, walls moving at shearReynolds = 100
+        function mglc_t2d_desc_init_sheared_rb(d) bind(C, name="mglc_t2d_desc_init_sheared_rb") result(rc)
             import :: c_int, mglc_t2d_desc
             type(mglc_t2d_desc), intent(out) :: d
             integer(c_int) :: rc

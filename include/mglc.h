@@ -413,11 +413,20 @@ typedef struct mglc_t2d_desc {
     double Rayleigh, Prandtl, Mach;      /* module.F90:31-33                                 */
     double Thot, Tcold, Tref, rho0;      /* module.F90:67-68                                 */
     double lengthUnit;                   /* 0 = dble(total_ny) (module.F90:29); the OpenACC program uses dble(nx) (acc:57) */
+    /* the sheared Rayleigh-Benard programs (seq/R_B_2d.F90, seq/bouyancy2d_omp.F90; 0 = the shipped MPI program):
+     * Uwall = UwallTopLeft, TopRight, BottomLeft, BottomRight, LeftTop, LeftBottom, RightTop, RightBottom (R_B_2d.F90:118-120;
+     * the halves meet at nxHalf / nyHalf, :87): initial() sets u, v on the walls (:466-481) and bounceback() subtracts
+     * rho*C/6 from the diagonal populations off a wall (:790-898); cornersT = 1: its bouncebackT() corner cells (:1086-1106) */
+    double Uwall[8];
+    int cornersT;
 } mglc_t2d_desc;
 enum { MGLC_T2D_MPI = 0, MGLC_T2D_ACC = 1 };
 int mglc_t2d_desc_init(mglc_t2d_desc *d);                               /* the shipped constants (201 x 201, Ra 1e7, side-heated) */
 /* the OpenACC program as shipped: 513 x 257, Ra 1e5, Rayleigh-Benard plates, periodic vertical walls, lengthUnit = 513 (acc:9-22,55-60) */
 int mglc_t2d_desc_init_acc(mglc_t2d_desc *d);
+/* seq/R_B_2d.F90 as shipped: 201 x 201, Ra 1e7, Pr 5.3, Rayleigh-Benard plates, walls moving at shearReynolds = 100 (U0 =
+ * 100*viscosity/ny; change total_ny / Prandtl / Rayleigh / Mach BEFORE calling, or recompute Uwall), cornersT = 1 (:56-61,79,118-120) */
+int mglc_t2d_desc_init_sheared_rb(mglc_t2d_desc *d);
 /* MPI_Dims_create(np,2) + MPI_Cart_create + decompose_1d + MPI_Cart_shift + MPI_Cart_find_corners + allocate -- main.F90:21-43,
  * initial.F90:177-197; tauf, viscosity, diffusivity, paraA, gBeta, Snu, Sq, Qd, Qnu -- module.F90:69-81; fails with
  * MGLC_E_INVALID where the reference stops (paraA outside (-4,1), initial.F90:30) */

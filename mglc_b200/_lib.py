@@ -55,7 +55,7 @@ class L2dDesc(C.Structure):
 class T2dDesc(C.Structure):
     _fields_ = [("total_nx", C.c_int), ("total_ny", C.c_int), ("arith", C.c_int), ("bcT", C.c_int * 4), ("variant", C.c_int),
                 ("Rayleigh", C.c_double), ("Prandtl", C.c_double), ("Mach", C.c_double), ("Thot", C.c_double), ("Tcold", C.c_double),
-                ("Tref", C.c_double), ("rho0", C.c_double), ("lengthUnit", C.c_double)]
+                ("Tref", C.c_double), ("rho0", C.c_double), ("lengthUnit", C.c_double), ("Uwall", C.c_double * 8), ("cornersT", C.c_int)]
 
 
 class AaDesc(C.Structure):
@@ -237,6 +237,7 @@ SIGNATURES = {
     "mglc_l2d_sync": (C.c_int, [_vp]),
     "mglc_t2d_desc_init": (C.c_int, [C.POINTER(T2dDesc)]),
     "mglc_t2d_desc_init_acc": (C.c_int, [C.POINTER(T2dDesc)]),
+    "mglc_t2d_desc_init_sheared_rb": (C.c_int, [C.POINTER(T2dDesc)]),
     "mglc_t2d_create": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, C.c_int, C.c_int, _vp]),
     "mglc_t2d_create_local": (C.c_int, [_vpp, C.POINTER(T2dDesc), _ip, C.c_int, _ip]),
     "mglc_t2d_destroy": (C.c_int, [_vp]),

@@ -30,6 +30,7 @@ struct T2Sub {
     int cnr[4];          // the neighbours populations 5..8 travel to                        MPI_Cart_find_corners, main.F90:228-240
     int device;
     Geom2 g;
+    T2Params p;          // the handle's parameters + this subdomain's place in the global lattice (start, total)
     double *F, *G;       // f, g        (pre-collision)
     double *P[2], *Q[2]; // f_post = P[cur], g_post = Q[cur]; the rotated loop ping-pongs between the two
     int cur;
@@ -85,6 +86,22 @@ extern "C" int mglc_t2d_desc_init_acc(mglc_t2d_desc *d) {
     d->bcT[2] = MGLC_BCT_CONST_COLD; d->bcT[3] = MGLC_BCT_CONST_HOT;            // acc:19-20: RayleighBenardCell, HorizontalWallsConstT
     d->Rayleigh = 1e5;                                                          // acc:59
     d->variant = MGLC_T2D_ACC; d->lengthUnit = 513.0;                           // acc:57: lengthUnit = dble(nx)
+    return MGLC_OK;
+}
+
+// seq/R_B_2d.F90 as shipped (also the macro set of seq/bouyancy2d_omp.F90): Rayleigh-Benard plates, Pr = 5.3, every wall moving
+// along itself at U0 = shearReynolds*viscosity/dble(ny) with shearReynolds = 100 (:61,79,118-120), its own corner cells in bouncebackT()
+extern "C" int mglc_t2d_desc_init_sheared_rb(mglc_t2d_desc *d) {
+    MGLC_TRY(mglc_t2d_desc_init(d));
+    d->Prandtl = 5.3;                                                           // RB2:61
+    d->bcT[0] = d->bcT[1] = MGLC_BCT_ADIABATIC;                                 // RB2:22-24: RayleighBenardCell
+    d->bcT[2] = MGLC_BCT_CONST_COLD; d->bcT[3] = MGLC_BCT_CONST_HOT;
+    const double lengthUnit = (double)d->total_ny;                              // RB2:58
+    const double tauf = 0.5 + d->Mach * lengthUnit * sqrt(3.0 * d->Prandtl / d->Rayleigh), viscosity = (tauf - 0.5) / 3.0;   // :96-97
+    const double U0 = 100.0 * viscosity / (double)d->total_ny;                  // :79,118
+    const double w[8] = {U0, -U0, -U0, U0, U0, U0, U0, U0};                     // :119-120
+    for (int q = 0; q < 8; ++q) d->Uwall[q] = w[q];
+    d->cornersT = 1;                                                            // :1086-1106
     return MGLC_OK;
 }
 
@@ -175,6 +192,8 @@ static int t2_make_sub(mglc_t2d *h, int rank, int device, T2Sub **out) {
     S->g = make_geom2(S->n[0], S->n[1]);
     S->g.wall[0] = c0 == h->dims[0] - 1 && !h->p.perx; S->g.wall[1] = c0 == 0 && !h->p.perx;
     S->g.wall[2] = c1 == h->dims[1] - 1; S->g.wall[3] = c1 == 0;
+    S->p = h->p;
+    for (int d = 0; d < 2; ++d) { S->p.start[d] = S->start[d]; S->p.total[d] = gn[d]; }
     auto fail = [&](int rc) { t2_free_sub(S); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return fail(MGLC_E_CUDA); }
     if (cudaStreamCreateWithFlags(&S->s, cudaStreamNonBlocking) != cudaSuccess) return fail(MGLC_E_CUDA);
@@ -271,6 +290,14 @@ static int t2_new(mglc_t2d **out, const mglc_t2d_desc *d, const int dims_or_zero
     for (int f = 0; f < 4; ++f) {
         p.bcT[f] = d->bcT[f] == MGLC_BCT_PERIODIC ? 0 : d->bcT[f];
         p.wallT[f] = (4.0 + p.paraA) / 10.0 * (d->bcT[f] == MGLC_BCT_CONST_HOT ? d->Thot : d->Tcold);    // evolution_g.F90:100,107,132,139
+    }
+    p.moving = 0;
+    for (int q = 0; q < 8; ++q) { p.Uwall[q] = d->Uwall[q]; p.moving |= d->Uwall[q] != 0.0; }     // seq/R_B_2d.F90:118-120
+    p.cornersT = d->cornersT != 0 && !perx;                                                        // :1086 #ifndef VerticalWallsPeriodicalT
+    if (p.moving && perx) {
+        set_error("mglc_t2d_create: moving walls with periodic vertical walls are not a configuration of the reference");
+        delete h;
+        return MGLC_E_INVALID;
     }
     *out = h;
     return MGLC_OK;
@@ -403,7 +430,7 @@ extern "C" int mglc_t2d_initial(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         const int axis = profile == 2 ? 1 : 0;
-        k_t2_initial<<<t2_grid_h(S), 128, 0, S->s>>>(S->g, h->p, profile, S->start[axis], axis ? h->d.total_ny : h->d.total_nx, S->F, S->G,
+        k_t2_initial<<<t2_grid_h(S), 128, 0, S->s>>>(S->g, S->p, profile, S->start[axis], axis ? h->d.total_ny : h->d.total_nx, S->F, S->G,
                                                      S->rho, S->u, S->v, S->T, S->up, S->vp, S->Tp);
         MGLC_CUDA(cudaMemsetAsync(S->P[S->cur], 0, 9 * (size_t)S->g.sq * sizeof(double), S->s));     // f_post = 0, initial.F90:334
         MGLC_CUDA(cudaMemsetAsync(S->Q[S->cur], 0, 5 * (size_t)S->g.sq * sizeof(double), S->s));     // g_post = 0, :335
@@ -416,7 +443,7 @@ static int t2_collision(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         S->launches += (h->d.arith == MGLC_ARITH_STRICT ? strict::launch_t2_collision : fast::launch_t2_collision)(
-            S->g, h->p, S->F, S->rho, S->u, S->v, S->T, S->P[S->cur], S->Fx, S->Fy, S->s);
+            S->g, S->p, S->F, S->rho, S->u, S->v, S->T, S->P[S->cur], S->Fx, S->Fy, S->s);
     }
     return MGLC_OK;
 }
@@ -424,7 +451,7 @@ static int t2_collisionT(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         S->launches += (h->d.arith == MGLC_ARITH_STRICT ? strict::launch_t2_collisionT : fast::launch_t2_collisionT)(
-            S->g, h->p, S->G, S->u, S->v, S->T, S->Q[S->cur], S->s);
+            S->g, S->p, S->G, S->u, S->v, S->T, S->Q[S->cur], S->s);
     }
     return MGLC_OK;
 }
@@ -497,7 +524,7 @@ extern "C" int mglc_t2d_bounceback(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         const int cells = 2 * S->n[0] + 2 * std::max(S->n[1] - 2, 0);
-        k_t2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p.perx, S->P[S->cur], S->F);
+        k_t2_bounceback<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, S->p, S->P[S->cur], S->F, S->rho);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -507,7 +534,7 @@ extern "C" int mglc_t2d_bouncebackT(mglc_t2d *h) {
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
         const int cells = 2 * S->n[0] + 2 * std::max(S->n[1] - 2, 0);
-        k_t2_bouncebackT<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, h->p, S->Q[S->cur], S->G);
+        k_t2_bouncebackT<<<(cells + 127) / 128, 128, 0, S->s>>>(S->g, S->p, S->Q[S->cur], S->G);
         S->launches += 1;
     }
     return MGLC_OK;
@@ -552,7 +579,7 @@ static int t2_step_impl(mglc_t2d *h, int nsteps) {
                 cudaGraph_t gr = nullptr;
                 MGLC_CUDA(cudaStreamBeginCapture(S->s, cudaStreamCaptureModeRelaxed));
                 int c = S->cur;
-                for (int q = 0; q < T2_GRAPH_STEPS; ++q, c ^= 1) fused(S->g, h->p, S->P[c], S->P[c ^ 1], S->Q[c], S->Q[c ^ 1], S->Fy, S->s);
+                for (int q = 0; q < T2_GRAPH_STEPS; ++q, c ^= 1) fused(S->g, S->p, S->P[c], S->P[c ^ 1], S->Q[c], S->Q[c ^ 1], S->Fy, S->rho, S->s);
                 const cudaError_t ce = cudaStreamEndCapture(S->s, &gr);
                 if (ce != cudaSuccess) { if (gr) cudaGraphDestroy(gr); (void)cudaGetLastError(); set_error("mglc_t2d_step: graph capture failed: %s", cudaGetErrorString(ce)); return MGLC_E_CUDA; }
                 const cudaError_t ie = cudaGraphInstantiate(&ge, gr, 0);
@@ -568,15 +595,15 @@ static int t2_step_impl(mglc_t2d *h, int nsteps) {
         MGLC_TRY(t2_exchange(h, 3));
         for (T2Sub *S : h->subs) {
             MGLC_TRY(t2_use(S));
-            S->launches += (strict_build ? strict::launch_t2_fused : fast::launch_t2_fused)(S->g, h->p, S->P[S->cur], S->P[S->cur ^ 1], S->Q[S->cur],
-                                                                                            S->Q[S->cur ^ 1], S->Fy, S->s);
+            S->launches += (strict_build ? strict::launch_t2_fused : fast::launch_t2_fused)(S->g, S->p, S->P[S->cur], S->P[S->cur ^ 1], S->Q[S->cur],
+                                                                                            S->Q[S->cur ^ 1], S->Fy, S->rho, S->s);
             S->cur ^= 1;
         }
     }
     MGLC_TRY(t2_exchange(h, 3));
     for (T2Sub *S : h->subs) {
         MGLC_TRY(t2_use(S));
-        S->launches += strict::launch_t2_stream_macro(S->g, h->p, S->P[S->cur], S->F, S->Q[S->cur], S->G, S->Fy, S->rho, S->u, S->v, S->T, S->s);
+        S->launches += strict::launch_t2_stream_macro(S->g, S->p, S->P[S->cur], S->F, S->Q[S->cur], S->G, S->Fy, S->rho, S->u, S->v, S->T, S->s);
     }
     return MGLC_OK;
 }

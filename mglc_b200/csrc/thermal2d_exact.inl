@@ -23,8 +23,17 @@ __global__ void __launch_bounds__(128) k_t2_initial(Geom2 g, T2Params p, int pro
     const double omega[9] = {4.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 9.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0, 1.0 / 36.0};
     const double oT0 = (1.0 - p.paraA) / 5.0, oT1 = (p.paraA + 4.0) / 20.0;
     const long long c = g.idx(0, i, j), m = g.cell(i, j);
-    const double r = p.rho0, uu = 0.0, vv = 0.0;
-    double t = 0.0;
+    const double r = p.rho0;
+    double uu = 0.0, vv = 0.0, t = 0.0;
+    if (p.moving) {                                // the walls' velocities, RB2:466-481 (v on the vertical walls leaves the corners out)
+        const int gi = p.start[0] + i, gj = p.start[1] + j;
+        if (gj == p.total[1]) uu = t2_wall_u(p, true, gi);
+        if (gj == 1) uu = t2_wall_u(p, false, gi);
+        if (gj >= 2 && gj <= p.total[1] - 1) {
+            if (gi == 1) vv = t2_wall_v(p, false, gj);
+            if (gi == p.total[0]) vv = t2_wall_v(p, true, gj);
+        }
+    }
     // profile 1: VerticalWallsConstT (linear in x, :258); 2: HorizontalWallsConstT (linear in y, :268); start/total along that axis
     if (profile) t = (double)(start + (profile == 1 ? i : j) - 1) / (double)(total - 1) * (p.Tcold - p.Thot) + p.Thot;
     rho[m] = r; u[m] = uu; v[m] = vv; T[m] = t; up[m] = 0.0; vp[m] = 0.0; Tp[m] = 0.0;
@@ -60,10 +69,13 @@ __device__ __forceinline__ bool t2_ring_cell(const Geom2 &g, int t, int &i, int 
 }
 
 // bounceback(): evolution_f.F90:283-321 (left, right, bottom, top; all half-way bounce-back)
-__global__ void __launch_bounds__(128) k_t2_bounceback(Geom2 g, int perx, const double *__restrict__ Fpost, double *__restrict__ F) {
+// + moving walls (RB2:790-898): the diagonal populations off a wall get - rho*C/6, rho as the last macro() left it
+__global__ void __launch_bounds__(128) k_t2_bounceback(Geom2 g, T2Params p, const double *__restrict__ Fpost, double *__restrict__ F,
+                                                       const double *__restrict__ rho) {
     int i, j;
     if (!t2_ring_cell(g, blockIdx.x * blockDim.x + threadIdx.x, i, j)) return;
     const long long c = g.idx(0, i, j), sq = g.sq;
+    const int perx = p.perx;
     if (perx) {   // VerticalWallsPeriodicalU, seq/bouyancy2d_acc.F90:777-791 (before the horizontal walls, like the reference)
         const long long wrap = g.nx - 1;
         if (i == 1) { F[1 * sq + c] = Fpost[1 * sq + c + wrap]; F[5 * sq + c] = Fpost[5 * sq + c + wrap]; F[8 * sq + c] = Fpost[8 * sq + c + wrap]; }
@@ -73,6 +85,15 @@ __global__ void __launch_bounds__(128) k_t2_bounceback(Geom2 g, int perx, const 
     if (g.wall[0] && i == g.nx) { F[3 * sq + c] = Fpost[1 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; F[7 * sq + c] = Fpost[5 * sq + c]; }
     if (g.wall[3] && j == 1) { F[2 * sq + c] = Fpost[4 * sq + c]; F[5 * sq + c] = Fpost[7 * sq + c]; F[6 * sq + c] = Fpost[8 * sq + c]; }
     if (g.wall[2] && j == g.ny) { F[4 * sq + c] = Fpost[2 * sq + c]; F[7 * sq + c] = Fpost[5 * sq + c]; F[8 * sq + c] = Fpost[6 * sq + c]; }
+    if (!p.moving) return;
+    const bool xp = g.wall[0] && i == g.nx, xm = g.wall[1] && i == 1, yp = g.wall[2] && j == g.ny, ym = g.wall[3] && j == 1;
+    const int gi = p.start[0] + i, gj = p.start[1] + j;
+    const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    for (int a = 5; a < 9; ++a) {
+        const int ex = c_t2_ex[a], ey = c_t2_ey[a];
+        const bool hx = (ex == 1 && xm) || (ex == -1 && xp), hy = (ey == 1 && ym) || (ey == -1 && yp);
+        if (hx | hy) F[a * sq + c] = Fpost[opp[a] * sq + c] - rho[g.cell(i, j)] * t2_wall_coef(p, ex, ey, hx, hy, gi, gj) / 6.0;
+    }
 }
 
 // bouncebackT(): evolution_g.F90:79-142 (adiabatic: g(a) = g_post(opp); constant T: g(a) = -g_post(opp) + (4+paraA)/10*T_wall)
@@ -88,6 +109,15 @@ __global__ void __launch_bounds__(128) k_t2_bouncebackT(Geom2 g, T2Params p, con
     if (g.wall[2] && j == g.ny) G[4 * sq + c] = p.bcT[2] ? -Gpost[2 * sq + c] + p.wallT[2] : Gpost[2 * sq + c];
     if (g.wall[1] && i == 1) G[1 * sq + c] = p.bcT[1] ? -Gpost[3 * sq + c] + p.wallT[1] : Gpost[3 * sq + c];
     if (g.wall[0] && i == g.nx) G[3 * sq + c] = p.bcT[0] ? -Gpost[1 * sq + c] + p.wallT[0] : Gpost[1 * sq + c];
+    // RB2:1086-1106: in a corner cell the population off the vertical wall takes the constant-temperature rule of the plate
+    const bool ym = g.wall[3] && j == 1, yp = g.wall[2] && j == g.ny;
+    if (p.cornersT && (ym | yp)) {
+        const int plate = ym ? 3 : 2;
+        if (p.bcT[plate]) {
+            if (g.wall[1] && i == 1) G[1 * sq + c] = -Gpost[3 * sq + c] + p.wallT[plate];
+            if (g.wall[0] && i == g.nx) G[3 * sq + c] = -Gpost[1 * sq + c] + p.wallT[plate];
+        }
+    }
 }
 
 // macro(): evolution_f.F90:328-342

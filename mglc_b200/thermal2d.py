@@ -20,12 +20,18 @@ class BuoyancyDrivenCavity2D:
     _FIELDS = ("rho", "u", "v", "T", "Fx", "Fy")
 
     def __init__(self, total=None, nprocs=1, dims=None, bcT=None, strict=False, devices=None, comm=None, device=0, variant="mpi",
-                 lengthUnit=None, **params):
+                 lengthUnit=None, Uwall=None, cornersT=None, shearReynolds=None, **params):
         """variant "mpi": mpi_blocked/ (201 x 201, Ra 1e7, side-heated); "acc": the OpenACC program seq/bouyancy2d_acc.F90
-        (513 x 257, Ra 1e5, Rayleigh-Benard plates, periodic vertical walls, lengthUnit = nx) -- each with its shipped defaults"""
+        (513 x 257, Ra 1e5, Rayleigh-Benard plates, periodic vertical walls, lengthUnit = nx); "sheared_rb": seq/R_B_2d.F90
+        (201 x 201, Ra 1e7, Pr 5.3, Rayleigh-Benard plates, walls moving at shearReynolds = 100, its corner cells in bouncebackT())
+        -- each with its shipped defaults.  Uwall = (TopLeft, TopRight, BottomLeft, BottomRight, LeftTop, LeftBottom, RightTop,
+        RightBottom) sets the wall velocities directly; shearReynolds = R sets them as R_B_2d.F90:118-120 does (U0 = R*viscosity/ny)."""
         lib = L.lib()
         d = L.T2dDesc()
-        L.check((lib.mglc_t2d_desc_init_acc if variant == "acc" else lib.mglc_t2d_desc_init)(C.byref(d)))
+        init = {"acc": lib.mglc_t2d_desc_init_acc, "sheared_rb": lib.mglc_t2d_desc_init_sheared_rb}.get(variant, lib.mglc_t2d_desc_init)
+        L.check(init(C.byref(d)))
+        if variant == "sheared_rb" and shearReynolds is None and Uwall is None:
+            shearReynolds = 100.0                      # R_B_2d.F90:79 (recomputed below for the lattice and parameters of this run)
         if variant == "acc" and total is not None and lengthUnit is None:
             lengthUnit = float(total[0])              # acc:57: lengthUnit = dble(nx)
         if lengthUnit is not None:
@@ -38,8 +44,19 @@ class BuoyancyDrivenCavity2D:
             if k not in ("Rayleigh", "Prandtl", "Mach", "Thot", "Tcold", "Tref", "rho0"):
                 raise TypeError(f"unknown parameter {k}")
             setattr(d, k, v)
+        if shearReynolds is not None:                 # R_B_2d.F90:58,96-97,118-120, the same products in the same order
+            import math
+            lu = d.lengthUnit if d.lengthUnit > 0.0 else float(d.total_ny)
+            tauf = 0.5 + d.Mach * lu * math.sqrt(3.0 * d.Prandtl / d.Rayleigh)
+            U0 = shearReynolds * ((tauf - 0.5) / 3.0) / float(d.total_ny)
+            Uwall = (U0, -U0, -U0, U0, U0, U0, U0, U0)
+        if Uwall is not None:
+            d.Uwall[:] = [float(x) for x in Uwall]
+        if cornersT is not None:
+            d.cornersT = int(bool(cornersT))
         d.arith = L.ARITH_STRICT if strict else L.ARITH_FAST
         self.desc, self.total, self.bcT, self.variant = d, (d.total_nx, d.total_ny), tuple(d.bcT), variant
+        self.Uwall, self.cornersT = tuple(d.Uwall), bool(d.cornersT)
         dz = (C.c_int * 2)(*(dims if dims else (0, 0)))
         self._h = C.c_void_p()
         if comm is not None:

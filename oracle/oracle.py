@@ -767,7 +767,9 @@ class Thermal2DWorld:
     """All P emulated ranks of the 2-D thermal driver in one process."""
     LEAD = {"f": 9, "f_post": 9, "g": 5, "g_post": 5}
 
-    def __init__(self, total=(201, 201), nprocs=1, dims=None, bcT=None, variant="mpi", lengthUnit=0.0, **params):
+    def __init__(self, total=(201, 201), nprocs=1, dims=None, bcT=None, variant="mpi", lengthUnit=0.0, Uwall=None, cornersT=False, **params):
+        """Uwall = (TopLeft, TopRight, BottomLeft, BottomRight, LeftTop, LeftBottom, RightTop, RightBottom), cornersT: the moving
+        walls and the corner rule of the sheared Rayleigh-Benard programs (seq/R_B_2d.F90:118-120, :1086-1106)"""
         self._lib = _t2_lib()
         d = (C.c_int * 2)(*(dims if dims else (0, 0)))
         pv = dict(Rayleigh=1e7, Prandtl=0.71, Mach=0.1, Thot=1.0, Tcold=0.0, Tref=0.0, rho0=1.0)
@@ -778,6 +780,9 @@ class Thermal2DWorld:
         self.variant = variant
         if variant != "mpi" or lengthUnit:
             self._lib.t2_world_set_variant(self._h, {"mpi": T2_MPI, "acc": T2_ACC}[variant], float(lengthUnit))
+        self.Uwall, self.cornersT = tuple(float(x) for x in (Uwall if Uwall is not None else [0.0] * 8)), bool(cornersT)
+        if Uwall is not None or cornersT:
+            self._lib.t2_world_set_walls(self._h, (C.c_double * 8)(*(Uwall if Uwall is not None else [0.0] * 8)), int(bool(cornersT)))
         self.total, self.nprocs = tuple(total), nprocs
         self.ranks = [Thermal2DRank(self, r) for r in range(nprocs)]
         dd, bb = (C.c_int * 2)(), (C.c_int * 4)()

@@ -49,6 +49,12 @@ typedef struct t2_world {
     int bcT[4];          /* +x (right), -x (left), +y (top), -y (bottom) : T2_*   macros.F90:16-27 */
     int variant;         /* T2_MPI: mpi_blocked/evolution_f.F90 ; T2_ACC: seq/bouyancy2d_acc.F90 (f_post(0) rounded term by term) */
     int periodic_x;      /* VerticalWallsPeriodicalU + VerticalWallsPeriodicalT (acc:15,22): needs dims[0] == 1 */
+    /* the sheared Rayleigh-Benard programs (RB2 = seq/R_B_2d.F90; seq/bouyancy2d_omp.F90): walls that move along themselves.
+     * Uwall = TopLeft, TopRight, BottomLeft, BottomRight (u of the horizontal walls, left / right half: i <= nxHalf or not),
+     * LeftTop, LeftBottom, RightTop, RightBottom (v of the vertical walls, j <= nyHalf = Bottom)            RB2:87,118-120 */
+    double Uwall[8];
+    int moving;          /* any Uwall != 0 */
+    int cornersT;        /* 1 = RB2:1086-1106: both populations of a corner cell take the plate's constant-temperature rule */
     t2_params p;
     double errorU, errorT;
     t2_rank *r;
@@ -139,6 +145,22 @@ void t2_world_set_variant(t2_world *w, int variant, double lengthUnit_or_0) {
     w->p.lengthUnit = lengthUnit_or_0;
     t2_derive_params(&w->p, w->total[1]);
 }
+/* moving walls and the corner rule of the sheared Rayleigh-Benard programs (RB2:118-120, :1086-1106) */
+void t2_world_set_walls(t2_world *w, const double *Uwall8, int cornersT) {
+    w->moving = 0;
+    for (int q = 0; q < 8; ++q) { w->Uwall[q] = Uwall8 ? Uwall8[q] : 0.0; w->moving |= w->Uwall[q] != 0.0; }
+    w->cornersT = cornersT;
+}
+/* RB2:87; velocity of the horizontal wall (top = 1 / bottom = 0) above or below global column gi, of the vertical wall
+ * (right = 1 / left = 0) beside global row gj */
+static double wall_u(const t2_world *w, int top, int gi) {
+    const int left = gi <= (w->total[0] - 1) / 2 + 1;
+    return w->Uwall[top ? (left ? 0 : 1) : (left ? 2 : 3)];
+}
+static double wall_v(const t2_world *w, int right, int gj) {
+    const int bottom = gj <= (w->total[1] - 1) / 2 + 1;
+    return w->Uwall[right ? (bottom ? 7 : 6) : (bottom ? 5 : 4)];
+}
 void t2_world_info(t2_world *w, int dims[2], t2_params *p, int bcT[4]) {
     dims[0] = w->dims[0]; dims[1] = w->dims[1];
     *p = w->p;
@@ -177,6 +199,15 @@ void t2_initial(t2_world *w) {
                 S(R, up, i, j) = 0.0; S(R, vp, i, j) = 0.0; S(R, Tp, i, j) = 0.0;
                 if (vertT) S(R, T, i, j) = (double)(R->start[0] + i - 1) / (double)(w->total[0] - 1) * (p->Tcold - p->Thot) + p->Thot;
                 if (horT) S(R, T, i, j) = (double)(R->start[1] + j - 1) / (double)(w->total[1] - 1) * (p->Tcold - p->Thot) + p->Thot;
+                if (w->moving) {                                                   /* RB2:466-481 */
+                    const int gi = R->start[0] + i, gj = R->start[1] + j;
+                    if (gj == w->total[1]) S(R, u, i, j) = wall_u(w, 1, gi);
+                    if (gj == 1) S(R, u, i, j) = wall_u(w, 0, gi);
+                    if (gj >= 2 && gj <= w->total[1] - 1) {
+                        if (gi == 1) S(R, v, i, j) = wall_v(w, 0, gj);
+                        if (gi == w->total[0]) S(R, v, i, j) = wall_v(w, 1, gj);
+                    }
+                }
             }
         for (int j = 1; j <= R->ny; ++j)
             for (int i = 1; i <= R->nx; ++i) {
@@ -367,6 +398,28 @@ void t2_bounceback(t2_world *w) {
             for (int i = 1; i <= nx; ++i) { F(R, 2, i, 1) = FP(R, 4, i, 1); F(R, 5, i, 1) = FP(R, 7, i, 1); F(R, 6, i, 1) = FP(R, 8, i, 1); }
         if (R->coords[1] == w->dims[1] - 1)
             for (int i = 1; i <= nx; ++i) { F(R, 4, i, ny) = FP(R, 2, i, ny); F(R, 7, i, ny) = FP(R, 5, i, ny); F(R, 8, i, ny) = FP(R, 6, i, ny); }
+        if (!w->moving) continue;
+        /* moving walls, RB2:790-898: a diagonal population that comes off a wall gets - rho*C/6 with rho of the previous
+         * macro(); C = -(ex*U) for a horizontal wall moving at U, -(ey*V) for a vertical wall moving at V, and in the corner
+         * cells the population that comes out of the corner itself takes both (RB2:872,880,888,896).  The walls' halves meet
+         * at nxHalf / nyHalf of the GLOBAL lattice. */
+        const int left = R->coords[0] == 0 && !w->periodic_x, right = R->coords[0] == w->dims[0] - 1 && !w->periodic_x;
+        const int bottom = R->coords[1] == 0, top = R->coords[1] == w->dims[1] - 1;
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                const int xm = left && i == 1, xp = right && i == nx, ym = bottom && j == 1, yp = top && j == ny;
+                if (!(xm | xp | ym | yp)) continue;
+                const int gi = R->start[0] + i, gj = R->start[1] + j;
+                for (int a = 5; a < Q9; ++a) {
+                    const int hx = (ex[a] == 1 && xm) || (ex[a] == -1 && xp);      /* upstream cell beyond a vertical wall   */
+                    const int hy = (ey[a] == 1 && ym) || (ey[a] == -1 && yp);      /* upstream cell beyond a horizontal wall */
+                    if (!(hx | hy)) continue;
+                    static const int opp[Q9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+                    const double cu = -((double)ex[a] * wall_u(w, ey[a] == -1, gi)), cv = -((double)ey[a] * wall_v(w, ex[a] == -1, gj));
+                    const double Cw = (hx && hy) ? cu + cv : hy ? cu : cv;
+                    F(R, a, i, j) = FP(R, opp[a], i, j) - S(R, rho, i, j) * Cw / 6.0;
+                }
+            }
     }
 }
 
@@ -396,6 +449,17 @@ void t2_bouncebackT(t2_world *w) {
                 else G(R, in_pop[face], i, j) = -GP(R, out_pop[face], i, j) + (4.0 + p->paraA) / 10.0 * Tw;
             }
         }
+        if (w->cornersT && !w->periodic_x)      /* RB2:1086-1106: in a corner cell the population off the vertical wall takes the plate's rule */
+            for (int cy = 0; cy < 2; ++cy)
+                for (int cx = 0; cx < 2; ++cx) {
+                    const int fx = cx ? 0 : 1, fy = cy ? 2 : 3;                  /* faces of this corner */
+                    if (!on[fx] || !on[fy]) continue;
+                    const int kind = w->bcT[fy];
+                    if (kind != T2_CONST_HOT && kind != T2_CONST_COLD) continue;
+                    const double Tw = kind == T2_CONST_HOT ? p->Thot : p->Tcold;
+                    const int i = cx ? nx : 1, j = cy ? ny : 1;
+                    G(R, in_pop[fx], i, j) = -GP(R, out_pop[fx], i, j) + (4.0 + p->paraA) / 10.0 * Tw;
+                }
     }
 }
 

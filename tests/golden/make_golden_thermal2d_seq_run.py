@@ -53,6 +53,14 @@ STEADY = dict(path=S2, defs=DEFS, name="ref_fortran_thermal2d_seq_run.npz", para
 STEADY_RB = dict(STEADY, name="ref_fortran_thermal2d_seq_run_rb.npz",
                  defs={"steadyFlow", "HorizontalWallsNoslip", "VerticalWallsNoslip", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsAdiabatic"},
                  ranges=dict(STEADY["ranges"], initT=(507, 526)))
+# the sheared Rayleigh-Benard program as shipped: the same text family with walls that MOVE (shearReynolds = 100, so U0 =
+# 100*viscosity/ny enters initial() :466-481 and bounceback() :755-898), Pr = 5.3, and its own corner cells in bouncebackT()
+# (:1086-1106: both populations of a corner cell take the plate's constant-temperature rule; the edge loops run 2..n-1)
+RB2 = "/root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/R_B_2d.F90"
+_shift = lambda r: {k: ((a, b) if b <= 744 else (a + 1, b + 1)) for k, (a, b) in r.items()}      # one more line after :744
+SHEARED_RB = dict(STEADY_RB, path=RB2, name="ref_fortran_thermal2d_seq_run_sheared_rb.npz", moving_walls=True,
+                  defs={"unsteadyFlow", "HorizontalWallsNoslip", "VerticalWallsNoslip", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsAdiabatic"},
+                  ranges=_shift(STEADY_RB["ranges"]))
 ACCRUN = dict(path=ACC, defs=ACC_DEFS, name="ref_fortran_thermal2d_acc_run.npz", param_lines=((55, 61), (90, 103)),
               size_text="nx=513, ny=257", reorder=True,
               ranges={"weights": (419, 430), "initT": (511, 520), "initial": (532, 544), "collision": (624, 707), "streaming": (722, 743),
@@ -68,9 +76,13 @@ def main(cfg=STEADY):
     text = text.replace(cfg["size_text"], f"nx={nx}, ny={ny}")
     P = eval_parameters(text)
     P.setdefault("rho0", 1.0)                  # ACC:416 `rho = 1.0d0`
-    assert (P["nx"], P["ny"], P["lengthunit"], P.get("u0", 0.0)) == (nx, ny, float(nx if cfg["reorder"] else ny), 0.0)
+    assert (P["nx"], P["ny"], P["lengthunit"]) == (nx, ny, float(nx if cfg["reorder"] else ny))
+    assert (P.get("u0", 0.0) != 0.0) == bool(cfg.get("moving_walls"))
     names_p = ("tauf", "viscosity", "diffusivity", "paraa", "gbeta", "snu", "sq", "qd", "qnu")
     out = {"params": np.array([P[k] for k in names_p]), "shape": np.array([nx, ny])}
+    if cfg.get("moving_walls"):                 # S:118-120, in the order of mglc_t2d_desc::Uwall
+        out["uwall"] = np.array([P["uwall" + k] for k in ("topleft", "topright", "bottomleft", "bottomright", "lefttop", "leftbottom", "righttop", "rightbottom")])
+        out["prandtl"] = np.array(P["prandtl"])
     sc = {k: v for k, v in P.items()}
     sc.update(itc=0)
     def tr(a, b):
@@ -127,6 +139,7 @@ def main(cfg=STEADY):
 
 
 if __name__ == "__main__":
-    main(STEADY)
-    main(STEADY_RB)
-    main(ACCRUN)
+    only = sys.argv[1:]
+    for cfg in (STEADY, STEADY_RB, SHEARED_RB, ACCRUN):
+        if not only or cfg["name"] in only:
+            main(cfg)

@@ -60,7 +60,8 @@ void to_aos(const Geom2 &g, int nq, const std::vector<double> &P, double *aos) {
 }  // namespace
 
 extern "C" {
-// par = Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, rho0, Thot, Tcold, perx, variant ; wallT[4], bcT[4], wall[4] as in T2Params / Geom2.
+// par = Snu, Sq, Qd, Qnu, paraA, gBeta, Tref, rho0, Thot, Tcold, perx, variant, Uwall[8], cornersT, start[2], total[2] (25 doubles);
+// wallT[4], bcT[4], wall[4] as in T2Params / Geom2.  fields4[0] = rho: read at the wall cells when walls move (mode 0 rewrites them).
 // mode 0: k_t2_fused         f_post, g_post (halo'd, in) -> f_post_out, g_post_out (halo'd, interior written), Fy in place
 // mode 1: k_t2_stream_macro  f_post, g_post -> f_out, g_out (halo'd arrays, interior written), rho,u,v,T (nx*ny each, in fields4)
 // mode 2: k_t2_collision + k_t2_collisionT: f_post/g_post hold f/g (halo'd arrays, interior used), fields4 = rho,u,v,T in;
@@ -72,6 +73,9 @@ int shim_t2d(int mode, int strict_build, int nx, int ny, const int *wall, const 
     T2Params p{};
     p.Snu = par[0]; p.Sq = par[1]; p.Qd = par[2]; p.Qnu = par[3]; p.paraA = par[4]; p.gBeta = par[5]; p.Tref = par[6]; p.rho0 = par[7];
     p.Thot = par[8]; p.Tcold = par[9]; p.perx = (int)par[10]; p.variant = (int)par[11];
+    p.moving = 0;
+    for (int q = 0; q < 8; ++q) { p.Uwall[q] = par[12 + q]; p.moving |= p.Uwall[q] != 0.0; }
+    p.cornersT = (int)par[20]; p.start[0] = (int)par[21]; p.start[1] = (int)par[22]; p.total[0] = (int)par[23]; p.total[1] = (int)par[24];
     for (int q = 0; q < 4; ++q) { p.wallT[q] = wallT[q]; p.bcT[q] = bcT[q]; }
     std::vector<double> Fi, Gi, Fo((size_t)9 * g.sq, 0.0), Go((size_t)5 * g.sq, 0.0);
     to_soa(g, 9, fin, Fi); to_soa(g, 5, gin, Gi);
@@ -79,8 +83,8 @@ int shim_t2d(int mode, int strict_build, int nx, int ny, const int *wall, const 
     double *rho = fields4, *u = fields4 + n, *v = fields4 + 2 * n, *T = fields4 + 3 * n;
     std::vector<double> Fx(n, -1.0);
     if (mode == 0) {
-        if (strict_build) sweep(g, [&] { strict::k_t2_fused(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy); });
-        else sweep(g, [&] { fast::k_t2_fused(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy); });
+        if (strict_build) sweep(g, [&] { strict::k_t2_fused(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy, rho); });
+        else sweep(g, [&] { fast::k_t2_fused(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy, rho); });
     } else if (mode == 1) {
         if (strict_build) sweep(g, [&] { strict::k_t2_stream_macro(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy, rho, u, v, T); });
         else sweep(g, [&] { fast::k_t2_stream_macro(g, p, Fi.data(), Fo.data(), Gi.data(), Go.data(), Fy, rho, u, v, T); });
@@ -133,6 +137,9 @@ void *shim_sub_create(int nx, int ny, const int *wall, const double *par, const 
     p = T2Params{};
     p.Snu = par[0]; p.Sq = par[1]; p.Qd = par[2]; p.Qnu = par[3]; p.paraA = par[4]; p.gBeta = par[5]; p.Tref = par[6]; p.rho0 = par[7];
     p.Thot = par[8]; p.Tcold = par[9]; p.perx = (int)par[10]; p.variant = (int)par[11];
+    p.moving = 0;
+    for (int q = 0; q < 8; ++q) { p.Uwall[q] = par[12 + q]; p.moving |= p.Uwall[q] != 0.0; }
+    p.cornersT = (int)par[20]; p.start[0] = (int)par[21]; p.start[1] = (int)par[22]; p.total[0] = (int)par[23]; p.total[1] = (int)par[24];
     for (int q = 0; q < 4; ++q) { p.wallT[q] = wallT[q]; p.bcT[q] = bcT[q]; }
     S->F.assign((size_t)9 * S->g.sq, 0.0); S->P.assign((size_t)9 * S->g.sq, 0.0);
     S->G.assign((size_t)5 * S->g.sq, 0.0); S->Q.assign((size_t)5 * S->g.sq, 0.0);
@@ -177,7 +184,7 @@ int shim_sub_op(void *h, int op, int a0, int a1, int a2) {
             std::fill(S->P.begin(), S->P.end(), 0.0); std::fill(S->Q.begin(), S->Q.end(), 0.0); break;
     case 1: sweep_grid(gx, g.ny, 128, [&] { k_t2_streaming(g, 9, S->P.data(), S->F.data()); }); break;
     case 2: sweep_grid(gx, g.ny, 128, [&] { k_t2_streaming(g, 5, S->Q.data(), S->G.data()); }); break;
-    case 3: sweep_grid(ring, 1, 128, [&] { k_t2_bounceback(g, S->p.perx, S->P.data(), S->F.data()); }); break;
+    case 3: sweep_grid(ring, 1, 128, [&] { k_t2_bounceback(g, S->p, S->P.data(), S->F.data(), rho); }); break;
     case 4: sweep_grid(ring, 1, 128, [&] { k_t2_bouncebackT(g, S->p, S->Q.data(), S->G.data()); }); break;
     case 5: sweep_grid(gx, g.ny, 128, [&] { k_t2_macro(g, S->F.data(), Fx, Fy, rho, u, v); }); break;
     case 6: sweep_grid(gx, g.ny, 128, [&] { k_t2_macroT(g, S->G.data(), T); }); break;

@@ -362,6 +362,57 @@ def test_oracle_reproduces_the_sequential_side_heated_programs_run(nprocs, dims,
     wd.close()
 
 
+SRUN_SHEAR = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_seq_run_sheared_rb.npz"))
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, (2, 2)), (6, (3, 2)), (3, (1, 3)), (12, (4, 3))])
+def test_oracle_reproduces_the_sheared_rayleigh_benard_programs_run(nprocs, dims):
+    """seq/R_B_2d.F90 AS SHIPPED (walls moving at shearReynolds = 100, Pr = 5.3, Rayleigh-Benard plates, its own corner cells in
+    bouncebackT()), evaluated from its text on 9 x 7: initial() with the wall velocities, 25 iterations, check().  The
+    restatement with Uwall and cornersT reproduces f, g, rho, u, v, T, Fx, Fy bit for bit on 1 to 12 ranks (the halves of the
+    walls meet at nxHalf / nyHalf of the global lattice, inside a subdomain or on a subdomain boundary)."""
+    S = SRUN_SHEAR
+    total = tuple(int(x) for x in S["shape"])
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=orc.T2_RAYLEIGH_BENARD, variant="mpi", Prandtl=float(S["prandtl"]),
+                            Uwall=[float(x) for x in S["uwall"]], cornersT=True)
+    assert tuple(getattr(wd.params, k) for k in ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")) == tuple(S["params"])
+    # U0 = shearReynolds*viscosity/dble(ny), R_B_2d.F90:118
+    assert S["uwall"][0] == 100.0 * wd.params.viscosity / float(total[1])
+    wd.initial()
+
+    def same(tag):
+        assert np.array_equal(wd.gather("f"), S[tag + "/f"]), tag
+        assert np.array_equal(wd.gather("g"), S[tag + "/g"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("rho", "u", "v", "T")]), S[tag + "/ruvT"]), tag
+        assert np.array_equal(np.stack([wd.gather(k) for k in ("Fx", "Fy")]), S[tag + "/F"]), tag
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 20):
+        wd.step(n - done); done = n
+        same(f"run{n}")
+    tol = 0 if nprocs == 1 else 1e-14
+    eu, et = wd.check()
+    assert abs(eu - S["run20/check"][0]) <= tol * abs(eu) and abs(et - S["run20/check"][1]) <= tol * abs(et)
+    wd.step(5)
+    same("run25")
+    wd.close()
+
+
+def test_walls_at_rest_and_plain_corners_are_the_default():
+    """Uwall = 0 and cornersT off change nothing (the shipped MPI program); each of the two options changes the run"""
+    total = (9, 7)
+    runs = {}
+    for name, kw in (("plain", {}), ("zero", dict(Uwall=[0.0] * 8)), ("corners", dict(cornersT=True)), ("moving", dict(Uwall=[1e-3] * 8))):
+        wd = orc.Thermal2DWorld(total, 1, None, bcT=orc.T2_RAYLEIGH_BENARD, **kw)
+        wd.initial(); wd.step(6)
+        runs[name] = wd.gather("f").copy(), wd.gather("g").copy()
+        wd.close()
+    assert np.array_equal(runs["plain"][0], runs["zero"][0]) and np.array_equal(runs["plain"][1], runs["zero"][1])
+    assert not np.array_equal(runs["plain"][1], runs["corners"][1])
+    assert not np.array_equal(runs["plain"][0], runs["moving"][0])
+
+
 ARUN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_acc_run.npz"))
 
 

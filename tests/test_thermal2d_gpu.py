@@ -393,3 +393,89 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         sim.upload(0, rho=np.zeros((3, 3)))
     sim.close()
+
+
+# ---- the sheared Rayleigh-Benard programs: moving walls, corner cells of bouncebackT() (seq/R_B_2d.F90) ------------------------
+SRUN_SHEAR = np.load(os.path.join(HERE, "golden", "ref_fortran_thermal2d_seq_run_sheared_rb.npz"))
+SHEAR_WALLS = [4e-3, -4e-3, -4e-3, 4e-3, 3e-3, 3.5e-3, 2.5e-3, 2e-3]
+
+
+def sheared_pair(total, nprocs, dims, strict, bcT=RAYLEIGH_BENARD, Uwall=SHEAR_WALLS, **params):
+    wd = orc.Thermal2DWorld(total, nprocs, dims, bcT=bcT, Uwall=Uwall, cornersT=True, **params)
+    sim = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, bcT=bcT, strict=strict, Uwall=Uwall, cornersT=True, **params)
+    wd.initial(); sim.initial()
+    return wd, sim
+
+
+@pytest.mark.parametrize("nprocs,dims", [(1, None), (2, None), (4, (2, 2)), (6, (3, 2)), (12, (4, 3))])
+def test_sheared_rb_program_as_shipped_reproduces_its_fortran_run(nprocs, dims):
+    """seq/R_B_2d.F90 AS SHIPPED, evaluated from its text on 9 x 7 (make_golden_thermal2d_seq_run.py): variant "sheared_rb" of the
+    driver (its desc_init: Pr 5.3, plates, shearReynolds = 100, corner cells) through step(): f, g, fields bit for bit"""
+    S = SRUN_SHEAR
+    total = tuple(int(x) for x in S["shape"])
+    sim = mg.BuoyancyDrivenCavity2D(total, nprocs=nprocs, dims=dims, strict=True, variant="sheared_rb")
+    assert sim.Uwall == tuple(float(x) for x in S["uwall"]) and sim.cornersT
+    assert tuple(sim.params[k] for k in ("tauf", "viscosity", "diffusivity", "paraA", "gBeta", "Snu", "Sq", "Qd", "Qnu")) == tuple(S["params"])
+    sim.initial()
+
+    def same(tag):
+        assert np.array_equal(sim.gather("f"), S[tag + "/f"]), tag
+        assert np.array_equal(sim.gather("g"), S[tag + "/g"]), tag
+        assert np.array_equal(np.stack([sim.gather(k) for k in FIELDS]), S[tag + "/ruvT"]), tag
+        assert np.array_equal(np.stack([sim.gather(k) for k in ("Fx", "Fy")]), S[tag + "/F"]), tag
+
+    same("run0")
+    done = 0
+    for n in (1, 2, 20, 25):
+        sim.step(n - done); done = n
+        same(f"run{n}")
+    sim.close()
+
+
+@pytest.mark.parametrize("total,nprocs,dims,bcT", [((34, 33), 1, None, RAYLEIGH_BENARD), ((23, 19), 4, None, RAYLEIGH_BENARD),
+                                                   ((23, 19), 6, None, SIDE_HEATED), ((130, 6), 2, None, RAYLEIGH_BENARD),
+                                                   ((9, 31), 3, (1, 3), RAYLEIGH_BENARD)])
+def test_sheared_walls_fused_step_and_subroutines_strict_bit_exact(total, nprocs, dims, bcT):
+    """eight different wall velocities: the fused step (rho of the previous macro() carried at the wall cells), then the
+    per-subroutine entry points (bounceback() with the rho field, bouncebackT() with the corner rule), then step() again"""
+    wd, sim = sheared_pair(total, nprocs, dims, True, bcT=bcT, Rayleigh=1e6)
+    assert_rank_arrays_equal(wd, sim, ("f", "g") + FIELDS)
+    for n in (1, 2, 17):
+        wd.step(n); sim.step(n)
+        assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+    wd.collision(); sim.collision(); wd.message_passing_f(); sim.message_passing_f()
+    wd.streaming(); sim.streaming(); wd.bounceback(); sim.bounceback()
+    assert_rank_arrays_equal(wd, sim, ("f",))
+    wd.collisionT(); sim.collisionT(); wd.message_passing_g(); sim.message_passing_g()
+    wd.streamingT(); sim.streamingT(); wd.bouncebackT(); sim.bouncebackT()
+    assert_rank_arrays_equal(wd, sim, ("g",))
+    wd.macro(); sim.macro(); wd.macroT(); sim.macroT()
+    wd.step(3); sim.step(3)
+    assert_rank_arrays_equal(wd, sim, ("f", "g", "f_post", "g_post", "Fx", "Fy") + FIELDS)
+    wd.close(); sim.close()
+
+
+def test_sheared_rb_graph_replay_and_fast_arithmetic():
+    """a single small subdomain replays its fused launches from CUDA graphs (the rho field is an argument of the captured
+    launches); fast arithmetic at 201 x 201 as shipped stays within the north-star tolerance over 1000 steps"""
+    wd, sim = sheared_pair((45, 38), 1, None, True, Rayleigh=1e5)
+    wd.step(136); sim.step(136)
+    assert_rank_arrays_equal(wd, sim, ("f", "g", "Fx", "Fy") + FIELDS)
+    wd.close(); sim.close()
+    sim = mg.BuoyancyDrivenCavity2D(None, strict=False, variant="sheared_rb")
+    wd = orc.Thermal2DWorld((201, 201), 1, None, bcT=RAYLEIGH_BENARD, Prandtl=5.3, Uwall=list(sim.Uwall), cornersT=True)
+    wd.initial(); sim.initial()
+    done = 0
+    for n in (1, 10, 100, 1000):
+        wd.step(n - done); sim.step(n - done); done = n
+        for k in FIELDS:
+            assert close_enough(sim.gather(k), wd.gather(k), floor=velocity_floor(wd) if k in ("u", "v") else 0.0), (n, k)
+    # the sheared top wall drags the fluid: u just below the top-left half of the lid follows UwallTopLeft's sign
+    assert np.sign(wd.gather("u")[20:80, -2].mean()) == np.sign(sim.Uwall[0])
+    wd.close(); sim.close()
+
+
+def test_moving_walls_with_periodic_vertical_walls_are_refused():
+    from mglc_b200 import _lib as L
+    with pytest.raises(L.MglcError):
+        mg.BuoyancyDrivenCavity2D((33, 17), variant="acc", Uwall=[1e-3] * 8)

@@ -46,7 +46,8 @@ def shim_params(w, R):
     p = w.params
     perx = orc.T2_PERIODIC in w.bcT
     wall = (C.c_int * 4)(R.coords[0] == w.dims[0] - 1 and not perx, R.coords[0] == 0 and not perx, R.coords[1] == w.dims[1] - 1, R.coords[1] == 0)
-    par = (C.c_double * 12)(p.Snu, p.Sq, p.Qd, p.Qnu, p.paraA, p.gBeta, p.Tref, p.rho0, p.Thot, p.Tcold, float(perx), float(w.variant == "acc"))
+    par = (C.c_double * 25)(p.Snu, p.Sq, p.Qd, p.Qnu, p.paraA, p.gBeta, p.Tref, p.rho0, p.Thot, p.Tcold, float(perx), float(w.variant == "acc"),
+                            *w.Uwall, float(w.cornersT and not perx), float(R.start[0]), float(R.start[1]), float(w.total[0]), float(w.total[1]))
     wallT = (C.c_double * 4)(*[(4.0 + p.paraA) / 10.0 * (p.Thot if k == orc.T2_CONST_HOT else p.Tcold) for k in w.bcT])
     bcT = (C.c_int * 4)(*[0 if k == orc.T2_PERIODIC else k for k in w.bcT])
     return wall, par, wallT, bcT
@@ -63,17 +64,23 @@ CASES = [((1, 1), orc.T2_SIDE_HEATED), ((2, 2), orc.T2_SIDE_HEATED), ((3, 3), or
          ((1, 1), orc.T2_RB_PERIODIC), ((1, 3), orc.T2_RB_PERIODIC)]      # the OpenACC program's set: periodic vertical walls, acc arithmetic
 
 
+# the sheared Rayleigh-Benard programs (seq/R_B_2d.F90): every wall moving along itself, halves with opposite signs, its corner rule
+SHEAR = dict(Uwall=[4e-3, -4e-3, -4e-3, 4e-3, 3e-3, 3.5e-3, 2.5e-3, 2e-3], cornersT=True)
+SHEARED_CASES = [((1, 1), orc.T2_RAYLEIGH_BENARD), ((2, 2), orc.T2_RAYLEIGH_BENARD), ((3, 3), orc.T2_RAYLEIGH_BENARD), ((4, 1), orc.T2_SIDE_HEATED)]
+
+
 def world_for(total, dims, bcT, **kw):
     acc = orc.T2_PERIODIC in bcT
     return orc.Thermal2DWorld(total, nprocs=dims[0] * dims[1], dims=dims, bcT=bcT, variant="acc" if acc else "mpi",
                               lengthUnit=float(total[0]) if acc else 0.0, **kw)
 
 
-@pytest.mark.parametrize("dims,bcT", CASES)
+@pytest.mark.parametrize("dims,bcT,walls", [c + ({},) for c in CASES] + [c + (SHEAR,) for c in SHEARED_CASES])
 @pytest.mark.parametrize("strict", [True, False])
-def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, strict):
-    """k_t2_fused on every rank == streaming .. macroT of this step + collision/collisionT of the next (oracle), wall halos poisoned"""
-    w = world_for((23, 19), dims, bcT, Rayleigh=1e6)
+def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, walls, strict):
+    """k_t2_fused on every rank == streaming .. macroT of this step + collision/collisionT of the next (oracle), wall halos poisoned;
+    with moving walls the kernel reads rho of the previous macro() at the wall cells and leaves the new one there"""
+    w = world_for((23, 19), dims, bcT, Rayleigh=1e6, **walls)
     w.initial()
     w.step(30)
     w.collision(); w.message_passing_f(); w.collisionT(); w.message_passing_g()          # rotated-loop state: halos valid
@@ -85,13 +92,21 @@ def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, strict)
         if R.coords[0] == dims[0] - 1: fp[:, -1, :] = gp[:, -1, :] = np.nan
         if R.coords[1] == 0: fp[:, :, 0] = gp[:, :, 0] = np.nan
         if R.coords[1] == dims[1] - 1: fp[:, :, -1] = gp[:, :, -1] = np.nan
-        snap.append((fp, gp, R.Fy.copy()))
+        snap.append((fp, gp, R.Fy.copy(), R.rho.copy()))
     # the oracle finishes the step and collides again
     w.streaming(); w.bounceback(); w.streamingT(); w.bouncebackT(); w.macro(); w.macroT()
     macros = [(R.f.copy(), R.g.copy(), R.rho.copy(), R.u.copy(), R.v.copy(), R.T.copy()) for R in w.ranks]
     w.collision(); w.collisionT()
-    for R, (fp, gp, Fy), mac in zip(w.ranks, snap, macros):
-        fo, go, Fy2, _ = run_shim(shim, w, R, 0, strict, fp, gp, Fy)
+    for R, (fp, gp, Fy, rho_prev), mac in zip(w.ranks, snap, macros):
+        prev = [rho_prev, rho_prev * 0, rho_prev * 0, rho_prev * 0]
+        fo, go, Fy2, fl0 = run_shim(shim, w, R, 0, strict, fp, gp, Fy, fields=prev)
+        if walls:                                   # the wall cells of the rho field now hold this step's macro()
+            ring = np.zeros(R.n, bool)
+            if R.coords[0] == 0: ring[0, :] = True
+            if R.coords[0] == dims[0] - 1: ring[-1, :] = True
+            if R.coords[1] == 0: ring[:, 0] = True
+            if R.coords[1] == dims[1] - 1: ring[:, -1] = True
+            assert np.array_equal(fl0[0][ring], mac[2][ring]) and np.array_equal(fl0[0][~ring], rho_prev[~ring])
         want_f, want_g = R.f_post[:, 1:-1, 1:-1], R.g_post[:, 1:-1, 1:-1]
         if strict:
             assert np.array_equal(fo[:, 1:-1, 1:-1], want_f) and np.array_equal(go[:, 1:-1, 1:-1], want_g) and np.array_equal(Fy2, R.Fy)
@@ -99,7 +114,7 @@ def test_fused_kernel_source_reproduces_one_oracle_step(shim, dims, bcT, strict)
             assert np.abs(fo[:, 1:-1, 1:-1] - want_f).max() < 2e-16 * 4 and np.abs(go[:, 1:-1, 1:-1] - want_g).max() < 1e-15
             assert np.array_equal(Fy2, R.Fy)          # the stored force is rounded like the reference in both builds
         # the epilogue kernel: bit-exact in both builds (copies, ordered adds, IEEE divisions)
-        fo, go, _, fl = run_shim(shim, w, R, 1, strict, fp, gp, Fy)
+        fo, go, _, fl = run_shim(shim, w, R, 1, strict, fp, gp, Fy, fields=prev)
         assert np.array_equal(fo[:, 1:-1, 1:-1], mac[0]) and np.array_equal(go[:, 1:-1, 1:-1], mac[1])
         for got, want in zip(fl, mac[2:]):
             assert np.array_equal(got, want)
@@ -223,10 +238,10 @@ class ShimWorld:
             self.S.shim_sub_unpack(self.subs[to], dr, n1, npop, buf.ctypes.data_as(dp))
 
 
-@pytest.mark.parametrize("dims,bcT", CASES + [((2, 3), (2, 1, 1, 2))])
-def test_exact_kernel_sources_follow_the_oracle_subroutine_by_subroutine(shim, dims, bcT):
+@pytest.mark.parametrize("dims,bcT,walls", [c + ({},) for c in CASES + [((2, 3), (2, 1, 1, 2))]] + [c + (SHEAR,) for c in SHEARED_CASES])
+def test_exact_kernel_sources_follow_the_oracle_subroutine_by_subroutine(shim, dims, bcT, walls):
     total = (23, 19)
-    w = world_for(total, dims, bcT, Rayleigh=1e6, Thot=0.75, Tcold=-0.25)
+    w = world_for(total, dims, bcT, Rayleigh=1e6, Thot=0.75, Tcold=-0.25, **walls)
     sw = ShimWorld(shim, w)
     P = range(w.nprocs)
 
@@ -239,11 +254,11 @@ def test_exact_kernel_sources_follow_the_oracle_subroutine_by_subroutine(shim, d
     # a seeded, fully non-trivial state (the collisions themselves are covered above)
     rng = np.random.default_rng(11)
     for r, R in enumerate(w.ranks):
-        for k in ("f", "g", "f_post", "g_post", "Fx", "Fy"):
+        for k in ("f", "g", "f_post", "g_post", "Fx", "Fy", "rho"):
             a = getattr(R, k)
-            a[...] = rng.random(a.shape) * (1e-3 if k in ("Fx", "Fy") else 1.0)
+            a[...] = rng.random(a.shape) * (1e-3 if k in ("Fx", "Fy") else 1.0) + (0.5 if k == "rho" else 0.0)
             sw.put(r, k, a)
-    same("f", "g", "f_post", "g_post", "Fx", "Fy")                 # the transposing upload / download kernels round-trip
+    same("f", "g", "f_post", "g_post", "Fx", "Fy", "rho")                 # the transposing upload / download kernels round-trip
     w.message_passing_f(); sw.exchange(1)
     same("f_post", "g_post")
     w.streaming(); sw.op(1)
