@@ -705,6 +705,24 @@ module mglc_iso_c
             type(c_ptr), value :: h
             integer(c_int) :: rc
         end function
+        !> the MPI lid driver on one lattice per rank: d describes the GLOBAL lattice (total_nx, total_ny, total_nz), comm as for
+        !> mglc_lbm_create, dims = the process grid or zeros (MPI_Dims_create's).  mglc_aa_initial / _step / _check / _upload /
+        !> _download_* on the handle are then collective calls, arrays are this rank's block (L3/main.f90:33-63)
+        function mglc_aa_create_comm(h, d, comm, dims) bind(C, name="mglc_aa_create_comm") result(rc)
+            import :: c_int, c_ptr, mglc_aa_desc
+            type(c_ptr), intent(out) :: h
+            type(mglc_aa_desc), intent(in) :: d
+            type(c_ptr), value :: comm
+            integer(c_int), intent(in) :: dims(3)
+            integer(c_int) :: rc
+        end function
+        !> ln = nx, ny, nz of this rank's block; start = i_start_global - 1, j_start_global - 1, k_start_global - 1
+        function mglc_aa_get_block(h, ln, start) bind(C, name="mglc_aa_get_block") result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int), intent(out) :: ln(3), start(3)
+            integer(c_int) :: rc
+        end function
         ! ---- in-loop diagnostics on the device and the drivers' on-disk formats ----------------------------------------
         !> calNuRe(), Buoyancy_driven_cavity/fortran/3d/mpi_blocked/RaNu.F90:13-47
         function mglc_calNuRe(h, prandtl, NuVolAvg, ReVolAvg) bind(C, name="mglc_calNuRe") result(rc)
