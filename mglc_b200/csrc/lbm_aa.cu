@@ -606,6 +606,7 @@ extern "C" int mglc_aa_create_comm(mglc_aa **out, const mglc_aa_desc *gd, mglc_c
     };
     memset(&h->peers, 0, sizeof h->peers);
     memset(&h->sync, 0, sizeof h->sync);
+    h->peers.err = h->d_err;
     for (int dd = 0; dd < 19 && ok; ++dd) {
         const int n = h->nbr[dd];
         if (dd == 6 || n < 0) continue;

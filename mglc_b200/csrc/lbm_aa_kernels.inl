@@ -103,6 +103,13 @@ __device__ __forceinline__ long long aa_peer_halo(const PeerTable &pt, int D, in
     }
 #define AA_PARK_EDGE(A, O, EX, EY, EZ)                                                                       \
     if (pm & (1u << (A))) pt.F[A][(O) * pt.sq[A] + aa_peer_halo<EX, EY, EZ>(pt, A, i, j, k)] = fp[A];
+// a cell on a face of the block may store into a neighbour -- unless the neighbour barrier has failed (sticky error word of
+// k_halo_wait, one process per GPU only): from then on nothing goes into a neighbour any more, as on the two-lattice path.
+// Read before the cell's lattice loads, so that no global load follows a store.
+__device__ __forceinline__ bool aa_may_store_to_peers(const PeerTable &pt, const Geom &g, int i, int j, int k) {
+    if (!((i == 1) | (i == g.nx) | (j == 1) | (j == g.ny) | (k == 1) | (k == g.nz))) return false;
+    return !(pt.err && *(const volatile int *)pt.err);
+}
 __device__ __forceinline__ void aa_peer_park(const PeerTable &pt, const Geom &g, int i, int j, int k, const double (&fp)[19]) {
     const unsigned pm = pt.mask;
     const bool xp = i == g.nx, xm = i == 1, yp = j == g.ny, ym = j == 1, zp = k == g.nz, zm = k == 1;
@@ -155,6 +162,7 @@ __global__ void __launch_bounds__(128, 4) k_aa_collide0(Geom g, LbmParams p, dou
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
     const long long sq = g.sq, c = g.idx(0, i, j, k), m = g.cell(i, j, k);
+    const bool park = PEER && aa_may_store_to_peers(pt, g, i, j, k);
     double f[19], fp[19];
 #pragma unroll
     for (int a = 0; a < 19; ++a) f[a] = A[a * sq + c];
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(128, 4) k_aa_collide0(Geom g, LbmParams p, dou
     A[c] = fp[0];
 #define AA_PARK(a, o, dx, dy, dz) A[(o) * sq + c] = fp[a];
     AA_FOR_ALL(AA_PARK)
-    if (PEER) aa_peer_park(pt, g, i, j, k, fp);
+    if (PEER && park) aa_peer_park(pt, g, i, j, k, fp);
 }
 
 // NATURAL -> POST: macro() of this loop body and collision() of the next, at the cell
@@ -173,6 +181,7 @@ __global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double 
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
     if (i > g.nx) return;
     const long long sq = g.sq, c = g.idx(0, i, j, k);
+    const bool park = PEER && aa_may_store_to_peers(pt, g, i, j, k);
     double f[19], fp[19];
 #pragma unroll
     for (int a = 0; a < 19; ++a) f[a] = __ldg(Ain + a * sq + c);
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(128, 5) k_aa_even(Geom g, LbmParams p, double 
     A[c] = fp[0];
     AA_FOR_ALL(AA_PARK)
 #undef AA_PARK
-    if (PEER) aa_peer_park(pt, g, i, j, k, fp);
+    if (PEER && park) aa_peer_park(pt, g, i, j, k, fp);
     // the moving-lid bounce-back of the next streaming step needs this macro()'s rho on the lid plane (bounce_back.f90:77-78)
     if (g.lid && k == g.nz) rho_lid_out[(i - 1) + (long long)g.nx * (j - 1)] = rho;
 }
@@ -210,7 +219,8 @@ __global__ void __launch_bounds__(128, 4) k_aa_odd(Geom g, LbmParams p, double *
     const bool x_shared = PEER && ((warp_lo && !g.wall[1]) | (warp_hi && !g.wall[0]));
     const int path = (yz_face | x_shared) ? 2 : ((warp_lo | warp_hi) ? 1 : 0);
     const bool peer_cell = PEER && ((i == g.nx && !g.wall[0]) | (i == 1 && !g.wall[1]) | (j == g.ny && !g.wall[2]) |
-                                    (j == 1 && !g.wall[3]) | (k == g.nz && !g.wall[4]) | (k == 1 && !g.wall[5]));
+                                    (j == 1 && !g.wall[3]) | (k == g.nz && !g.wall[4]) | (k == 1 && !g.wall[5])) &&
+                           aa_may_store_to_peers(pt, g, i, j, k);     // barrier failed: the push stays in the block's own halo ring
     double f[19], fp[19];
     if (path == 0) {
         f[0] = __ldg(Ain + c);
