@@ -286,6 +286,17 @@ m13() {   # 4 GPUs: parity and the weak-scaling line at N = 4 (1x2x2); e2e / tra
     ( time timeout 240 $TR bench.py --gpus 4 --steps 20 --warmup 5 --no-e2e --no-extras > $O/bench_lid_4gpu.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 3500 $O/bench_lid_4gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
 }
 
+m14() {   # 2 GPUs, round end: the multi-process suite (now with lid_aa) and the default bench line (parity block with the single-lattice verdict)
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+    (timeout 600 python -m pytest tests/test_multigpu.py -q -m gpu -x -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_multigpu.log); tail -n 4 $O/pytest_multigpu.log
+    ( time timeout 400 $TR bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e > $O/bench_lid_2gpu.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 2600 $O/bench_lid_2gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
+}
+s9() {   # 1 GPU, round end: whole GPU suite, smoke, the default bench line
+    (timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log); tail -n 4 $O/pytest_gpu.log
+    (timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log); tail -n 3 $O/smoke.log
+    ( time timeout 600 python bench.py > $O/bench_lid_768_1gpu.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 2000 $O/bench_lid_768_1gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
+}
+
 "$S"
 clk
 ls -la $O | tail -30
