@@ -297,6 +297,23 @@ s9() {   # 1 GPU, round end: whole GPU suite, smoke, the default bench line
     ( time timeout 600 python bench.py > $O/bench_lid_768_1gpu.json 2> $O/b1.err ) 2> $O/time.txt; tail -c 2000 $O/bench_lid_768_1gpu.json; tail -n 3 $O/b1.err; tail -n 3 $O/time.txt
 }
 
+s10() {   # 1 GPU: particle collision kernel with the next row's solid flag loaded ahead (experiment, not adopted: profiles/r2t_*)
+    (timeout 400 python -m pytest tests/test_particles_gpu.py -q -m gpu -x > $O/pytest_particles.log 2>&1; echo "pytest rc=$?" >> $O/pytest_particles.log); tail -n 3 $O/pytest_particles.log
+    timeout 200 python bench.py --workload particles --size 8192 --steps 20 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_1gpu.json 2> $O/b1.err
+    python -c "
+import json;d=json.loads(open('$O/bench_particles_8192_1gpu.json').read().strip().splitlines()[-1]);print('particles 8192', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])"
+    timeout 300 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -s 40 -c 24 --csv --log-file $O/launches_particles_8192.csv \
+        python bench.py --workload particles --size 8192 --steps 4 --warmup 3 --no-e2e --no-cpu > $O/b12.log 2>&1; echo "ncu particles rc=$?"
+}
+
+s11() {   # 1 GPU: A/B of the flag-ahead order in k_p_collision_sum on ONE box (experiment build with the MGLC_P2D_FLAG_AHEAD knob, not adopted)
+    for v in 1 0 1 0; do
+        MGLC_P2D_FLAG_AHEAD=$v timeout 200 python bench.py --workload particles --size 8192 --steps 30 --warmup 3 --no-cpu --no-e2e > $O/bench_particles_8192_ahead$v.json 2> $O/b1.err
+        python -c "
+import json;d=json.loads(open('$O/bench_particles_8192_ahead$v.json').read().strip().splitlines()[-1]);print('particles 8192 flag_ahead=$v', d['value'], d['ms_per_step'], 'ms', d['roofline']['frac'])" | tee -a $O/ab.txt
+    done
+}
+
 "$S"
 clk
 ls -la $O | tail -30
