@@ -314,6 +314,16 @@ import json;d=json.loads(open('$O/bench_particles_8192_ahead$v.json').read().str
     done
 }
 
+san2() {   # 1 GPU: compute-sanitizer memcheck + initcheck + racecheck over what this round added last: single-lattice blocks storing
+           # into each other (4 and 12 blocks in one process), the sheared Rayleigh-Benard walls of the 2-D thermal driver
+    SEL='(test_group_blocks_strict_bit_exact and mrt and (4-None or 12-dims3)) or test_group_from_initial_and_reinitialised or (test_sheared_walls_fused_step and total1) or (test_sheared_rb_program_as_shipped and 4-dims2)'
+    FILES="tests/test_aa_gpu.py tests/test_thermal2d_gpu.py"
+    for tool in memcheck initcheck racecheck; do
+        (timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest $FILES -m gpu -q -x -k "$SEL" > $O/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a $O/sanitizer_$tool.log)
+        grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" $O/sanitizer_$tool.log | tail -n 4
+    done
+}
+
 "$S"
 clk
 ls -la $O | tail -30
