@@ -61,6 +61,14 @@ _shift = lambda r: {k: ((a, b) if b <= 744 else (a + 1, b + 1)) for k, (a, b) in
 SHEARED_RB = dict(STEADY_RB, path=RB2, name="ref_fortran_thermal2d_seq_run_sheared_rb.npz", moving_walls=True,
                   defs={"unsteadyFlow", "HorizontalWallsNoslip", "VerticalWallsNoslip", "RayleighBenardCell", "HorizontalWallsConstT", "VerticalWallsAdiabatic"},
                   ranges=_shift(STEADY_RB["ranges"]))
+# the OpenMP program of the same family as shipped (same macro set, same moving walls and corner cells; its irregular-geometry,
+# tilted-cell and tracer-particle branches are compiled out / never reached in the first 25 iterations)
+OMP2 = "/root/reference/MPI/Buoyancy_driven_cavity/fortran/2d/seq/bouyancy2d_omp.F90"
+SHEARED_OMP = dict(SHEARED_RB, path=OMP2, name="ref_fortran_thermal2d_seq_run_sheared_omp.npz",
+                   param_lines=((65, 71), (88, 88), (96, 96), (111, 125), (133, 135)),
+                   ranges={"weights": (598, 609), "initU": (662, 677), "initT": (741, 760), "initial": (779, 791), "collision": (881, 969),
+                           "streaming": (986, 997), "bounceback": (1089, 1232), "macro": (1262, 1274), "collisionT": (1293, 1336),
+                           "streamingT": (1353, 1365), "bouncebackT": (1440, 1535), "macroT": (1550, 1556), "check": (1572, 1597)})
 ACCRUN = dict(path=ACC, defs=ACC_DEFS, name="ref_fortran_thermal2d_acc_run.npz", param_lines=((55, 61), (90, 103)),
               size_text="nx=513, ny=257", reorder=True,
               ranges={"weights": (419, 430), "initT": (511, 520), "initial": (532, 544), "collision": (624, 707), "streaming": (722, 743),
@@ -140,6 +148,6 @@ def main(cfg=STEADY):
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for cfg in (STEADY, STEADY_RB, SHEARED_RB, ACCRUN):
+    for cfg in (STEADY, STEADY_RB, SHEARED_RB, SHEARED_OMP, ACCRUN):
         if not only or cfg["name"] in only:
             main(cfg)

@@ -399,6 +399,15 @@ def test_oracle_reproduces_the_sheared_rayleigh_benard_programs_run(nprocs, dims
     wd.close()
 
 
+def test_the_openmp_program_of_the_family_runs_identically():
+    """seq/bouyancy2d_omp.F90 as shipped (its irregular-geometry / tilted-cell / tracer-particle branches compiled out or not
+    reached), evaluated from ITS text: the same numbers as seq/R_B_2d.F90's run, array for array -- one descriptor covers both"""
+    omp = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fortran_thermal2d_seq_run_sheared_omp.npz"))
+    assert sorted(omp.keys()) == sorted(SRUN_SHEAR.keys())
+    for k in omp.keys():
+        assert np.array_equal(omp[k], SRUN_SHEAR[k]), k
+
+
 def test_walls_at_rest_and_plain_corners_are_the_default():
     """Uwall = 0 and cornersT off change nothing (the shipped MPI program); each of the two options changes the run"""
     total = (9, 7)
