@@ -324,6 +324,11 @@ san2() {   # 1 GPU: compute-sanitizer memcheck + initcheck + racecheck over what
     done
 }
 
+m15() {   # 8 GPUs: strong scaling of the 768^3 lattice (384^3 blocks) with the shipped default transport (push from 2^25 cells)
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
+    timeout 200 $TR bench.py --gpus 8 --scaling strong --size 768 --steps 100 --warmup 10 --no-e2e --no-parity --no-extras --no-cpu > $O/bench_lid_strong_8gpu.json 2> $O/b1.err; tail -c 1500 $O/bench_lid_strong_8gpu.json; tail -n 3 $O/b1.err
+}
+
 "$S"
 clk
 ls -la $O | tail -30
