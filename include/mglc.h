@@ -203,14 +203,16 @@ int mglc_lbm_set_profiling(mglc_lbm *h, int on);
  *   2  direct halo stores: the fused kernel writes the outgoing populations of its boundary cells straight into the
  *      neighbours' halo cells over NVLink (peer access inside one process, CUDA IPC mappings between processes, set up
  *      collectively by mglc_lbm_create / mglc_group_create), followed by a flag barrier between neighbours.  No pack,
- *      send/recv or unpack; the transfer overlaps the update cell by cell.  Default when the mappings exist.
+ *      send/recv or unpack; the transfer overlaps the update cell by cell.  Default when the mappings exist and the block has
+ *      fewer than 2^25 cells (env MGLC_HALO_MODE=2|3 overrides the choice between 2 and 3).
  *   1  overlapped exchange: boundary shell first, pack -> ncclSend/ncclRecv -> unpack on a second stream beside the
  *      interior update, the schedule of collision_with_message_exchange, lid3_mpi_nonblock.f90:1108-1230.
  *      Default otherwise.
  *   0  blocking exchange, then update: message_passing_sendrecv() as the blocking driver does it, L3/main.f90:89-93.
  *   3  halo push: the plain fused kernel, then ONE small launch that copies every outgoing message (same sets) from the
  *      boundary cells straight into the neighbours' halo cells over the same mappings as mode 2 -- no send buffers, no NCCL,
- *      no unpack, and no message code inside the update kernel.
+ *      no unpack, and no message code inside the update kernel.  Default when the mappings exist and the block has 2^25 cells
+ *      or more (384^3 and up: the stores of a face cost less from a separate launch than from inside the update).
  * With modes 2 and 3 every call that leaves the fused loop (upload, download, the per-subroutine entry points) must be made
  * by all ranks between the same two mglc_lbm_step calls, like the reference's subroutines; a rank out of step is
  * reported by mglc_lbm_sync / mglc_check as MGLC_E_STATE instead of hanging. */
