@@ -286,3 +286,41 @@ def test_rows_of_one_to_five_warps_strict(shim, nx):
         assert np.array_equal(sim.f(), wd.gather("f")), (nx, n)
         assert np.array_equal(two.gather("f"), wd.gather("f")), (nx, n, "two blocks")
     sim.close(); two.close(); wd.close(); w2.close()
+
+
+# ---- randomised decompositions (hypothesis): the park / push protocol must hold for any block grid, any remainder, both orders ----
+try:
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:                                   # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+
+if HAVE_HYPOTHESIS:
+    @st.composite
+    def block_grids(draw):
+        dims = tuple(draw(st.integers(1, 3)) for _ in range(3))
+        total = tuple(draw(st.integers(d, d + 5)) for d in dims)          # at least one cell per block, uneven remainders
+        return dims, total
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(grid=block_grids(), order=st.integers(0, 1), steps=st.lists(st.integers(1, 4), min_size=1, max_size=3),
+           bgk=st.booleans(), seed=st.integers(0, 10**6))
+    def test_any_block_grid_matches_the_single_rank_oracle(shim, grid, order, steps, bgk, seed):
+        dims, total = grid
+        nprocs = dims[0] * dims[1] * dims[2]
+        collision = "bgk" if bgk else "mrt"
+        ref = orc.LidWorld(total, 1, collision=collision)
+        ref.initial()
+        wd = orc.LidWorld(total, nprocs, dims=dims, collision=collision)
+        wd.initial()
+        seeded_world(wd, seed)
+        for k in ("rho", "u", "v", "w", "f"):
+            getattr(ref.ranks[0], k)[...] = wd.gather(k)
+        sim = AaWorld(shim, wd, strict=True, bgk=bgk)
+        sim.upload()
+        for n in steps:
+            ref.step(n); sim.step(n, order)
+        for k in ("rho", "u", "v", "w", "f"):
+            assert np.array_equal(sim.gather(k), ref.gather(k)), (dims, total, steps, k)
+        sim.close(); wd.close(); ref.close()
